@@ -1,0 +1,132 @@
+// extern "C" surface of libcsb200.so — see include/cs_b200.h for the contract of every entry point.
+#include "cs_host.h"
+// after cs_host.h: the public macros shadow the identically valued internal enums
+#include "../../include/cs_b200.h"
+
+namespace cs {
+const char* last_error();
+unsigned long long launch_count();
+void reset_launch_count();
+
+int gn_stats_launch(const void*, int, int, int, int, float*, int, cudaStream_t);
+int gn_finalize_launch(float*, const float*, const float*, int, int, int, int, float, float*, cudaStream_t);
+int gn_apply_launch(const void*, int, int, int, int, const float*, int, void*, int, int, cudaStream_t);
+int layernorm_launch(const void*, long long, int, int, const float*, const float*, float, void*, int, cudaStream_t);
+int attention_launch(const void*, const void*, const void*, void*, int, int, int, int, int, int, int, int, int,
+                     float, cudaStream_t);
+int geglu_launch(const void*, long long, int, int, void*, int, cudaStream_t);
+int upsample_launch(const void*, int, int, int, int, int, int, int, int, int, void*, int, cudaStream_t);
+int im2col_small_launch(const float*, int, int, int, int, int, int, int, void*, cudaStream_t);
+int timestep_embedding_launch(const long long*, int, int, float, float*, cudaStream_t);
+int linear_small_launch(const float*, int, int, int, const float*, const float*, int, int, int, float*, int,
+                        cudaStream_t);
+int ddim_step_launch(const float*, const float*, long long, int, float, float, float, float, float, const float*,
+                     float*, float*, cudaStream_t);
+int q_sample_launch(const float*, const float*, const long long*, const float*, const float*, long long, int,
+                    float*, cudaStream_t);
+int ncdhw_to_ndhwc_launch(const float*, int, int, long long, int, void*, cudaStream_t);
+int ndhwc_to_ncdhw_launch(const void*, int, int, long long, int, float*, cudaStream_t);
+}  // namespace cs
+
+static inline cudaStream_t S(cs_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+extern "C" {
+
+int cs_abi_version(void) { return 1; }
+const char* cs_last_error(void) { return cs::last_error(); }
+uint64_t cs_launch_count(void) { return cs::launch_count(); }
+void cs_reset_launch_count(void) { cs::reset_launch_count(); }
+
+int cs_device_check(void) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) {
+    cs::set_cuda_error(e, "cs_device_check");
+    return CS_ERR_NO_DEVICE;
+  }
+  int major = 0;
+  e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (e != cudaSuccess || major != 10) {
+    cs::set_error(CS_ERR_NO_DEVICE, "cs_device_check: the current device is not compute capability 10.x (sm_100a)");
+    return CS_ERR_NO_DEVICE;
+  }
+  return CS_OK;
+}
+
+int cs_conv3d(const cs_conv3d_args* a, cs_stream_t stream) {
+  if (!a || !a->in1 || !a->weight || !a->out) return cs::set_error(CS_ERR_INVALID, "cs_conv3d: null pointer");
+  cs::IgemmArgs g{};
+  g.in1 = a->in1; g.C1 = a->C1; g.in1_pitch = a->in1_pitch;
+  g.in2 = a->in2; g.C2 = a->in2 ? a->C2 : 0; g.in2_pitch = a->in2_pitch;
+  g.B = a->B; g.D = a->D; g.H = a->H; g.W = a->W;
+  g.weight = a->weight; g.Cout = a->Cout;
+  g.kd = a->kd; g.kh = a->kh; g.kw = a->kw; g.sd = a->sd; g.sh = a->sh; g.sw = a->sw;
+  g.pd = a->pd; g.ph = a->ph; g.pw = a->pw; g.pd_back = a->pd_back; g.ph_back = a->ph_back; g.pw_back = a->pw_back;
+  g.bias = a->bias; g.rowvec = a->rowvec; g.rowvec_pitch = a->rowvec_pitch;
+  g.residual = a->residual; g.res_pitch = a->res_pitch;
+  g.out = a->out; g.out_pitch = a->out_pitch; g.out_mode = a->out_mode; g.act = a->act;
+  g.stat_sum = a->stat_sum; g.stat_pitch = a->stat_pitch; g.bn_hint = a->bn_hint;
+  if (g.kd < 1 || g.kh < 1 || g.kw < 1 || g.sd < 1 || g.sh < 1 || g.sw < 1 || g.B < 1)
+    return cs::set_error(CS_ERR_INVALID, "cs_conv3d: bad filter/stride/batch");
+  return cs::igemm_launch(g, S(stream));
+}
+
+int cs_groupnorm_stats(const void* x, int32_t B, int32_t Sp, int32_t C, int32_t pitch, float* stat,
+                       int32_t stat_pitch, cs_stream_t stream) {
+  return cs::gn_stats_launch(x, B, Sp, C, pitch, stat, stat_pitch, S(stream));
+}
+int cs_groupnorm_finalize(float* stat, const float* gamma, const float* beta, int32_t B, int32_t C, int32_t groups,
+                          int32_t Sp, float eps, float* scale_shift, cs_stream_t stream) {
+  return cs::gn_finalize_launch(stat, gamma, beta, B, C, groups, Sp, eps, scale_shift, S(stream));
+}
+int cs_groupnorm_apply(const void* x, int32_t B, int32_t Sp, int32_t C, int32_t pitch, const float* scale_shift,
+                       int32_t ss_pitch, void* y, int32_t y_pitch, int32_t act, cs_stream_t stream) {
+  return cs::gn_apply_launch(x, B, Sp, C, pitch, scale_shift, ss_pitch, y, y_pitch, act, S(stream));
+}
+int cs_layernorm(const void* x, int64_t M, int32_t C, int32_t pitch, const float* gamma, const float* beta,
+                 float eps, void* y, int32_t y_pitch, cs_stream_t stream) {
+  return cs::layernorm_launch(x, M, C, pitch, gamma, beta, eps, y, y_pitch, S(stream));
+}
+int cs_attention(const void* q, const void* k, const void* v, void* out, int32_t B, int32_t H, int32_t Nq,
+                 int32_t Nk, int32_t Dp, int32_t q_pitch, int32_t kv_pitch, int32_t o_pitch, int32_t d_out,
+                 float scale, cs_stream_t stream) {
+  return cs::attention_launch(q, k, v, out, B, H, Nq, Nk, Dp, q_pitch, kv_pitch, o_pitch, d_out, scale, S(stream));
+}
+int cs_geglu(const void* x, int64_t M, int32_t Ch, int32_t pitch, void* y, int32_t y_pitch, cs_stream_t stream) {
+  return cs::geglu_launch(x, M, Ch, pitch, y, y_pitch, S(stream));
+}
+int cs_upsample_nearest(const void* x, int32_t B, int32_t D, int32_t H, int32_t W, int32_t C, int32_t pitch,
+                        int32_t fd, int32_t fh, int32_t fw, void* y, int32_t y_pitch, cs_stream_t stream) {
+  return cs::upsample_launch(x, B, D, H, W, C, pitch, fd, fh, fw, y, y_pitch, S(stream));
+}
+int cs_im2col_small(const float* x, int32_t Bsrc, int32_t B, int32_t C, int32_t D, int32_t H, int32_t W, int32_t Kp,
+                    void* col, cs_stream_t stream) {
+  return cs::im2col_small_launch(x, Bsrc, B, C, D, H, W, Kp, col, S(stream));
+}
+int cs_timestep_embedding(const int64_t* t, int32_t B, int32_t dim, float max_period, float* out,
+                          cs_stream_t stream) {
+  return cs::timestep_embedding_launch(reinterpret_cast<const long long*>(t), B, dim, max_period, out, S(stream));
+}
+int cs_linear_small(const float* x, int32_t M, int32_t K, int32_t x_pitch, const float* W, const float* bias,
+                    int32_t N, int32_t act_in, int32_t act_out, float* y, int32_t y_pitch, cs_stream_t stream) {
+  return cs::linear_small_launch(x, M, K, x_pitch, W, bias, N, act_in, act_out, y, y_pitch, S(stream));
+}
+int cs_ddim_step(const float* x, const float* eps, int64_t n, int32_t guided, float scale, float a_t, float a_prev,
+                 float sigma, float sqrt_one_minus_at, const float* noise, float* x_prev, float* pred_x0,
+                 cs_stream_t stream) {
+  return cs::ddim_step_launch(x, eps, n, guided, scale, a_t, a_prev, sigma, sqrt_one_minus_at, noise, x_prev,
+                              pred_x0, S(stream));
+}
+int cs_q_sample(const float* x0, const float* noise, const int64_t* t, const float* sqrt_ac, const float* sqrt_1mac,
+                int64_t per_sample, int32_t B, float* out, cs_stream_t stream) {
+  return cs::q_sample_launch(x0, noise, reinterpret_cast<const long long*>(t), sqrt_ac, sqrt_1mac, per_sample, B,
+                             out, S(stream));
+}
+int cs_ncdhw_to_ndhwc(const float* x, int32_t B, int32_t C, int64_t Sp, int32_t Cp, void* y, cs_stream_t stream) {
+  return cs::ncdhw_to_ndhwc_launch(x, B, C, Sp, Cp, y, S(stream));
+}
+int cs_ndhwc_to_ncdhw(const void* x, int32_t B, int32_t C, int64_t Sp, int32_t pitch, float* y, cs_stream_t stream) {
+  return cs::ndhwc_to_ncdhw_launch(x, B, C, Sp, pitch, y, S(stream));
+}
+
+}  // extern "C"

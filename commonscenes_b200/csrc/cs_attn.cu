@@ -1,0 +1,253 @@
+// Fused softmax(Q K^T * scale) V for the transformer blocks of the denoiser and the VQ-VAE mid block.
+//
+// Reference semantics: CrossAttention.forward (model/networks/diffusion_networks/attention.py:172-219,
+// 8 heads, no mask, scale = dim_head ** -0.5) and AttnBlock.forward
+// (model/networks/vqvae_networks/vqvae_modules.py:154-178, single head, scale = c ** -0.5).
+// The reference materialises the (B*heads, N, N) fp32 score matrix; this kernel keeps it on chip
+// (online softmax, fp32 statistics).
+//
+// Round-1 implementation: warp-level mma.sync.m16n8k16 (bf16 in, fp32 accumulate), cp.async double
+// buffering of K/V.  Attention is 1.9 % of the path's FLOPs; the tcgen05 version is
+// scheduled after the convolution path is at its roofline.
+//
+// Layout: q[(b*Nq + i) * q_pitch + h*Dp + d], k/v[(b*Nk + j) * kv_pitch + h*Dp + d]  (bf16, head dim
+// zero-padded to Dp by the weight packing), out[(b*Nq + i) * o_pitch + h*d_out + d] for d < d_out.
+#include "cs_host.h"
+
+namespace cs {
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+  const uint32_t d = smem_u32(smem_dst);
+  const int sz = valid ? 16 : 0;  // src-size 0 -> zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int DP>
+__global__ void __launch_bounds__(128)
+attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
+                 const __nv_bfloat16* __restrict__ v, __nv_bfloat16* __restrict__ out, int Nq, int Nk,
+                 int q_pitch, int kv_pitch, int o_pitch, int d_out, float scale_log2) {
+  constexpr int BM = 64, BN = 64;
+  constexpr int PITCH = DP + 8;          // elements; (DP*2+16) bytes = odd multiple of 16 -> conflict-free ldmatrix
+  constexpr int CPR = DP / 8;            // 16-byte chunks per row
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_raw);
+  __nv_bfloat16* sK = sQ + BM * PITCH;   // [2][BN][PITCH]
+  __nv_bfloat16* sV = sK + 2 * BN * PITCH;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.x * BM;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const __nv_bfloat16* qg = q + (static_cast<long long>(b) * Nq) * q_pitch + h * DP;
+  const __nv_bfloat16* kg = k + (static_cast<long long>(b) * Nk) * kv_pitch + h * DP;
+  const __nv_bfloat16* vg = v + (static_cast<long long>(b) * Nk) * kv_pitch + h * DP;
+
+  // ---- stage Q and the first K/V tile ----
+  for (int i = tid; i < BM * CPR; i += 128) {
+    const int r = i / CPR, c = i - r * CPR;
+    const bool ok = (m0 + r) < Nq;
+    cp_async16(sQ + r * PITCH + c * 8, qg + static_cast<long long>(ok ? m0 + r : 0) * q_pitch + c * 8, ok);
+  }
+  auto load_kv = [&](int tile, int buf) {
+    const int j0 = tile * BN;
+    for (int i = tid; i < BN * CPR; i += 128) {
+      const int r = i / CPR, c = i - r * CPR;
+      const bool ok = (j0 + r) < Nk;
+      const long long off = static_cast<long long>(ok ? j0 + r : 0) * kv_pitch + c * 8;
+      cp_async16(sK + (buf * BN + r) * PITCH + c * 8, kg + off, ok);
+      cp_async16(sV + (buf * BN + r) * PITCH + c * 8, vg + off, ok);
+    }
+  };
+  load_kv(0, 0);
+  cp_async_commit();
+
+  float o[DP / 8][4];
+#pragma unroll
+  for (int i = 0; i < DP / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+  float row_max[2] = {-INFINITY, -INFINITY};
+  float row_sum[2] = {0.f, 0.f};
+
+  const int ntiles = (Nk + BN - 1) / BN;
+  const uint32_t sQ_u = smem_u32(sQ), sK_u = smem_u32(sK), sV_u = smem_u32(sV);
+  // per-lane ldmatrix offsets (bytes)
+  const uint32_t a_off = static_cast<uint32_t>(((warp * 16 + (lane & 15)) * PITCH + (lane >> 4) * 8) * 2);
+  const uint32_t kb_off = static_cast<uint32_t>((((lane & 7) + ((lane >> 4) << 3)) * PITCH + ((lane >> 3) & 1) * 8) * 2);
+  const uint32_t vb_off = static_cast<uint32_t>((((lane & 7) + ((lane >> 3) & 1) * 8) * PITCH + (lane >> 4) * 8) * 2);
+
+  for (int t = 0; t < ntiles; ++t) {
+    const int buf = t & 1;
+    if (t + 1 < ntiles) {
+      load_kv(t + 1, buf ^ 1);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+
+    // ---- S = Q K^T (16 x 64 per warp) ----
+    float s[BN / 8][4];
+#pragma unroll
+    for (int i = 0; i < BN / 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+    const uint32_t kbase = sK_u + static_cast<uint32_t>(buf * BN * PITCH * 2);
+#pragma unroll
+    for (int kk = 0; kk < DP / 16; ++kk) {
+      uint32_t a[4];
+      ldsm_x4(sQ_u + a_off + kk * 32, a[0], a[1], a[2], a[3]);
+#pragma unroll
+      for (int np = 0; np < BN / 16; ++np) {
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4(kbase + kb_off + static_cast<uint32_t>(np * 16 * PITCH * 2) + kk * 32, b0, b1, b2, b3);
+        mma_bf16_16816(s[2 * np], a, b0, b1);
+        mma_bf16_16816(s[2 * np + 1], a, b2, b3);
+      }
+    }
+    // ---- mask the key tail ----
+    const int j0 = t * BN;
+    if (j0 + BN > Nk) {
+#pragma unroll
+      for (int ni = 0; ni < BN / 8; ++ni) {
+        const int j = j0 + ni * 8 + (lane & 3) * 2;
+        if (j >= Nk) { s[ni][0] = -INFINITY; s[ni][2] = -INFINITY; }
+        if (j + 1 >= Nk) { s[ni][1] = -INFINITY; s[ni][3] = -INFINITY; }
+      }
+    }
+    // ---- online softmax (rows g and g+8 of the warp's 16) ----
+    float mx[2] = {row_max[0], row_max[1]};
+#pragma unroll
+    for (int ni = 0; ni < BN / 8; ++ni) {
+      mx[0] = fmaxf(mx[0], fmaxf(s[ni][0], s[ni][1]));
+      mx[1] = fmaxf(mx[1], fmaxf(s[ni][2], s[ni][3]));
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+    }
+    float corr[2], msc[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      corr[r] = exp2f((row_max[r] - mx[r]) * scale_log2);  // row_max = -inf on the first tile -> 0
+      msc[r] = mx[r] * scale_log2;
+      row_max[r] = mx[r];
+      row_sum[r] *= corr[r];
+    }
+#pragma unroll
+    for (int i = 0; i < DP / 8; ++i) {
+      o[i][0] *= corr[0]; o[i][1] *= corr[0];
+      o[i][2] *= corr[1]; o[i][3] *= corr[1];
+    }
+#pragma unroll
+    for (int ni = 0; ni < BN / 8; ++ni) {
+      s[ni][0] = exp2f(s[ni][0] * scale_log2 - msc[0]);
+      s[ni][1] = exp2f(s[ni][1] * scale_log2 - msc[0]);
+      s[ni][2] = exp2f(s[ni][2] * scale_log2 - msc[1]);
+      s[ni][3] = exp2f(s[ni][3] * scale_log2 - msc[1]);
+      row_sum[0] += s[ni][0] + s[ni][1];
+      row_sum[1] += s[ni][2] + s[ni][3];
+    }
+    // ---- O += P V ----
+    const uint32_t vbase = sV_u + static_cast<uint32_t>(buf * BN * PITCH * 2);
+#pragma unroll
+    for (int kk = 0; kk < BN / 16; ++kk) {
+      uint32_t a[4];
+      a[0] = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
+      a[1] = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
+      a[2] = pack_bf16x2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+      a[3] = pack_bf16x2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+      for (int dp = 0; dp < DP / 16; ++dp) {
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4_t(vbase + vb_off + static_cast<uint32_t>(kk * 16 * PITCH * 2) + dp * 32, b0, b1, b2, b3);
+        mma_bf16_16816(o[2 * dp], a, b0, b1);
+        mma_bf16_16816(o[2 * dp + 1], a, b2, b3);
+      }
+    }
+    __syncthreads();  // everyone done with this K/V buffer before it is refilled
+  }
+
+  // ---- normalise and store ----
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    row_sum[r] += __shfl_xor_sync(0xffffffffu, row_sum[r], 1);
+    row_sum[r] += __shfl_xor_sync(0xffffffffu, row_sum[r], 2);
+  }
+  const float inv0 = 1.f / row_sum[0], inv1 = 1.f / row_sum[1];
+  const int r0 = m0 + warp * 16 + (lane >> 2), r1 = r0 + 8;
+  __nv_bfloat16* og = out + (static_cast<long long>(b) * Nq) * o_pitch + h * d_out;
+#pragma unroll
+  for (int ni = 0; ni < DP / 8; ++ni) {
+    const int d = ni * 8 + (lane & 3) * 2;
+    if (d < d_out) {  // d_out is even, so d+1 < d_out as well
+      if (r0 < Nq)
+        *reinterpret_cast<uint32_t*>(og + static_cast<long long>(r0) * o_pitch + d) =
+            pack_bf16x2(o[ni][0] * inv0, o[ni][1] * inv0);
+      if (r1 < Nq)
+        *reinterpret_cast<uint32_t*>(og + static_cast<long long>(r1) * o_pitch + d) =
+            pack_bf16x2(o[ni][2] * inv1, o[ni][3] * inv1);
+    }
+  }
+}
+
+template <int DP>
+static int attention_launch_t(const void* q, const void* k, const void* v, void* out, int B, int H, int Nq,
+                              int Nk, int q_pitch, int kv_pitch, int o_pitch, int d_out, float scale,
+                              cudaStream_t st) {
+  constexpr int PITCH = DP + 8;
+  const size_t smem = static_cast<size_t>(64 + 4 * 64) * PITCH * 2;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(attention_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_cuda_error(e, "attention: cudaFuncSetAttribute");
+    attr = true;
+  }
+  const float scale_log2 = scale * 1.4426950408889634f;
+  attention_kernel<DP><<<dim3((Nq + 63) / 64, H, B), 128, smem, st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(q), reinterpret_cast<const __nv_bfloat16*>(k),
+      reinterpret_cast<const __nv_bfloat16*>(v), reinterpret_cast<__nv_bfloat16*>(out), Nq, Nk, q_pitch,
+      kv_pitch, o_pitch, d_out, scale_log2);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(e, "attention: launch");
+  count_launch();
+  return CS_OK;
+}
+
+int attention_launch(const void* q, const void* k, const void* v, void* out, int B, int H, int Nq, int Nk,
+                     int Dp, int q_pitch, int kv_pitch, int o_pitch, int d_out, float scale, cudaStream_t st) {
+  if (q_pitch % 8 || kv_pitch % 8 || o_pitch % 2 || d_out % 2 || d_out > Dp || Nk < 1)
+    return set_error(CS_ERR_INVALID, "attention: pitches must be multiples of 8, d_out even and <= Dp");
+  if (reinterpret_cast<uintptr_t>(q) % 16 || reinterpret_cast<uintptr_t>(k) % 16 ||
+      reinterpret_cast<uintptr_t>(v) % 16 || reinterpret_cast<uintptr_t>(out) % 4 || (H * d_out) % 2)
+    return set_error(CS_ERR_INVALID, "attention: q/k/v must be 16-byte aligned");
+  switch (Dp) {
+    case 32: return attention_launch_t<32>(q, k, v, out, B, H, Nq, Nk, q_pitch, kv_pitch, o_pitch, d_out, scale, st);
+    case 64: return attention_launch_t<64>(q, k, v, out, B, H, Nq, Nk, q_pitch, kv_pitch, o_pitch, d_out, scale, st);
+    case 96: return attention_launch_t<96>(q, k, v, out, B, H, Nq, Nk, q_pitch, kv_pitch, o_pitch, d_out, scale, st);
+    case 128: return attention_launch_t<128>(q, k, v, out, B, H, Nq, Nk, q_pitch, kv_pitch, o_pitch, d_out, scale, st);
+    case 256: return attention_launch_t<256>(q, k, v, out, B, H, Nq, Nk, q_pitch, kv_pitch, o_pitch, d_out, scale, st);
+    default: return set_error(CS_ERR_UNSUPPORTED, "attention: padded head dim must be 32, 64, 96, 128 or 256");
+  }
+}
+
+}  // namespace cs

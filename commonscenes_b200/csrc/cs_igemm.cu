@@ -1,0 +1,409 @@
+// tcgen05 implicit-GEMM for the 3-D convolutions and linear layers of the denoiser hot path.
+//
+// One kernel covers every GEMM-class op of the path:
+//   * 3x3x3 convolutions of UNet3DModel's ResBlocks / Down / Upsample
+//     (reference: model/networks/diffusion_networks/openai_model_3d.py:130-314) and of the
+//     VQ-VAE encoder/decoder (model/networks/vqvae_networks/vqvae_modules.py:33-123),
+//   * 1x1x1 convolutions and nn.Linear layers of SpatialTransformer3D
+//     (model/networks/diffusion_networks/attention.py:39-66,154-219,298-351).
+//
+// Formulation: activations live in HBM as channels-last bf16 [B][D][H][W][C]; weights as
+// [Cout][taps][Cin] bf16 (K-major).  Output tile = 128 voxels x BN channels, accumulated in TMEM.
+// For each filter tap and each 64-channel chunk, TMA loads a *shifted* 5-D box of the activation
+// (out-of-bounds voxels are zero-filled by the TMA unit = the convolution's zero padding, so there
+// is no im2col buffer and no halo logic) plus the matching [BN][64] weight slab, both landing in
+// 128B-swizzled shared memory exactly in the UMMA canonical K-major layout.  A single elected
+// thread issues tcgen05.mma (M=128, N=BN, K=16) and tcgen05.commit; four epilogue warps drain the
+// fp32 accumulator with tcgen05.ld and apply bias / per-sample vector / residual / activation and
+// (optionally) accumulate the GroupNorm statistics of the result.
+//
+// Roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2-5 = epilogue.  Persistent over tiles; TMEM accumulator is double buffered so the
+// epilogue of tile i overlaps the main loop of tile i+1.
+#include "cs_common.cuh"
+#include "cs_igemm.cuh"
+
+namespace cs {
+
+static constexpr int kIgemmThreads = 192;
+static constexpr int kMaxStages = 8;
+static constexpr int kABytes = 128 * 128;  // 128 voxels x 64 bf16
+
+struct __align__(8) IgemmBarriers {
+  uint64_t full[kMaxStages];
+  uint64_t empty[kMaxStages];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kIgemmThreads, 1)
+igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
+             const __grid_constant__ CUtensorMap tmW, const IgemmParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ IgemmBarriers bars;
+
+  // 1024-byte alignment is required by the 128B swizzle atoms.
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int stage_bytes = kABytes + p.BN * 128;
+  const int nch1 = (p.C1 + 63) >> 6;
+  const int nch2 = (p.C2 + 63) >> 6;
+  const int nch = nch1 + nch2;
+  const int ntaps = p.kd * p.kh * p.kw;
+  const int kiters = ntaps * nch;
+  const int total_tiles = p.m_tiles * p.n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA1);
+    if (p.C2 > 0) tma_prefetch_desc(&tmA2);
+    tma_prefetch_desc(&tmW);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&bars.full[s], 1);
+      mbar_init(&bars.empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&bars.tmem_full[a], 1);
+      mbar_init(&bars.tmem_empty[a], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&bars.tmem_base, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars.tmem_base;
+
+  const int tiles_w = p.Wo / p.bw, tiles_h = p.Ho / p.bh, tiles_d = p.Do / p.bd;
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const int ctot = p.C1 + p.C2;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_tiles;
+        int mt = tile / p.n_tiles;
+        const int tw = mt % tiles_w; mt /= tiles_w;
+        const int th = mt % tiles_h; mt /= tiles_h;
+        const int td = mt % tiles_d; mt /= tiles_d;
+        const int b0 = mt * p.bb;
+        const int w0 = tw * p.bw * p.sw - p.pw;
+        const int h0 = th * p.bh * p.sh - p.ph;
+        const int d0 = td * p.bd * p.sd - p.pd;
+        const int n0 = nt * p.BN;
+        for (int zd = 0; zd < p.kd; ++zd)
+          for (int zh = 0; zh < p.kh; ++zh)
+            for (int zw = 0; zw < p.kw; ++zw) {
+              const int tap = (zd * p.kh + zh) * p.kw + zw;
+              for (int ch = 0; ch < nch; ++ch) {
+                mbar_wait(&bars.empty[stage], phase ^ 1);
+                uint8_t* sa = smem + stage * stage_bytes;
+                uint8_t* sb = sa + kABytes;
+                mbar_arrive_expect_tx(&bars.full[stage], stage_bytes);
+                int kcol;
+                if (ch < nch1) {
+                  tma_load_5d(&tmA1, &bars.full[stage], sa, ch * 64, w0 + zw, h0 + zh, d0 + zd, b0);
+                  kcol = tap * ctot + ch * 64;
+                } else {
+                  tma_load_5d(&tmA2, &bars.full[stage], sa, (ch - nch1) * 64, w0 + zw, h0 + zh,
+                              d0 + zd, b0);
+                  kcol = tap * ctot + p.C1 + (ch - nch1) * 64;
+                }
+                tma_load_2d(&tmW, &bars.full[stage], sb, kcol, n0);
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+              }
+            }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      const uint32_t idesc = umma_idesc_bf16_m128(static_cast<uint32_t>(p.BN));
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&bars.tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * 256);
+        uint32_t accumulate = 0;
+        for (int tap = 0; tap < ntaps; ++tap) {
+          for (int ch = 0; ch < nch; ++ch) {
+            const int valid = (ch < nch1) ? min(64, p.C1 - ch * 64) : min(64, p.C2 - (ch - nch1) * 64);
+            const int ksteps = (valid + 15) >> 4;
+            mbar_wait(&bars.full[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+            const uint64_t adesc = umma_desc_k_sw128(sa);
+            const uint64_t bdesc = umma_desc_k_sw128(sa + kABytes);
+            for (int k = 0; k < ksteps; ++k) {
+              // +32 bytes (= 16 bf16) along K inside the 128-byte swizzled row
+              umma_bf16(d_tmem, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2),
+                        idesc, accumulate);
+              accumulate = 1;
+            }
+            umma_commit(&bars.empty[stage]);  // frees the smem stage once these MMAs retire
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+        }
+        umma_commit(&bars.tmem_full[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // =========================== epilogue (warps 2..5) ===========================
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = quarter * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const int rows_per_sample = p.bd * p.bh * p.bw;
+    const long long spatial = static_cast<long long>(p.Do) * p.Ho * p.Wo;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int nt = tile % p.n_tiles;
+      int mt = tile / p.n_tiles;
+      const int tw = mt % tiles_w; mt /= tiles_w;
+      const int th = mt % tiles_h; mt /= tiles_h;
+      const int td = mt % tiles_d; mt /= tiles_d;
+      // voxel of this thread's accumulator row
+      int r = row;
+      const int iw = r % p.bw; r /= p.bw;
+      const int ih = r % p.bh; r /= p.bh;
+      const int id = r % p.bd; r /= p.bd;
+      const int b = mt * p.bb + r;
+      const long long sidx =
+          (static_cast<long long>(td * p.bd + id) * p.Ho + (th * p.bh + ih)) * p.Wo + (tw * p.bw + iw);
+      const long long m = static_cast<long long>(b) * spatial + sidx;
+      const int n0 = nt * p.BN;
+
+      mbar_wait(&bars.tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                             static_cast<uint32_t>(acc * 256);
+      for (int c0 = 0; c0 < p.BN; c0 += 16) {
+        if (n0 + c0 >= p.Cout) break;  // warp-uniform
+        uint32_t raw[16];
+        tmem_ld16(t_row + static_cast<uint32_t>(c0), raw);
+        tmem_ld_wait();
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]);
+        const int n = n0 + c0;
+        const bool full16 = (n + 16 <= p.Cout);
+        if (p.bias) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (full16 || n + j < p.Cout) v[j] += __ldg(p.bias + n + j);
+        }
+        if (p.rowvec) {
+          const float* rv = p.rowvec + static_cast<long long>(b) * p.rowvec_pitch + n;
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (full16 || n + j < p.Cout) v[j] += __ldg(rv + j);
+        }
+        if (p.residual) {
+          const __nv_bfloat16* rp =
+              reinterpret_cast<const __nv_bfloat16*>(p.residual) + m * p.res_pitch + n;
+          if (full16) {
+            const uint4 q0 = *reinterpret_cast<const uint4*>(rp);
+            const uint4 q1 = *reinterpret_cast<const uint4*>(rp + 8);
+            const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float2 f = unpack_bf16x2(w[j]);
+              v[2 * j] += f.x;
+              v[2 * j + 1] += f.y;
+            }
+          } else {
+            for (int j = 0; j < 16; ++j)
+              if (n + j < p.Cout) v[j] += __bfloat162float(rp[j]);
+          }
+        }
+        if (p.act == CS_ACT_SILU) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = silu_f(v[j]);
+        } else if (p.act == CS_ACT_GELU) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = gelu_erf_f(v[j]);
+        }
+        if (p.out_mode == CS_OUT_BF16_NDHWC) {
+          __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + m * p.out_pitch + n;
+          if (full16) {
+            uint4 q0, q1;
+            q0.x = pack_bf16x2(v[0], v[1]);   q0.y = pack_bf16x2(v[2], v[3]);
+            q0.z = pack_bf16x2(v[4], v[5]);   q0.w = pack_bf16x2(v[6], v[7]);
+            q1.x = pack_bf16x2(v[8], v[9]);   q1.y = pack_bf16x2(v[10], v[11]);
+            q1.z = pack_bf16x2(v[12], v[13]); q1.w = pack_bf16x2(v[14], v[15]);
+            *reinterpret_cast<uint4*>(op) = q0;
+            *reinterpret_cast<uint4*>(op + 8) = q1;
+          } else {
+            for (int j = 0; j < 16; ++j)
+              if (n + j < p.Cout) op[j] = __float2bfloat16_rn(v[j]);
+          }
+        } else if (p.out_mode == CS_OUT_F32_NDHWC) {
+          float* op = reinterpret_cast<float*>(p.out) + m * p.out_pitch + n;
+          for (int j = 0; j < 16; ++j)
+            if (n + j < p.Cout) op[j] = v[j];
+        } else {  // CS_OUT_F32_NCDHW: consecutive lanes = consecutive voxels -> coalesced per channel
+          float* op = reinterpret_cast<float*>(p.out) +
+                      (static_cast<long long>(b) * p.Cout + n) * spatial + sidx;
+          for (int j = 0; j < 16; ++j)
+            if (n + j < p.Cout) op[static_cast<long long>(j) * spatial] = v[j];
+        }
+        if (p.stat_sum) {
+          // GroupNorm statistics of the value just produced (host guarantees a warp's 32 rows
+          // belong to one sample): butterfly over rows, lane j keeps column j.
+          float mys = 0.f, myq = 0.f;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float s = warp_sum(v[j]);
+            const float q = warp_sum(v[j] * v[j]);
+            if (lane == j) { mys = s; myq = q; }
+          }
+          if (lane < 16 && n + lane < p.Cout) {
+            float* sp = p.stat_sum + (static_cast<long long>(b) * p.stat_pitch + n + lane) * 2;
+            atomicAdd(sp, mys);
+            atomicAdd(sp + 1, myq);
+          }
+        }
+      }
+      (void)rows_per_sample;
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars.tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  // teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace cs
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+#include "cs_host.h"
+
+namespace cs {
+
+static int pick_tile_box(int B, int Do, int Ho, int Wo, int* bb, int* bd, int* bh, int* bw) {
+  int rem = 128;
+  auto take = [&rem](int extent) {
+    int t = 1;
+    while (t * 2 <= rem && extent % (t * 2) == 0) t *= 2;
+    rem /= t;
+    return t;
+  };
+  *bw = take(Wo);
+  // the box must cover W fully before it may grow in H (rows stay a dense raster of the tile)
+  *bh = (*bw == Wo) ? take(Ho) : 1;
+  *bd = (*bw == Wo && *bh == Ho) ? take(Do) : 1;
+  *bb = (*bw == Wo && *bh == Ho && *bd == Do) ? take(B) : 1;
+  return rem == 1 ? 0 : -1;
+}
+
+int igemm_launch(const IgemmArgs& a, cudaStream_t stream) {
+  if (a.C1 <= 0 || a.C1 % 8 || a.C2 % 8 || a.Cout <= 0) return set_error(CS_ERR_INVALID, "igemm: channels must be multiples of 8");
+  if (a.in1_pitch % 8 || (a.C2 > 0 && a.in2_pitch % 8)) return set_error(CS_ERR_INVALID, "igemm: input pitch must be a multiple of 8");
+  if (a.C2 > 0 && a.C1 % 16) return set_error(CS_ERR_INVALID, "igemm: two-source concat needs C1 % 16 == 0");
+  if (reinterpret_cast<uintptr_t>(a.in1) % 16 || reinterpret_cast<uintptr_t>(a.in2) % 16 ||
+      reinterpret_cast<uintptr_t>(a.weight) % 16)
+    return set_error(CS_ERR_INVALID, "igemm: pointers must be 16-byte aligned");
+
+  IgemmParams p{};
+  p.B = a.B;
+  // output extent (PyTorch conv arithmetic with explicit front/back padding)
+  p.Do = (a.D + a.pd + a.pd_back - a.kd) / a.sd + 1;
+  p.Ho = (a.H + a.ph + a.ph_back - a.kh) / a.sh + 1;
+  p.Wo = (a.W + a.pw + a.pw_back - a.kw) / a.sw + 1;
+  if (p.Do <= 0 || p.Ho <= 0 || p.Wo <= 0) return set_error(CS_ERR_INVALID, "igemm: empty output");
+  if (pick_tile_box(p.B, p.Do, p.Ho, p.Wo, &p.bb, &p.bd, &p.bh, &p.bw))
+    return set_error(CS_ERR_UNSUPPORTED, "igemm: output grid cannot be tiled into 128-voxel boxes");
+  p.kd = a.kd; p.kh = a.kh; p.kw = a.kw;
+  p.sd = a.sd; p.sh = a.sh; p.sw = a.sw;
+  p.pd = a.pd; p.ph = a.ph; p.pw = a.pw;
+  p.C1 = a.C1; p.C2 = a.C2; p.Cout = a.Cout;
+  // N tile: largest multiple of 16 <= 256 that splits Cout evenly-ish
+  int bn = a.bn_hint;
+  if (bn <= 0) {
+    const int cpad = (a.Cout + 15) / 16 * 16;
+    int nt = (cpad + 255) / 256;
+    bn = ((cpad + nt - 1) / nt + 15) / 16 * 16;
+  }
+  if (bn % 16 || bn < 16 || bn > 256) return set_error(CS_ERR_INVALID, "igemm: bad N tile");
+  p.BN = bn;
+  p.n_tiles = (a.Cout + bn - 1) / bn;
+  p.m_tiles = (p.B / p.bb) * (p.Do / p.bd) * (p.Ho / p.bh) * (p.Wo / p.bw);
+  const int stage_bytes = kABytes + bn * 128;
+  const int smem_budget = 227 * 1024 - 2048;
+  int stages = smem_budget / stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) return set_error(CS_ERR_INVALID, "igemm: tile too large for shared memory");
+  p.stages = stages;
+  p.bias = a.bias; p.rowvec = a.rowvec; p.rowvec_pitch = a.rowvec_pitch;
+  p.residual = a.residual; p.res_pitch = a.res_pitch;
+  p.out = a.out; p.out_pitch = a.out_pitch; p.out_mode = a.out_mode; p.act = a.act;
+  p.stat_sum = a.stat_sum; p.stat_pitch = a.stat_pitch;
+  if (p.stat_sum && (p.bd * p.bh * p.bw) % 32) return set_error(CS_ERR_UNSUPPORTED, "igemm: fused stats need >= 32 voxels per sample per tile");
+  if (p.out_mode == CS_OUT_BF16_NDHWC && (a.out_pitch % 8 || reinterpret_cast<uintptr_t>(a.out) % 16))
+    return set_error(CS_ERR_INVALID, "igemm: bf16 output must be 16-byte aligned with pitch % 8 == 0");
+  if (p.residual && (a.res_pitch % 8 || reinterpret_cast<uintptr_t>(a.residual) % 16))
+    return set_error(CS_ERR_INVALID, "igemm: residual must be 16-byte aligned with pitch % 8 == 0");
+
+  CUtensorMap tmA1, tmA2, tmW;
+  {
+    const uint64_t dims[5] = {(uint64_t)a.C1, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.D, (uint64_t)a.B};
+    const uint64_t pitch = (uint64_t)a.in1_pitch * 2;
+    const uint64_t strides[4] = {pitch, pitch * a.W, pitch * a.W * a.H, pitch * a.W * a.H * a.D};
+    const uint32_t box[5] = {64u, (uint32_t)(p.bw * a.sw), (uint32_t)(p.bh * a.sh), (uint32_t)(p.bd * a.sd), (uint32_t)p.bb};
+    const uint32_t estr[5] = {1u, (uint32_t)a.sw, (uint32_t)a.sh, (uint32_t)a.sd, 1u};
+    int rc = make_tensor_map(&tmA1, a.in1, 5, dims, strides, box, estr);
+    if (rc) return rc;
+    tmA2 = tmA1;
+    if (a.C2 > 0) {
+      const uint64_t dims2[5] = {(uint64_t)a.C2, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.D, (uint64_t)a.B};
+      const uint64_t pitch2 = (uint64_t)a.in2_pitch * 2;
+      const uint64_t strides2[4] = {pitch2, pitch2 * a.W, pitch2 * a.W * a.H, pitch2 * a.W * a.H * a.D};
+      rc = make_tensor_map(&tmA2, a.in2, 5, dims2, strides2, box, estr);
+      if (rc) return rc;
+    }
+    const uint64_t ktot = (uint64_t)(a.C1 + a.C2) * a.kd * a.kh * a.kw;
+    const uint64_t wd[2] = {ktot, (uint64_t)a.Cout};
+    const uint64_t ws[1] = {ktot * 2};
+    const uint32_t wb[2] = {64u, (uint32_t)bn};
+    const uint32_t we[2] = {1u, 1u};
+    rc = make_tensor_map(&tmW, a.weight, 2, wd, ws, wb, we);
+    if (rc) return rc;
+  }
+
+  static bool attr_set = false;
+  const int smem_bytes = stages * stage_bytes + 1024;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return set_cuda_error(e, "igemm: cudaFuncSetAttribute");
+    attr_set = true;
+  }
+  const int total = p.m_tiles * p.n_tiles;
+  const int grid = total < num_sms() ? total : num_sms();
+  igemm_kernel<<<grid, kIgemmThreads, smem_bytes, stream>>>(tmA1, tmA2, tmW, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(e, "igemm: launch");
+  count_launch();
+  return CS_OK;
+}
+
+}  // namespace cs

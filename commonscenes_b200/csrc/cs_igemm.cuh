@@ -1,0 +1,40 @@
+// Parameter block shared by the tcgen05 implicit-GEMM kernel and its host launcher.
+#pragma once
+#include <stdint.h>
+
+namespace cs {
+
+enum : int { CS_OUT_BF16_NDHWC = 0, CS_OUT_F32_NCDHW = 1, CS_OUT_F32_NDHWC = 2 };
+enum : int { CS_ACT_NONE = 0, CS_ACT_SILU = 1, CS_ACT_GELU = 2 };
+
+struct IgemmParams {
+  // output grid (voxels) and the 128-voxel tile box over it
+  int B, Do, Ho, Wo;
+  int bb, bd, bh, bw;  // bb*bd*bh*bw == 128
+  // filter
+  int kd, kh, kw;
+  int sd, sh, sw;
+  int pd, ph, pw;
+  // channels: up to two concatenated input sources (C2 == 0 -> single source)
+  int C1, C2;
+  int Cout;
+  int BN;       // N tile (multiple of 16, <= 256)
+  int n_tiles;  // ceil(Cout / BN)
+  int m_tiles;
+  int stages;
+  // epilogue
+  const float* bias;      // [Cout] or null
+  const float* rowvec;    // [B][rowvec_pitch] per-sample vector added to every voxel, or null
+  int rowvec_pitch;
+  const void* residual;   // bf16 [M][res_pitch] or null
+  int res_pitch;
+  void* out;              // see out_mode
+  int out_pitch;          // elements per output row (NDHWC modes)
+  int out_mode;
+  int act;
+  // optional fused GroupNorm statistics of the OUTPUT: per (sample, channel) sum and sum of squares
+  float* stat_sum;        // [B][stat_pitch][2] fp32, atomically accumulated, or null
+  int stat_pitch;
+};
+
+}  // namespace cs

@@ -1,0 +1,237 @@
+// GroupNorm / LayerNorm for channels-last bf16 activations (HBM-bound kernels).
+//
+// GroupNorm follows the reference's GroupNorm32 (fp32 statistics, biased variance):
+//   model/networks/diffusion_networks/ldm_diffusion_util.py:237-239 (32 groups, eps 1e-5),
+//   model/networks/diffusion_networks/attention.py:78-79 and
+//   model/networks/vqvae_networks/vqvae_modules.py:13-21 (32 groups, eps 1e-6).
+// It is split into   stats  ->  finalize  ->  apply(+SiLU/GELU)   so that the statistics can
+// also be produced by the implicit-GEMM epilogue (cs_igemm.cu, stat_sum) and so that a
+// channel-concatenated input (UNet skip connections) never has to be materialised un-normalised.
+//
+// LayerNorm follows nn.LayerNorm(dim) (attention.py:229-231): one warp per token.
+#include "cs_host.h"
+
+namespace cs {
+
+// ------------------------------------------------------------------------------------------------
+// per-(sample, channel) sum / sum-of-squares, atomically added into stat[B][stat_pitch][2]
+// ------------------------------------------------------------------------------------------------
+__global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x, int S, int C, int pitch,
+                                float* __restrict__ stat, int stat_pitch, int vox_per_cta) {
+  extern __shared__ float red[];  // [R][cv][16]
+  const int cv = C >> 3;
+  const int R = blockDim.x / cv;
+  const int r = threadIdx.x / cv;
+  const int v = threadIdx.x - r * cv;
+  const int b = blockIdx.y;
+  const int s_begin = blockIdx.x * vox_per_cta;
+  const int s_end = min(S, s_begin + vox_per_cta);
+  float s[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+  if (r < R) {
+    const __nv_bfloat16* xb = x + (static_cast<long long>(b) * S) * pitch + v * 8;
+    for (int i = s_begin + r; i < s_end; i += R) {
+      const uint4 u = *reinterpret_cast<const uint4*>(xb + static_cast<long long>(i) * pitch);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16x2(w[j]);
+        s[2 * j] += f.x; q[2 * j] += f.x * f.x;
+        s[2 * j + 1] += f.y; q[2 * j + 1] += f.y * f.y;
+      }
+    }
+    float* dst = red + (r * cv + v) * 16;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { dst[j] = s[j]; dst[8 + j] = q[j]; }
+  }
+  __syncthreads();
+  // thread t < cv*16 reduces one (vector, component) over the R rows
+  for (int t = threadIdx.x; t < cv * 16; t += blockDim.x) {
+    float acc = 0.f;
+    for (int rr = 0; rr < R; ++rr) acc += red[rr * cv * 16 + t];
+    const int vv = t >> 4, comp = t & 15;
+    const int c = vv * 8 + (comp & 7);
+    atomicAdd(stat + (static_cast<long long>(b) * stat_pitch + c) * 2 + (comp >> 3), acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// finalize: (sum, sumsq) -> per-(sample, channel) affine (scale, shift); clears the accumulators
+// ------------------------------------------------------------------------------------------------
+__global__ void gn_finalize_kernel(float* __restrict__ stat, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, int C, int groups, int S, float eps,
+                                   float2* __restrict__ ss) {
+  extern __shared__ float sm[];  // [C][2]
+  const int b = blockIdx.x;
+  float* st = stat + static_cast<long long>(b) * C * 2;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = st[i];
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) st[i] = 0.f;
+  const int cpg = C / groups;
+  const double inv_n = 1.0 / (static_cast<double>(S) * cpg);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g0 = (c / cpg) * cpg;
+    double s = 0.0, q = 0.0;
+    for (int j = 0; j < cpg; ++j) { s += sm[2 * (g0 + j)]; q += sm[2 * (g0 + j) + 1]; }
+    const double mean = s * inv_n;
+    double var = q * inv_n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    const float ga = gamma ? gamma[c] : 1.f;
+    const float be = beta ? beta[c] : 0.f;
+    ss[static_cast<long long>(b) * C + c] = make_float2(ga * rstd, be - static_cast<float>(mean) * rstd * ga);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// apply: y = act(x * scale + shift), bf16 -> bf16, 8 channels per thread
+// ------------------------------------------------------------------------------------------------
+__global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x, int S, int C, int pitch,
+                                const float2* __restrict__ ss, int ss_pitch,
+                                __nv_bfloat16* __restrict__ y, int y_pitch, int act, long long total_vec) {
+  const int cv = C >> 3;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total_vec;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long row = i / cv;
+    const int v = static_cast<int>(i - row * cv);
+    const int b = static_cast<int>(row / S);
+    const uint4 u = *reinterpret_cast<const uint4*>(x + row * pitch + v * 8);
+    const float2* sp = ss + static_cast<long long>(b) * ss_pitch + v * 8;
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = unpack_bf16x2(w[j]);
+      const float2 a0 = __ldg(sp + 2 * j), a1 = __ldg(sp + 2 * j + 1);
+      float y0 = fmaf(f.x, a0.x, a0.y), y1 = fmaf(f.y, a1.x, a1.y);
+      if (act == CS_ACT_SILU) { y0 = silu_f(y0); y1 = silu_f(y1); }
+      else if (act == CS_ACT_GELU) { y0 = gelu_erf_f(y0); y1 = gelu_erf_f(y1); }
+      o[j] = pack_bf16x2(y0, y1);
+    }
+    *reinterpret_cast<uint4*>(y + row * y_pitch + v * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm over the last dim; one warp per row; C % 8 == 0, C <= 1024
+// ------------------------------------------------------------------------------------------------
+__global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long M, int C, int pitch,
+                                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                 __nv_bfloat16* __restrict__ y, int y_pitch) {
+  const int lane = threadIdx.x & 31;
+  const long long row = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int cv = C >> 3;
+  float v[4][8];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int vi = lane + 32 * k;
+    if (vi < cv) {
+      const uint4 u = *reinterpret_cast<const uint4*>(x + row * pitch + vi * 8);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16x2(w[j]);
+        v[k][2 * j] = f.x; v[k][2 * j + 1] = f.y;
+        s += f.x + f.y;
+      }
+    }
+  }
+  const float mean = warp_sum(s) / C;
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (lane + 32 * k < cv) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float d = v[k][j] - mean; q += d * d; }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / C + eps);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int vi = lane + 32 * k;
+    if (vi < cv) {
+      uint32_t o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = vi * 8 + 2 * j;
+        const float y0 = (v[k][2 * j] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
+        const float y1 = (v[k][2 * j + 1] - mean) * rstd * __ldg(gamma + c + 1) + __ldg(beta + c + 1);
+        o[j] = pack_bf16x2(y0, y1);
+      }
+      *reinterpret_cast<uint4*>(y + row * y_pitch + vi * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------------
+int gn_stats_launch(const void* x, int B, int S, int C, int pitch, float* stat, int stat_pitch,
+                    cudaStream_t st) {
+  if (C % 8 || pitch % 8 || C > 2048 || reinterpret_cast<uintptr_t>(x) % 16)
+    return set_error(CS_ERR_INVALID, "groupnorm_stats: C and pitch must be multiples of 8 (C <= 2048), x 16B aligned");
+  const int cv = C / 8;
+  int R = 256 / cv; if (R < 1) R = 1;
+  const int threads = ((R * cv + 31) / 32) * 32;
+  // aim for ~4 CTAs per SM over the whole launch
+  int splits = (4 * num_sms() + B - 1) / B;
+  int vox = (S + splits - 1) / splits;
+  if (vox < R) vox = R;
+  splits = (S + vox - 1) / vox;
+  const size_t smem = static_cast<size_t>(R) * cv * 16 * sizeof(float);
+  gn_stats_kernel<<<dim3(splits, B), threads, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), S, C,
+                                                           pitch, stat, stat_pitch, vox);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(e, "groupnorm_stats: launch");
+  count_launch();
+  return CS_OK;
+}
+
+int gn_finalize_launch(float* stat, const float* gamma, const float* beta, int B, int C, int groups, int S,
+                       float eps, float* scale_shift, cudaStream_t st) {
+  if (groups <= 0 || C % groups) return set_error(CS_ERR_INVALID, "groupnorm_finalize: C % groups != 0");
+  if (C > 4096) return set_error(CS_ERR_INVALID, "groupnorm_finalize: C too large");
+  gn_finalize_kernel<<<B, 256, static_cast<size_t>(C) * 2 * sizeof(float), st>>>(
+      stat, gamma, beta, C, groups, S, eps, reinterpret_cast<float2*>(scale_shift));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(e, "groupnorm_finalize: launch");
+  count_launch();
+  return CS_OK;
+}
+
+int gn_apply_launch(const void* x, int B, int S, int C, int pitch, const float* scale_shift, int ss_pitch,
+                    void* y, int y_pitch, int act, cudaStream_t st) {
+  if (C % 8 || pitch % 8 || y_pitch % 8 || reinterpret_cast<uintptr_t>(x) % 16 ||
+      reinterpret_cast<uintptr_t>(y) % 16)
+    return set_error(CS_ERR_INVALID, "groupnorm_apply: alignment");
+  const long long total = static_cast<long long>(B) * S * (C / 8);
+  long long blocks = (total + 255) / 256;
+  const long long cap = static_cast<long long>(num_sms()) * 16;
+  if (blocks > cap) blocks = cap;
+  gn_apply_kernel<<<static_cast<int>(blocks), 256, 0, st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), S, C, pitch, reinterpret_cast<const float2*>(scale_shift),
+      ss_pitch, reinterpret_cast<__nv_bfloat16*>(y), y_pitch, act, total);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(e, "groupnorm_apply: launch");
+  count_launch();
+  return CS_OK;
+}
+
+int layernorm_launch(const void* x, long long M, int C, int pitch, const float* gamma, const float* beta,
+                     float eps, void* y, int y_pitch, cudaStream_t st) {
+  if (C % 8 || C > 1024 || pitch % 8 || y_pitch % 8) return set_error(CS_ERR_INVALID, "layernorm: C % 8, C <= 1024");
+  const int warps = 8;
+  const long long blocks = (M + warps - 1) / warps;
+  layernorm_kernel<<<static_cast<unsigned>(blocks), warps * 32, 0, st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), M, C, pitch, gamma, beta, eps,
+      reinterpret_cast<__nv_bfloat16*>(y), y_pitch);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(e, "layernorm: launch");
+  count_launch();
+  return CS_OK;
+}
+
+}  // namespace cs

@@ -1,0 +1,351 @@
+"""Torch-tensor front end of the C ABI (include/cs_b200.h).
+
+Everything here is plumbing: it validates shapes/dtypes (mirroring the CHECK_INPUT style of the
+reference's own native code, scripts/pytorch_structural_losses/src/structural_loss.cpp:10-12),
+allocates outputs with torch, and passes raw device pointers plus the current CUDA stream to
+libcsb200.so.  No arithmetic of the hot path is done by torch.
+
+Activation convention: channels-last bf16 tensors of shape (B, D, H, W, C) whose last dim is
+contiguous; the row pitch (stride of W) may be larger than C, so a tensor may be a channel slice
+of a wider buffer.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import (ACT_GELU, ACT_NONE, ACT_SILU, OUT_BF16_NDHWC, OUT_F32_NCDHW, OUT_F32_NDHWC,
+                   Conv3dArgs, check)
+
+__all__ = [
+    "ACT_NONE", "ACT_SILU", "ACT_GELU", "conv3d", "linear_tokens", "groupnorm", "layernorm", "attention",
+    "geglu", "upsample_nearest", "im2col_small", "timestep_embedding", "linear_small", "ddim_step",
+    "q_sample", "to_channels_last", "to_ncdhw", "pack_conv_weight", "pack_linear_weight", "launch_count",
+    "reset_launch_count",
+]
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _check_act(x: torch.Tensor, name: str) -> Tuple[int, int, int, int, int, int]:
+    """Validate a channels-last bf16 activation; returns (B, D, H, W, C, pitch)."""
+    if not x.is_cuda:
+        raise _lib.CsError(f"{name}: expected a CUDA tensor (commonscenes_b200 has no CPU path)")
+    if x.dtype != torch.bfloat16 or x.dim() != 5:
+        raise _lib.CsError(f"{name}: expected a 5-D bf16 channels-last tensor, got {x.dtype} {tuple(x.shape)}")
+    B, D, H, W, Cc = x.shape
+    sb, sd, sh, sw, sc = x.stride()
+    if sc != 1 and Cc != 1:
+        raise _lib.CsError(f"{name}: channel dim must be contiguous")
+    pitch = sw if W > 1 else (sh if H > 1 else (sd if D > 1 else (sb if B > 1 else Cc)))
+    dense = (W == 1 or sw == pitch) and (H == 1 or sh == W * pitch) and (D == 1 or sd == H * W * pitch) \
+        and (B == 1 or sb == D * H * W * pitch)
+    if not dense or pitch < Cc:
+        raise _lib.CsError(f"{name}: spatial dims must be densely packed (strides {x.stride()})")
+    return B, D, H, W, Cc, pitch
+
+
+def _f32(t: Optional[torch.Tensor], name: str) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    if t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous():
+        raise _lib.CsError(f"{name}: expected a contiguous fp32 CUDA tensor")
+    return t
+
+
+def launch_count() -> int:
+    return int(_lib.load().cs_launch_count())
+
+
+def reset_launch_count() -> None:
+    _lib.load().cs_reset_launch_count()
+
+
+# ----------------------------------------------------------------------------------------------
+# weight packing (one-off, at load / after an optimizer step) — layout plumbing, done with torch
+# ----------------------------------------------------------------------------------------------
+def pack_conv_weight(w: torch.Tensor) -> torch.Tensor:
+    """(Cout, Cin, kd, kh, kw) fp32 -> (Cout, kd*kh*kw, Cin) bf16, the K-major layout cs_conv3d reads."""
+    co, ci = w.shape[0], w.shape[1]
+    return w.detach().reshape(co, ci, -1).permute(0, 2, 1).contiguous().to(torch.bfloat16)
+
+
+def pack_linear_weight(w: torch.Tensor) -> torch.Tensor:
+    """(out, in) fp32 -> (out, 1, in) bf16."""
+    return w.detach().reshape(w.shape[0], 1, w.shape[1]).contiguous().to(torch.bfloat16)
+
+
+# ----------------------------------------------------------------------------------------------
+# GEMM-class
+# ----------------------------------------------------------------------------------------------
+def conv3d(x: torch.Tensor, weight: torch.Tensor, *, ksize: Sequence[int] = (3, 3, 3),
+           stride: Sequence[int] = (1, 1, 1), pad: Sequence[int] = (1, 1, 1),
+           pad_back: Optional[Sequence[int]] = None, bias: Optional[torch.Tensor] = None,
+           rowvec: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
+           x2: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, out_mode: int = OUT_BF16_NDHWC,
+           act: int = ACT_NONE, stat_sum: Optional[torch.Tensor] = None, bn_hint: int = 0) -> torch.Tensor:
+    """act(conv3d(cat(x, x2)) + bias + rowvec[b] + residual) on the tcgen05 implicit-GEMM kernel.
+
+    `weight` is the packed (Cout, taps, Cin) bf16 tensor of `pack_conv_weight`.
+    """
+    lib = _lib.load()
+    B, D, H, W, C1, p1 = _check_act(x, "conv3d.x")
+    C2, p2 = 0, 0
+    if x2 is not None:
+        B2, D2, H2, W2, C2, p2 = _check_act(x2, "conv3d.x2")
+        if (B2, D2, H2, W2) != (B, D, H, W):
+            raise _lib.CsError("conv3d: x and x2 must share batch and spatial dims")
+    kd, kh, kw = ksize
+    if weight.dtype != torch.bfloat16 or weight.dim() != 3 or not weight.is_contiguous() or \
+            weight.shape[1] != kd * kh * kw or weight.shape[2] != C1 + C2:
+        raise _lib.CsError(f"conv3d: packed weight must be bf16 (Cout, {kd * kh * kw}, {C1 + C2}), got {tuple(weight.shape)}")
+    Cout = weight.shape[0]
+    pb = tuple(pad) if pad_back is None else tuple(pad_back)
+    Do = (D + pad[0] + pb[0] - kd) // stride[0] + 1
+    Ho = (H + pad[1] + pb[1] - kh) // stride[1] + 1
+    Wo = (W + pad[2] + pb[2] - kw) // stride[2] + 1
+    if out is None:
+        if out_mode == OUT_BF16_NDHWC:
+            out = torch.empty((B, Do, Ho, Wo, Cout), dtype=torch.bfloat16, device=x.device)
+        elif out_mode == OUT_F32_NCDHW:
+            out = torch.empty((B, Cout, Do, Ho, Wo), dtype=torch.float32, device=x.device)
+        else:
+            out = torch.empty((B, Do, Ho, Wo, Cout), dtype=torch.float32, device=x.device)
+    if out_mode == OUT_F32_NCDHW:
+        if out.dtype != torch.float32 or not out.is_contiguous() or tuple(out.shape) != (B, Cout, Do, Ho, Wo):
+            raise _lib.CsError("conv3d: NCDHW output must be contiguous fp32 (B, Cout, Do, Ho, Wo)")
+        out_pitch = 0
+    else:
+        want = torch.bfloat16 if out_mode == OUT_BF16_NDHWC else torch.float32
+        if out.dtype != want or tuple(out.shape) != (B, Do, Ho, Wo, Cout) or out.stride(-1) != 1:
+            raise _lib.CsError(f"conv3d: output must be {want} (B, Do, Ho, Wo, Cout)")
+        out_pitch = out.stride(3)
+    a = Conv3dArgs()
+    a.in1, a.C1, a.in1_pitch = x.data_ptr(), C1, p1
+    a.in2, a.C2, a.in2_pitch = _ptr(x2), C2, p2
+    a.B, a.D, a.H, a.W = B, D, H, W
+    a.weight, a.Cout = weight.data_ptr(), Cout
+    a.kd, a.kh, a.kw = kd, kh, kw
+    a.sd, a.sh, a.sw = stride
+    a.pd, a.ph, a.pw = pad
+    a.pd_back, a.ph_back, a.pw_back = pb
+    a.bias = _ptr(_f32(bias, "conv3d.bias"))
+    if rowvec is not None:
+        _f32(rowvec, "conv3d.rowvec") if rowvec.is_contiguous() else None
+        if rowvec.dtype != torch.float32 or rowvec.dim() != 2 or rowvec.shape[0] != B or rowvec.shape[1] != Cout \
+                or rowvec.stride(1) != 1:
+            raise _lib.CsError("conv3d: rowvec must be fp32 (B, Cout)")
+        a.rowvec, a.rowvec_pitch = rowvec.data_ptr(), rowvec.stride(0)
+    if residual is not None:
+        rB, rD, rH, rW, rC, rp = _check_act(residual, "conv3d.residual")
+        if (rB, rD, rH, rW, rC) != (B, Do, Ho, Wo, Cout):
+            raise _lib.CsError("conv3d: residual shape must equal the output shape")
+        a.residual, a.res_pitch = residual.data_ptr(), rp
+    a.out, a.out_pitch, a.out_mode, a.act = out.data_ptr(), out_pitch, out_mode, act
+    if stat_sum is not None:
+        a.stat_sum, a.stat_pitch = stat_sum.data_ptr(), stat_sum.shape[1]
+    a.bn_hint = bn_hint
+    check(lib.cs_conv3d(C.byref(a), _stream()), "cs_conv3d")
+    return out
+
+
+def linear_tokens(x: torch.Tensor, weight: torch.Tensor, **kw) -> torch.Tensor:
+    """nn.Linear / 1x1x1 conv over a (B, D, H, W, C) token grid (same kernel, one tap)."""
+    return conv3d(x, weight, ksize=(1, 1, 1), pad=(0, 0, 0), **kw)
+
+
+# ----------------------------------------------------------------------------------------------
+# normalisation
+# ----------------------------------------------------------------------------------------------
+_ws: dict = {}
+
+
+def _workspace(device: torch.device, key: str, numel: int, zero: bool = False) -> torch.Tensor:
+    k = (device, key)
+    t = _ws.get(k)
+    if t is None or t.numel() < numel:
+        t = torch.zeros(numel, dtype=torch.float32, device=device)
+        _ws[k] = t
+    return t
+
+
+def groupnorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, groups: int = 32, eps: float = 1e-5,
+              act: int = ACT_NONE, x2: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+              stat_sum: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """act(GroupNorm(cat(x, x2))) -> bf16 channels-last.  If `stat_sum` (B, C, 2) already holds the
+    per-channel sums (produced by a conv epilogue) the statistics pass is skipped."""
+    lib = _lib.load()
+    B, D, H, W, C1, p1 = _check_act(x, "groupnorm.x")
+    S = D * H * W
+    C2 = 0
+    if x2 is not None:
+        _, _, _, _, C2, p2 = _check_act(x2, "groupnorm.x2")
+    Ct = C1 + C2
+    if out is None:
+        out = torch.empty((B, D, H, W, Ct), dtype=torch.bfloat16, device=x.device)
+    oB, oD, oH, oW, oC, op = _check_act(out, "groupnorm.out")
+    if (oB, oD, oH, oW, oC) != (B, D, H, W, Ct):
+        raise _lib.CsError("groupnorm: bad output shape")
+    st = _stream()
+    if stat_sum is None:
+        stat = _workspace(x.device, "gn_stat", B * Ct * 2)  # kept all-zero between calls by finalize
+        check(lib.cs_groupnorm_stats(x.data_ptr(), B, S, C1, p1, stat.data_ptr(), Ct, st), "cs_groupnorm_stats")
+        if x2 is not None:
+            check(lib.cs_groupnorm_stats(x2.data_ptr(), B, S, C2, p2, stat.data_ptr() + C1 * 8, Ct, st),
+                  "cs_groupnorm_stats")
+    else:
+        stat = stat_sum
+    ss = _workspace(x.device, "gn_ss", B * Ct * 2)
+    check(lib.cs_groupnorm_finalize(stat.data_ptr(), _ptr(_f32(gamma, "gamma")), _ptr(_f32(beta, "beta")), B, Ct,
+                                    groups, S, eps, ss.data_ptr(), st), "cs_groupnorm_finalize")
+    check(lib.cs_groupnorm_apply(x.data_ptr(), B, S, C1, p1, ss.data_ptr(), Ct, out.data_ptr(), op, act, st),
+          "cs_groupnorm_apply")
+    if x2 is not None:
+        check(lib.cs_groupnorm_apply(x2.data_ptr(), B, S, C2, p2, ss.data_ptr() + C1 * 8, Ct,
+                                     out.data_ptr() + C1 * 2, op, act, st), "cs_groupnorm_apply")
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    B, D, H, W, Cc, p = _check_act(x, "layernorm.x")
+    if out is None:
+        out = torch.empty((B, D, H, W, Cc), dtype=torch.bfloat16, device=x.device)
+    check(_lib.load().cs_layernorm(x.data_ptr(), B * D * H * W, Cc, p, _f32(gamma, "gamma").data_ptr(),
+                                   _f32(beta, "beta").data_ptr(), eps, out.data_ptr(), out.stride(3), _stream()),
+          "cs_layernorm")
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# attention / pointwise
+# ----------------------------------------------------------------------------------------------
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, heads: int, head_dim: int, head_dim_padded: int,
+              scale: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """q: (B, Nq, >=heads*Dp) / k,v: (B, Nk, >=heads*Dp) bf16 row-pitched views -> (B, Nq, heads*head_dim)."""
+    for t, n in ((q, "q"), (k, "k"), (v, "v")):
+        if t.dtype != torch.bfloat16 or t.dim() != 3 or t.stride(2) != 1 or not t.is_cuda:
+            raise _lib.CsError(f"attention.{n}: expected bf16 (B, N, heads*Dp) with contiguous last dim")
+    B, Nq = q.shape[0], q.shape[1]
+    Nk = k.shape[1]
+    if q.stride(0) != Nq * q.stride(1) or k.stride(0) != Nk * k.stride(1) or v.stride() != k.stride():
+        raise _lib.CsError("attention: batch stride must equal N * row pitch; k and v must share strides")
+    if out is None:
+        out = torch.empty((B, Nq, heads * head_dim), dtype=torch.bfloat16, device=q.device)
+    check(_lib.load().cs_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, heads, Nq, Nk,
+                                   head_dim_padded, q.stride(1), k.stride(1), out.stride(1), head_dim, scale,
+                                   _stream()), "cs_attention")
+    return out
+
+
+def geglu(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    B, D, H, W, C2, p = _check_act(x, "geglu.x")
+    Ch = C2 // 2
+    if out is None:
+        out = torch.empty((B, D, H, W, Ch), dtype=torch.bfloat16, device=x.device)
+    check(_lib.load().cs_geglu(x.data_ptr(), B * D * H * W, Ch, p, out.data_ptr(), out.stride(3), _stream()),
+          "cs_geglu")
+    return out
+
+
+def upsample_nearest(x: torch.Tensor, factors: Sequence[int], out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    B, D, H, W, Cc, p = _check_act(x, "upsample.x")
+    fd, fh, fw = factors
+    if out is None:
+        out = torch.empty((B, D * fd, H * fh, W * fw, Cc), dtype=torch.bfloat16, device=x.device)
+    check(_lib.load().cs_upsample_nearest(x.data_ptr(), B, D, H, W, Cc, p, fd, fh, fw, out.data_ptr(),
+                                          out.stride(3), _stream()), "cs_upsample_nearest")
+    return out
+
+
+def im2col_small(x: torch.Tensor, batch: Optional[int] = None, kp: Optional[int] = None) -> torch.Tensor:
+    """fp32 NCDHW (few channels) -> bf16 (B, D, H, W, Kp) patch matrix for a 3x3x3 / pad 1 conv."""
+    _f32(x, "im2col_small.x")
+    Bs, Cc, D, H, W = x.shape
+    B = Bs if batch is None else batch
+    if kp is None:
+        kp = (27 * Cc + 15) // 16 * 16
+    col = torch.empty((B, D, H, W, kp), dtype=torch.bfloat16, device=x.device)
+    check(_lib.load().cs_im2col_small(x.data_ptr(), Bs, B, Cc, D, H, W, kp, col.data_ptr(), _stream()),
+          "cs_im2col_small")
+    return col
+
+
+def timestep_embedding(t: torch.Tensor, dim: int, max_period: float = 10000.0) -> torch.Tensor:
+    if t.dtype != torch.int64 or not t.is_cuda or not t.is_contiguous():
+        raise _lib.CsError("timestep_embedding: t must be a contiguous int64 CUDA tensor")
+    out = torch.empty((t.shape[0], dim), dtype=torch.float32, device=t.device)
+    check(_lib.load().cs_timestep_embedding(t.data_ptr(), t.shape[0], dim, max_period, out.data_ptr(), _stream()),
+          "cs_timestep_embedding")
+    return out
+
+
+def linear_small(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, act_in: int = ACT_NONE,
+                 act_out: int = ACT_NONE, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 (M, K) @ (N, K)^T for a handful of rows (time embedding / context projections)."""
+    if x.dtype != torch.float32 or x.dim() != 2 or x.stride(1) != 1 or not x.is_cuda:
+        raise _lib.CsError("linear_small: x must be fp32 (M, K)")
+    _f32(w, "linear_small.w")
+    M, K = x.shape
+    N = w.shape[0]
+    if w.shape[1] != K:
+        raise _lib.CsError("linear_small: weight must be (N, K)")
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=x.device)
+    check(_lib.load().cs_linear_small(x.data_ptr(), M, K, x.stride(0), w.data_ptr(), _ptr(_f32(bias, "bias")), N,
+                                      act_in, act_out, out.data_ptr(), out.stride(0), _stream()), "cs_linear_small")
+    return out
+
+
+def ddim_step(x: torch.Tensor, eps: torch.Tensor, *, guided: bool, scale: float, a_t: float, a_prev: float,
+              sigma: float, sqrt_one_minus_at: float, noise: Optional[torch.Tensor] = None,
+              want_pred_x0: bool = True) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    _f32(x, "ddim_step.x"), _f32(eps, "ddim_step.eps")
+    n = x.numel()
+    if eps.numel() != (2 * n if guided else n):
+        raise _lib.CsError("ddim_step: eps must hold [uncond; cond] (2x) when guided, else 1x")
+    x_prev = torch.empty_like(x)
+    pred = torch.empty_like(x) if want_pred_x0 else None
+    check(_lib.load().cs_ddim_step(x.data_ptr(), eps.data_ptr(), n, int(guided), scale, a_t, a_prev, sigma,
+                                   sqrt_one_minus_at, _ptr(_f32(noise, "noise")), x_prev.data_ptr(), _ptr(pred),
+                                   _stream()), "cs_ddim_step")
+    return x_prev, pred
+
+
+def q_sample(x0: torch.Tensor, noise: torch.Tensor, t: torch.Tensor, sqrt_ac: torch.Tensor,
+             sqrt_1mac: torch.Tensor) -> torch.Tensor:
+    _f32(x0, "x0"), _f32(noise, "noise"), _f32(sqrt_ac, "sqrt_ac"), _f32(sqrt_1mac, "sqrt_1mac")
+    out = torch.empty_like(x0)
+    B = x0.shape[0]
+    check(_lib.load().cs_q_sample(x0.data_ptr(), noise.data_ptr(), t.data_ptr(), sqrt_ac.data_ptr(),
+                                  sqrt_1mac.data_ptr(), x0.numel() // B, B, out.data_ptr(), _stream()), "cs_q_sample")
+    return out
+
+
+def to_channels_last(x: torch.Tensor, c_pad: Optional[int] = None) -> torch.Tensor:
+    """NCDHW fp32 -> (B, D, H, W, Cp) bf16, channels zero-padded to Cp."""
+    _f32(x, "to_channels_last.x")
+    B, Cc, D, H, W = x.shape
+    cp = Cc if c_pad is None else c_pad
+    y = torch.empty((B, D, H, W, cp), dtype=torch.bfloat16, device=x.device)
+    check(_lib.load().cs_ncdhw_to_ndhwc(x.data_ptr(), B, Cc, D * H * W, cp, y.data_ptr(), _stream()),
+          "cs_ncdhw_to_ndhwc")
+    return y
+
+
+def to_ncdhw(x: torch.Tensor, channels: Optional[int] = None) -> torch.Tensor:
+    B, D, H, W, Cc, p = _check_act(x, "to_ncdhw.x")
+    cc = Cc if channels is None else channels
+    y = torch.empty((B, cc, D, H, W), dtype=torch.float32, device=x.device)
+    check(_lib.load().cs_ndhwc_to_ncdhw(x.data_ptr(), B, cc, D * H * W, p, y.data_ptr(), _stream()),
+          "cs_ndhwc_to_ncdhw")
+    return y

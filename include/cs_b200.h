@@ -1,0 +1,128 @@
+/* cs_b200.h — C ABI of libcsb200.so, the B200 (sm_100a) kernels behind the CommonScenes
+ * shape-branch denoising hot path.
+ *
+ * The reference (ymxlzgy/commonscenes) has no FFI on this path: the seam is a set of Python classes
+ * that call torch ops.  Each entry point below therefore replaces the torch call(s)
+ * named in its comment (reference file:line); commonscenes_b200/ops.py is the ctypes binding and
+ * INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless stated otherwise; no torch types cross this boundary
+ *   - activations are channels-last bf16  [B][D][H][W][C]  (row pitch in ELEMENTS may exceed C so that
+ *     a tensor can be a channel slice of a wider buffer); boundary tensors are NCDHW fp32 as in the
+ *     reference
+ *   - every function enqueues on `stream` (a cudaStream_t), allocates nothing, never synchronises,
+ *     and is CUDA-graph capturable
+ *   - return value: 0 = ok, otherwise one of CS_ERR_*; cs_last_error() gives the message for the
+ *     calling thread.  Nothing throws across the boundary.
+ */
+#ifndef CS_B200_H
+#define CS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CS_OK 0
+#define CS_ERR_INVALID 1
+#define CS_ERR_CUDA 2
+#define CS_ERR_UNSUPPORTED 3
+#define CS_ERR_NO_DEVICE 4
+
+#define CS_OUT_BF16_NDHWC 0
+#define CS_OUT_F32_NCDHW 1
+#define CS_OUT_F32_NDHWC 2
+
+#define CS_ACT_NONE 0
+#define CS_ACT_SILU 1
+#define CS_ACT_GELU 2
+
+typedef void* cs_stream_t; /* cudaStream_t */
+
+/* ---- library state ------------------------------------------------------------------------- */
+int cs_abi_version(void);
+const char* cs_last_error(void);
+/* 0 when the current CUDA device is compute capability 10.x, CS_ERR_NO_DEVICE otherwise. */
+int cs_device_check(void);
+/* number of kernels this library has launched (the bench's `gpu_launches` evidence) */
+uint64_t cs_launch_count(void);
+void cs_reset_launch_count(void);
+
+/* ---- GEMM-class ops: tcgen05 implicit GEMM ---------------------------------------------------
+ * y = act( conv3d(cat(in1, in2), W) + bias + rowvec[b] + residual )
+ * Replaces nn.Conv3d / conv_nd (openai_model_3d.py:146,190,243,269,276-280,561,727;
+ * vqvae_modules.py:40-58,77-101,139-152,205-209,370-374), nn.Linear on token matrices
+ * (attention.py:42,62,163-170) and the `h + emb_out` / `skip_connection(x) + h` / `x + x_in`
+ * adds that follow them (openai_model_3d.py:312-314, attention.py:238-244,351).
+ * A linear layer is the kd=kh=kw=1 case on a [B][D][H][W] token grid. */
+typedef struct cs_conv3d_args {
+  const void* in1; int32_t C1; int32_t in1_pitch;   /* bf16 channels-last, C1 % 8 == 0 */
+  const void* in2; int32_t C2; int32_t in2_pitch;   /* optional second source (channel concat) */
+  int32_t B, D, H, W;                                /* INPUT spatial extent */
+  const void* weight; int32_t Cout;                  /* bf16 [Cout][kd*kh*kw][C1+C2] */
+  int32_t kd, kh, kw, sd, sh, sw;
+  int32_t pd, ph, pw, pd_back, ph_back, pw_back;     /* zero padding, front / back */
+  const float* bias;                                 /* [Cout] or NULL */
+  const float* rowvec; int32_t rowvec_pitch;         /* [B][pitch] per-sample vector or NULL */
+  const void* residual; int32_t res_pitch;           /* bf16 [B*Do*Ho*Wo][pitch] or NULL */
+  void* out; int32_t out_pitch; int32_t out_mode; int32_t act;
+  float* stat_sum; int32_t stat_pitch;               /* optional fused GroupNorm sums [B][pitch][2] */
+  int32_t bn_hint;                                   /* N tile override, 0 = auto */
+} cs_conv3d_args;
+int cs_conv3d(const cs_conv3d_args* args, cs_stream_t stream);
+
+/* ---- GroupNorm (GroupNorm32: ldm_diffusion_util.py:237-239; Normalize: attention.py:78-79,
+ *      vqvae_modules.py:13-21) --------------------------------------------------------------- */
+/* stat[b][c][0..1] += sum / sum of squares over the S voxels of sample b */
+int cs_groupnorm_stats(const void* x, int32_t B, int32_t S, int32_t C, int32_t pitch, float* stat,
+                       int32_t stat_pitch, cs_stream_t stream);
+/* (sum,sumsq) -> scale_shift[b][c] = (gamma*rstd, beta - mean*rstd*gamma); zeroes `stat` */
+int cs_groupnorm_finalize(float* stat, const float* gamma, const float* beta, int32_t B, int32_t C,
+                          int32_t groups, int32_t S, float eps, float* scale_shift, cs_stream_t stream);
+/* y = act(x * scale + shift) */
+int cs_groupnorm_apply(const void* x, int32_t B, int32_t S, int32_t C, int32_t pitch,
+                       const float* scale_shift, int32_t ss_pitch, void* y, int32_t y_pitch, int32_t act,
+                       cs_stream_t stream);
+
+/* ---- LayerNorm over the last dim (nn.LayerNorm, attention.py:229-231) ------------------------ */
+int cs_layernorm(const void* x, int64_t M, int32_t C, int32_t pitch, const float* gamma, const float* beta,
+                 float eps, void* y, int32_t y_pitch, cs_stream_t stream);
+
+/* ---- attention core: softmax(q k^T * scale) v  (attention.py:201-218; vqvae_modules.py:160-175) */
+int cs_attention(const void* q, const void* k, const void* v, void* out, int32_t B, int32_t H, int32_t Nq,
+                 int32_t Nk, int32_t Dp, int32_t q_pitch, int32_t kv_pitch, int32_t o_pitch, int32_t d_out,
+                 float scale, cs_stream_t stream);
+
+/* ---- pointwise glue -------------------------------------------------------------------------- */
+/* y[m][0:Ch] = x[m][0:Ch] * gelu_erf(x[m][Ch:2Ch])                       (attention.py:44-46) */
+int cs_geglu(const void* x, int64_t M, int32_t Ch, int32_t pitch, void* y, int32_t y_pitch, cs_stream_t stream);
+/* F.interpolate(mode="nearest") by integer factors                      (openai_model_3d.py:150-155) */
+int cs_upsample_nearest(const void* x, int32_t B, int32_t D, int32_t H, int32_t W, int32_t C, int32_t pitch,
+                        int32_t fd, int32_t fh, int32_t fw, void* y, int32_t y_pitch, cs_stream_t stream);
+/* 3x3x3/pad-1 im2col of a few-channel fp32 NCDHW tensor -> bf16 [B*D*H*W][Kp]; sample b reads
+ * source sample b % Bsrc                                               (openai_model_3d.py:561) */
+int cs_im2col_small(const float* x, int32_t Bsrc, int32_t B, int32_t C, int32_t D, int32_t H, int32_t W,
+                    int32_t Kp, void* col, cs_stream_t stream);
+/* sinusoidal timestep embedding                                         (ldm_diffusion_util.py:174-194) */
+int cs_timestep_embedding(const int64_t* t, int32_t B, int32_t dim, float max_period, float* out,
+                          cs_stream_t stream);
+/* y = act_out(act_in(x) W^T + bias), fp32, few rows                      (openai_model_3d.py:549-553,257-263) */
+int cs_linear_small(const float* x, int32_t M, int32_t K, int32_t x_pitch, const float* W, const float* bias,
+                    int32_t N, int32_t act_in, int32_t act_out, float* y, int32_t y_pitch, cs_stream_t stream);
+/* one DDIM update incl. classifier-free guidance                         (samplers/ddim.py:206-243) */
+int cs_ddim_step(const float* x, const float* eps, int64_t n, int32_t guided, float scale, float a_t,
+                 float a_prev, float sigma, float sqrt_one_minus_at, const float* noise, float* x_prev,
+                 float* pred_x0, cs_stream_t stream);
+/* x_t = sqrt(abar_t) x0 + sqrt(1-abar_t) noise                           (sdfusion_txt2shape_model.py:268-272) */
+int cs_q_sample(const float* x0, const float* noise, const int64_t* t, const float* sqrt_ac,
+                const float* sqrt_1mac, int64_t per_sample, int32_t B, float* out, cs_stream_t stream);
+/* NCDHW fp32 -> channels-last bf16 (channels zero-padded to Cp) and back */
+int cs_ncdhw_to_ndhwc(const float* x, int32_t B, int32_t C, int64_t S, int32_t Cp, void* y, cs_stream_t stream);
+int cs_ndhwc_to_ncdhw(const void* x, int32_t B, int32_t C, int64_t S, int32_t pitch, float* y, cs_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CS_B200_H */

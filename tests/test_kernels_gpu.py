@@ -1,0 +1,284 @@
+"""Per-kernel numerics on a real B200: every C-ABI entry point against a plain PyTorch fp32 reference
+of the same op (inputs pre-rounded to bf16 where the kernel consumes bf16, TF32 off).
+
+Tolerances (stated per test): GEMM-class kernels accumulate in fp32 and round the result to bf16 once,
+so |err| <= 2^-8 * |ref| + small absolute slack; fp32 kernels are compared at 1e-5.
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from commonscenes_b200 import _lib, ops as o
+    _lib.require_device()
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return o
+
+
+def _bf(x):
+    return x.to(torch.bfloat16)
+
+
+def _cl(x):  # NCDHW fp32 -> channels-last bf16
+    return _bf(x.permute(0, 2, 3, 4, 1).contiguous())
+
+
+def _ncdhw(x):  # channels-last bf16 -> NCDHW fp32
+    return x.float().permute(0, 4, 1, 2, 3).contiguous()
+
+
+def _report(name, got, ref, rtol, atol):
+    err = (got - ref).abs()
+    bound = atol + rtol * ref.abs()
+    bad = (err > bound)
+    rel_l2 = (got - ref).norm() / ref.norm().clamp_min(1e-12)
+    msg = (f"{name}: max_abs_err={err.max().item():.4e} rel_l2={rel_l2.item():.4e} "
+           f"violations={int(bad.sum())}/{bad.numel()} ref_absmax={ref.abs().max().item():.3e}")
+    print(msg)
+    assert not bad.any(), msg
+
+
+CONV_CASES = [
+    # name, B, Cin, Cout, (D,H,W), ksize, stride, pad
+    ("res224_16^3", 2, 224, 224, (16, 16, 16), 3, (1, 1, 1), 1),
+    ("res448_16x8x8", 2, 448, 448, (16, 8, 8), 3, (1, 1, 1), 1),
+    ("res672_16x4x4", 4, 672, 672, (16, 4, 4), 3, (1, 1, 1), 1),
+    ("in4_224to448", 2, 224, 448, (16, 8, 8), 3, (1, 1, 1), 1),
+    ("lin448to3584", 2, 448, 3584, (16, 8, 8), 1, (1, 1, 1), 0),
+    ("lin1792to448", 2, 1792, 448, (16, 8, 8), 1, (1, 1, 1), 0),
+    ("vq64_32^3", 1, 64, 128, (32, 32, 32), 3, (1, 1, 1), 1),
+    ("small_c32", 2, 32, 32, (16, 4, 4), 3, (1, 1, 1), 1),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
+def test_conv3d_matches_torch(ops, case):
+    name, B, Cin, Cout, (D, H, W), k, stride, pad = case
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    x = torch.randn(B, Cin, D, H, W, device="cuda", generator=g)
+    w = torch.randn(Cout, Cin, k, k, k, device="cuda", generator=g) / math.sqrt(Cin * k ** 3)
+    b = torch.randn(Cout, device="cuda", generator=g)
+    xb, wb = _bf(x).float(), _bf(w).float()
+    ref = F.conv3d(xb, wb, b, stride=stride, padding=pad)
+    got = ops.conv3d(_cl(x), ops.pack_conv_weight(w), ksize=(k, k, k), stride=stride, pad=(pad,) * 3, bias=b)
+    torch.cuda.synchronize()
+    _report(name, _ncdhw(got), ref, rtol=2 ** -7, atol=2e-3)
+
+
+def test_conv3d_epilogue_rowvec_residual_stats(ops):
+    B, C, D, H, W = 2, 224, 16, 8, 8
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = torch.randn(B, C, D, H, W, device="cuda", generator=g)
+    w = torch.randn(C, C, 3, 3, 3, device="cuda", generator=g) / math.sqrt(C * 27)
+    b = torch.randn(C, device="cuda", generator=g)
+    rv = torch.randn(B, C, device="cuda", generator=g)
+    res = torch.randn(B, C, D, H, W, device="cuda", generator=g)
+    ref = F.conv3d(_bf(x).float(), _bf(w).float(), b, padding=1) + rv[:, :, None, None, None] + _bf(res).float()
+    stat = torch.zeros(B, C, 2, device="cuda")
+    got = ops.conv3d(_cl(x), ops.pack_conv_weight(w), bias=b, rowvec=rv, residual=_cl(res), stat_sum=stat)
+    torch.cuda.synchronize()
+    _report("epilogue", _ncdhw(got), ref, rtol=2 ** -7, atol=4e-3)
+    s_ref = torch.stack([ref.sum(dim=(2, 3, 4)), (ref * ref).sum(dim=(2, 3, 4))], dim=-1)
+    _report("fused_stats", stat, s_ref, rtol=1e-3, atol=0.5)
+
+
+def test_conv3d_two_sources_equals_concat(ops):
+    B, C1, C2, Cout, D, H, W = 2, 448, 224, 224, 16, 16, 16
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x1 = torch.randn(B, C1, D, H, W, device="cuda", generator=g)
+    x2 = torch.randn(B, C2, D, H, W, device="cuda", generator=g)
+    w = torch.randn(Cout, C1 + C2, 3, 3, 3, device="cuda", generator=g) / math.sqrt((C1 + C2) * 27)
+    ref = F.conv3d(_bf(torch.cat([x1, x2], 1)).float(), _bf(w).float(), None, padding=1)
+    got = ops.conv3d(_cl(x1), ops.pack_conv_weight(w), x2=_cl(x2))
+    torch.cuda.synchronize()
+    _report("two_source", _ncdhw(got), ref, rtol=2 ** -7, atol=2e-3)
+
+
+@pytest.mark.parametrize("shape", [(224, (16, 16, 16)), (448, (16, 8, 8))], ids=["224", "448"])
+def test_conv3d_stride_1_2_2(ops, shape):
+    C, (D, H, W) = shape
+    B = 2
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(B, C, D, H, W, device="cuda", generator=g)
+    w = torch.randn(C, C, 3, 3, 3, device="cuda", generator=g) / math.sqrt(C * 27)
+    b = torch.randn(C, device="cuda", generator=g)
+    ref = F.conv3d(_bf(x).float(), _bf(w).float(), b, stride=(1, 2, 2), padding=1)
+    got = ops.conv3d(_cl(x), ops.pack_conv_weight(w), stride=(1, 2, 2), bias=b)
+    torch.cuda.synchronize()
+    _report("stride122", _ncdhw(got), ref, rtol=2 ** -7, atol=2e-3)
+
+
+def test_conv3d_stride2_asymmetric_pad(ops):
+    # VQ-VAE Downsample: pad (0,1) per dim then 3x3x3 stride 2 (vqvae_modules.py:54-58)
+    B, C, R = 1, 64, 32
+    g = torch.Generator(device="cuda").manual_seed(6)
+    x = torch.randn(B, C, R, R, R, device="cuda", generator=g)
+    w = torch.randn(C, C, 3, 3, 3, device="cuda", generator=g) / math.sqrt(C * 27)
+    ref = F.conv3d(F.pad(_bf(x).float(), (0, 1, 0, 1, 0, 1)), _bf(w).float(), None, stride=2)
+    got = ops.conv3d(_cl(x), ops.pack_conv_weight(w), stride=(2, 2, 2), pad=(0, 0, 0), pad_back=(1, 1, 1))
+    torch.cuda.synchronize()
+    _report("stride2_asym", _ncdhw(got), ref, rtol=2 ** -7, atol=2e-3)
+
+
+def test_conv3d_head_small_cout_ncdhw_f32(ops):
+    B, C, D, H, W = 2, 224, 16, 16, 16
+    g = torch.Generator(device="cuda").manual_seed(8)
+    x = torch.randn(B, C, D, H, W, device="cuda", generator=g)
+    w = torch.randn(3, C, 3, 3, 3, device="cuda", generator=g) / math.sqrt(C * 27)
+    b = torch.randn(3, device="cuda", generator=g)
+    ref = F.conv3d(_bf(x).float(), _bf(w).float(), b, padding=1)
+    from commonscenes_b200._lib import OUT_F32_NCDHW
+    got = ops.conv3d(_cl(x), ops.pack_conv_weight(w), bias=b, out_mode=OUT_F32_NCDHW)
+    torch.cuda.synchronize()
+    _report("head", got, ref, rtol=1e-4, atol=1e-4)
+
+
+def test_stem_im2col_gemm(ops):
+    B, D = 4, 16
+    g = torch.Generator(device="cuda").manual_seed(9)
+    x = torch.randn(2, 3, D, D, D, device="cuda", generator=g)
+    w = torch.randn(224, 3, 3, 3, 3, device="cuda", generator=g) / math.sqrt(81)
+    b = torch.randn(224, device="cuda", generator=g)
+    col = ops.im2col_small(x, batch=B)
+    kp = col.shape[-1]
+    wp = torch.zeros(224, 1, kp, device="cuda")
+    wp[:, 0, :81] = w.permute(0, 2, 3, 4, 1).reshape(224, 81)  # (tap, c) order
+    got = ops.linear_tokens(col, wp.to(torch.bfloat16), bias=b)
+    torch.cuda.synchronize()
+    ref = F.conv3d(_bf(torch.cat([x, x])).float(), _bf(w).float(), b, padding=1)
+    _report("stem", _ncdhw(got), ref, rtol=2 ** -7, atol=2e-3)
+
+
+@pytest.mark.parametrize("C,eps,act", [(224, 1e-5, "silu"), (672, 1e-6, "none"), (64, 1e-6, "gelu")])
+def test_groupnorm(ops, C, eps, act):
+    B, D, H, W = 3, 16, 8, 8
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn(B, C, D, H, W, device="cuda", generator=g) * 1.7 + 0.3
+    ga = torch.randn(C, device="cuda", generator=g)
+    be = torch.randn(C, device="cuda", generator=g)
+    ref = F.group_norm(_bf(x).float(), 32, ga, be, eps)
+    ref = {"silu": F.silu, "gelu": F.gelu, "none": lambda t: t}[act](ref)
+    code = {"none": ops.ACT_NONE, "silu": ops.ACT_SILU, "gelu": ops.ACT_GELU}[act]
+    got = ops.groupnorm(_cl(x), ga, be, eps=eps, act=code)
+    torch.cuda.synchronize()
+    _report(f"groupnorm{C}", _ncdhw(got), ref, rtol=2 ** -7, atol=2e-3)
+
+
+def test_groupnorm_two_sources(ops):
+    B, C1, C2, D, H, W = 2, 448, 224, 16, 8, 8
+    g = torch.Generator(device="cuda").manual_seed(4)
+    x1 = torch.randn(B, C1, D, H, W, device="cuda", generator=g)
+    x2 = torch.randn(B, C2, D, H, W, device="cuda", generator=g) * 2 + 1
+    ga = torch.randn(C1 + C2, device="cuda", generator=g)
+    be = torch.randn(C1 + C2, device="cuda", generator=g)
+    ref = F.silu(F.group_norm(_bf(torch.cat([x1, x2], 1)).float(), 32, ga, be, 1e-5))
+    got = ops.groupnorm(_cl(x1), ga, be, act=ops.ACT_SILU, x2=_cl(x2))
+    torch.cuda.synchronize()
+    _report("groupnorm_cat", _ncdhw(got), ref, rtol=2 ** -7, atol=2e-3)
+
+
+@pytest.mark.parametrize("C", [448, 672])
+def test_layernorm(ops, C):
+    g = torch.Generator(device="cuda").manual_seed(2)
+    x = torch.randn(2, 16, 4, 4, C, device="cuda", generator=g) * 2 + 0.5
+    ga = torch.randn(C, device="cuda", generator=g)
+    be = torch.randn(C, device="cuda", generator=g)
+    ref = F.layer_norm(_bf(x).float(), (C,), ga, be, 1e-5)
+    got = ops.layernorm(_bf(x), ga, be)
+    torch.cuda.synchronize()
+    _report(f"layernorm{C}", got.float(), ref, rtol=2 ** -7, atol=2e-3)
+
+
+@pytest.mark.parametrize("N,heads,d,dp", [(1024, 8, 56, 64), (256, 8, 84, 96), (4096, 1, 256, 256), (256, 8, 4, 32)],
+                         ids=["n1024d56", "n256d84", "vq4096d256", "tiny"])
+def test_attention(ops, N, heads, d, dp):
+    B = 2
+    g = torch.Generator(device="cuda").manual_seed(1)
+    qkv = torch.zeros(B, N, 3 * heads * dp, device="cuda")
+    for i in range(3):
+        for h in range(heads):
+            qkv[:, :, (i * heads + h) * dp:(i * heads + h) * dp + d] = torch.randn(B, N, d, device="cuda", generator=g)
+    qkv = _bf(qkv)
+    q, k, v = (qkv[:, :, i * heads * dp:(i + 1) * heads * dp] for i in range(3))
+    scale = d ** -0.5
+    got = ops.attention(q, k, v, heads=heads, head_dim=d, head_dim_padded=dp, scale=scale)
+    torch.cuda.synchronize()
+
+    def split(t):
+        return t.float().reshape(B, N, heads, dp)[..., :d].permute(0, 2, 1, 3)
+    qf, kf, vf = split(q), split(k), split(v)
+    attn = torch.softmax(qf @ kf.transpose(-1, -2) * scale, dim=-1)
+    ref = (attn @ vf).permute(0, 2, 1, 3).reshape(B, N, heads * d)
+    _report("attention", got.float(), ref, rtol=2e-2, atol=1e-2)
+
+
+def test_attention_cross_short_context(ops):
+    # generic cross-attention with a ragged (non multiple of 64) context length
+    B, Nq, Nk, heads, d, dp = 2, 256, 77, 8, 56, 64
+    g = torch.Generator(device="cuda").manual_seed(12)
+    q = _bf(torch.randn(B, Nq, heads * dp, device="cuda", generator=g))
+    k = _bf(torch.randn(B, Nk, heads * dp, device="cuda", generator=g))
+    v = _bf(torch.randn(B, Nk, heads * dp, device="cuda", generator=g))
+    got = ops.attention(q, k, v, heads=heads, head_dim=d, head_dim_padded=dp, scale=d ** -0.5)
+    torch.cuda.synchronize()
+    qf = q.float().reshape(B, Nq, heads, dp).permute(0, 2, 1, 3)
+    kf = k.float().reshape(B, Nk, heads, dp).permute(0, 2, 1, 3)
+    vf = v.float().reshape(B, Nk, heads, dp).permute(0, 2, 1, 3)
+    ref = (torch.softmax(qf @ kf.transpose(-1, -2) * d ** -0.5, -1) @ vf)[..., :d].permute(0, 2, 1, 3).reshape(B, Nq, heads * d)
+    _report("cross_attention", got.float(), ref, rtol=2e-2, atol=1e-2)
+
+
+def test_geglu_upsample_layout(ops):
+    g = torch.Generator(device="cuda").manual_seed(13)
+    x = _bf(torch.randn(2, 16, 4, 4, 2 * 1792, device="cuda", generator=g))
+    a, gate = x.float().chunk(2, dim=-1)
+    _report("geglu", ops.geglu(x).float(), a * F.gelu(gate), rtol=2 ** -7, atol=1e-3)
+    y = _bf(torch.randn(2, 16, 4, 4, 672, device="cuda", generator=g))
+    up = ops.upsample_nearest(y, (1, 2, 2))
+    ref = F.interpolate(_ncdhw(y), (16, 8, 8), mode="nearest")
+    assert torch.equal(_ncdhw(up), ref)
+    z = torch.randn(3, 3, 16, 16, 16, device="cuda", generator=g)
+    cl = ops.to_channels_last(z, 8)
+    assert torch.equal(cl[..., :3].float(), _bf(z).float().permute(0, 2, 3, 4, 1))
+    assert float(cl[..., 3:].abs().max()) == 0.0
+    assert torch.equal(ops.to_ncdhw(cl, 3), _bf(z).float())
+
+
+def test_timestep_embedding_and_small_linear(ops):
+    t = torch.tensor([0, 1, 11, 500, 991, 999], device="cuda", dtype=torch.int64)
+    dim, half = 224, 112
+    freqs = torch.exp(-math.log(10000) * torch.arange(0, half, dtype=torch.float32, device="cuda") / half)
+    args = t[:, None].float() * freqs[None]
+    ref = torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
+    _report("timestep_embedding", ops.timestep_embedding(t, dim), ref, rtol=0, atol=2e-4)
+    g = torch.Generator(device="cuda").manual_seed(14)
+    x = torch.randn(13, 896, device="cuda", generator=g)
+    w = torch.randn(672, 896, device="cuda", generator=g) / 30
+    b = torch.randn(672, device="cuda", generator=g)
+    got = ops.linear_small(x, w, b, act_in=ops.ACT_SILU)
+    _report("linear_small", got, F.linear(F.silu(x), w, b), rtol=1e-4, atol=1e-4)
+
+
+def test_ddim_step_and_q_sample(ops):
+    g = torch.Generator(device="cuda").manual_seed(15)
+    x = torch.randn(4, 3, 16, 16, 16, device="cuda", generator=g)
+    eps = torch.randn(8, 3, 16, 16, 16, device="cuda", generator=g)
+    a_t, a_prev, sigma, s1m = 0.37, 0.41, 0.0, math.sqrt(1 - 0.37)
+    e = eps[:4] + 3.0 * (eps[4:] - eps[:4])
+    pred = (x - s1m * e) / math.sqrt(a_t)
+    ref = math.sqrt(a_prev) * pred + math.sqrt(1 - a_prev - sigma ** 2) * e
+    xp, p0 = ops.ddim_step(x, eps, guided=True, scale=3.0, a_t=a_t, a_prev=a_prev, sigma=sigma, sqrt_one_minus_at=s1m)
+    _report("ddim_x_prev", xp, ref, rtol=1e-5, atol=1e-5)
+    _report("ddim_pred_x0", p0, pred, rtol=1e-5, atol=1e-5)
+    ac = torch.linspace(0.99, 0.01, 1000, device="cuda")
+    t = torch.tensor([0, 10, 500, 999], device="cuda")
+    noise = torch.randn_like(x)
+    ref = ac.sqrt()[t].view(-1, 1, 1, 1, 1) * x + (1 - ac).sqrt()[t].view(-1, 1, 1, 1, 1) * noise
+    _report("q_sample", ops.q_sample(x, noise, t, ac.sqrt().contiguous(), (1 - ac).sqrt().contiguous()), ref, 1e-6, 1e-6)
