@@ -349,7 +349,8 @@ int igemm_launch(const IgemmArgs& a, cudaStream_t stream) {
   p.n_tiles = (a.Cout + bn - 1) / bn;
   p.m_tiles = (p.B / p.bb) * (p.Do / p.bd) * (p.Ho / p.bh) * (p.Wo / p.bw);
   const int stage_bytes = kABytes + bn * 128;
-  const int smem_budget = 227 * 1024 - 2048;
+  // 227 KB per CTA minus the kernel's static shared memory (barriers) and the 1 KB alignment slack
+  const int smem_budget = 227 * 1024 - 4096;
   int stages = smem_budget / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return set_error(CS_ERR_INVALID, "igemm: tile too large for shared memory");
@@ -390,12 +391,12 @@ int igemm_launch(const IgemmArgs& a, cudaStream_t stream) {
     if (rc) return rc;
   }
 
-  static bool attr_set = false;
+  static int attr_smem = 0;
   const int smem_bytes = stages * stage_bytes + 1024;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (smem_bytes > attr_smem) {
+    cudaError_t e = cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return set_cuda_error(e, "igemm: cudaFuncSetAttribute");
-    attr_set = true;
+    attr_smem = smem_bytes;
   }
   const int total = p.m_tiles * p.n_tiles;
   const int grid = total < num_sms() ? total : num_sms();
