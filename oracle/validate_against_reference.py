@@ -1,0 +1,198 @@
+"""Pin the oracle against the reference's own modules (run in the BUILD container only: it imports
+/root/reference, which does not exist on the GPU box).
+
+    python oracle/validate_against_reference.py [--full]
+
+For each sub-system it (1) checks that the oracle's state-dict key/shape inventory equals the reference
+module's state_dict() exactly — that inventory is the drop-in contract of SURVEY.md §8b — and (2) runs the
+reference module and the oracle on identical seeded weights/inputs and reports the max abs difference
+(expected ~1e-6: same fp32 torch ops, possibly different association).  --full adds the full-size UNet.
+Exit code 0 iff everything is within 2e-5 relative.
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+import types
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.environ.get("CS_REFERENCE", "/root/reference")
+sys.path.insert(0, ROOT)
+
+
+def import_reference():
+    """Make `model.*` of the reference importable (one shim: a stub omegaconf.listconfig)."""
+    if not os.path.isdir(REF):
+        raise SystemExit(f"{REF} not found: this script only runs where the reference is mounted")
+    if "omegaconf" not in sys.modules:
+        oc = types.ModuleType("omegaconf")
+        lc = types.ModuleType("omegaconf.listconfig")
+
+        class ListConfig(list):
+            pass
+        lc.ListConfig = ListConfig
+        oc.listconfig = lc
+        sys.modules["omegaconf"] = oc
+        sys.modules["omegaconf.listconfig"] = lc
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    from model.networks.diffusion_networks.network import DiffusionUNet
+    from model.networks.vqvae_networks.network import VQVAE
+    from model import graph as ref_graph
+    return DiffusionUNet, VQVAE, ref_graph
+
+
+def ref_unet(cfg, seed):
+    from oracle import weights
+    DiffusionUNet, _, _ = import_reference()
+    params = dict(cfg)
+    params["attention_resolutions"] = list(cfg["attention_resolutions"])
+    params["channel_mult"] = list(cfg["channel_mult"])
+    params.update(use_spatial_transformer=True, use_checkpoint=False, legacy=False)
+    m = DiffusionUNet(params, conditioning_key="crossattn").eval()
+    weights.fill_module_(m, seed)
+    return m
+
+
+def ref_vqvae(cfg, seed):
+    from oracle import weights
+    _, VQVAE, _ = import_reference()
+    dd = dict(double_z=False, z_channels=cfg["z_channels"], resolution=cfg["resolution"], in_channels=cfg["in_channels"],
+              out_ch=cfg["out_ch"], ch=cfg["ch"], ch_mult=list(cfg["ch_mult"]), num_res_blocks=cfg["num_res_blocks"],
+              attn_resolutions=[], dropout=0.0)
+    m = VQVAE(dd, cfg["n_embed"], cfg["embed_dim"]).eval()
+    weights.fill_module_(m, seed)
+    return m
+
+
+class RefE2(torch.nn.Module):
+    """The encoder_2 slice of Sg2ScVAEModel (VAEGAN_V2FULL.py:69-75, 128-155, 220-242) built from the
+    reference's own GraphTripleConvNet2 / make_mlp (the full class needs omegaconf/pytorch3d to import)."""
+
+    def __init__(self, cfg):
+        super().__init__()
+        _, _, g = import_reference()
+        e, add = cfg["embedding_dim"], cfg["add_dim"]
+        self.obj_embeddings_dc = torch.nn.Embedding(cfg["num_objs"] + 1, e)
+        self.pred_embeddings_dc = torch.nn.Embedding(cfg["num_preds"], 2 * e)
+        self.gconv_net_ec_rel = g.GraphTripleConvNet2(input_dim_obj=2 * e + add, input_dim_pred=2 * e + add, hidden_dim=4 * e,
+                                                      pooling="avg", num_layers=cfg["num_layers"], mlp_normalization="batch",
+                                                      residual=True)
+        self.rel_mlp = g.make_mlp([2 * e + add, cfg["rel_hidden"], cfg["rel_out"]], batch_norm="batch", norelu=True)
+
+    def forward(self, z, objs, triples, text_feat, rel_feat):
+        s, p, o = [x.squeeze(1) for x in triples.chunk(3, dim=1)]
+        edges = torch.stack([s, o], dim=1)
+        obj_vecs_ = torch.cat([text_feat, self.obj_embeddings_dc(objs)], dim=1)
+        pred_vecs_ = torch.cat([rel_feat, self.pred_embeddings_dc(p)], dim=1)
+        rel_vecs_ = torch.cat([obj_vecs_, z], dim=1)
+        rel2, _ = self.gconv_net_ec_rel(rel_vecs_, pred_vecs_, edges)
+        return self.rel_mlp(rel_vecs_).unsqueeze(1), self.rel_mlp(rel2).unsqueeze(1)
+
+
+def synth_graph(cfg, n_obj, n_tri, seed):
+    g = torch.Generator().manual_seed(seed)
+    objs = torch.randint(1, cfg["num_objs"], (n_obj,), generator=g)
+    s = torch.randint(0, n_obj, (n_tri,), generator=g)
+    o = (s + 1 + torch.randint(0, n_obj - 1, (n_tri,), generator=g)) % n_obj
+    p = torch.randint(1, cfg["num_preds"], (n_tri,), generator=g)
+    triples = torch.stack([s, p, o], dim=1)
+    text = torch.randn(n_obj, cfg["add_dim"], generator=g)
+    rel = torch.randn(n_tri, cfg["add_dim"], generator=g)
+    z = torch.randn(n_obj, cfg["embedding_dim"], generator=g)
+    return z, objs, triples, text, rel
+
+
+def _cmp(name, a, b, tol=2e-5):
+    err = (a - b).abs().max().item()
+    scale = b.abs().max().item()
+    ok = err <= tol * max(scale, 1.0)
+    print(f"{'ok ' if ok else 'BAD'} {name}: max|oracle-ref|={err:.3e} (ref absmax {scale:.3e})")
+    return ok
+
+
+def _keys(name, shapes, module):
+    ref = {k: tuple(v.shape) for k, v in module.state_dict().items()}
+    ok = ref == dict(shapes)
+    if not ok:
+        missing = sorted(set(ref) - set(shapes))[:5]
+        extra = sorted(set(shapes) - set(ref))[:5]
+        diff = [k for k in ref if k in shapes and ref[k] != tuple(shapes[k])][:5]
+        print(f"BAD {name} keys: missing {missing} extra {extra} shape-mismatch {diff}")
+    else:
+        print(f"ok  {name}: {len(ref)} state-dict keys/shapes identical to the reference")
+    return ok
+
+
+@torch.no_grad()
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--full", action="store_true", help="also run the full-size UNet / VQ-VAE (slow)")
+    args = ap.parse_args()
+    torch.manual_seed(0)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    from oracle import denoiser as D, graph as G, vqvae as V, weights as Wt
+    ok = True
+
+    for tag, cfg in [("tiny", D.UNET_TINY)] + ([("full", D.UNET_FULL)] if args.full else []):
+        m = ref_unet(cfg, seed=1)
+        shapes = D.unet_param_shapes(cfg)
+        ok &= _keys(f"unet[{tag}]", shapes, m)
+        sd = Wt.synth_state_dict(shapes, seed=1)
+        r = cfg["image_size"]
+        g = torch.Generator().manual_seed(2)
+        x = torch.randn(2, cfg["in_channels"], r, r, r, generator=g)
+        t = torch.tensor([500, 37])
+        ctx = torch.randn(2, 1, cfg["context_dim"], generator=g)
+        ok &= _cmp(f"unet_forward[{tag}]", D.unet_forward(sd, cfg, x, t, ctx), m(x, t, c_crossattn=[ctx]))
+        if tag == "tiny":
+            sys.path.insert(0, REF)
+            from model.networks.diffusion_networks import ldm_diffusion_util as U
+            sched = D.register_schedule(**D.DIFFUSION)
+            betas = U.make_beta_schedule("linear", 1000, linear_start=0.00085, linear_end=0.012)
+            ok &= _cmp("betas", sched["betas"], torch.tensor(betas, dtype=torch.float32), 0)
+            dd = D.ddim_schedule(sched, 100)
+            ts = U.make_ddim_timesteps("uniform", 100, 1000, verbose=False)
+            sig, al, alp = U.make_ddim_sampling_parameters(sched["alphas_cumprod"], ts, 0.0, verbose=False)
+            ok &= bool((ts == dd["timesteps"]).all())
+            ok &= _cmp("ddim_alphas", torch.tensor(dd["alphas"]), torch.as_tensor(al), 0)
+            ok &= _cmp("ddim_alphas_prev", torch.tensor(dd["alphas_prev"]), torch.as_tensor(alp).float(), 0)
+            ok &= _cmp("timestep_embedding", D.timestep_embedding(t, 224), U.timestep_embedding(t, 224), 0)
+
+    for tag, cfg in [("tiny", V.VQ_TINY)] + ([("full", V.VQ_FULL)] if args.full else []):
+        m = ref_vqvae(cfg, seed=3)
+        shapes = V.vq_param_shapes(cfg)
+        ok &= _keys(f"vqvae[{tag}]", shapes, m)
+        sd = Wt.synth_state_dict(shapes, seed=3)
+        g = torch.Generator().manual_seed(4)
+        r = cfg["resolution"]
+        x = (torch.randn(1, 1, r, r, r, generator=g) * 0.1).clamp(-0.2, 0.2)
+        z_ref = m(x, forward_no_quant=True, encode_only=True)
+        z = V.encode_no_quant(sd, cfg, x)
+        ok &= _cmp(f"vq_encode_no_quant[{tag}]", z, z_ref)
+        ok &= _cmp(f"vq_decode_no_quant[{tag}]", V.decode_no_quant(sd, cfg, z_ref), m.decode_no_quant(z_ref))
+        zq_ref, _, (_, _, idx_ref) = m.quantize(z_ref, is_voxel=True)
+        zq, idx = V.quantize(sd, z_ref)
+        ok &= bool((idx == idx_ref).all()) and _cmp(f"vq_quantize[{tag}]", zq, zq_ref, 0)
+
+    for tag, cfg in [("tiny", G.GCN_TINY), ("full", G.GCN_FULL)]:
+        m = RefE2(cfg)
+        shapes = G.gcn_param_shapes(cfg)
+        ok &= _keys(f"encoder_2[{tag}]", shapes, m)
+        Wt.fill_module_(m, seed=5)
+        sd = Wt.synth_state_dict(shapes, seed=5)
+        inp = synth_graph(cfg, 9, 20, seed=6)
+        for training in (False, True):
+            m.train(training)
+            uc_ref, c_ref = m(*inp)
+            uc, c = G.encoder_2(sd, cfg, *inp, training=training)
+            ok &= _cmp(f"encoder_2.c[{tag},train={training}]", c, c_ref) and _cmp(f"encoder_2.uc[{tag},train={training}]", uc, uc_ref)
+    print("ORACLE PINNED" if ok else "ORACLE MISMATCH")
+    return 0 if ok else 1
+
+
+if __name__ == "__main__":
+    raise SystemExit(main())

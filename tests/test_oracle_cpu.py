@@ -1,0 +1,112 @@
+"""CPU suite, part 1: the oracle against the golden fixtures that the REFERENCE's own modules produced
+(tests/golden/make_golden.py).  fp32 CPU torch on both sides -> tolerance 2e-5 relative to the output range
+(differences come only from thread-count dependent reduction order)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import denoiser as D, graph as G, vqvae as V, weights as Wt
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _load(name):
+    return np.load(os.path.join(GOLD, name))
+
+
+def _close(got, ref, tol=2e-5):
+    got, ref = torch.as_tensor(got), torch.as_tensor(ref)
+    err = (got - ref).abs().max().item()
+    assert err <= tol * max(1.0, ref.abs().max().item()), f"max err {err}"
+
+
+@pytest.mark.parametrize("tag,cfg", [("tiny", D.UNET_TINY), ("full", D.UNET_FULL)])
+def test_unet_forward_matches_reference_golden(tag, cfg):
+    g = _load(f"unet_{tag}.npz")
+    sd = Wt.synth_state_dict(D.unet_param_shapes(cfg), int(g["weight_seed"]))
+    with torch.no_grad():
+        eps = D.unet_forward(sd, cfg, torch.tensor(g["x"]), torch.tensor(g["t"]), torch.tensor(g["ctx"]))
+    _close(eps, g["eps"])
+
+
+def test_unet_inventory_counts():
+    shapes = D.unet_param_shapes(D.UNET_FULL)
+    assert len(shapes) == 496                                            # SURVEY.md §8b [probe]
+    assert sum(int(np.prod(s)) for s in shapes.values()) == 413_540_739  # SURVEY.md §3a [probe]
+    assert sum(int(np.prod(s)) for s in V.vq_param_shapes(V.VQ_FULL).values()) == 26_349_788
+
+
+def test_schedule_known_values():
+    s = D.register_schedule(**D.DIFFUSION)
+    assert abs(float(s["betas"][0]) - 8.5e-4) < 1e-9 and abs(float(s["betas"][-1]) - 1.2e-2) < 1e-8
+    assert abs(float(s["alphas_cumprod"][-1]) - 0.0046601) < 1e-6       # SURVEY.md §8 a12 [probe]
+    dd = D.ddim_schedule(s, 100)
+    assert dd["timesteps"][0] == 1 and dd["timesteps"][-1] == 991 and len(dd["timesteps"]) == 100
+    assert float(dd["alphas_prev"][0]) == float(s["alphas_cumprod"][0])  # ldm_diffusion_util.py:88
+    with pytest.raises(IndexError):                                      # S=1000 overruns the table
+        D.ddim_schedule(s, 1000)
+
+
+def test_ddim_guided_steps_match_reference_sampler():
+    g = _load("ddim_tiny.npz")
+    cfg = D.UNET_TINY
+    sd = Wt.synth_state_dict(D.unet_param_shapes(cfg), int(g["weight_seed"]))
+    sched = D.register_schedule(**D.DIFFUSION)
+    dd = D.ddim_schedule(sched, 100)
+    assert (dd["timesteps"] == g["ddim_timesteps"]).all()
+    np.testing.assert_array_equal(dd["alphas"], g["ddim_alphas"])
+    with torch.no_grad():
+        x, trace = D.ddim_sample(sd, cfg, sched, torch.tensor(g["c"]), torch.tensor(g["uc"]), torch.tensor(g["x_T"]),
+                                 S=100, scale=3.0, max_steps=4)
+    for i, (xp, p0, _) in enumerate(trace):
+        _close(xp, g["x_steps"][i], 5e-5)
+        _close(p0, g["pred_x0_steps"][i], 5e-5)
+
+
+def test_p_losses_properties():
+    cfg = D.UNET_TINY
+    sd = Wt.synth_state_dict(D.unet_param_shapes(cfg), 11)
+    sched = D.register_schedule(**D.DIFFUSION)
+    g = torch.Generator().manual_seed(0)
+    x0 = torch.randn(2, 3, 8, 8, 8, generator=g)
+    noise = torch.randn(2, 3, 8, 8, 8, generator=g)
+    ctx = torch.randn(2, 1, 64, generator=g)
+    t = torch.tensor([10, 900])
+    with torch.no_grad():
+        x_noisy, target, loss, ld = D.p_losses(sd, cfg, sched, x0, ctx, t, noise)
+        eps = D.unet_forward(sd, cfg, x_noisy, t, ctx)
+    assert torch.equal(target, noise)
+    assert abs(float(loss) - float(((eps - noise) ** 2).mean())) < 1e-6
+    assert set(ld) == {"loss_simple", "loss_vlb", "loss_total"}          # sdfusion_txt2shape_model.py:329-343
+
+
+@pytest.mark.parametrize("tag,cfg", [("tiny", V.VQ_TINY), ("full", V.VQ_FULL)])
+def test_vqvae_matches_reference_golden(tag, cfg):
+    g = _load(f"vqvae_{tag}.npz")
+    sd = Wt.synth_state_dict(V.vq_param_shapes(cfg), int(g["weight_seed"]))
+    gen = torch.Generator().manual_seed(int(g["input_seed"]))
+    r = cfg["resolution"]
+    x = (torch.randn(1, 1, r, r, r, generator=gen) * 0.1).clamp(-0.2, 0.2)
+    with torch.no_grad():
+        z = V.encode_no_quant(sd, cfg, x)
+        _close(z, g["z"], 5e-5)
+        zq, idx = V.quantize(sd, torch.tensor(g["z"]))
+        assert (idx.numpy() == g["idx"]).all()
+        dec = V.decode_no_quant(sd, cfg, torch.tensor(g["z"]))
+    sub = dec[:, :, ::4, ::4, ::4] if tag == "full" else dec
+    _close(sub, g["dec_sub"], 5e-5)
+    assert abs(float(dec.double().abs().sum()) - float(g["dec_abs_sum"])) <= 1e-4 * float(g["dec_abs_sum"])
+
+
+@pytest.mark.parametrize("tag,cfg", [("tiny", G.GCN_TINY), ("full", G.GCN_FULL)])
+def test_encoder2_matches_reference_golden(tag, cfg):
+    g = _load(f"gcn_{tag}.npz")
+    sd = Wt.synth_state_dict(G.gcn_param_shapes(cfg), int(g["weight_seed"]))
+    args = [torch.tensor(g[k]) for k in ("z", "objs", "triples", "text", "rel")]
+    for mode in ("eval", "train"):
+        with torch.no_grad():
+            uc, c = G.encoder_2(sd, cfg, *args, training=(mode == "train"))
+        _close(c, g[f"c_{mode}"], 5e-5)
+        _close(uc, g[f"uc_{mode}"], 5e-5)
