@@ -10,7 +10,8 @@ enum : int { CS_ACT_NONE = 0, CS_ACT_SILU = 1, CS_ACT_GELU = 2 };
 struct IgemmParams {
   // output grid (voxels) and the 128-voxel tile box over it
   int B, Do, Ho, Wo;
-  int bb, bd, bh, bw;  // bb*bd*bh*bw == 128
+  int bb, bd, bh, bw;  // bb*bd*bh*bw == rows <= 128 (== 128 unless the whole problem is smaller)
+  int rows;
   // filter
   int kd, kh, kw;
   int sd, sh, sw;

@@ -1,0 +1,337 @@
+"""UNet3DModel — the shape-branch denoiser on the B200 kernels.
+
+Drop-in for the reference's model/networks/diffusion_networks/openai_model_3d.py: same class names,
+constructor signature, child-module names (hence the same 496 state-dict keys) and the same
+forward(x, timesteps, context) contract (NCDHW fp32 in / out; openai_model_3d.py:752-789).
+
+Differences are internal only:
+  * activations are channels-last bf16 between kernels (fp32 accumulation, fp32 norm statistics);
+  * every 3x3x3 / 1x1x1 conv and linear is the tcgen05 implicit GEMM (cs_conv3d); `h + emb_out`, the
+    skip add, the skip-concat of the decoder (two-source K loop) and the GroupNorm statistics of a conv's
+    output are fused into its epilogue / operand fetch;
+  * all 17 `emb_layers` share one GEMV per step and all 11 cross-attention blocks one GEMV per context;
+  * no activation checkpointing, no NaN-check host syncs (attention.py:183,205), CUDA-graph capturable.
+The nn.Conv3d / nn.Linear / norm children only hold parameters; packed bf16 copies are rebuilt lazily when
+a parameter's version counter changes (i.e. after an optimizer step or load_state_dict).
+"""
+from __future__ import annotations
+
+from abc import abstractmethod
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+
+from .... import _lib, ops
+from .attention import SpatialTransformer3D
+from .ldm_diffusion_util import conv_nd, linear, normalization, timestep_embedding, zero_module
+
+
+def _f(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().float().contiguous()
+
+
+class TimestepBlock(nn.Module):
+    """Any module whose run() takes the timestep-embedding vector as a second argument."""
+
+    @abstractmethod
+    def run(self, pk, x, emb_vec, skip=None):
+        ...
+
+
+class TimestepEmbedSequential(nn.Sequential, TimestepBlock):
+    """Children are applied in order; ResBlocks get the time vector, transformers the context vectors
+    (reference: openai_model_3d.py:113-127)."""
+
+
+class Upsample(nn.Module):
+    def __init__(self, channels, use_conv, dims=2, out_channels=None, padding=1):
+        super().__init__()
+        self.channels = channels
+        self.out_channels = out_channels or channels
+        self.use_conv = use_conv
+        self.dims = dims
+        if use_conv:
+            self.conv = conv_nd(dims, self.channels, self.out_channels, 3, padding=padding)
+
+    def pack(self):
+        return {"w": ops.pack_conv_weight(self.conv.weight), "b": _f(self.conv.bias)} if self.use_conv else {}
+
+    def run(self, pk, x):
+        # dims == 3 keeps D and doubles H, W (the inherited "video" convention, :150-153); dims == 4 is isotropic
+        x = ops.upsample_nearest(x, (1, 2, 2) if self.dims == 3 else (2, 2, 2))
+        return ops.conv3d(x, pk["w"], bias=pk["b"]) if self.use_conv else x
+
+
+class Downsample(nn.Module):
+    def __init__(self, channels, use_conv, dims=2, out_channels=None, padding=1):
+        super().__init__()
+        self.channels = channels
+        self.out_channels = out_channels or channels
+        self.use_conv = use_conv
+        self.dims = dims
+        self.stride = (2, 2, 2) if dims != 3 else (1, 2, 2)
+        if not use_conv:
+            raise NotImplementedError("average-pool downsampling is not used by the reference configs (conv_resample=True)")
+        self.op = conv_nd(dims, self.channels, self.out_channels, 3, stride=self.stride, padding=padding)
+
+    def pack(self):
+        return {"w": ops.pack_conv_weight(self.op.weight), "b": _f(self.op.bias)}
+
+    def run(self, pk, x):
+        return ops.conv3d(x, pk["w"], stride=self.stride, bias=pk["b"])
+
+
+class ResBlock(TimestepBlock):
+    def __init__(self, channels, emb_channels, dropout, out_channels=None, use_conv=False, use_scale_shift_norm=False,
+                 dims=2, use_checkpoint=False, up=False, down=False):
+        super().__init__()
+        if use_scale_shift_norm or up or down or use_conv:
+            raise NotImplementedError("scale-shift norm / resblock up-down / conv skip are not used by the reference configs")
+        self.channels = channels
+        self.emb_channels = emb_channels
+        self.dropout = dropout
+        self.out_channels = out_channels or channels
+        self.use_checkpoint = use_checkpoint
+        self.in_layers = nn.Sequential(normalization(channels), nn.SiLU(), conv_nd(dims, channels, self.out_channels, 3, padding=1))
+        self.emb_layers = nn.Sequential(nn.SiLU(), linear(emb_channels, self.out_channels))
+        self.out_layers = nn.Sequential(normalization(self.out_channels), nn.SiLU(), nn.Dropout(p=dropout),
+                                        zero_module(conv_nd(dims, self.out_channels, self.out_channels, 3, padding=1)))
+        if self.out_channels == channels:
+            self.skip_connection = nn.Identity()
+        else:
+            self.skip_connection = conv_nd(dims, channels, self.out_channels, 1)
+
+    def pack(self):
+        pk = {"gn1": (_f(self.in_layers[0].weight), _f(self.in_layers[0].bias)),
+              "w1": ops.pack_conv_weight(self.in_layers[2].weight), "b1": _f(self.in_layers[2].bias),
+              "gn2": (_f(self.out_layers[0].weight), _f(self.out_layers[0].bias)),
+              "w2": ops.pack_conv_weight(self.out_layers[3].weight), "b2": _f(self.out_layers[3].bias)}
+        if not isinstance(self.skip_connection, nn.Identity):
+            pk["ws"] = ops.pack_conv_weight(self.skip_connection.weight)
+            pk["bs"] = _f(self.skip_connection.bias)
+        return pk
+
+    def run(self, pk, x, emb_vec, skip=None):
+        """x (and optionally the encoder skip tensor, logically concatenated after x on the channel axis):
+        (B, D, H, W, C) bf16; emb_vec: fp32 (B, out_channels) = emb_layers(emb)."""
+        B, C = x.shape[0], self.out_channels
+        a = ops.groupnorm(x, *pk["gn1"], eps=self.in_layers[0].eps, act=ops.ACT_SILU, x2=skip)
+        S = x.shape[1] * x.shape[2] * x.shape[3]
+        stat = ops.zero_stat_buffer(x.device, B, C) if S % 32 == 0 else None   # fused sums need whole warps per sample
+        h = ops.conv3d(a, pk["w1"], bias=pk["b1"], rowvec=emb_vec, stat_sum=stat)          # conv + bias + emb, GN sums fused
+        a = ops.groupnorm(h, *pk["gn2"], eps=self.out_layers[0].eps, act=ops.ACT_SILU, stat_sum=stat)
+        if "ws" in pk:
+            res = ops.linear_tokens(x, pk["ws"], bias=pk["bs"], x2=skip)                    # 1x1x1 skip on the raw concat
+        else:
+            res = x
+        return ops.conv3d(a, pk["w2"], bias=pk["b2"], residual=res)
+
+
+class UNet3DModel(nn.Module):
+    def __init__(self, image_size, in_channels, model_channels, out_channels, num_res_blocks, attention_resolutions,
+                 dropout=0, channel_mult=(1, 2, 4, 8), conv_resample=True, dims=2, num_classes=None,
+                 use_checkpoint=False, use_fp16=False, num_heads=-1, num_head_channels=-1, num_heads_upsample=-1,
+                 use_scale_shift_norm=False, resblock_updown=False, use_new_attention_order=False,
+                 use_spatial_transformer=False, transformer_depth=1, context_dim=None, n_embed=None, legacy=True):
+        super().__init__()
+        if use_spatial_transformer:
+            assert context_dim is not None, "You forgot to include the dimension of your cross-attention conditioning..."
+        if context_dim is not None:
+            assert use_spatial_transformer, "You forgot to use the spatial transformer for your cross-attention conditioning..."
+            if not isinstance(context_dim, int):
+                context_dim = list(context_dim)
+        if not use_spatial_transformer:
+            raise NotImplementedError("the AttentionBlock (concat-conditioning) variant is SURVEY.md §8f rank 1, not built yet")
+        if num_classes is not None or resblock_updown or n_embed is not None:
+            raise NotImplementedError("class conditioning / resblock_updown / codebook-id head are unused by the reference configs")
+        if num_heads_upsample == -1:
+            num_heads_upsample = num_heads
+        if num_heads == -1:
+            assert num_head_channels != -1, "Either num_heads or num_head_channels has to be set"
+        if num_head_channels == -1:
+            assert num_heads != -1, "Either num_heads or num_head_channels has to be set"
+
+        self.image_size = image_size
+        self.in_channels = in_channels
+        self.model_channels = model_channels
+        self.out_channels = out_channels
+        self.num_res_blocks = num_res_blocks
+        self.attention_resolutions = attention_resolutions
+        self.dropout = dropout
+        self.channel_mult = channel_mult
+        self.conv_resample = conv_resample
+        self.num_classes = num_classes
+        self.use_checkpoint = use_checkpoint
+        self.dtype = torch.float32
+        self.num_heads = num_heads
+        self.num_head_channels = num_head_channels
+        self.num_heads_upsample = num_heads_upsample
+        self.predict_codebook_ids = False
+        self.dims = dims
+
+        time_embed_dim = model_channels * 4
+        self.time_embed = nn.Sequential(linear(model_channels, time_embed_dim), nn.SiLU(), linear(time_embed_dim, time_embed_dim))
+
+        def transformer(ch, heads):
+            if num_head_channels == -1:
+                dim_head = ch // heads
+            else:
+                heads, dim_head = ch // num_head_channels, num_head_channels
+            if legacy:
+                dim_head = ch // heads
+            return SpatialTransformer3D(ch, heads, dim_head, depth=transformer_depth, context_dim=context_dim)
+
+        def res(cin, cout):
+            return ResBlock(cin, time_embed_dim, dropout, out_channels=cout, dims=dims, use_checkpoint=use_checkpoint)
+
+        self.input_blocks = nn.ModuleList([TimestepEmbedSequential(conv_nd(dims, in_channels, model_channels, 3, padding=1))])
+        input_block_chans = [model_channels]
+        ch, ds = model_channels, 1
+        for level, mult in enumerate(channel_mult):
+            for _ in range(num_res_blocks):
+                layers = [res(ch, mult * model_channels)]
+                ch = mult * model_channels
+                if ds in attention_resolutions:
+                    layers.append(transformer(ch, num_heads))
+                self.input_blocks.append(TimestepEmbedSequential(*layers))
+                input_block_chans.append(ch)
+            if level != len(channel_mult) - 1:
+                self.input_blocks.append(TimestepEmbedSequential(Downsample(ch, conv_resample, dims=dims, out_channels=ch)))
+                input_block_chans.append(ch)
+                ds *= 2
+        self.middle_block = TimestepEmbedSequential(res(ch, ch), transformer(ch, num_heads), res(ch, ch))
+        self.output_blocks = nn.ModuleList([])
+        for level, mult in list(enumerate(channel_mult))[::-1]:
+            for i in range(num_res_blocks + 1):
+                ich = input_block_chans.pop()
+                layers = [res(ch + ich, model_channels * mult)]
+                ch = model_channels * mult
+                if ds in attention_resolutions:
+                    layers.append(transformer(ch, num_heads_upsample))
+                if level and i == num_res_blocks:
+                    layers.append(Upsample(ch, conv_resample, dims=dims, out_channels=ch))
+                    ds //= 2
+                self.output_blocks.append(TimestepEmbedSequential(*layers))
+        self.out = nn.Sequential(normalization(ch), nn.SiLU(), zero_module(conv_nd(dims, model_channels, out_channels, 3, padding=1)))
+
+        self._packed = None
+        self._packed_key = None
+
+    # ------------------------------------------------------------------------------------------
+    # weight packing
+    # ------------------------------------------------------------------------------------------
+    def _blocks(self):
+        yield from self.input_blocks
+        yield self.middle_block
+        yield from self.output_blocks
+
+    def _version_key(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def repack(self) -> None:
+        """Rebuild the kernel-layout (bf16, K-major) copies of all weights."""
+        dev = self.out[2].weight.device
+        pk = {"blocks": [], "te": (_f(self.time_embed[0].weight), _f(self.time_embed[0].bias),
+                                   _f(self.time_embed[2].weight), _f(self.time_embed[2].bias))}
+        emb_w, emb_b, ca_w, ca_b = [], [], [], []
+        emb_off = ca_off = 0
+        for bi, block in enumerate(self._blocks()):
+            entries = []
+            for layer in block:
+                if isinstance(layer, ResBlock):
+                    e = {"kind": "res", "pk": layer.pack(), "emb": (emb_off, layer.out_channels)}
+                    emb_w.append(_f(layer.emb_layers[1].weight)); emb_b.append(_f(layer.emb_layers[1].bias))
+                    emb_off += layer.out_channels
+                elif isinstance(layer, SpatialTransformer3D):
+                    offs = []
+                    for tb in layer.transformer_blocks:
+                        w, b = tb.attn2.composed_single_token()
+                        ca_w.append(w); ca_b.append(b)
+                        offs.append((ca_off, w.shape[0])); ca_off += w.shape[0]
+                    e = {"kind": "st", "pk": layer.pack(), "ca": offs}
+                elif isinstance(layer, (Downsample, Upsample)):
+                    e = {"kind": "resample", "pk": layer.pack()}
+                elif isinstance(layer, nn.Conv3d):      # the stem: few input channels -> im2col + GEMM
+                    w = layer.weight.detach().float()
+                    k = 27 * w.shape[1]
+                    kp = (k + 15) // 16 * 16
+                    wp = torch.zeros(w.shape[0], 1, kp, device=dev)
+                    wp[:, 0, :k] = w.permute(0, 2, 3, 4, 1).reshape(w.shape[0], k)
+                    e = {"kind": "stem", "pk": {"w": wp.to(torch.bfloat16), "b": _f(layer.bias), "kp": kp}}
+                else:
+                    raise TypeError(f"unexpected layer {type(layer)}")
+                entries.append(e)
+            pk["blocks"].append(entries)
+        pk["emb_w"], pk["emb_b"] = torch.cat(emb_w).contiguous(), torch.cat(emb_b).contiguous()
+        pk["ca_w"], pk["ca_b"] = torch.cat(ca_w).contiguous(), torch.cat(ca_b).contiguous()
+        pk["out_gn"] = (_f(self.out[0].weight), _f(self.out[0].bias))
+        pk["out_w"], pk["out_b"] = ops.pack_conv_weight(self.out[2].weight), _f(self.out[2].bias)
+        self._packed, self._packed_key = pk, self._version_key()
+        self._pack_generation = getattr(self, "_pack_generation", 0) + 1
+
+    def _ensure_packed(self):
+        if self._packed is None or self._packed_key != self._version_key():
+            self.repack()
+        return self._packed
+
+    # ------------------------------------------------------------------------------------------
+    # forward
+    # ------------------------------------------------------------------------------------------
+    def context_vectors(self, context: torch.Tensor) -> torch.Tensor:
+        """All cross-attention outputs for a (B, 1, context_dim) conditioning: fp32 (B, sum of block widths).
+        Depends only on the context, so samplers may compute it once per trajectory."""
+        pk = self._ensure_packed()
+        if context.dim() != 3 or context.shape[1] != 1:
+            raise NotImplementedError(
+                "cross-attention over more than one context token: the scene-graph conditioning is one token per "
+                "object (VAEGAN_V2FULL.py:237-240); the multi-token path is not built yet")
+        return ops.linear_small(context[:, 0].float().contiguous(), pk["ca_w"], pk["ca_b"])
+
+    @torch.no_grad()
+    def forward(self, x, timesteps=None, context=None, y=None, context_vecs=None, **kwargs):
+        """x: (B, C, D, H, W) fp32 NCDHW, timesteps: (B,) int64, context: (B, 1, context_dim) -> eps (B, C, D, H, W).
+
+        Extensions: `context_vecs` = a cached context_vectors(context) result; x may hold B/r samples, in which
+        case sample b reads x[b % (B/r)] (a guided sampler passes x once for [uncond; cond]).
+        """
+        assert (y is not None) == (self.num_classes is not None), "must specify y if and only if the model is class-conditional"
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and x.requires_grad:
+            raise NotImplementedError("the backward pass of the B200 denoiser is not built yet (round 2)")
+        _lib.require_device()
+        pk = self._ensure_packed()
+        B = timesteps.shape[0]
+        x = x.float().contiguous()
+        t_emb = timestep_embedding(timesteps, self.model_channels)
+        w0, b0, w2, b2 = pk["te"]
+        emb = ops.linear_small(ops.linear_small(t_emb, w0, b0, act_out=ops.ACT_SILU), w2, b2)
+        emb_vecs = ops.linear_small(emb, pk["emb_w"], pk["emb_b"], act_in=ops.ACT_SILU)     # every ResBlock's emb_layers at once
+        ca_vecs = context_vecs if context_vecs is not None else self.context_vectors(context)
+
+        def run_block(block, entries, h, skip=None):
+            for layer, e in zip(block, entries):
+                if e["kind"] == "res":
+                    off, n = e["emb"]
+                    h = layer.run(e["pk"], h, emb_vecs[:, off:off + n], skip=skip)
+                    skip = None
+                elif e["kind"] == "st":
+                    h = layer.run(e["pk"], h, [ca_vecs[:, o:o + n] for o, n in e["ca"]])
+                elif e["kind"] == "resample":
+                    h = layer.run(e["pk"], h)
+                else:
+                    col = ops.im2col_small(h, batch=B, kp=e["pk"]["kp"])
+                    h = ops.linear_tokens(col, e["pk"]["w"], bias=e["pk"]["b"])
+            return h
+
+        entries = pk["blocks"]
+        n_in = len(self.input_blocks)
+        hs: List[torch.Tensor] = []
+        h = x
+        for i, block in enumerate(self.input_blocks):
+            h = run_block(block, entries[i], h)
+            hs.append(h)
+        h = run_block(self.middle_block, entries[n_in], h)
+        for i, block in enumerate(self.output_blocks):
+            h = run_block(block, entries[n_in + 1 + i], h, skip=hs.pop())    # th.cat([h, hs.pop()], dim=1), never materialised raw
+        a = ops.groupnorm(h, *pk["out_gn"], eps=self.out[0].eps, act=ops.ACT_SILU)
+        return ops.conv3d(a, pk["out_w"], bias=pk["out_b"], out_mode=_lib.OUT_F32_NCDHW)

@@ -24,7 +24,7 @@ __all__ = [
     "ACT_NONE", "ACT_SILU", "ACT_GELU", "conv3d", "linear_tokens", "groupnorm", "layernorm", "attention",
     "geglu", "upsample_nearest", "im2col_small", "timestep_embedding", "linear_small", "ddim_step",
     "q_sample", "to_channels_last", "to_ncdhw", "pack_conv_weight", "pack_linear_weight", "launch_count",
-    "reset_launch_count",
+    "reset_launch_count", "zero_stat_buffer",
 ]
 
 
@@ -140,7 +140,6 @@ def conv3d(x: torch.Tensor, weight: torch.Tensor, *, ksize: Sequence[int] = (3, 
     a.pd_back, a.ph_back, a.pw_back = pb
     a.bias = _ptr(_f32(bias, "conv3d.bias"))
     if rowvec is not None:
-        _f32(rowvec, "conv3d.rowvec") if rowvec.is_contiguous() else None
         if rowvec.dtype != torch.float32 or rowvec.dim() != 2 or rowvec.shape[0] != B or rowvec.shape[1] != Cout \
                 or rowvec.stride(1) != 1:
             raise _lib.CsError("conv3d: rowvec must be fp32 (B, Cout)")
@@ -176,6 +175,13 @@ def _workspace(device: torch.device, key: str, numel: int, zero: bool = False) -
         t = torch.zeros(numel, dtype=torch.float32, device=device)
         _ws[k] = t
     return t
+
+
+def zero_stat_buffer(device: torch.device, B: int, C: int) -> torch.Tensor:
+    """(B, C, 2) fp32 view of the shared GroupNorm-sum workspace.  It is all-zero on return (the finalize
+    kernel clears what it consumes); pass it as `stat_sum` to conv3d and then to the groupnorm that follows,
+    with no other groupnorm in between."""
+    return _workspace(device, "gn_stat", B * C * 2)[:B * C * 2].view(B, C, 2)
 
 
 def groupnorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, groups: int = 32, eps: float = 1e-5,

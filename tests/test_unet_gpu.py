@@ -1,0 +1,128 @@
+"""Parity of the CUDA denoiser with the reference (golden fixtures) and with the oracle.
+
+Tolerance: the CUDA path keeps activations in bf16 between kernels (fp32 accumulate / fp32 norm statistics)
+while the reference is fp32 end to end, so the bar is the one SURVEY.md §8c states for a bf16 path:
+relative L2 error of eps_hat <= 3e-2 under teacher-forced (x_t, t, cond) inputs.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import denoiser as D, weights as Wt
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+REL_L2_TOL = 3e-2
+
+
+def _build(cfg, seed):
+    from commonscenes_b200.model.networks.diffusion_networks.network import DiffusionUNet
+    params = dict(cfg, use_spatial_transformer=True, use_checkpoint=True, legacy=False)
+    m = DiffusionUNet(params, conditioning_key="crossattn")
+    Wt.fill_module_(m, seed)          # same (seed, key, shape) recipe the golden generator used on the reference
+    return m.cuda().eval()
+
+
+def _rel_l2(got, ref):
+    return float((got - ref).norm() / ref.norm())
+
+
+@pytest.mark.parametrize("tag,cfg", [("tiny", D.UNET_TINY), ("full", D.UNET_FULL)])
+def test_unet_eps_matches_reference_golden(tag, cfg):
+    g = np.load(os.path.join(GOLD, f"unet_{tag}.npz"))
+    m = _build(cfg, int(g["weight_seed"]))
+    x, t, ctx = (torch.tensor(g[k]).cuda() for k in ("x", "t", "ctx"))
+    eps = m(x, t, c_crossattn=[ctx]).cpu()
+    ref = torch.tensor(g["eps"])
+    err = _rel_l2(eps, ref)
+    print(f"unet[{tag}] rel-L2 vs reference golden = {err:.4e}; max abs err {float((eps - ref).abs().max()):.4e}")
+    assert eps.shape == ref.shape and torch.isfinite(eps).all()
+    assert err <= REL_L2_TOL
+
+
+def test_unet_matches_oracle_on_fresh_inputs():
+    cfg = D.UNET_TINY
+    m = _build(cfg, 21)
+    sd = Wt.synth_state_dict(D.unet_param_shapes(cfg), 21)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(3, 3, 8, 8, 8, generator=g)
+    t = torch.tensor([999, 0, 421])
+    ctx = torch.randn(3, 1, cfg["context_dim"], generator=g)
+    with torch.no_grad():
+        ref = D.unet_forward(sd, cfg, x, t, ctx)
+    eps = m(x.cuda(), t.cuda(), c_crossattn=[ctx.cuda()]).cpu()
+    assert _rel_l2(eps, ref) <= REL_L2_TOL
+
+
+def test_samples_are_independent_and_batch_invariant():
+    """Objects are independent units: a sample's eps must not depend on its batch mates."""
+    cfg = D.UNET_TINY
+    m = _build(cfg, 22)
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(4, 3, 8, 8, 8, generator=g).cuda()
+    t = torch.tensor([10, 500, 900, 77]).cuda()
+    ctx = torch.randn(4, 1, cfg["context_dim"], generator=g).cuda()
+    full = m(x, t, c_crossattn=[ctx])
+    half = m(x[2:].contiguous(), t[2:].contiguous(), c_crossattn=[ctx[2:].contiguous()])
+    assert _rel_l2(full[2:].cpu(), half.cpu()) < 1e-3
+
+
+def test_ddim_guided_steps_match_reference_sampler():
+    from commonscenes_b200.model.networks.diffusion_networks.samplers.ddim import DDIMSampler
+    g = np.load(os.path.join(GOLD, "ddim_tiny.npz"))
+    m = _build(D.UNET_TINY, int(g["weight_seed"]))
+    sched = D.register_schedule(**D.DIFFUSION)
+
+    class Host:
+        num_timesteps = 1000
+        betas = sched["betas"].cuda()
+        alphas_cumprod = sched["alphas_cumprod"].cuda()
+        df = m
+    for use_graph in (False, True):
+        s = DDIMSampler(Host(), use_cuda_graph=use_graph)
+        s.make_schedule(100, ddim_eta=0.0, verbose=False)
+        assert (s.ddim_timesteps == g["ddim_timesteps"]).all()
+        np.testing.assert_array_equal(s.ddim_alphas, g["ddim_alphas"])
+        np.testing.assert_array_equal(s.ddim_alphas_prev, g["ddim_alphas_prev"].astype(np.float32))
+        c, uc, x = (torch.tensor(g[k]).cuda() for k in ("c", "uc", "x_T"))
+        ca = m.diffusion_net.context_vectors(torch.cat([uc, c]))
+        steps = np.flip(s.ddim_timesteps)
+        t_dev = torch.empty(6, dtype=torch.int64, device="cuda")
+        for i in range(4):
+            # teacher forcing: every step starts from the reference's own x_t (north_star: identical (x_t, t, cond))
+            x_in = x if i == 0 else torch.tensor(g["x_steps"][i - 1]).cuda()
+            t_dev.fill_(int(steps[i]))
+            eps = s._eps(x_in, t_dev, ca)
+            index = len(steps) - i - 1
+            from commonscenes_b200 import ops
+            xp, p0 = ops.ddim_step(x_in, eps, guided=True, scale=3.0, a_t=float(s.ddim_alphas[index]),
+                                   a_prev=float(s.ddim_alphas_prev[index]), sigma=0.0,
+                                   sqrt_one_minus_at=float(s.ddim_sqrt_one_minus_alphas[index]))
+            e_x = _rel_l2(xp.cpu(), torch.tensor(g["x_steps"][i]))
+            e_p = _rel_l2(p0.cpu(), torch.tensor(g["pred_x0_steps"][i]))
+            print(f"ddim step {i} graph={use_graph}: rel-L2 x_prev {e_x:.3e} pred_x0 {e_p:.3e}")
+            assert e_x <= REL_L2_TOL and e_p <= 2 * REL_L2_TOL
+
+
+def test_sampler_public_api_runs_and_counts_kernels():
+    from commonscenes_b200 import ops
+    from commonscenes_b200.model.networks.diffusion_networks.samplers.ddim import DDIMSampler
+    m = _build(D.UNET_TINY, 23)
+    sched = D.register_schedule(**D.DIFFUSION)
+
+    class Host:
+        num_timesteps = 1000
+        betas = sched["betas"].cuda()
+        alphas_cumprod = sched["alphas_cumprod"].cuda()
+        df = m
+    s = DDIMSampler(Host())
+    g = torch.Generator().manual_seed(9)
+    c = torch.randn(2, 1, 64, generator=g).cuda()
+    uc = torch.randn(2, 1, 64, generator=g).cuda()
+    n0 = ops.launch_count()
+    out, inter = s.sample(S=10, batch_size=2, shape=(3, 8, 8, 8), conditioning=c, verbose=False,
+                          unconditional_guidance_scale=3.0, unconditional_conditioning=uc, eta=0.0)
+    assert out.shape == (2, 3, 8, 8, 8) and torch.isfinite(out).all()
+    assert ops.launch_count() > n0 and set(inter) == {"x_inter", "pred_x0"}
