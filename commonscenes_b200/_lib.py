@@ -60,6 +60,8 @@ SIGNATURES = {
     "cs_q_sample": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp]),
     "cs_ncdhw_to_ndhwc": (_i32, [_vp, _i32, _i32, _i64, _i32, _vp, _vp]),
     "cs_ndhwc_to_ncdhw": (_i32, [_vp, _i32, _i32, _i64, _i32, _vp, _vp]),
+    "cs_channel_mix": (_i32, [_vp, _i32, _i32, _i32, _i64, _vp, _vp, _vp, _vp]),
+    "cs_vq_quantize": (_i32, [_vp, _i32, _i32, _i64, _vp, _i32, _vp, _vp, _i32, _vp, _vp, _vp]),
 }
 
 _lib = None

@@ -26,6 +26,9 @@ int q_sample_launch(const float*, const float*, const long long*, const float*, 
                     float*, cudaStream_t);
 int ncdhw_to_ndhwc_launch(const float*, int, int, long long, int, void*, cudaStream_t);
 int ndhwc_to_ncdhw_launch(const void*, int, int, long long, int, float*, cudaStream_t);
+int channel_mix_launch(const float*, int, int, int, long long, const float*, const float*, float*, cudaStream_t);
+int vq_quantize_launch(const float*, int, int, long long, const float*, int, const float*, const float*, int, float*,
+                       long long*, cudaStream_t);
 }  // namespace cs
 
 static inline cudaStream_t S(cs_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
@@ -127,6 +130,19 @@ int cs_ncdhw_to_ndhwc(const float* x, int32_t B, int32_t C, int64_t Sp, int32_t 
 }
 int cs_ndhwc_to_ncdhw(const void* x, int32_t B, int32_t C, int64_t Sp, int32_t pitch, float* y, cs_stream_t stream) {
   return cs::ndhwc_to_ncdhw_launch(x, B, C, Sp, pitch, y, S(stream));
+}
+
+int cs_vq_quantize(const float* z, int32_t B, int32_t E, int64_t Sp, const float* codebook, int32_t n_e,
+                   const float* post_w, const float* post_b, int32_t Zc, float* zq_out, int64_t* idx_out,
+                   cs_stream_t stream) {
+  if (!z || !codebook || !zq_out) return cs::set_error(CS_ERR_INVALID, "cs_vq_quantize: null pointer");
+  return cs::vq_quantize_launch(z, B, E, Sp, codebook, n_e, post_w, post_b, Zc, zq_out,
+                                reinterpret_cast<long long*>(idx_out), S(stream));
+}
+
+int cs_channel_mix(const float* x, int32_t B, int32_t Ci, int32_t Co, int64_t Sp, const float* w, const float* bias,
+                   float* y, cs_stream_t stream) {
+  return cs::channel_mix_launch(x, B, Ci, Co, Sp, w, bias, y, S(stream));
 }
 
 }  // extern "C"

@@ -303,4 +303,27 @@ int ndhwc_to_ncdhw_launch(const void* x, int B, int C, long long S, int pitch, f
   CS_LAUNCH_CHECK("ndhwc_to_ncdhw");
 }
 
+// ------------------------------------------------------------------------------------------------
+// 1x1x1 convolution between few-channel fp32 NCDHW tensors (quant_conv / post_quant_conv, 3 -> 3):
+// y[b][o][s] = sum_c w[o][c] x[b][c][s] + bias[o]
+__global__ void channel_mix_kernel(const float* __restrict__ x, int Ci, int Co, long long S, long long total,
+                                   const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ y) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long b = i / S, s = i - b * S;
+    for (int o = 0; o < Co; ++o) {
+      float acc = bias ? bias[o] : 0.f;
+      for (int c = 0; c < Ci; ++c) acc = fmaf(w[o * Ci + c], x[(b * Ci + c) * S + s], acc);
+      y[(b * Co + o) * S + s] = acc;
+    }
+  }
+}
+int channel_mix_launch(const float* x, int B, int Ci, int Co, long long S, const float* w, const float* bias, float* y,
+                       cudaStream_t st) {
+  if (Ci < 1 || Co < 1 || Ci > 16 || Co > 16) return set_error(CS_ERR_UNSUPPORTED, "channel_mix: 1..16 channels");
+  const long long total = static_cast<long long>(B) * S;
+  channel_mix_kernel<<<grid_for(total, 256, 8), 256, 0, st>>>(x, Ci, Co, S, total, w, bias, y);
+  CS_LAUNCH_CHECK("channel_mix");
+}
+
 }  // namespace cs

@@ -106,21 +106,13 @@ class DDIMSampler(object):
         total_steps = timesteps.shape[0]
 
         guided = unconditional_conditioning is not None and unconditional_guidance_scale != 1.
-        unet = self._unet()
         ctx = torch.cat([unconditional_conditioning, cond]) if guided else cond     # [uncond; cond] (ddim.py:206-209)
-        ca_vecs = unet.context_vectors(ctx)                                          # once per trajectory
-        nb = 2 * b if guided else b
-        t_dev = torch.empty(nb, dtype=torch.int64, device=device)
+        ca_vecs = self._unet().context_vectors(ctx)                                  # once per trajectory
+        t_dev = torch.empty(2 * b if guided else b, dtype=torch.int64, device=device)
         for i, step in enumerate(time_range):
             index = total_steps - i - 1
             t_dev.fill_(int(step))
-            eps = self._eps(img, t_dev, ca_vecs)
-            sigma = float(self.ddim_sigmas[index])
-            noise = torch.randn_like(img) * temperature if sigma > 0 else None
-            img, pred_x0 = ops.ddim_step(img, eps, guided=guided, scale=float(unconditional_guidance_scale),
-                                         a_t=float(self.ddim_alphas[index]), a_prev=float(self.ddim_alphas_prev[index]),
-                                         sigma=sigma, sqrt_one_minus_at=float(self.ddim_sqrt_one_minus_alphas[index]),
-                                         noise=noise, want_pred_x0=True)
+            img, pred_x0 = self._step(img, t_dev, ca_vecs, index, guided, float(unconditional_guidance_scale), temperature)
             if callback:
                 callback(i)
             if img_callback:
@@ -130,17 +122,25 @@ class DDIMSampler(object):
                 intermediates["pred_x0"].append(pred_x0)
         return img, intermediates
 
-    @torch.no_grad()
-    def p_sample_ddim(self, x, c, t, index, unconditional_guidance_scale=1., unconditional_conditioning=None,
-                      temperature=1., **kwargs):
-        """One reverse step (ddim.py:182-244); returns (x_prev, pred_x0)."""
-        guided = unconditional_conditioning is not None and unconditional_guidance_scale != 1.
-        unet = self._unet()
-        ctx = torch.cat([unconditional_conditioning, c]) if guided else c
-        tt = torch.cat([t] * 2) if guided else t
-        eps = unet(x.float().contiguous(), tt.contiguous(), context=ctx)
+    def _step(self, x, t_dev, ca_vecs, index, guided, scale, temperature=1., want_pred_x0=True):
+        """UNet evaluation (graph replay) + fused CFG / pred_x0 / x_prev update (cs_ddim_step)."""
+        eps = self._eps(x, t_dev, ca_vecs)
         sigma = float(self.ddim_sigmas[index])
         noise = torch.randn_like(x) * temperature if sigma > 0 else None
-        return ops.ddim_step(x.float().contiguous(), eps, guided=guided, scale=float(unconditional_guidance_scale),
-                             a_t=float(self.ddim_alphas[index]), a_prev=float(self.ddim_alphas_prev[index]), sigma=sigma,
-                             sqrt_one_minus_at=float(self.ddim_sqrt_one_minus_alphas[index]), noise=noise)
+        return ops.ddim_step(x, eps, guided=guided, scale=scale, a_t=float(self.ddim_alphas[index]),
+                             a_prev=float(self.ddim_alphas_prev[index]), sigma=sigma,
+                             sqrt_one_minus_at=float(self.ddim_sqrt_one_minus_alphas[index]), noise=noise,
+                             want_pred_x0=want_pred_x0)
+
+    @torch.no_grad()
+    def p_sample_ddim(self, x, c, t, index, repeat_noise=False, use_original_steps=False, quantize_denoised=False,
+                      temperature=1., noise_dropout=0., score_corrector=None, corrector_kwargs=None,
+                      unconditional_guidance_scale=1., unconditional_conditioning=None, mm_cls_free=False):
+        """One reverse step (ddim.py:182-244); returns (x_prev, pred_x0).  `t` is the (b,) timestep tensor."""
+        if use_original_steps or quantize_denoised or score_corrector is not None or mm_cls_free or noise_dropout > 0.:
+            raise NotImplementedError("options unused by the shape branch")
+        guided = unconditional_conditioning is not None and unconditional_guidance_scale != 1.
+        ctx = torch.cat([unconditional_conditioning, c]) if guided else c
+        ca_vecs = self._unet().context_vectors(ctx)
+        tt = (torch.cat([t] * 2) if guided else t).to(torch.int64).contiguous()
+        return self._step(x.float().contiguous(), tt, ca_vecs, index, guided, float(unconditional_guidance_scale), temperature)

@@ -24,7 +24,7 @@ __all__ = [
     "ACT_NONE", "ACT_SILU", "ACT_GELU", "conv3d", "linear_tokens", "groupnorm", "layernorm", "attention",
     "geglu", "upsample_nearest", "im2col_small", "timestep_embedding", "linear_small", "ddim_step",
     "q_sample", "to_channels_last", "to_ncdhw", "pack_conv_weight", "pack_linear_weight", "launch_count",
-    "reset_launch_count", "zero_stat_buffer",
+    "reset_launch_count", "zero_stat_buffer", "ConvProfiler", "vq_quantize", "channel_mix",
 ]
 
 
@@ -87,6 +87,30 @@ def pack_linear_weight(w: torch.Tensor) -> torch.Tensor:
 # ----------------------------------------------------------------------------------------------
 # GEMM-class
 # ----------------------------------------------------------------------------------------------
+class ConvProfiler:
+    """Context manager: brackets every cs_conv3d launch with CUDA events on the launching stream and records its
+    algorithmic FLOPs (2*MAC over real channels/taps).  Used by bench.py for the live roofline numbers."""
+    active: Optional["ConvProfiler"] = None
+
+    def __init__(self):
+        self.records = []   # (start_event, end_event, flops, tag)
+
+    def __enter__(self):
+        ConvProfiler.active = self
+        return self
+
+    def __exit__(self, *exc):
+        ConvProfiler.active = None
+
+    def summary(self):
+        """(total ms, total TFLOP, launches) — call after a synchronize."""
+        ms = sum(a.elapsed_time(b) for a, b, _, _ in self.records)
+        return ms, sum(f for _, _, f, _ in self.records) / 1e12, len(self.records)
+
+    def table(self):
+        return [(tag, a.elapsed_time(b), f) for a, b, f, tag in self.records]
+
+
 def conv3d(x: torch.Tensor, weight: torch.Tensor, *, ksize: Sequence[int] = (3, 3, 3),
            stride: Sequence[int] = (1, 1, 1), pad: Sequence[int] = (1, 1, 1),
            pad_back: Optional[Sequence[int]] = None, bias: Optional[torch.Tensor] = None,
@@ -153,7 +177,15 @@ def conv3d(x: torch.Tensor, weight: torch.Tensor, *, ksize: Sequence[int] = (3, 
     if stat_sum is not None:
         a.stat_sum, a.stat_pitch = stat_sum.data_ptr(), stat_sum.shape[1]
     a.bn_hint = bn_hint
+    prof = ConvProfiler.active
+    if prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     check(lib.cs_conv3d(C.byref(a), _stream()), "cs_conv3d")
+    if prof is not None:
+        e1.record()
+        flops = 2.0 * B * Do * Ho * Wo * Cout * (C1 + C2) * kd * kh * kw
+        prof.records.append((e0, e1, flops, f"{C1 + C2}->{Cout} k{kd}{kh}{kw} s{stride[0]}{stride[1]}{stride[2]} @{Do}x{Ho}x{Wo} B{B}"))
     return out
 
 
@@ -354,4 +386,30 @@ def to_ncdhw(x: torch.Tensor, channels: Optional[int] = None) -> torch.Tensor:
     y = torch.empty((B, cc, D, H, W), dtype=torch.float32, device=x.device)
     check(_lib.load().cs_ndhwc_to_ncdhw(x.data_ptr(), B, cc, D * H * W, p, y.data_ptr(), _stream()),
           "cs_ndhwc_to_ncdhw")
+    return y
+
+
+def vq_quantize(z: torch.Tensor, codebook: torch.Tensor, post_w: Optional[torch.Tensor] = None,
+                post_b: Optional[torch.Tensor] = None, want_indices: bool = True):
+    """z: fp32 NCDHW (B, E, D, H, W) -> (z_q [optionally through post_quant_conv], int64 indices (B*D*H*W,))."""
+    _f32(z, "vq_quantize.z"), _f32(codebook, "vq_quantize.codebook")
+    B, E = z.shape[0], z.shape[1]
+    S = z.numel() // (B * E)
+    zc = E if post_w is None else post_w.shape[0]
+    out = torch.empty((B, zc) + tuple(z.shape[2:]), dtype=torch.float32, device=z.device)
+    idx = torch.empty(B * S, dtype=torch.int64, device=z.device) if want_indices else None
+    check(_lib.load().cs_vq_quantize(z.data_ptr(), B, E, S, codebook.data_ptr(), codebook.shape[0],
+                                     _ptr(_f32(post_w, "post_w")), _ptr(_f32(post_b, "post_b")), zc, out.data_ptr(),
+                                     _ptr(idx), _stream()), "cs_vq_quantize")
+    return out, idx
+
+
+def channel_mix(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """1x1x1 conv on a few-channel fp32 NCDHW tensor: (B, Ci, ...) x (Co, Ci) -> (B, Co, ...)."""
+    _f32(x, "channel_mix.x"), _f32(w, "channel_mix.w")
+    B, Ci = x.shape[0], x.shape[1]
+    S = x.numel() // (B * Ci)
+    y = torch.empty((B, w.shape[0]) + tuple(x.shape[2:]), dtype=torch.float32, device=x.device)
+    check(_lib.load().cs_channel_mix(x.data_ptr(), B, Ci, w.shape[0], S, w.data_ptr(), _ptr(_f32(bias, "bias")),
+                                     y.data_ptr(), _stream()), "cs_channel_mix")
     return y

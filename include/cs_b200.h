@@ -122,6 +122,19 @@ int cs_q_sample(const float* x0, const float* noise, const int64_t* t, const flo
 int cs_ncdhw_to_ndhwc(const float* x, int32_t B, int32_t C, int64_t S, int32_t Cp, void* y, cs_stream_t stream);
 int cs_ndhwc_to_ncdhw(const void* x, int32_t B, int32_t C, int64_t S, int32_t pitch, float* y, cs_stream_t stream);
 
+/* ---- VQ-VAE codebook lookup (VectorQuantizer.forward, quantizer.py:68-99) + optional post_quant_conv ----
+ * z: fp32 NCDHW [B][E][S]; codebook fp32 [n_e][E]; idx_out int64 [B*S] or NULL.
+ * post_w == NULL: zq_out[B][E][S] = e[argmin]; else zq_out[B][Zc][S] = post_w[Zc][E] e[argmin] + post_b
+ * (vqvae_networks/network.py:95-101). */
+int cs_vq_quantize(const float* z, int32_t B, int32_t E, int64_t S, const float* codebook, int32_t n_e,
+                   const float* post_w, const float* post_b, int32_t Zc, float* zq_out, int64_t* idx_out,
+                   cs_stream_t stream);
+
+/* 1x1x1 conv between few-channel fp32 NCDHW tensors: y[b][o][s] = sum_c w[o][c] x[b][c][s] + bias[o]
+ * (quant_conv / post_quant_conv, vqvae_networks/network.py:70-71) */
+int cs_channel_mix(const float* x, int32_t B, int32_t Ci, int32_t Co, int64_t S, const float* w, const float* bias,
+                   float* y, cs_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
