@@ -15,7 +15,7 @@ LIB_PATH = _HERE / "libcsb200.so"
 
 CS_OK, CS_ERR_INVALID, CS_ERR_CUDA, CS_ERR_UNSUPPORTED, CS_ERR_NO_DEVICE = range(5)
 OUT_BF16_NDHWC, OUT_F32_NCDHW, OUT_F32_NDHWC = 0, 1, 2
-ACT_NONE, ACT_SILU, ACT_GELU = 0, 1, 2
+ACT_NONE, ACT_SILU, ACT_GELU, ACT_GEGLU = 0, 1, 2, 3
 
 _vp, _i32, _i64, _f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 

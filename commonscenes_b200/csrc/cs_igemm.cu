@@ -35,7 +35,146 @@ struct __align__(8) IgemmBarriers {
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
   uint32_t tmem_base;
+  float colvec[2][256];  // per accumulator buffer: bias + per-sample vector of the tile's columns
 };
+
+
+// ------------------------------------------------------------------------------------------------
+// Fast epilogue (bf16 channels-last output, Cout % 8 == 0, one sample per tile).
+// Per warp: 32 accumulator rows.  Columns are processed 64 at a time: TMEM -> registers (4 x tcgen05.ld in
+// flight), + column vector (bias + per-sample vector, staged once per tile in shared memory), + residual
+// (fetched coalesced through the staging buffer), activation / GEGLU, GroupNorm sums (butterfly
+// transpose-reduce), pack to bf16, stage in 128B-XOR-swizzled shared memory and write out with every store
+// instruction covering whole 128-byte row segments.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void colsum32(float (&a)[32], int lane) {
+  // after the call a[0] of lane l holds the sum over the warp's 32 rows of column l
+#pragma unroll
+  for (int half = 16; half >= 1; half >>= 1) {
+    const bool upper = (lane & half) != 0;
+#pragma unroll
+    for (int j = 0; j < half; ++j) {
+      const float send = upper ? a[j] : a[j + half];
+      const float keep = upper ? a[j + half] : a[j];
+      a[j] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+    }
+  }
+}
+
+__device__ __forceinline__ void epilogue_fast_tile(const IgemmParams& p, uint32_t t_row, int lane, int warp_rows0,
+                                                   long long m_tile0, int b, int n0, const float* colvec,
+                                                   uint8_t* stage) {
+  // warp_rows0: first accumulator row of this warp inside the tile; m_tile0: global row of the tile's row 0
+  const int rows_valid = min(32, p.rows - warp_rows0);          // <= 0: nothing to do for this warp
+  const long long m_w0 = m_tile0 + warp_rows0;
+  const bool geglu = (p.act == CS_ACT_GEGLU);
+  const uint32_t stage_u = smem_u32(stage);
+  for (int c0 = 0; c0 < p.BN; c0 += 64) {
+    const int n = n0 + c0;
+    if (n >= p.Cout) break;                                     // warp-uniform
+    const int ncols = min(64, min(p.BN - c0, p.Cout - n));      // multiple of 8 (16 for the TMEM loads below)
+    uint32_t raw[4][16];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (q * 16 < ncols) tmem_ld16(t_row + static_cast<uint32_t>(c0 + q * 16), raw[q]);
+    // residual: coalesced global -> swizzled staging, while the TMEM loads are in flight
+    if (p.residual) {
+      const __nv_bfloat16* rbase = reinterpret_cast<const __nv_bfloat16*>(p.residual);
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int r = it * 4 + (lane >> 3), ch = lane & 7;
+        if (r < rows_valid && ch * 8 < ncols) {
+          const uint4 u = *reinterpret_cast<const uint4*>(rbase + (m_w0 + r) * p.res_pitch + n + ch * 8);
+          *reinterpret_cast<uint4*>(stage + r * 128 + ((ch ^ (r & 7)) << 4)) = u;
+        }
+      }
+      __syncwarp();
+    }
+    tmem_ld_wait();
+    float v[64];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[q * 16 + j] = (q * 16 < ncols) ? __uint_as_float(raw[q][j]) + colvec[c0 + q * 16 + j] : 0.f;
+    if (p.residual) {
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) {
+        if (ch * 8 < ncols) {
+          const uint4 u = *reinterpret_cast<const uint4*>(stage + lane * 128 + ((ch ^ (lane & 7)) << 4));
+          const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = unpack_bf16x2(w[j]);
+            v[ch * 8 + 2 * j] += f.x;
+            v[ch * 8 + 2 * j + 1] += f.y;
+          }
+        }
+      }
+      __syncwarp();                                             // everyone has read before the buffer is reused
+    }
+    if (p.act == CS_ACT_SILU) {
+#pragma unroll
+      for (int j = 0; j < 64; ++j) v[j] = silu_f(v[j]);
+    } else if (p.act == CS_ACT_GELU) {
+#pragma unroll
+      for (int j = 0; j < 64; ++j) v[j] = gelu_erf_f(v[j]);
+    }
+    int out_cols = ncols, out_n = n;
+    if (geglu) {
+      // packed weight rows interleave 16 value / 16 gate columns: out[16g + j] = v[32g + j] * gelu(v[32g + 16 + j])
+#pragma unroll
+      for (int g = 0; g < 2; ++g)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[16 * g + j] = v[32 * g + j] * gelu_erf_f(v[32 * g + 16 + j]);
+      out_cols = ncols >> 1;
+      out_n = n >> 1;
+    }
+    if (p.stat_sum) {
+      if (lane >= rows_valid) {
+#pragma unroll
+        for (int j = 0; j < 64; ++j) v[j] = 0.f;               // rows past a short tile must not be summed
+      }
+#pragma unroll
+      for (int hblk = 0; hblk < 2; ++hblk) {
+        if (hblk * 32 < out_cols) {
+          float a[32], q2[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { a[j] = v[hblk * 32 + j]; q2[j] = a[j] * a[j]; }
+          colsum32(a, lane);
+          colsum32(q2, lane);
+          if (hblk * 32 + lane < out_cols && rows_valid > 0) {
+            float* sp = p.stat_sum + (static_cast<long long>(b) * p.stat_pitch + out_n + hblk * 32 + lane) * 2;
+            atomicAdd(sp, a[0]);
+            atomicAdd(sp + 1, q2[0]);
+          }
+        }
+      }
+    }
+    // pack -> swizzled staging -> coalesced global stores
+    const int out_chunks = out_cols >> 3;                       // 16-byte chunks per row
+#pragma unroll
+    for (int ch = 0; ch < 8; ++ch) {
+      if (ch < out_chunks) {
+        uint4 u;
+        u.x = pack_bf16x2(v[ch * 8 + 0], v[ch * 8 + 1]); u.y = pack_bf16x2(v[ch * 8 + 2], v[ch * 8 + 3]);
+        u.z = pack_bf16x2(v[ch * 8 + 4], v[ch * 8 + 5]); u.w = pack_bf16x2(v[ch * 8 + 6], v[ch * 8 + 7]);
+        *reinterpret_cast<uint4*>(stage + lane * 128 + ((ch ^ (lane & 7)) << 4)) = u;
+      }
+    }
+    __syncwarp();
+    __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(p.out);
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int r = it * 4 + (lane >> 3), ch = lane & 7;
+      if (r < rows_valid && ch < out_chunks) {
+        const uint4 u = *reinterpret_cast<const uint4*>(stage + r * 128 + ((ch ^ (r & 7)) << 4));
+        *reinterpret_cast<uint4*>(obase + (m_w0 + r) * p.out_pitch + out_n + ch * 8) = u;
+      }
+    }
+    __syncwarp();
+    (void)stage_u;
+  }
+}
 
 __global__ void __launch_bounds__(kIgemmThreads, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
@@ -166,6 +305,35 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
     int acc = 0;
     uint32_t acc_phase = 0;
     const long long spatial = static_cast<long long>(p.Do) * p.Ho * p.Wo;
+    if (p.fast_epilogue) {
+      uint8_t* stage = smem + p.stages * stage_bytes + (warp - 2) * 4096;
+      const int et = threadIdx.x - 64;                           // 0..127 among the epilogue threads
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_tiles;
+        const int mt = tile / p.n_tiles;
+        const long long m_tile0 = static_cast<long long>(mt) * p.rows;   // tiles are contiguous runs of voxels
+        const int b = static_cast<int>(m_tile0 / spatial);               // one sample per tile (bb == 1)
+        const int n0 = nt * p.BN;
+        // column vector for this tile (bias + per-sample vector), double buffered with the accumulator
+        for (int c = et; c < p.BN; c += 128) {
+          float cv = 0.f;
+          if (n0 + c < p.Cout) {
+            if (p.bias) cv += __ldg(p.bias + n0 + c);
+            if (p.rowvec) cv += __ldg(p.rowvec + static_cast<long long>(b) * p.rowvec_pitch + n0 + c);
+          }
+          bars.colvec[acc][c] = cv;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        mbar_wait(&bars.tmem_full[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * 256);
+        epilogue_fast_tile(p, t_row, lane, quarter * 32, m_tile0, b, n0, bars.colvec[acc], stage);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars.tmem_empty[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    } else
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int nt = tile % p.n_tiles;
       int mt = tile / p.n_tiles;
@@ -351,7 +519,7 @@ int igemm_launch(const IgemmArgs& a, cudaStream_t stream) {
   p.m_tiles = (p.B / p.bb) * (p.Do / p.bd) * (p.Ho / p.bh) * (p.Wo / p.bw);
   const int stage_bytes = kABytes + bn * 128;
   // 227 KB per CTA minus the kernel's static shared memory (barriers) and the 1 KB alignment slack
-  const int smem_budget = 227 * 1024 - 4096;
+  const int smem_budget = 227 * 1024 - 4096 - 4 * 4096;  // 4 x 4 KB epilogue staging buffers
   int stages = smem_budget / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return set_error(CS_ERR_INVALID, "igemm: tile too large for shared memory");
@@ -392,8 +560,11 @@ int igemm_launch(const IgemmArgs& a, cudaStream_t stream) {
     if (rc) return rc;
   }
 
+  p.fast_epilogue = (p.out_mode == CS_OUT_BF16_NDHWC && a.Cout % 8 == 0 && p.bb == 1) ? 1 : 0;
+  if (p.act == CS_ACT_GEGLU && (!p.fast_epilogue || bn % 32 || a.Cout % 32 || p.residual || p.stat_sum))
+    return set_error(CS_ERR_INVALID, "igemm: GEGLU epilogue needs bf16 output, Cout % 32 == 0 and no residual/stats");
   static int attr_smem = 0;
-  const int smem_bytes = stages * stage_bytes + 1024;
+  const int smem_bytes = stages * stage_bytes + 4 * 4096 + 1024;
   if (smem_bytes > attr_smem) {
     cudaError_t e = cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return set_cuda_error(e, "igemm: cudaFuncSetAttribute");

@@ -5,7 +5,7 @@
 namespace cs {
 
 enum : int { CS_OUT_BF16_NDHWC = 0, CS_OUT_F32_NCDHW = 1, CS_OUT_F32_NDHWC = 2 };
-enum : int { CS_ACT_NONE = 0, CS_ACT_SILU = 1, CS_ACT_GELU = 2 };
+enum : int { CS_ACT_NONE = 0, CS_ACT_SILU = 1, CS_ACT_GELU = 2, CS_ACT_GEGLU = 3 };
 
 struct IgemmParams {
   // output grid (voxels) and the 128-voxel tile box over it
@@ -23,6 +23,7 @@ struct IgemmParams {
   int n_tiles;  // ceil(Cout / BN)
   int m_tiles;
   int stages;
+  int fast_epilogue;  // bf16 output staged through shared memory (coalesced), host-selected
   // epilogue
   const float* bias;      // [Cout] or null
   const float* rowvec;    // [B][rowvec_pitch] per-sample vector added to every voxel, or null

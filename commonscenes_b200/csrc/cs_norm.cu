@@ -85,31 +85,40 @@ __global__ void gn_finalize_kernel(float* __restrict__ stat, const float* __rest
 }
 
 // ------------------------------------------------------------------------------------------------
-// apply: y = act(x * scale + shift), bf16 -> bf16, 8 channels per thread
+// apply: y = act(x * scale + shift), bf16 -> bf16.  A thread owns one 8-channel vector of one sample for a
+// slab of voxels, so its 8 (scale, shift) pairs are loaded once and stay in registers.
 // ------------------------------------------------------------------------------------------------
 __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x, int S, int C, int pitch,
                                 const float2* __restrict__ ss, int ss_pitch,
-                                __nv_bfloat16* __restrict__ y, int y_pitch, int act, long long total_vec) {
+                                __nv_bfloat16* __restrict__ y, int y_pitch, int act, int vox_per_cta) {
   const int cv = C >> 3;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total_vec;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long row = i / cv;
-    const int v = static_cast<int>(i - row * cv);
-    const int b = static_cast<int>(row / S);
-    const uint4 u = *reinterpret_cast<const uint4*>(x + row * pitch + v * 8);
-    const float2* sp = ss + static_cast<long long>(b) * ss_pitch + v * 8;
+  const int R = blockDim.x / cv;
+  const int r = threadIdx.x / cv;
+  const int v = threadIdx.x - r * cv;
+  if (r >= R) return;
+  const int b = blockIdx.y;
+  const int s_begin = blockIdx.x * vox_per_cta;
+  const int s_end = min(S, s_begin + vox_per_cta);
+  float2 a[8];
+  const float2* sp = ss + static_cast<long long>(b) * ss_pitch + v * 8;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = __ldg(sp + j);
+  const __nv_bfloat16* xb = x + (static_cast<long long>(b) * S) * pitch + v * 8;
+  __nv_bfloat16* yb = y + (static_cast<long long>(b) * S) * y_pitch + v * 8;
+#pragma unroll 4
+  for (int i = s_begin + r; i < s_end; i += R) {
+    const uint4 u = *reinterpret_cast<const uint4*>(xb + static_cast<long long>(i) * pitch);
     const uint32_t w[4] = {u.x, u.y, u.z, u.w};
     uint32_t o[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float2 f = unpack_bf16x2(w[j]);
-      const float2 a0 = __ldg(sp + 2 * j), a1 = __ldg(sp + 2 * j + 1);
-      float y0 = fmaf(f.x, a0.x, a0.y), y1 = fmaf(f.y, a1.x, a1.y);
+      float y0 = fmaf(f.x, a[2 * j].x, a[2 * j].y), y1 = fmaf(f.y, a[2 * j + 1].x, a[2 * j + 1].y);
       if (act == CS_ACT_SILU) { y0 = silu_f(y0); y1 = silu_f(y1); }
       else if (act == CS_ACT_GELU) { y0 = gelu_erf_f(y0); y1 = gelu_erf_f(y1); }
       o[j] = pack_bf16x2(y0, y1);
     }
-    *reinterpret_cast<uint4*>(y + row * y_pitch + v * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<uint4*>(yb + static_cast<long long>(i) * y_pitch) = make_uint4(o[0], o[1], o[2], o[3]);
   }
 }
 
@@ -207,13 +216,17 @@ int gn_apply_launch(const void* x, int B, int S, int C, int pitch, const float* 
   if (C % 8 || pitch % 8 || y_pitch % 8 || reinterpret_cast<uintptr_t>(x) % 16 ||
       reinterpret_cast<uintptr_t>(y) % 16)
     return set_error(CS_ERR_INVALID, "groupnorm_apply: alignment");
-  const long long total = static_cast<long long>(B) * S * (C / 8);
-  long long blocks = (total + 255) / 256;
-  const long long cap = static_cast<long long>(num_sms()) * 16;
-  if (blocks > cap) blocks = cap;
-  gn_apply_kernel<<<static_cast<int>(blocks), 256, 0, st>>>(
+  if (C > 2048) return set_error(CS_ERR_INVALID, "groupnorm_apply: C <= 2048");
+  const int cv = C / 8;
+  int R = 256 / cv; if (R < 1) R = 1;
+  const int threads = ((R * cv + 31) / 32) * 32;
+  int splits = (8 * num_sms() + B - 1) / B;
+  int vox = (S + splits - 1) / splits;
+  if (vox < 4 * R) vox = 4 * R;
+  splits = (S + vox - 1) / vox;
+  gn_apply_kernel<<<dim3(splits, B), threads, 0, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(x), S, C, pitch, reinterpret_cast<const float2*>(scale_shift),
-      ss_pitch, reinterpret_cast<__nv_bfloat16*>(y), y_pitch, act, total);
+      ss_pitch, reinterpret_cast<__nv_bfloat16*>(y), y_pitch, act, vox);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error(e, "groupnorm_apply: launch");
   count_launch();

@@ -56,7 +56,10 @@ __global__ void vq_quantize_kernel(const float* __restrict__ z, const float* __r
   if (idx_out) idx_out[v] = best_j;
   float q[E];
 #pragma unroll
-  for (int e = 0; e < E; ++e) q[e] = codebook[static_cast<long long>(best_j) * E + e];
+  for (int e = 0; e < E; ++e) {
+    // forward value of the straight-through estimator, z + (z_q - z), in the reference's fp32 association
+    q[e] = zv[e] + (codebook[static_cast<long long>(best_j) * E + e] - zv[e]);
+  }
   if (pw) {  // post_quant_conv: out[c] = sum_e pw[c][e] q[e] + pb[c]
     for (int c = 0; c < Zc; ++c) {
       float acc = pb ? pb[c] : 0.f;

@@ -67,13 +67,14 @@ class FeedForward(nn.Module):
         self.net = nn.Sequential(GEGLU(dim, inner_dim), nn.Dropout(dropout), nn.Linear(inner_dim, dim_out))
 
     def pack(self):
-        return {"w1": ops.pack_linear_weight(self.net[0].proj.weight), "b1": self.net[0].proj.bias.detach().float().contiguous(),
+        w1, b1 = ops.pack_geglu_weight(self.net[0].proj.weight, self.net[0].proj.bias)
+        return {"w1": w1, "b1": b1,
                 "w2": ops.pack_linear_weight(self.net[2].weight), "b2": self.net[2].bias.detach().float().contiguous()}
 
     @staticmethod
     def run(pk, x_ln, residual):
-        h = ops.linear_tokens(x_ln, pk["w1"], bias=pk["b1"])
-        return ops.linear_tokens(ops.geglu(h), pk["w2"], bias=pk["b2"], residual=residual)
+        h = ops.linear_tokens(x_ln, pk["w1"], bias=pk["b1"], act=ops.ACT_GEGLU)     # x * gelu(gate) fused in the epilogue
+        return ops.linear_tokens(h, pk["w2"], bias=pk["b2"], residual=residual)
 
 
 class CrossAttention(nn.Module):

@@ -17,11 +17,11 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import (ACT_GELU, ACT_NONE, ACT_SILU, OUT_BF16_NDHWC, OUT_F32_NCDHW, OUT_F32_NDHWC,
+from ._lib import (ACT_GEGLU, ACT_GELU, ACT_NONE, ACT_SILU, OUT_BF16_NDHWC, OUT_F32_NCDHW, OUT_F32_NDHWC,
                    Conv3dArgs, check)
 
 __all__ = [
-    "ACT_NONE", "ACT_SILU", "ACT_GELU", "conv3d", "linear_tokens", "groupnorm", "layernorm", "attention",
+    "ACT_NONE", "ACT_SILU", "ACT_GELU", "ACT_GEGLU", "pack_geglu_weight", "conv3d", "linear_tokens", "groupnorm", "layernorm", "attention",
     "geglu", "upsample_nearest", "im2col_small", "timestep_embedding", "linear_small", "ddim_step",
     "q_sample", "to_channels_last", "to_ncdhw", "pack_conv_weight", "pack_linear_weight", "launch_count",
     "reset_launch_count", "zero_stat_buffer", "ConvProfiler", "vq_quantize", "channel_mix",
@@ -79,6 +79,17 @@ def pack_conv_weight(w: torch.Tensor) -> torch.Tensor:
     return w.detach().reshape(co, ci, -1).permute(0, 2, 1).contiguous().to(torch.bfloat16)
 
 
+def pack_geglu_weight(w: torch.Tensor, b: torch.Tensor):
+    """GEGLU projection (2*inner, in): reorder rows so every 32-column group of the GEMM output holds 16 value
+    columns followed by their 16 gate columns (what the ACT_GEGLU epilogue expects).  Returns (packed w, fp32 bias)."""
+    inner = w.shape[0] // 2
+    if inner % 16:
+        raise _lib.CsError("pack_geglu_weight: inner dim must be a multiple of 16")
+    idx = torch.arange(inner, device=w.device).view(-1, 16)
+    perm = torch.cat([idx, idx + inner], dim=1).reshape(-1)
+    return pack_linear_weight(w.detach()[perm]), b.detach().float()[perm].contiguous()
+
+
 def pack_linear_weight(w: torch.Tensor) -> torch.Tensor:
     """(out, in) fp32 -> (out, 1, in) bf16."""
     return w.detach().reshape(w.shape[0], 1, w.shape[1]).contiguous().to(torch.bfloat16)
@@ -133,13 +144,14 @@ def conv3d(x: torch.Tensor, weight: torch.Tensor, *, ksize: Sequence[int] = (3, 
             weight.shape[1] != kd * kh * kw or weight.shape[2] != C1 + C2:
         raise _lib.CsError(f"conv3d: packed weight must be bf16 (Cout, {kd * kh * kw}, {C1 + C2}), got {tuple(weight.shape)}")
     Cout = weight.shape[0]
+    Cres = Cout // 2 if act == ACT_GEGLU else Cout      # channels of the tensor written
     pb = tuple(pad) if pad_back is None else tuple(pad_back)
     Do = (D + pad[0] + pb[0] - kd) // stride[0] + 1
     Ho = (H + pad[1] + pb[1] - kh) // stride[1] + 1
     Wo = (W + pad[2] + pb[2] - kw) // stride[2] + 1
     if out is None:
         if out_mode == OUT_BF16_NDHWC:
-            out = torch.empty((B, Do, Ho, Wo, Cout), dtype=torch.bfloat16, device=x.device)
+            out = torch.empty((B, Do, Ho, Wo, Cres), dtype=torch.bfloat16, device=x.device)
         elif out_mode == OUT_F32_NCDHW:
             out = torch.empty((B, Cout, Do, Ho, Wo), dtype=torch.float32, device=x.device)
         else:
@@ -150,7 +162,7 @@ def conv3d(x: torch.Tensor, weight: torch.Tensor, *, ksize: Sequence[int] = (3, 
         out_pitch = 0
     else:
         want = torch.bfloat16 if out_mode == OUT_BF16_NDHWC else torch.float32
-        if out.dtype != want or tuple(out.shape) != (B, Do, Ho, Wo, Cout) or out.stride(-1) != 1:
+        if out.dtype != want or tuple(out.shape) != (B, Do, Ho, Wo, Cres) or out.stride(-1) != 1:
             raise _lib.CsError(f"conv3d: output must be {want} (B, Do, Ho, Wo, Cout)")
         out_pitch = out.stride(3)
     a = Conv3dArgs()

@@ -38,6 +38,8 @@ extern "C" {
 #define CS_ACT_NONE 0
 #define CS_ACT_SILU 1
 #define CS_ACT_GELU 2
+/* GEGLU: weight rows interleave 16 value / 16 gate columns; output has Cout/2 channels: v * gelu_erf(g) */
+#define CS_ACT_GEGLU 3
 
 typedef void* cs_stream_t; /* cudaStream_t */
 

@@ -282,3 +282,34 @@ def test_ddim_step_and_q_sample(ops):
     noise = torch.randn_like(x)
     ref = ac.sqrt()[t].view(-1, 1, 1, 1, 1) * x + (1 - ac).sqrt()[t].view(-1, 1, 1, 1, 1) * noise
     _report("q_sample", ops.q_sample(x, noise, t, ac.sqrt().contiguous(), (1 - ac).sqrt().contiguous()), ref, 1e-6, 1e-6)
+
+
+def test_linear_geglu_fused_epilogue(ops):
+    B, C = 2, 448
+    g = torch.Generator(device="cuda").manual_seed(21)
+    x = torch.randn(B, 16, 8, 8, C, device="cuda", generator=g)
+    w = torch.randn(8 * C, C, device="cuda", generator=g) / math.sqrt(C)
+    b = torch.randn(8 * C, device="cuda", generator=g)
+    a, gate = F.linear(_bf(x).float(), _bf(w).float(), b).chunk(2, dim=-1)
+    ref = a * F.gelu(gate)
+    wp, bp = ops.pack_geglu_weight(w, b)
+    got = ops.linear_tokens(_bf(x), wp, bias=bp, act=ops.ACT_GEGLU)
+    torch.cuda.synchronize()
+    assert got.shape[-1] == 4 * C
+    _report("geglu_fused", got.float(), ref, rtol=2 ** -7, atol=4e-3)
+
+
+def test_conv3d_residual_view_and_pitched_output(ops):
+    """Output / residual may be channel slices of wider buffers (row pitch > C)."""
+    B, C, D, H, W = 2, 224, 16, 8, 8
+    g = torch.Generator(device="cuda").manual_seed(22)
+    x = torch.randn(B, C, D, H, W, device="cuda", generator=g)
+    w = torch.randn(C, C, 3, 3, 3, device="cuda", generator=g) / math.sqrt(C * 27)
+    wide_res = _bf(torch.randn(B, D, H, W, 2 * C, device="cuda", generator=g))
+    wide_out = torch.zeros(B, D, H, W, 3 * C, device="cuda", dtype=torch.bfloat16)
+    res, out = wide_res[..., C:], wide_out[..., C:2 * C]
+    ops.conv3d(_cl(x), ops.pack_conv_weight(w), residual=res, out=out)
+    torch.cuda.synchronize()
+    ref = F.conv3d(_bf(x).float(), _bf(w).float(), None, padding=1) + res.float().permute(0, 4, 1, 2, 3)
+    _report("pitched", _ncdhw(out), ref, rtol=2 ** -7, atol=4e-3)
+    assert float(wide_out[..., :C].abs().max()) == 0.0 and float(wide_out[..., 2 * C:].abs().max()) == 0.0

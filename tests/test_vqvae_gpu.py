@@ -62,7 +62,7 @@ def test_quantizer_indices_and_post_quant(monkeypatch=None):
     same = (idx.cpu() == idx_ref).view(2, 1, 16, 16, 16).expand_as(zq_ref)
     assert torch.equal(zq.cpu()[same], zq_ref[same])
     zp, _ = ops.vq_quantize(z.cuda(), e.cuda(), pw.cuda(), pb.cuda())
-    ref = torch.einsum("oc,bcdhw->bodhw", pw, e[idx.cpu()].view(2, 16, 16, 16, 3).permute(0, 4, 1, 2, 3)) + pb[None, :, None, None, None]
+    ref = torch.einsum("oc,bcdhw->bodhw", pw, zq.cpu()) + pb[None, :, None, None, None]
     assert torch.allclose(zp.cpu(), ref, atol=1e-5)
     y = ops.channel_mix(z.cuda(), pw.cuda(), pb.cuda()).cpu()
     assert torch.allclose(y, torch.einsum("oc,bcdhw->bodhw", pw, z) + pb[None, :, None, None, None], atol=1e-5)

@@ -1,0 +1,43 @@
+"""Per-shape timing of the implicit-GEMM kernel on the conv / linear shapes of one UNet evaluation at batch 64
+(SURVEY.md Appendix A.1/A.2).  Prints TFLOP/s per shape; `--only i` runs a single shape (for ncu)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from commonscenes_b200 import ops
+
+B = 64
+SHAPES = [  # (Cin, Cout, (D,H,W), k, stride, count per UNet eval)
+    (224, 224, (16, 16, 16), 3, (1, 1, 1), 7), (448, 448, (16, 8, 8), 3, (1, 1, 1), 6), (672, 672, (16, 4, 4), 3, (1, 1, 1), 10),
+    (448, 448, (16, 16, 16), 3, (1, 1, 1), 1), (448, 224, (16, 16, 16), 3, (1, 1, 1), 2), (672, 224, (16, 16, 16), 3, (1, 1, 1), 1),
+    (1120, 448, (16, 8, 8), 3, (1, 1, 1), 1), (1344, 672, (16, 4, 4), 3, (1, 1, 1), 2), (672, 672, (16, 8, 8), 3, (1, 1, 1), 1),
+    (896, 448, (16, 8, 8), 3, (1, 1, 1), 1), (672, 448, (16, 8, 8), 3, (1, 1, 1), 1), (1120, 672, (16, 4, 4), 3, (1, 1, 1), 1),
+    (224, 448, (16, 8, 8), 3, (1, 1, 1), 1), (448, 672, (16, 4, 4), 3, (1, 1, 1), 1),
+    (224, 224, (16, 16, 16), 3, (1, 2, 2), 1), (448, 448, (16, 8, 8), 3, (1, 2, 2), 1),
+    (448, 3584, (16, 8, 8), 1, (1, 1, 1), 5), (448, 1536, (16, 8, 8), 1, (1, 1, 1), 5), (448, 448, (16, 8, 8), 1, (1, 1, 1), 15),
+    (1792, 448, (16, 8, 8), 1, (1, 1, 1), 5), (672, 5376, (16, 4, 4), 1, (1, 1, 1), 6), (672, 2304, (16, 4, 4), 1, (1, 1, 1), 6),
+    (672, 672, (16, 4, 4), 1, (1, 1, 1), 18), (2688, 672, (16, 4, 4), 1, (1, 1, 1), 6),
+]
+only = int(sys.argv[sys.argv.index("--only") + 1]) if "--only" in sys.argv else None
+reps = 1 if only is not None else 5
+tot_ms = tot_fl = 0.0
+for i, (ci, co, (D, H, W), k, st, cnt) in enumerate(SHAPES):
+    if only is not None and i != only:
+        continue
+    x = torch.randn(B, D, H, W, ci, device="cuda").to(torch.bfloat16)
+    w = (torch.randn(co, k ** 3, ci, device="cuda") / (ci * k ** 3) ** 0.5).to(torch.bfloat16)
+    b = torch.randn(co, device="cuda")
+    pad = (k // 2,) * 3
+    for _ in range(2):
+        y = ops.conv3d(x, w, ksize=(k, k, k), stride=st, pad=pad, bias=b)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        y = ops.conv3d(x, w, ksize=(k, k, k), stride=st, pad=pad, bias=b)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    fl = 2.0 * y.shape[0] * y.shape[1] * y.shape[2] * y.shape[3] * co * ci * k ** 3
+    tot_ms += ms * cnt; tot_fl += fl * cnt
+    print(f"[{i:2d}] {ci:5d}->{co:5d} k{k} s{st} @{D}x{H}x{W}: {ms:8.3f} ms  {fl / ms / 1e9:8.1f} TFLOP/s  x{cnt}  ({ms * cnt:7.2f} ms/eval)")
+if only is None:
+    print(f"sum over one UNet eval: {tot_ms:.2f} ms, {tot_fl / tot_ms / 1e9:.1f} TFLOP/s")
