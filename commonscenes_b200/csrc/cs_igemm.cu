@@ -560,7 +560,8 @@ int igemm_launch(const IgemmArgs& a, cudaStream_t stream) {
     if (rc) return rc;
   }
 
-  p.fast_epilogue = (p.out_mode == CS_OUT_BF16_NDHWC && a.Cout % 8 == 0 && p.bb == 1) ? 1 : 0;
+  // tiles that span several samples (tiny grids) can use it when nothing in the epilogue is per-sample
+  p.fast_epilogue = (p.out_mode == CS_OUT_BF16_NDHWC && a.Cout % 8 == 0 && (p.bb == 1 || (!p.rowvec && !p.stat_sum))) ? 1 : 0;
   if (p.act == CS_ACT_GEGLU && (!p.fast_epilogue || bn % 32 || a.Cout % 32 || p.residual || p.stat_sum))
     return set_error(CS_ERR_INVALID, "igemm: GEGLU epilogue needs bf16 output, Cout % 32 == 0 and no residual/stats");
   static int attr_smem = 0;
