@@ -61,6 +61,7 @@ SIGNATURES = {
     "cs_ncdhw_to_ndhwc": (_i32, [_vp, _i32, _i32, _i64, _i32, _vp, _vp]),
     "cs_ndhwc_to_ncdhw": (_i32, [_vp, _i32, _i32, _i64, _i32, _vp, _vp]),
     "cs_channel_mix": (_i32, [_vp, _i32, _i32, _i32, _i64, _vp, _vp, _vp, _vp]),
+    "cs_tap_gather": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "cs_vq_quantize": (_i32, [_vp, _i32, _i32, _i64, _vp, _i32, _vp, _vp, _i32, _vp, _vp, _vp]),
 }
 

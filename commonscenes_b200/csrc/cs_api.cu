@@ -27,6 +27,7 @@ int q_sample_launch(const float*, const float*, const long long*, const float*, 
 int ncdhw_to_ndhwc_launch(const float*, int, int, long long, int, void*, cudaStream_t);
 int ndhwc_to_ncdhw_launch(const void*, int, int, long long, int, float*, cudaStream_t);
 int channel_mix_launch(const float*, int, int, int, long long, const float*, const float*, float*, cudaStream_t);
+int tap_gather_launch(const float*, int, int, int, int, int, int, const float*, float*, cudaStream_t);
 int vq_quantize_launch(const float*, int, int, long long, const float*, int, const float*, const float*, int, float*,
                        long long*, cudaStream_t);
 }  // namespace cs
@@ -143,6 +144,11 @@ int cs_vq_quantize(const float* z, int32_t B, int32_t E, int64_t Sp, const float
 int cs_channel_mix(const float* x, int32_t B, int32_t Ci, int32_t Co, int64_t Sp, const float* w, const float* bias,
                    float* y, cs_stream_t stream) {
   return cs::channel_mix_launch(x, B, Ci, Co, Sp, w, bias, y, S(stream));
+}
+
+int cs_tap_gather(const float* y, int32_t B, int32_t Cy, int32_t Co, int32_t D, int32_t H, int32_t W, const float* bias,
+                  float* out, cs_stream_t stream) {
+  return cs::tap_gather_launch(y, B, Cy, Co, D, H, W, bias, out, S(stream));
 }
 
 }  // extern "C"

@@ -80,13 +80,18 @@ __device__ __forceinline__ void epilogue_fast_tile(const IgemmParams& p, uint32_
     // residual: coalesced global -> swizzled staging, while the TMEM loads are in flight
     if (p.residual) {
       const __nv_bfloat16* rbase = reinterpret_cast<const __nv_bfloat16*>(p.residual);
+      uint4 rr[8];                                              // all eight loads in flight before any store
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
         const int r = it * 4 + (lane >> 3), ch = lane & 7;
-        if (r < rows_valid && ch * 8 < ncols) {
-          const uint4 u = *reinterpret_cast<const uint4*>(rbase + (m_w0 + r) * p.res_pitch + n + ch * 8);
-          *reinterpret_cast<uint4*>(stage + r * 128 + ((ch ^ (r & 7)) << 4)) = u;
-        }
+        rr[it] = make_uint4(0u, 0u, 0u, 0u);
+        if (r < rows_valid && ch * 8 < ncols)
+          rr[it] = __ldg(reinterpret_cast<const uint4*>(rbase + (m_w0 + r) * p.res_pitch + n + ch * 8));
+      }
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int r = it * 4 + (lane >> 3), ch = lane & 7;
+        *reinterpret_cast<uint4*>(stage + r * 128 + ((ch ^ (r & 7)) << 4)) = rr[it];
       }
       __syncwarp();
     }
@@ -163,13 +168,17 @@ __device__ __forceinline__ void epilogue_fast_tile(const IgemmParams& p, uint32_
     }
     __syncwarp();
     __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(p.out);
+    uint4 oo[8];
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
       const int r = it * 4 + (lane >> 3), ch = lane & 7;
-      if (r < rows_valid && ch < out_chunks) {
-        const uint4 u = *reinterpret_cast<const uint4*>(stage + r * 128 + ((ch ^ (r & 7)) << 4));
-        *reinterpret_cast<uint4*>(obase + (m_w0 + r) * p.out_pitch + out_n + ch * 8) = u;
-      }
+      oo[it] = *reinterpret_cast<const uint4*>(stage + r * 128 + ((ch ^ (r & 7)) << 4));
+    }
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int r = it * 4 + (lane >> 3), ch = lane & 7;
+      if (r < rows_valid && ch < out_chunks)
+        *reinterpret_cast<uint4*>(obase + (m_w0 + r) * p.out_pitch + out_n + ch * 8) = oo[it];
     }
     __syncwarp();
     (void)stage_u;

@@ -326,4 +326,52 @@ int channel_mix_launch(const float* x, int B, int Ci, int Co, long long S, const
   CS_LAUNCH_CHECK("channel_mix");
 }
 
+// ------------------------------------------------------------------------------------------------
+// Few-output-channel 3x3x3 convolution, second half.  A conv is linear in its taps:
+//   out[m] = bias + sum_tap W_tap x[m + d_tap] = bias + sum_tap (W_tap x)[m + d_tap]
+// so for Cout <= 4 (UNet head 224->3, VQ-VAE conv_out 64->1 / 256->3) the tensor-core GEMM computes
+// Y[b][tap*Co + co][voxel] = W_tap[co] . x[voxel] ONCE per voxel (no 27x re-read of the input through a
+// 16-column tile), and this kernel gathers the 27 shifted planes.  Y and out are fp32 NCDHW; zero padding 1.
+__global__ void tap_gather_kernel(const float* __restrict__ y, int Cy, int Co, int D, int H, int W, long long total,
+                                  const float* __restrict__ bias, float* __restrict__ out) {
+  const long long S = static_cast<long long>(D) * H * W;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    long long r = i;
+    const int w = static_cast<int>(r % W); r /= W;
+    const int h = static_cast<int>(r % H); r /= H;
+    const int d = static_cast<int>(r % D); r /= D;
+    const long long b = r;
+    const long long s = i - b * S;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const float* yb = y + b * Cy * S;
+#pragma unroll
+    for (int zd = 0; zd < 3; ++zd) {
+      const int dd = d + zd - 1;
+      if (dd < 0 || dd >= D) continue;
+#pragma unroll
+      for (int zh = 0; zh < 3; ++zh) {
+        const int hh = h + zh - 1;
+        if (hh < 0 || hh >= H) continue;
+#pragma unroll
+        for (int zw = 0; zw < 3; ++zw) {
+          const int ww = w + zw - 1;
+          if (ww < 0 || ww >= W) continue;
+          const int tap = (zd * 3 + zh) * 3 + zw;
+          const long long sp = (static_cast<long long>(dd) * H + hh) * W + ww;
+          for (int co = 0; co < Co; ++co) acc[co] += __ldg(yb + (tap * Co + co) * S + sp);
+        }
+      }
+    }
+    for (int co = 0; co < Co; ++co) out[(b * Co + co) * S + s] = acc[co] + (bias ? bias[co] : 0.f);
+  }
+}
+int tap_gather_launch(const float* y, int B, int Cy, int Co, int D, int H, int W, const float* bias, float* out,
+                      cudaStream_t st) {
+  if (Co < 1 || Co > 4 || Cy < 27 * Co) return set_error(CS_ERR_INVALID, "tap_gather: 1 <= Co <= 4 and Cy >= 27*Co");
+  const long long total = static_cast<long long>(B) * D * H * W;
+  tap_gather_kernel<<<grid_for(total, 256, 8), 256, 0, st>>>(y, Cy, Co, D, H, W, total, bias, out);
+  CS_LAUNCH_CHECK("tap_gather");
+}
+
 }  // namespace cs

@@ -266,7 +266,7 @@ class UNet3DModel(nn.Module):
         pk["emb_w"], pk["emb_b"] = torch.cat(emb_w).contiguous(), torch.cat(emb_b).contiguous()
         pk["ca_w"], pk["ca_b"] = torch.cat(ca_w).contiguous(), torch.cat(ca_b).contiguous()
         pk["out_gn"] = (_f(self.out[0].weight), _f(self.out[0].bias))
-        pk["out_w"], pk["out_b"] = ops.pack_conv_weight(self.out[2].weight), _f(self.out[2].bias)
+        pk["out_w"], pk["out_b"] = ops.pack_small_cout_conv(self.out[2].weight), _f(self.out[2].bias)
         self._packed, self._packed_key = pk, self._version_key()
         self._pack_generation = getattr(self, "_pack_generation", 0) + 1
 
@@ -334,4 +334,4 @@ class UNet3DModel(nn.Module):
         for i, block in enumerate(self.output_blocks):
             h = run_block(block, entries[n_in + 1 + i], h, skip=hs.pop())    # th.cat([h, hs.pop()], dim=1), never materialised raw
         a = ops.groupnorm(h, *pk["out_gn"], eps=self.out[0].eps, act=ops.ACT_SILU)
-        return ops.conv3d(a, pk["out_w"], bias=pk["out_b"], out_mode=_lib.OUT_F32_NCDHW)
+        return ops.conv3d_small_cout(a, pk["out_w"], pk["out_b"], self.out_channels)

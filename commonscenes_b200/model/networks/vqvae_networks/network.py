@@ -59,13 +59,13 @@ class VQVAE(nn.Module):
             wq2 = wq.reshape(wq.shape[0], wq.shape[1])
             w = torch.einsum("oz,zcdhw->ocdhw", wq2, wc).float()
             b = (wq2 @ bc + bq).float().contiguous()
-            self._enc_out = (key, ops.pack_conv_weight(w), b)
+            self._enc_out = (key, ops.pack_small_cout_conv(w), b)
         return self._enc_out[1], self._enc_out[2]
 
     @torch.no_grad()
     def encode_no_quant(self, x):
         w, b = self._encoder_head()
-        return ops.conv3d(self.encoder.run_trunk(x), w, bias=b, out_mode=_lib.OUT_F32_NCDHW)
+        return ops.conv3d_small_cout(self.encoder.run_trunk(x), w, b, self.embed_dim)
 
     @torch.no_grad()
     def encode(self, x):

@@ -216,7 +216,8 @@ class Encoder3D(_Packed):
     @torch.no_grad()
     def forward(self, x):
         a = self.run_trunk(x)
-        return ops.conv3d(a, ops.pack_conv_weight(self.conv_out.weight), bias=_f(self.conv_out.bias), out_mode=_lib.OUT_F32_NCDHW)
+        return ops.conv3d_small_cout(a, ops.pack_small_cout_conv(self.conv_out.weight), _f(self.conv_out.bias),
+                                     self.conv_out.weight.shape[0])
 
 
 class Decoder3D(_Packed):
@@ -255,7 +256,7 @@ class Decoder3D(_Packed):
         self.conv_out = torch.nn.Conv3d(block_in, out_ch, kernel_size=3, stride=1, padding=1)
 
     def pack(self):
-        return {"in": _small_cin_conv_pack(self.conv_in), "out": (ops.pack_conv_weight(self.conv_out.weight), _f(self.conv_out.bias))}
+        return {"in": _small_cin_conv_pack(self.conv_in), "out": (ops.pack_small_cout_conv(self.conv_out.weight), _f(self.conv_out.bias))}
 
     @torch.no_grad()
     def forward(self, z):
@@ -271,4 +272,4 @@ class Decoder3D(_Packed):
             if i_level != 0:
                 h = self.up[i_level].upsample.run(h)
         wo, bo = pk["out"]
-        return ops.conv3d(_gn(self.norm_out, h, ops.ACT_GELU), wo, bias=bo, out_mode=_lib.OUT_F32_NCDHW)
+        return ops.conv3d_small_cout(_gn(self.norm_out, h, ops.ACT_GELU), wo, bo, self.conv_out.weight.shape[0])

@@ -24,7 +24,7 @@ __all__ = [
     "ACT_NONE", "ACT_SILU", "ACT_GELU", "ACT_GEGLU", "pack_geglu_weight", "conv3d", "linear_tokens", "groupnorm", "layernorm", "attention",
     "geglu", "upsample_nearest", "im2col_small", "timestep_embedding", "linear_small", "ddim_step",
     "q_sample", "to_channels_last", "to_ncdhw", "pack_conv_weight", "pack_linear_weight", "launch_count",
-    "reset_launch_count", "zero_stat_buffer", "ConvProfiler", "vq_quantize", "channel_mix",
+    "reset_launch_count", "zero_stat_buffer", "ConvProfiler", "vq_quantize", "channel_mix", "pack_small_cout_conv", "conv3d_small_cout",
 ]
 
 
@@ -425,3 +425,23 @@ def channel_mix(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] =
     check(_lib.load().cs_channel_mix(x.data_ptr(), B, Ci, w.shape[0], S, w.data_ptr(), _ptr(_f32(bias, "bias")),
                                      y.data_ptr(), _stream()), "cs_channel_mix")
     return y
+
+
+def pack_small_cout_conv(w: torch.Tensor):
+    """(Co <= 4, Cin, 3, 3, 3) -> per-tap GEMM weight (27*Co padded to 16, 1, Cin) bf16: row tap*Co + co = w[co, :, tap]."""
+    co, ci = w.shape[0], w.shape[1]
+    rows = (27 * co + 15) // 16 * 16
+    wt = torch.zeros(rows, 1, ci, dtype=torch.float32, device=w.device)
+    wt[:27 * co, 0] = w.detach().float().reshape(co, ci, 27).permute(2, 0, 1).reshape(27 * co, ci)
+    return wt.to(torch.bfloat16)
+
+
+def conv3d_small_cout(x: torch.Tensor, w_taps: torch.Tensor, bias: Optional[torch.Tensor], cout: int) -> torch.Tensor:
+    """3x3x3 / pad 1 conv to <= 4 channels: one tensor-core GEMM over the taps + a gather of the 27 shifted planes.
+    x: channels-last bf16 (B, D, H, W, Cin) -> fp32 NCDHW (B, cout, D, H, W)."""
+    B, D, H, W, _, _ = _check_act(x, "conv3d_small_cout.x")
+    y = conv3d(x, w_taps, ksize=(1, 1, 1), pad=(0, 0, 0), out_mode=OUT_F32_NCDHW)
+    out = torch.empty((B, cout, D, H, W), dtype=torch.float32, device=x.device)
+    check(_lib.load().cs_tap_gather(y.data_ptr(), B, y.shape[1], cout, D, H, W, _ptr(_f32(bias, "bias")), out.data_ptr(),
+                                    _stream()), "cs_tap_gather")
+    return out

@@ -137,6 +137,12 @@ int cs_vq_quantize(const float* z, int32_t B, int32_t E, int64_t S, const float*
 int cs_channel_mix(const float* x, int32_t B, int32_t Ci, int32_t Co, int64_t S, const float* w, const float* bias,
                    float* y, cs_stream_t stream);
 
+/* second half of a 3x3x3 / pad-1 convolution with <= 4 output channels (openai_model_3d.py:727, vqvae_modules.py:370-374):
+ * y fp32 [B][Cy][D][H][W] holds the per-tap products y[b][tap*Co+co][v] = W_tap[co] . x[v] (one cs_conv3d k=1 GEMM);
+ * out[b][co][v] = bias[co] + sum_tap y[b][tap*Co+co][v + offset(tap)] */
+int cs_tap_gather(const float* y, int32_t B, int32_t Cy, int32_t Co, int32_t D, int32_t H, int32_t W, const float* bias,
+                  float* out, cs_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -313,3 +313,16 @@ def test_conv3d_residual_view_and_pitched_output(ops):
     ref = F.conv3d(_bf(x).float(), _bf(w).float(), None, padding=1) + res.float().permute(0, 4, 1, 2, 3)
     _report("pitched", _ncdhw(out), ref, rtol=2 ** -7, atol=4e-3)
     assert float(wide_out[..., :C].abs().max()) == 0.0 and float(wide_out[..., 2 * C:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("cin,cout,res", [(224, 3, 16), (64, 1, 32), (256, 3, 16)], ids=["unet_head", "vq_dec_out", "vq_enc_out"])
+def test_conv3d_small_cout_tap_gemm_gather(ops, cin, cout, res):
+    B = 2
+    g = torch.Generator(device="cuda").manual_seed(31)
+    x = torch.randn(B, cin, res, res, res, device="cuda", generator=g)
+    w = torch.randn(cout, cin, 3, 3, 3, device="cuda", generator=g) / math.sqrt(cin * 27)
+    b = torch.randn(cout, device="cuda", generator=g)
+    ref = F.conv3d(_bf(x).float(), _bf(w).float(), b, padding=1)
+    got = ops.conv3d_small_cout(_cl(x), ops.pack_small_cout_conv(w), b, cout)
+    torch.cuda.synchronize()
+    _report("small_cout", got, ref, rtol=1e-4, atol=2e-4)
