@@ -17,15 +17,15 @@
 // fp32 accumulator with tcgen05.ld and apply bias / per-sample vector / residual / activation and
 // (optionally) accumulate the GroupNorm statistics of the result.
 //
-// Roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
-// warps 2-5 = epilogue.  Persistent over tiles; TMEM accumulator is double buffered so the
+// Roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2-9 = epilogue (two warps per TMEM lane quarter, each draining alternate 32-column chunks).  Persistent over tiles; TMEM accumulator is double buffered so the
 // epilogue of tile i overlaps the main loop of tile i+1.
 #include "cs_common.cuh"
 #include "cs_igemm.cuh"
 
 namespace cs {
 
-static constexpr int kIgemmThreads = 192;
+static constexpr int kIgemmThreads = 320;  // TMA warp + MMA warp + 8 epilogue warps (two per TMEM lane quarter)
 static constexpr int kMaxStages = 8;
 static constexpr int kABytes = 128 * 128;  // 128 voxels x 64 bf16
 
@@ -35,7 +35,7 @@ struct __align__(8) IgemmBarriers {
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
   uint32_t tmem_base;
-  float colvec[2][256];  // per accumulator buffer: bias + per-sample vector of the tile's columns
+  __align__(16) float colvec[2][256];  // per accumulator buffer: bias + per-sample vector of the tile's columns
 };
 
 
@@ -61,51 +61,71 @@ __device__ __forceinline__ void colsum32(float (&a)[32], int lane) {
   }
 }
 
-__device__ __forceinline__ void epilogue_fast_tile(const IgemmParams& p, uint32_t t_row, int lane, int warp_rows0,
-                                                   long long m_tile0, int b, int n0, const float* colvec,
-                                                   uint8_t* stage) {
-  // warp_rows0: first accumulator row of this warp inside the tile; m_tile0: global row of the tile's row 0
+// erf via Abramowitz-Stegun 7.1.26 (|abs err| < 1.5e-7, far below the bf16 rounding of the result): one exp,
+// one reciprocal and five FMAs instead of libdevice's erff -- the GEGLU epilogue evaluates it 112 times per row.
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float erf_abs = 1.f - poly * t * __expf(-z * z);
+  return 0.5f * x * (1.f + copysignf(erf_abs, x));
+}
+
+__device__ __forceinline__ void epilogue_fast_tile(const IgemmParams& p, uint32_t t_row, int lane, int half,
+                                                   int warp_rows0, long long m_tile0, int b, int n0,
+                                                   const float* __restrict__ colvec, uint8_t* __restrict__ stage) {
+  // warp_rows0: first accumulator row of this warp inside the tile; m_tile0: global row of the tile's row 0.
+  // Two warps share each 32-row quarter: `half` selects the even / odd 32-column chunks.
   const int rows_valid = min(32, p.rows - warp_rows0);          // <= 0: nothing to do for this warp
   const long long m_w0 = m_tile0 + warp_rows0;
   const bool geglu = (p.act == CS_ACT_GEGLU);
-  const uint32_t stage_u = smem_u32(stage);
-  for (int c0 = 0; c0 < p.BN; c0 += 64) {
+  const int sw = (lane >> 1) & 3;                               // XOR swizzle of this lane's staging row (64-byte rows)
+  for (int c0 = half * 32; c0 < p.BN; c0 += 64) {
     const int n = n0 + c0;
     if (n >= p.Cout) break;                                     // warp-uniform
-    const int ncols = min(64, min(p.BN - c0, p.Cout - n));      // multiple of 8 (16 for the TMEM loads below)
-    uint32_t raw[4][16];
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-      if (q * 16 < ncols) tmem_ld16(t_row + static_cast<uint32_t>(c0 + q * 16), raw[q]);
+    const int ncols = min(32, min(p.BN - c0, p.Cout - n));      // 8, 16, 24 or 32
+    uint32_t raw[2][16];
+    tmem_ld16(t_row + static_cast<uint32_t>(c0), raw[0]);
+    if (ncols > 16) tmem_ld16(t_row + static_cast<uint32_t>(c0 + 16), raw[1]);
     // residual: coalesced global -> swizzled staging, while the TMEM loads are in flight
     if (p.residual) {
       const __nv_bfloat16* rbase = reinterpret_cast<const __nv_bfloat16*>(p.residual);
-      uint4 rr[8];                                              // all eight loads in flight before any store
+      uint4 rr[4];
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int r = it * 4 + (lane >> 3), ch = lane & 7;
+      for (int it = 0; it < 4; ++it) {
+        const int r = it * 8 + (lane >> 2), ch = lane & 3;
         rr[it] = make_uint4(0u, 0u, 0u, 0u);
         if (r < rows_valid && ch * 8 < ncols)
           rr[it] = __ldg(reinterpret_cast<const uint4*>(rbase + (m_w0 + r) * p.res_pitch + n + ch * 8));
       }
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int r = it * 4 + (lane >> 3), ch = lane & 7;
-        *reinterpret_cast<uint4*>(stage + r * 128 + ((ch ^ (r & 7)) << 4)) = rr[it];
+      for (int it = 0; it < 4; ++it) {
+        const int r = it * 8 + (lane >> 2), ch = lane & 3;
+        *reinterpret_cast<uint4*>(stage + r * 64 + ((ch ^ ((r >> 1) & 3)) << 4)) = rr[it];
       }
       __syncwarp();
     }
     tmem_ld_wait();
-    float v[64];
+    float v[32];
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
+    for (int q = 0; q < 2; ++q)
 #pragma unroll
-      for (int j = 0; j < 16; ++j) v[q * 16 + j] = (q * 16 < ncols) ? __uint_as_float(raw[q][j]) + colvec[c0 + q * 16 + j] : 0.f;
+      for (int j4 = 0; j4 < 4; ++j4) {
+        const float4 cvv = *reinterpret_cast<const float4*>(colvec + c0 + q * 16 + j4 * 4);
+        const bool on = (q * 16 < ncols);
+        v[q * 16 + j4 * 4 + 0] = on ? __uint_as_float(raw[q][j4 * 4 + 0]) + cvv.x : 0.f;
+        v[q * 16 + j4 * 4 + 1] = on ? __uint_as_float(raw[q][j4 * 4 + 1]) + cvv.y : 0.f;
+        v[q * 16 + j4 * 4 + 2] = on ? __uint_as_float(raw[q][j4 * 4 + 2]) + cvv.z : 0.f;
+        v[q * 16 + j4 * 4 + 3] = on ? __uint_as_float(raw[q][j4 * 4 + 3]) + cvv.w : 0.f;
+      }
     if (p.residual) {
 #pragma unroll
-      for (int ch = 0; ch < 8; ++ch) {
+      for (int ch = 0; ch < 4; ++ch) {
         if (ch * 8 < ncols) {
-          const uint4 u = *reinterpret_cast<const uint4*>(stage + lane * 128 + ((ch ^ (lane & 7)) << 4));
+          const uint4 u = *reinterpret_cast<const uint4*>(stage + lane * 64 + ((ch ^ sw) << 4));
           const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -119,69 +139,58 @@ __device__ __forceinline__ void epilogue_fast_tile(const IgemmParams& p, uint32_
     }
     if (p.act == CS_ACT_SILU) {
 #pragma unroll
-      for (int j = 0; j < 64; ++j) v[j] = silu_f(v[j]);
+      for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
     } else if (p.act == CS_ACT_GELU) {
 #pragma unroll
-      for (int j = 0; j < 64; ++j) v[j] = gelu_erf_f(v[j]);
+      for (int j = 0; j < 32; ++j) v[j] = gelu_erf_f(v[j]);
     }
     int out_cols = ncols, out_n = n;
     if (geglu) {
-      // packed weight rows interleave 16 value / 16 gate columns: out[16g + j] = v[32g + j] * gelu(v[32g + 16 + j])
+      // packed weight rows interleave 16 value / 16 gate columns: out[j] = v[j] * gelu(v[16 + j])
 #pragma unroll
-      for (int g = 0; g < 2; ++g)
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[16 * g + j] = v[32 * g + j] * gelu_erf_f(v[32 * g + 16 + j]);
+      for (int j = 0; j < 16; ++j) v[j] = v[j] * gelu_erf_fast(v[16 + j]);
       out_cols = ncols >> 1;
       out_n = n >> 1;
     }
     if (p.stat_sum) {
-      if (lane >= rows_valid) {
+      float a[32], q2[32];
+      const bool live = lane < rows_valid;                      // rows past a short tile must not be summed
 #pragma unroll
-        for (int j = 0; j < 64; ++j) v[j] = 0.f;               // rows past a short tile must not be summed
-      }
-#pragma unroll
-      for (int hblk = 0; hblk < 2; ++hblk) {
-        if (hblk * 32 < out_cols) {
-          float a[32], q2[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) { a[j] = v[hblk * 32 + j]; q2[j] = a[j] * a[j]; }
-          colsum32(a, lane);
-          colsum32(q2, lane);
-          if (hblk * 32 + lane < out_cols && rows_valid > 0) {
-            float* sp = p.stat_sum + (static_cast<long long>(b) * p.stat_pitch + out_n + hblk * 32 + lane) * 2;
-            atomicAdd(sp, a[0]);
-            atomicAdd(sp + 1, q2[0]);
-          }
-        }
+      for (int j = 0; j < 32; ++j) { a[j] = live ? v[j] : 0.f; q2[j] = a[j] * a[j]; }
+      colsum32(a, lane);
+      colsum32(q2, lane);
+      if (lane < out_cols && rows_valid > 0) {
+        float* sp = p.stat_sum + (static_cast<long long>(b) * p.stat_pitch + out_n + lane) * 2;
+        atomicAdd(sp, a[0]);
+        atomicAdd(sp + 1, q2[0]);
       }
     }
     // pack -> swizzled staging -> coalesced global stores
-    const int out_chunks = out_cols >> 3;                       // 16-byte chunks per row
+    const int out_chunks = out_cols >> 3;                       // 16-byte chunks per row (1..4)
 #pragma unroll
-    for (int ch = 0; ch < 8; ++ch) {
+    for (int ch = 0; ch < 4; ++ch) {
       if (ch < out_chunks) {
         uint4 u;
         u.x = pack_bf16x2(v[ch * 8 + 0], v[ch * 8 + 1]); u.y = pack_bf16x2(v[ch * 8 + 2], v[ch * 8 + 3]);
         u.z = pack_bf16x2(v[ch * 8 + 4], v[ch * 8 + 5]); u.w = pack_bf16x2(v[ch * 8 + 6], v[ch * 8 + 7]);
-        *reinterpret_cast<uint4*>(stage + lane * 128 + ((ch ^ (lane & 7)) << 4)) = u;
+        *reinterpret_cast<uint4*>(stage + lane * 64 + ((ch ^ sw) << 4)) = u;
       }
     }
     __syncwarp();
     __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(p.out);
-    uint4 oo[8];
+    uint4 oo[4];
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int r = it * 4 + (lane >> 3), ch = lane & 7;
-      oo[it] = *reinterpret_cast<const uint4*>(stage + r * 128 + ((ch ^ (r & 7)) << 4));
+    for (int it = 0; it < 4; ++it) {
+      const int r = it * 8 + (lane >> 2), ch = lane & 3;
+      oo[it] = *reinterpret_cast<const uint4*>(stage + r * 64 + ((ch ^ ((r >> 1) & 3)) << 4));
     }
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int r = it * 4 + (lane >> 3), ch = lane & 7;
+    for (int it = 0; it < 4; ++it) {
+      const int r = it * 8 + (lane >> 2), ch = lane & 3;
       if (r < rows_valid && ch < out_chunks)
         *reinterpret_cast<uint4*>(obase + (m_w0 + r) * p.out_pitch + out_n + ch * 8) = oo[it];
     }
     __syncwarp();
-    (void)stage_u;
   }
 }
 
@@ -214,7 +223,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&bars.tmem_full[a], 1);
-      mbar_init(&bars.tmem_empty[a], 4);
+      mbar_init(&bars.tmem_empty[a], 8);
     }
     fence_mbar_init();
   }
@@ -314,9 +323,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
     int acc = 0;
     uint32_t acc_phase = 0;
     const long long spatial = static_cast<long long>(p.Do) * p.Ho * p.Wo;
+    const int half = (warp - 2) >> 2;  // fast path: which 32-column chunks this warp drains; generic path: half 1 idles
     if (p.fast_epilogue) {
-      uint8_t* stage = smem + p.stages * stage_bytes + (warp - 2) * 4096;
-      const int et = threadIdx.x - 64;                           // 0..127 among the epilogue threads
+      uint8_t* stage = smem + p.stages * stage_bytes + (warp - 2) * 2048;
+      const int et = threadIdx.x - 64;                           // 0..255 among the epilogue threads
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int nt = tile % p.n_tiles;
         const int mt = tile / p.n_tiles;
@@ -324,7 +334,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
         const int b = static_cast<int>(m_tile0 / spatial);               // one sample per tile (bb == 1)
         const int n0 = nt * p.BN;
         // column vector for this tile (bias + per-sample vector), double buffered with the accumulator
-        for (int c = et; c < p.BN; c += 128) {
+        for (int c = et; c < p.BN; c += 256) {
           float cv = 0.f;
           if (n0 + c < p.Cout) {
             if (p.bias) cv += __ldg(p.bias + n0 + c);
@@ -332,11 +342,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
           }
           bars.colvec[acc][c] = cv;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         mbar_wait(&bars.tmem_full[acc], acc_phase);
         tc_fence_after();
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * 256);
-        epilogue_fast_tile(p, t_row, lane, quarter * 32, m_tile0, b, n0, bars.colvec[acc], stage);
+        epilogue_fast_tile(p, t_row, lane, half, quarter * 32, m_tile0, b, n0, bars.colvec[acc], stage);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars.tmem_empty[acc]);
@@ -363,7 +373,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                              static_cast<uint32_t>(acc * 256);
-      for (int c0 = 0; c0 < p.BN; c0 += 16) {
+      for (int c0 = 0; c0 < p.BN && half == 0; c0 += 16) {
         if (n0 + c0 >= p.Cout) break;  // warp-uniform
         uint32_t raw[16];
         tmem_ld16(t_row + static_cast<uint32_t>(c0), raw);
@@ -528,7 +538,7 @@ int igemm_launch(const IgemmArgs& a, cudaStream_t stream) {
   p.m_tiles = (p.B / p.bb) * (p.Do / p.bd) * (p.Ho / p.bh) * (p.Wo / p.bw);
   const int stage_bytes = kABytes + bn * 128;
   // 227 KB per CTA minus the kernel's static shared memory (barriers) and the 1 KB alignment slack
-  const int smem_budget = 227 * 1024 - 4096 - 4 * 4096;  // 4 x 4 KB epilogue staging buffers
+  const int smem_budget = 227 * 1024 - 4096 - 8 * 2048;  // 8 x 2 KB epilogue staging buffers
   int stages = smem_budget / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return set_error(CS_ERR_INVALID, "igemm: tile too large for shared memory");
@@ -574,7 +584,7 @@ int igemm_launch(const IgemmArgs& a, cudaStream_t stream) {
   if (p.act == CS_ACT_GEGLU && (!p.fast_epilogue || bn % 32 || a.Cout % 32 || p.residual || p.stat_sum))
     return set_error(CS_ERR_INVALID, "igemm: GEGLU epilogue needs bf16 output, Cout % 32 == 0 and no residual/stats");
   static int attr_smem = 0;
-  const int smem_bytes = stages * stage_bytes + 4 * 4096 + 1024;
+  const int smem_bytes = stages * stage_bytes + 8 * 2048 + 1024;
   if (smem_bytes > attr_smem) {
     cudaError_t e = cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return set_cuda_error(e, "igemm: cudaFuncSetAttribute");

@@ -58,6 +58,8 @@ class GEGLU(nn.Module):
 
 
 class FeedForward(nn.Module):
+    FUSE_GEGLU = False
+
     def __init__(self, dim, dim_out=None, mult=4, glu=False, dropout=0.):
         super().__init__()
         if not glu:
@@ -67,13 +69,22 @@ class FeedForward(nn.Module):
         self.net = nn.Sequential(GEGLU(dim, inner_dim), nn.Dropout(dropout), nn.Linear(inner_dim, dim_out))
 
     def pack(self):
-        w1, b1 = ops.pack_geglu_weight(self.net[0].proj.weight, self.net[0].proj.bias)
-        return {"w1": w1, "b1": b1,
+        # FUSE_GEGLU: x * gelu(gate) inside the GEMM epilogue (ACT_GEGLU).  Measured on B200 at batch 64 the K=448/672
+        # projection is epilogue-bound, and 112 erf evaluations per accumulator row on 8 epilogue warps cost more
+        # (454 us) than the plain GEMM (264 us) plus the bandwidth-bound cs_geglu pass (110 us): off by default.
+        if FeedForward.FUSE_GEGLU:
+            w1, b1 = ops.pack_geglu_weight(self.net[0].proj.weight, self.net[0].proj.bias)
+        else:
+            w1, b1 = ops.pack_linear_weight(self.net[0].proj.weight), self.net[0].proj.bias.detach().float().contiguous()
+        return {"w1": w1, "b1": b1, "fused": FeedForward.FUSE_GEGLU,
                 "w2": ops.pack_linear_weight(self.net[2].weight), "b2": self.net[2].bias.detach().float().contiguous()}
 
     @staticmethod
     def run(pk, x_ln, residual):
-        h = ops.linear_tokens(x_ln, pk["w1"], bias=pk["b1"], act=ops.ACT_GEGLU)     # x * gelu(gate) fused in the epilogue
+        if pk["fused"]:
+            h = ops.linear_tokens(x_ln, pk["w1"], bias=pk["b1"], act=ops.ACT_GEGLU)
+        else:
+            h = ops.geglu(ops.linear_tokens(x_ln, pk["w1"], bias=pk["b1"]))
         return ops.linear_tokens(h, pk["w2"], bias=pk["b2"], residual=residual)
 
 
