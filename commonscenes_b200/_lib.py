@@ -61,6 +61,10 @@ SIGNATURES = {
     "cs_ncdhw_to_ndhwc": (_i32, [_vp, _i32, _i32, _i64, _i32, _vp, _vp]),
     "cs_ndhwc_to_ncdhw": (_i32, [_vp, _i32, _i32, _i64, _i32, _vp, _vp]),
     "cs_channel_mix": (_i32, [_vp, _i32, _i32, _i32, _i64, _vp, _vp, _vp, _vp]),
+    "cs_gcn_gather_triples": (_i32, [_vp, _i32, _i32, _vp, _i32, _i32, _vp, _vp, _vp]),
+    "cs_gcn_scatter_mean": (_i32, [_vp, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _vp, _vp]),
+    "cs_batchnorm_relu": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _f32, _f32, _i32, _vp, _i32, _vp]),
+    "cs_add_rows": (_i32, [_vp, _i32, _vp, _i32, _i32, _i32, _vp, _i32, _vp]),
     "cs_tap_gather": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "cs_vq_quantize": (_i32, [_vp, _i32, _i32, _i64, _vp, _i32, _vp, _vp, _i32, _vp, _vp, _vp]),
 }

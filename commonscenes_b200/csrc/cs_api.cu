@@ -28,6 +28,11 @@ int ncdhw_to_ndhwc_launch(const float*, int, int, long long, int, void*, cudaStr
 int ndhwc_to_ncdhw_launch(const void*, int, int, long long, int, float*, cudaStream_t);
 int channel_mix_launch(const float*, int, int, int, long long, const float*, const float*, float*, cudaStream_t);
 int tap_gather_launch(const float*, int, int, int, int, int, int, const float*, float*, cudaStream_t);
+int gather_triples_launch(const float*, int, int, const float*, int, int, const long long*, float*, cudaStream_t);
+int scatter_mean_launch(const float*, int, int, int, int, const long long*, int, int, float*, cudaStream_t);
+int batchnorm_relu_launch(const float*, int, int, int, const float*, const float*, float*, float*, int, float, float, int,
+                          float*, int, cudaStream_t);
+int add_rows_launch(const float*, int, const float*, int, int, int, float*, int, cudaStream_t);
 int vq_quantize_launch(const float*, int, int, long long, const float*, int, const float*, const float*, int, float*,
                        long long*, cudaStream_t);
 }  // namespace cs
@@ -149,6 +154,26 @@ int cs_channel_mix(const float* x, int32_t B, int32_t Ci, int32_t Co, int64_t Sp
 int cs_tap_gather(const float* y, int32_t B, int32_t Cy, int32_t Co, int32_t D, int32_t H, int32_t W, const float* bias,
                   float* out, cs_stream_t stream) {
   return cs::tap_gather_launch(y, B, Cy, Co, D, H, W, bias, out, S(stream));
+}
+
+int cs_gcn_gather_triples(const float* obj, int32_t O, int32_t Do, const float* pred, int32_t T, int32_t Dp,
+                          const int64_t* edges, float* out, cs_stream_t stream) {
+  return cs::gather_triples_launch(obj, O, Do, pred, T, Dp, reinterpret_cast<const long long*>(edges), out, S(stream));
+}
+int cs_gcn_scatter_mean(const float* tv, int32_t pitch, int32_t s_off, int32_t o_off, int32_t Hd, const int64_t* edges,
+                        int32_t T, int32_t O, float* pooled, cs_stream_t stream) {
+  return cs::scatter_mean_launch(tv, pitch, s_off, o_off, Hd, reinterpret_cast<const long long*>(edges), T, O, pooled,
+                                 S(stream));
+}
+int cs_batchnorm_relu(const float* x, int32_t M, int32_t C, int32_t pitch, const float* gamma, const float* beta,
+                      float* running_mean, float* running_var, int32_t training, float momentum, float eps, int32_t relu,
+                      float* y, int32_t y_pitch, cs_stream_t stream) {
+  return cs::batchnorm_relu_launch(x, M, C, pitch, gamma, beta, running_mean, running_var, training, momentum, eps, relu,
+                                   y, y_pitch, S(stream));
+}
+int cs_add_rows(const float* a, int32_t a_pitch, const float* b, int32_t b_pitch, int32_t M, int32_t C, float* y,
+                int32_t y_pitch, cs_stream_t stream) {
+  return cs::add_rows_launch(a, a_pitch, b, b_pitch, M, C, y, y_pitch, S(stream));
 }
 
 }  // extern "C"

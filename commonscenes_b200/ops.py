@@ -24,7 +24,8 @@ __all__ = [
     "ACT_NONE", "ACT_SILU", "ACT_GELU", "ACT_GEGLU", "pack_geglu_weight", "conv3d", "linear_tokens", "groupnorm", "layernorm", "attention",
     "geglu", "upsample_nearest", "im2col_small", "timestep_embedding", "linear_small", "ddim_step",
     "q_sample", "to_channels_last", "to_ncdhw", "pack_conv_weight", "pack_linear_weight", "launch_count",
-    "reset_launch_count", "zero_stat_buffer", "ConvProfiler", "vq_quantize", "channel_mix", "pack_small_cout_conv", "conv3d_small_cout",
+    "reset_launch_count", "zero_stat_buffer", "ConvProfiler", "vq_quantize", "channel_mix", "pack_small_cout_conv", "conv3d_small_cout", "gcn_gather_triples", "gcn_scatter_mean",
+    "batchnorm_relu", "add_rows",
 ]
 
 
@@ -445,3 +446,54 @@ def conv3d_small_cout(x: torch.Tensor, w_taps: torch.Tensor, bias: Optional[torc
     check(_lib.load().cs_tap_gather(y.data_ptr(), B, y.shape[1], cout, D, H, W, _ptr(_f32(bias, "bias")), out.data_ptr(),
                                     _stream()), "cs_tap_gather")
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# scene-graph conditioning (fp32, tiny)
+# ----------------------------------------------------------------------------------------------
+def _mat(t: torch.Tensor, name: str) -> torch.Tensor:
+    if t.dtype != torch.float32 or t.dim() != 2 or not t.is_cuda or (t.shape[1] > 1 and t.stride(1) != 1):
+        raise _lib.CsError(f"{name}: expected an fp32 (M, C) CUDA matrix with contiguous rows")
+    return t
+
+
+def gcn_gather_triples(obj: torch.Tensor, pred: torch.Tensor, edges: torch.Tensor) -> torch.Tensor:
+    _f32(obj, "obj"), _f32(pred, "pred")
+    if edges.dtype != torch.int64 or not edges.is_contiguous() or edges.dim() != 2 or edges.shape[1] != 2:
+        raise _lib.CsError("gcn_gather_triples: edges must be contiguous int64 (T, 2)")
+    O, Do = obj.shape
+    T, Dp = pred.shape
+    out = torch.empty((T, 2 * Do + Dp), dtype=torch.float32, device=obj.device)
+    check(_lib.load().cs_gcn_gather_triples(obj.data_ptr(), O, Do, pred.data_ptr(), T, Dp, edges.data_ptr(), out.data_ptr(),
+                                            _stream()), "cs_gcn_gather_triples")
+    return out
+
+
+def gcn_scatter_mean(tv: torch.Tensor, s_off: int, o_off: int, hidden: int, edges: torch.Tensor, num_objs: int) -> torch.Tensor:
+    _mat(tv, "tv")
+    pooled = torch.empty((num_objs, hidden), dtype=torch.float32, device=tv.device)
+    check(_lib.load().cs_gcn_scatter_mean(tv.data_ptr(), tv.stride(0), s_off, o_off, hidden, edges.data_ptr(), tv.shape[0],
+                                          num_objs, pooled.data_ptr(), _stream()), "cs_gcn_scatter_mean")
+    return pooled
+
+
+def batchnorm_relu(x: torch.Tensor, gamma, beta, running_mean, running_var, training: bool, momentum: float = 0.1,
+                   eps: float = 1e-5, relu: bool = True) -> torch.Tensor:
+    _mat(x, "batchnorm.x")
+    M, Cc = x.shape
+    if training and M < 2:
+        raise ValueError(f"Expected more than 1 value per channel when training, got input size {tuple(x.shape)}")
+    y = torch.empty((M, Cc), dtype=torch.float32, device=x.device)
+    check(_lib.load().cs_batchnorm_relu(x.data_ptr(), M, Cc, x.stride(0), _ptr(gamma), _ptr(beta), _ptr(running_mean),
+                                        _ptr(running_var), int(training), momentum, eps, int(relu), y.data_ptr(), y.stride(0),
+                                        _stream()), "cs_batchnorm_relu")
+    return y
+
+
+def add_rows(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    _mat(a, "add_rows.a"), _mat(b, "add_rows.b")
+    M, Cc = a.shape
+    y = torch.empty((M, Cc), dtype=torch.float32, device=a.device)
+    check(_lib.load().cs_add_rows(a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), M, Cc, y.data_ptr(), y.stride(0),
+                                  _stream()), "cs_add_rows")
+    return y

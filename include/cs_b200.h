@@ -143,6 +143,21 @@ int cs_channel_mix(const float* x, int32_t B, int32_t Ci, int32_t Co, int64_t S,
 int cs_tap_gather(const float* y, int32_t B, int32_t Cy, int32_t Co, int32_t D, int32_t H, int32_t W, const float* bias,
                   float* out, cs_stream_t stream);
 
+/* ---- scene-graph conditioning (GraphTripleConv, model/graph.py:124-211; build_mlp, model/layers.py:21-38); fp32 ---- */
+/* out[t] = cat(obj[edges[t][0]], pred[t], obj[edges[t][1]])                                    (graph.py:139-147) */
+int cs_gcn_gather_triples(const float* obj, int32_t O, int32_t Do, const float* pred, int32_t T, int32_t Dp,
+                          const int64_t* edges, float* out, cs_stream_t stream);
+/* pooled[o] = mean over incident triples of the subject / object halves of tv               (graph.py:165-195) */
+int cs_gcn_scatter_mean(const float* tv, int32_t pitch, int32_t s_off, int32_t o_off, int32_t Hd, const int64_t* edges,
+                        int32_t T, int32_t O, float* pooled, cs_stream_t stream);
+/* nn.BatchNorm1d (+ReLU): batch statistics and running-stat update when training != 0, running statistics otherwise */
+int cs_batchnorm_relu(const float* x, int32_t M, int32_t C, int32_t pitch, const float* gamma, const float* beta,
+                      float* running_mean, float* running_var, int32_t training, float momentum, float eps, int32_t relu,
+                      float* y, int32_t y_pitch, cs_stream_t stream);
+/* y = a + b on (M, C) fp32 row-pitched matrices                                               (graph.py:205-209) */
+int cs_add_rows(const float* a, int32_t a_pitch, const float* b, int32_t b_pitch, int32_t M, int32_t C, float* y,
+                int32_t y_pitch, cs_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
