@@ -33,6 +33,7 @@ int scatter_mean_launch(const float*, int, int, int, int, const long long*, int,
 int batchnorm_relu_launch(const float*, int, int, int, const float*, const float*, float*, float*, int, float, float, int,
                           float*, int, cudaStream_t);
 int add_rows_launch(const float*, int, const float*, int, int, int, float*, int, cudaStream_t);
+void igemm_set_debug(int);
 int vq_quantize_launch(const float*, int, int, long long, const float*, int, const float*, const float*, int, float*,
                        long long*, cudaStream_t);
 }  // namespace cs
@@ -175,5 +176,7 @@ int cs_add_rows(const float* a, int32_t a_pitch, const float* b, int32_t b_pitch
                 int32_t y_pitch, cs_stream_t stream) {
   return cs::add_rows_launch(a, a_pitch, b, b_pitch, M, C, y, y_pitch, S(stream));
 }
+
+void cs_debug_set(int32_t flags) { cs::igemm_set_debug(flags); }
 
 }  // extern "C"

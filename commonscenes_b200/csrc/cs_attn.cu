@@ -43,12 +43,12 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-template <int DP>
-__global__ void __launch_bounds__(128)
+template <int DP, int BM>
+__global__ void __launch_bounds__(BM * 2)
 attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
                  const __nv_bfloat16* __restrict__ v, __nv_bfloat16* __restrict__ out, int Nq, int Nk,
                  int q_pitch, int kv_pitch, int o_pitch, int d_out, float scale_log2) {
-  constexpr int BM = 64, BN = 64;
+  constexpr int BN = 64, NT = BM * 2;  // BM/16 warps of 16 query rows each; K/V tiles of 64 keys shared by all of them
   constexpr int PITCH = DP + 8;          // elements; (DP*2+16) bytes = odd multiple of 16 -> conflict-free ldmatrix
   constexpr int CPR = DP / 8;            // 16-byte chunks per row
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -64,14 +64,14 @@ attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __res
   const __nv_bfloat16* vg = v + (static_cast<long long>(b) * Nk) * kv_pitch + h * DP;
 
   // ---- stage Q and the first K/V tile ----
-  for (int i = tid; i < BM * CPR; i += 128) {
+  for (int i = tid; i < BM * CPR; i += NT) {
     const int r = i / CPR, c = i - r * CPR;
     const bool ok = (m0 + r) < Nq;
     cp_async16(sQ + r * PITCH + c * 8, qg + static_cast<long long>(ok ? m0 + r : 0) * q_pitch + c * 8, ok);
   }
   auto load_kv = [&](int tile, int buf) {
     const int j0 = tile * BN;
-    for (int i = tid; i < BN * CPR; i += 128) {
+    for (int i = tid; i < BN * CPR; i += NT) {
       const int r = i / CPR, c = i - r * CPR;
       const bool ok = (j0 + r) < Nk;
       const long long off = static_cast<long long>(ok ? j0 + r : 0) * kv_pitch + c * 8;
@@ -210,20 +210,20 @@ attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __res
   }
 }
 
-template <int DP>
+template <int DP, int BM>
 static int attention_launch_t(const void* q, const void* k, const void* v, void* out, int B, int H, int Nq,
                               int Nk, int q_pitch, int kv_pitch, int o_pitch, int d_out, float scale,
                               cudaStream_t st) {
   constexpr int PITCH = DP + 8;
-  const size_t smem = static_cast<size_t>(64 + 4 * 64) * PITCH * 2;
+  const size_t smem = static_cast<size_t>(BM + 4 * 64) * PITCH * 2;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(attention_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(attention_kernel<DP, BM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_cuda_error(e, "attention: cudaFuncSetAttribute");
     attr = true;
   }
   const float scale_log2 = scale * 1.4426950408889634f;
-  attention_kernel<DP><<<dim3((Nq + 63) / 64, H, B), 128, smem, st>>>(
+  attention_kernel<DP, BM><<<dim3((Nq + BM - 1) / BM, H, B), BM * 2, smem, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(q), reinterpret_cast<const __nv_bfloat16*>(k),
       reinterpret_cast<const __nv_bfloat16*>(v), reinterpret_cast<__nv_bfloat16*>(out), Nq, Nk, q_pitch,
       kv_pitch, o_pitch, d_out, scale_log2);
@@ -233,6 +233,15 @@ static int attention_launch_t(const void* q, const void* k, const void* v, void*
   return CS_OK;
 }
 
+// 128-query CTAs halve the K/V traffic out of L2 (the kernel's bound at N = 1024); short sequences and the
+// 256-wide head (register / smem budget) keep 64.
+#define CS_ATTN_DISPATCH(DPV)                                                                                        \
+  case DPV:                                                                                                          \
+    if (DPV <= 128 && Nq >= 128)                                                                                     \
+      return attention_launch_t<DPV, (DPV <= 128 ? 128 : 64)>(q, k, v, out, B, H, Nq, Nk, q_pitch, kv_pitch, o_pitch, \
+                                                             d_out, scale, st);                                      \
+    return attention_launch_t<DPV, 64>(q, k, v, out, B, H, Nq, Nk, q_pitch, kv_pitch, o_pitch, d_out, scale, st);
+
 int attention_launch(const void* q, const void* k, const void* v, void* out, int B, int H, int Nq, int Nk,
                      int Dp, int q_pitch, int kv_pitch, int o_pitch, int d_out, float scale, cudaStream_t st) {
   if (q_pitch % 8 || kv_pitch % 8 || o_pitch % 2 || d_out % 2 || d_out > Dp || Nk < 1)
@@ -241,11 +250,11 @@ int attention_launch(const void* q, const void* k, const void* v, void* out, int
       reinterpret_cast<uintptr_t>(v) % 16 || reinterpret_cast<uintptr_t>(out) % 4 || (H * d_out) % 2)
     return set_error(CS_ERR_INVALID, "attention: q/k/v must be 16-byte aligned");
   switch (Dp) {
-    case 32: return attention_launch_t<32>(q, k, v, out, B, H, Nq, Nk, q_pitch, kv_pitch, o_pitch, d_out, scale, st);
-    case 64: return attention_launch_t<64>(q, k, v, out, B, H, Nq, Nk, q_pitch, kv_pitch, o_pitch, d_out, scale, st);
-    case 96: return attention_launch_t<96>(q, k, v, out, B, H, Nq, Nk, q_pitch, kv_pitch, o_pitch, d_out, scale, st);
-    case 128: return attention_launch_t<128>(q, k, v, out, B, H, Nq, Nk, q_pitch, kv_pitch, o_pitch, d_out, scale, st);
-    case 256: return attention_launch_t<256>(q, k, v, out, B, H, Nq, Nk, q_pitch, kv_pitch, o_pitch, d_out, scale, st);
+    CS_ATTN_DISPATCH(32)
+    CS_ATTN_DISPATCH(64)
+    CS_ATTN_DISPATCH(96)
+    CS_ATTN_DISPATCH(128)
+    CS_ATTN_DISPATCH(256)
     default: return set_error(CS_ERR_UNSUPPORTED, "attention: padded head dim must be 32, 64, 96, 128 or 256");
   }
 }

@@ -187,10 +187,25 @@ __device__ __forceinline__ void epilogue_fast_tile(const IgemmParams& p, uint32_
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
       const int r = it * 8 + (lane >> 2), ch = lane & 3;
-      if (r < rows_valid && ch < out_chunks)
+      if (r < rows_valid && ch < out_chunks && !(p.debug & 1))
         *reinterpret_cast<uint4*>(obase + (m_w0 + r) * p.out_pitch + out_n + ch * 8) = oo[it];
     }
     __syncwarp();
+  }
+}
+
+// Work item -> (first m-tile, number of m-tiles (1 or 2), n-tile).  Pair items come first and cover m-tiles
+// [0, 2 * n_pair_items / n_tiles); single items cover the rest.
+__device__ __forceinline__ void decode_item(const IgemmParams& p, int item, int& mt0, int& cnt, int& nt) {
+  if (item < p.n_pair_items) {
+    nt = item % p.n_tiles;
+    mt0 = (item / p.n_tiles) * 2;
+    cnt = 2;
+  } else {
+    const int r = item - p.n_pair_items;
+    nt = r % p.n_tiles;
+    mt0 = (p.n_pair_items / p.n_tiles) * 2 + r / p.n_tiles;
+    cnt = 1;
   }
 }
 
@@ -205,13 +220,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
                                              ~static_cast<uintptr_t>(1023));
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int stage_bytes = kABytes + p.BN * 128;
+  const int stage_bytes = p.mt * kABytes + p.BN * 128;
   const int nch1 = (p.C1 + 63) >> 6;
   const int nch2 = (p.C2 + 63) >> 6;
   const int nch = nch1 + nch2;
   const int ntaps = p.kd * p.kh * p.kw;
-  const int total_tiles = p.m_tiles * p.n_tiles;
-  const int tx_bytes = p.rows * 128 + p.BN * 128;  // a tile smaller than 128 voxels leaves its tail rows unwritten
+  const int total_tiles = p.n_items;  // a tile smaller than 128 voxels leaves its tail rows unwritten
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA1);
@@ -245,15 +259,20 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
       uint32_t phase = 0;
       const int ctot = p.C1 + p.C2;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int nt = tile % p.n_tiles;
-        int mt = tile / p.n_tiles;
-        const int tw = mt % tiles_w; mt /= tiles_w;
-        const int th = mt % tiles_h; mt /= tiles_h;
-        const int td = mt % tiles_d; mt /= tiles_d;
-        const int b0 = mt * p.bb;
-        const int w0 = tw * p.bw * p.sw - p.pw;
-        const int h0 = th * p.bh * p.sh - p.ph;
-        const int d0 = td * p.bd * p.sd - p.pd;
+        int mt_first, cnt, nt;
+        decode_item(p, tile, mt_first, cnt, nt);
+        const int tx_bytes = cnt * p.rows * 128 + p.BN * 128;  // a tile smaller than 128 voxels leaves its tail rows unwritten
+        int b0[2], w0[2], h0[2], d0[2];
+        for (int i = 0; i < cnt; ++i) {
+          int mt = mt_first + i;
+          const int tw = mt % tiles_w; mt /= tiles_w;
+          const int th = mt % tiles_h; mt /= tiles_h;
+          const int td = mt % tiles_d; mt /= tiles_d;
+          b0[i] = mt * p.bb;
+          w0[i] = tw * p.bw * p.sw - p.pw;
+          h0[i] = th * p.bh * p.sh - p.ph;
+          d0[i] = td * p.bd * p.sd - p.pd;
+        }
         const int n0 = nt * p.BN;
         for (int zd = 0; zd < p.kd; ++zd)
           for (int zh = 0; zh < p.kh; ++zh)
@@ -262,17 +281,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
               for (int ch = 0; ch < nch; ++ch) {
                 mbar_wait(&bars.empty[stage], phase ^ 1);
                 uint8_t* sa = smem + stage * stage_bytes;
-                uint8_t* sb = sa + kABytes;
+                uint8_t* sb = sa + p.mt * kABytes;
                 mbar_arrive_expect_tx(&bars.full[stage], tx_bytes);
-                int kcol;
-                if (ch < nch1) {
-                  tma_load_5d(&tmA1, &bars.full[stage], sa, ch * 64, w0 + zw, h0 + zh, d0 + zd, b0);
-                  kcol = tap * ctot + ch * 64;
-                } else {
-                  tma_load_5d(&tmA2, &bars.full[stage], sa, (ch - nch1) * 64, w0 + zw, h0 + zh,
-                              d0 + zd, b0);
-                  kcol = tap * ctot + p.C1 + (ch - nch1) * 64;
-                }
+                const bool first = ch < nch1;
+                const int ccoord = first ? ch * 64 : (ch - nch1) * 64;
+                const int kcol = tap * ctot + (first ? ch * 64 : p.C1 + (ch - nch1) * 64);
+                for (int i = 0; i < cnt; ++i)
+                  tma_load_5d(first ? &tmA1 : &tmA2, &bars.full[stage], sa + i * kABytes, ccoord, w0[i] + zw, h0[i] + zh,
+                              d0[i] + zd, b0[i]);
                 tma_load_2d(&tmW, &bars.full[stage], sb, kcol, n0);
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
               }
@@ -284,13 +300,17 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
+      int acc = 0;                       // next accumulator buffer for a single tile
+      uint32_t buf_phase[2] = {0, 0};    // per-buffer use parity (pairs use both buffers, singles alternate)
       const uint32_t idesc = umma_idesc_bf16_m128(static_cast<uint32_t>(p.BN));
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        mbar_wait(&bars.tmem_empty[acc], acc_phase ^ 1);
+        int mt_first, cnt, nt;
+        decode_item(p, tile, mt_first, cnt, nt);
+        const int a0 = (cnt == 2) ? 0 : acc;
+        mbar_wait(&bars.tmem_empty[a0], buf_phase[a0] ^ 1);
+        if (cnt == 2) mbar_wait(&bars.tmem_empty[1], buf_phase[1] ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * 256);
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(a0 * 256);
         uint32_t accumulate = 0;
         for (int tap = 0; tap < ntaps; ++tap) {
           for (int ch = 0; ch < nch; ++ch) {
@@ -300,19 +320,29 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
             tc_fence_after();
             const uint32_t sa = smem_u32(smem + stage * stage_bytes);
             const uint64_t adesc = umma_desc_k_sw128(sa);
-            const uint64_t bdesc = umma_desc_k_sw128(sa + kABytes);
-            for (int k = 0; k < ksteps; ++k) {
+            const uint64_t adesc2 = umma_desc_k_sw128(sa + kABytes);
+            const uint64_t bdesc = umma_desc_k_sw128(sa + p.mt * kABytes);
+            for (int k = 0; k < ksteps && !(p.debug & 4); ++k) {
               // +32 bytes (= 16 bf16) along K inside the 128-byte swizzled row
               umma_bf16(d_tmem, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2),
                         idesc, accumulate);
+              if (cnt == 2)
+                umma_bf16(d_tmem + 256u, adesc2 + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2),
+                          idesc, accumulate);
               accumulate = 1;
             }
             umma_commit(&bars.empty[stage]);  // frees the smem stage once these MMAs retire
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
         }
-        umma_commit(&bars.tmem_full[acc]);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        umma_commit(&bars.tmem_full[a0]);
+        buf_phase[a0] ^= 1;
+        if (cnt == 2) {
+          umma_commit(&bars.tmem_full[1]);
+          buf_phase[1] ^= 1;
+        } else {
+          acc ^= 1;
+        }
       }
     }
   } else {
@@ -327,30 +357,35 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
     if (p.fast_epilogue) {
       uint8_t* stage = smem + p.stages * stage_bytes + (warp - 2) * 2048;
       const int et = threadIdx.x - 64;                           // 0..255 among the epilogue threads
+      uint32_t buf_phase[2] = {0, 0};
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int nt = tile % p.n_tiles;
-        const int mt = tile / p.n_tiles;
-        const long long m_tile0 = static_cast<long long>(mt) * p.rows;   // tiles are contiguous runs of voxels
-        const int b = static_cast<int>(m_tile0 / spatial);               // one sample per tile (bb == 1)
+        int mt_first, cnt, nt;
+        decode_item(p, tile, mt_first, cnt, nt);
         const int n0 = nt * p.BN;
-        // column vector for this tile (bias + per-sample vector), double buffered with the accumulator
-        for (int c = et; c < p.BN; c += 256) {
-          float cv = 0.f;
-          if (n0 + c < p.Cout) {
-            if (p.bias) cv += __ldg(p.bias + n0 + c);
-            if (p.rowvec) cv += __ldg(p.rowvec + static_cast<long long>(b) * p.rowvec_pitch + n0 + c);
+        for (int i = 0; i < cnt; ++i) {
+          const int ab = (cnt == 2) ? i : acc;
+          const long long m_tile0 = static_cast<long long>(mt_first + i) * p.rows;    // tiles are contiguous runs of voxels
+          const int b = static_cast<int>(m_tile0 / spatial);                           // one sample per tile (bb == 1)
+          // column vector for this tile (bias + per-sample vector), double buffered with the accumulator
+          for (int c = et; c < p.BN; c += 256) {
+            float cv = 0.f;
+            if (n0 + c < p.Cout) {
+              if (p.bias) cv += __ldg(p.bias + n0 + c);
+              if (p.rowvec) cv += __ldg(p.rowvec + static_cast<long long>(b) * p.rowvec_pitch + n0 + c);
+            }
+            bars.colvec[ab][c] = cv;
           }
-          bars.colvec[acc][c] = cv;
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          mbar_wait(&bars.tmem_full[ab], buf_phase[ab]);
+          tc_fence_after();
+          const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(ab * 256);
+          if (!(p.debug & 2)) epilogue_fast_tile(p, t_row, lane, half, quarter * 32, m_tile0, b, n0, bars.colvec[ab], stage);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars.tmem_empty[ab]);
+          buf_phase[ab] ^= 1;
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        mbar_wait(&bars.tmem_full[acc], acc_phase);
-        tc_fence_after();
-        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * 256);
-        epilogue_fast_tile(p, t_row, lane, half, quarter * 32, m_tile0, b, n0, bars.colvec[acc], stage);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bars.tmem_empty[acc]);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (cnt == 1) acc ^= 1;
       }
     } else
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -503,6 +538,9 @@ static int pick_tile_box(int B, int Do, int Ho, int Wo, int* bb, int* bd, int* b
   return 128 / rem;  // rows covered by the box (== 128 unless the whole output grid is smaller)
 }
 
+static int g_debug_flags = 0;
+void igemm_set_debug(int flags) { g_debug_flags = flags; }
+
 int igemm_launch(const IgemmArgs& a, cudaStream_t stream) {
   if (a.C1 <= 0 || a.C1 % 8 || a.C2 % 8 || a.Cout <= 0) return set_error(CS_ERR_INVALID, "igemm: channels must be multiples of 8");
   if (a.in1_pitch % 8 || (a.C2 > 0 && a.in2_pitch % 8)) return set_error(CS_ERR_INVALID, "igemm: input pitch must be a multiple of 8");
@@ -536,13 +574,55 @@ int igemm_launch(const IgemmArgs& a, cudaStream_t stream) {
   p.BN = bn;
   p.n_tiles = (a.Cout + bn - 1) / bn;
   p.m_tiles = (p.B / p.bb) * (p.Do / p.bd) * (p.Ho / p.bh) * (p.Wo / p.bw);
-  const int stage_bytes = kABytes + bn * 128;
+  p.out_mode = a.out_mode; p.rowvec = a.rowvec; p.stat_sum = a.stat_sum;
+  // tiles that span several samples (tiny grids) can use the fast epilogue when nothing in it is per-sample
+  p.fast_epilogue = (p.out_mode == CS_OUT_BF16_NDHWC && a.Cout % 8 == 0 && (p.bb == 1 || (!p.rowvec && !p.stat_sum))) ? 1 : 0;
+  // Pair mode (two 128-voxel accumulators per CTA share every weight slab): the main loop is bound by the rate at
+  // which one SM can ingest operands (~90 B/clk measured: profiles/r1_tma_ingest.txt), and pairing cuts the bytes per
+  // MMA cycle from (16 + BN/8) KB / (BN/2 + ..) to 0.68x.  It gives up the TMEM double buffer (exposed epilogue), so it
+  // is used for long K loops (3x3x3 convs) when the halved tile count still fills the 148 SMs well.
+  const int kiters = a.kd * a.kh * a.kw * ((a.C1 + 63) / 64 + (a.C2 + 63) / 64);
+  p.mt = 1;
+  p.n_pair_items = 0;
+  if (p.fast_epilogue && p.rows == 128 && p.bb == 1 && p.m_tiles >= 2 && kiters >= 27 && !(g_debug_flags & 32)) {
+    // Work list = P pairs of m-tiles (x n_tiles) followed by the remaining single tiles, dealt round-robin to the
+    // persistent CTAs.  Pick P minimising the busiest CTA's estimated time (pair = 1.40 single-tile units, measured).
+    const int sms = num_sms();
+    const int max_pairs = p.m_tiles / 2;
+    auto busiest = [&](int P) {
+      const long long ip = static_cast<long long>(P) * p.n_tiles;
+      const long long total = ip + static_cast<long long>(p.m_tiles - 2 * P) * p.n_tiles;
+      double worst = 0.0;
+      for (int c = 0; c < sms; ++c) {
+        const long long n_all = total > c ? (total - c + sms - 1) / sms : 0;
+        const long long n_pair = ip > c ? (ip - c + sms - 1) / sms : 0;
+        const double t = 1.40 * n_pair + 1.0 * (n_all - n_pair);
+        if (t > worst) worst = t;
+      }
+      return worst;
+    };
+    int best_p = 0;
+    double best_t = busiest(0);
+    for (int k = 1;; ++k) {   // candidates: whole rounds of pairs, and "everything paired"
+      int P = static_cast<int>((static_cast<long long>(k) * sms) / p.n_tiles);
+      const bool last = P >= max_pairs;
+      if (last) P = max_pairs;
+      const double t = busiest(P);
+      if (t < best_t) { best_t = t; best_p = P; }
+      if (last) break;
+    }
+    if (g_debug_flags & 64) best_p = max_pairs;
+    if (best_p > 0) { p.mt = 2; p.n_pair_items = best_p * p.n_tiles; }
+  }
+  p.n_items = p.n_pair_items + (p.m_tiles - 2 * (p.n_pair_items / p.n_tiles)) * p.n_tiles;
+  const int stage_bytes = p.mt * kABytes + bn * 128;
   // 227 KB per CTA minus the kernel's static shared memory (barriers) and the 1 KB alignment slack
   const int smem_budget = 227 * 1024 - 4096 - 8 * 2048;  // 8 x 2 KB epilogue staging buffers
   int stages = smem_budget / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return set_error(CS_ERR_INVALID, "igemm: tile too large for shared memory");
   p.stages = stages;
+  p.debug = g_debug_flags;
   p.bias = a.bias; p.rowvec = a.rowvec; p.rowvec_pitch = a.rowvec_pitch;
   p.residual = a.residual; p.res_pitch = a.res_pitch;
   p.out = a.out; p.out_pitch = a.out_pitch; p.out_mode = a.out_mode; p.act = a.act;
@@ -579,8 +659,6 @@ int igemm_launch(const IgemmArgs& a, cudaStream_t stream) {
     if (rc) return rc;
   }
 
-  // tiles that span several samples (tiny grids) can use it when nothing in the epilogue is per-sample
-  p.fast_epilogue = (p.out_mode == CS_OUT_BF16_NDHWC && a.Cout % 8 == 0 && (p.bb == 1 || (!p.rowvec && !p.stat_sum))) ? 1 : 0;
   if (p.act == CS_ACT_GEGLU && (!p.fast_epilogue || bn % 32 || a.Cout % 32 || p.residual || p.stat_sum))
     return set_error(CS_ERR_INVALID, "igemm: GEGLU epilogue needs bf16 output, Cout % 32 == 0 and no residual/stats");
   static int attr_smem = 0;
@@ -590,8 +668,10 @@ int igemm_launch(const IgemmArgs& a, cudaStream_t stream) {
     if (e != cudaSuccess) return set_cuda_error(e, "igemm: cudaFuncSetAttribute");
     attr_smem = smem_bytes;
   }
-  const int total = p.m_tiles * p.n_tiles;
-  const int grid = total < num_sms() ? total : num_sms();
+  const int total = p.n_items;
+  int grid = total < num_sms() ? total : num_sms();
+  if ((g_debug_flags & 8) && grid > 74) grid = 74;   // experiment: half the SMs
+  if ((g_debug_flags & 16) && grid > 37) grid = 37;  // experiment: a quarter of the SMs
   igemm_kernel<<<grid, kIgemmThreads, smem_bytes, stream>>>(tmA1, tmA2, tmW, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error(e, "igemm: launch");

@@ -22,7 +22,12 @@ struct IgemmParams {
   int BN;       // N tile (multiple of 16, <= 256)
   int n_tiles;  // ceil(Cout / BN)
   int m_tiles;
+  int mt;       // 1, or 2 = pair mode available (smem stages sized for two 128-voxel A tiles)
+  int n_pair_items;  // work items [0, n_pair_items) are PAIRS of m-tiles (two accumulators share every weight slab),
+                     // items after that are single m-tiles; item order is n-tile fastest within each class
+  int n_items;
   int stages;
+  int debug;          // tuning experiments only (cs_debug_set): 1 = no global stores, 2 = empty epilogue, 4 = no MMA
   int fast_epilogue;  // bf16 output staged through shared memory (coalesced), host-selected
   // epilogue
   const float* bias;      // [Cout] or null

@@ -236,7 +236,7 @@ int gn_apply_launch(const void* x, int B, int S, int C, int pitch, const float* 
 int layernorm_launch(const void* x, long long M, int C, int pitch, const float* gamma, const float* beta,
                      float eps, void* y, int y_pitch, cudaStream_t st) {
   if (C % 8 || C > 1024 || pitch % 8 || y_pitch % 8) return set_error(CS_ERR_INVALID, "layernorm: C % 8, C <= 1024");
-  const int warps = 8;
+  const int warps = 4;  // small CTAs: many resident per SM, every warp has its whole row (<= 4 x 16 B per lane) in flight
   const long long blocks = (M + warps - 1) / warps;
   layernorm_kernel<<<static_cast<unsigned>(blocks), warps * 32, 0, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(x), M, C, pitch, gamma, beta, eps,

@@ -18,10 +18,14 @@ SHAPES = [  # (Cin, Cout, (D,H,W), k, stride, count per UNet eval)
     (672, 672, (16, 4, 4), 1, (1, 1, 1), 18), (2688, 672, (16, 4, 4), 1, (1, 1, 1), 6),
 ]
 only = int(sys.argv[sys.argv.index("--only") + 1]) if "--only" in sys.argv else None
+if "--debug" in sys.argv:
+    from commonscenes_b200 import _lib
+    _lib.load().cs_debug_set(int(sys.argv[sys.argv.index("--debug") + 1]))
+first = int(sys.argv[sys.argv.index("--from") + 1]) if "--from" in sys.argv else 0
 reps = 1 if only is not None else 5
 tot_ms = tot_fl = 0.0
 for i, (ci, co, (D, H, W), k, st, cnt) in enumerate(SHAPES):
-    if only is not None and i != only:
+    if (only is not None and i != only) or i < first:
         continue
     x = torch.randn(B, D, H, W, ci, device="cuda").to(torch.bfloat16)
     w = (torch.randn(co, k ** 3, ci, device="cuda") / (ci * k ** 3) ** 0.5).to(torch.bfloat16)
