@@ -8,7 +8,8 @@
 //     (model/networks/diffusion_networks/attention.py:39-66,154-219,298-351).
 //
 // Formulation: activations live in HBM as channels-last bf16 [B][D][H][W][C]; weights as
-// [Cout][taps][Cin] bf16 (K-major).  Output tile = 128 voxels x BN channels, accumulated in TMEM.
+// [Cout][taps][pad64(Cin)] bf16 (K-major, every tap's channel run zero-padded to a multiple of 64 so that each
+// 64-channel slab starts on a 128-byte boundary).  Output tile = 128 voxels x BN channels, accumulated in TMEM.
 // For each filter tap and each 64-channel chunk, TMA loads a *shifted* 5-D box of the activation
 // (out-of-bounds voxels are zero-filled by the TMA unit = the convolution's zero padding, so there
 // is no im2col buffer and no halo logic) plus the matching [BN][64] weight slab, both landing in
@@ -257,7 +258,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const int ctot = p.C1 + p.C2;
+      const int ctot = nch * 64;  // packed weights pad every source's channels to a multiple of 64 per tap (128-byte aligned slabs)
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         int mt_first, cnt, nt;
         decode_item(p, tile, mt_first, cnt, nt);
@@ -285,7 +286,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
                 mbar_arrive_expect_tx(&bars.full[stage], tx_bytes);
                 const bool first = ch < nch1;
                 const int ccoord = first ? ch * 64 : (ch - nch1) * 64;
-                const int kcol = tap * ctot + (first ? ch * 64 : p.C1 + (ch - nch1) * 64);
+                const int kcol = tap * ctot + ch * 64;
                 for (int i = 0; i < cnt; ++i)
                   tma_load_5d(first ? &tmA1 : &tmA2, &bars.full[stage], sa + i * kABytes, ccoord, w0[i] + zw, h0[i] + zh,
                               d0[i] + zd, b0[i]);
@@ -544,7 +545,6 @@ void igemm_set_debug(int flags) { g_debug_flags = flags; }
 int igemm_launch(const IgemmArgs& a, cudaStream_t stream) {
   if (a.C1 <= 0 || a.C1 % 8 || a.C2 % 8 || a.Cout <= 0) return set_error(CS_ERR_INVALID, "igemm: channels must be multiples of 8");
   if (a.in1_pitch % 8 || (a.C2 > 0 && a.in2_pitch % 8)) return set_error(CS_ERR_INVALID, "igemm: input pitch must be a multiple of 8");
-  if (a.C2 > 0 && a.C1 % 16) return set_error(CS_ERR_INVALID, "igemm: two-source concat needs C1 % 16 == 0");
   if (reinterpret_cast<uintptr_t>(a.in1) % 16 || reinterpret_cast<uintptr_t>(a.in2) % 16 ||
       reinterpret_cast<uintptr_t>(a.weight) % 16)
     return set_error(CS_ERR_INVALID, "igemm: pointers must be 16-byte aligned");
@@ -650,7 +650,7 @@ int igemm_launch(const IgemmArgs& a, cudaStream_t stream) {
       rc = make_tensor_map(&tmA2, a.in2, 5, dims2, strides2, box, estr);
       if (rc) return rc;
     }
-    const uint64_t ktot = (uint64_t)(a.C1 + a.C2) * a.kd * a.kh * a.kw;
+    const uint64_t ktot = (uint64_t)(((a.C1 + 63) / 64 + (a.C2 + 63) / 64) * 64) * a.kd * a.kh * a.kw;
     const uint64_t wd[2] = {ktot, (uint64_t)a.Cout};
     const uint64_t ws[1] = {ktot * 2};
     const uint32_t wb[2] = {64u, (uint32_t)bn};

@@ -102,13 +102,15 @@ class ResBlock(TimestepBlock):
         else:
             self.skip_connection = conv_nd(dims, channels, self.out_channels, 1)
 
-    def pack(self):
+    def pack(self, skip_channels: int = 0):
+        """skip_channels > 0: the block's input is cat([h, skip]) with that many skip channels (decoder blocks)."""
+        split = (self.channels - skip_channels, skip_channels) if skip_channels else None
         pk = {"gn1": (_f(self.in_layers[0].weight), _f(self.in_layers[0].bias)),
               "w1": ops.pack_conv_weight(self.in_layers[2].weight), "b1": _f(self.in_layers[2].bias),
               "gn2": (_f(self.out_layers[0].weight), _f(self.out_layers[0].bias)),
               "w2": ops.pack_conv_weight(self.out_layers[3].weight), "b2": _f(self.out_layers[3].bias)}
         if not isinstance(self.skip_connection, nn.Identity):
-            pk["ws"] = ops.pack_conv_weight(self.skip_connection.weight)
+            pk["ws"] = ops.pack_conv_weight(self.skip_connection.weight, split)
             pk["bs"] = _f(self.skip_connection.bias)
         return pk
 
@@ -206,6 +208,7 @@ class UNet3DModel(nn.Module):
             for i in range(num_res_blocks + 1):
                 ich = input_block_chans.pop()
                 layers = [res(ch + ich, model_channels * mult)]
+                layers[0].skip_in_channels = ich      # this block consumes cat([h, skip]): `ich` channels come from the skip
                 ch = model_channels * mult
                 if ds in attention_resolutions:
                     layers.append(transformer(ch, num_heads_upsample))
@@ -240,7 +243,7 @@ class UNet3DModel(nn.Module):
             entries = []
             for layer in block:
                 if isinstance(layer, ResBlock):
-                    e = {"kind": "res", "pk": layer.pack(), "emb": (emb_off, layer.out_channels)}
+                    e = {"kind": "res", "pk": layer.pack(getattr(layer, "skip_in_channels", 0)), "emb": (emb_off, layer.out_channels)}
                     emb_w.append(_f(layer.emb_layers[1].weight)); emb_b.append(_f(layer.emb_layers[1].bias))
                     emb_off += layer.out_channels
                 elif isinstance(layer, SpatialTransformer3D):
@@ -253,12 +256,8 @@ class UNet3DModel(nn.Module):
                 elif isinstance(layer, (Downsample, Upsample)):
                     e = {"kind": "resample", "pk": layer.pack()}
                 elif isinstance(layer, nn.Conv3d):      # the stem: few input channels -> im2col + GEMM
-                    w = layer.weight.detach().float()
-                    k = 27 * w.shape[1]
-                    kp = (k + 15) // 16 * 16
-                    wp = torch.zeros(w.shape[0], 1, kp, device=dev)
-                    wp[:, 0, :k] = w.permute(0, 2, 3, 4, 1).reshape(w.shape[0], k)
-                    e = {"kind": "stem", "pk": {"w": wp.to(torch.bfloat16), "b": _f(layer.bias), "kp": kp}}
+                    wp, kp = ops.pack_patch_weight(layer.weight)
+                    e = {"kind": "stem", "pk": {"w": wp, "b": _f(layer.bias), "kp": kp}}
                 else:
                     raise TypeError(f"unexpected layer {type(layer)}")
                 entries.append(e)

@@ -156,13 +156,9 @@ class AttnBlock(_Packed):
 
 
 def _small_cin_conv_pack(conv: nn.Conv3d):
-    """3x3x3 conv with 1-4 input channels -> GEMM weight over the cs_im2col_small patch matrix (column = tap*C + c)."""
-    w = conv.weight.detach().float()
-    k = 27 * w.shape[1]
-    kp = (k + 15) // 16 * 16
-    wp = torch.zeros(w.shape[0], 1, kp, device=w.device)
-    wp[:, 0, :k] = w.permute(0, 2, 3, 4, 1).reshape(w.shape[0], k)
-    return wp.to(torch.bfloat16), _f(conv.bias), kp
+    """3x3x3 conv with 1-4 input channels -> GEMM weight over the cs_im2col_small patch matrix."""
+    wp, kp = ops.pack_patch_weight(conv.weight)
+    return wp, _f(conv.bias), kp
 
 
 class Encoder3D(_Packed):

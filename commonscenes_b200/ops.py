@@ -21,7 +21,7 @@ from ._lib import (ACT_GEGLU, ACT_GELU, ACT_NONE, ACT_SILU, OUT_BF16_NDHWC, OUT_
                    Conv3dArgs, check)
 
 __all__ = [
-    "ACT_NONE", "ACT_SILU", "ACT_GELU", "ACT_GEGLU", "pack_geglu_weight", "conv3d", "linear_tokens", "groupnorm", "layernorm", "attention",
+    "ACT_NONE", "ACT_SILU", "ACT_GELU", "ACT_GEGLU", "pack_geglu_weight", "pack_patch_weight", "conv3d", "linear_tokens", "groupnorm", "layernorm", "attention",
     "geglu", "upsample_nearest", "im2col_small", "timestep_embedding", "linear_small", "ddim_step",
     "q_sample", "to_channels_last", "to_ncdhw", "pack_conv_weight", "pack_linear_weight", "launch_count",
     "reset_launch_count", "zero_stat_buffer", "ConvProfiler", "vq_quantize", "channel_mix", "pack_small_cout_conv", "conv3d_small_cout", "gcn_gather_triples", "gcn_scatter_mean",
@@ -74,10 +74,30 @@ def reset_launch_count() -> None:
 # ----------------------------------------------------------------------------------------------
 # weight packing (one-off, at load / after an optimizer step) — layout plumbing, done with torch
 # ----------------------------------------------------------------------------------------------
-def pack_conv_weight(w: torch.Tensor) -> torch.Tensor:
-    """(Cout, Cin, kd, kh, kw) fp32 -> (Cout, kd*kh*kw, Cin) bf16, the K-major layout cs_conv3d reads."""
+def _pad64(c: int) -> int:
+    return (c + 63) // 64 * 64
+
+
+def _pad_k(wt: torch.Tensor, split=None) -> torch.Tensor:
+    """(Cout, taps, Cin) -> bf16 (Cout, taps, pad64(C1) [+ pad64(C2)]): each source's channel run is zero-padded to a
+    multiple of 64 so that every 64-channel slab the kernel fetches starts on a 128-byte boundary."""
+    co, taps, ci = wt.shape
+    parts = [ci] if split is None else [int(c) for c in split]
+    if sum(parts) != ci:
+        raise _lib.CsError(f"pack: channel split {parts} does not sum to {ci}")
+    out = torch.zeros((co, taps, sum(_pad64(c) for c in parts)), dtype=torch.bfloat16, device=wt.device)
+    src = dst = 0
+    for c in parts:
+        out[:, :, dst:dst + c] = wt[:, :, src:src + c]
+        src, dst = src + c, dst + _pad64(c)
+    return out
+
+
+def pack_conv_weight(w: torch.Tensor, split=None) -> torch.Tensor:
+    """(Cout, Cin, kd, kh, kw) fp32 -> the K-major bf16 layout cs_conv3d reads (see _pad_k).  `split` = (C1, C2) when the
+    conv consumes the channel concatenation of two tensors."""
     co, ci = w.shape[0], w.shape[1]
-    return w.detach().reshape(co, ci, -1).permute(0, 2, 1).contiguous().to(torch.bfloat16)
+    return _pad_k(w.detach().reshape(co, ci, -1).permute(0, 2, 1), split)
 
 
 def pack_geglu_weight(w: torch.Tensor, b: torch.Tensor):
@@ -91,9 +111,20 @@ def pack_geglu_weight(w: torch.Tensor, b: torch.Tensor):
     return pack_linear_weight(w.detach()[perm]), b.detach().float()[perm].contiguous()
 
 
+def pack_patch_weight(w: torch.Tensor):
+    """3x3x3 conv with a few input channels -> GEMM weight over the cs_im2col_small patch matrix (column = tap*C + c).
+    Returns (packed weight, Kp) with Kp = patch-matrix width (27*C rounded up to 16)."""
+    w = w.detach().float()
+    k = 27 * w.shape[1]
+    kp = (k + 15) // 16 * 16
+    wp = torch.zeros(w.shape[0], 1, kp, device=w.device)
+    wp[:, 0, :k] = w.permute(0, 2, 3, 4, 1).reshape(w.shape[0], k)
+    return _pad_k(wp), kp
+
+
 def pack_linear_weight(w: torch.Tensor) -> torch.Tensor:
-    """(out, in) fp32 -> (out, 1, in) bf16."""
-    return w.detach().reshape(w.shape[0], 1, w.shape[1]).contiguous().to(torch.bfloat16)
+    """(out, in) fp32 -> (out, 1, pad64(in)) bf16."""
+    return _pad_k(w.detach().reshape(w.shape[0], 1, w.shape[1]))
 
 
 # ----------------------------------------------------------------------------------------------
@@ -142,8 +173,9 @@ def conv3d(x: torch.Tensor, weight: torch.Tensor, *, ksize: Sequence[int] = (3, 
             raise _lib.CsError("conv3d: x and x2 must share batch and spatial dims")
     kd, kh, kw = ksize
     if weight.dtype != torch.bfloat16 or weight.dim() != 3 or not weight.is_contiguous() or \
-            weight.shape[1] != kd * kh * kw or weight.shape[2] != C1 + C2:
-        raise _lib.CsError(f"conv3d: packed weight must be bf16 (Cout, {kd * kh * kw}, {C1 + C2}), got {tuple(weight.shape)}")
+            weight.shape[1] != kd * kh * kw or weight.shape[2] != _pad64(C1) + _pad64(C2):
+        raise _lib.CsError(f"conv3d: packed weight must be bf16 (Cout, {kd * kh * kw}, {_pad64(C1) + _pad64(C2)}), "
+                           f"got {tuple(weight.shape)} (use pack_conv_weight / pack_linear_weight)")
     Cout = weight.shape[0]
     Cres = Cout // 2 if act == ACT_GEGLU else Cout      # channels of the tensor written
     pb = tuple(pad) if pad_back is None else tuple(pad_back)
@@ -434,7 +466,7 @@ def pack_small_cout_conv(w: torch.Tensor):
     rows = (27 * co + 15) // 16 * 16
     wt = torch.zeros(rows, 1, ci, dtype=torch.float32, device=w.device)
     wt[:27 * co, 0] = w.detach().float().reshape(co, ci, 27).permute(2, 0, 1).reshape(27 * co, ci)
-    return wt.to(torch.bfloat16)
+    return _pad_k(wt)
 
 
 def conv3d_small_cout(x: torch.Tensor, w_taps: torch.Tensor, bias: Optional[torch.Tensor], cout: int) -> torch.Tensor:

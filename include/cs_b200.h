@@ -63,7 +63,7 @@ typedef struct cs_conv3d_args {
   const void* in1; int32_t C1; int32_t in1_pitch;   /* bf16 channels-last, C1 % 8 == 0 */
   const void* in2; int32_t C2; int32_t in2_pitch;   /* optional second source (channel concat) */
   int32_t B, D, H, W;                                /* INPUT spatial extent */
-  const void* weight; int32_t Cout;                  /* bf16 [Cout][kd*kh*kw][C1+C2] */
+  const void* weight; int32_t Cout;                  /* bf16 [Cout][kd*kh*kw][pad64(C1)+pad64(C2)], zero padded */
   int32_t kd, kh, kw, sd, sh, sw;
   int32_t pd, ph, pw, pd_back, ph_back, pw_back;     /* zero padding, front / back */
   const float* bias;                                 /* [Cout] or NULL */

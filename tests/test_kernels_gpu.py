@@ -96,7 +96,7 @@ def test_conv3d_two_sources_equals_concat(ops):
     x2 = torch.randn(B, C2, D, H, W, device="cuda", generator=g)
     w = torch.randn(Cout, C1 + C2, 3, 3, 3, device="cuda", generator=g) / math.sqrt((C1 + C2) * 27)
     ref = F.conv3d(_bf(torch.cat([x1, x2], 1)).float(), _bf(w).float(), None, padding=1)
-    got = ops.conv3d(_cl(x1), ops.pack_conv_weight(w), x2=_cl(x2))
+    got = ops.conv3d(_cl(x1), ops.pack_conv_weight(w, split=(C1, C2)), x2=_cl(x2))
     torch.cuda.synchronize()
     _report("two_source", _ncdhw(got), ref, rtol=2 ** -7, atol=2e-3)
 
@@ -146,11 +146,9 @@ def test_stem_im2col_gemm(ops):
     x = torch.randn(2, 3, D, D, D, device="cuda", generator=g)
     w = torch.randn(224, 3, 3, 3, 3, device="cuda", generator=g) / math.sqrt(81)
     b = torch.randn(224, device="cuda", generator=g)
-    col = ops.im2col_small(x, batch=B)
-    kp = col.shape[-1]
-    wp = torch.zeros(224, 1, kp, device="cuda")
-    wp[:, 0, :81] = w.permute(0, 2, 3, 4, 1).reshape(224, 81)  # (tap, c) order
-    got = ops.linear_tokens(col, wp.to(torch.bfloat16), bias=b)
+    wp, kp = ops.pack_patch_weight(w)                             # columns in (tap, c) order
+    col = ops.im2col_small(x, batch=B, kp=kp)
+    got = ops.linear_tokens(col, wp, bias=b)
     torch.cuda.synchronize()
     ref = F.conv3d(_bf(torch.cat([x, x])).float(), _bf(w).float(), b, padding=1)
     _report("stem", _ncdhw(got), ref, rtol=2 ** -7, atol=2e-3)

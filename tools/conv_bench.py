@@ -28,7 +28,7 @@ for i, (ci, co, (D, H, W), k, st, cnt) in enumerate(SHAPES):
     if (only is not None and i != only) or i < first:
         continue
     x = torch.randn(B, D, H, W, ci, device="cuda").to(torch.bfloat16)
-    w = (torch.randn(co, k ** 3, ci, device="cuda") / (ci * k ** 3) ** 0.5).to(torch.bfloat16)
+    w = ops.pack_conv_weight(torch.randn(co, ci, k, k, k, device="cuda") / (ci * k ** 3) ** 0.5)
     b = torch.randn(co, device="cuda")
     pad = (k // 2,) * 3
     for _ in range(2):
