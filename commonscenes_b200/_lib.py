@@ -49,6 +49,8 @@ SIGNATURES = {
     "cs_groupnorm_stats": (_i32, [_vp, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
     "cs_groupnorm_finalize": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _vp, _vp]),
     "cs_groupnorm_apply": (_i32, [_vp, _i32, _i32, _i32, _i32, _vp, _i32, _vp, _i32, _i32, _vp]),
+    "cs_groupnorm_apply_fused": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _i32, _f32, _vp, _i32,
+                                        _i32, _vp]),
     "cs_layernorm": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp, _f32, _vp, _i32, _vp]),
     "cs_attention": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp]),
     "cs_geglu": (_i32, [_vp, _i64, _i32, _i32, _vp, _i32, _vp]),

@@ -11,6 +11,8 @@ void reset_launch_count();
 int gn_stats_launch(const void*, int, int, int, int, float*, int, cudaStream_t);
 int gn_finalize_launch(float*, const float*, const float*, int, int, int, int, float, float*, cudaStream_t);
 int gn_apply_launch(const void*, int, int, int, int, const float*, int, void*, int, int, cudaStream_t);
+int gn_apply_fused_launch(const void*, int, int, int, int, int, const float*, int, const float*, int, const float*,
+                          const float*, int, float, void*, int, int, cudaStream_t);
 int layernorm_launch(const void*, long long, int, int, const float*, const float*, float, void*, int, cudaStream_t);
 int attention_launch(const void*, const void*, const void*, void*, int, int, int, int, int, int, int, int, int,
                      float, cudaStream_t);
@@ -178,5 +180,14 @@ int cs_add_rows(const float* a, int32_t a_pitch, const float* b, int32_t b_pitch
 }
 
 void cs_debug_set(int32_t flags) { cs::igemm_set_debug(flags); }
+
+int cs_groupnorm_apply_fused(const void* x, int32_t B, int32_t Sp, int32_t C, int32_t pitch, int32_t ch_off,
+                             const float* stat1, int32_t C1, const float* stat2, int32_t C2, const float* gamma,
+                             const float* beta, int32_t groups, float eps, void* y, int32_t y_pitch, int32_t act,
+                             cs_stream_t stream) {
+  if (!x || !stat1 || !y) return cs::set_error(CS_ERR_INVALID, "cs_groupnorm_apply_fused: null pointer");
+  return cs::gn_apply_fused_launch(x, B, Sp, C, pitch, ch_off, stat1, C1, stat2, C2, gamma, beta, groups, eps, y, y_pitch,
+                                   act, S(stream));
+}
 
 }  // extern "C"

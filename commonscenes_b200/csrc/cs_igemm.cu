@@ -62,19 +62,6 @@ __device__ __forceinline__ void colsum32(float (&a)[32], int lane) {
   }
 }
 
-// erf via Abramowitz-Stegun 7.1.26 (|abs err| < 1.5e-7, far below the bf16 rounding of the result): one exp,
-// one reciprocal and five FMAs instead of libdevice's erff -- the GEGLU epilogue evaluates it 112 times per row.
-__device__ __forceinline__ float gelu_erf_fast(float x) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.f));
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  const float erf_abs = 1.f - poly * t * __expf(-z * z);
-  return 0.5f * x * (1.f + copysignf(erf_abs, x));
-}
-
 __device__ __forceinline__ void epilogue_fast_tile(const IgemmParams& p, uint32_t t_row, int lane, int half,
                                                    int warp_rows0, long long m_tile0, int b, int n0,
                                                    const float* __restrict__ colvec, uint8_t* __restrict__ stage) {

@@ -123,15 +123,82 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x, int S, int 
 }
 
 // ------------------------------------------------------------------------------------------------
+// fused finalize + apply: y = act(GroupNorm(cat(x1, x2)))[this source's channels].  The per-(sample, channel) sums of
+// BOTH concatenated sources (produced by the epilogues of the convs that wrote them, or by gn_stats_kernel) are reduced
+// to group statistics in the CTA prologue (one thread per group, fp64, fixed order), then every thread derives the
+// (scale, shift) pairs of its 8 channels and streams its slab of voxels.  Sums are only read, never cleared: a tensor
+// may be normalised more than once (block output -> next block AND decoder skip).
+// ------------------------------------------------------------------------------------------------
+__global__ void gn_apply_fused_kernel(const __nv_bfloat16* __restrict__ x, int S, int C, int pitch, int ch_off,
+                                      const float* __restrict__ stat1, int C1, const float* __restrict__ stat2, int C2,
+                                      const float* __restrict__ gamma, const float* __restrict__ beta, int groups,
+                                      float eps, __nv_bfloat16* __restrict__ y, int y_pitch, int act, int vox_per_cta) {
+  __shared__ float g_mean[64], g_rstd[64];
+  const int b = blockIdx.y;
+  const int Ct = C1 + C2;
+  const int cpg = Ct / groups;
+  if (threadIdx.x < groups) {
+    double s = 0.0, q = 0.0;
+    for (int j = 0; j < cpg; ++j) {
+      const int c = threadIdx.x * cpg + j;
+      const float* sp = (c < C1) ? stat1 + (static_cast<long long>(b) * C1 + c) * 2
+                                 : stat2 + (static_cast<long long>(b) * C2 + (c - C1)) * 2;
+      s += sp[0];
+      q += sp[1];
+    }
+    const double inv_n = 1.0 / (static_cast<double>(S) * cpg);
+    const double mean = s * inv_n;
+    double var = q * inv_n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    g_mean[threadIdx.x] = static_cast<float>(mean);
+    g_rstd[threadIdx.x] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  }
+  __syncthreads();
+  const int cv = C >> 3;
+  const int R = blockDim.x / cv;
+  const int r = threadIdx.x / cv;
+  const int v = threadIdx.x - r * cv;
+  if (r >= R) return;
+  float2 a[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = ch_off + v * 8 + j;      // channel index inside the concatenation
+    const int g = c / cpg;
+    const float ga = gamma ? __ldg(gamma + c) : 1.f, be = beta ? __ldg(beta + c) : 0.f;
+    const float sc = ga * g_rstd[g];
+    a[j] = make_float2(sc, be - g_mean[g] * sc);
+  }
+  const int s_begin = blockIdx.x * vox_per_cta;
+  const int s_end = min(S, s_begin + vox_per_cta);
+  const __nv_bfloat16* xb = x + (static_cast<long long>(b) * S) * pitch + v * 8;
+  __nv_bfloat16* yb = y + (static_cast<long long>(b) * S) * y_pitch + v * 8;
+#pragma unroll 4
+  for (int i = s_begin + r; i < s_end; i += R) {
+    const uint4 u = *reinterpret_cast<const uint4*>(xb + static_cast<long long>(i) * pitch);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = unpack_bf16x2(w[j]);
+      float y0 = fmaf(f.x, a[2 * j].x, a[2 * j].y), y1 = fmaf(f.y, a[2 * j + 1].x, a[2 * j + 1].y);
+      if (act == CS_ACT_SILU) { y0 = silu_f(y0); y1 = silu_f(y1); }
+      else if (act == CS_ACT_GELU) { y0 = gelu_erf_fast(y0); y1 = gelu_erf_fast(y1); }
+      o[j] = pack_bf16x2(y0, y1);
+    }
+    *reinterpret_cast<uint4*>(yb + static_cast<long long>(i) * y_pitch) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // LayerNorm over the last dim; one warp per row; C % 8 == 0, C <= 1024
 // ------------------------------------------------------------------------------------------------
 __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long M, int C, int pitch,
                                  const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                  __nv_bfloat16* __restrict__ y, int y_pitch) {
   const int lane = threadIdx.x & 31;
-  const long long row = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= M) return;
   const int cv = C >> 3;
+  const long long warps_total = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
+  for (long long row = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5); row < M; row += warps_total) {
   float v[4][8];
   float s = 0.f;
 #pragma unroll
@@ -172,6 +239,7 @@ __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long 
       }
       *reinterpret_cast<uint4*>(y + row * y_pitch + vi * 8) = make_uint4(o[0], o[1], o[2], o[3]);
     }
+  }
   }
 }
 
@@ -236,13 +304,41 @@ int gn_apply_launch(const void* x, int B, int S, int C, int pitch, const float* 
 int layernorm_launch(const void* x, long long M, int C, int pitch, const float* gamma, const float* beta,
                      float eps, void* y, int y_pitch, cudaStream_t st) {
   if (C % 8 || C > 1024 || pitch % 8 || y_pitch % 8) return set_error(CS_ERR_INVALID, "layernorm: C % 8, C <= 1024");
-  const int warps = 4;  // small CTAs: many resident per SM, every warp has its whole row (<= 4 x 16 B per lane) in flight
-  const long long blocks = (M + warps - 1) / warps;
+  const int warps = 8;
+  long long blocks = (M + warps - 1) / warps;
+  const long long cap = static_cast<long long>(num_sms()) * 8;   // grid-stride over rows: 8 resident CTAs per SM
+  if (blocks > cap) blocks = cap;
   layernorm_kernel<<<static_cast<unsigned>(blocks), warps * 32, 0, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(x), M, C, pitch, gamma, beta, eps,
       reinterpret_cast<__nv_bfloat16*>(y), y_pitch);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error(e, "layernorm: launch");
+  count_launch();
+  return CS_OK;
+}
+
+int gn_apply_fused_launch(const void* x, int B, int S, int C, int pitch, int ch_off, const float* stat1, int C1,
+                          const float* stat2, int C2, const float* gamma, const float* beta, int groups, float eps, void* y,
+                          int y_pitch, int act, cudaStream_t st) {
+  const int Ct = C1 + (stat2 ? C2 : 0);
+  if (C % 8 || pitch % 8 || y_pitch % 8 || ch_off % 8 || C > 2048 || reinterpret_cast<uintptr_t>(x) % 16 ||
+      reinterpret_cast<uintptr_t>(y) % 16)
+    return set_error(CS_ERR_INVALID, "groupnorm_apply_fused: alignment (C, pitches, channel offset multiples of 8)");
+  if (groups < 1 || groups > 64 || Ct % groups || ch_off + C > Ct)
+    return set_error(CS_ERR_INVALID, "groupnorm_apply_fused: groups must divide C1 + C2 (<= 64 groups)");
+  const int cv = C / 8;
+  int R = 256 / cv; if (R < 1) R = 1;
+  int threads = ((R * cv + 31) / 32) * 32;
+  if (threads < 64) threads = 64;   // the prologue needs one thread per group
+  int splits = (8 * num_sms() + B - 1) / B;
+  int vox = (S + splits - 1) / splits;
+  if (vox < 4 * R) vox = 4 * R;
+  splits = (S + vox - 1) / vox;
+  gn_apply_fused_kernel<<<dim3(splits, B), threads, 0, st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), S, C, pitch, ch_off, stat1, C1, stat2, stat2 ? C2 : 0, gamma, beta, groups,
+      eps, reinterpret_cast<__nv_bfloat16*>(y), y_pitch, act, vox);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(e, "groupnorm_apply_fused: launch");
   count_launch();
   return CS_OK;
 }

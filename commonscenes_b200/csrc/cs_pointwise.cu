@@ -44,7 +44,7 @@ __global__ void geglu_kernel(const __nv_bfloat16* __restrict__ x, long long M, i
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float2 af = unpack_bf16x2(aw[j]), gf = unpack_bf16x2(gw[j]);
-      o[j] = pack_bf16x2(af.x * gelu_erf_f(gf.x), af.y * gelu_erf_f(gf.y));
+      o[j] = pack_bf16x2(af.x * gelu_erf_fast(gf.x), af.y * gelu_erf_fast(gf.y));
     }
     *reinterpret_cast<uint4*>(y + row * y_pitch + v * 8) = make_uint4(o[0], o[1], o[2], o[3]);
   }

@@ -177,9 +177,12 @@ class SpatialTransformer3D(nn.Module):
                 "w_out": ops.pack_conv_weight(self.proj_out.weight), "b_out": f(self.proj_out.bias),
                 "blocks": [b.pack() for b in self.transformer_blocks]}
 
-    def run(self, pk, x, ctx_vecs):
-        """x: (B, D, H, W, C) bf16; ctx_vecs: one fp32 (B, inner) vector per transformer block."""
-        t = ops.linear_tokens(ops.groupnorm(x, *pk["gn"], eps=self.norm.eps), pk["w_in"], bias=pk["b_in"])
+    def run(self, pk, x, ctx_vecs, arena):
+        """x: Act over (B, D, H, W, C) bf16 (with its GroupNorm sums); ctx_vecs: one fp32 (B, inner) vector per block."""
+        from .openai_model_3d import _with_stats
+        B, D, H, W, C = x.t.shape
+        t = ops.linear_tokens(ops.groupnorm_fused(x.t, x.stat, *pk["gn"], eps=self.norm.eps), pk["w_in"], bias=pk["b_in"])
         for blk, bpk, vec in zip(self.transformer_blocks, pk["blocks"], ctx_vecs):
             t = blk.run(bpk, t, vec)
-        return ops.linear_tokens(t, pk["w_out"], bias=pk["b_out"], residual=x)
+        return _with_stats(arena, lambda st: ops.linear_tokens(t, pk["w_out"], bias=pk["b_out"], residual=x.t, stat_sum=st),
+                           B, C, D * H * W)

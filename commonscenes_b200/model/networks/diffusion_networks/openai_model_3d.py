@@ -31,6 +31,47 @@ def _f(t: torch.Tensor) -> torch.Tensor:
     return t.detach().float().contiguous()
 
 
+class Act:
+    """A channels-last bf16 activation together with the per-(sample, channel) (sum, sum of squares) its producer's
+    epilogue accumulated — everything a later GroupNorm of this tensor needs (fp32 (B, C, 2), read-only for consumers)."""
+    __slots__ = ("t", "stat")
+
+    def __init__(self, t, stat):
+        self.t, self.stat = t, stat
+
+
+class StatArena:
+    """One zero-initialised fp32 buffer per forward pass from which the GroupNorm sum buffers are carved (a single memset
+    instead of one per tensor; CUDA-graph friendly: the buffer is persistent, the memset is captured)."""
+
+    def __init__(self, device, numel):
+        self.buf = torch.zeros(numel, dtype=torch.float32, device=device)
+        self.off = 0
+
+    def reset(self):
+        self.buf.zero_()
+        self.off = 0
+
+    def take(self, B, C):
+        n = B * C * 2
+        if self.off + n > self.buf.numel():
+            raise RuntimeError("StatArena exhausted (repack() under-counted the normalised tensors)")
+        v = self.buf[self.off:self.off + n].view(B, C, 2)
+        self.off += n
+        return v
+
+
+def _with_stats(arena, make, B, C, S):
+    """Run `make(stat_or_None)` (a conv / linear launch) so that its output comes with GroupNorm sums: fused into the
+    epilogue when whole warps of accumulator rows belong to one sample, else by a separate statistics pass."""
+    stat = arena.take(B, C)
+    if S % 32 == 0:
+        return Act(make(stat), stat)
+    t = make(None)
+    ops.groupnorm_stats(t, stat)
+    return Act(t, stat)
+
+
 class TimestepBlock(nn.Module):
     """Any module whose run() takes the timestep-embedding vector as a second argument."""
 
@@ -57,10 +98,14 @@ class Upsample(nn.Module):
     def pack(self):
         return {"w": ops.pack_conv_weight(self.conv.weight), "b": _f(self.conv.bias)} if self.use_conv else {}
 
-    def run(self, pk, x):
+    def run(self, pk, x, arena):
         # dims == 3 keeps D and doubles H, W (the inherited "video" convention, :150-153); dims == 4 is isotropic
-        x = ops.upsample_nearest(x, (1, 2, 2) if self.dims == 3 else (2, 2, 2))
-        return ops.conv3d(x, pk["w"], bias=pk["b"]) if self.use_conv else x
+        u = ops.upsample_nearest(x.t, (1, 2, 2) if self.dims == 3 else (2, 2, 2))
+        B, D, H, W, _ = u.shape
+        if not self.use_conv:
+            stat = arena.take(B, self.channels)
+            return Act(u, ops.groupnorm_stats(u, stat))
+        return _with_stats(arena, lambda st: ops.conv3d(u, pk["w"], bias=pk["b"], stat_sum=st), B, self.out_channels, D * H * W)
 
 
 class Downsample(nn.Module):
@@ -78,8 +123,11 @@ class Downsample(nn.Module):
     def pack(self):
         return {"w": ops.pack_conv_weight(self.op.weight), "b": _f(self.op.bias)}
 
-    def run(self, pk, x):
-        return ops.conv3d(x, pk["w"], stride=self.stride, bias=pk["b"])
+    def run(self, pk, x, arena):
+        B, D, H, W, _ = x.t.shape
+        So = (D // self.stride[0]) * (H // self.stride[1]) * (W // self.stride[2])
+        return _with_stats(arena, lambda st: ops.conv3d(x.t, pk["w"], stride=self.stride, bias=pk["b"], stat_sum=st), B,
+                           self.out_channels, So)
 
 
 class ResBlock(TimestepBlock):
@@ -114,20 +162,20 @@ class ResBlock(TimestepBlock):
             pk["bs"] = _f(self.skip_connection.bias)
         return pk
 
-    def run(self, pk, x, emb_vec, skip=None):
-        """x (and optionally the encoder skip tensor, logically concatenated after x on the channel axis):
-        (B, D, H, W, C) bf16; emb_vec: fp32 (B, out_channels) = emb_layers(emb)."""
-        B, C = x.shape[0], self.out_channels
-        a = ops.groupnorm(x, *pk["gn1"], eps=self.in_layers[0].eps, act=ops.ACT_SILU, x2=skip)
-        S = x.shape[1] * x.shape[2] * x.shape[3]
-        stat = ops.zero_stat_buffer(x.device, B, C) if S % 32 == 0 else None   # fused sums need whole warps per sample
-        h = ops.conv3d(a, pk["w1"], bias=pk["b1"], rowvec=emb_vec, stat_sum=stat)          # conv + bias + emb, GN sums fused
-        a = ops.groupnorm(h, *pk["gn2"], eps=self.out_layers[0].eps, act=ops.ACT_SILU, stat_sum=stat)
+    def run(self, pk, x, emb_vec, arena, skip=None):
+        """x (and optionally the encoder skip tensor, logically concatenated after x on the channel axis): Act over
+        (B, D, H, W, C) bf16; emb_vec: fp32 (B, out_channels) = emb_layers(emb).  Returns the block output as an Act."""
+        B, D, H, W, _ = x.t.shape
+        S, C = D * H * W, self.out_channels
+        a = ops.groupnorm_fused(x.t, x.stat, *pk["gn1"], eps=self.in_layers[0].eps, act=ops.ACT_SILU,
+                                x2=None if skip is None else skip.t, stat2=None if skip is None else skip.stat)
+        h = _with_stats(arena, lambda st: ops.conv3d(a, pk["w1"], bias=pk["b1"], rowvec=emb_vec, stat_sum=st), B, C, S)
+        a = ops.groupnorm_fused(h.t, h.stat, *pk["gn2"], eps=self.out_layers[0].eps, act=ops.ACT_SILU)
         if "ws" in pk:
-            res = ops.linear_tokens(x, pk["ws"], bias=pk["bs"], x2=skip)                    # 1x1x1 skip on the raw concat
+            res = ops.linear_tokens(x.t, pk["ws"], bias=pk["bs"], x2=None if skip is None else skip.t)   # 1x1x1 skip on the raw concat
         else:
-            res = x
-        return ops.conv3d(a, pk["w2"], bias=pk["b2"], residual=res)
+            res = x.t
+        return _with_stats(arena, lambda st: ops.conv3d(a, pk["w2"], bias=pk["b2"], residual=res, stat_sum=st), B, C, S)
 
 
 class UNet3DModel(nn.Module):
@@ -239,6 +287,7 @@ class UNet3DModel(nn.Module):
                                    _f(self.time_embed[2].weight), _f(self.time_embed[2].bias))}
         emb_w, emb_b, ca_w, ca_b = [], [], [], []
         emb_off = ca_off = 0
+        stat_channels = 0            # total channels of all tensors that carry GroupNorm sums (sizes the StatArena)
         for bi, block in enumerate(self._blocks()):
             entries = []
             for layer in block:
@@ -246,6 +295,7 @@ class UNet3DModel(nn.Module):
                     e = {"kind": "res", "pk": layer.pack(getattr(layer, "skip_in_channels", 0)), "emb": (emb_off, layer.out_channels)}
                     emb_w.append(_f(layer.emb_layers[1].weight)); emb_b.append(_f(layer.emb_layers[1].bias))
                     emb_off += layer.out_channels
+                    stat_channels += 2 * layer.out_channels
                 elif isinstance(layer, SpatialTransformer3D):
                     offs = []
                     for tb in layer.transformer_blocks:
@@ -253,17 +303,22 @@ class UNet3DModel(nn.Module):
                         ca_w.append(w); ca_b.append(b)
                         offs.append((ca_off, w.shape[0])); ca_off += w.shape[0]
                     e = {"kind": "st", "pk": layer.pack(), "ca": offs}
+                    stat_channels += layer.in_channels
                 elif isinstance(layer, (Downsample, Upsample)):
                     e = {"kind": "resample", "pk": layer.pack()}
+                    stat_channels += layer.out_channels
                 elif isinstance(layer, nn.Conv3d):      # the stem: few input channels -> im2col + GEMM
                     wp, kp = ops.pack_patch_weight(layer.weight)
                     e = {"kind": "stem", "pk": {"w": wp, "b": _f(layer.bias), "kp": kp}}
+                    stat_channels += layer.out_channels
                 else:
                     raise TypeError(f"unexpected layer {type(layer)}")
                 entries.append(e)
             pk["blocks"].append(entries)
         pk["emb_w"], pk["emb_b"] = torch.cat(emb_w).contiguous(), torch.cat(emb_b).contiguous()
         pk["ca_w"], pk["ca_b"] = torch.cat(ca_w).contiguous(), torch.cat(ca_b).contiguous()
+        pk["stat_channels"] = stat_channels
+        self._arenas = {}
         pk["out_gn"] = (_f(self.out[0].weight), _f(self.out[0].bias))
         pk["out_w"], pk["out_b"] = ops.pack_small_cout_conv(self.out[2].weight), _f(self.out[2].bias)
         self._packed, self._packed_key = pk, self._version_key()
@@ -307,24 +362,31 @@ class UNet3DModel(nn.Module):
         emb_vecs = ops.linear_small(emb, pk["emb_w"], pk["emb_b"], act_in=ops.ACT_SILU)     # every ResBlock's emb_layers at once
         ca_vecs = context_vecs if context_vecs is not None else self.context_vectors(context)
 
+        arena = self._arenas.get(B)
+        if arena is None:
+            arena = self._arenas[B] = StatArena(x.device, B * pk["stat_channels"] * 2)
+        arena.reset()
+
         def run_block(block, entries, h, skip=None):
             for layer, e in zip(block, entries):
                 if e["kind"] == "res":
                     off, n = e["emb"]
-                    h = layer.run(e["pk"], h, emb_vecs[:, off:off + n], skip=skip)
+                    h = layer.run(e["pk"], h, emb_vecs[:, off:off + n], arena, skip=skip)
                     skip = None
                 elif e["kind"] == "st":
-                    h = layer.run(e["pk"], h, [ca_vecs[:, o:o + n] for o, n in e["ca"]])
+                    h = layer.run(e["pk"], h, [ca_vecs[:, o:o + n] for o, n in e["ca"]], arena)
                 elif e["kind"] == "resample":
-                    h = layer.run(e["pk"], h)
+                    h = layer.run(e["pk"], h, arena)
                 else:
                     col = ops.im2col_small(h, batch=B, kp=e["pk"]["kp"])
-                    h = ops.linear_tokens(col, e["pk"]["w"], bias=e["pk"]["b"])
+                    S = col.shape[1] * col.shape[2] * col.shape[3]
+                    h = _with_stats(arena, lambda st: ops.linear_tokens(col, e["pk"]["w"], bias=e["pk"]["b"], stat_sum=st), B,
+                                    layer.out_channels, S)
             return h
 
         entries = pk["blocks"]
         n_in = len(self.input_blocks)
-        hs: List[torch.Tensor] = []
+        hs: List[Act] = []
         h = x
         for i, block in enumerate(self.input_blocks):
             h = run_block(block, entries[i], h)
@@ -332,5 +394,5 @@ class UNet3DModel(nn.Module):
         h = run_block(self.middle_block, entries[n_in], h)
         for i, block in enumerate(self.output_blocks):
             h = run_block(block, entries[n_in + 1 + i], h, skip=hs.pop())    # th.cat([h, hs.pop()], dim=1), never materialised raw
-        a = ops.groupnorm(h, *pk["out_gn"], eps=self.out[0].eps, act=ops.ACT_SILU)
+        a = ops.groupnorm_fused(h.t, h.stat, *pk["out_gn"], eps=self.out[0].eps, act=ops.ACT_SILU)
         return ops.conv3d_small_cout(a, pk["out_w"], pk["out_b"], self.out_channels)

@@ -24,7 +24,7 @@ __all__ = [
     "ACT_NONE", "ACT_SILU", "ACT_GELU", "ACT_GEGLU", "pack_geglu_weight", "pack_patch_weight", "conv3d", "linear_tokens", "groupnorm", "layernorm", "attention",
     "geglu", "upsample_nearest", "im2col_small", "timestep_embedding", "linear_small", "ddim_step",
     "q_sample", "to_channels_last", "to_ncdhw", "pack_conv_weight", "pack_linear_weight", "launch_count",
-    "reset_launch_count", "zero_stat_buffer", "ConvProfiler", "vq_quantize", "channel_mix", "pack_small_cout_conv", "conv3d_small_cout", "gcn_gather_triples", "gcn_scatter_mean",
+    "reset_launch_count", "zero_stat_buffer", "groupnorm_stats", "groupnorm_fused", "ConvProfiler", "vq_quantize", "channel_mix", "pack_small_cout_conv", "conv3d_small_cout", "gcn_gather_triples", "gcn_scatter_mean",
     "batchnorm_relu", "add_rows",
 ]
 
@@ -295,6 +295,38 @@ def groupnorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, group
     if x2 is not None:
         check(lib.cs_groupnorm_apply(x2.data_ptr(), B, S, C2, p2, ss.data_ptr() + C1 * 8, Ct,
                                      out.data_ptr() + C1 * 2, op, act, st), "cs_groupnorm_apply")
+    return out
+
+
+def groupnorm_stats(x: torch.Tensor, stat: torch.Tensor) -> torch.Tensor:
+    """Accumulate the per-(sample, channel) sum / sum of squares of x into the ZEROED fp32 buffer stat (B, C, 2)."""
+    B, D, H, W, Cc, p = _check_act(x, "groupnorm_stats.x")
+    check(_lib.load().cs_groupnorm_stats(x.data_ptr(), B, D * H * W, Cc, p, stat.data_ptr(), Cc, _stream()), "cs_groupnorm_stats")
+    return stat
+
+
+def groupnorm_fused(x: torch.Tensor, stat: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, groups: int = 32,
+                    eps: float = 1e-5, act: int = ACT_NONE, x2: Optional[torch.Tensor] = None,
+                    stat2: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """act(GroupNorm(cat(x, x2))) from per-channel sums that already exist (`stat`, `stat2`: fp32 (B, C, 2) written by the
+    producing conv's epilogue or by groupnorm_stats).  One kernel per source; nothing is cleared."""
+    lib = _lib.load()
+    B, D, H, W, C1, p1 = _check_act(x, "groupnorm_fused.x")
+    S = D * H * W
+    C2 = 0
+    if x2 is not None:
+        _, _, _, _, C2, p2 = _check_act(x2, "groupnorm_fused.x2")
+    Ct = C1 + C2
+    if out is None:
+        out = torch.empty((B, D, H, W, Ct), dtype=torch.bfloat16, device=x.device)
+    op = out.stride(3)
+    st = _stream()
+    g, bta = _ptr(_f32(gamma, "gamma")), _ptr(_f32(beta, "beta"))
+    check(lib.cs_groupnorm_apply_fused(x.data_ptr(), B, S, C1, p1, 0, stat.data_ptr(), C1, _ptr(stat2), C2, g, bta, groups, eps,
+                                       out.data_ptr(), op, act, st), "cs_groupnorm_apply_fused")
+    if x2 is not None:
+        check(lib.cs_groupnorm_apply_fused(x2.data_ptr(), B, S, C2, p2, C1, stat.data_ptr(), C1, stat2.data_ptr(), C2, g, bta,
+                                           groups, eps, out.data_ptr() + C1 * 2, op, act, st), "cs_groupnorm_apply_fused")
     return out
 
 

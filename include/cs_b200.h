@@ -88,6 +88,15 @@ int cs_groupnorm_apply(const void* x, int32_t B, int32_t S, int32_t C, int32_t p
                        const float* scale_shift, int32_t ss_pitch, void* y, int32_t y_pitch, int32_t act,
                        cs_stream_t stream);
 
+/* finalize + apply in one pass: y = act(GroupNorm(cat(x1, x2)))[channels ch_off .. ch_off+C) of the concatenation], where
+ * stat1 [B][C1][2] / stat2 [B][C2][2] (or NULL) hold the per-channel (sum, sum of squares) of the two concatenated sources
+ * (written by cs_conv3d's stat_sum epilogue or cs_groupnorm_stats); x is the source that owns those channels.  The sums
+ * are read only, so one tensor can be normalised by several consumers. */
+int cs_groupnorm_apply_fused(const void* x, int32_t B, int32_t S, int32_t C, int32_t pitch, int32_t ch_off,
+                             const float* stat1, int32_t C1, const float* stat2, int32_t C2, const float* gamma,
+                             const float* beta, int32_t groups, float eps, void* y, int32_t y_pitch, int32_t act,
+                             cs_stream_t stream);
+
 /* ---- LayerNorm over the last dim (nn.LayerNorm, attention.py:229-231) ------------------------ */
 int cs_layernorm(const void* x, int64_t M, int32_t C, int32_t pitch, const float* gamma, const float* beta,
                  float eps, void* y, int32_t y_pitch, cs_stream_t stream);

@@ -42,3 +42,12 @@ ev[1].record(); torch.cuda.synchronize()
 ms = ev[0].elapsed_time(ev[1]) / 5
 print(f"graph: {ms:.2f} ms per UNet(B={B}) -> {1000 / ms:.2f} denoising-steps/s; {B * 557.6e9 / ms / 1e9:.1f} TFLOP/s")
 print("finite:", bool(torch.isfinite(eps).all()), "absmean", float(eps.abs().mean()))
+
+# box speed index: sustained cuBLAS bf16 GEMM on the same box right after the run (boxes differ by +-20 %)
+a = torch.randn(8192, 8192, device="cuda", dtype=torch.bfloat16); b2 = torch.randn(8192, 8192, device="cuda", dtype=torch.bfloat16)
+for _ in range(10): a @ b2
+torch.cuda.synchronize(); ev[0].record()
+for _ in range(100): a @ b2
+ev[1].record(); torch.cuda.synchronize()
+cub = 100 * 2 * 8192 ** 3 / ev[0].elapsed_time(ev[1]) / 1e9
+print(f"box index: cuBLAS bf16 8192^3 sustained {cub:.0f} TFLOP/s -> whole-step fraction {B * 557.6e9 / ms / 1e9 / cub:.3f}")
