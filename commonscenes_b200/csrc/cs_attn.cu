@@ -242,6 +242,10 @@ static int attention_launch_t(const void* q, const void* k, const void* v, void*
                                                              d_out, scale, st);                                      \
     return attention_launch_t<DPV, 64>(q, k, v, out, B, H, Nq, Nk, q_pitch, kv_pitch, o_pitch, d_out, scale, st);
 
+int attention_tc_launch(const void* q, const void* k, const void* v, void* out, int B, int H, int N, int q_pitch,
+                        int kv_pitch, int o_pitch, int d_out, float scale, cudaStream_t st);
+int igemm_debug_flags();
+
 int attention_launch(const void* q, const void* k, const void* v, void* out, int B, int H, int Nq, int Nk,
                      int Dp, int q_pitch, int kv_pitch, int o_pitch, int d_out, float scale, cudaStream_t st) {
   if (q_pitch % 8 || kv_pitch % 8 || o_pitch % 2 || d_out % 2 || d_out > Dp || Nk < 1)
@@ -249,6 +253,8 @@ int attention_launch(const void* q, const void* k, const void* v, void* out, int
   if (reinterpret_cast<uintptr_t>(q) % 16 || reinterpret_cast<uintptr_t>(k) % 16 ||
       reinterpret_cast<uintptr_t>(v) % 16 || reinterpret_cast<uintptr_t>(out) % 4 || (H * d_out) % 2)
     return set_error(CS_ERR_INVALID, "attention: q/k/v must be 16-byte aligned");
+  if (Dp == 64 && Nq == Nk && Nq % 128 == 0 && !(igemm_debug_flags() & 128))   // tcgen05 path (cs_attn_tc.cu)
+    return attention_tc_launch(q, k, v, out, B, H, Nq, q_pitch, kv_pitch, o_pitch, d_out, scale, st);
   switch (Dp) {
     CS_ATTN_DISPATCH(32)
     CS_ATTN_DISPATCH(64)

@@ -528,6 +528,7 @@ static int pick_tile_box(int B, int Do, int Ho, int Wo, int* bb, int* bd, int* b
 
 static int g_debug_flags = 0;
 void igemm_set_debug(int flags) { g_debug_flags = flags; }
+int igemm_debug_flags() { return g_debug_flags; }
 
 int igemm_launch(const IgemmArgs& a, cudaStream_t stream) {
   if (a.C1 <= 0 || a.C1 % 8 || a.C2 % 8 || a.Cout <= 0) return set_error(CS_ERR_INVALID, "igemm: channels must be multiples of 8");

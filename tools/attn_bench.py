@@ -1,0 +1,26 @@
+"""Self-attention core timing at the denoiser's level-1 shape (B=64, 8 heads, N=1024, d=56 padded to 64)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from commonscenes_b200 import _lib, ops
+B, H, N, d, dp = 64, 8, 1024, 56, 64
+qkv = torch.randn(B, N, 3 * H * dp, device="cuda").to(torch.bfloat16)
+q, k, v = (qkv[:, :, i * H * dp:(i + 1) * H * dp] for i in range(3))
+fl = 4.0 * B * H * N * N * d
+for name, flag in (("tcgen05", 0), ("mma.sync", 128)):
+    _lib.load().cs_debug_set(flag)
+    for _ in range(3):
+        o = ops.attention(q, k, v, heads=H, head_dim=d, head_dim_padded=dp, scale=d ** -0.5)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        o = ops.attention(q, k, v, heads=H, head_dim=d, head_dim_padded=dp, scale=d ** -0.5)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    print(f"{name:9s}: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s (unpadded FLOPs)")
+    if flag == 0:
+        o_tc = o.float()
+    else:
+        print("max |tc - mma.sync| =", float((o_tc - o.float()).abs().max()))
+_lib.load().cs_debug_set(0)
