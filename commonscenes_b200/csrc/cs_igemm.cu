@@ -291,6 +291,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
       int acc = 0;                       // next accumulator buffer for a single tile
       uint32_t buf_phase[2] = {0, 0};    // per-buffer use parity (pairs use both buffers, singles alternate)
       const uint32_t idesc = umma_idesc_bf16_m128(static_cast<uint32_t>(p.BN));
+      const uint32_t desc_hi = static_cast<uint32_t>(umma_desc_k_sw128(0) >> 32);
+      const uint32_t smem_base_u = smem_u32(smem);
+      const uint32_t b_off = static_cast<uint32_t>(p.mt * kABytes);
+      const int ks_last1 = (min(64, p.C1 - (nch1 - 1) * 64) + 15) >> 4;
+      const int ks_last2 = nch2 ? (min(64, p.C2 - (nch2 - 1) * 64) + 15) >> 4 : 4;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         int mt_first, cnt, nt;
         decode_item(p, tile, mt_first, cnt, nt);
@@ -300,24 +305,34 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(a0 * 256);
         uint32_t accumulate = 0;
+        // Lean issue loop: this single thread must stay ahead of the tensor pipe, so descriptors are built from
+        // 32-bit halves (constant high word, low word = encoded smem address + 2 per 16-element K step).
         for (int tap = 0; tap < ntaps; ++tap) {
           for (int ch = 0; ch < nch; ++ch) {
-            const int valid = (ch < nch1) ? min(64, p.C1 - ch * 64) : min(64, p.C2 - (ch - nch1) * 64);
-            const int ksteps = (valid + 15) >> 4;
+            const int ksteps = (ch == nch1 - 1) ? ks_last1 : ((ch == nch - 1) ? ks_last2 : 4);
             mbar_wait(&bars.full[stage], phase);
             tc_fence_after();
-            const uint32_t sa = smem_u32(smem + stage * stage_bytes);
-            const uint64_t adesc = umma_desc_k_sw128(sa);
-            const uint64_t adesc2 = umma_desc_k_sw128(sa + kABytes);
-            const uint64_t bdesc = umma_desc_k_sw128(sa + p.mt * kABytes);
-            for (int k = 0; k < ksteps && !(p.debug & 4); ++k) {
-              // +32 bytes (= 16 bf16) along K inside the 128-byte swizzled row
-              umma_bf16(d_tmem, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2),
-                        idesc, accumulate);
-              if (cnt == 2)
-                umma_bf16(d_tmem + 256u, adesc2 + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2),
-                          idesc, accumulate);
-              accumulate = 1;
+            const uint32_t sa = smem_base_u + static_cast<uint32_t>(stage * stage_bytes);
+            const uint32_t a_lo = ((sa >> 4) & 0x3FFFu) | 0x10000u;
+            const uint32_t a2_lo = (((sa + kABytes) >> 4) & 0x3FFFu) | 0x10000u;
+            const uint32_t b_lo = (((sa + b_off) >> 4) & 0x3FFFu) | 0x10000u;
+            if (!(p.debug & 4)) {
+              if (cnt == 2) {
+#pragma unroll 4
+                for (int k = 0; k < ksteps; ++k) {
+                  const uint64_t bd = (static_cast<uint64_t>(desc_hi) << 32) | (b_lo + 2u * k);
+                  umma_bf16(d_tmem, (static_cast<uint64_t>(desc_hi) << 32) | (a_lo + 2u * k), bd, idesc, accumulate);
+                  umma_bf16(d_tmem + 256u, (static_cast<uint64_t>(desc_hi) << 32) | (a2_lo + 2u * k), bd, idesc, accumulate);
+                  accumulate = 1;
+                }
+              } else {
+#pragma unroll 4
+                for (int k = 0; k < ksteps; ++k) {
+                  umma_bf16(d_tmem, (static_cast<uint64_t>(desc_hi) << 32) | (a_lo + 2u * k),
+                            (static_cast<uint64_t>(desc_hi) << 32) | (b_lo + 2u * k), idesc, accumulate);
+                  accumulate = 1;
+                }
+              }
             }
             umma_commit(&bars.empty[stage]);  // frees the smem stage once these MMAs retire
             if (++stage == p.stages) { stage = 0; phase ^= 1; }

@@ -45,3 +45,10 @@ for i, (ci, co, (D, H, W), k, st, cnt) in enumerate(SHAPES):
     print(f"[{i:2d}] {ci:5d}->{co:5d} k{k} s{st} @{D}x{H}x{W}: {ms:8.3f} ms  {fl / ms / 1e9:8.1f} TFLOP/s  x{cnt}  ({ms * cnt:7.2f} ms/eval)")
 if only is None:
     print(f"sum over one UNet eval: {tot_ms:.2f} ms, {tot_fl / tot_ms / 1e9:.1f} TFLOP/s")
+
+a = torch.randn(8192, 8192, device="cuda", dtype=torch.bfloat16); b2 = torch.randn(8192, 8192, device="cuda", dtype=torch.bfloat16)
+for _ in range(10): a @ b2
+torch.cuda.synchronize(); e0.record()
+for _ in range(50): a @ b2
+e1.record(); torch.cuda.synchronize()
+print(f"box index: cuBLAS bf16 8192^3 {50 * 2 * 8192 ** 3 / e0.elapsed_time(e1) / 1e9:.0f} TFLOP/s")
