@@ -226,7 +226,8 @@ __host__ __device__ __forceinline__ uint32_t umma_idesc_bf16_m128(uint32_t n) {
 // ----------------------------------------------------------------------------------------------
 // small numeric helpers
 // ----------------------------------------------------------------------------------------------
-__device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
+// x * sigmoid(x); approximate division (MUFU.RCP + FMUL, <= 2 ulp) keeps the bandwidth-bound kernels off the issue limit
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.f + __expf(-x)); }
 __device__ __forceinline__ float gelu_erf_f(float x) {
   return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
 }

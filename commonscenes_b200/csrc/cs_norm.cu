@@ -190,56 +190,84 @@ __global__ void gn_apply_fused_kernel(const __nv_bfloat16* __restrict__ x, int S
 }
 
 // ------------------------------------------------------------------------------------------------
-// LayerNorm over the last dim; one warp per row; C % 8 == 0, C <= 1024
+// LayerNorm over the last dim; C % 8 == 0, C <= 1024.  One warp normalises RPW rows at a time (their loads and the
+// two butterfly reductions are independent, which is what hides the memory latency of this bandwidth-bound kernel).
 // ------------------------------------------------------------------------------------------------
+template <int VPL, int RPW>
 __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long M, int C, int pitch,
                                  const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                  __nv_bfloat16* __restrict__ y, int y_pitch) {
   const int lane = threadIdx.x & 31;
   const int cv = C >> 3;
   const long long warps_total = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
-  for (long long row = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5); row < M; row += warps_total) {
-  float v[4][8];
-  float s = 0.f;
+  const float inv_c = 1.f / C;
+  for (long long row0 = (blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW; row0 < M;
+       row0 += warps_total * RPW) {
+    float v[RPW][VPL][8];
+    float s[RPW];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int vi = lane + 32 * k;
-    if (vi < cv) {
-      const uint4 u = *reinterpret_cast<const uint4*>(x + row * pitch + vi * 8);
-      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    for (int r = 0; r < RPW; ++r) {
+      s[r] = 0.f;
+      const long long row = row0 + r;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = unpack_bf16x2(w[j]);
-        v[k][2 * j] = f.x; v[k][2 * j + 1] = f.y;
-        s += f.x + f.y;
+      for (int k = 0; k < VPL; ++k) {
+        const int vi = lane + 32 * k;
+        uint4 u = make_uint4(0u, 0u, 0u, 0u);
+        if (vi < cv && row < M) u = *reinterpret_cast<const uint4*>(x + row * pitch + vi * 8);
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = unpack_bf16x2(w[j]);
+          v[r][k][2 * j] = f.x; v[r][k][2 * j + 1] = f.y;
+          s[r] += f.x + f.y;
+        }
       }
     }
-  }
-  const float mean = warp_sum(s) / C;
-  float q = 0.f;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    if (lane + 32 * k < cv) {
+    for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { const float d = v[k][j] - mean; q += d * d; }
+      for (int r = 0; r < RPW; ++r) s[r] += __shfl_xor_sync(0xffffffffu, s[r], o);
+    float q[RPW];
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+      const float mean = s[r] * inv_c;
+      s[r] = mean;
+      q[r] = 0.f;
+#pragma unroll
+      for (int k = 0; k < VPL; ++k)
+        if (lane + 32 * k < cv) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { const float d = v[r][k][j] - mean; q[r] += d * d; }
+        }
     }
-  }
-  const float rstd = rsqrtf(warp_sum(q) / C + eps);
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int vi = lane + 32 * k;
-    if (vi < cv) {
-      uint32_t o[4];
+    for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int c = vi * 8 + 2 * j;
-        const float y0 = (v[k][2 * j] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
-        const float y1 = (v[k][2 * j + 1] - mean) * rstd * __ldg(gamma + c + 1) + __ldg(beta + c + 1);
-        o[j] = pack_bf16x2(y0, y1);
+      for (int r = 0; r < RPW; ++r) q[r] += __shfl_xor_sync(0xffffffffu, q[r], o);
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const int vi = lane + 32 * k;
+      if (vi < cv) {
+        float g[8], bt[8];
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8 + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8)), b1 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8 + 4));
+        g[0] = g0.x; g[1] = g0.y; g[2] = g0.z; g[3] = g0.w; g[4] = g1.x; g[5] = g1.y; g[6] = g1.z; g[7] = g1.w;
+        bt[0] = b0.x; bt[1] = b0.y; bt[2] = b0.z; bt[3] = b0.w; bt[4] = b1.x; bt[5] = b1.y; bt[6] = b1.z; bt[7] = b1.w;
+#pragma unroll
+        for (int r = 0; r < RPW; ++r) {
+          const long long row = row0 + r;
+          if (row < M) {
+            const float rstd = rsqrtf(q[r] * inv_c + eps);
+            uint32_t o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              o[j] = pack_bf16x2((v[r][k][2 * j] - s[r]) * rstd * g[2 * j] + bt[2 * j],
+                                 (v[r][k][2 * j + 1] - s[r]) * rstd * g[2 * j + 1] + bt[2 * j + 1]);
+            *reinterpret_cast<uint4*>(y + row * y_pitch + vi * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+          }
+        }
       }
-      *reinterpret_cast<uint4*>(y + row * y_pitch + vi * 8) = make_uint4(o[0], o[1], o[2], o[3]);
     }
-  }
   }
 }
 
@@ -304,13 +332,23 @@ int gn_apply_launch(const void* x, int B, int S, int C, int pitch, const float* 
 int layernorm_launch(const void* x, long long M, int C, int pitch, const float* gamma, const float* beta,
                      float eps, void* y, int y_pitch, cudaStream_t st) {
   if (C % 8 || C > 1024 || pitch % 8 || y_pitch % 8) return set_error(CS_ERR_INVALID, "layernorm: C % 8, C <= 1024");
+  if (reinterpret_cast<uintptr_t>(gamma) % 16 || reinterpret_cast<uintptr_t>(beta) % 16)
+    return set_error(CS_ERR_INVALID, "layernorm: gamma/beta must be 16-byte aligned");
   const int warps = 8;
-  long long blocks = (M + warps - 1) / warps;
-  const long long cap = static_cast<long long>(num_sms()) * 8;   // grid-stride over rows: 8 resident CTAs per SM
+  const int vpl = (C / 8 + 31) / 32;                             // 16-byte vectors per lane
+  const int rpw = vpl <= 2 ? 4 : 2;                              // rows in flight per warp
+  long long blocks = (M + warps * rpw - 1) / (warps * rpw);
+  const long long cap = static_cast<long long>(num_sms()) * 6;   // grid-stride over rows
   if (blocks > cap) blocks = cap;
-  layernorm_kernel<<<static_cast<unsigned>(blocks), warps * 32, 0, st>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x), M, C, pitch, gamma, beta, eps,
-      reinterpret_cast<__nv_bfloat16*>(y), y_pitch);
+  const unsigned g = static_cast<unsigned>(blocks);
+  const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x);
+  __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(y);
+  switch (vpl) {
+    case 1: layernorm_kernel<1, 4><<<g, warps * 32, 0, st>>>(xp, M, C, pitch, gamma, beta, eps, yp, y_pitch); break;
+    case 2: layernorm_kernel<2, 4><<<g, warps * 32, 0, st>>>(xp, M, C, pitch, gamma, beta, eps, yp, y_pitch); break;
+    case 3: layernorm_kernel<3, 2><<<g, warps * 32, 0, st>>>(xp, M, C, pitch, gamma, beta, eps, yp, y_pitch); break;
+    default: layernorm_kernel<4, 2><<<g, warps * 32, 0, st>>>(xp, M, C, pitch, gamma, beta, eps, yp, y_pitch); break;
+  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error(e, "layernorm: launch");
   count_launch();
