@@ -26,7 +26,6 @@
 
 namespace cs {
 
-static constexpr int kIgemmThreads = 320;  // TMA warp + MMA warp + 8 epilogue warps (two per TMEM lane quarter)
 static constexpr int kMaxStages = 8;
 static constexpr int kABytes = 128 * 128;  // 128 voxels x 64 bf16
 
@@ -62,7 +61,7 @@ __device__ __forceinline__ void colsum32(float (&a)[32], int lane) {
   }
 }
 
-__device__ __forceinline__ void epilogue_fast_tile(const IgemmParams& p, uint32_t t_row, int lane, int half,
+__device__ __forceinline__ void epilogue_fast_tile(const IgemmParams& p, uint32_t t_row, int lane, int half, int chunk_stride,
                                                    int warp_rows0, long long m_tile0, int b, int n0,
                                                    const float* __restrict__ colvec, uint8_t* __restrict__ stage) {
   // warp_rows0: first accumulator row of this warp inside the tile; m_tile0: global row of the tile's row 0.
@@ -71,7 +70,7 @@ __device__ __forceinline__ void epilogue_fast_tile(const IgemmParams& p, uint32_
   const long long m_w0 = m_tile0 + warp_rows0;
   const bool geglu = (p.act == CS_ACT_GEGLU);
   const int sw = (lane >> 1) & 3;                               // XOR swizzle of this lane's staging row (64-byte rows)
-  for (int c0 = half * 32; c0 < p.BN; c0 += 64) {
+  for (int c0 = half * 32; c0 < p.BN; c0 += chunk_stride) {
     const int n = n0 + c0;
     if (n >= p.Cout) break;                                     // warp-uniform
     const int ncols = min(32, min(p.BN - c0, p.Cout - n));      // 8, 16, 24 or 32
@@ -197,9 +196,15 @@ __device__ __forceinline__ void decode_item(const IgemmParams& p, int item, int&
   }
 }
 
-__global__ void __launch_bounds__(kIgemmThreads, 1)
+// EPI_WARPS == 8: one CTA per SM, double-buffered accumulator (512 TMEM columns), deep smem pipeline -- long K loops.
+// EPI_WARPS == 4: "light" variant for short K loops (linear layers): 192 threads, one 256-column accumulator, two smem
+// stages, so TWO CTAs fit on an SM and one CTA's epilogue / pipeline fill overlaps the other's main loop.
+template <int EPI_WARPS>
+__global__ void __launch_bounds__((2 + EPI_WARPS) * 32, EPI_WARPS == 4 ? 2 : 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
              const __grid_constant__ CUtensorMap tmW, const IgemmParams p) {
+  constexpr int kTmemCols = EPI_WARPS == 4 ? 256 : 512;
+  constexpr int kAccBufs = EPI_WARPS == 4 ? 1 : 2;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ IgemmBarriers bars;
 
@@ -225,12 +230,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&bars.tmem_full[a], 1);
-      mbar_init(&bars.tmem_empty[a], 8);
+      mbar_init(&bars.tmem_empty[a], EPI_WARPS);
     }
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(&bars.tmem_base, 512);
+    tmem_alloc(&bars.tmem_base, kTmemCols);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -344,7 +349,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
           umma_commit(&bars.tmem_full[1]);
           buf_phase[1] ^= 1;
         } else {
-          acc ^= 1;
+          acc = (acc + 1) % kAccBufs;
         }
       }
     }
@@ -357,6 +362,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
     uint32_t acc_phase = 0;
     const long long spatial = static_cast<long long>(p.Do) * p.Ho * p.Wo;
     const int half = (warp - 2) >> 2;  // fast path: which 32-column chunks this warp drains; generic path: half 1 idles
+    constexpr int kChunkStride = EPI_WARPS == 8 ? 64 : 32;
     if (p.fast_epilogue) {
       uint8_t* stage = smem + p.stages * stage_bytes + (warp - 2) * 2048;
       const int et = threadIdx.x - 64;                           // 0..255 among the epilogue threads
@@ -370,7 +376,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
           const long long m_tile0 = static_cast<long long>(mt_first + i) * p.rows;    // tiles are contiguous runs of voxels
           const int b = static_cast<int>(m_tile0 / spatial);                           // one sample per tile (bb == 1)
           // column vector for this tile (bias + per-sample vector), double buffered with the accumulator
-          for (int c = et; c < p.BN; c += 256) {
+          for (int c = et; c < p.BN; c += EPI_WARPS * 32) {
             float cv = 0.f;
             if (n0 + c < p.Cout) {
               if (p.bias) cv += __ldg(p.bias + n0 + c);
@@ -378,17 +384,17 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
             }
             bars.colvec[ab][c] = cv;
           }
-          asm volatile("bar.sync 1, 256;" ::: "memory");
+          asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
           mbar_wait(&bars.tmem_full[ab], buf_phase[ab]);
           tc_fence_after();
           const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(ab * 256);
-          if (!(p.debug & 2)) epilogue_fast_tile(p, t_row, lane, half, quarter * 32, m_tile0, b, n0, bars.colvec[ab], stage);
+          if (!(p.debug & 2)) epilogue_fast_tile(p, t_row, lane, half, kChunkStride, quarter * 32, m_tile0, b, n0, bars.colvec[ab], stage);
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&bars.tmem_empty[ab]);
           buf_phase[ab] ^= 1;
         }
-        if (cnt == 1) acc ^= 1;
+        if (cnt == 1) acc = (acc + 1) % kAccBufs;
       }
     } else
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -503,7 +509,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars.tmem_empty[acc]);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (++acc == kAccBufs) { acc = 0; acc_phase ^= 1; }
     }
   }
 
@@ -512,7 +518,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -619,8 +625,13 @@ int igemm_launch(const IgemmArgs& a, cudaStream_t stream) {
   }
   p.n_items = p.n_pair_items + (p.m_tiles - 2 * (p.n_pair_items / p.n_tiles)) * p.n_tiles;
   const int stage_bytes = p.mt * kABytes + bn * 128;
-  // 227 KB per CTA minus the kernel's static shared memory (barriers) and the 1 KB alignment slack
-  const int smem_budget = 227 * 1024 - 4096 - 8 * 2048;  // 8 x 2 KB epilogue staging buffers
+  // Short K loops (linear layers, <= 16 slabs): the light variant, two CTAs per SM.  Per-CTA shared memory budget is
+  // half an SM's 227 KB minus the driver's 1 KB per CTA, the static barriers and the alignment slack.
+  // Measured on B200 (profiles/r1_experiments.txt): 5-8 % SLOWER than the one-CTA variant on every linear shape of the
+  // denoiser -- the short-K GEMMs are limited by operand bytes in flight, not by pipeline bubbles -- so it is opt-in.
+  const bool light = p.mt == 1 && kiters <= 16 && (g_debug_flags & 256);
+  const int epi_warps = light ? 4 : 8;
+  const int smem_budget = (light ? 112 * 1024 : 227 * 1024) - 4096 - epi_warps * 2048;
   int stages = smem_budget / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return set_error(CS_ERR_INVALID, "igemm: tile too large for shared memory");
@@ -664,18 +675,23 @@ int igemm_launch(const IgemmArgs& a, cudaStream_t stream) {
 
   if (p.act == CS_ACT_GEGLU && (!p.fast_epilogue || bn % 32 || a.Cout % 32 || p.residual || p.stat_sum))
     return set_error(CS_ERR_INVALID, "igemm: GEGLU epilogue needs bf16 output, Cout % 32 == 0 and no residual/stats");
-  static int attr_smem = 0;
-  const int smem_bytes = stages * stage_bytes + 8 * 2048 + 1024;
-  if (smem_bytes > attr_smem) {
-    cudaError_t e = cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  static int attr_smem[2] = {0, 0};
+  const int smem_bytes = stages * stage_bytes + epi_warps * 2048 + 1024;
+  if (smem_bytes > attr_smem[light]) {
+    cudaError_t e = light ? cudaFuncSetAttribute(igemm_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)
+                          : cudaFuncSetAttribute(igemm_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return set_cuda_error(e, "igemm: cudaFuncSetAttribute");
-    attr_smem = smem_bytes;
+    attr_smem[light] = smem_bytes;
   }
   const int total = p.n_items;
-  int grid = total < num_sms() ? total : num_sms();
+  const int ctas = light ? 2 * num_sms() : num_sms();
+  int grid = total < ctas ? total : ctas;
   if ((g_debug_flags & 8) && grid > 74) grid = 74;   // experiment: half the SMs
   if ((g_debug_flags & 16) && grid > 37) grid = 37;  // experiment: a quarter of the SMs
-  igemm_kernel<<<grid, kIgemmThreads, smem_bytes, stream>>>(tmA1, tmA2, tmW, p);
+  if (light)
+    igemm_kernel<4><<<grid, 192, smem_bytes, stream>>>(tmA1, tmA2, tmW, p);
+  else
+    igemm_kernel<8><<<grid, 320, smem_bytes, stream>>>(tmA1, tmA2, tmW, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error(e, "igemm: launch");
   count_launch();
