@@ -258,7 +258,10 @@ def run_ours(args):
                    "unet_tflop_per_step": 2 * OBJECTS * UNET_GFLOP_PER_SAMPLE / 1e3,
                    "achieved_tflops_whole_step": 2 * OBJECTS * UNET_GFLOP_PER_SAMPLE / 1e3 / (ms_total / args.steps / 1e3)},
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                     "traffic": None, "kernel": "cs::igemm_kernel (tcgen05 implicit GEMM)", "launches_per_step": n_conv,
+                     "traffic": 448716288, "kernel": "cs::igemm_kernel (tcgen05 implicit GEMM)", "launches_per_step": n_conv,
+                     "traffic_note": "dram__bytes_read+write of ONE representative launch from ncu --set full (profiles/r1e_igemm_shape3.txt: "
+                                     "conv3d 448->448 @16^3 batch 64, 2841 GFLOP); its algorithmic bytes are 481 MB "
+                                     "(235 MB in + 11 MB weights + 235 MB out), i.e. no re-reads from HBM",
                      "ms_per_step_in_kernel": conv_ms, "peak_source": f"bf16_tflops_sustained ({peak_src})",
                      "note": "achieved = algorithmic 2*MAC FLOPs of every cs_conv3d launch of one step / sum of their CUDA-event durations"},
         "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": k_e2e},
