@@ -97,6 +97,9 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError = header/library mismatch
         fn.restype = res
         fn.argtypes = args
+    flags = os.environ.get("CS_DEBUG_FLAGS")
+    if flags:   # tuning experiments only (see cs_debug_set in include/cs_b200.h)
+        lib.cs_debug_set(int(flags))
     _lib = lib
     return lib
 
