@@ -68,6 +68,7 @@ SIGNATURES = {
     "cs_batchnorm_relu": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _f32, _f32, _i32, _vp, _i32, _vp]),
     "cs_add_rows": (_i32, [_vp, _i32, _vp, _i32, _i32, _i32, _vp, _i32, _vp]),
     "cs_tap_gather": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "cs_cast_f32_to_bf16": (_i32, [_vp, _i64, _vp, _vp]),
     "cs_debug_set": (None, [_i32]),
     "cs_vq_quantize": (_i32, [_vp, _i32, _i32, _i64, _vp, _i32, _vp, _vp, _i32, _vp, _vp, _vp]),
 }

@@ -36,6 +36,7 @@ int batchnorm_relu_launch(const float*, int, int, int, const float*, const float
                           float*, int, cudaStream_t);
 int add_rows_launch(const float*, int, const float*, int, int, int, float*, int, cudaStream_t);
 void igemm_set_debug(int);
+int cast_bf16_launch(const float*, long long, void*, cudaStream_t);
 int vq_quantize_launch(const float*, int, int, long long, const float*, int, const float*, const float*, int, float*,
                        long long*, cudaStream_t);
 }  // namespace cs
@@ -188,6 +189,10 @@ int cs_groupnorm_apply_fused(const void* x, int32_t B, int32_t Sp, int32_t C, in
   if (!x || !stat1 || !y) return cs::set_error(CS_ERR_INVALID, "cs_groupnorm_apply_fused: null pointer");
   return cs::gn_apply_fused_launch(x, B, Sp, C, pitch, ch_off, stat1, C1, stat2, C2, gamma, beta, groups, eps, y, y_pitch,
                                    act, S(stream));
+}
+
+int cs_cast_f32_to_bf16(const float* x, int64_t n, void* y, cs_stream_t stream) {
+  return cs::cast_bf16_launch(x, n, y, S(stream));
 }
 
 }  // extern "C"

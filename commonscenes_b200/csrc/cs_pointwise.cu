@@ -374,4 +374,16 @@ int tap_gather_launch(const float* y, int B, int Cy, int Co, int D, int H, int W
   CS_LAUNCH_CHECK("tap_gather");
 }
 
+// ------------------------------------------------------------------------------------------------
+// fp32 -> bf16 row-pitched copy (context keys / values of the generic cross-attention path)
+__global__ void cast_bf16_kernel(const float* __restrict__ x, long long n, __nv_bfloat16* __restrict__ y) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    y[i] = __float2bfloat16_rn(x[i]);
+}
+int cast_bf16_launch(const float* x, long long n, void* y, cudaStream_t st) {
+  cast_bf16_kernel<<<grid_for(n, 256, 8), 256, 0, st>>>(x, n, reinterpret_cast<__nv_bfloat16*>(y));
+  CS_LAUNCH_CHECK("cast_bf16");
+}
+
 }  // namespace cs

@@ -122,6 +122,31 @@ class CrossAttention(nn.Module):
         o = ops.attention(q, k, v, heads=h, head_dim=d, head_dim_padded=dp, scale=self.scale)
         return ops.linear_tokens(o.view(B, D, H, W, h * d), pk["wo"], bias=pk["bo"], rowvec=rowvec, residual=residual)
 
+    # --- generic cross-attention over a multi-token context (API completeness; v2_full always has ONE token) ---
+    def pack_cross(self):
+        h, d = self.heads, self.dim_head
+        dp = _pad_head_dim(d)
+
+        def padded(lin):
+            w = torch.zeros(h, dp, lin.weight.shape[1], dtype=torch.float32, device=lin.weight.device)
+            w[:, :d] = lin.weight.detach().float().reshape(h, d, -1)
+            return w.reshape(h * dp, -1)
+        return {"wq": ops.pack_linear_weight(padded(self.to_q)), "wk": padded(self.to_k).contiguous(),
+                "wv": padded(self.to_v).contiguous(), "dp": dp,
+                "wo": ops.pack_linear_weight(self.to_out[0].weight), "bo": self.to_out[0].bias.detach().float().contiguous()}
+
+    def run_cross(self, pk, x_ln, context, residual):
+        """to_out(softmax(q k^T * scale) v) + bias + residual with k, v projected from `context` (B, M, context_dim) fp32."""
+        B, D, H, W, _ = x_ln.shape
+        h, d, dp = self.heads, self.dim_head, pk["dp"]
+        M = context.shape[1]
+        q = ops.linear_tokens(x_ln, pk["wq"]).view(B, D * H * W, h * dp)
+        ctx = context.float().reshape(B * M, -1).contiguous()
+        k = ops.cast_bf16(ops.linear_small(ctx, pk["wk"])).view(B, M, h * dp)
+        v = ops.cast_bf16(ops.linear_small(ctx, pk["wv"])).view(B, M, h * dp)
+        o = ops.attention(q, k, v, heads=h, head_dim=d, head_dim_padded=dp, scale=self.scale)
+        return ops.linear_tokens(o.view(B, D, H, W, h * d), pk["wo"], bias=pk["bo"], residual=residual)
+
     # --- cross-attention with a single context token: attn2(x, ctx) == to_out(to_v(ctx)) ---
     def composed_single_token(self):
         """(W_out @ W_v, b_out) in fp32: maps the context token straight to the block's additive vector."""
@@ -143,10 +168,18 @@ class BasicTransformerBlock(nn.Module):
 
     def pack(self):
         f = lambda t: t.detach().float().contiguous()
-        return {"attn1": self.attn1.pack_self(), "ff": self.ff.pack(),
-                "ln1": (f(self.norm1.weight), f(self.norm1.bias)), "ln3": (f(self.norm3.weight), f(self.norm3.bias))}
+        return {"attn1": self.attn1.pack_self(), "ff": self.ff.pack(), "attn2": None,
+                "ln1": (f(self.norm1.weight), f(self.norm1.bias)), "ln2": (f(self.norm2.weight), f(self.norm2.bias)),
+                "ln3": (f(self.norm3.weight), f(self.norm3.bias))}
 
-    def run(self, pk, x, ctx_vec):
+    def run(self, pk, x, ctx_vec, context=None):
+        """ctx_vec: the block's single-token cross-attention vector (fast path), or None with `context` (B, M > 1, dim)."""
+        if ctx_vec is None:
+            if pk["attn2"] is None:
+                pk["attn2"] = self.attn2.pack_cross()          # packed on first use: the v2_full path never needs it
+            x = self.attn1.run_self(pk["attn1"], ops.layernorm(x, *pk["ln1"], eps=self.norm1.eps), residual=x)
+            x = self.attn2.run_cross(pk["attn2"], ops.layernorm(x, *pk["ln2"], eps=self.norm2.eps), context, residual=x)
+            return FeedForward.run(pk["ff"], ops.layernorm(x, *pk["ln3"], eps=self.norm3.eps), residual=x)
         # x = attn1(norm1(x)) + x ; x = attn2(norm2(x), ctx) + x   [attn2 == ctx_vec, independent of x]
         x = self.attn1.run_self(pk["attn1"], ops.layernorm(x, *pk["ln1"], eps=self.norm1.eps), residual=x, rowvec=ctx_vec)
         # x = ff(norm3(x)) + x
@@ -177,12 +210,13 @@ class SpatialTransformer3D(nn.Module):
                 "w_out": ops.pack_conv_weight(self.proj_out.weight), "b_out": f(self.proj_out.bias),
                 "blocks": [b.pack() for b in self.transformer_blocks]}
 
-    def run(self, pk, x, ctx_vecs, arena):
-        """x: Act over (B, D, H, W, C) bf16 (with its GroupNorm sums); ctx_vecs: one fp32 (B, inner) vector per block."""
+    def run(self, pk, x, ctx_vecs, arena, context=None):
+        """x: Act over (B, D, H, W, C) bf16 (with its GroupNorm sums); ctx_vecs: one fp32 (B, inner) vector per block
+        (single-token context), or None entries with the raw multi-token `context`."""
         from .openai_model_3d import _with_stats
         B, D, H, W, C = x.t.shape
         t = ops.linear_tokens(ops.groupnorm_fused(x.t, x.stat, *pk["gn"], eps=self.norm.eps), pk["w_in"], bias=pk["b_in"])
         for blk, bpk, vec in zip(self.transformer_blocks, pk["blocks"], ctx_vecs):
-            t = blk.run(bpk, t, vec)
+            t = blk.run(bpk, t, vec, context)
         return _with_stats(arena, lambda st: ops.linear_tokens(t, pk["w_out"], bias=pk["b_out"], residual=x.t, stat_sum=st),
                            B, C, D * H * W)

@@ -337,9 +337,7 @@ class UNet3DModel(nn.Module):
         Depends only on the context, so samplers may compute it once per trajectory."""
         pk = self._ensure_packed()
         if context.dim() != 3 or context.shape[1] != 1:
-            raise NotImplementedError(
-                "cross-attention over more than one context token: the scene-graph conditioning is one token per "
-                "object (VAEGAN_V2FULL.py:237-240); the multi-token path is not built yet")
+            raise ValueError("context_vectors() is the single-token fast path; pass multi-token contexts to forward()")
         return ops.linear_small(context[:, 0].float().contiguous(), pk["ca_w"], pk["ca_b"])
 
     @torch.no_grad()
@@ -360,7 +358,8 @@ class UNet3DModel(nn.Module):
         w0, b0, w2, b2 = pk["te"]
         emb = ops.linear_small(ops.linear_small(t_emb, w0, b0, act_out=ops.ACT_SILU), w2, b2)
         emb_vecs = ops.linear_small(emb, pk["emb_w"], pk["emb_b"], act_in=ops.ACT_SILU)     # every ResBlock's emb_layers at once
-        ca_vecs = context_vecs if context_vecs is not None else self.context_vectors(context)
+        multi = context_vecs is None and context is not None and context.dim() == 3 and context.shape[1] > 1
+        ca_vecs = None if multi else (context_vecs if context_vecs is not None else self.context_vectors(context))
 
         arena = self._arenas.get(B)
         if arena is None:
@@ -374,7 +373,10 @@ class UNet3DModel(nn.Module):
                     h = layer.run(e["pk"], h, emb_vecs[:, off:off + n], arena, skip=skip)
                     skip = None
                 elif e["kind"] == "st":
-                    h = layer.run(e["pk"], h, [ca_vecs[:, o:o + n] for o, n in e["ca"]], arena)
+                    if multi:    # generic cross-attention over all context tokens (attention.py:172-219)
+                        h = layer.run(e["pk"], h, [None] * len(e["ca"]), arena, context=context)
+                    else:
+                        h = layer.run(e["pk"], h, [ca_vecs[:, o:o + n] for o, n in e["ca"]], arena)
                 elif e["kind"] == "resample":
                     h = layer.run(e["pk"], h, arena)
                 else:

@@ -25,7 +25,7 @@ __all__ = [
     "geglu", "upsample_nearest", "im2col_small", "timestep_embedding", "linear_small", "ddim_step",
     "q_sample", "to_channels_last", "to_ncdhw", "pack_conv_weight", "pack_linear_weight", "launch_count",
     "reset_launch_count", "zero_stat_buffer", "groupnorm_stats", "groupnorm_fused", "ConvProfiler", "vq_quantize", "channel_mix", "pack_small_cout_conv", "conv3d_small_cout", "gcn_gather_triples", "gcn_scatter_mean",
-    "batchnorm_relu", "add_rows",
+    "batchnorm_relu", "add_rows", "cast_bf16",
 ]
 
 
@@ -560,4 +560,12 @@ def add_rows(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     y = torch.empty((M, Cc), dtype=torch.float32, device=a.device)
     check(_lib.load().cs_add_rows(a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), M, Cc, y.data_ptr(), y.stride(0),
                                   _stream()), "cs_add_rows")
+    return y
+
+
+def cast_bf16(x: torch.Tensor) -> torch.Tensor:
+    """contiguous fp32 CUDA tensor -> bf16 copy of the same shape."""
+    _f32(x, "cast_bf16.x")
+    y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    check(_lib.load().cs_cast_f32_to_bf16(x.data_ptr(), x.numel(), y.data_ptr(), _stream()), "cs_cast_f32_to_bf16")
     return y

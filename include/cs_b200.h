@@ -167,6 +167,9 @@ int cs_batchnorm_relu(const float* x, int32_t M, int32_t C, int32_t pitch, const
 int cs_add_rows(const float* a, int32_t a_pitch, const float* b, int32_t b_pitch, int32_t M, int32_t C, float* y,
                 int32_t y_pitch, cs_stream_t stream);
 
+/* contiguous fp32 -> bf16 (keys / values of a multi-token cross-attention context, attention.py:186-187) */
+int cs_cast_f32_to_bf16(const float* x, int64_t n, void* y, cs_stream_t stream);
+
 /* tuning experiments only (tools/): bit 0 = drop the epilogue's global stores, bit 1 = empty epilogue, bit 2 = no MMA.
  * Results are WRONG while any bit is set; 0 restores normal operation. */
 void cs_debug_set(int32_t flags);

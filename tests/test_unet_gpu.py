@@ -135,3 +135,36 @@ def test_sampler_public_api_runs_and_counts_kernels():
                           unconditional_guidance_scale=3.0, unconditional_conditioning=uc, eta=0.0)
     assert out.shape == (2, 3, 8, 8, 8) and torch.isfinite(out).all()
     assert ops.launch_count() > n0 and set(inter) == {"x_inter", "pred_x0"}
+
+
+def test_multi_token_context_generic_cross_attention():
+    """The reference API accepts (B, M, context_dim) contexts; v2_full always has M = 1 (fast path) but M > 1 must work."""
+    cfg = D.UNET_TINY
+    m = _build(cfg, 24)
+    sd = Wt.synth_state_dict(D.unet_param_shapes(cfg), 24)
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(2, 3, 8, 8, 8, generator=g)
+    t = torch.tensor([3, 700])
+    ctx = torch.randn(2, 5, cfg["context_dim"], generator=g)
+    with torch.no_grad():
+        ref = D.unet_forward(sd, cfg, x, t, ctx)
+    eps = m(x.cuda(), t.cuda(), c_crossattn=[ctx.cuda()]).cpu()
+    err = _rel_l2(eps, ref)
+    print(f"multi-token context (M=5): rel-L2 {err:.3e}")
+    assert err <= REL_L2_TOL
+
+
+@pytest.mark.parametrize("B", [1, 7])
+def test_odd_and_unit_batches(B):
+    """Ragged batch sizes (the reference samples in mini-batches of 7; a scene can have a single object)."""
+    cfg = D.UNET_TINY
+    m = _build(cfg, 25)
+    sd = Wt.synth_state_dict(D.unet_param_shapes(cfg), 25)
+    g = torch.Generator().manual_seed(9 + B)
+    x = torch.randn(B, 3, 8, 8, 8, generator=g)
+    t = torch.randint(0, 1000, (B,), generator=g)
+    ctx = torch.randn(B, 1, cfg["context_dim"], generator=g)
+    with torch.no_grad():
+        ref = D.unet_forward(sd, cfg, x, t, ctx)
+    eps = m(x.cuda(), t.cuda(), c_crossattn=[ctx.cuda()]).cpu()
+    assert _rel_l2(eps, ref) <= REL_L2_TOL
