@@ -548,8 +548,14 @@ int igemm_launch(const IgemmArgs& a, cudaStream_t stream) {
   // and the accumulator stays double buffered: 10-13 % faster than the one-CTA kernel on every linear shape of the
   // denoiser.  Long-K convs keep pair mode / hybrid scheduling, which measured faster (profiles/r1_experiments.txt).
   // Debug flags: 512 = never use it, 1024 = use it instead of pair mode as well.
-  if ((g_debug_flags & 1024) && p.mt == 2) { p.mt = 1; p.n_pair_items = 0; p.n_items = p.m_tiles * p.n_tiles; }
-  if (!(g_debug_flags & 512) && (kiters < 27 || (g_debug_flags & 1024)) && p.fast_epilogue && p.rows == 128 && p.bb == 1 && p.m_tiles % 2 == 0 && p.mt == 1 && bn >= 32) {
+  // CTA pairs with TWO accumulators each (512 voxels x BN per cluster item): 46 KB of operands per 896 MMA cycles per SM.
+  // +5-6 % over one-CTA pair mode on the 16^3-level convs (>= ~7 rounds of work for the 74 clusters), neutral or worse
+  // where fewer items make the coarser granularity cost a round.  Debug flag 4096 forces it, 8192 disables it.
+  const bool quad = p.mt == 2 && p.m_tiles % 4 == 0 && !(g_debug_flags & 8192) &&
+                    ((g_debug_flags & 4096) || (p.m_tiles / 4) * p.n_tiles >= 400);
+  if ((g_debug_flags & 1024) && p.mt == 2 && !quad) { p.mt = 1; p.n_pair_items = 0; p.n_items = p.m_tiles * p.n_tiles; }
+  if (!(g_debug_flags & 512) && (kiters < 27 || (g_debug_flags & 1024) || quad) && p.fast_epilogue && p.rows == 128 && p.bb == 1 &&
+      p.m_tiles % 2 == 0 && (p.mt == 1 || quad) && bn >= 32) {
     CUtensorMap tmWh;
     const uint64_t ktot = (uint64_t)(((a.C1 + 63) / 64 + (a.C2 + 63) / 64) * 64) * a.kd * a.kh * a.kw;
     const uint64_t wd[2] = {ktot, (uint64_t)a.Cout};
@@ -558,9 +564,9 @@ int igemm_launch(const IgemmArgs& a, cudaStream_t stream) {
     const uint32_t we[2] = {1u, 1u};
     int rc = make_tensor_map(&tmWh, a.weight, 2, wd, ws, wb, we);
     if (rc) return rc;
-    int st2 = (227 * 1024 - 4096 - 8 * 2048) / (kABytes + (bn / 2) * 128);
+    int st2 = (227 * 1024 - 4096 - 8 * 2048) / (p.mt * kABytes + (bn / 2) * 128);
     if (st2 > kMaxStages) st2 = kMaxStages;
-    if (g_debug_flags & 2048) fprintf(stderr, "  -> CTA-pair kernel, %d stages\n", st2);
+    if (g_debug_flags & 2048) fprintf(stderr, "  -> CTA-pair kernel, mt=%d, %d stages\n", p.mt, st2);
     return igemm2_launch(tmA1, tmA2, tmWh, p, st2, stream);
   }
   static int attr_smem[2] = {0, 0};

@@ -106,10 +106,11 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ 
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const int half_bn = p.BN >> 1;
-  const int stage_bytes = kABytes2 + half_bn * 128;
+  const int mt = p.mt;                                               // 128-voxel tiles per CTA per item (1 or 2)
+  const int stage_bytes = mt * kABytes2 + half_bn * 128;
   const int nch1 = (p.C1 + 63) >> 6, nch2 = (p.C2 + 63) >> 6, nch = nch1 + nch2;
   const int ntaps = p.kd * p.kh * p.kw;
-  const int n_items = (p.m_tiles >> 1) * p.n_tiles;                 // one item = a PAIR of m-tiles x one n-tile
+  const int n_items = (p.m_tiles / (2 * mt)) * p.n_tiles;           // one item = 2*mt m-tiles (mt per CTA) x one n-tile
   const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
 
   if (warp == 0 && lane == 0) {
@@ -146,12 +147,15 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ 
       const uint32_t pair_bytes = static_cast<uint32_t>(2 * stage_bytes);
       for (int item = cluster_id; item < n_items; item += n_clusters) {
         const int nt = item % p.n_tiles;
-        int mt = (item / p.n_tiles) * 2 + static_cast<int>(rank);
-        const int tw = mt % tiles_w; mt /= tiles_w;
-        const int th = mt % tiles_h; mt /= tiles_h;
-        const int td = mt % tiles_d; mt /= tiles_d;
-        const int b0 = mt;                                          // bb == 1 (host-checked)
-        const int w0 = tw * p.bw * p.sw - p.pw, h0 = th * p.bh * p.sh - p.ph, d0 = td * p.bd * p.sd - p.pd;
+        int b0[2], w0[2], h0[2], d0[2];
+        for (int i = 0; i < mt; ++i) {
+          int t = (item / p.n_tiles) * (2 * mt) + 2 * i + static_cast<int>(rank);   // this CTA's i-th m-tile of the item
+          const int tw = t % tiles_w; t /= tiles_w;
+          const int th = t % tiles_h; t /= tiles_h;
+          const int td = t % tiles_d; t /= tiles_d;
+          b0[i] = t;                                                // bb == 1 (host-checked)
+          w0[i] = tw * p.bw * p.sw - p.pw; h0[i] = th * p.bh * p.sh - p.ph; d0[i] = td * p.bd * p.sd - p.pd;
+        }
         const int n0 = nt * p.BN + static_cast<int>(rank) * half_bn;
         for (int zd = 0; zd < p.kd; ++zd)
           for (int zh = 0; zh < p.kh; ++zh)
@@ -164,9 +168,10 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ 
                 else mbar_arrive_remote(&bars.full[stage], 0);
                 const bool first = ch < nch1;
                 const uint32_t lbar = mapa_u32(&bars.full[stage], 0);
-                tma2_load_5d(first ? &tmA1 : &tmA2, lbar, sa, first ? ch * 64 : (ch - nch1) * 64, w0 + zw, h0 + zh,
-                             d0 + zd, b0);
-                tma2_load_2d(&tmW, lbar, sa + kABytes2, tap * ctot + ch * 64, n0);
+                for (int i = 0; i < mt; ++i)
+                  tma2_load_5d(first ? &tmA1 : &tmA2, lbar, sa + i * kABytes2, first ? ch * 64 : (ch - nch1) * 64, w0[i] + zw,
+                               h0[i] + zh, d0[i] + zd, b0[i]);
+                tma2_load_2d(&tmW, lbar, sa + mt * kABytes2, tap * ctot + ch * 64, n0);
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
               }
             }
@@ -184,9 +189,11 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ 
       const int ks_last1 = (min(64, p.C1 - (nch1 - 1) * 64) + 15) >> 4;
       const int ks_last2 = nch2 ? (min(64, p.C2 - (nch2 - 1) * 64) + 15) >> 4 : 4;
       for (int item = cluster_id; item < n_items; item += n_clusters) {
-        mbar_wait(&bars.tmem_empty[acc], buf_phase[acc] ^ 1);
+        const int a0 = (mt == 2) ? 0 : acc;
+        mbar_wait(&bars.tmem_empty[a0], buf_phase[a0] ^ 1);
+        if (mt == 2) mbar_wait(&bars.tmem_empty[1], buf_phase[1] ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * 256);
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(a0 * 256);
         uint32_t accumulate = 0;
         for (int tap = 0; tap < ntaps; ++tap) {
           for (int ch = 0; ch < nch; ++ch) {
@@ -195,20 +202,27 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ 
             tc_fence_after();
             const uint32_t sa = smem_base_u + static_cast<uint32_t>(stage * stage_bytes);
             const uint32_t a_lo = ((sa >> 4) & 0x3FFFu) | 0x10000u;
-            const uint32_t b_lo = (((sa + kABytes2) >> 4) & 0x3FFFu) | 0x10000u;
+            const uint32_t a2_lo = (((sa + kABytes2) >> 4) & 0x3FFFu) | 0x10000u;
+            const uint32_t b_lo = (((sa + mt * kABytes2) >> 4) & 0x3FFFu) | 0x10000u;
 #pragma unroll 4
             for (int k = 0; k < ksteps; ++k) {
-              umma2_bf16(d_tmem, (static_cast<uint64_t>(desc_hi) << 32) | (a_lo + 2u * k),
-                         (static_cast<uint64_t>(desc_hi) << 32) | (b_lo + 2u * k), idesc, accumulate);
+              const uint64_t bd = (static_cast<uint64_t>(desc_hi) << 32) | (b_lo + 2u * k);
+              umma2_bf16(d_tmem, (static_cast<uint64_t>(desc_hi) << 32) | (a_lo + 2u * k), bd, idesc, accumulate);
+              if (mt == 2) umma2_bf16(d_tmem + 256u, (static_cast<uint64_t>(desc_hi) << 32) | (a2_lo + 2u * k), bd, idesc, accumulate);
               accumulate = 1;
             }
             umma2_commit_mc(&bars.empty[stage]);
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
         }
-        umma2_commit_mc(&bars.tmem_full[acc]);
-        buf_phase[acc] ^= 1;
-        acc ^= 1;
+        umma2_commit_mc(&bars.tmem_full[a0]);
+        buf_phase[a0] ^= 1;
+        if (mt == 2) {
+          umma2_commit_mc(&bars.tmem_full[1]);
+          buf_phase[1] ^= 1;
+        } else {
+          acc ^= 1;
+        }
       }
     }
   } else {
@@ -222,31 +236,34 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ 
     uint32_t buf_phase[2] = {0, 0};
     for (int item = cluster_id; item < n_items; item += n_clusters) {
       const int nt = item % p.n_tiles;
-      const int mt = (item / p.n_tiles) * 2 + static_cast<int>(rank);
       const int n0 = nt * p.BN;
-      const long long m_tile0 = static_cast<long long>(mt) * 128;
-      const int b = static_cast<int>(m_tile0 / spatial);
-      for (int c = et; c < p.BN; c += 256) {
-        float cv = 0.f;
-        if (n0 + c < p.Cout) {
-          if (p.bias) cv += __ldg(p.bias + n0 + c);
-          if (p.rowvec) cv += __ldg(p.rowvec + static_cast<long long>(b) * p.rowvec_pitch + n0 + c);
+      for (int i = 0; i < mt; ++i) {
+        const int ab = (mt == 2) ? i : acc;
+        const int tile = (item / p.n_tiles) * (2 * mt) + 2 * i + static_cast<int>(rank);
+        const long long m_tile0 = static_cast<long long>(tile) * 128;
+        const int b = static_cast<int>(m_tile0 / spatial);
+        for (int c = et; c < p.BN; c += 256) {
+          float cv = 0.f;
+          if (n0 + c < p.Cout) {
+            if (p.bias) cv += __ldg(p.bias + n0 + c);
+            if (p.rowvec) cv += __ldg(p.rowvec + static_cast<long long>(b) * p.rowvec_pitch + n0 + c);
+          }
+          bars.colvec[ab][c] = cv;
         }
-        bars.colvec[acc][c] = cv;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        mbar_wait(&bars.tmem_full[ab], buf_phase[ab]);
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(ab * 256);
+        epilogue_fast_tile(p, t_row, lane, half, 64, quarter * 32, m_tile0, b, n0, bars.colvec[ab], stage_buf);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (leader) mbar_arrive(&bars.tmem_empty[ab]);
+          else mbar_arrive_remote(&bars.tmem_empty[ab], 0);
+        }
+        buf_phase[ab] ^= 1;
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      mbar_wait(&bars.tmem_full[acc], buf_phase[acc]);
-      tc_fence_after();
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * 256);
-      epilogue_fast_tile(p, t_row, lane, half, 64, quarter * 32, m_tile0, b, n0, bars.colvec[acc], stage_buf);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (leader) mbar_arrive(&bars.tmem_empty[acc]);
-        else mbar_arrive_remote(&bars.tmem_empty[acc], 0);
-      }
-      buf_phase[acc] ^= 1;
-      acc ^= 1;
+      if (mt == 1) acc ^= 1;
     }
   }
 
@@ -268,7 +285,7 @@ namespace cs {
 int igemm2_launch(const CUtensorMap& tmA1, const CUtensorMap& tmA2, const CUtensorMap& tmW_half, IgemmParams p, int stages,
                   cudaStream_t stream) {
   p.stages = stages;
-  const int stage_bytes = kABytes2 + (p.BN / 2) * 128;
+  const int stage_bytes = p.mt * kABytes2 + (p.BN / 2) * 128;
   const int smem_bytes = stages * stage_bytes + 8 * 2048 + 1024;
   static int attr_smem = 0;
   if (smem_bytes > attr_smem) {
@@ -276,7 +293,7 @@ int igemm2_launch(const CUtensorMap& tmA1, const CUtensorMap& tmA2, const CUtens
     if (e != cudaSuccess) return set_cuda_error(e, "igemm2: cudaFuncSetAttribute");
     attr_smem = smem_bytes;
   }
-  const int items = (p.m_tiles / 2) * p.n_tiles;
+  const int items = (p.m_tiles / (2 * p.mt)) * p.n_tiles;
   int clusters = num_sms() / 2;
   if (items < clusters) clusters = items;
   igemm2_kernel<<<2 * clusters, kThreads2, smem_bytes, stream>>>(tmA1, tmA2, tmW_half, p);
