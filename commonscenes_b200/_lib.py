@@ -38,6 +38,19 @@ class Conv3dArgs(C.Structure):
     ]
 
 
+class WgradArgs(C.Structure):
+    """Mirror of `cs_conv3d_wgrad_args` (include/cs_b200.h)."""
+    _fields_ = [
+        ("x1", _vp), ("C1", _i32), ("x1_pitch", _i32),
+        ("x2", _vp), ("C2", _i32), ("x2_pitch", _i32),
+        ("B", _i32), ("D", _i32), ("H", _i32), ("W", _i32),
+        ("dy", _vp), ("Cout", _i32), ("dy_pitch", _i32),
+        ("kd", _i32), ("kh", _i32), ("kw", _i32), ("sd", _i32), ("sh", _i32), ("sw", _i32),
+        ("pd", _i32), ("ph", _i32), ("pw", _i32), ("pd_back", _i32), ("ph_back", _i32), ("pw_back", _i32),
+        ("dw", _vp),
+    ]
+
+
 # name -> (restype, argtypes); must list EVERY symbol include/cs_b200.h declares
 SIGNATURES = {
     "cs_abi_version": (_i32, []),
@@ -46,6 +59,7 @@ SIGNATURES = {
     "cs_launch_count": (C.c_uint64, []),
     "cs_reset_launch_count": (None, []),
     "cs_conv3d": (_i32, [C.POINTER(Conv3dArgs), _vp]),
+    "cs_conv3d_wgrad": (_i32, [C.POINTER(WgradArgs), _vp]),
     "cs_groupnorm_stats": (_i32, [_vp, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
     "cs_groupnorm_finalize": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _vp, _vp]),
     "cs_groupnorm_apply": (_i32, [_vp, _i32, _i32, _i32, _i32, _vp, _i32, _vp, _i32, _i32, _vp]),

@@ -1,5 +1,6 @@
 // extern "C" surface of libcsb200.so — see include/cs_b200.h for the contract of every entry point.
 #include "cs_host.h"
+#include "cs_wgrad.cuh"
 // after cs_host.h: the public macros shadow the identically valued internal enums
 #include "../../include/cs_b200.h"
 
@@ -82,6 +83,21 @@ int cs_conv3d(const cs_conv3d_args* a, cs_stream_t stream) {
   if (g.kd < 1 || g.kh < 1 || g.kw < 1 || g.sd < 1 || g.sh < 1 || g.sw < 1 || g.B < 1)
     return cs::set_error(CS_ERR_INVALID, "cs_conv3d: bad filter/stride/batch");
   return cs::igemm_launch(g, S(stream));
+}
+
+int cs_conv3d_wgrad(const cs_conv3d_wgrad_args* a, cs_stream_t stream) {
+  if (!a || !a->x1 || !a->dy || !a->dw) return cs::set_error(CS_ERR_INVALID, "cs_conv3d_wgrad: null pointer");
+  cs::WgradArgs g{};
+  g.x1 = a->x1; g.C1 = a->C1; g.x1_pitch = a->x1_pitch;
+  g.x2 = a->x2; g.C2 = a->x2 ? a->C2 : 0; g.x2_pitch = a->x2_pitch;
+  g.B = a->B; g.D = a->D; g.H = a->H; g.W = a->W;
+  g.dy = a->dy; g.Cout = a->Cout; g.dy_pitch = a->dy_pitch;
+  g.kd = a->kd; g.kh = a->kh; g.kw = a->kw; g.sd = a->sd; g.sh = a->sh; g.sw = a->sw;
+  g.pd = a->pd; g.ph = a->ph; g.pw = a->pw; g.pd_back = a->pd_back; g.ph_back = a->ph_back; g.pw_back = a->pw_back;
+  g.dw = a->dw;
+  if (g.kd < 1 || g.kh < 1 || g.kw < 1 || g.sd < 1 || g.sh < 1 || g.sw < 1 || g.B < 1)
+    return cs::set_error(CS_ERR_INVALID, "cs_conv3d_wgrad: bad filter/stride/batch");
+  return cs::wgrad_launch(g, S(stream));
 }
 
 int cs_groupnorm_stats(const void* x, int32_t B, int32_t Sp, int32_t C, int32_t pitch, float* stat,

@@ -75,6 +75,23 @@ typedef struct cs_conv3d_args {
 } cs_conv3d_args;
 int cs_conv3d(const cs_conv3d_args* args, cs_stream_t stream);
 
+/* ---- training path: gradients of the GEMM-class ops -------------------------------------------------------------
+ * The reference gets these from autograd (loss.backward(), sdfusion_txt2shape_model.py:568-575) through nn.Conv3d /
+ * nn.Linear of openai_model_3d.py:130-314 and attention.py:39-66,154-219.
+ *  - data gradient: a stride-1 conv's dX is cs_conv3d of dY with the filter flipped and Cin/Cout swapped
+ *    (commonscenes_b200.ops_bwd.pack_dgrad_weight); strided convs insert zeros first (cs_zero_insert).
+ *  - weight gradient: dW[co][tap][ci] += sum_v dY[v][co] * X[shift_tap(v)][ci], fp32, in the packed forward layout. */
+typedef struct cs_conv3d_wgrad_args {
+  const void* x1; int32_t C1; int32_t x1_pitch;     /* the conv's input, bf16 channels-last [B][D][H][W][pitch] */
+  const void* x2; int32_t C2; int32_t x2_pitch;     /* optional second source (channel concat) */
+  int32_t B, D, H, W;                                /* INPUT spatial extent */
+  const void* dy; int32_t Cout; int32_t dy_pitch;   /* gradient of the output, bf16 channels-last [B][Do][Ho][Wo][pitch] */
+  int32_t kd, kh, kw, sd, sh, sw;
+  int32_t pd, ph, pw, pd_back, ph_back, pw_back;
+  float* dw;                                         /* fp32 [Cout][kd*kh*kw][pad64(C1)+pad64(C2)], accumulated into */
+} cs_conv3d_wgrad_args;
+int cs_conv3d_wgrad(const cs_conv3d_wgrad_args* args, cs_stream_t stream);
+
 /* ---- GroupNorm (GroupNorm32: ldm_diffusion_util.py:237-239; Normalize: attention.py:78-79,
  *      vqvae_modules.py:13-21) --------------------------------------------------------------- */
 /* stat[b][c][0..1] += sum / sum of squares over the S voxels of sample b */
