@@ -60,6 +60,23 @@ SIGNATURES = {
     "cs_reset_launch_count": (None, []),
     "cs_conv3d": (_i32, [C.POINTER(Conv3dArgs), _vp]),
     "cs_conv3d_wgrad": (_i32, [C.POINTER(WgradArgs), _vp]),
+    "cs_unpack_wgrad": (_i32, [_vp, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "cs_groupnorm_bwd": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _i32, _f32,
+                                _i32, _vp, _vp, _i32, _vp, _i32, _i32, _vp]),
+    "cs_batch_reduce": (_i32, [_vp, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "cs_layernorm_bwd": (_i32, [_vp, _i64, _i32, _i32, _vp, _i32, _vp, _f32, _vp, _i32, _vp, _i32, _vp, _vp, _vp]),
+    "cs_geglu_bwd": (_i32, [_vp, _i64, _i32, _i32, _vp, _i32, _vp, _i32, _vp]),
+    "cs_upsample_nearest_bwd": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
+    "cs_zero_insert": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
+    "cs_add_bf16": (_i32, [_vp, _i32, _vp, _i32, _i64, _i32, _vp]),
+    "cs_cast_rows": (_i32, [_vp, _i32, _i64, _i32, _vp, _i32, _vp]),
+    "cs_sgemm_small": (_i32, [_vp, _i32, _i32, _vp, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
+    "cs_mse_loss_grad": (_i32, [_vp, _vp, _i64, _f32, _vp, _vp, _vp]),
+    "cs_sumsq": (_i32, [_vp, _i64, _vp, _vp]),
+    "cs_adamw": (_i32, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _i32, _vp, _f32, _f32, _vp]),
+    "cs_attention_lse": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _vp]),
+    "cs_attention_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32,
+                                _i32, _i32, _f32, _vp]),
     "cs_groupnorm_stats": (_i32, [_vp, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
     "cs_groupnorm_finalize": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _vp, _vp]),
     "cs_groupnorm_apply": (_i32, [_vp, _i32, _i32, _i32, _i32, _vp, _i32, _vp, _i32, _i32, _vp]),

@@ -36,6 +36,27 @@ int scatter_mean_launch(const float*, int, int, int, int, const long long*, int,
 int batchnorm_relu_launch(const float*, int, int, int, const float*, const float*, float*, float*, int, float, float, int,
                           float*, int, cudaStream_t);
 int add_rows_launch(const float*, int, const float*, int, int, int, float*, int, cudaStream_t);
+int gn_bwd_launch(const void*, int, int, int, int, int, const void*, int, int, const float*, int, const float*, int, const float*,
+                  const float*, int, float, int, float*, const void*, int, void*, int, int, cudaStream_t);
+int batch_reduce_launch(const float*, int, int, int, int, float*, cudaStream_t);
+int layernorm_bwd_launch(const void*, long long, int, int, const void*, int, const float*, float, const void*, int, void*, int,
+                         float*, float*, cudaStream_t);
+int geglu_bwd_launch(const void*, long long, int, int, const void*, int, void*, int, cudaStream_t);
+int upsample_bwd_launch(const void*, int, int, int, int, int, int, int, int, int, void*, int, cudaStream_t);
+int zero_insert_launch(const void*, int, int, int, int, int, int, int, int, int, void*, int, cudaStream_t);
+int add_bf16_launch(void*, int, const void*, int, long long, int, cudaStream_t);
+int cast_rows_launch(const float*, int, long long, int, void*, int, cudaStream_t);
+int sgemm_small_launch(const float*, int, int, const float*, int, int, float*, int, int, int, int, int, const float*, int,
+                       cudaStream_t);
+int mse_loss_grad_launch(const float*, const float*, long long, float, float*, float*, cudaStream_t);
+int sumsq_launch(const float*, long long, float*, cudaStream_t);
+int adamw_launch(float*, const float*, float*, float*, long long, float, float, float, float, float, int, const float*, float,
+                 float, cudaStream_t);
+int unpack_wgrad_launch(const float*, int, int, int, int, float*, cudaStream_t);
+int attention_lse_launch(const void*, const void*, const void*, void*, int, int, int, int, int, int, int, int, int, float, float*,
+                         cudaStream_t);
+int attention_bwd_launch(const void*, const void*, const void*, const void*, const void*, const float*, float*, float*, void*,
+                         void*, int, int, int, int, int, int, int, int, int, float, cudaStream_t);
 void igemm_set_debug(int);
 int cast_bf16_launch(const float*, long long, void*, cudaStream_t);
 int vq_quantize_launch(const float*, int, int, long long, const float*, int, const float*, const float*, int, float*,
@@ -211,4 +232,69 @@ int cs_cast_f32_to_bf16(const float* x, int64_t n, void* y, cs_stream_t stream) 
   return cs::cast_bf16_launch(x, n, y, S(stream));
 }
 
+// ---- training path -----------------------------------------------------------------------------------------------
+int cs_groupnorm_bwd(const void* x, int32_t B, int32_t Sp, int32_t C, int32_t pitch, int32_t ch_off, const void* dy,
+                     int32_t dy_pitch, int32_t dy_off, const float* stat1, int32_t C1, const float* stat2, int32_t C2,
+                     const float* gamma, const float* beta, int32_t groups, float eps, int32_t act, float* red,
+                     const void* extra, int32_t extra_pitch, void* dx, int32_t dx_pitch, int32_t pass, cs_stream_t stream) {
+  return cs::gn_bwd_launch(x, B, Sp, C, pitch, ch_off, dy, dy_pitch, dy_off, stat1, C1, stat2, C2, gamma, beta, groups, eps, act,
+                           red, extra, extra_pitch, dx, dx_pitch, pass, S(stream));
+}
+int cs_batch_reduce(const float* in, int32_t B, int32_t C, int32_t comp, int32_t ncomp, float* out, cs_stream_t stream) {
+  return cs::batch_reduce_launch(in, B, C, comp, ncomp, out, S(stream));
+}
+int cs_layernorm_bwd(const void* x, int64_t M, int32_t C, int32_t pitch, const void* dy, int32_t dy_pitch, const float* gamma,
+                     float eps, const void* extra, int32_t extra_pitch, void* dx, int32_t dx_pitch, float* dgamma, float* dbeta,
+                     cs_stream_t stream) {
+  return cs::layernorm_bwd_launch(x, M, C, pitch, dy, dy_pitch, gamma, eps, extra, extra_pitch, dx, dx_pitch, dgamma, dbeta,
+                                  S(stream));
+}
+int cs_geglu_bwd(const void* u, int64_t M, int32_t I, int32_t u_pitch, const void* df, int32_t df_pitch, void* du,
+                 int32_t du_pitch, cs_stream_t stream) {
+  return cs::geglu_bwd_launch(u, M, I, u_pitch, df, df_pitch, du, du_pitch, S(stream));
+}
+int cs_upsample_nearest_bwd(const void* dy, int32_t B, int32_t D, int32_t H, int32_t W, int32_t C, int32_t fd, int32_t fh,
+                            int32_t fw, int32_t dy_pitch, void* dx, int32_t dx_pitch, cs_stream_t stream) {
+  return cs::upsample_bwd_launch(dy, B, D, H, W, C, fd, fh, fw, dy_pitch, dx, dx_pitch, S(stream));
+}
+int cs_zero_insert(const void* in, int32_t B, int32_t D, int32_t H, int32_t W, int32_t C, int32_t sd, int32_t sh, int32_t sw,
+                   int32_t in_pitch, void* out, int32_t out_pitch, cs_stream_t stream) {
+  return cs::zero_insert_launch(in, B, D, H, W, C, sd, sh, sw, in_pitch, out, out_pitch, S(stream));
+}
+int cs_add_bf16(void* y, int32_t y_pitch, const void* x, int32_t x_pitch, int64_t M, int32_t C, cs_stream_t stream) {
+  return cs::add_bf16_launch(y, y_pitch, x, x_pitch, M, C, S(stream));
+}
+int cs_cast_rows(const float* in, int32_t in_pitch, int64_t M, int32_t C, void* out, int32_t out_pitch, cs_stream_t stream) {
+  return cs::cast_rows_launch(in, in_pitch, M, C, out, out_pitch, S(stream));
+}
+int cs_sgemm_small(const float* A, int32_t lda, int32_t trans_a, const float* Bm, int32_t ldb, int32_t trans_b, float* Cm,
+                   int32_t ldc, int32_t M, int32_t N, int32_t K, int32_t accumulate, const float* silu_pre, int32_t ld_pre,
+                   cs_stream_t stream) {
+  return cs::sgemm_small_launch(A, lda, trans_a, Bm, ldb, trans_b, Cm, ldc, M, N, K, accumulate, silu_pre, ld_pre, S(stream));
+}
+int cs_mse_loss_grad(const float* pred, const float* target, int64_t n, float loss_scale, float* grad, float* loss,
+                     cs_stream_t stream) {
+  return cs::mse_loss_grad_launch(pred, target, n, loss_scale, grad, loss, S(stream));
+}
+int cs_sumsq(const float* g, int64_t n, float* out, cs_stream_t stream) { return cs::sumsq_launch(g, n, out, S(stream)); }
+int cs_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+             float weight_decay, int32_t step, const float* sumsq, float max_norm, float grad_scale, cs_stream_t stream) {
+  return cs::adamw_launch(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, step, sumsq, max_norm, grad_scale, S(stream));
+}
+int cs_unpack_wgrad(const float* dw, int32_t Cout, int32_t taps, int32_t C1, int32_t C2, float* grad, cs_stream_t stream) {
+  return cs::unpack_wgrad_launch(dw, Cout, taps, C1, C2, grad, S(stream));
+}
+int cs_attention_lse(const void* q, const void* k, const void* v, void* out, int32_t B, int32_t H, int32_t Nq, int32_t Nk,
+                     int32_t Dp, int32_t q_pitch, int32_t kv_pitch, int32_t o_pitch, int32_t d_out, float scale, float* lse,
+                     cs_stream_t stream) {
+  if (!lse) return cs::set_error(CS_ERR_INVALID, "cs_attention_lse: lse is null");
+  return cs::attention_lse_launch(q, k, v, out, B, H, Nq, Nk, Dp, q_pitch, kv_pitch, o_pitch, d_out, scale, lse, S(stream));
+}
+int cs_attention_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse,
+                     float* dsum_ws, float* dq, void* dk, void* dv, int32_t B, int32_t H, int32_t N, int32_t Dp,
+                     int32_t qkv_pitch, int32_t o_pitch, int32_t do_pitch, int32_t dqkv_pitch, int32_t d_out, float scale,
+                     cs_stream_t stream) {
+  return cs::attention_bwd_launch(q, k, v, o, dout, lse, dsum_ws, dq, dk, dv, B, H, N, Dp, qkv_pitch, o_pitch, do_pitch,
+                                  dqkv_pitch, d_out, scale, S(stream));
+}
 }  // extern "C"

@@ -47,7 +47,7 @@ template <int DP, int BM>
 __global__ void __launch_bounds__(BM * 2)
 attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
                  const __nv_bfloat16* __restrict__ v, __nv_bfloat16* __restrict__ out, int Nq, int Nk,
-                 int q_pitch, int kv_pitch, int o_pitch, int d_out, float scale_log2) {
+                 int q_pitch, int kv_pitch, int o_pitch, int d_out, float scale_log2, float* __restrict__ lse) {
   constexpr int BN = 64, NT = BM * 2;  // BM/16 warps of 16 query rows each; K/V tiles of 64 keys shared by all of them
   constexpr int PITCH = DP + 8;          // elements; (DP*2+16) bytes = odd multiple of 16 -> conflict-free ldmatrix
   constexpr int CPR = DP / 8;            // 16-byte chunks per row
@@ -195,6 +195,11 @@ attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __res
   }
   const float inv0 = 1.f / row_sum[0], inv1 = 1.f / row_sum[1];
   const int r0 = m0 + warp * 16 + (lane >> 2), r1 = r0 + 8;
+  if (lse && (lane & 3) == 0) {   // base-2 log-sum-exp of the scaled scores, kept for the backward pass
+    float* lrow = lse + (static_cast<long long>(b) * gridDim.y + h) * Nq;
+    if (r0 < Nq) lrow[r0] = row_max[0] * scale_log2 + log2f(row_sum[0]);
+    if (r1 < Nq) lrow[r1] = row_max[1] * scale_log2 + log2f(row_sum[1]);
+  }
   __nv_bfloat16* og = out + (static_cast<long long>(b) * Nq) * o_pitch + h * d_out;
 #pragma unroll
   for (int ni = 0; ni < DP / 8; ++ni) {
@@ -213,7 +218,7 @@ attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __res
 template <int DP, int BM>
 static int attention_launch_t(const void* q, const void* k, const void* v, void* out, int B, int H, int Nq,
                               int Nk, int q_pitch, int kv_pitch, int o_pitch, int d_out, float scale,
-                              cudaStream_t st) {
+                              cudaStream_t st, float* lse = nullptr) {
   constexpr int PITCH = DP + 8;
   const size_t smem = static_cast<size_t>(BM + 4 * 64) * PITCH * 2;
   static bool attr = false;
@@ -226,7 +231,7 @@ static int attention_launch_t(const void* q, const void* k, const void* v, void*
   attention_kernel<DP, BM><<<dim3((Nq + BM - 1) / BM, H, B), BM * 2, smem, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(q), reinterpret_cast<const __nv_bfloat16*>(k),
       reinterpret_cast<const __nv_bfloat16*>(v), reinterpret_cast<__nv_bfloat16*>(out), Nq, Nk, q_pitch,
-      kv_pitch, o_pitch, d_out, scale_log2);
+      kv_pitch, o_pitch, d_out, scale_log2, lse);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error(e, "attention: launch");
   count_launch();
@@ -239,21 +244,30 @@ static int attention_launch_t(const void* q, const void* k, const void* v, void*
   case DPV:                                                                                                          \
     if (DPV <= 128 && Nq >= 128)                                                                                     \
       return attention_launch_t<DPV, (DPV <= 128 ? 128 : 64)>(q, k, v, out, B, H, Nq, Nk, q_pitch, kv_pitch, o_pitch, \
-                                                             d_out, scale, st);                                      \
-    return attention_launch_t<DPV, 64>(q, k, v, out, B, H, Nq, Nk, q_pitch, kv_pitch, o_pitch, d_out, scale, st);
+                                                             d_out, scale, st, lse);                                 \
+    return attention_launch_t<DPV, 64>(q, k, v, out, B, H, Nq, Nk, q_pitch, kv_pitch, o_pitch, d_out, scale, st, lse);
 
 int attention_tc_launch(const void* q, const void* k, const void* v, void* out, int B, int H, int N, int q_pitch,
                         int kv_pitch, int o_pitch, int d_out, float scale, cudaStream_t st);
 int igemm_debug_flags();
 
+int attention_lse_launch(const void* q, const void* k, const void* v, void* out, int B, int H, int Nq, int Nk,
+                         int Dp, int q_pitch, int kv_pitch, int o_pitch, int d_out, float scale, float* lse, cudaStream_t st);
+
 int attention_launch(const void* q, const void* k, const void* v, void* out, int B, int H, int Nq, int Nk,
                      int Dp, int q_pitch, int kv_pitch, int o_pitch, int d_out, float scale, cudaStream_t st) {
+  return attention_lse_launch(q, k, v, out, B, H, Nq, Nk, Dp, q_pitch, kv_pitch, o_pitch, d_out, scale, nullptr, st);
+}
+
+// lse != null (training): also writes the base-2 log-sum-exp of every score row, fp32 [B][H][Nq]
+int attention_lse_launch(const void* q, const void* k, const void* v, void* out, int B, int H, int Nq, int Nk,
+                         int Dp, int q_pitch, int kv_pitch, int o_pitch, int d_out, float scale, float* lse, cudaStream_t st) {
   if (q_pitch % 8 || kv_pitch % 8 || o_pitch % 2 || d_out % 2 || d_out > Dp || Nk < 1)
     return set_error(CS_ERR_INVALID, "attention: pitches must be multiples of 8, d_out even and <= Dp");
   if (reinterpret_cast<uintptr_t>(q) % 16 || reinterpret_cast<uintptr_t>(k) % 16 ||
       reinterpret_cast<uintptr_t>(v) % 16 || reinterpret_cast<uintptr_t>(out) % 4 || (H * d_out) % 2)
     return set_error(CS_ERR_INVALID, "attention: q/k/v must be 16-byte aligned");
-  if (Dp == 64 && Nq == Nk && Nq % 128 == 0 && !(igemm_debug_flags() & 128))   // tcgen05 path (cs_attn_tc.cu)
+  if (!lse && Dp == 64 && Nq == Nk && Nq % 128 == 0 && !(igemm_debug_flags() & 128))   // tcgen05 path (cs_attn_tc.cu)
     return attention_tc_launch(q, k, v, out, B, H, Nq, q_pitch, kv_pitch, o_pitch, d_out, scale, st);
   switch (Dp) {
     CS_ATTN_DISPATCH(32)

@@ -1,0 +1,778 @@
+// Backward kernels of the normalisation / pointwise ops of the denoiser, and the optimizer step.
+//
+// The reference obtains all of these from autograd (loss.backward() in sdfusion_txt2shape_model.py:568-575 through
+// GroupNorm32 / SiLU (openai_model_3d.py:294-314), nn.LayerNorm + GEGLU (attention.py:39-66, 229-245), nearest
+// upsampling (openai_model_3d.py:150-155)) and steps with torch.optim.AdamW (VAEGAN_V2FULL.py:642-650).
+// Everything here is HBM-bound: activations bf16 channels-last, 16-byte vector accesses, fp32 arithmetic, fp32
+// parameter gradients accumulated with atomics.
+#include "cs_host.h"
+
+namespace cs {
+
+__device__ __forceinline__ float act_grad(float z, int act) {
+  if (act == CS_ACT_SILU) {
+    const float s = __fdividef(1.f, 1.f + __expf(-z));
+    return s * (1.f + z * (1.f - s));
+  }
+  if (act == CS_ACT_GELU) {
+    const float cdf = 0.5f * (1.f + erff(z * 0.70710678118654752f));
+    return cdf + z * 0.3989422804014327f * __expf(-0.5f * z * z);
+  }
+  return 1.f;
+}
+
+// group statistics of sample b from the per-channel (sum, sumsq) of the two concatenated sources (same arithmetic as
+// gn_apply_fused_kernel so forward and backward see identical mean / rstd)
+__device__ __forceinline__ void gn_group_stats(int b, int S, int cpg, const float* stat1, int C1, const float* stat2, int C2,
+                                               float eps, float* g_mean, float* g_rstd, int groups) {
+  if (threadIdx.x < groups) {
+    double s = 0.0, q = 0.0;
+    for (int j = 0; j < cpg; ++j) {
+      const int c = threadIdx.x * cpg + j;
+      const float* sp = (c < C1) ? stat1 + (static_cast<long long>(b) * C1 + c) * 2
+                                 : stat2 + (static_cast<long long>(b) * C2 + (c - C1)) * 2;
+      s += sp[0];
+      q += sp[1];
+    }
+    const double inv_n = 1.0 / (static_cast<double>(S) * cpg);
+    const double mean = s * inv_n;
+    double var = q * inv_n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    g_mean[threadIdx.x] = static_cast<float>(mean);
+    g_rstd[threadIdx.x] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm(+act) backward, pass 1: red[b][c][0] += sum_v dz, red[b][c][1] += sum_v dz * xhat   (c = concat channel)
+// with z = gamma * xhat + beta, dz = dy * act'(z).  x is the source that owns concat channels [ch_off, ch_off + C).
+// ------------------------------------------------------------------------------------------------
+__global__ void gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ x, int S, int C, int pitch, int ch_off,
+                                     const __nv_bfloat16* __restrict__ dy, int dy_pitch, int dy_off,
+                                     const float* __restrict__ stat1, int C1, const float* __restrict__ stat2, int C2,
+                                     const float* __restrict__ gamma, const float* __restrict__ beta, int groups, float eps,
+                                     int act, float* __restrict__ red, int vox_per_cta) {
+  __shared__ float g_mean[64], g_rstd[64];
+  extern __shared__ float sred[];   // [cv * 8][2] partial sums per channel
+  const int b = blockIdx.y;
+  const int Ct = C1 + C2;
+  const int cpg = Ct / groups;
+  gn_group_stats(b, S, cpg, stat1, C1, stat2, C2, eps, g_mean, g_rstd, groups);
+  for (int i = threadIdx.x; i < C * 2; i += blockDim.x) sred[i] = 0.f;
+  __syncthreads();
+  const int cv = C >> 3;
+  const int R = blockDim.x / cv;
+  const int r = threadIdx.x / cv;
+  const int v = threadIdx.x - r * cv;
+  if (r < R) {
+    float ga[8], be[8], mu[8], rs[8], s1[8], s2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = ch_off + v * 8 + j;
+      const int g = c / cpg;
+      ga[j] = gamma ? __ldg(gamma + c) : 1.f;
+      be[j] = beta ? __ldg(beta + c) : 0.f;
+      mu[j] = g_mean[g];
+      rs[j] = g_rstd[g];
+      s1[j] = s2[j] = 0.f;
+    }
+    const int s_begin = blockIdx.x * vox_per_cta;
+    const int s_end = min(S, s_begin + vox_per_cta);
+    const __nv_bfloat16* xb = x + (static_cast<long long>(b) * S) * pitch + v * 8;
+    const __nv_bfloat16* db = dy + (static_cast<long long>(b) * S) * dy_pitch + dy_off + v * 8;
+#pragma unroll 2
+    for (int i = s_begin + r; i < s_end; i += R) {
+      const uint4 u = *reinterpret_cast<const uint4*>(xb + static_cast<long long>(i) * pitch);
+      const uint4 d = *reinterpret_cast<const uint4*>(db + static_cast<long long>(i) * dy_pitch);
+      const uint32_t xw[4] = {u.x, u.y, u.z, u.w}, dw[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 xf = unpack_bf16x2(xw[j]), df = unpack_bf16x2(dw[j]);
+        const float h0 = (xf.x - mu[2 * j]) * rs[2 * j], h1 = (xf.y - mu[2 * j + 1]) * rs[2 * j + 1];
+        const float z0 = df.x * act_grad(fmaf(ga[2 * j], h0, be[2 * j]), act);
+        const float z1 = df.y * act_grad(fmaf(ga[2 * j + 1], h1, be[2 * j + 1]), act);
+        s1[2 * j] += z0; s2[2 * j] += z0 * h0;
+        s1[2 * j + 1] += z1; s2[2 * j + 1] += z1 * h1;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&sred[(v * 8 + j) * 2], s1[j]);
+      atomicAdd(&sred[(v * 8 + j) * 2 + 1], s2[j]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C * 2; i += blockDim.x)
+    atomicAdd(red + (static_cast<long long>(b) * Ct + ch_off) * 2 + i, sred[i]);
+}
+
+// pass 2: dx = rstd * (gamma * dz - mean_g(gamma dz) - xhat * mean_g(gamma dz xhat)) [+ extra]
+__global__ void gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, int S, int C, int pitch, int ch_off,
+                                    const __nv_bfloat16* __restrict__ dy, int dy_pitch, int dy_off,
+                                    const float* __restrict__ stat1, int C1, const float* __restrict__ stat2, int C2,
+                                    const float* __restrict__ gamma, const float* __restrict__ beta, int groups, float eps,
+                                    int act, const float* __restrict__ red, const __nv_bfloat16* __restrict__ extra,
+                                    int extra_pitch, __nv_bfloat16* __restrict__ dx, int dx_pitch, int vox_per_cta) {
+  __shared__ float g_mean[64], g_rstd[64], g_a[64], g_b[64];
+  const int b = blockIdx.y;
+  const int Ct = C1 + C2;
+  const int cpg = Ct / groups;
+  gn_group_stats(b, S, cpg, stat1, C1, stat2, C2, eps, g_mean, g_rstd, groups);
+  if (threadIdx.x < groups) {
+    double sa = 0.0, sb = 0.0;
+    for (int j = 0; j < cpg; ++j) {
+      const int c = threadIdx.x * cpg + j;
+      const float g = gamma ? gamma[c] : 1.f;
+      sa += static_cast<double>(g) * red[(static_cast<long long>(b) * Ct + c) * 2];
+      sb += static_cast<double>(g) * red[(static_cast<long long>(b) * Ct + c) * 2 + 1];
+    }
+    const double inv_n = 1.0 / (static_cast<double>(S) * cpg);
+    g_a[threadIdx.x] = static_cast<float>(sa * inv_n);
+    g_b[threadIdx.x] = static_cast<float>(sb * inv_n);
+  }
+  __syncthreads();
+  const int cv = C >> 3;
+  const int R = blockDim.x / cv;
+  const int r = threadIdx.x / cv;
+  const int v = threadIdx.x - r * cv;
+  if (r >= R) return;
+  float ga[8], be[8], mu[8], rs[8], ma[8], mb[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = ch_off + v * 8 + j;
+    const int g = c / cpg;
+    ga[j] = gamma ? __ldg(gamma + c) : 1.f;
+    be[j] = beta ? __ldg(beta + c) : 0.f;
+    mu[j] = g_mean[g]; rs[j] = g_rstd[g]; ma[j] = g_a[g]; mb[j] = g_b[g];
+  }
+  const int s_begin = blockIdx.x * vox_per_cta;
+  const int s_end = min(S, s_begin + vox_per_cta);
+  const __nv_bfloat16* xb = x + (static_cast<long long>(b) * S) * pitch + v * 8;
+  const __nv_bfloat16* db = dy + (static_cast<long long>(b) * S) * dy_pitch + dy_off + v * 8;
+  const __nv_bfloat16* eb = extra ? extra + (static_cast<long long>(b) * S) * extra_pitch + v * 8 : nullptr;
+  __nv_bfloat16* ob = dx + (static_cast<long long>(b) * S) * dx_pitch + v * 8;
+#pragma unroll 2
+  for (int i = s_begin + r; i < s_end; i += R) {
+    const uint4 u = *reinterpret_cast<const uint4*>(xb + static_cast<long long>(i) * pitch);
+    const uint4 d = *reinterpret_cast<const uint4*>(db + static_cast<long long>(i) * dy_pitch);
+    uint4 e = make_uint4(0u, 0u, 0u, 0u);
+    if (eb) e = *reinterpret_cast<const uint4*>(eb + static_cast<long long>(i) * extra_pitch);
+    const uint32_t xw[4] = {u.x, u.y, u.z, u.w}, dw[4] = {d.x, d.y, d.z, d.w}, ew[4] = {e.x, e.y, e.z, e.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 xf = unpack_bf16x2(xw[j]), df = unpack_bf16x2(dw[j]), ef = unpack_bf16x2(ew[j]);
+      const float h0 = (xf.x - mu[2 * j]) * rs[2 * j], h1 = (xf.y - mu[2 * j + 1]) * rs[2 * j + 1];
+      const float z0 = df.x * act_grad(fmaf(ga[2 * j], h0, be[2 * j]), act);
+      const float z1 = df.y * act_grad(fmaf(ga[2 * j + 1], h1, be[2 * j + 1]), act);
+      const float o0 = rs[2 * j] * (ga[2 * j] * z0 - ma[2 * j] - h0 * mb[2 * j]) + ef.x;
+      const float o1 = rs[2 * j + 1] * (ga[2 * j + 1] * z1 - ma[2 * j + 1] - h1 * mb[2 * j + 1]) + ef.y;
+      o[j] = pack_bf16x2(o0, o1);
+    }
+    *reinterpret_cast<uint4*>(ob + static_cast<long long>(i) * dx_pitch) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+static int gn_geometry(int B, int S, int C, int groups, int* threads, int* R, int* splits, int* vox) {
+  const int cv = C / 8;
+  if (cv > 1024) return 1;
+  int r = 256 / cv;
+  if (r < 1) r = 1;
+  int t = (r * cv + 31) / 32 * 32;
+  if (t < 64) t = 64;
+  if (t < groups) t = groups;
+  int sp = (8 * num_sms() + B - 1) / B;
+  int vx = (S + sp - 1) / sp;
+  if (vx < 4 * r) vx = 4 * r;
+  sp = (S + vx - 1) / vx;
+  *threads = t; *R = r; *splits = sp; *vox = vx;
+  return 0;
+}
+
+int gn_bwd_launch(const void* x, int B, int S, int C, int pitch, int ch_off, const void* dy, int dy_pitch, int dy_off,
+                  const float* stat1, int C1, const float* stat2, int C2, const float* gamma, const float* beta, int groups,
+                  float eps, int act, float* red, const void* extra, int extra_pitch, void* dx, int dx_pitch, int pass,
+                  cudaStream_t st) {
+  const int Ct = C1 + (stat2 ? C2 : 0);
+  if (C % 8 || pitch % 8 || dy_pitch % 8 || dy_off % 8 || ch_off % 8 || groups > 64 || groups < 1 || Ct % groups || ch_off + C > Ct)
+    return set_error(CS_ERR_INVALID, "groupnorm_bwd: channels/pitches must be multiples of 8, <= 64 groups");
+  if (B == 0 || S == 0) return CS_OK;
+  int threads, R, splits, vox;
+  if (gn_geometry(B, S, C, groups, &threads, &R, &splits, &vox)) return set_error(CS_ERR_INVALID, "groupnorm_bwd: C too large");
+  const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x);
+  const __nv_bfloat16* db = reinterpret_cast<const __nv_bfloat16*>(dy);
+  if (pass == 0) {
+    gn_bwd_reduce_kernel<<<dim3(splits, B), threads, C * 2 * sizeof(float), st>>>(
+        xb, S, C, pitch, ch_off, db, dy_pitch, dy_off, stat1, C1, stat2, stat2 ? C2 : 0, gamma, beta, groups, eps, act, red, vox);
+  } else {
+    if (dx_pitch % 8 || (extra && extra_pitch % 8)) return set_error(CS_ERR_INVALID, "groupnorm_bwd: output pitch % 8");
+    gn_bwd_apply_kernel<<<dim3(splits, B), threads, 0, st>>>(
+        xb, S, C, pitch, ch_off, db, dy_pitch, dy_off, stat1, C1, stat2, stat2 ? C2 : 0, gamma, beta, groups, eps, act, red,
+        reinterpret_cast<const __nv_bfloat16*>(extra), extra_pitch, reinterpret_cast<__nv_bfloat16*>(dx), dx_pitch, vox);
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(e, "groupnorm_bwd: launch");
+  count_launch();
+  return CS_OK;
+}
+
+// out[c] += scale * sum_b in[b][c][comp]   (parameter gradients from per-sample sums: d beta, d gamma, conv bias grads)
+__global__ void batch_reduce_kernel(const float* __restrict__ in, int B, int C, int comp, int ncomp, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s = 0.f;
+  for (int b = 0; b < B; ++b) s += in[(static_cast<long long>(b) * C + c) * ncomp + comp];
+  out[c] += s;
+}
+int batch_reduce_launch(const float* in, int B, int C, int comp, int ncomp, float* out, cudaStream_t st) {
+  if (B == 0 || C == 0) return CS_OK;
+  batch_reduce_kernel<<<(C + 127) / 128, 128, 0, st>>>(in, B, C, comp, ncomp, out);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(e, "batch_reduce: launch");
+  count_launch();
+  return CS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm backward: one warp per row; dgamma / dbeta accumulate per lane over the warp's rows, then CTA -> global.
+// dx = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat)) [+ extra]
+// ------------------------------------------------------------------------------------------------
+template <int VPL>
+__global__ void __launch_bounds__(256)
+layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, long long M, int C, int pitch, const __nv_bfloat16* __restrict__ dy,
+                     int dy_pitch, const float* __restrict__ gamma, float eps, const __nv_bfloat16* __restrict__ extra,
+                     int extra_pitch, __nv_bfloat16* __restrict__ dx, int dx_pitch, float* __restrict__ dgamma,
+                     float* __restrict__ dbeta) {
+  extern __shared__ float sacc[];   // [2][C]
+  const int lane = threadIdx.x & 31;
+  const int cv = C >> 3;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sacc[i] = 0.f;
+  __syncthreads();
+  float g[VPL][8], ag[VPL][8], ab[VPL][8];
+#pragma unroll
+  for (int k = 0; k < VPL; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = (lane + 32 * k) * 8 + j;
+      g[k][j] = (c < C) ? __ldg(gamma + c) : 0.f;
+      ag[k][j] = ab[k][j] = 0.f;
+    }
+  const float inv_c = 1.f / C;
+  const long long warps_total = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
+  for (long long row = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5); row < M; row += warps_total) {
+    float xv[VPL][8], dv[VPL][8];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const int vi = lane + 32 * k;
+      uint4 u = make_uint4(0u, 0u, 0u, 0u), d = make_uint4(0u, 0u, 0u, 0u);
+      if (vi < cv) {
+        u = *reinterpret_cast<const uint4*>(x + row * pitch + vi * 8);
+        d = *reinterpret_cast<const uint4*>(dy + row * dy_pitch + vi * 8);
+      }
+      const uint32_t xw[4] = {u.x, u.y, u.z, u.w}, dw[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 xf = unpack_bf16x2(xw[j]), df = unpack_bf16x2(dw[j]);
+        xv[k][2 * j] = xf.x; xv[k][2 * j + 1] = xf.y;
+        dv[k][2 * j] = df.x; dv[k][2 * j + 1] = df.y;
+        s += xf.x + xf.y;
+      }
+    }
+    const float mean = warp_sum(s) * inv_c;
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const bool ok = (lane + 32 * k) < cv;
+        const float dlt = ok ? xv[k][j] - mean : 0.f;
+        xv[k][j] = dlt;
+        q += dlt * dlt;
+      }
+    const float rstd = rsqrtf(warp_sum(q) * inv_c + eps);
+    float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float h = xv[k][j] * rstd;
+        xv[k][j] = h;
+        ab[k][j] += dv[k][j];
+        ag[k][j] += dv[k][j] * h;
+        const float gd = g[k][j] * dv[k][j];
+        dv[k][j] = gd;
+        m1 += gd;
+        m2 += gd * h;
+      }
+    m1 = warp_sum(m1) * inv_c;
+    m2 = warp_sum(m2) * inv_c;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const int vi = lane + 32 * k;
+      if (vi < cv) {
+        uint4 e = make_uint4(0u, 0u, 0u, 0u);
+        if (extra) e = *reinterpret_cast<const uint4*>(extra + row * extra_pitch + vi * 8);
+        const uint32_t ew[4] = {e.x, e.y, e.z, e.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 ef = unpack_bf16x2(ew[j]);
+          o[j] = pack_bf16x2(rstd * (dv[k][2 * j] - m1 - xv[k][2 * j] * m2) + ef.x,
+                             rstd * (dv[k][2 * j + 1] - m1 - xv[k][2 * j + 1] * m2) + ef.y);
+        }
+        *reinterpret_cast<uint4*>(dx + row * dx_pitch + vi * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < VPL; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = (lane + 32 * k) * 8 + j;
+      if (c < C) {
+        atomicAdd(&sacc[c], ag[k][j]);
+        atomicAdd(&sacc[C + c], ab[k][j]);
+      }
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    atomicAdd(dgamma + i, sacc[i]);
+    atomicAdd(dbeta + i, sacc[C + i]);
+  }
+}
+
+int layernorm_bwd_launch(const void* x, long long M, int C, int pitch, const void* dy, int dy_pitch, const float* gamma,
+                         float eps, const void* extra, int extra_pitch, void* dx, int dx_pitch, float* dgamma, float* dbeta,
+                         cudaStream_t st) {
+  if (C % 8 || C > 1024 || pitch % 8 || dy_pitch % 8 || dx_pitch % 8 || (extra && extra_pitch % 8))
+    return set_error(CS_ERR_INVALID, "layernorm_bwd: C % 8 == 0, C <= 1024, pitches % 8 == 0");
+  if (M == 0) return CS_OK;
+  const int vpl = (C / 8 + 31) / 32;
+  long long blocks = (M + 7) / 8;
+  const long long cap = 4ll * num_sms();
+  if (blocks > cap) blocks = cap;
+  const size_t sm = 2 * C * sizeof(float);
+#define CS_LNB(V)                                                                                                        \
+  layernorm_bwd_kernel<V><<<(int)blocks, 256, sm, st>>>(                                                                 \
+      reinterpret_cast<const __nv_bfloat16*>(x), M, C, pitch, reinterpret_cast<const __nv_bfloat16*>(dy), dy_pitch, gamma, \
+      eps, reinterpret_cast<const __nv_bfloat16*>(extra), extra_pitch, reinterpret_cast<__nv_bfloat16*>(dx), dx_pitch,   \
+      dgamma, dbeta)
+  switch (vpl) {
+    case 1: CS_LNB(1); break;
+    case 2: CS_LNB(2); break;
+    case 3: CS_LNB(3); break;
+    default: CS_LNB(4); break;
+  }
+#undef CS_LNB
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(e, "layernorm_bwd: launch");
+  count_launch();
+  return CS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// GEGLU backward: u = [a | g] (M, 2I), f = a * gelu(g); du = [df * gelu(g) | df * a * gelu'(g)]
+// ------------------------------------------------------------------------------------------------
+__global__ void geglu_bwd_kernel(const __nv_bfloat16* __restrict__ u, long long M, int I, int u_pitch,
+                                 const __nv_bfloat16* __restrict__ df, int df_pitch, __nv_bfloat16* __restrict__ du, int du_pitch) {
+  const int iv = I >> 3;
+  const long long total = M * iv;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long row = idx / iv;
+    const int c = static_cast<int>(idx - row * iv) * 8;
+    const uint4 a4 = *reinterpret_cast<const uint4*>(u + row * u_pitch + c);
+    const uint4 g4 = *reinterpret_cast<const uint4*>(u + row * u_pitch + I + c);
+    const uint4 d4 = *reinterpret_cast<const uint4*>(df + row * df_pitch + c);
+    const uint32_t aw[4] = {a4.x, a4.y, a4.z, a4.w}, gw[4] = {g4.x, g4.y, g4.z, g4.w}, dw[4] = {d4.x, d4.y, d4.z, d4.w};
+    uint32_t oa[4], og[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 af = unpack_bf16x2(aw[j]), gf = unpack_bf16x2(gw[j]), dd = unpack_bf16x2(dw[j]);
+      oa[j] = pack_bf16x2(dd.x * gelu_erf_f(gf.x), dd.y * gelu_erf_f(gf.y));
+      og[j] = pack_bf16x2(dd.x * af.x * act_grad(gf.x, CS_ACT_GELU), dd.y * af.y * act_grad(gf.y, CS_ACT_GELU));
+    }
+    *reinterpret_cast<uint4*>(du + row * du_pitch + c) = make_uint4(oa[0], oa[1], oa[2], oa[3]);
+    *reinterpret_cast<uint4*>(du + row * du_pitch + I + c) = make_uint4(og[0], og[1], og[2], og[3]);
+  }
+}
+int geglu_bwd_launch(const void* u, long long M, int I, int u_pitch, const void* df, int df_pitch, void* du, int du_pitch,
+                     cudaStream_t st) {
+  if (I % 8 || u_pitch % 8 || df_pitch % 8 || du_pitch % 8) return set_error(CS_ERR_INVALID, "geglu_bwd: dims % 8");
+  if (M == 0) return CS_OK;
+  long long blocks = (M * (I / 8) + 255) / 256;
+  const long long cap = 16ll * num_sms();
+  if (blocks > cap) blocks = cap;
+  geglu_bwd_kernel<<<(int)blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(u), M, I, u_pitch,
+                                                 reinterpret_cast<const __nv_bfloat16*>(df), df_pitch,
+                                                 reinterpret_cast<__nv_bfloat16*>(du), du_pitch);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(e, "geglu_bwd: launch");
+  count_launch();
+  return CS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// nearest-upsample backward (sum over each fd x fh x fw block) and zero insertion (data gradient of a strided conv)
+// ------------------------------------------------------------------------------------------------
+__global__ void upsample_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int B, int D, int H, int W, int C, int fd, int fh,
+                                    int fw, int dy_pitch, __nv_bfloat16* __restrict__ dx, int dx_pitch) {
+  const int cv = C >> 3;
+  const long long total = static_cast<long long>(B) * D * H * W * cv;
+  const int Ho = H * fh, Wo = W * fw, Do = D * fd;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    long long t = idx;
+    const int c = static_cast<int>(t % cv) * 8; t /= cv;
+    const int w = static_cast<int>(t % W); t /= W;
+    const int h = static_cast<int>(t % H); t /= H;
+    const int d = static_cast<int>(t % D); t /= D;
+    const int b = static_cast<int>(t);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int a = 0; a < fd; ++a)
+      for (int e = 0; e < fh; ++e)
+        for (int f = 0; f < fw; ++f) {
+          const long long vox = ((static_cast<long long>(b) * Do + d * fd + a) * Ho + h * fh + e) * Wo + w * fw + f;
+          const uint4 u = *reinterpret_cast<const uint4*>(dy + vox * dy_pitch + c);
+          const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 ff = unpack_bf16x2(uw[j]);
+            acc[2 * j] += ff.x; acc[2 * j + 1] += ff.y;
+          }
+        }
+    const long long vox = ((static_cast<long long>(b) * D + d) * H + h) * W + w;
+    *reinterpret_cast<uint4*>(dx + vox * dx_pitch + c) =
+        make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
+  }
+}
+int upsample_bwd_launch(const void* dy, int B, int D, int H, int W, int C, int fd, int fh, int fw, int dy_pitch, void* dx,
+                        int dx_pitch, cudaStream_t st) {
+  if (C % 8 || dy_pitch % 8 || dx_pitch % 8) return set_error(CS_ERR_INVALID, "upsample_bwd: C, pitches % 8");
+  const long long total = static_cast<long long>(B) * D * H * W * (C / 8);
+  if (total == 0) return CS_OK;
+  long long blocks = (total + 255) / 256;
+  const long long cap = 16ll * num_sms();
+  if (blocks > cap) blocks = cap;
+  upsample_bwd_kernel<<<(int)blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(dy), B, D, H, W, C, fd, fh, fw,
+                                                    dy_pitch, reinterpret_cast<__nv_bfloat16*>(dx), dx_pitch);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(e, "upsample_bwd: launch");
+  count_launch();
+  return CS_OK;
+}
+
+// out (B, D*sd, H*sh, W*sw, C): out[b][d*sd][h*sh][w*sw] = in[b][d][h][w], zero elsewhere
+__global__ void zero_insert_kernel(const __nv_bfloat16* __restrict__ in, int B, int D, int H, int W, int C, int sd, int sh, int sw,
+                                   int in_pitch, __nv_bfloat16* __restrict__ out, int out_pitch) {
+  const int cv = C >> 3;
+  const int Do = D * sd, Ho = H * sh, Wo = W * sw;
+  const long long total = static_cast<long long>(B) * Do * Ho * Wo * cv;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    long long t = idx;
+    const int c = static_cast<int>(t % cv) * 8; t /= cv;
+    const int w = static_cast<int>(t % Wo); t /= Wo;
+    const int h = static_cast<int>(t % Ho); t /= Ho;
+    const int d = static_cast<int>(t % Do); t /= Do;
+    const int b = static_cast<int>(t);
+    uint4 u = make_uint4(0u, 0u, 0u, 0u);
+    if (d % sd == 0 && h % sh == 0 && w % sw == 0) {
+      const long long vin = ((static_cast<long long>(b) * D + d / sd) * H + h / sh) * W + w / sw;
+      u = *reinterpret_cast<const uint4*>(in + vin * in_pitch + c);
+    }
+    const long long vout = ((static_cast<long long>(b) * Do + d) * Ho + h) * Wo + w;
+    *reinterpret_cast<uint4*>(out + vout * out_pitch + c) = u;
+  }
+}
+int zero_insert_launch(const void* in, int B, int D, int H, int W, int C, int sd, int sh, int sw, int in_pitch, void* out,
+                       int out_pitch, cudaStream_t st) {
+  if (C % 8 || in_pitch % 8 || out_pitch % 8) return set_error(CS_ERR_INVALID, "zero_insert: C, pitches % 8");
+  const long long total = static_cast<long long>(B) * D * sd * H * sh * W * sw * (C / 8);
+  if (total == 0) return CS_OK;
+  long long blocks = (total + 255) / 256;
+  const long long cap = 16ll * num_sms();
+  if (blocks > cap) blocks = cap;
+  zero_insert_kernel<<<(int)blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(in), B, D, H, W, C, sd, sh, sw,
+                                                   in_pitch, reinterpret_cast<__nv_bfloat16*>(out), out_pitch);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(e, "zero_insert: launch");
+  count_launch();
+  return CS_OK;
+}
+
+// y (bf16, rows x C with pitch) += x
+__global__ void add_bf16_kernel(__nv_bfloat16* __restrict__ y, int y_pitch, const __nv_bfloat16* __restrict__ x, int x_pitch,
+                                long long M, int C) {
+  const int cv = C >> 3;
+  const long long total = M * cv;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long row = idx / cv;
+    const int c = static_cast<int>(idx - row * cv) * 8;
+    const uint4 a = *reinterpret_cast<const uint4*>(y + row * y_pitch + c);
+    const uint4 b = *reinterpret_cast<const uint4*>(x + row * x_pitch + c);
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 af = unpack_bf16x2(aw[j]), bf = unpack_bf16x2(bw[j]);
+      o[j] = pack_bf16x2(af.x + bf.x, af.y + bf.y);
+    }
+    *reinterpret_cast<uint4*>(y + row * y_pitch + c) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+int add_bf16_launch(void* y, int y_pitch, const void* x, int x_pitch, long long M, int C, cudaStream_t st) {
+  if (C % 8 || y_pitch % 8 || x_pitch % 8) return set_error(CS_ERR_INVALID, "add_bf16: C, pitches % 8");
+  if (M == 0) return CS_OK;
+  long long blocks = (M * (C / 8) + 255) / 256;
+  const long long cap = 16ll * num_sms();
+  if (blocks > cap) blocks = cap;
+  add_bf16_kernel<<<(int)blocks, 256, 0, st>>>(reinterpret_cast<__nv_bfloat16*>(y), y_pitch,
+                                                reinterpret_cast<const __nv_bfloat16*>(x), x_pitch, M, C);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(e, "add_bf16: launch");
+  count_launch();
+  return CS_OK;
+}
+
+// fp32 rows -> bf16 rows with independent pitches (dQ accumulator -> the q section of d_qkv)
+__global__ void cast_rows_kernel(const float* __restrict__ in, int in_pitch, long long M, int C, __nv_bfloat16* __restrict__ out,
+                                 int out_pitch) {
+  const int cv = C >> 3;
+  const long long total = M * cv;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long row = idx / cv;
+    const int c = static_cast<int>(idx - row * cv) * 8;
+    const float4 a = *reinterpret_cast<const float4*>(in + row * in_pitch + c);
+    const float4 b = *reinterpret_cast<const float4*>(in + row * in_pitch + c + 4);
+    *reinterpret_cast<uint4*>(out + row * out_pitch + c) =
+        make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
+  }
+}
+int cast_rows_launch(const float* in, int in_pitch, long long M, int C, void* out, int out_pitch, cudaStream_t st) {
+  if (C % 8 || in_pitch % 4 || out_pitch % 8) return set_error(CS_ERR_INVALID, "cast_rows: C % 8, pitches");
+  if (M == 0) return CS_OK;
+  long long blocks = (M * (C / 8) + 255) / 256;
+  const long long cap = 16ll * num_sms();
+  if (blocks > cap) blocks = cap;
+  cast_rows_kernel<<<(int)blocks, 256, 0, st>>>(in, in_pitch, M, C, reinterpret_cast<__nv_bfloat16*>(out), out_pitch);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(e, "cast_rows: launch");
+  count_launch();
+  return CS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Small fp32 GEMM for the per-sample vectors of the path (time embedding, emb_layers, single-token cross-attention):
+// C[M][N] = (accumulate ? C : 0) + op(A)[M][K] * op(B)[K][N], row-major, op = optional transpose; optional SiLU'(pre)
+// multiplier on the output (pre[M][N] = the pre-activation whose SiLU fed the forward).  Tiny problems (M or N = batch).
+// ------------------------------------------------------------------------------------------------
+__global__ void sgemm_small_kernel(const float* __restrict__ A, int lda, int ta, const float* __restrict__ Bm, int ldb, int tb,
+                                   float* __restrict__ Cm, int ldc, int M, int N, int K, int accumulate,
+                                   const float* __restrict__ silu_pre, int ld_pre) {
+  __shared__ float sA[32][33], sB[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8 threads, each 4 rows of a 32 x 32 tile
+  const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int k0 = 0; k0 < K; k0 += 32) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = ty + 8 * i;
+      // sA[r][tx] = op(A)[m0 + r][k0 + tx]; read along the contiguous axis of the stored matrix
+      if (!ta) {
+        const int m = m0 + r, k = k0 + tx;
+        sA[r][tx] = (m < M && k < K) ? A[static_cast<long long>(m) * lda + k] : 0.f;
+      } else {
+        const int k = k0 + r, m = m0 + tx;
+        sA[tx][r] = (m < M && k < K) ? A[static_cast<long long>(k) * lda + m] : 0.f;
+      }
+      if (!tb) {
+        const int k = k0 + r, n = n0 + tx;
+        sB[r][tx] = (k < K && n < N) ? Bm[static_cast<long long>(k) * ldb + n] : 0.f;
+      } else {
+        const int n = n0 + r, k = k0 + tx;
+        sB[tx][r] = (k < K && n < N) ? Bm[static_cast<long long>(n) * ldb + k] : 0.f;
+      }
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) {
+      const float b = sB[k][tx];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[i] = fmaf(sA[ty + 8 * i][k], b, acc[i]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty + 8 * i, n = n0 + tx;
+    if (m < M && n < N) {
+      float v = acc[i];
+      if (silu_pre) v *= act_grad(silu_pre[static_cast<long long>(m) * ld_pre + n], CS_ACT_SILU);
+      float* c = Cm + static_cast<long long>(m) * ldc + n;
+      *c = accumulate ? *c + v : v;
+    }
+  }
+}
+int sgemm_small_launch(const float* A, int lda, int ta, const float* Bm, int ldb, int tb, float* Cm, int ldc, int M, int N, int K,
+                       int accumulate, const float* silu_pre, int ld_pre, cudaStream_t st) {
+  if (M <= 0 || N <= 0 || K <= 0) return CS_OK;
+  sgemm_small_kernel<<<dim3((N + 31) / 32, (M + 31) / 32), 256, 0, st>>>(A, lda, ta, Bm, ldb, tb, Cm, ldc, M, N, K, accumulate,
+                                                                       silu_pre, ld_pre);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(e, "sgemm_small: launch");
+  count_launch();
+  return CS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// loss = mean((eps_hat - eps)^2) (p_losses, sdfusion_txt2shape_model.py:311-345: mean over (c,d,h,w) then over b, both
+// with equal counts = one global mean); d_eps = 2 (eps_hat - eps) * loss_scale / n.  loss accumulates into *loss.
+// ------------------------------------------------------------------------------------------------
+__global__ void mse_loss_grad_kernel(const float* __restrict__ pred, const float* __restrict__ target, long long n, float gscale,
+                                     float* __restrict__ grad, float* __restrict__ loss) {
+  float s = 0.f;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float d = pred[i] - target[i];
+    s += d * d;
+    if (grad) grad[i] = 2.f * d * gscale;
+  }
+  s = warp_sum(s);
+  __shared__ float ws[32];
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < (blockDim.x >> 5) ? ws[threadIdx.x] : 0.f;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) atomicAdd(loss, t / static_cast<float>(n));
+  }
+}
+int mse_loss_grad_launch(const float* pred, const float* target, long long n, float loss_scale, float* grad, float* loss,
+                         cudaStream_t st) {
+  if (n <= 0) return CS_OK;
+  long long blocks = (n + 1023) / 1024;
+  if (blocks > 2 * num_sms()) blocks = 2 * num_sms();
+  mse_loss_grad_kernel<<<(int)blocks, 256, 0, st>>>(pred, target, n, loss_scale / static_cast<float>(n), grad, loss);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(e, "mse_loss_grad: launch");
+  count_launch();
+  return CS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// AdamW over a flat fp32 parameter buffer (torch.optim.AdamW semantics: decoupled weight decay, bias-corrected moments,
+// eps added outside the sqrt), with the gradient-clipping factor of clip_grad_norm_ folded in:
+//   clip = min(1, max_norm / (sqrt(*sumsq) + 1e-6))   (train_3dfront.py:399; *sumsq from sumsq_kernel, or null)
+// ------------------------------------------------------------------------------------------------
+__global__ void sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ out) {
+  float s = 0.f;
+  const long long n4 = n >> 2;
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 v = g4[i];
+    s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const float v = g[(n4 << 2) + threadIdx.x];
+    s += v * v;
+  }
+  s = warp_sum(s);
+  __shared__ float ws[32];
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < (blockDim.x >> 5) ? ws[threadIdx.x] : 0.f;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) atomicAdd(out, t);
+  }
+}
+int sumsq_launch(const float* g, long long n, float* out, cudaStream_t st) {
+  if (n <= 0) return CS_OK;
+  if (reinterpret_cast<uintptr_t>(g) % 16) return set_error(CS_ERR_INVALID, "sumsq: buffer must be 16-byte aligned");
+  long long blocks = (n / 4 + 255) / 256;
+  if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
+  if (blocks < 1) blocks = 1;
+  sumsq_kernel<<<(int)blocks, 256, 0, st>>>(g, n, out);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(e, "sumsq: launch");
+  count_launch();
+  return CS_OK;
+}
+
+__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                             long long n, float lr, float beta1, float beta2, float eps, float wd, float bc1, float bc2_sqrt,
+                             const float* __restrict__ sumsq, float max_norm, float grad_scale) {
+  float clip = grad_scale;
+  if (sumsq) {
+    const float norm = sqrtf(*sumsq) * grad_scale;
+    clip *= fminf(1.f, max_norm / (norm + 1e-6f));
+  }
+  const float step = lr / bc1;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float gi = g[i] * clip;
+    const float mi = beta1 * m[i] + (1.f - beta1) * gi;
+    const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = p[i] * (1.f - lr * wd) - step * (mi / denom);
+  }
+}
+int adamw_launch(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+                 float wd, int step, const float* sumsq, float max_norm, float grad_scale, cudaStream_t st) {
+  if (n <= 0) return CS_OK;
+  if (step < 1) return set_error(CS_ERR_INVALID, "adamw: step counts from 1");
+  const float bc1 = 1.f - powf(beta1, static_cast<float>(step));
+  const float bc2 = 1.f - powf(beta2, static_cast<float>(step));
+  long long blocks = (n + 255) / 256;
+  if (blocks > 16 * num_sms()) blocks = 16 * num_sms();
+  adamw_kernel<<<(int)blocks, 256, 0, st>>>(p, g, m, v, n, lr, beta1, beta2, eps, wd, bc1, sqrtf(bc2), sumsq, max_norm, grad_scale);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(e, "adamw: launch");
+  count_launch();
+  return CS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// packed fp32 weight gradient (Cout, taps, pad64(C1) + pad64(C2)) -> parameter layout (Cout, C1 + C2, taps), accumulated
+// ------------------------------------------------------------------------------------------------
+__global__ void unpack_wgrad_kernel(const float* __restrict__ dw, int taps, int C1, int C2, int C1pad, int ctot,
+                                    float* __restrict__ grad) {
+  extern __shared__ float tile[];   // [taps][65]
+  const int co = blockIdx.y;
+  const int Cin = C1 + C2;
+  const int ci0 = blockIdx.x * 64;
+  const float* src = dw + static_cast<long long>(co) * taps * ctot;
+  for (int i = threadIdx.x; i < taps * 64; i += blockDim.x) {
+    const int t = i >> 6, c = i & 63, ci = ci0 + c;
+    float v = 0.f;
+    if (ci < Cin) v = src[static_cast<long long>(t) * ctot + (ci < C1 ? ci : C1pad + (ci - C1))];
+    tile[t * 65 + c] = v;
+  }
+  __syncthreads();
+  float* dst = grad + (static_cast<long long>(co) * Cin + ci0) * taps;
+  const int n = min(64, Cin - ci0) * taps;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int c = i / taps, t = i - c * taps;
+    dst[i] += tile[t * 65 + c];
+  }
+}
+int unpack_wgrad_launch(const float* dw, int Cout, int taps, int C1, int C2, float* grad, cudaStream_t st) {
+  if (Cout <= 0 || taps <= 0 || C1 <= 0) return set_error(CS_ERR_INVALID, "unpack_wgrad: bad dims");
+  const int c1p = (C1 + 63) / 64 * 64, c2p = (C2 + 63) / 64 * 64;
+  const size_t sm = static_cast<size_t>(taps) * 65 * sizeof(float);
+  if (sm > 48 * 1024) return set_error(CS_ERR_UNSUPPORTED, "unpack_wgrad: too many taps");
+  unpack_wgrad_kernel<<<dim3((C1 + C2 + 63) / 64, Cout), 256, sm, st>>>(dw, taps, C1, C2, c1p, c1p + c2p, grad);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(e, "unpack_wgrad: launch");
+  count_launch();
+  return CS_OK;
+}
+
+}  // namespace cs

@@ -80,3 +80,207 @@ def unpack_wgrad(dw: torch.Tensor, shape: Sequence[int], split=None) -> torch.Te
         off += _pad64(c)
     g = cols[0] if len(cols) == 1 else torch.cat(cols, dim=2)
     return g.permute(0, 2, 1).reshape(shape)
+
+
+def unpack_wgrad_into(dw: torch.Tensor, grad: torch.Tensor, split=None) -> torch.Tensor:
+    """grad (the parameter's layout: (Cout, Cin, kd, kh, kw) or (out, in), fp32 contiguous) += packed dw."""
+    co, taps, _ = dw.shape
+    ci = grad.shape[1]
+    c1, c2 = (ci, 0) if split is None else (int(split[0]), int(split[1]))
+    if grad.dtype != torch.float32 or not grad.is_contiguous() or grad.numel() != co * ci * taps or c1 + c2 != ci:
+        raise _lib.CsError("unpack_wgrad_into: grad must be contiguous fp32 of the parameter's shape")
+    check(_lib.load().cs_unpack_wgrad(dw.data_ptr(), co, taps, c1, c2, grad.data_ptr(), _stream()), "cs_unpack_wgrad")
+    return grad
+
+
+# ----------------------------------------------------------------------------------------------
+# normalisation / pointwise gradients
+# ----------------------------------------------------------------------------------------------
+def groupnorm_bwd(x: torch.Tensor, stat: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, dy: torch.Tensor, *,
+                  groups: int = 32, eps: float = 1e-5, act: int = 0, x2: Optional[torch.Tensor] = None,
+                  stat2: Optional[torch.Tensor] = None, extra: Optional[torch.Tensor] = None,
+                  extra2: Optional[torch.Tensor] = None, dgamma: Optional[torch.Tensor] = None,
+                  dbeta: Optional[torch.Tensor] = None, need_dx: bool = True):
+    """Backward of ops.groupnorm_fused: dy is the gradient of act(GN(cat(x, x2))) over all C1 + C2 channels.
+    Returns (dx, dx2) (bf16, + extra / extra2 when given) and accumulates dgamma / dbeta (fp32 (C1 + C2,), +=)."""
+    lib = _lib.load()
+    B, D, H, W, C1, p1 = _check_act(x, "groupnorm_bwd.x")
+    S = D * H * W
+    C2, p2 = 0, 0
+    if x2 is not None:
+        _, _, _, _, C2, p2 = _check_act(x2, "groupnorm_bwd.x2")
+    Ct = C1 + C2
+    dB, dD, dH, dW, dC, pdy = _check_act(dy, "groupnorm_bwd.dy")
+    if (dB, dD * dH * dW, dC) != (B, S, Ct):
+        raise _lib.CsError("groupnorm_bwd: dy must cover all channels of the normalised tensor")
+    st = _stream()
+    red = torch.zeros((B, Ct, 2), dtype=torch.float32, device=x.device)
+    g, bta = _ptr(gamma), _ptr(beta)
+    srcs = [(x, C1, p1, 0, extra)] + ([(x2, C2, p2, C1, extra2)] if x2 is not None else [])
+    for t, c, p, off, _ in srcs:
+        check(lib.cs_groupnorm_bwd(t.data_ptr(), B, S, c, p, off, dy.data_ptr(), pdy, off, stat.data_ptr(), C1, _ptr(stat2), C2,
+                                   g, bta, groups, eps, act, red.data_ptr(), None, 0, None, 0, 0, st), "cs_groupnorm_bwd")
+    outs = []
+    if need_dx:
+        for t, c, p, off, ex in srcs:
+            dx = torch.empty((B, D, H, W, c), dtype=torch.bfloat16, device=x.device)
+            check(lib.cs_groupnorm_bwd(t.data_ptr(), B, S, c, p, off, dy.data_ptr(), pdy, off, stat.data_ptr(), C1, _ptr(stat2),
+                                       C2, g, bta, groups, eps, act, red.data_ptr(), _ptr(ex), 0 if ex is None else ex.stride(3),
+                                       dx.data_ptr(), c, 1, st), "cs_groupnorm_bwd")
+            outs.append(dx)
+    if dbeta is not None:
+        check(lib.cs_batch_reduce(red.data_ptr(), B, Ct, 0, 2, dbeta.data_ptr(), st), "cs_batch_reduce")
+    if dgamma is not None:
+        check(lib.cs_batch_reduce(red.data_ptr(), B, Ct, 1, 2, dgamma.data_ptr(), st), "cs_batch_reduce")
+    if not need_dx:
+        return None, None
+    return outs[0], (outs[1] if len(outs) > 1 else None)
+
+
+def batch_reduce(stat: torch.Tensor, comp: int, out: torch.Tensor) -> torch.Tensor:
+    """out (C,) += sum_b stat[b, :, comp]   (stat fp32 (B, C, ncomp) contiguous)."""
+    B, Cc, n = stat.shape
+    check(_lib.load().cs_batch_reduce(stat.data_ptr(), B, Cc, comp, n, out.data_ptr(), _stream()), "cs_batch_reduce")
+    return out
+
+
+def layernorm_bwd(x: torch.Tensor, gamma: torch.Tensor, dy: torch.Tensor, dgamma: torch.Tensor, dbeta: torch.Tensor,
+                  eps: float = 1e-5, extra: Optional[torch.Tensor] = None) -> torch.Tensor:
+    B, D, H, W, Cc, p = _check_act(x, "layernorm_bwd.x")
+    _, _, _, _, _, pdy = _check_act(dy, "layernorm_bwd.dy")
+    dx = torch.empty((B, D, H, W, Cc), dtype=torch.bfloat16, device=x.device)
+    check(_lib.load().cs_layernorm_bwd(x.data_ptr(), B * D * H * W, Cc, p, dy.data_ptr(), pdy, gamma.data_ptr(), eps, _ptr(extra),
+                                       0 if extra is None else extra.stride(3), dx.data_ptr(), Cc, dgamma.data_ptr(),
+                                       dbeta.data_ptr(), _stream()), "cs_layernorm_bwd")
+    return dx
+
+
+def geglu_bwd(u: torch.Tensor, df: torch.Tensor) -> torch.Tensor:
+    B, D, H, W, C2, p = _check_act(u, "geglu_bwd.u")
+    _, _, _, _, I, pdf = _check_act(df, "geglu_bwd.df")
+    if I * 2 != C2:
+        raise _lib.CsError("geglu_bwd: df must have half the channels of u")
+    du = torch.empty((B, D, H, W, C2), dtype=torch.bfloat16, device=u.device)
+    check(_lib.load().cs_geglu_bwd(u.data_ptr(), B * D * H * W, I, p, df.data_ptr(), pdf, du.data_ptr(), C2, _stream()),
+          "cs_geglu_bwd")
+    return du
+
+
+def upsample_nearest_bwd(dy: torch.Tensor, factors: Sequence[int]) -> torch.Tensor:
+    B, Do, Ho, Wo, Cc, p = _check_act(dy, "upsample_bwd.dy")
+    fd, fh, fw = factors
+    D, H, W = Do // fd, Ho // fh, Wo // fw
+    dx = torch.empty((B, D, H, W, Cc), dtype=torch.bfloat16, device=dy.device)
+    check(_lib.load().cs_upsample_nearest_bwd(dy.data_ptr(), B, D, H, W, Cc, fd, fh, fw, p, dx.data_ptr(), Cc, _stream()),
+          "cs_upsample_nearest_bwd")
+    return dx
+
+
+def zero_insert(x: torch.Tensor, stride: Sequence[int]) -> torch.Tensor:
+    B, D, H, W, Cc, p = _check_act(x, "zero_insert.x")
+    sd, sh, sw = stride
+    out = torch.empty((B, D * sd, H * sh, W * sw, Cc), dtype=torch.bfloat16, device=x.device)
+    check(_lib.load().cs_zero_insert(x.data_ptr(), B, D, H, W, Cc, sd, sh, sw, p, out.data_ptr(), Cc, _stream()), "cs_zero_insert")
+    return out
+
+
+def conv3d_dgrad_strided(dy: torch.Tensor, w_dgrad: torch.Tensor, stride: Sequence[int], **kw) -> torch.Tensor:
+    """dX of a 3x3x3 / pad 1 conv with stride (sd, sh, sw) over an input whose extent is stride * output extent
+    (Downsample, openai_model_3d.py:186-190): zero insertion followed by the stride-1 data-gradient conv."""
+    return conv3d_dgrad(zero_insert(dy, stride), w_dgrad, **kw)
+
+
+def add_(y: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    """y += x (bf16 channels-last, same logical shape)."""
+    B, D, H, W, Cc, py = _check_act(y, "add_.y")
+    _, _, _, _, Cx, px = _check_act(x, "add_.x")
+    if Cx != Cc or x.numel() != y.numel():
+        raise _lib.CsError("add_: shape mismatch")
+    check(_lib.load().cs_add_bf16(y.data_ptr(), py, x.data_ptr(), px, B * D * H * W, Cc, _stream()), "cs_add_bf16")
+    return y
+
+
+def sgemm(a: torch.Tensor, b: torch.Tensor, *, trans_a: bool = False, trans_b: bool = False, out: Optional[torch.Tensor] = None,
+          accumulate: bool = False, silu_pre: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 out (M, N) [+]= op(a) @ op(b), optionally times SiLU'(silu_pre) elementwise; row-pitched 2-D operands."""
+    for t in (a, b):
+        if t.dtype != torch.float32 or t.dim() != 2 or t.stride(1) != 1 or not t.is_cuda:
+            raise _lib.CsError("sgemm: operands must be fp32 2-D CUDA tensors with a contiguous last dim")
+    M, K = (a.shape[1], a.shape[0]) if trans_a else (a.shape[0], a.shape[1])
+    K2, N = (b.shape[1], b.shape[0]) if trans_b else (b.shape[0], b.shape[1])
+    if K != K2:
+        raise _lib.CsError(f"sgemm: inner dimensions differ ({K} vs {K2})")
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+        accumulate = False
+    if out.dtype != torch.float32 or tuple(out.shape) != (M, N) or out.stride(1) != 1:
+        raise _lib.CsError("sgemm: bad output")
+    check(_lib.load().cs_sgemm_small(a.data_ptr(), a.stride(0), int(trans_a), b.data_ptr(), b.stride(0), int(trans_b),
+                                     out.data_ptr(), out.stride(0), M, N, K, int(accumulate), _ptr(silu_pre),
+                                     0 if silu_pre is None else silu_pre.stride(0), _stream()), "cs_sgemm_small")
+    return out
+
+
+def mse_loss_grad(pred: torch.Tensor, target: torch.Tensor, loss: torch.Tensor, loss_scale: float = 1.0,
+                  need_grad: bool = True):
+    """loss (fp32 scalar tensor) += mean((pred - target)^2); returns d(loss_scale * mean)/d pred (fp32) or None."""
+    if pred.dtype != torch.float32 or target.dtype != torch.float32 or not pred.is_contiguous() or not target.is_contiguous() \
+            or pred.shape != target.shape:
+        raise _lib.CsError("mse_loss_grad: pred / target must be contiguous fp32 of the same shape")
+    grad = torch.empty_like(pred) if need_grad else None
+    check(_lib.load().cs_mse_loss_grad(pred.data_ptr(), target.data_ptr(), pred.numel(), loss_scale, _ptr(grad), loss.data_ptr(),
+                                       _stream()), "cs_mse_loss_grad")
+    return grad
+
+
+def sumsq(g: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    check(_lib.load().cs_sumsq(g.data_ptr(), g.numel(), out.data_ptr(), _stream()), "cs_sumsq")
+    return out
+
+
+def adamw_step(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor, *, lr: float, betas=(0.9, 0.999),
+               eps: float = 1e-8, weight_decay: float = 0.01, step: int, sumsq_buf: Optional[torch.Tensor] = None,
+               max_norm: float = 0.0, grad_scale: float = 1.0) -> None:
+    """In-place torch.optim.AdamW step over flat fp32 buffers (same update rule; clip factor from sumsq_buf if given)."""
+    for t in (p, g, m, v):
+        if t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != p.numel():
+            raise _lib.CsError("adamw_step: p, g, m, v must be contiguous fp32 of equal size")
+    check(_lib.load().cs_adamw(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, betas[0], betas[1], eps,
+                               weight_decay, step, _ptr(sumsq_buf), max_norm, grad_scale, _stream()), "cs_adamw")
+
+
+# ----------------------------------------------------------------------------------------------
+# attention
+# ----------------------------------------------------------------------------------------------
+def attention_lse(q, k, v, *, heads: int, head_dim: int, head_dim_padded: int, scale: float):
+    """ops.attention that also returns the (B, heads, N) base-2 log-sum-exp rows the backward needs."""
+    B, Nq = q.shape[0], q.shape[1]
+    Nk = k.shape[1]
+    out = torch.empty((B, Nq, heads * head_dim), dtype=torch.bfloat16, device=q.device)
+    lse = torch.empty((B, heads, Nq), dtype=torch.float32, device=q.device)
+    check(_lib.load().cs_attention_lse(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, heads, Nq, Nk,
+                                       head_dim_padded, q.stride(1), k.stride(1), out.stride(1), head_dim, scale, lse.data_ptr(),
+                                       _stream()), "cs_attention_lse")
+    return out, lse
+
+
+def attention_bwd(qkv: torch.Tensor, o: torch.Tensor, do: torch.Tensor, lse: torch.Tensor, *, heads: int, head_dim: int,
+                  head_dim_padded: int, scale: float) -> torch.Tensor:
+    """qkv: (B, N, 3 * heads * Dp) bf16 (the fused projection), o / do: (B, N, heads * head_dim) bf16 -> d_qkv like qkv."""
+    B, N, W3 = qkv.shape
+    hd = heads * head_dim_padded
+    if W3 != 3 * hd or qkv.dtype != torch.bfloat16 or not qkv.is_contiguous():
+        raise _lib.CsError("attention_bwd: qkv must be contiguous bf16 (B, N, 3 * heads * Dp)")
+    if do.dtype != torch.bfloat16 or do.stride(-1) != 1 or o.stride(-1) != 1:
+        raise _lib.CsError("attention_bwd: o / do must be bf16 with a contiguous last dim")
+    dqkv = torch.empty_like(qkv)
+    dq32 = torch.zeros((B, N, hd), dtype=torch.float32, device=qkv.device)
+    dsum = torch.empty((B, heads, N), dtype=torch.float32, device=qkv.device)
+    lib = _lib.load()
+    es = qkv.element_size()
+    check(lib.cs_attention_bwd(qkv.data_ptr(), qkv.data_ptr() + hd * es, qkv.data_ptr() + 2 * hd * es, o.data_ptr(),
+                               do.data_ptr(), lse.data_ptr(), dsum.data_ptr(), dq32.data_ptr(), dqkv.data_ptr() + hd * es,
+                               dqkv.data_ptr() + 2 * hd * es, B, heads, N, head_dim_padded, W3, o.stride(-2), do.stride(-2), W3,
+                               head_dim, scale, _stream()), "cs_attention_bwd")
+    check(lib.cs_cast_rows(dq32.data_ptr(), hd, B * N, hd, dqkv.data_ptr(), W3, _stream()), "cs_cast_rows")
+    return dqkv

@@ -91,6 +91,63 @@ typedef struct cs_conv3d_wgrad_args {
   float* dw;                                         /* fp32 [Cout][kd*kh*kw][pad64(C1)+pad64(C2)], accumulated into */
 } cs_conv3d_wgrad_args;
 int cs_conv3d_wgrad(const cs_conv3d_wgrad_args* args, cs_stream_t stream);
+/* packed fp32 weight gradient -> the parameter's own layout: grad[co][ci][tap] += dw[co][tap][packed(ci)] */
+int cs_unpack_wgrad(const float* dw, int32_t Cout, int32_t taps, int32_t C1, int32_t C2, float* grad, cs_stream_t stream);
+
+/* GroupNorm(+act) backward (GroupNorm32 + SiLU, openai_model_3d.py:294-314; Normalize, attention.py:78-79).  x is the
+ * source owning channels [ch_off, ch_off + C) of the (two-source) concatenation whose sums are stat1 / stat2, exactly as in
+ * cs_groupnorm_apply_fused; dy is the gradient of act(GN(x)) for those channels (read at column dy_off).
+ *   pass 0: red[b][c][0..1] += sum_v (dz, dz * xhat), dz = dy * act'(gamma * xhat + beta)      (c = concat channel)
+ *   pass 1: dx = rstd * (gamma dz - mean_g(gamma dz) - xhat mean_g(gamma dz xhat)) + extra       (extra optional, bf16)
+ * Parameter gradients: dbeta[c] = sum_b red[b][c][0], dgamma[c] = sum_b red[b][c][1] (cs_batch_reduce). */
+int cs_groupnorm_bwd(const void* x, int32_t B, int32_t S, int32_t C, int32_t pitch, int32_t ch_off, const void* dy,
+                     int32_t dy_pitch, int32_t dy_off, const float* stat1, int32_t C1, const float* stat2, int32_t C2,
+                     const float* gamma, const float* beta, int32_t groups, float eps, int32_t act, float* red,
+                     const void* extra, int32_t extra_pitch, void* dx, int32_t dx_pitch, int32_t pass, cs_stream_t stream);
+/* out[c] += sum_b in[b][c][comp]   (in: fp32 [B][C][ncomp]) */
+int cs_batch_reduce(const float* in, int32_t B, int32_t C, int32_t comp, int32_t ncomp, float* out, cs_stream_t stream);
+/* nn.LayerNorm backward (attention.py:229-231): dx = LN'(x) dy + extra; dgamma / dbeta accumulated (+=) */
+int cs_layernorm_bwd(const void* x, int64_t M, int32_t C, int32_t pitch, const void* dy, int32_t dy_pitch, const float* gamma,
+                     float eps, const void* extra, int32_t extra_pitch, void* dx, int32_t dx_pitch, float* dgamma, float* dbeta,
+                     cs_stream_t stream);
+/* GEGLU backward (attention.py:44-46): u = [a | g] (M, 2I), du = [df gelu(g) | df a gelu'(g)] */
+int cs_geglu_bwd(const void* u, int64_t M, int32_t I, int32_t u_pitch, const void* df, int32_t df_pitch, void* du,
+                 int32_t du_pitch, cs_stream_t stream);
+/* nearest-upsample backward (openai_model_3d.py:150-155): dx (B, D, H, W, C) = sums of fd x fh x fw blocks of dy */
+int cs_upsample_nearest_bwd(const void* dy, int32_t B, int32_t D, int32_t H, int32_t W, int32_t C, int32_t fd, int32_t fh,
+                            int32_t fw, int32_t dy_pitch, void* dx, int32_t dx_pitch, cs_stream_t stream);
+/* out (B, D*sd, H*sh, W*sw, C): in at the stride lattice, zero elsewhere (data gradient of Downsample's strided conv,
+ * openai_model_3d.py:186-190, = cs_conv3d of this tensor with the flipped filter) */
+int cs_zero_insert(const void* in, int32_t B, int32_t D, int32_t H, int32_t W, int32_t C, int32_t sd, int32_t sh, int32_t sw,
+                   int32_t in_pitch, void* out, int32_t out_pitch, cs_stream_t stream);
+/* y += x on (M, C) bf16 row-pitched matrices (gradient of a tensor with two consumers: block output + decoder skip) */
+int cs_add_bf16(void* y, int32_t y_pitch, const void* x, int32_t x_pitch, int64_t M, int32_t C, cs_stream_t stream);
+/* fp32 rows -> bf16 rows */
+int cs_cast_rows(const float* in, int32_t in_pitch, int64_t M, int32_t C, void* out, int32_t out_pitch, cs_stream_t stream);
+/* small fp32 GEMM for the per-sample vectors (time_embed / emb_layers / single-token cross-attention and their gradients):
+ * C[M][N] = (accumulate ? C : 0) + op(A) op(B), row-major, optionally multiplied by SiLU'(silu_pre[m][n]) */
+int cs_sgemm_small(const float* A, int32_t lda, int32_t trans_a, const float* Bm, int32_t ldb, int32_t trans_b, float* Cm,
+                   int32_t ldc, int32_t M, int32_t N, int32_t K, int32_t accumulate, const float* silu_pre, int32_t ld_pre,
+                   cs_stream_t stream);
+/* p_losses (sdfusion_txt2shape_model.py:311-345): *loss += mean((pred - target)^2); grad = 2 (pred - target) loss_scale / n */
+int cs_mse_loss_grad(const float* pred, const float* target, int64_t n, float loss_scale, float* grad, float* loss,
+                     cs_stream_t stream);
+/* *out += sum g^2 (clip_grad_norm_, train_3dfront.py:399) */
+int cs_sumsq(const float* g, int64_t n, float* out, cs_stream_t stream);
+/* torch.optim.AdamW step (VAEGAN_V2FULL.py:642-650) over a flat fp32 buffer; gradient = g * grad_scale, additionally
+ * clipped to max_norm when `sumsq` (device scalar from cs_sumsq over the same g) is not NULL */
+int cs_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+             float weight_decay, int32_t step, const float* sumsq, float max_norm, float grad_scale, cs_stream_t stream);
+/* cs_attention that also writes the base-2 log-sum-exp of every score row (fp32 [B][H][Nq]) for cs_attention_bwd */
+int cs_attention_lse(const void* q, const void* k, const void* v, void* out, int32_t B, int32_t H, int32_t Nq, int32_t Nk,
+                     int32_t Dp, int32_t q_pitch, int32_t kv_pitch, int32_t o_pitch, int32_t d_out, float scale, float* lse,
+                     cs_stream_t stream);
+/* self-attention backward (attention.py:201-218): dk / dv bf16 laid out like k / v (pitch dqkv_pitch); dq fp32
+ * [B][N][H*Dp], must be zero on entry (accumulated with atomics); dsum_ws fp32 [B][H][N] scratch */
+int cs_attention_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse,
+                     float* dsum_ws, float* dq, void* dk, void* dv, int32_t B, int32_t H, int32_t N, int32_t Dp,
+                     int32_t qkv_pitch, int32_t o_pitch, int32_t do_pitch, int32_t dqkv_pitch, int32_t d_out, float scale,
+                     cs_stream_t stream);
 
 /* ---- GroupNorm (GroupNorm32: ldm_diffusion_util.py:237-239; Normalize: attention.py:78-79,
  *      vqvae_modules.py:13-21) --------------------------------------------------------------- */
