@@ -340,16 +340,33 @@ class UNet3DModel(nn.Module):
             raise ValueError("context_vectors() is the single-token fast path; pass multi-token contexts to forward()")
         return ops.linear_small(context[:, 0].float().contiguous(), pk["ca_w"], pk["ca_b"])
 
-    @torch.no_grad()
+    def trainer(self):
+        """The UNetTrainer (forward with saved activations + explicit backward kernels) bound to this module."""
+        tr = getattr(self, "_trainer_obj", None)
+        if tr is None:
+            from .unet_train import UNetTrainer
+            tr = self._trainer_obj = UNetTrainer(self)
+        return tr
+
     def forward(self, x, timesteps=None, context=None, y=None, context_vecs=None, **kwargs):
         """x: (B, C, D, H, W) fp32 NCDHW, timesteps: (B,) int64, context: (B, 1, context_dim) -> eps (B, C, D, H, W).
+
+        With autograd enabled and trainable parameters (or a context that requires grad) the result carries a grad_fn:
+        `loss.backward()` runs the explicit backward kernels (unet_train.py) and fills `.grad` of every parameter and of
+        `context`, as the reference's autograd does (no gradient is produced for x: the reference never asks for it).
 
         Extensions: `context_vecs` = a cached context_vectors(context) result; x may hold B/r samples, in which
         case sample b reads x[b % (B/r)] (a guided sampler passes x once for [uncond; cond]).
         """
         assert (y is not None) == (self.num_classes is not None), "must specify y if and only if the model is class-conditional"
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and x.requires_grad:
-            raise NotImplementedError("the backward pass of the B200 denoiser is not built yet (round 2)")
+        if torch.is_grad_enabled() and context_vecs is None and context is not None and \
+                (context.requires_grad or any(p.requires_grad for p in self.parameters())):
+            params = [p for p in self.parameters() if p.requires_grad]
+            return _UNetFunction.apply(self, x, timesteps, context, *params)
+        with torch.no_grad():
+            return self._forward_inference(x, timesteps, context, context_vecs)
+
+    def _forward_inference(self, x, timesteps, context, context_vecs):
         _lib.require_device()
         pk = self._ensure_packed()
         B = timesteps.shape[0]
@@ -398,3 +415,22 @@ class UNet3DModel(nn.Module):
             h = run_block(block, entries[n_in + 1 + i], h, skip=hs.pop())    # th.cat([h, hs.pop()], dim=1), never materialised raw
         a = ops.groupnorm_fused(h.t, h.stat, *pk["out_gn"], eps=self.out[0].eps, act=ops.ACT_SILU)
         return ops.conv3d_small_cout(a, pk["out_w"], pk["out_b"], self.out_channels)
+
+
+class _UNetFunction(torch.autograd.Function):
+    """Autograd bridge: forward = UNetTrainer.forward_train, backward = UNetTrainer.backward (explicit kernels)."""
+
+    @staticmethod
+    def forward(ctx, unet, x, timesteps, context, *params):
+        eps, tape = unet.trainer().forward_train(x.detach(), timesteps, context.detach())
+        ctx.unet, ctx.tape, ctx.params = unet, tape, params
+        ctx.need_dcontext = context.requires_grad
+        return eps
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, d_eps):
+        sink, dctx = ctx.unet.trainer().backward(ctx.tape, d_eps, need_dcontext=ctx.need_dcontext)
+        ctx.tape = None
+        grads = tuple(sink.grads.get(p) for p in ctx.params)
+        return (None, None, None, dctx) + grads

@@ -80,7 +80,7 @@ class UNetTrainer:
     def _ensure(self):
         u = self.unet
         pk = u._ensure_packed()
-        if self._dpk is not None and self._key == u._packed_key:
+        if self._dpk is not None and self._key == u._pack_generation:
             return pk, self._dpk
         d: Dict[nn.Parameter, torch.Tensor] = {}
 
@@ -126,7 +126,7 @@ class UNetTrainer:
         biggest = max(biggest, 128 * ops._pad64(ci), u.model_channels * 128)
         if self._scratch is None or self._scratch.numel() < biggest:
             self._scratch = torch.empty(biggest, dtype=torch.float32, device=w.device)
-        self._dpk, self._key = d, u._packed_key
+        self._dpk, self._key = d, u._pack_generation
         return pk, d
 
     # ------------------------------------------------------------------------------------------
@@ -155,6 +155,12 @@ class UNetTrainer:
         return ops.groupnorm_stats(dy, st)
 
     def _bias_grad(self, sink, param, dy, sums=None):
+        if sums is None and dy.shape[-1] > 2048:       # cs_groupnorm_stats handles <= 2048 channels per call
+            g = sink.grad(param)
+            for c0 in range(0, dy.shape[-1], 2048):
+                c1 = min(dy.shape[-1], c0 + 2048)
+                ops_bwd.batch_reduce(self._colsums(dy[..., c0:c1]), 0, g[c0:c1])
+            return None
         sums = self._colsums(dy) if sums is None else sums
         ops_bwd.batch_reduce(sums, 0, sink.grad(param))
         return sums
@@ -288,9 +294,14 @@ class UNetTrainer:
     # ------------------------------------------------------------------------------------------
     # backward
     # ------------------------------------------------------------------------------------------
-    def backward(self, tape: dict, d_eps: torch.Tensor, sink: Optional[GradSink] = None, need_dcontext: bool = True):
+    def backward(self, tape: dict, d_eps: torch.Tensor, sink: Optional[GradSink] = None, need_dcontext: bool = True,
+                 on_block_done=None):
         """d_eps: gradient wrt the fp32 NCDHW output of forward_train.  Accumulates every parameter gradient into `sink`
-        (created if None) and returns (sink, d_context (B, 1, context_dim) fp32 or None)."""
+        (created if None) and returns (sink, d_context (B, 1, context_dim) fp32 or None).
+
+        Layers are visited in exactly the reverse of `unet.parameters()` order; `on_block_done(p)` is called after each
+        layer with its first parameter p: the gradients of p and of every parameter after it are final at that point
+        (what a data-parallel caller needs to start all-reducing them while the rest of the backward runs)."""
         u = self.unet
         pk, dpk = self._ensure()
         sink = sink or GradSink()
@@ -299,6 +310,7 @@ class UNetTrainer:
         dev = d_eps.device
         d_emb_vecs = torch.zeros(tape["emb_vecs_shape"], dtype=torch.float32, device=dev)
         d_ctx = torch.zeros_like(tape["ctx"])
+        se = F.silu(tape["emb"])
 
         # --- out head: conv3x3x3 224 -> 3 (im2col of d_eps on both sides), GroupNorm + SiLU -----
         h, a = tape["head_in"], tape["head_a"]
@@ -314,11 +326,13 @@ class UNetTrainer:
         dh, _ = ops_bwd.groupnorm_bwd(h.t, h.stat, *pk["out_gn"], da, eps=u.out[0].eps, act=ops.ACT_SILU,
                                       dgamma=sink.grad(u.out[0].weight), dbeta=sink.grad(u.out[0].bias))
         _acc(h, dh)
+        if on_block_done is not None:
+            on_block_done(u.out[0].weight)
 
         for rec in reversed(tape["records"]):
             kind = rec["kind"]
             if kind == "res":
-                self._res_bwd(rec, sink, dpk, d_emb_vecs)
+                self._res_bwd(rec, sink, dpk, d_emb_vecs, se)
             elif kind == "st":
                 self._st_bwd(rec, sink, dpk, tape["ctx"], d_ctx)
             elif kind == "up":
@@ -342,20 +356,12 @@ class UNetTrainer:
                 sink.grad(conv.weight).add_(g.reshape(conv.weight.shape))
                 self._bias_grad(sink, conv.bias, dy)
             rec["out"].grad = None
+            if on_block_done is not None:
+                on_block_done(next(rec["layer"].parameters()))
 
-        # --- emb_layers / time_embed ------------------------------------------------------------
+        # --- time_embed (the emb_layers weights were handled inside their ResBlocks) --------------
         emb, h1, t_emb = tape["emb"], tape["h1"], tape["t_emb"]
-        se, s1 = F.silu(emb), F.silu(h1)
-        off = 0
-        for block in u._blocks():
-            for layer in block:
-                if isinstance(layer, ResBlock):
-                    n = layer.out_channels
-                    lin = layer.emb_layers[1]
-                    dv = d_emb_vecs[:, off:off + n]
-                    ops_bwd.sgemm(dv, se, trans_a=True, out=sink.grad(lin.weight), accumulate=True)
-                    ops_bwd.batch_reduce(dv.contiguous().view(B, n, 1), 0, sink.grad(lin.bias))
-                    off += n
+        s1 = F.silu(h1)
         d_emb = ops_bwd.sgemm(d_emb_vecs, pk["emb_w"], silu_pre=emb)                      # (B, 896), through SiLU(emb)
         te0, te2 = u.time_embed[0], u.time_embed[2]
         ops_bwd.sgemm(d_emb, s1, trans_a=True, out=sink.grad(te2.weight), accumulate=True)
@@ -365,7 +371,7 @@ class UNetTrainer:
         ops_bwd.batch_reduce(d_h1.view(B, -1, 1), 0, sink.grad(te0.bias))
         return sink, (d_ctx[:, None, :] if need_dcontext else None)
 
-    def _res_bwd(self, rec, sink, dpk, d_emb_vecs):
+    def _res_bwd(self, rec, sink, dpk, d_emb_vecs, se):
         layer, pk, x, skip, out = rec["layer"], rec["pk"], rec["x"], rec["skip"], rec["out"]
         dy = out.grad
         B = dy.shape[0]
@@ -380,7 +386,11 @@ class UNetTrainer:
         # h = conv1(a1) + b1 + emb_vec[b]
         hs = self._bias_grad(sink, conv1.bias, dh)
         off, n = rec["emb"]
-        d_emb_vecs[:, off:off + n] = hs[:, :, 0]
+        dvec = hs[:, :, 0].contiguous()
+        d_emb_vecs[:, off:off + n] = dvec
+        lin = layer.emb_layers[1]                  # emb_vec = Linear(SiLU(emb))
+        ops_bwd.sgemm(dvec, se, trans_a=True, out=sink.grad(lin.weight), accumulate=True)
+        ops_bwd.batch_reduce(hs, 0, sink.grad(lin.bias))
         self._wgrad(sink, conv1.weight, rec["a1"], dh)
         da1 = ops_bwd.conv3d_dgrad(dh, dpk[conv1.weight])
         c1 = x.t.shape[-1]

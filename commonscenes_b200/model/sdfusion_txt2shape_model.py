@@ -189,13 +189,29 @@ class SDFusionText2ShapeModel(BaseModel):
         return x_noisy, target, loss, loss_dict
 
     def forward(self):
+        """One training forward (reference :348-365): frozen VQ-VAE encode, random t, p_losses.  `loss_df` carries a grad_fn
+        when the denoiser's parameters (or the conditioning) require grad."""
         self.switch_train()
         with torch.no_grad():
             z = self.vqvae(self.x, forward_no_quant=True, encode_only=True)
-            t = torch.randint(0, self.num_timesteps, (z.shape[0],), device=self.device).long()
-            z_noisy, target, loss, loss_dict = self.p_losses(z, self.rel, t)
+        t = torch.randint(0, self.num_timesteps, (z.shape[0],), device=self.device).long()
+        z_noisy, target, loss, loss_dict = self.p_losses(z, self.rel, t)
         self.loss_df = loss
         self.loss_dict = loss_dict
+
+    def backward(self, retain_graph=False):
+        """reference :568-580 (loss-dict reduction across ranks is the caller's `reduce_loss_dict`; values are unchanged
+        on a single process)."""
+        self.update_loss()
+        self.loss.backward(retain_graph=retain_graph)
+
+    def optimize_parameters(self, total_steps=0):
+        """reference :591-600"""
+        self.set_requires_grad([self.df], requires_grad=True)
+        self.forward()
+        self.optimizer.zero_grad()
+        self.backward()
+        self.optimizer.step()
 
     def update_loss(self):
         self.loss = self.loss_df

@@ -1,0 +1,128 @@
+"""Native training step of the shape-branch denoiser (SURVEY.md §8 a10-a11, §8e "training partition").
+
+What the reference does per iteration (train_3dfront.py:345-418 with VAEGAN_V2FULL.py:642-650):
+    z = VQVAE.encode(sdf) (frozen) ; t ~ U[0, T) ; x_t = q_sample(z, t, eps) ; loss = 100 * mse(UNet(x_t, t, c), eps)
+    loss.backward() ; clip_grad_norm_(df_module.parameters(), 5.0) ; AdamW.step()
+and, under DistributedDataParallel, an all-reduce (mean) of the gradients across ranks.
+
+`DenoiserTrainStep` is that iteration on the B200 kernels without autograd or DDP wrappers:
+  * all trainable parameters of the denoiser are re-homed into ONE flat fp32 buffer (the nn.Parameters become views, so
+    state_dict()/load_state_dict() and the reference's checkpoint format are unchanged), with matching flat buffers for
+    the gradient and the AdamW moments;
+  * forward_train / backward are the explicit kernels of unet_train.py, writing gradients straight into the flat buffer;
+  * multi-GPU: one NCCL all-reduce per gradient bucket on a side stream, issued as soon as the backward has passed the
+    bucket's blocks (buckets follow the UNet's block order, i.e. the reverse of the backward), then ONE cs_sumsq + ONE
+    cs_adamw launch over the flat buffers (clip factor computed on the device, no host sync).
+The conditioning gradient d_c is returned so the caller can continue into rel_mlp / GCN-E2.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from . import ops, ops_bwd
+from .model.networks.diffusion_networks.unet_train import GradSink
+
+
+class DenoiserTrainStep:
+    def __init__(self, diff_model, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.01,
+                 max_grad_norm: float = 5.0, loss_scale: float = 100.0, group: Optional[dist.ProcessGroup] = None,
+                 bucket_mb: int = 256):
+        """diff_model: SDFusionText2ShapeModel mirror (uses .df.diffusion_net, the schedule tables and q_sample).
+        Defaults follow the reference: AdamW lr 1e-4 (VAEGAN_V2FULL.py:642-650; torch's default betas/eps/decay), clip 5.0
+        (train_3dfront.py:399), total loss weight 100 on loss_df (train_3dfront.py:387)."""
+        self.model = diff_model
+        self.unet = diff_model.df.diffusion_net
+        self.trainer = self.unet.trainer()
+        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        self.max_grad_norm, self.loss_scale = max_grad_norm, loss_scale
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.step_count = 0
+        params = [p for p in self.unet.parameters() if p.requires_grad]
+        dev = params[0].device
+        sizes = [(p.numel() + 3) // 4 * 4 for p in params]          # keep every view 16-byte aligned
+        total = sum(sizes)
+        self.flat_p = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_m = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_v = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.views: Dict[nn.Parameter, torch.Tensor] = {}
+        self.offsets: Dict[nn.Parameter, int] = {}
+        off = 0
+        with torch.no_grad():
+            for p, n in zip(params, sizes):
+                v = self.flat_p[off:off + p.numel()].view(p.shape)
+                v.copy_(p.data)
+                p.data = v
+                self.views[p] = self.flat_g[off:off + p.numel()].view(p.shape)
+                self.offsets[p] = off
+                off += n
+        self.params = params
+        self.sumsq = torch.zeros((), dtype=torch.float32, device=dev)
+        self.loss = torch.zeros((), dtype=torch.float32, device=dev)
+        # gradient buckets in parameter order; the backward fills them from the last to the first
+        self.buckets: List[tuple] = []
+        limit = bucket_mb * (1 << 20) // 4
+        start = 0
+        acc = 0
+        for p, n in zip(params, sizes):
+            acc += n
+            if acc >= limit:
+                self.buckets.append((start, start + acc))
+                start, acc = start + acc, 0
+        if acc:
+            self.buckets.append((start, start + acc))
+        self.comm_stream = torch.cuda.Stream(device=dev) if self.world > 1 else None
+        self.unet._packed = None        # parameters moved: rebuild the kernel-layout copies
+
+    # ------------------------------------------------------------------------------------------
+    def _allreduce_ready(self, done_off: int, pending: List[int]):
+        """Launch the all-reduce of every bucket that lies entirely at or after `done_off` (already final)."""
+        while pending and self.buckets[pending[-1]][0] >= done_off:
+            lo, hi = self.buckets[pending.pop()]
+            self.comm_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.comm_stream):
+                dist.all_reduce(self.flat_g[lo:hi], op=dist.ReduceOp.SUM, group=self.group)
+
+    def step(self, z: torch.Tensor, cond: torch.Tensor, t: Optional[torch.Tensor] = None, noise: Optional[torch.Tensor] = None,
+             need_dcond: bool = False):
+        """One optimisation step on this rank's shard.  z: (B, 3, 16, 16, 16) fp32 latents (VQVAE encode_only output),
+        cond: (B, 1, context_dim) fp32.  Returns (loss tensor on the device [mean MSE, unscaled], d_cond or None)."""
+        m = self.model
+        B = z.shape[0]
+        dev = z.device
+        if t is None:
+            t = torch.randint(0, m.num_timesteps, (B,), device=dev).long()
+        if noise is None:
+            noise = torch.randn_like(z)
+        x_t = m.q_sample(z, t, noise)
+        eps, tape = self.trainer.forward_train(x_t, t, cond)
+        self.loss.zero_()
+        d_eps = ops_bwd.mse_loss_grad(eps, noise.float().contiguous(), self.loss, loss_scale=self.loss_scale)
+        self.flat_g.zero_()
+        sink = GradSink(self.views)
+        if self.world > 1:
+            pending = list(range(len(self.buckets)))
+            # the backward visits layers in reverse parameter order: once a layer is done, its gradients and those of every
+            # later parameter are final, so the buckets lying wholly beyond that offset can be reduced while the backward
+            # continues (time_embed comes last: bucket 0 goes out after the backward).
+            _, d_ctx = self.trainer.backward(tape, d_eps, sink=sink, need_dcontext=need_dcond,
+                                             on_block_done=lambda p: self._allreduce_ready(self.offsets[p], pending))
+            self._allreduce_ready(0, pending)
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+        else:
+            _, d_ctx = self.trainer.backward(tape, d_eps, sink=sink, need_dcontext=need_dcond)
+        self.step_count += 1
+        self.sumsq.zero_()
+        ops_bwd.sumsq(self.flat_g, self.sumsq)
+        # gradients were summed over ranks: the mean (DDP semantics) is a scale folded into the optimizer kernel
+        gscale = 1.0 / self.world
+        ops_bwd.adamw_step(self.flat_p, self.flat_g, self.flat_m, self.flat_v, lr=self.lr, betas=self.betas, eps=self.eps,
+                           weight_decay=self.weight_decay, step=self.step_count, sumsq_buf=self.sumsq,
+                           max_norm=self.max_grad_norm, grad_scale=gscale)
+        self.unet._packed = None        # weights changed in place (kernel write: no autograd version bump)
+        return self.loss, d_ctx
