@@ -51,12 +51,13 @@ int sgemm_small_launch(const float*, int, int, const float*, int, int, float*, i
 int mse_loss_grad_launch(const float*, const float*, long long, float, float*, float*, cudaStream_t);
 int sumsq_launch(const float*, long long, float*, cudaStream_t);
 int adamw_launch(float*, const float*, float*, float*, long long, float, float, float, float, float, int, const float*, float,
-                 float, cudaStream_t);
+                 float, const int*, cudaStream_t);
 int unpack_wgrad_launch(const float*, int, int, int, int, float*, cudaStream_t);
 int attention_lse_launch(const void*, const void*, const void*, void*, int, int, int, int, int, int, int, int, int, float, float*,
                          cudaStream_t);
 int attention_bwd_launch(const void*, const void*, const void*, const void*, const void*, const float*, float*, float*, void*,
                          void*, int, int, int, int, int, int, int, int, int, float, cudaStream_t);
+int pack_weight_launch(const float*, int, int, int, int, void*, void*, cudaStream_t);
 void igemm_set_debug(int);
 int cast_bf16_launch(const float*, long long, void*, cudaStream_t);
 int vq_quantize_launch(const float*, int, int, long long, const float*, int, const float*, const float*, int, float*,
@@ -278,11 +279,16 @@ int cs_mse_loss_grad(const float* pred, const float* target, int64_t n, float lo
 }
 int cs_sumsq(const float* g, int64_t n, float* out, cs_stream_t stream) { return cs::sumsq_launch(g, n, out, S(stream)); }
 int cs_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
-             float weight_decay, int32_t step, const float* sumsq, float max_norm, float grad_scale, cs_stream_t stream) {
-  return cs::adamw_launch(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, step, sumsq, max_norm, grad_scale, S(stream));
+             float weight_decay, int32_t step, const float* sumsq, float max_norm, float grad_scale, const int32_t* step_dev,
+             cs_stream_t stream) {
+  return cs::adamw_launch(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, step, sumsq, max_norm, grad_scale, step_dev,
+                          S(stream));
 }
 int cs_unpack_wgrad(const float* dw, int32_t Cout, int32_t taps, int32_t C1, int32_t C2, float* grad, cs_stream_t stream) {
   return cs::unpack_wgrad_launch(dw, Cout, taps, C1, C2, grad, S(stream));
+}
+int cs_pack_weight(const float* w, int32_t Cout, int32_t Cin, int32_t taps, int32_t C1, void* fwd, void* dgrad, cs_stream_t stream) {
+  return cs::pack_weight_launch(w, Cout, Cin, taps, C1, fwd, dgrad, S(stream));
 }
 int cs_attention_lse(const void* q, const void* k, const void* v, void* out, int32_t B, int32_t H, int32_t Nq, int32_t Nk,
                      int32_t Dp, int32_t q_pitch, int32_t kv_pitch, int32_t o_pitch, int32_t d_out, float scale, float* lse,

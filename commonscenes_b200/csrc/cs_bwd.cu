@@ -706,7 +706,12 @@ int sumsq_launch(const float* g, long long n, float* out, cudaStream_t st) {
 
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                              long long n, float lr, float beta1, float beta2, float eps, float wd, float bc1, float bc2_sqrt,
-                             const float* __restrict__ sumsq, float max_norm, float grad_scale) {
+                             const float* __restrict__ sumsq, float max_norm, float grad_scale, const int* __restrict__ step_dev) {
+  if (step_dev) {   // step count kept on the device (CUDA-graph replays): bias corrections computed here
+    const float st = static_cast<float>(*step_dev);
+    bc1 = 1.f - powf(beta1, st);
+    bc2_sqrt = sqrtf(1.f - powf(beta2, st));
+  }
   float clip = grad_scale;
   if (sumsq) {
     const float norm = sqrtf(*sumsq) * grad_scale;
@@ -725,14 +730,16 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
   }
 }
 int adamw_launch(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
-                 float wd, int step, const float* sumsq, float max_norm, float grad_scale, cudaStream_t st) {
+                 float wd, int step, const float* sumsq, float max_norm, float grad_scale, const int* step_dev, cudaStream_t st) {
   if (n <= 0) return CS_OK;
-  if (step < 1) return set_error(CS_ERR_INVALID, "adamw: step counts from 1");
+  if (step < 1 && !step_dev) return set_error(CS_ERR_INVALID, "adamw: step counts from 1");
+  if (step < 1) step = 1;
   const float bc1 = 1.f - powf(beta1, static_cast<float>(step));
   const float bc2 = 1.f - powf(beta2, static_cast<float>(step));
   long long blocks = (n + 255) / 256;
   if (blocks > 16 * num_sms()) blocks = 16 * num_sms();
-  adamw_kernel<<<(int)blocks, 256, 0, st>>>(p, g, m, v, n, lr, beta1, beta2, eps, wd, bc1, sqrtf(bc2), sumsq, max_norm, grad_scale);
+  adamw_kernel<<<(int)blocks, 256, 0, st>>>(p, g, m, v, n, lr, beta1, beta2, eps, wd, bc1, sqrtf(bc2), sumsq, max_norm, grad_scale,
+                                            step_dev);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error(e, "adamw: launch");
   count_launch();
@@ -772,6 +779,75 @@ int unpack_wgrad_launch(const float* dw, int Cout, int taps, int C1, int C2, flo
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error(e, "unpack_wgrad: launch");
   count_launch();
+  return CS_OK;
+}
+
+}  // namespace cs
+
+namespace cs {
+
+// ------------------------------------------------------------------------------------------------
+// Weight packing on the device (runs after every optimizer step in training): fp32 parameter (Cout, Cin, taps) ->
+//   fwd  : bf16 [Cout][taps][pad64(C1) + pad64(C2)]              (what cs_conv3d reads; Cin = C1 + C2)
+//   dgrad: bf16 [Cin][taps, flipped][pad64(Cout)]                 (cs_conv3d weight that maps dY to dX)
+// Pad columns are never written: the destination buffers must be zero-initialised once.
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_fwd_kernel(const float* __restrict__ w, int Cin, int taps, int C1, int C1pad, int ctot,
+                                __nv_bfloat16* __restrict__ out) {
+  extern __shared__ float tile[];   // [64][taps + 1]
+  const int co = blockIdx.y, ci0 = blockIdx.x * 64;
+  const int n = min(64, Cin - ci0);
+  const float* src = w + (static_cast<long long>(co) * Cin + ci0) * taps;
+  for (int i = threadIdx.x; i < n * taps; i += blockDim.x) tile[(i / taps) * (taps + 1) + i % taps] = src[i];
+  __syncthreads();
+  __nv_bfloat16* dst = out + static_cast<long long>(co) * taps * ctot;
+  for (int i = threadIdx.x; i < taps * 64; i += blockDim.x) {
+    const int t = i >> 6, c = i & 63, ci = ci0 + c;
+    if (c < n) dst[static_cast<long long>(t) * ctot + (ci < C1 ? ci : C1pad + (ci - C1))] = __float2bfloat16(tile[c * (taps + 1) + t]);
+  }
+}
+
+__global__ void pack_dgrad_kernel(const float* __restrict__ w, int Cout, int Cin, int taps, int copad,
+                                  __nv_bfloat16* __restrict__ out) {
+  extern __shared__ float tile[];   // [16 co][16 ci * taps + 1]
+  const int co0 = blockIdx.y * 16, ci0 = blockIdx.x * 16;
+  const int nco = min(16, Cout - co0), nci = min(16, Cin - ci0);
+  const int run = nci * taps, pitch = 16 * taps + 1;
+  for (int i = threadIdx.x; i < nco * run; i += blockDim.x) {
+    const int r = i / run, j = i - r * run;
+    tile[r * pitch + j] = w[(static_cast<long long>(co0 + r) * Cin + ci0) * taps + j];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nci * taps * 16; i += blockDim.x) {
+    const int r = i & 15, ct = i >> 4;          // r = co (fastest -> contiguous stores), ct = ci * taps + t
+    const int c = ct / taps, t = ct - c * taps;
+    if (r < nco)
+      out[(static_cast<long long>(ci0 + c) * taps + (taps - 1 - t)) * copad + co0 + r] = __float2bfloat16(tile[r * pitch + ct]);
+  }
+}
+
+int pack_weight_launch(const float* w, int Cout, int Cin, int taps, int C1, void* fwd, void* dgrad, cudaStream_t st) {
+  if (Cout <= 0 || Cin <= 0 || taps <= 0 || C1 <= 0 || C1 > Cin) return set_error(CS_ERR_INVALID, "pack_weight: bad dims");
+  const int C2 = Cin - C1;
+  const int c1p = (C1 + 63) / 64 * 64, c2p = (C2 + 63) / 64 * 64;
+  if (fwd) {
+    const size_t sm = static_cast<size_t>(64) * (taps + 1) * sizeof(float);
+    if (sm > 48 * 1024) return set_error(CS_ERR_UNSUPPORTED, "pack_weight: too many taps");
+    pack_fwd_kernel<<<dim3((Cin + 63) / 64, Cout), 256, sm, st>>>(w, Cin, taps, C1, c1p, c1p + c2p,
+                                                                 reinterpret_cast<__nv_bfloat16*>(fwd));
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error(e, "pack_weight: fwd launch");
+    count_launch();
+  }
+  if (dgrad) {
+    const size_t sm = static_cast<size_t>(16) * (16 * taps + 1) * sizeof(float);
+    if (sm > 48 * 1024) return set_error(CS_ERR_UNSUPPORTED, "pack_weight: too many taps");
+    pack_dgrad_kernel<<<dim3((Cin + 15) / 16, (Cout + 15) / 16), 256, sm, st>>>(w, Cout, Cin, taps, (Cout + 63) / 64 * 64,
+                                                                               reinterpret_cast<__nv_bfloat16*>(dgrad));
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error(e, "pack_weight: dgrad launch");
+    count_launch();
+  }
   return CS_OK;
 }
 

@@ -97,7 +97,16 @@ def pack_conv_weight(w: torch.Tensor, split=None) -> torch.Tensor:
     """(Cout, Cin, kd, kh, kw) fp32 -> the K-major bf16 layout cs_conv3d reads (see _pad_k).  `split` = (C1, C2) when the
     conv consumes the channel concatenation of two tensors."""
     co, ci = w.shape[0], w.shape[1]
-    return _pad_k(w.detach().reshape(co, ci, -1).permute(0, 2, 1), split)
+    wd = w.detach()
+    if wd.is_cuda and wd.dtype == torch.float32 and wd.is_contiguous():      # device kernel (training re-packs every step)
+        taps = wd.numel() // (co * ci)
+        parts = [ci] if split is None else [int(c) for c in split]
+        if sum(parts) != ci:
+            raise _lib.CsError(f"pack: channel split {parts} does not sum to {ci}")
+        out = torch.zeros((co, taps, sum(_pad64(c) for c in parts)), dtype=torch.bfloat16, device=w.device)
+        check(_lib.load().cs_pack_weight(wd.data_ptr(), co, ci, taps, parts[0], out.data_ptr(), None, _stream()), "cs_pack_weight")
+        return out
+    return _pad_k(wd.reshape(co, ci, -1).permute(0, 2, 1), split)
 
 
 def pack_geglu_weight(w: torch.Tensor, b: torch.Tensor):
@@ -124,6 +133,8 @@ def pack_patch_weight(w: torch.Tensor):
 
 def pack_linear_weight(w: torch.Tensor) -> torch.Tensor:
     """(out, in) fp32 -> (out, 1, pad64(in)) bf16."""
+    if w.is_cuda and w.dtype == torch.float32 and w.is_contiguous():
+        return pack_conv_weight(w)
     return _pad_k(w.detach().reshape(w.shape[0], 1, w.shape[1]))
 
 

@@ -23,7 +23,13 @@ def pack_dgrad_weight(w: torch.Tensor) -> torch.Tensor:
     """(Cout, Cin, kd, kh, kw) fp32 -> packed bf16 (Cin, taps, pad64(Cout)) with the filter flipped: the weight with which
     cs_conv3d maps dY (Cout channels) to dX (Cin channels) for a stride-1 convolution."""
     co, ci = w.shape[0], w.shape[1]
-    wt = w.detach().reshape(co, ci, -1).flip(2).permute(1, 2, 0)     # (Cin, taps flipped, Cout)
+    wd = w.detach()
+    if wd.is_cuda and wd.dtype == torch.float32 and wd.is_contiguous():
+        taps = wd.numel() // (co * ci)
+        out = torch.zeros((ci, taps, _pad64(co)), dtype=torch.bfloat16, device=w.device)
+        check(_lib.load().cs_pack_weight(wd.data_ptr(), co, ci, taps, ci, None, out.data_ptr(), _stream()), "cs_pack_weight")
+        return out
+    wt = wd.reshape(co, ci, -1).flip(2).permute(1, 2, 0)     # (Cin, taps flipped, Cout)
     return _pad_k(wt)
 
 
@@ -239,14 +245,17 @@ def sumsq(g: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
 
 
 def adamw_step(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor, *, lr: float, betas=(0.9, 0.999),
-               eps: float = 1e-8, weight_decay: float = 0.01, step: int, sumsq_buf: Optional[torch.Tensor] = None,
-               max_norm: float = 0.0, grad_scale: float = 1.0) -> None:
-    """In-place torch.optim.AdamW step over flat fp32 buffers (same update rule; clip factor from sumsq_buf if given)."""
+               eps: float = 1e-8, weight_decay: float = 0.01, step: int = 0, sumsq_buf: Optional[torch.Tensor] = None,
+               max_norm: float = 0.0, grad_scale: float = 1.0, step_dev: Optional[torch.Tensor] = None) -> None:
+    """In-place torch.optim.AdamW step over flat fp32 buffers (same update rule; clip factor from sumsq_buf if given).
+    `step_dev`: int32 device scalar holding the step number (overrides `step`; lets a CUDA graph be replayed)."""
+    if step_dev is not None and (step_dev.dtype != torch.int32 or not step_dev.is_cuda):
+        raise _lib.CsError("adamw_step: step_dev must be an int32 CUDA scalar")
     for t in (p, g, m, v):
         if t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != p.numel():
             raise _lib.CsError("adamw_step: p, g, m, v must be contiguous fp32 of equal size")
     check(_lib.load().cs_adamw(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, betas[0], betas[1], eps,
-                               weight_decay, step, _ptr(sumsq_buf), max_norm, grad_scale, _stream()), "cs_adamw")
+                               weight_decay, step, _ptr(sumsq_buf), max_norm, grad_scale, _ptr(step_dev), _stream()), "cs_adamw")
 
 
 # ----------------------------------------------------------------------------------------------

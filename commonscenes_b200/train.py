@@ -62,6 +62,8 @@ class DenoiserTrainStep:
                 self.offsets[p] = off
                 off += n
         self.params = params
+        self.step_dev = torch.zeros((), dtype=torch.int32, device=dev)     # device copy of step_count (graph replays)
+        self.graph = None
         self.sumsq = torch.zeros((), dtype=torch.float32, device=dev)
         self.loss = torch.zeros((), dtype=torch.float32, device=dev)
         # gradient buckets in parameter order; the backward fills them from the last to the first
@@ -117,12 +119,63 @@ class DenoiserTrainStep:
         else:
             _, d_ctx = self.trainer.backward(tape, d_eps, sink=sink, need_dcontext=need_dcond)
         self.step_count += 1
+        self.step_dev.add_(1)
         self.sumsq.zero_()
         ops_bwd.sumsq(self.flat_g, self.sumsq)
         # gradients were summed over ranks: the mean (DDP semantics) is a scale folded into the optimizer kernel
         gscale = 1.0 / self.world
         ops_bwd.adamw_step(self.flat_p, self.flat_g, self.flat_m, self.flat_v, lr=self.lr, betas=self.betas, eps=self.eps,
-                           weight_decay=self.weight_decay, step=self.step_count, sumsq_buf=self.sumsq,
-                           max_norm=self.max_grad_norm, grad_scale=gscale)
+                           weight_decay=self.weight_decay, sumsq_buf=self.sumsq, max_norm=self.max_grad_norm, grad_scale=gscale,
+                           step_dev=self.step_dev)
         self.unet._packed = None        # weights changed in place (kernel write: no autograd version bump)
         return self.loss, d_ctx
+
+    # ------------------------------------------------------------------------------------------
+    def capture(self, batch: int, context_dim: int, need_dcond: bool = False, warmup: int = 2) -> None:
+        """Capture the whole iteration (weight re-pack, forward, backward, all-reduce, clip, AdamW) into ONE CUDA graph for
+        a fixed batch size: ~1200 launches per step are then replayed without host work.  The warm-up iterations needed
+        before capture run on zeros and are rolled back (parameters, moments and step counter are restored)."""
+        dev = self.flat_p.device
+        zs = self.model.z_shape if hasattr(self.model, "z_shape") else (3, 16, 16, 16)
+        self._gz = torch.zeros((batch,) + tuple(zs), dtype=torch.float32, device=dev)
+        self._gc = torch.zeros((batch, 1, context_dim), dtype=torch.float32, device=dev)
+        self._gt = torch.zeros((batch,), dtype=torch.int64, device=dev)
+        self._gn = torch.zeros_like(self._gz)
+        saved = (self.flat_p.clone(), self.flat_m.clone(), self.flat_v.clone(), self.step_dev.clone(), self.step_count)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.step(self._gz, self._gc, t=self._gt, noise=self._gn, need_dcond=need_dcond)
+        torch.cuda.current_stream().wait_stream(side)
+
+        def restore():
+            self.flat_p.copy_(saved[0]); self.flat_m.copy_(saved[1]); self.flat_v.copy_(saved[2]); self.step_dev.copy_(saved[3])
+            self.step_count = saved[4]
+        restore()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._gout = self.step(self._gz, self._gc, t=self._gt, noise=self._gn, need_dcond=need_dcond)
+        restore()      # capture does not execute, but step() bumped the host-side counter
+        self.unet._packed = None
+        self.graph = g
+
+    def step_graphed(self, z: torch.Tensor, cond: torch.Tensor, t: Optional[torch.Tensor] = None,
+                     noise: Optional[torch.Tensor] = None):
+        """step() through the captured graph (call capture() first; same batch size).  Returns (loss, d_cond) tensors that
+        are overwritten by the next replay."""
+        if self.graph is None:
+            raise RuntimeError("DenoiserTrainStep.step_graphed: call capture() first")
+        self._gz.copy_(z)
+        self._gc.copy_(cond)
+        if t is None:
+            torch.randint(0, self.model.num_timesteps, self._gt.shape, device=self._gt.device, out=self._gt)
+        else:
+            self._gt.copy_(t)
+        if noise is None:
+            self._gn.normal_()
+        else:
+            self._gn.copy_(noise)
+        self.graph.replay()
+        self.step_count += 1
+        return self._gout

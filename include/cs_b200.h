@@ -135,9 +135,17 @@ int cs_mse_loss_grad(const float* pred, const float* target, int64_t n, float lo
 /* *out += sum g^2 (clip_grad_norm_, train_3dfront.py:399) */
 int cs_sumsq(const float* g, int64_t n, float* out, cs_stream_t stream);
 /* torch.optim.AdamW step (VAEGAN_V2FULL.py:642-650) over a flat fp32 buffer; gradient = g * grad_scale, additionally
- * clipped to max_norm when `sumsq` (device scalar from cs_sumsq over the same g) is not NULL */
+ * clipped to max_norm when `sumsq` (device scalar from cs_sumsq over the same g) is not NULL.  The step number (from 1)
+ * is `step`, or *step_dev when step_dev is not NULL (a device counter, so that a captured CUDA graph can be replayed) */
 int cs_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
-             float weight_decay, int32_t step, const float* sumsq, float max_norm, float grad_scale, cs_stream_t stream);
+             float weight_decay, int32_t step, const float* sumsq, float max_norm, float grad_scale, const int32_t* step_dev,
+             cs_stream_t stream);
+/* device-side weight packing (after every optimizer step): w fp32 (Cout, Cin, taps) ->
+ *   fwd   bf16 [Cout][taps][pad64(C1) + pad64(Cin - C1)]   the layout cs_conv3d reads (NULL = skip)
+ *   dgrad bf16 [Cin][taps flipped][pad64(Cout)]             the cs_conv3d weight mapping dY to dX (NULL = skip)
+ * pad columns are not written: zero the destinations once */
+int cs_pack_weight(const float* w, int32_t Cout, int32_t Cin, int32_t taps, int32_t C1, void* fwd, void* dgrad,
+                   cs_stream_t stream);
 /* cs_attention that also writes the base-2 log-sum-exp of every score row (fp32 [B][H][Nq]) for cs_attention_bwd */
 int cs_attention_lse(const void* q, const void* k, const void* v, void* out, int32_t B, int32_t H, int32_t Nq, int32_t Nk,
                      int32_t Dp, int32_t q_pitch, int32_t kv_pitch, int32_t o_pitch, int32_t d_out, float scale, float* lse,

@@ -187,3 +187,39 @@ def test_unet_backward_full_config_vs_oracle_on_device():
     print("worst tensors:", [(f"{r:.3e}", k) for r, k in worst[:6]])
     print(f"full config: whole-gradient rel-L2 {(num / den) ** 0.5:.3e}, cosine {dot / (den * gg) ** 0.5:.6f}")
     assert (num / den) ** 0.5 < 3e-2 and dot / (den * gg) ** 0.5 > 0.999
+
+
+def test_graphed_train_step_matches_eager():
+    from commonscenes_b200.model.sdfusion_txt2shape_model import SDFusionText2ShapeModel, diffusion_schedule
+    from commonscenes_b200.train import DenoiserTrainStep
+    cfg = D.UNET_TINY
+
+    class Stub:
+        q_sample = SDFusionText2ShapeModel.q_sample
+        z_shape = (3, 8, 8, 8)
+
+        def __init__(self, df):
+            self.df, self.num_timesteps, self.device = df, 1000, "cuda"
+            for k, v in diffusion_schedule(1000, 0.00085, 0.012).items():
+                setattr(self, k, v.cuda())
+
+    g = torch.Generator().manual_seed(12)
+    B = 4
+    z = torch.randn(B, 3, 8, 8, 8, generator=g).cuda()
+    ctx = torch.randn(B, 1, cfg["context_dim"], generator=g).cuda()
+    t = torch.tensor([10, 999, 500, 250]).cuda()
+    noise = torch.randn(B, 3, 8, 8, 8, generator=g).cuda()
+    ma, mb = Stub(_build(cfg, 61)), Stub(_build(cfg, 61))
+    sa, sb = DenoiserTrainStep(ma), DenoiserTrainStep(mb)
+    p0 = sa.flat_p.clone()
+    sb.capture(B, cfg["context_dim"], need_dcond=True)
+    assert torch.equal(sb.flat_p, p0) and sb.step_count == 0      # warm-up iterations were rolled back
+    for _ in range(3):
+        la, da = sa.step(z, ctx, t=t, noise=noise, need_dcond=True)
+        lb, db = sb.step_graphed(z, ctx, t=t, noise=noise)
+        assert abs(la.item() - lb.item()) / la.item() < 1e-2
+    ua, ub = sa.flat_p - p0, sb.flat_p - p0
+    rel = float((ua - ub).norm() / ua.norm())
+    print(f"graphed vs eager parameter update rel-L2 after 3 steps: {rel:.3e}")
+    assert rel < 0.25 and int(sb.step_dev.item()) == 3
+    assert float((da - db).norm() / da.norm()) < 0.1

@@ -23,6 +23,11 @@ if "--debug" in sys.argv:
     _lib.load().cs_debug_set(int(sys.argv[sys.argv.index("--debug") + 1]))
 first = int(sys.argv[sys.argv.index("--from") + 1]) if "--from" in sys.argv else 0
 reps = 1 if only is not None else 5
+mode = "wgrad" if "--wgrad" in sys.argv else ("dgrad" if "--dgrad" in sys.argv else "fwd")
+if "--b" in sys.argv:
+    B = int(sys.argv[sys.argv.index("--b") + 1])
+if mode != "fwd":
+    from commonscenes_b200 import ops_bwd
 tot_ms = tot_fl = 0.0
 for i, (ci, co, (D, H, W), k, st, cnt) in enumerate(SHAPES):
     if (only is not None and i != only) or i < first:
@@ -31,13 +36,24 @@ for i, (ci, co, (D, H, W), k, st, cnt) in enumerate(SHAPES):
     w = ops.pack_conv_weight(torch.randn(co, ci, k, k, k, device="cuda") / (ci * k ** 3) ** 0.5)
     b = torch.randn(co, device="cuda")
     pad = (k // 2,) * 3
+    y = ops.conv3d(x, w, ksize=(k, k, k), stride=st, pad=pad, bias=b)
+    if mode == "wgrad":
+        dw = torch.zeros(co, k ** 3, ops._pad64(ci), device="cuda")
+        run = lambda: ops_bwd.conv3d_wgrad(x, y, dw, ksize=(k, k, k), stride=st, pad=pad)
+    elif mode == "dgrad":
+        if st != (1, 1, 1):
+            continue
+        wd = ops_bwd.pack_dgrad_weight(torch.randn(co, ci, k, k, k, device="cuda") / (ci * k ** 3) ** 0.5)
+        run = lambda: ops_bwd.conv3d_dgrad(y, wd, ksize=(k, k, k), pad=pad)
+    else:
+        run = lambda: ops.conv3d(x, w, ksize=(k, k, k), stride=st, pad=pad, bias=b)
     for _ in range(2):
-        y = ops.conv3d(x, w, ksize=(k, k, k), stride=st, pad=pad, bias=b)
+        run()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(reps):
-        y = ops.conv3d(x, w, ksize=(k, k, k), stride=st, pad=pad, bias=b)
+        run()
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     fl = 2.0 * y.shape[0] * y.shape[1] * y.shape[2] * y.shape[3] * co * ci * k ** 3

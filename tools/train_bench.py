@@ -46,8 +46,14 @@ def timed(fn, reps=3):
 for _ in range(2):
     loss, _ = step.step(z, ctx)
 print("loss after warm-up:", loss.item())
-ms_step, _ = timed(lambda: step.step(z, ctx), reps=5)
-print(f"train step B={B}: {ms_step:.1f} ms -> {1000 / ms_step:.2f} steps/s, {B * 1000 / ms_step:.1f} objects/s "
+ms_eager, _ = timed(lambda: step.step(z, ctx), reps=3)
+print(f"eager train step B={B}: {ms_eager:.1f} ms")
+step.capture(B, 1280)
+for _ in range(2):
+    loss, _ = step.step_graphed(z, ctx)
+ms_step, _ = timed(lambda: step.step_graphed(z, ctx), reps=5)
+print("loss (graphed):", loss.item())
+print(f"graphed train step B={B}: {ms_step:.1f} ms -> {1000 / ms_step:.2f} steps/s, {B * 1000 / ms_step:.1f} objects/s "
       f"({3 * B * 0.5576 / ms_step:.1f} TFLOP/s algorithmic, fwd+bwd = 3 x 557.6 GF/sample)")
 tr = step.trainer
 t = torch.randint(0, 1000, (B,), device="cuda")
@@ -69,6 +75,6 @@ print(f"memory: allocated {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB pe
 if "--profile" in sys.argv:
     from torch.profiler import profile, ProfilerActivity
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
-        step.step(z, ctx)
+        step.step_graphed(z, ctx)
         torch.cuda.synchronize()
-    print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25, max_name_column_width=60))
+    print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=60))
