@@ -718,15 +718,28 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
     clip *= fminf(1.f, max_norm / (norm + 1e-6f));
   }
   const float step = lr / bc1;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+  const float decay = 1.f - lr * wd;
+  const long long n4 = n >> 2;
+  float4* p4 = reinterpret_cast<float4*>(p);
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  float4* m4 = reinterpret_cast<float4*>(m);
+  float4* v4 = reinterpret_cast<float4*>(v);
+  auto upd = [&](float& pi, float gi, float& mi, float& vi) {
+    gi *= clip;
+    mi = beta1 * mi + (1.f - beta1) * gi;
+    vi = beta2 * vi + (1.f - beta2) * gi * gi;
+    pi = pi * decay - step * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+  };
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const float gi = g[i] * clip;
-    const float mi = beta1 * m[i] + (1.f - beta1) * gi;
-    const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
-    m[i] = mi;
-    v[i] = vi;
-    const float denom = sqrtf(vi) / bc2_sqrt + eps;
-    p[i] = p[i] * (1.f - lr * wd) - step * (mi / denom);
+    float4 pp = p4[i], mm = m4[i], vv = v4[i];
+    const float4 gg = g4[i];
+    upd(pp.x, gg.x, mm.x, vv.x); upd(pp.y, gg.y, mm.y, vv.y); upd(pp.z, gg.z, mm.z, vv.z); upd(pp.w, gg.w, mm.w, vv.w);
+    p4[i] = pp; m4[i] = mm; v4[i] = vv;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const long long i = (n4 << 2) + threadIdx.x;
+    upd(p[i], g[i], m[i], v[i]);
   }
 }
 int adamw_launch(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
@@ -734,10 +747,14 @@ int adamw_launch(float* p, const float* g, float* m, float* v, long long n, floa
   if (n <= 0) return CS_OK;
   if (step < 1 && !step_dev) return set_error(CS_ERR_INVALID, "adamw: step counts from 1");
   if (step < 1) step = 1;
+  if (reinterpret_cast<uintptr_t>(p) % 16 || reinterpret_cast<uintptr_t>(g) % 16 || reinterpret_cast<uintptr_t>(m) % 16 ||
+      reinterpret_cast<uintptr_t>(v) % 16)
+    return set_error(CS_ERR_INVALID, "adamw: buffers must be 16-byte aligned");
   const float bc1 = 1.f - powf(beta1, static_cast<float>(step));
   const float bc2 = 1.f - powf(beta2, static_cast<float>(step));
-  long long blocks = (n + 255) / 256;
+  long long blocks = (n / 4 + 255) / 256;
   if (blocks > 16 * num_sms()) blocks = 16 * num_sms();
+  if (blocks < 1) blocks = 1;
   adamw_kernel<<<(int)blocks, 256, 0, st>>>(p, g, m, v, n, lr, beta1, beta2, eps, wd, bc1, sqrtf(bc2), sumsq, max_norm, grad_scale,
                                             step_dev);
   cudaError_t e = cudaGetLastError();

@@ -16,7 +16,8 @@
 // 148 SMs, and items accumulate into the fp32 packed gradient [Cout][taps][pad64(C1)+pad64(C2)] with coalesced
 // red.global.add.f32 (lane = ci, which is the contiguous axis of the packed layout).
 //
-// Roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = epilogue.
+// Roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-9 = epilogue (two warps per
+// TMEM lane quarter, each draining alternate 32-column chunks: the accumulators are single-buffered, so the epilogue is exposed).
 #include "cs_common.cuh"
 #include "cs_host.h"
 #include "cs_wgrad.cuh"
@@ -61,7 +62,7 @@ __device__ __forceinline__ WgItem wg_decode(const WgradParams& p, int item) {
   return it;
 }
 
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 wgrad_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ CUtensorMap tmX2,
              const __grid_constant__ CUtensorMap tmDY, const WgradParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -79,7 +80,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ C
       mbar_init(&bars.empty[s], 1);
     }
     mbar_init(&bars.acc_full, 1);
-    mbar_init(&bars.acc_empty, 4);
+    mbar_init(&bars.acc_empty, 8);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -162,6 +163,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ C
   } else {
     // epilogue: warp q drains TMEM lanes [32q, 32q + 32) = input channels ci0 + 128 * acc + 32q + lane
     const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
     uint32_t acc_phase = 0;
     const int ctot = p.C1pad + p.C2pad;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
@@ -177,7 +179,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ C
           const int ci = it.ci0 + acc * 128 + quarter * 32 + lane;
           const bool ci_ok = ci < cpad;
           float* base = p.dw + static_cast<long long>(it.tap) * ctot + coff + ci;
-          for (int c0 = 0; c0 < p.BN; c0 += 32) {
+          for (int c0 = half * 32; c0 < p.BN; c0 += 64) {
             uint32_t r[32];
             tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * 256 + c0), r);
             tmem_ld_wait();
@@ -250,10 +252,19 @@ int wgrad_launch(const WgradArgs& a, cudaStream_t stream) {
   p.m_chunks = (p.B / p.bb) * (p.Do / p.bd) * (p.Ho / p.bh) * (p.Wo / p.bw);
   const int units = p.ntaps * p.n_pairs * p.n_tiles;
   const int sms = num_sms();
-  int nsplit = (4 * sms + units - 1) / units;
+  // Split of the voxel axis: pick the number of splits whose item count fills whole rounds of the persistent CTAs best
+  // (items / (ceil(items / SMs) * SMs)), keeping >= 16 K chunks per item and preferring fewer, longer items on ties
+  // (each item pays one exposed epilogue).
   const int max_split = p.m_chunks / 16 > 0 ? p.m_chunks / 16 : 1;
-  if (nsplit > max_split) nsplit = max_split;
-  if (nsplit < 1) nsplit = 1;
+  int nsplit = 1;
+  double best = 0.0;
+  for (int ns = 1; ns <= max_split && ns <= 64; ++ns) {
+    const long long items = static_cast<long long>(units) * ns;
+    const long long rounds = (items + sms - 1) / sms;
+    double eff = static_cast<double>(items) / static_cast<double>(rounds * sms);
+    eff *= 1.0 - 0.02 * static_cast<double>(rounds > 8 ? 8 : rounds) / (static_cast<double>(p.m_chunks) / ns / 64.0 + 1.0);  // epilogue share
+    if (eff > best + 1e-3) { best = eff; nsplit = ns; }
+  }
   p.nsplit = nsplit;
   p.n_items = units * nsplit;
   p.dw = a.dw;
@@ -291,7 +302,7 @@ int wgrad_launch(const WgradArgs& a, cudaStream_t stream) {
     attr_set = true;
   }
   const int grid = p.n_items < sms ? p.n_items : sms;
-  wgrad_kernel<<<grid, 192, smem_bytes, stream>>>(tmX1, tmX2, tmDY, p);
+  wgrad_kernel<<<grid, 320, smem_bytes, stream>>>(tmX1, tmX2, tmDY, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error(e, "wgrad: launch");
   count_launch();

@@ -137,6 +137,10 @@ class UNetTrainer:
         c2 = 0 if x2 is None else x2.shape[-1]
         co, taps = dy.shape[-1], ksize[0] * ksize[1] * ksize[2]
         cp = ops._pad64(c1) + ops._pad64(c2)
+        if param is not None and taps == 1 and x2 is None and cp == c1:
+            # a linear layer without channel padding: the packed gradient layout IS the parameter's (out, in) layout
+            ops_bwd.conv3d_wgrad(x, dy, sink.grad(param).view(co, 1, c1), ksize=ksize, stride=stride, pad=pad)
+            return None
         dw = self._scratch[:co * taps * cp].view(co, taps, cp)
         dw.zero_()
         ops_bwd.conv3d_wgrad(x, dy, dw, ksize=ksize, stride=stride, pad=pad, x2=x2)
