@@ -99,6 +99,11 @@ SIGNATURES = {
     "cs_gcn_scatter_mean": (_i32, [_vp, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _vp, _vp]),
     "cs_batchnorm_relu": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _f32, _f32, _i32, _vp, _i32, _vp]),
     "cs_add_rows": (_i32, [_vp, _i32, _vp, _i32, _i32, _i32, _vp, _i32, _vp]),
+    "cs_batchnorm_relu_bwd": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _f32, _i32, _vp, _i32, _vp, _i32, _vp, _i32,
+                                     _vp, _vp, _vp]),
+    "cs_gcn_scatter_mean_bwd": (_i32, [_vp, _i32, _vp, _i32, _i32, _vp, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "cs_gcn_gather_triples_bwd": (_i32, [_vp, _i32, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _vp]),
+    "cs_embedding_bwd": (_i32, [_vp, _i32, _i32, _i32, _vp, _i32, _i32, _vp, _vp]),
     "cs_tap_gather": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "cs_cast_f32_to_bf16": (_i32, [_vp, _i64, _vp, _vp]),
     "cs_debug_set": (None, [_i32]),

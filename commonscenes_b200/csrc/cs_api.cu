@@ -36,6 +36,12 @@ int scatter_mean_launch(const float*, int, int, int, int, const long long*, int,
 int batchnorm_relu_launch(const float*, int, int, int, const float*, const float*, float*, float*, int, float, float, int,
                           float*, int, cudaStream_t);
 int add_rows_launch(const float*, int, const float*, int, int, int, float*, int, cudaStream_t);
+int batchnorm_relu_bwd_launch(const float*, int, int, int, const float*, const float*, const float*, int, float, int,
+                              const float*, int, const float*, int, float*, int, float*, float*, cudaStream_t);
+int scatter_mean_bwd_launch(const float*, int, const long long*, int, int, const float*, int, int, float*, int, int, int,
+                            int, cudaStream_t);
+int gather_triples_bwd_launch(const float*, int, int, int, int, const long long*, int, float*, float*, cudaStream_t);
+int embedding_bwd_launch(const float*, int, int, int, const long long*, int, int, float*, cudaStream_t);
 int gn_bwd_launch(const void*, int, int, int, int, int, const void*, int, int, const float*, int, const float*, int, const float*,
                   const float*, int, float, int, float*, const void*, int, void*, int, int, cudaStream_t);
 int batch_reduce_launch(const float*, int, int, int, int, float*, cudaStream_t);
@@ -216,6 +222,30 @@ int cs_batchnorm_relu(const float* x, int32_t M, int32_t C, int32_t pitch, const
 int cs_add_rows(const float* a, int32_t a_pitch, const float* b, int32_t b_pitch, int32_t M, int32_t C, float* y,
                 int32_t y_pitch, cs_stream_t stream) {
   return cs::add_rows_launch(a, a_pitch, b, b_pitch, M, C, y, y_pitch, S(stream));
+}
+
+int cs_batchnorm_relu_bwd(const float* x, int32_t M, int32_t C, int32_t pitch, const float* gamma,
+                          const float* running_mean, const float* running_var, int32_t training, float eps, int32_t relu,
+                          const float* y, int32_t y_pitch, const float* dy, int32_t dy_pitch, float* dx, int32_t dx_pitch,
+                          float* dgamma, float* dbeta, cs_stream_t stream) {
+  return cs::batchnorm_relu_bwd_launch(x, M, C, pitch, gamma, running_mean, running_var, training, eps, relu, y, y_pitch,
+                                       dy, dy_pitch, dx, dx_pitch, dgamma, dbeta, S(stream));
+}
+int cs_gcn_scatter_mean_bwd(const float* d_pooled, int32_t Hd, const int64_t* edges, int32_t T, int32_t O,
+                            const float* d_mid, int32_t mid_pitch, int32_t mid_w, float* d_tv, int32_t pitch,
+                            int32_t s_off, int32_t mid_off, int32_t o_off, cs_stream_t stream) {
+  return cs::scatter_mean_bwd_launch(d_pooled, Hd, reinterpret_cast<const long long*>(edges), T, O, d_mid, mid_pitch,
+                                     mid_w, d_tv, pitch, s_off, mid_off, o_off, S(stream));
+}
+int cs_gcn_gather_triples_bwd(const float* d_in, int32_t O, int32_t Do, int32_t T, int32_t Dp, const int64_t* edges,
+                              int32_t accumulate, float* d_obj, float* d_pred, cs_stream_t stream) {
+  return cs::gather_triples_bwd_launch(d_in, O, Do, T, Dp, reinterpret_cast<const long long*>(edges), accumulate, d_obj,
+                                       d_pred, S(stream));
+}
+int cs_embedding_bwd(const float* d_rows, int32_t pitch, int32_t col_off, int32_t D, const int64_t* idx, int32_t R,
+                     int32_t V, float* d_weight, cs_stream_t stream) {
+  return cs::embedding_bwd_launch(d_rows, pitch, col_off, D, reinterpret_cast<const long long*>(idx), R, V, d_weight,
+                                  S(stream));
 }
 
 void cs_debug_set(int32_t flags) { cs::igemm_set_debug(flags); }

@@ -15,8 +15,9 @@ import numpy as np
 import torch
 import torch.nn as nn
 
+from .. import ops
 from .graph import GraphTripleConvNet2, make_mlp
-from .layers import run_mlp
+from .layers import run_mlp, run_mlp_train
 from .sdfusion_txt2shape_model import SDFusionText2ShapeModel, default_opt
 
 
@@ -41,8 +42,24 @@ class Sg2ScVAEModel(nn.Module):
                                                         mlp_normalization=mlp_normalization, residual=residual)
         self.rel_mlp = make_mlp([gconv_dim * 2 + add_dim, 960, 1280], batch_norm=mlp_normalization, norelu=True)
 
-    @torch.no_grad()
     def encoder_2(self, z, objs, triples, dec_text_feat, dec_rel_feat, attributes=None, manipulate=False):
+        """(uc_rel, c_rel), each (O, 1, 1280) (reference :220-242).  With autograd enabled and trainable parameters the
+        outputs carry a grad_fn whose backward runs the explicit GCN / MLP gradient kernels (encoder_2_backward) and fills
+        `.grad` of rel_mlp, gconv_net_ec_rel, the two decoder embeddings and of `z`, as the reference's autograd does."""
+        if torch.is_grad_enabled() and (z.requires_grad or any(p.requires_grad for p in self._enc2_params())):
+            params = [p for p in self._enc2_params() if p.requires_grad]
+            uc, c = _Encoder2Function.apply(self, z, objs, triples, dec_text_feat, dec_rel_feat, *params)
+            return uc, (c if self.use_E2 else None)
+        with torch.no_grad():
+            uc, c, _ = self._encoder_2_impl(z, objs, triples, dec_text_feat, dec_rel_feat, train=False)
+        return uc, c
+
+    def _enc2_params(self):
+        mods = [self.obj_embeddings_dc, self.pred_embeddings_dc, self.rel_mlp] + ([self.gconv_net_ec_rel] if self.use_E2 else [])
+        return [p for m in mods for p in m.parameters()]
+
+    @torch.no_grad()
+    def _encoder_2_impl(self, z, objs, triples, dec_text_feat, dec_rel_feat, train: bool):
         s, p, o = [x.squeeze(1) for x in triples.chunk(3, dim=1)]
         edges = torch.stack([s, o], dim=1)
         obj_vecs = self.obj_embeddings_dc(objs)              # embedding row gathers: index plumbing
@@ -53,11 +70,53 @@ class Sg2ScVAEModel(nn.Module):
         else:
             obj_vecs_, pred_vecs_ = obj_vecs, pred_vecs
         rel_vecs_ = torch.cat([obj_vecs_, z], dim=1).float().contiguous()
-        rel_vecs_2 = None
+        rel_vecs_2, tape = None, None
+        if not train:
+            if self.use_E2:
+                rel_vecs_2, _ = self.gconv_net_ec_rel(rel_vecs_, pred_vecs_, edges)
+                rel_vecs_2 = run_mlp(self.rel_mlp, rel_vecs_2).unsqueeze(1)
+            return run_mlp(self.rel_mlp, rel_vecs_).unsqueeze(1), rel_vecs_2, None
+        gcn_tapes = mlp_c = None
         if self.use_E2:
-            rel_vecs_2, _ = self.gconv_net_ec_rel(rel_vecs_, pred_vecs_, edges)
-            rel_vecs_2 = run_mlp(self.rel_mlp, rel_vecs_2).unsqueeze(1)
-        return run_mlp(self.rel_mlp, rel_vecs_).unsqueeze(1), rel_vecs_2
+            ov, _, gcn_tapes = self.gconv_net_ec_rel.forward_train(rel_vecs_, pred_vecs_, edges)
+            rel_vecs_2, mlp_c = run_mlp_train(self.rel_mlp, ov)
+            rel_vecs_2 = rel_vecs_2.unsqueeze(1)
+        uc, mlp_uc = run_mlp_train(self.rel_mlp, rel_vecs_)
+        tape = dict(gcn=gcn_tapes, mlp_c=mlp_c, mlp_uc=mlp_uc, objs=objs.to(torch.int64).contiguous(),
+                    preds=p.to(torch.int64).contiguous(), n_text=dec_text_feat.shape[1] if self.clip else 0,
+                    n_rel=dec_rel_feat.shape[1] if self.clip else 0, z_dim=z.shape[1])
+        return uc.unsqueeze(1), rel_vecs_2, tape
+
+    def encoder_2_train(self, z, objs, triples, dec_text_feat, dec_rel_feat):
+        """encoder_2 keeping the activations: returns (uc_rel, c_rel, tape) for encoder_2_backward."""
+        return self._encoder_2_impl(z, objs, triples, dec_text_feat, dec_rel_feat, train=True)
+
+    @torch.no_grad()
+    def encoder_2_backward(self, tape, d_c=None, d_uc=None, sink=None):
+        """Gradients of every encoder_2 parameter (accumulated into `sink`, a GradSink) and d_z (O, z_dim), from the gradients
+        of c_rel and / or uc_rel ((O, 1, 1280) or (O, 1280)).  The training loss only uses c_rel (sdfusion_txt2shape_model.py
+        :348-361), so d_uc is normally None."""
+        from .. import ops_bwd
+        from .layers import mlp_backward
+        from .networks.diffusion_networks.unet_train import GradSink
+        sink = GradSink() if sink is None else sink
+        E = self.embedding_dim
+        n_obj_in = tape["n_text"] + E + tape["z_dim"]
+        d_rel_in = None                                     # gradient of rel_vecs_ = [text | Emb(obj) | z]
+        d_pred_in = None
+        if d_c is not None and tape["gcn"] is not None:
+            d_ov = mlp_backward(tape["mlp_c"], d_c.reshape(d_c.shape[0], -1).float().contiguous(), sink)
+            d_rel_in, d_pred_in = self.gconv_net_ec_rel.backward(tape["gcn"], d_ov, None, sink)   # E2's predicate output is unused
+        if d_uc is not None:
+            d2 = mlp_backward(tape["mlp_uc"], d_uc.reshape(d_uc.shape[0], -1).float().contiguous(), sink)
+            d_rel_in = d2 if d_rel_in is None else ops.add_rows(d_rel_in, d2)
+        if d_rel_in is None:
+            return sink, None
+        if self.obj_embeddings_dc.weight.requires_grad:
+            ops_bwd.embedding_bwd(d_rel_in, tape["n_text"], tape["objs"], sink.grad(self.obj_embeddings_dc.weight))
+        if d_pred_in is not None and self.pred_embeddings_dc.weight.requires_grad:
+            ops_bwd.embedding_bwd(d_pred_in, tape["n_rel"], tape["preds"], sink.grad(self.pred_embeddings_dc.weight))
+        return sink, d_rel_in[:, n_obj_in - tape["z_dim"]:].contiguous()
 
     def balance_objects(self, id_list, object_list, n):
         """Pick n objects covering distinct fine-grained classes first (host-side, python `random`, as the reference)."""
@@ -109,3 +168,25 @@ class Sg2ScVAEModel(nn.Module):
         c = uc if c is None else c
         diff_dict = {"sdf": dec_sdfs[ids], "rel": c[ids], "uc": uc[ids]}
         return self.Diff.rel2shape(diff_dict, ddim_steps=ddim_steps, uc_scale=uc_scale, seed=seed), dec_objs[ids]
+
+
+class _Encoder2Function(torch.autograd.Function):
+    """Autograd bridge for encoder_2: forward = encoder_2_train, backward = encoder_2_backward (explicit kernels)."""
+
+    @staticmethod
+    def forward(ctx, model, z, objs, triples, text_feat, rel_feat, *params):
+        uc, c, tape = model.encoder_2_train(z.detach(), objs, triples, text_feat.detach(), rel_feat.detach())
+        ctx.model, ctx.tape, ctx.params, ctx.need_dz = model, tape, params, z.requires_grad
+        ctx.set_materialize_grads(False)        # an unused output (uc_rel in training) arrives as None, not as zeros
+        if c is None:
+            c = uc.new_zeros(uc.shape)
+        return uc, c
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, d_uc, d_c):
+        sink, d_z = ctx.model.encoder_2_backward(ctx.tape, d_c=d_c if ctx.tape["gcn"] is not None else None, d_uc=d_uc)
+        ctx.tape = None
+        grads = tuple(sink.grads.get(p) for p in ctx.params)
+        return (None, d_z if ctx.need_dz else None, None, None, None, None) + grads
+

@@ -12,7 +12,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
-from .layers import build_mlp, run_mlp
+from .layers import build_mlp, linear_backward, mlp_backward, run_mlp, run_mlp_train
 
 
 def make_mlp(dim_list, activation="relu", batch_norm="none", dropout=0, norelu=False):
@@ -62,6 +62,45 @@ class GraphTripleConv(nn.Module):
             new_p = new_p.contiguous()
         return new_obj, new_p
 
+    # ---- training path: forward keeping the activations + explicit backward (the reference relies on autograd) ----
+    @torch.no_grad()
+    def forward_train(self, obj_vecs, pred_vecs, edges):
+        """forward() that also returns the tape for backward()."""
+        H, Dout = self.hidden_dim, self.output_dim
+        obj_vecs, pred_vecs = obj_vecs.float().contiguous(), pred_vecs.float().contiguous()
+        edges = edges.to(torch.int64).contiguous()
+        num_objs = obj_vecs.size(0)
+        new_t, tape1 = run_mlp_train(self.net1, ops.gcn_gather_triples(obj_vecs, pred_vecs, edges))
+        pooled = ops.gcn_scatter_mean(new_t, 0, H + Dout, H, edges, num_objs)
+        new_obj, tape2 = run_mlp_train(self.net2, pooled)
+        new_p = new_t[:, H:H + Dout]
+        if self.residual:
+            f = lambda t: t.detach().float().contiguous()
+            new_obj = ops.add_rows(new_obj, ops.linear_small(obj_vecs, f(self.linear_projection.weight), f(self.linear_projection.bias)))
+            new_p = ops.add_rows(new_p, ops.linear_small(pred_vecs, f(self.linear_projection_pred.weight), f(self.linear_projection_pred.bias)))
+        else:
+            new_p = new_p.contiguous()
+        return new_obj, new_p, (obj_vecs, pred_vecs, edges, tape1, tape2)
+
+    @torch.no_grad()
+    def backward(self, tape, d_new_obj, d_new_p, sink):
+        """(d_obj_vecs, d_pred_vecs) from the gradients of the two outputs; parameter gradients accumulate into `sink`."""
+        from .. import ops_bwd
+        obj_vecs, pred_vecs, edges, tape1, tape2 = tape
+        H, Do, Dp = self.hidden_dim, self.input_dim_obj, self.input_dim_pred
+        d_new_obj = d_new_obj.float().contiguous()
+        d_new_p = None if d_new_p is None else d_new_p.float().contiguous()      # None: the predicate output is unused
+        d_obj = linear_backward(self.linear_projection, obj_vecs, d_new_obj, sink) if self.residual else torch.zeros_like(obj_vecs)
+        if self.residual and d_new_p is not None:
+            d_pred = linear_backward(self.linear_projection_pred, pred_vecs, d_new_p, sink)
+        else:
+            d_pred = torch.zeros_like(pred_vecs)
+        d_pooled = mlp_backward(tape2, d_new_obj, sink)
+        d_new_t = ops_bwd.gcn_scatter_mean_bwd(d_pooled, edges, H, d_new_p, mid_w=self.output_dim)
+        d_in = mlp_backward(tape1, d_new_t, sink)
+        ops_bwd.gcn_gather_triples_bwd(d_in, edges, Do, Dp, d_obj, d_pred, accumulate=True)
+        return d_obj, d_pred
+
 
 class GraphTripleConvNet(nn.Module):
     """A sequence of scene graph convolution layers."""
@@ -81,6 +120,18 @@ class GraphTripleConvNet(nn.Module):
         for gconv in self.gconvs:
             obj_vecs, pred_vecs = gconv(obj_vecs, pred_vecs, edges)
         return obj_vecs, pred_vecs
+
+    def forward_train(self, obj_vecs, pred_vecs, edges):
+        tapes = []
+        for gconv in self.gconvs:
+            obj_vecs, pred_vecs, tape = gconv.forward_train(obj_vecs, pred_vecs, edges)
+            tapes.append(tape)
+        return obj_vecs, pred_vecs, tapes
+
+    def backward(self, tapes, d_obj, d_pred, sink):
+        for gconv, tape in zip(reversed(self.gconvs), reversed(tapes)):
+            d_obj, d_pred = gconv.backward(tape, d_obj, d_pred, sink)
+        return d_obj, d_pred
 
 
 class GraphTripleConvNet2(GraphTripleConvNet):

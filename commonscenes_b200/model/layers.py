@@ -58,3 +58,85 @@ def run_mlp(mlp: nn.Sequential, x: torch.Tensor) -> torch.Tensor:
         else:
             raise NotImplementedError(f"build_mlp layer {type(m).__name__}")
     return x
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# training path: the same stacks with the activations kept, and their explicit backward (what the reference's autograd
+# does for `loss.backward()` through rel_mlp / the GraphTripleConv nets, train_3dfront.py:387-391)
+# ----------------------------------------------------------------------------------------------------------------------
+_ONES = {}
+
+
+def _ones_row(m: int, device) -> torch.Tensor:
+    key = (m, str(device))
+    t = _ONES.get(key)
+    if t is None:
+        t = _ONES[key] = torch.ones((1, m), dtype=torch.float32, device=device)
+    return t
+
+
+def linear_backward(lin: nn.Linear, x: torch.Tensor, dy: torch.Tensor, sink, need_dx: bool = True):
+    """Gradients of y = x W^T + b: dW += dy^T x, db += column sums of dy (both into `sink`), returns dx = dy W (or None)."""
+    from .. import ops_bwd
+    if lin.weight.requires_grad:
+        ops_bwd.sgemm(dy, x, trans_a=True, out=sink.grad(lin.weight), accumulate=True)
+    if lin.bias is not None and lin.bias.requires_grad:
+        ops_bwd.sgemm(_ones_row(dy.shape[0], dy.device), dy, out=sink.grad(lin.bias).view(1, -1), accumulate=True)
+    return ops_bwd.sgemm(dy, lin.weight.detach().float().contiguous()) if need_dx else None
+
+
+@torch.no_grad()
+def run_mlp_train(mlp: nn.Sequential, x: torch.Tensor):
+    """run_mlp that also returns the tape [(module, input, output, training)] its backward needs."""
+    mods = list(mlp)
+    tape = []
+    i = 0
+    while i < len(mods):
+        m = mods[i]
+        if isinstance(m, nn.Linear):
+            y = ops.linear_small(x, m.weight.detach().float().contiguous(),
+                                 None if m.bias is None else m.bias.detach().float().contiguous())
+            tape.append(("linear", m, x, None, False))
+            i += 1
+        elif isinstance(m, nn.BatchNorm1d):
+            relu = i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU)
+            training = m.training or not m.track_running_stats
+            if training and m.track_running_stats:
+                m.num_batches_tracked += 1
+            y = ops.batchnorm_relu(x, m.weight, m.bias, m.running_mean, m.running_var, training,
+                                   momentum=0.1 if m.momentum is None else m.momentum, eps=m.eps, relu=relu)
+            tape.append(("bn_relu" if relu else "bn", m, x, y, training))
+            i += 2 if relu else 1
+        elif isinstance(m, nn.ReLU):
+            y = ops.batchnorm_relu(x, None, None, torch.zeros(x.shape[1], device=x.device), torch.ones(x.shape[1], device=x.device),
+                                   False, eps=0.0, relu=True)
+            tape.append(("relu", m, x, y, False))
+            i += 1
+        elif isinstance(m, nn.Dropout):
+            if m.training and m.p > 0:
+                raise NotImplementedError("dropout > 0 is not used by the v2_full configuration")
+            y = x
+            i += 1
+        else:
+            raise NotImplementedError(f"build_mlp layer {type(m).__name__}")
+        x = y
+    return x, tape
+
+
+@torch.no_grad()
+def mlp_backward(tape, dy: torch.Tensor, sink, need_dx: bool = True):
+    """Backward through a run_mlp_train tape; parameter gradients accumulate into `sink`; returns dx (or None)."""
+    from .. import ops_bwd
+    for k, (kind, m, x, y, training) in enumerate(reversed(tape)):
+        first = k == len(tape) - 1
+        if kind == "linear":
+            dy = linear_backward(m, x, dy, sink, need_dx=need_dx or not first)
+        elif kind in ("bn", "bn_relu"):
+            dg = sink.grad(m.weight) if m.affine and m.weight.requires_grad else None
+            db = sink.grad(m.bias) if m.affine and m.bias.requires_grad else None
+            dy = ops_bwd.batchnorm_relu_bwd(x, y, dy, m.weight.detach() if m.affine else None, m.running_mean, m.running_var,
+                                            training, eps=m.eps, relu=(kind == "bn_relu"), dgamma=dg, dbeta=db)
+        else:   # plain ReLU
+            dy = ops_bwd.batchnorm_relu_bwd(x, y, dy, None, torch.zeros(x.shape[1], device=x.device),
+                                            torch.ones(x.shape[1], device=x.device), False, eps=0.0, relu=True)
+    return dy

@@ -293,3 +293,65 @@ def attention_bwd(qkv: torch.Tensor, o: torch.Tensor, do: torch.Tensor, lse: tor
                                head_dim, scale, _stream()), "cs_attention_bwd")
     check(lib.cs_cast_rows(dq32.data_ptr(), hd, B * N, hd, dqkv.data_ptr(), W3, _stream()), "cs_cast_rows")
     return dqkv
+
+
+# ----------------------------------------------------------------------------------------------
+# scene-graph conditioning gradients (fp32 row matrices; graphs have tens of rows)
+# ----------------------------------------------------------------------------------------------
+def _mat(t: torch.Tensor, name: str) -> torch.Tensor:
+    if t.dtype != torch.float32 or t.dim() != 2 or not t.is_cuda or (t.shape[1] > 1 and t.stride(1) != 1):
+        raise _lib.CsError(f"{name}: expected an fp32 (M, C) CUDA matrix with contiguous rows")
+    return t
+
+
+def batchnorm_relu_bwd(x: torch.Tensor, y: Optional[torch.Tensor], dy: torch.Tensor, gamma, running_mean, running_var,
+                       training: bool, eps: float = 1e-5, relu: bool = True, dgamma: Optional[torch.Tensor] = None,
+                       dbeta: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dx of y = [relu](BatchNorm1d(x)); dgamma / dbeta (fp32 (C,)) are accumulated in place when given."""
+    _mat(x, "batchnorm_bwd.x"), _mat(dy, "batchnorm_bwd.dy")
+    M, Cc = x.shape
+    if tuple(dy.shape) != (M, Cc) or (y is not None and tuple(_mat(y, "batchnorm_bwd.y").shape) != (M, Cc)):
+        raise _lib.CsError("batchnorm_bwd: shape mismatch")
+    dx = torch.empty((M, Cc), dtype=torch.float32, device=x.device)
+    check(_lib.load().cs_batchnorm_relu_bwd(x.data_ptr(), M, Cc, x.stride(0), _ptr(gamma), _ptr(running_mean), _ptr(running_var),
+                                            int(training), eps, int(relu), _ptr(y), 0 if y is None else y.stride(0),
+                                            dy.data_ptr(), dy.stride(0), dx.data_ptr(), dx.stride(0), _ptr(dgamma), _ptr(dbeta),
+                                            _stream()), "cs_batchnorm_relu_bwd")
+    return dx
+
+
+def gcn_scatter_mean_bwd(d_pooled: torch.Tensor, edges: torch.Tensor, hidden: int, mid: Optional[torch.Tensor],
+                         mid_w: Optional[int] = None) -> torch.Tensor:
+    """Gradient of net1's output (T, 2*hidden + mid_w) = [s | mid | o] from d_pooled (O, hidden) and the gradient of the middle
+    (predicate) slice (`mid` None = that slice received no gradient: zeros of width mid_w)."""
+    _mat(d_pooled, "scatter_mean_bwd.d_pooled")
+    if not d_pooled.is_contiguous() or d_pooled.shape[1] != hidden:
+        raise _lib.CsError("scatter_mean_bwd: d_pooled must be contiguous (O, hidden)")
+    T, O = edges.shape[0], d_pooled.shape[0]
+    mid_w = (mid_w or 0) if mid is None else _mat(mid, "scatter_mean_bwd.mid").shape[1]
+    out = torch.empty((T, 2 * hidden + mid_w), dtype=torch.float32, device=d_pooled.device)
+    check(_lib.load().cs_gcn_scatter_mean_bwd(d_pooled.data_ptr(), hidden, edges.data_ptr(), T, O, _ptr(mid),
+                                              0 if mid is None else mid.stride(0), mid_w, out.data_ptr(), out.stride(0), 0, hidden,
+                                              hidden + mid_w, _stream()), "cs_gcn_scatter_mean_bwd")
+    return out
+
+
+def gcn_gather_triples_bwd(d_in: torch.Tensor, edges: torch.Tensor, Do: int, Dp: int, d_obj: torch.Tensor, d_pred: torch.Tensor,
+                           accumulate: bool = True) -> None:
+    """d_obj (O, Do) / d_pred (T, Dp) (+)= the gradient of cat([obj[s], pred, obj[o]]) = d_in (T, 2*Do + Dp)."""
+    _mat(d_in, "gather_bwd.d_in")
+    if not (d_in.is_contiguous() and d_obj.is_contiguous() and d_pred.is_contiguous()) or d_in.shape[1] != 2 * Do + Dp:
+        raise _lib.CsError("gather_triples_bwd: contiguous matrices of widths 2*Do+Dp / Do / Dp expected")
+    check(_lib.load().cs_gcn_gather_triples_bwd(d_in.data_ptr(), d_obj.shape[0], Do, d_in.shape[0], Dp, edges.data_ptr(),
+                                                int(accumulate), d_obj.data_ptr(), d_pred.data_ptr(), _stream()),
+          "cs_gcn_gather_triples_bwd")
+
+
+def embedding_bwd(d_rows: torch.Tensor, col_off: int, idx: torch.Tensor, d_weight: torch.Tensor) -> None:
+    """d_weight (V, D) += scatter of d_rows[:, col_off:col_off+D] by idx (int64 (R,))."""
+    _mat(d_rows, "embedding_bwd.d_rows")
+    if idx.dtype != torch.int64 or not idx.is_contiguous() or idx.shape[0] != d_rows.shape[0] or not d_weight.is_contiguous():
+        raise _lib.CsError("embedding_bwd: idx must be contiguous int64 (R,), d_weight contiguous")
+    V, Dm = d_weight.shape
+    check(_lib.load().cs_embedding_bwd(d_rows.data_ptr(), d_rows.stride(0), col_off, Dm, idx.data_ptr(), idx.shape[0], V,
+                                       d_weight.data_ptr(), _stream()), "cs_embedding_bwd")

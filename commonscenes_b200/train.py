@@ -27,6 +27,20 @@ from . import ops, ops_bwd
 from .model.networks.diffusion_networks.unet_train import GradSink
 
 
+def make_buckets(sizes: List[int], limit: int) -> List[tuple]:
+    """Contiguous [lo, hi) element ranges of the flat gradient buffer, each closed as soon as it holds >= limit elements
+    (parameter order; the backward finishes them from the last to the first)."""
+    buckets, start, acc = [], 0, 0
+    for n in sizes:
+        acc += n
+        if acc >= limit:
+            buckets.append((start, start + acc))
+            start, acc = start + acc, 0
+    if acc:
+        buckets.append((start, start + acc))
+    return buckets
+
+
 class DenoiserTrainStep:
     def __init__(self, diff_model, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.01,
                  max_grad_norm: float = 5.0, loss_scale: float = 100.0, group: Optional[dist.ProcessGroup] = None,
@@ -67,17 +81,7 @@ class DenoiserTrainStep:
         self.sumsq = torch.zeros((), dtype=torch.float32, device=dev)
         self.loss = torch.zeros((), dtype=torch.float32, device=dev)
         # gradient buckets in parameter order; the backward fills them from the last to the first
-        self.buckets: List[tuple] = []
-        limit = bucket_mb * (1 << 20) // 4
-        start = 0
-        acc = 0
-        for p, n in zip(params, sizes):
-            acc += n
-            if acc >= limit:
-                self.buckets.append((start, start + acc))
-                start, acc = start + acc, 0
-        if acc:
-            self.buckets.append((start, start + acc))
+        self.buckets: List[tuple] = make_buckets(sizes, bucket_mb * (1 << 20) // 4)
         self.comm_stream = torch.cuda.Stream(device=dev) if self.world > 1 else None
         self.unet._packed = None        # parameters moved: rebuild the kernel-layout copies
 
@@ -86,6 +90,9 @@ class DenoiserTrainStep:
         """Launch the all-reduce of every bucket that lies entirely at or after `done_off` (already final)."""
         while pending and self.buckets[pending[-1]][0] >= done_off:
             lo, hi = self.buckets[pending.pop()]
+            if self.comm_stream is None:        # host tensors (the gloo CPU tests of this scheduling logic)
+                dist.all_reduce(self.flat_g[lo:hi], op=dist.ReduceOp.SUM, group=self.group)
+                continue
             self.comm_stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self.comm_stream):
                 dist.all_reduce(self.flat_g[lo:hi], op=dist.ReduceOp.SUM, group=self.group)
@@ -179,3 +186,88 @@ class DenoiserTrainStep:
         self.graph.replay()
         self.step_count += 1
         return self._gout
+
+
+class _FlatGroup:
+    """A parameter group re-homed into flat fp32 buffers (values, gradients, AdamW moments) so that the clip norm and the
+    optimizer are ONE launch each and a multi-GPU step is ONE all-reduce.  The nn.Parameters become views: state_dict()
+    / load_state_dict() keep working and keep the reference's keys."""
+
+    def __init__(self, params: List[nn.Parameter]):
+        self.params = params
+        dev = params[0].device
+        sizes = [(p.numel() + 3) // 4 * 4 for p in params]
+        total = sum(sizes)
+        self.flat_p, self.flat_g, self.flat_m, self.flat_v = (torch.zeros(total, dtype=torch.float32, device=dev) for _ in range(4))
+        self.views: Dict[nn.Parameter, torch.Tensor] = {}
+        off = 0
+        with torch.no_grad():
+            for p, n in zip(params, sizes):
+                v = self.flat_p[off:off + p.numel()].view(p.shape)
+                v.copy_(p.data)
+                p.data = v
+                self.views[p] = self.flat_g[off:off + p.numel()].view(p.shape)
+                off += n
+        self.sumsq = torch.zeros((), dtype=torch.float32, device=dev)
+        self.step_dev = torch.zeros((), dtype=torch.int32, device=dev)
+
+    def clip_and_step(self, lr, betas, eps, weight_decay, max_norm, grad_scale):
+        self.step_dev.add_(1)
+        self.sumsq.zero_()
+        ops_bwd.sumsq(self.flat_g, self.sumsq)
+        ops_bwd.adamw_step(self.flat_p, self.flat_g, self.flat_m, self.flat_v, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay,
+                           sumsq_buf=self.sumsq, max_norm=max_norm, grad_scale=grad_scale, step_dev=self.step_dev)
+
+
+class ShapeBranchTrainStep:
+    """One v2_full shape-branch training iteration (BASELINE cfg3 / cfg4; reference: Sg2ScVAEModel.forward :511-521 +
+    train_3dfront.py:387-418): scene-graph batch -> encoder_2 (GCN-E2 + rel_mlp, BatchNorm in train mode) -> frozen VQ-VAE
+    encode of the selected objects' SDFs -> denoiser forward / backward (DenoiserTrainStep) -> d_c back through rel_mlp /
+    GCN-E2 / the embeddings -> clip 5.0 per group (train_3dfront.py:396-399) -> AdamW on both groups.
+
+    Multi-GPU: every rank runs encoder_2 on the WHOLE graph batch (so BatchNorm statistics equal the
+    single-process ones) and the denoiser on its own block of the selected objects; the denoiser gradients are all-reduced
+    in buckets during its backward, the graph-side gradients (each rank holds the part that flows through its objects)
+    in one all-reduce; both are means over ranks (DistributedDataParallel semantics)."""
+
+    def __init__(self, model, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.01,
+                 max_grad_norm: float = 5.0, loss_scale: float = 100.0, group: Optional[dist.ProcessGroup] = None):
+        self.model = model
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if self.world > 1 else 0
+        self.hp = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+        self.max_grad_norm = max_grad_norm
+        self.denoiser = DenoiserTrainStep(model.Diff, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay,
+                                          max_grad_norm=max_grad_norm, loss_scale=loss_scale, group=group)
+        self.graph_params = _FlatGroup([p for p in model._enc2_params() if p.requires_grad])
+
+    def shard(self, n_selected: int):
+        """This rank's contiguous block of the selected objects (parallel.py's block partition)."""
+        from .parallel import partition
+        return partition(n_selected, self.world)[self.rank]
+
+    def step(self, z, objs, triples, text_feat, rel_feat, sdfs, rows: Optional[torch.Tensor] = None,
+             t: Optional[torch.Tensor] = None, noise: Optional[torch.Tensor] = None):
+        """z (O, 64) layout latents, objs (O,), triples (T, 3), CLIP features (O, 512) / (T, 512), sdfs (O, 1, 64, 64, 64).
+        rows: indices of the objects that enter the denoiser on THIS rank (default: this rank's block of all O objects);
+        t / noise: optional fixed timesteps and noise for those rows.  Returns (loss [mean MSE on this rank], d_z (O, 64))."""
+        m = self.model
+        O = objs.shape[0]
+        if rows is None:
+            lo, hi = self.shard(O)
+            rows = torch.arange(lo, hi, device=objs.device)
+        uc, c, tape = m.encoder_2_train(z, objs, triples, text_feat, rel_feat)
+        c = uc if c is None else c
+        with torch.no_grad():
+            lat = m.Diff.vqvae(sdfs[rows].to(c.device), forward_no_quant=True, encode_only=True)
+        loss, d_c_rows = self.denoiser.step(lat, c[rows].contiguous(), t=t, noise=noise, need_dcond=True)
+        d_c = torch.zeros((O, c.shape[-1]), dtype=torch.float32, device=c.device)
+        d_c.index_copy_(0, rows, d_c_rows.reshape(rows.shape[0], -1).float())
+        g = self.graph_params
+        g.flat_g.zero_()
+        _, d_z = m.encoder_2_backward(tape, d_c=d_c if m.use_E2 else None, d_uc=None if m.use_E2 else d_c, sink=GradSink(g.views))
+        if self.world > 1:
+            dist.all_reduce(g.flat_g, op=dist.ReduceOp.SUM, group=self.group)
+        g.clip_and_step(max_norm=self.max_grad_norm, grad_scale=1.0 / self.world, **self.hp)
+        return loss, d_z

@@ -249,6 +249,25 @@ int cs_batchnorm_relu(const float* x, int32_t M, int32_t C, int32_t pitch, const
 int cs_add_rows(const float* a, int32_t a_pitch, const float* b, int32_t b_pitch, int32_t M, int32_t C, float* y,
                 int32_t y_pitch, cs_stream_t stream);
 
+/* ---- backward of the scene-graph conditioning (the gradient the reference's autograd sends from the diffusion loss into
+ * rel_mlp / gconv_net_ec_rel / the decoder embeddings: VAEGAN_V2FULL.py:511-521, train_3dfront.py:387-391); fp32,
+ * deterministic (no atomics).  Linear layers use cs_sgemm_small. ---- */
+/* dx (+ dgamma/dbeta accumulated in place when non-NULL) of y = [relu](BatchNorm1d(x)); y supplies the ReLU mask */
+int cs_batchnorm_relu_bwd(const float* x, int32_t M, int32_t C, int32_t pitch, const float* gamma,
+                          const float* running_mean, const float* running_var, int32_t training, float eps, int32_t relu,
+                          const float* y, int32_t y_pitch, const float* dy, int32_t dy_pitch, float* dx, int32_t dx_pitch,
+                          float* dgamma, float* dbeta, cs_stream_t stream);
+/* d_tv[t] = [d_pooled[s_t]/n(s_t) at s_off | d_mid[t] (zeros if NULL) at mid_off | d_pooled[o_t]/n(o_t) at o_off]  (graph.py:165-195) */
+int cs_gcn_scatter_mean_bwd(const float* d_pooled, int32_t Hd, const int64_t* edges, int32_t T, int32_t O,
+                            const float* d_mid, int32_t mid_pitch, int32_t mid_w, float* d_tv, int32_t pitch,
+                            int32_t s_off, int32_t mid_off, int32_t o_off, cs_stream_t stream);
+/* d_obj[i] (+)= sum of the subject / object slices of d_in over the triples incident to i; d_pred[t] (+)= middle slice (graph.py:139-147) */
+int cs_gcn_gather_triples_bwd(const float* d_in, int32_t O, int32_t Do, int32_t T, int32_t Dp, const int64_t* edges,
+                              int32_t accumulate, float* d_obj, float* d_pred, cs_stream_t stream);
+/* d_weight[v] += sum_{r: idx[r]=v} d_rows[r][col_off:col_off+D]   (nn.Embedding backward, VAEGAN_V2FULL.py:223-224) */
+int cs_embedding_bwd(const float* d_rows, int32_t pitch, int32_t col_off, int32_t D, const int64_t* idx, int32_t R,
+                     int32_t V, float* d_weight, cs_stream_t stream);
+
 /* contiguous fp32 -> bf16 (keys / values of a multi-token cross-attention context, attention.py:186-187) */
 int cs_cast_f32_to_bf16(const float* x, int64_t n, void* y, cs_stream_t stream);
 

@@ -65,3 +65,52 @@ def test_sharded_sampling_gathers_objects_in_order_world2():
             p.join(timeout=120)
             assert p.exitcode == 0
         assert dict(ret) == {0: True, 1: True}
+
+
+# ---- training partition: bucketed gradient all-reduce scheduling of DenoiserTrainStep ----
+def test_gradient_buckets_cover_the_flat_buffer():
+    from commonscenes_b200.train import make_buckets
+    sizes = [4, 100, 28, 64, 8, 300, 12]
+    b = make_buckets(sizes, 128)
+    assert b[0][0] == 0 and b[-1][1] == sum(sizes) and all(b[i][1] == b[i + 1][0] for i in range(len(b) - 1))
+    assert b == [(0, 132), (132, 504), (504, 516)]
+    assert make_buckets([8, 8], 1 << 30) == [(0, 16)] and make_buckets([], 4) == []
+
+
+def _train_worker(rank, world, port, ret):
+    from commonscenes_b200.train import DenoiserTrainStep, make_buckets
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sizes = [16, 48, 32, 8, 64, 24]
+        offs = [sum(sizes[:i]) for i in range(len(sizes))]
+        st = object.__new__(DenoiserTrainStep)          # only the scheduling state: no CUDA in this container
+        st.buckets, st.comm_stream, st.group = make_buckets(sizes, 60), None, None
+        g = torch.Generator().manual_seed(rank)
+        st.flat_g = torch.randn(sum(sizes), generator=g)
+        mine = st.flat_g.clone()
+        other = torch.randn(sum(sizes), generator=torch.Generator().manual_seed(1 - rank))
+        pending = list(range(len(st.buckets)))
+        reduced_after = []
+        for off in reversed(offs):                      # the backward finishes parameters from the last to the first
+            st._allreduce_ready(off, pending)
+            reduced_after.append(len(st.buckets) - len(pending))
+        st._allreduce_ready(0, pending)
+        ok = not pending and torch.allclose(st.flat_g, mine + other)           # every bucket reduced exactly once
+        ok = ok and reduced_after == sorted(reduced_after) and reduced_after[0] <= 1   # buckets go out as soon as they are final
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_bucketed_allreduce_schedule_world2():
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    port = _free_port()
+    procs = [ctx.Process(target=_train_worker, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert dict(ret) == {0: True, 1: True}

@@ -148,10 +148,12 @@ def test_multi_token_context_generic_cross_attention():
     ctx = torch.randn(2, 5, cfg["context_dim"], generator=g)
     with torch.no_grad():
         ref = D.unet_forward(sd, cfg, x, t, ctx)
-    eps = m(x.cuda(), t.cuda(), c_crossattn=[ctx.cuda()]).cpu()
+        eps = m(x.cuda(), t.cuda(), c_crossattn=[ctx.cuda()]).cpu()      # inference path (the training path is single-token)
     err = _rel_l2(eps, ref)
     print(f"multi-token context (M=5): rel-L2 {err:.3e}")
     assert err <= REL_L2_TOL
+    with pytest.raises(NotImplementedError):                             # gradients through M > 1 contexts fail loudly
+        m(x.cuda(), t.cuda(), c_crossattn=[ctx.cuda()])
 
 
 @pytest.mark.parametrize("B", [1, 7])
