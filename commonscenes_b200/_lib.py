@@ -72,7 +72,7 @@ SIGNATURES = {
     "cs_cast_rows": (_i32, [_vp, _i32, _i64, _i32, _vp, _i32, _vp]),
     "cs_sgemm_small": (_i32, [_vp, _i32, _i32, _vp, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
     "cs_mse_loss_grad": (_i32, [_vp, _vp, _i64, _f32, _vp, _vp, _vp]),
-    "cs_sumsq": (_i32, [_vp, _i64, _vp, _vp]),
+    "cs_sumsq": (_i32, [_vp, _i64, _vp, _vp, _i64, _vp]),
     "cs_adamw": (_i32, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _i32, _vp, _f32, _f32, _vp, _vp]),
     "cs_pack_weight": (_i32, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "cs_attention_lse": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _vp]),

@@ -55,7 +55,7 @@ int cast_rows_launch(const float*, int, long long, int, void*, int, cudaStream_t
 int sgemm_small_launch(const float*, int, int, const float*, int, int, float*, int, int, int, int, int, const float*, int,
                        cudaStream_t);
 int mse_loss_grad_launch(const float*, const float*, long long, float, float*, float*, cudaStream_t);
-int sumsq_launch(const float*, long long, float*, cudaStream_t);
+int sumsq_launch(const float*, long long, float*, void*, long long, cudaStream_t);
 int adamw_launch(float*, const float*, float*, float*, long long, float, float, float, float, float, int, const float*, float,
                  float, const int*, cudaStream_t);
 int unpack_wgrad_launch(const float*, int, int, int, int, float*, cudaStream_t);
@@ -307,7 +307,9 @@ int cs_mse_loss_grad(const float* pred, const float* target, int64_t n, float lo
                      cs_stream_t stream) {
   return cs::mse_loss_grad_launch(pred, target, n, loss_scale, grad, loss, S(stream));
 }
-int cs_sumsq(const float* g, int64_t n, float* out, cs_stream_t stream) { return cs::sumsq_launch(g, n, out, S(stream)); }
+int cs_sumsq(const float* g, int64_t n, float* out, void* workspace, int64_t workspace_bytes, cs_stream_t stream) {
+  return cs::sumsq_launch(g, n, out, workspace, workspace_bytes, S(stream));
+}
 int cs_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
              float weight_decay, int32_t step, const float* sumsq, float max_norm, float grad_scale, const int32_t* step_dev,
              cs_stream_t stream) {

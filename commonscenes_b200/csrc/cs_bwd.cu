@@ -668,7 +668,11 @@ int mse_loss_grad_launch(const float* pred, const float* target, long long n, fl
 // eps added outside the sqrt), with the gradient-clipping factor of clip_grad_norm_ folded in:
 //   clip = min(1, max_norm / (sqrt(*sumsq) + 1e-6))   (train_3dfront.py:399; *sumsq from sumsq_kernel, or null)
 // ------------------------------------------------------------------------------------------------
-__global__ void sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ out) {
+// Deterministic: block partials go to `partial`, the last block to finish (ticket counter) adds them up in a fixed order,
+// so every data-parallel replica computes the bit-identical norm (and clip factor) from its bit-identical all-reduced
+// gradient -- replicas must not drift apart.
+__global__ void sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ out, float* __restrict__ partial,
+                             unsigned* __restrict__ ticket) {
   float s = 0.f;
   const long long n4 = n >> 2;
   const float4* g4 = reinterpret_cast<const float4*>(g);
@@ -683,21 +687,48 @@ __global__ void sumsq_kernel(const float* __restrict__ g, long long n, float* __
   }
   s = warp_sum(s);
   __shared__ float ws[32];
+  __shared__ bool last;
   if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
   __syncthreads();
   if (threadIdx.x < 32) {
     float t = threadIdx.x < (blockDim.x >> 5) ? ws[threadIdx.x] : 0.f;
     t = warp_sum(t);
-    if (threadIdx.x == 0) atomicAdd(out, t);
+    if (threadIdx.x == 0) {
+      partial[blockIdx.x] = t;
+      __threadfence();
+      last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  float t = 0.f;
+  for (unsigned i = threadIdx.x; i < gridDim.x; i += blockDim.x) t += __ldcg(partial + i);
+  t = warp_sum(t);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = t;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float u = threadIdx.x < (blockDim.x >> 5) ? ws[threadIdx.x] : 0.f;
+    u = warp_sum(u);
+    if (threadIdx.x == 0) {
+      *out += u;
+      *ticket = 0;      // ready for the next launch on this workspace
+    }
   }
 }
-int sumsq_launch(const float* g, long long n, float* out, cudaStream_t st) {
+int sumsq_launch(const float* g, long long n, float* out, void* workspace, long long workspace_bytes, cudaStream_t st) {
   if (n <= 0) return CS_OK;
   if (reinterpret_cast<uintptr_t>(g) % 16) return set_error(CS_ERR_INVALID, "sumsq: buffer must be 16-byte aligned");
   long long blocks = (n / 4 + 255) / 256;
   if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
+  if (blocks > 2047) blocks = 2047;
   if (blocks < 1) blocks = 1;
-  sumsq_kernel<<<(int)blocks, 256, 0, st>>>(g, n, out);
+  if (!workspace || workspace_bytes < 8192 || reinterpret_cast<uintptr_t>(workspace) % 4)
+    return set_error(CS_ERR_INVALID, "sumsq: needs a zero-initialised 8192-byte workspace (block partials + ticket)");
+  float* partial = static_cast<float*>(workspace);
+  unsigned* ticket = reinterpret_cast<unsigned*>(partial + 2047);
+  sumsq_kernel<<<(int)blocks, 256, 0, st>>>(g, n, out, partial, ticket);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error(e, "sumsq: launch");
   count_launch();

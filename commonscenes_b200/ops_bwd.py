@@ -239,8 +239,16 @@ def mse_loss_grad(pred: torch.Tensor, target: torch.Tensor, loss: torch.Tensor, 
     return grad
 
 
+_SUMSQ_WS = {}
+
+
 def sumsq(g: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
-    check(_lib.load().cs_sumsq(g.data_ptr(), g.numel(), out.data_ptr(), _stream()), "cs_sumsq")
+    """out (fp32 scalar) += sum(g^2), summed in a fixed order (bit-identical on every data-parallel replica)."""
+    key = g.device
+    ws = _SUMSQ_WS.get(key)
+    if ws is None:      # block partials + ticket; one per device (calls are stream-ordered), zeroed once, left zeroed by the kernel
+        ws = _SUMSQ_WS[key] = torch.zeros(2048, dtype=torch.float32, device=g.device)
+    check(_lib.load().cs_sumsq(g.data_ptr(), g.numel(), out.data_ptr(), ws.data_ptr(), ws.numel() * 4, _stream()), "cs_sumsq")
     return out
 
 

@@ -132,8 +132,10 @@ int cs_sgemm_small(const float* A, int32_t lda, int32_t trans_a, const float* Bm
 /* p_losses (sdfusion_txt2shape_model.py:311-345): *loss += mean((pred - target)^2); grad = 2 (pred - target) loss_scale / n */
 int cs_mse_loss_grad(const float* pred, const float* target, int64_t n, float loss_scale, float* grad, float* loss,
                      cs_stream_t stream);
-/* *out += sum g^2 (clip_grad_norm_, train_3dfront.py:399) */
-int cs_sumsq(const float* g, int64_t n, float* out, cs_stream_t stream);
+/* *out += sum g^2 (clip_grad_norm_, train_3dfront.py:399).  Deterministic (fixed summation order, so data-parallel replicas
+ * clip identically).  workspace: >= 8192 bytes, zero-initialised once by the caller, private to one stream at a time (the
+ * kernel leaves it zeroed for the next call). */
+int cs_sumsq(const float* g, int64_t n, float* out, void* workspace, int64_t workspace_bytes, cs_stream_t stream);
 /* torch.optim.AdamW step (VAEGAN_V2FULL.py:642-650) over a flat fp32 buffer; gradient = g * grad_scale, additionally
  * clipped to max_norm when `sumsq` (device scalar from cs_sumsq over the same g) is not NULL.  The step number (from 1)
  * is `step`, or *step_dev when step_dev is not NULL (a device counter, so that a captured CUDA graph can be replayed) */
