@@ -1,6 +1,6 @@
 """Data-parallel training check + timing (BASELINE cfg4 at N ranks; run under torchrun, one rank per GPU):
 
-  torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tools/ddp_check.py [--objs-per-rank 4] [--time]
+  torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tests/ddp_check.py [--objs-per-rank 4] [--time]
 
 1. correctness: the N-rank ShapeBranchTrainStep (objects block-partitioned over ranks, bucketed NCCL all-reduce of the
    denoiser gradients overlapped with the backward, one all-reduce of the graph-side gradients) must produce the gradients
@@ -13,7 +13,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import torch.distributed as dist
 
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from test_shape_branch_train_gpu import _model, _scene_batch      # synthetic cfg3 batch + seeded model (test infrastructure)
 from commonscenes_b200.train import ShapeBranchTrainStep
 

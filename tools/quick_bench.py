@@ -2,12 +2,12 @@
 import sys, time, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from oracle import denoiser as D
 from commonscenes_b200 import ops
 from commonscenes_b200.model.networks.diffusion_networks.network import DiffusionUNet
+from commonscenes_b200.model.sdfusion_txt2shape_model import UNET_PARAMS
 
 objs = int(sys.argv[1]) if len(sys.argv) > 1 else 32
-cfg = D.UNET_FULL
+cfg = UNET_PARAMS
 torch.manual_seed(0)
 with torch.device("cuda"):
     m = DiffusionUNet(dict(cfg, use_spatial_transformer=True, legacy=False), conditioning_key="crossattn")

@@ -54,7 +54,7 @@ for _ in range(2):
 ms_step, _ = timed(lambda: step.step_graphed(z, ctx), reps=5)
 print("loss (graphed):", loss.item())
 print(f"graphed train step B={B}: {ms_step:.1f} ms -> {1000 / ms_step:.2f} steps/s, {B * 1000 / ms_step:.1f} objects/s "
-      f"({3 * B * 0.5576 / ms_step:.1f} TFLOP/s algorithmic, fwd+bwd = 3 x 557.6 GF/sample)")
+      f"({3 * B * 557.6 / ms_step:.0f} TFLOP/s algorithmic, fwd+bwd = 3 x 557.6 GF/sample)")
 tr = step.trainer
 t = torch.randint(0, 1000, (B,), device="cuda")
 noise = torch.randn_like(z)
