@@ -61,7 +61,7 @@ int adamw_launch(float*, const float*, float*, float*, long long, float, float, 
 int unpack_wgrad_launch(const float*, int, int, int, int, float*, cudaStream_t);
 int attention_lse_launch(const void*, const void*, const void*, void*, int, int, int, int, int, int, int, int, int, float, float*,
                          cudaStream_t);
-int attention_bwd_launch(const void*, const void*, const void*, const void*, const void*, const float*, float*, float*, void*,
+int attention_bwd_launch(const void*, const void*, const void*, const void*, const void*, const float*, float*, void*, void*,
                          void*, int, int, int, int, int, int, int, int, int, float, cudaStream_t);
 int pack_weight_launch(const float*, int, int, int, int, void*, void*, cudaStream_t);
 void igemm_set_debug(int);
@@ -329,7 +329,7 @@ int cs_attention_lse(const void* q, const void* k, const void* v, void* out, int
   return cs::attention_lse_launch(q, k, v, out, B, H, Nq, Nk, Dp, q_pitch, kv_pitch, o_pitch, d_out, scale, lse, S(stream));
 }
 int cs_attention_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse,
-                     float* dsum_ws, float* dq, void* dk, void* dv, int32_t B, int32_t H, int32_t N, int32_t Dp,
+                     float* dsum_ws, void* dq, void* dk, void* dv, int32_t B, int32_t H, int32_t N, int32_t Dp,
                      int32_t qkv_pitch, int32_t o_pitch, int32_t do_pitch, int32_t dqkv_pitch, int32_t d_out, float scale,
                      cs_stream_t stream) {
   return cs::attention_bwd_launch(q, k, v, o, dout, lse, dsum_ws, dq, dk, dv, B, H, N, Dp, qkv_pitch, o_pitch, do_pitch,

@@ -291,15 +291,12 @@ def attention_bwd(qkv: torch.Tensor, o: torch.Tensor, do: torch.Tensor, lse: tor
     if do.dtype != torch.bfloat16 or do.stride(-1) != 1 or o.stride(-1) != 1:
         raise _lib.CsError("attention_bwd: o / do must be bf16 with a contiguous last dim")
     dqkv = torch.empty_like(qkv)
-    dq32 = torch.zeros((B, N, hd), dtype=torch.float32, device=qkv.device)
     dsum = torch.empty((B, heads, N), dtype=torch.float32, device=qkv.device)
-    lib = _lib.load()
     es = qkv.element_size()
-    check(lib.cs_attention_bwd(qkv.data_ptr(), qkv.data_ptr() + hd * es, qkv.data_ptr() + 2 * hd * es, o.data_ptr(),
-                               do.data_ptr(), lse.data_ptr(), dsum.data_ptr(), dq32.data_ptr(), dqkv.data_ptr() + hd * es,
-                               dqkv.data_ptr() + 2 * hd * es, B, heads, N, head_dim_padded, W3, o.stride(-2), do.stride(-2), W3,
-                               head_dim, scale, _stream()), "cs_attention_bwd")
-    check(lib.cs_cast_rows(dq32.data_ptr(), hd, B * N, hd, dqkv.data_ptr(), W3, _stream()), "cs_cast_rows")
+    check(_lib.load().cs_attention_bwd(qkv.data_ptr(), qkv.data_ptr() + hd * es, qkv.data_ptr() + 2 * hd * es, o.data_ptr(),
+                                       do.data_ptr(), lse.data_ptr(), dsum.data_ptr(), dqkv.data_ptr(), dqkv.data_ptr() + hd * es,
+                                       dqkv.data_ptr() + 2 * hd * es, B, heads, N, head_dim_padded, W3, o.stride(-2),
+                                       do.stride(-2), W3, head_dim, scale, _stream()), "cs_attention_bwd")
     return dqkv
 
 

@@ -152,10 +152,10 @@ int cs_pack_weight(const float* w, int32_t Cout, int32_t Cin, int32_t taps, int3
 int cs_attention_lse(const void* q, const void* k, const void* v, void* out, int32_t B, int32_t H, int32_t Nq, int32_t Nk,
                      int32_t Dp, int32_t q_pitch, int32_t kv_pitch, int32_t o_pitch, int32_t d_out, float scale, float* lse,
                      cs_stream_t stream);
-/* self-attention backward (attention.py:201-218): dk / dv bf16 laid out like k / v (pitch dqkv_pitch); dq fp32
- * [B][N][H*Dp], must be zero on entry (accumulated with atomics); dsum_ws fp32 [B][H][N] scratch */
+/* self-attention backward (attention.py:201-218): dq / dk / dv bf16 laid out like q / k / v (pitch dqkv_pitch, all Dp
+ * columns written); dsum_ws fp32 [B][H][N] scratch.  Deterministic (no atomics). */
 int cs_attention_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse,
-                     float* dsum_ws, float* dq, void* dk, void* dv, int32_t B, int32_t H, int32_t N, int32_t Dp,
+                     float* dsum_ws, void* dq, void* dk, void* dv, int32_t B, int32_t H, int32_t N, int32_t Dp,
                      int32_t qkv_pitch, int32_t o_pitch, int32_t do_pitch, int32_t dqkv_pitch, int32_t d_out, float scale,
                      cs_stream_t stream);
 
