@@ -9,8 +9,9 @@ rel2shape, save, load_ckpt, state-dict layout {'vqvae','df','global_step'[,'opt'
 visuals (pytorch3d, mcubes) are outside the hot path and not provided.
 
 Differences underneath: rel2shape runs ALL objects in one batch (the reference's mini-batches of 7 exist for A100
-memory, :493; objects are independent so results are identical), the x_T noise may be seeded, and forward() computes the
-diffusion loss without autograd (the backward kernels are the next round's work — see DESIGN.md).
+memory, :493; objects are independent so results are identical), the x_T noise may be seeded, rel2shape can also run the
+1000-step ancestral sampler (samplers/ddpm.py), and `loss_df` from forward() back-propagates through explicit CUDA backward
+kernels (autograd bridge in UNet3DModel.forward; native step in commonscenes_b200/train.py).
 """
 from __future__ import annotations
 
@@ -237,8 +238,10 @@ class SDFusionText2ShapeModel(BaseModel):
         self.switch_train()
 
     @torch.no_grad()
-    def rel2shape(self, data, ddim_steps=100, ddim_eta=0.0, uc_scale=None, seed=None, return_latent=False):
-        """Scene-graph conditioning -> (O, 1, R, R, R) SDFs.  One shared x_T for all objects (reference :487-491)."""
+    def rel2shape(self, data, ddim_steps=100, ddim_eta=0.0, uc_scale=None, seed=None, return_latent=False, sampler="ddim"):
+        """Scene-graph conditioning -> (O, 1, R, R, R) SDFs.  One shared x_T for all objects (reference :487-491).
+        sampler="ddpm": ancestral sampling over all num_timesteps (BASELINE cfg5; samplers/ddpm.py) instead of DDIM —
+        `ddim_steps` is then ignored unless it is smaller than num_timesteps AND explicitly meant to truncate (tests)."""
         self.switch_eval()
         self.set_input(data)
         ddim_steps = self.ddim_steps if ddim_steps is None else ddim_steps
@@ -247,9 +250,19 @@ class SDFusionText2ShapeModel(BaseModel):
         gen = torch.Generator(device=self.device)
         gen.manual_seed(int(time.time()) if seed is None else int(seed))
         noise = torch.randn((1, *self.z_shape), device=self.device, generator=gen).repeat(B, 1, 1, 1, 1)
-        samples, _ = self.ddim_sampler.sample(S=ddim_steps, batch_size=B, shape=self.z_shape, conditioning=self.rel, x_T=noise,
-                                              verbose=False, unconditional_guidance_scale=uc_scale,
-                                              unconditional_conditioning=self.uc_rel, eta=ddim_eta)
+        if sampler == "ddpm":
+            if getattr(self, "ddpm_sampler", None) is None:
+                from .networks.diffusion_networks.samplers.ddpm import DDPMSampler
+                self.ddpm_sampler = DDPMSampler(self)
+            samples, _ = self.ddpm_sampler.sample(batch_size=B, shape=self.z_shape, conditioning=self.rel, x_T=noise,
+                                                  unconditional_guidance_scale=uc_scale, unconditional_conditioning=self.uc_rel,
+                                                  timesteps=None if ddim_steps in (None, 100) else ddim_steps, generator=gen)
+        elif sampler == "ddim":
+            samples, _ = self.ddim_sampler.sample(S=ddim_steps, batch_size=B, shape=self.z_shape, conditioning=self.rel, x_T=noise,
+                                                  verbose=False, unconditional_guidance_scale=uc_scale,
+                                                  unconditional_conditioning=self.uc_rel, eta=ddim_eta)
+        else:
+            raise ValueError(f"unknown sampler '{sampler}' (ddim | ddpm)")
         self.gen_df = self.vqvae_module.decode_no_quant(samples)
         return (self.gen_df, samples) if return_latent else self.gen_df
 

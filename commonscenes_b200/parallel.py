@@ -46,18 +46,18 @@ def gather_objects(local: torch.Tensor, num_objects: int, group: Optional[dist.P
 
 @torch.no_grad()
 def rel2shape_sharded(diff_model, data: dict, ddim_steps: int = 100, ddim_eta: float = 0.0, uc_scale: float = 3.0,
-                      seed: Optional[int] = None, group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
+                      seed: Optional[int] = None, group: Optional[dist.ProcessGroup] = None, **sampler_kw) -> torch.Tensor:
     """SDFusionText2ShapeModel.rel2shape with the objects of `data` ('sdf', 'rel', 'uc': one row per object) split
     across the ranks of `group`; every rank returns the full (O, 1, R, R, R) result.  All ranks must pass the same
     `data` and `seed` (the reference shares one x_T across objects, sdfusion_txt2shape_model.py:487-491)."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
-        return diff_model.rel2shape(data, ddim_steps=ddim_steps, ddim_eta=ddim_eta, uc_scale=uc_scale, seed=seed)
+        return diff_model.rel2shape(data, ddim_steps=ddim_steps, ddim_eta=ddim_eta, uc_scale=uc_scale, seed=seed, **sampler_kw)
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     n = data["rel"].shape[0]
     lo, hi = partition(n, world)[rank]
     if hi > lo:
         local = {k: v[lo:hi] for k, v in data.items()}
-        out = diff_model.rel2shape(local, ddim_steps=ddim_steps, ddim_eta=ddim_eta, uc_scale=uc_scale, seed=seed)
+        out = diff_model.rel2shape(local, ddim_steps=ddim_steps, ddim_eta=ddim_eta, uc_scale=uc_scale, seed=seed, **sampler_kw)
     else:   # more ranks than objects: this rank only takes part in the gather
         r = diff_model.z_shape[-1] * 4
         out = torch.zeros((0, 1, r, r, r), dtype=torch.float32, device=data["rel"].device)

@@ -335,3 +335,22 @@ def ddim_sample(sd, cfg, sched, cond: Tensor, uc: Optional[Tensor], x_T: Tensor,
         x, pred_x0, e_t = p_sample_ddim(sd, cfg, dd, x, cond, int(step), index, scale, uc)
         trace.append((x, pred_x0, e_t))
     return x, trace
+
+
+def p_sample_ddpm(sd, cfg, sched, x: Tensor, c: Tensor, t_int: int, scale: float, uc: Optional[Tensor], noise: Tensor):
+    """One ancestral DDPM step (BASELINE cfg5) in the posterior-mean form, from the buffers the reference registers in
+    register_schedule (sdfusion_txt2shape_model.py:214-224: sqrt_recip(m1)_alphas_cumprod, posterior_mean_coef1/2,
+    posterior_log_variance_clipped) with DDIMSampler's guidance rule (samplers/ddim.py:206-210).
+    PARITY UNPINNED for the step itself: the reference ships no ancestral sampler to run against -- this is
+    the textbook DDPM posterior over the reference's own (pinned) schedule tables."""
+    b = x.shape[0]
+    t = torch.full((b,), int(t_int), dtype=torch.long)
+    if uc is None or scale == 1.0:
+        e_t = unet_forward(sd, cfg, x, t, c)
+    else:
+        e_uc, e_c = unet_forward(sd, cfg, torch.cat([x] * 2), torch.cat([t] * 2), torch.cat([uc, c])).chunk(2)
+        e_t = e_uc + scale * (e_c - e_uc)
+    x0 = sched["sqrt_recip_alphas_cumprod"][t_int] * x - sched["sqrt_recipm1_alphas_cumprod"][t_int] * e_t
+    mean = sched["posterior_mean_coef1"][t_int] * x0 + sched["posterior_mean_coef2"][t_int] * x
+    nonzero = 0.0 if t_int == 0 else 1.0
+    return mean + nonzero * torch.exp(0.5 * sched["posterior_log_variance_clipped"][t_int]) * noise, x0, e_t

@@ -110,3 +110,24 @@ def test_encoder2_matches_reference_golden(tag, cfg):
             uc, c = G.encoder_2(sd, cfg, *args, training=(mode == "train"))
         _close(c, g[f"c_{mode}"], 5e-5)
         _close(uc, g[f"uc_{mode}"], 5e-5)
+
+
+def test_ddpm_posterior_equals_eta1_ddim_form():
+    """The ancestral sampler feeds cs_ddim_step with (abar_t, abar_{t-1}, sigma_t = sqrt(beta~_t)); that DDIM-form update must
+    equal the posterior-mean form the oracle restates from the reference's registered buffers, for every t."""
+    from oracle import denoiser as D
+    sched = D.register_schedule(**D.DIFFUSION)
+    ac = sched["alphas_cumprod"].double().numpy()
+    ac_prev = np.append(1.0, ac[:-1])
+    betas = 1.0 - ac / ac_prev
+    sig = np.sqrt(betas * (1.0 - ac_prev) / (1.0 - ac))
+    assert sig[0] == 0.0
+    g = torch.Generator().manual_seed(0)
+    x, e = torch.randn(64, generator=g).double(), torch.randn(64, generator=g).double()
+    for t in (0, 1, 2, 10, 500, 998, 999):
+        x0 = (x - np.sqrt(1.0 - ac[t]) * e) / np.sqrt(ac[t])
+        ddim_form = np.sqrt(ac_prev[t]) * x0 + np.sqrt(max(1.0 - ac_prev[t] - sig[t] ** 2, 0.0)) * e
+        x0_ref = sched["sqrt_recip_alphas_cumprod"][t].double() * x - sched["sqrt_recipm1_alphas_cumprod"][t].double() * e
+        post = sched["posterior_mean_coef1"][t].double() * x0_ref + sched["posterior_mean_coef2"][t].double() * x
+        assert float((ddim_form - post).abs().max()) < 2e-5, t           # fp32 tables vs float64 recomputation
+        assert abs(sig[t] - float(torch.exp(0.5 * sched["posterior_log_variance_clipped"][t]))) < 1e-6 or t == 0

@@ -59,3 +59,21 @@ def test_training_forward_loss_matches_definition(model):
     errs = model.get_current_errors()
     assert set(errs) == {"total", "simple", "vlb"} and all(torch.isfinite(v) for v in errs.values())
     assert abs(float(errs["total"]) - float(errs["simple"])) < 1e-6      # l_simple_weight = 1, elbo weight = 0, logvar = 0
+
+
+def test_cfg5_ancestral_sampling_ten_objects(model):
+    """BASELINE.json configs[4] (one livingroom-sized scene, 10 objects, ancestral DDPM with CFG, decode to 64^3): a
+    truncated chain here (the full 1000 steps are timed by tools/scene_sample_bench.py); checks shapes, finiteness, that
+    the chain is reproducible under a seed and really stochastic (differs from the eta = 0 DDIM result)."""
+    g = torch.Generator(device="cuda").manual_seed(9)
+    n = 10
+    data = {"sdf": torch.zeros(n, 1, 64, 64, 64, device="cuda"), "rel": torch.randn(n, 1, 1280, device="cuda", generator=g),
+            "uc": torch.randn(n, 1, 1280, device="cuda", generator=g)}
+    sdf, z = model.rel2shape(data, ddim_steps=40, uc_scale=3.0, seed=3, return_latent=True, sampler="ddpm")
+    assert sdf.shape == (n, 1, 64, 64, 64) and torch.isfinite(sdf).all() and torch.isfinite(z).all()
+    _, z2 = model.rel2shape(data, ddim_steps=40, uc_scale=3.0, seed=3, return_latent=True, sampler="ddpm")
+    assert float((z - z2).norm() / z.norm()) < 5e-2
+    _, z3 = model.rel2shape(data, ddim_steps=40, uc_scale=3.0, seed=4, return_latent=True, sampler="ddpm")
+    assert float((z - z3).norm() / z.norm()) > 0.2
+    with pytest.raises(ValueError):
+        model.rel2shape(data, sampler="plms")

@@ -137,6 +137,43 @@ def test_sampler_public_api_runs_and_counts_kernels():
     assert ops.launch_count() > n0 and set(inter) == {"x_inter", "pred_x0"}
 
 
+def test_ddpm_ancestral_steps_match_oracle_posterior():
+    """BASELINE cfg5: ancestral DDPM steps (posterior mean + sqrt(beta~) z) vs the oracle's posterior-form step, teacher
+    forced on the same (x_t, t, cond, z), at the last / a middle / the first two timesteps of the chain (t = 0 adds no noise)."""
+    from commonscenes_b200.model.networks.diffusion_networks.samplers.ddpm import DDPMSampler
+    seed = 27
+    m = _build(D.UNET_TINY, seed)
+    sd = Wt.synth_state_dict(D.unet_param_shapes(D.UNET_TINY), seed)
+    sched = D.register_schedule(**D.DIFFUSION)
+
+    class Host:
+        num_timesteps = 1000
+        betas = sched["betas"].cuda()
+        alphas_cumprod = sched["alphas_cumprod"].cuda()
+        df = m
+    s = DDPMSampler(Host())
+    s.make_schedule()
+    g = torch.Generator().manual_seed(10)
+    c, uc = torch.randn(3, 1, 64, generator=g), torch.randn(3, 1, 64, generator=g)
+    ca = m.diffusion_net.context_vectors(torch.cat([uc, c]).cuda())
+    t_dev = torch.empty(6, dtype=torch.int64, device="cuda")
+    for t in (999, 500, 1, 0):
+        x = torch.randn(3, 3, 8, 8, 8, generator=g)
+        z = torch.randn(3, 3, 8, 8, 8, generator=g)
+        with torch.no_grad():
+            ref_x, ref_p0, _ = D.p_sample_ddpm(sd, D.UNET_TINY, sched, x, c, t, 3.0, uc, z)
+        t_dev.fill_(t)
+        xp, p0 = s.p_sample(x.cuda(), t_dev, ca, t, True, 3.0, noise=z.cuda())
+        e_x, e_p = _rel_l2(xp.cpu(), ref_x), _rel_l2(p0.cpu(), ref_p0)
+        print(f"ddpm step t={t}: rel-L2 x_prev {e_x:.3e} pred_x0 {e_p:.3e}")
+        assert e_x <= REL_L2_TOL and e_p <= 2 * REL_L2_TOL
+        if t == 0:
+            assert torch.equal(xp, p0)              # the chain ends on pred_x0: no noise at t = 0
+    out, inter = s.sample(batch_size=3, shape=(3, 8, 8, 8), conditioning=c.cuda(), unconditional_guidance_scale=3.0,
+                          unconditional_conditioning=uc.cuda(), timesteps=12, generator=torch.Generator(device="cuda").manual_seed(1))
+    assert out.shape == (3, 3, 8, 8, 8) and torch.isfinite(out).all() and set(inter) == {"x_inter", "pred_x0"}
+
+
 def test_multi_token_context_generic_cross_attention():
     """The reference API accepts (B, M, context_dim) contexts; v2_full always has M = 1 (fast path) but M > 1 must work."""
     cfg = D.UNET_TINY
