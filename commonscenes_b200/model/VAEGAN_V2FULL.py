@@ -40,7 +40,10 @@ class Sg2ScVAEModel(nn.Module):
             self.gconv_net_ec_rel = GraphTripleConvNet2(input_dim_obj=gconv_dim * 2 + add_dim, input_dim_pred=gconv_dim * 2 + add_dim,
                                                         hidden_dim=hidden, pooling=gconv_pooling, num_layers=gconv_num_layers,
                                                         mlp_normalization=mlp_normalization, residual=residual)
-        self.rel_mlp = make_mlp([gconv_dim * 2 + add_dim, 960, 1280], batch_norm=mlp_normalization, norelu=True)
+        net_rel_layers = [gconv_dim * 2 + add_dim, 960, 1280]
+        if self.Diff.df.conditioning_key == "concat":          # reference :152-154: 4096 = one 16^3 latent channel
+            net_rel_layers = [gconv_dim * 2 + add_dim, 1280, 4096]
+        self.rel_mlp = make_mlp(net_rel_layers, batch_norm=mlp_normalization, norelu=True)
 
     def encoder_2(self, z, objs, triples, dec_text_feat, dec_rel_feat, attributes=None, manipulate=False):
         """(uc_rel, c_rel), each (O, 1, 1280) (reference :220-242).  With autograd enabled and trainable parameters the

@@ -91,6 +91,8 @@ def normalization(channels):
 
 
 def conv_nd(dims, *args, **kwargs):
+    if dims == 1:                      # the 1x1 qkv / proj_out projections of AttentionBlock (openai_model_3d.py:340,348)
+        return nn.Conv1d(*args, **kwargs)
     if dims in (3, 4):
         return nn.Conv3d(*args, **kwargs)
     raise ValueError(f"unsupported dimensions: {dims} (the shape branch is 3-D)")

@@ -18,10 +18,13 @@ class DiffusionUNet(nn.Module):
 
     def forward(self, x, t, c_concat: list = None, c_crossattn: list = None, **kw):
         if self.conditioning_key is None:
-            raise NotImplementedError("unconditional UNet: the v2_full shape branch is cross-attention conditioned")
+            return self.diffusion_net(x, t, **kw)
         if self.conditioning_key == "crossattn":
             cc = c_crossattn[0] if len(c_crossattn) == 1 else torch.cat(c_crossattn, 1)
             return self.diffusion_net(x, t, context=cc, **kw)
-        if self.conditioning_key in ("concat", "hybrid", "adm"):
-            raise NotImplementedError(f"conditioning_key={self.conditioning_key!r}: SURVEY.md §8f rank 1 (concat variant), not built yet")
+        if self.conditioning_key == "concat":           # reference network.py:25-27
+            xc = torch.cat([x.float()] + [c.float() for c in c_concat], dim=1)
+            return self.diffusion_net(xc, t, **kw)
+        if self.conditioning_key in ("hybrid", "adm"):
+            raise NotImplementedError(f"conditioning_key={self.conditioning_key!r} is not used by any reference config")
         raise NotImplementedError()

@@ -23,7 +23,7 @@ import torch
 import torch.nn as nn
 
 from .... import _lib, ops
-from .attention import SpatialTransformer3D
+from .attention import SpatialTransformer3D, _pad_head_dim
 from .ldm_diffusion_util import conv_nd, linear, normalization, timestep_embedding, zero_module
 
 
@@ -178,6 +178,70 @@ class ResBlock(TimestepBlock):
         return _with_stats(arena, lambda st: ops.conv3d(a, pk["w2"], bias=pk["b2"], residual=res, stat_sum=st), B, C, S)
 
 
+class QKVAttentionLegacy(nn.Module):
+    """Parameter-free marker kept for module-tree parity (openai_model_3d.py:386-411): heads are split BEFORE q/k/v."""
+
+    def __init__(self, n_heads):
+        super().__init__()
+        self.n_heads = n_heads
+
+
+class QKVAttention(QKVAttentionLegacy):
+    """use_new_attention_order=True (:417-447): q/k/v are split before the heads."""
+
+
+class AttentionBlock(nn.Module):
+    """Self-attention over all voxels, used by the concat-conditioning denoiser instead of the spatial transformer
+    (reference openai_model_3d.py:317-364): x + proj_out(attention(qkv(GroupNorm32(x)))), tokens in (d h w) order,
+    softmax(q k^T / sqrt(ch)) (the reference scales q and k by ch^-1/4 each).  Same children / state-dict keys
+    (norm, qkv [Conv1d k=1], proj_out [Conv1d k=1]); run() = GroupNorm kernel -> one qkv GEMM (head-padded q|k|v layout,
+    the legacy head-major row order is undone in the weight packing) -> flash attention kernel -> proj_out GEMM whose
+    epilogue adds the residual and accumulates the next GroupNorm's sums."""
+
+    def __init__(self, channels, num_heads=1, num_head_channels=-1, use_checkpoint=False, use_new_attention_order=False):
+        super().__init__()
+        self.channels = channels
+        if num_head_channels == -1:
+            self.num_heads = num_heads
+        else:
+            assert channels % num_head_channels == 0, \
+                f"q,k,v channels {channels} is not divisible by num_head_channels {num_head_channels}"
+            self.num_heads = channels // num_head_channels
+        self.use_checkpoint = use_checkpoint
+        self.norm = normalization(channels)
+        self.qkv = conv_nd(1, channels, channels * 3, 1)
+        self.attention = QKVAttention(self.num_heads) if use_new_attention_order else QKVAttentionLegacy(self.num_heads)
+        self.proj_out = zero_module(conv_nd(1, channels, channels, 1))
+
+    def pack(self):
+        C, h = self.channels, self.num_heads
+        ch = C // h
+        dp = _pad_head_dim(ch)
+        w = self.qkv.weight.detach().float().reshape(3 * C, C)
+        b = self.qkv.bias.detach().float()
+        if isinstance(self.attention, QKVAttention):                  # rows ordered [q|k|v][head][ch]
+            w, b = w.reshape(3, h, ch, C), b.reshape(3, h, ch)
+        else:                                                         # legacy: rows ordered [head][q|k|v][ch]
+            w, b = w.reshape(h, 3, ch, C).permute(1, 0, 2, 3), b.reshape(h, 3, ch).permute(1, 0, 2)
+        wp = torch.zeros(3, h, dp, C, dtype=torch.float32, device=w.device)
+        bp = torch.zeros(3, h, dp, dtype=torch.float32, device=w.device)
+        wp[:, :, :ch], bp[:, :, :ch] = w, b
+        return {"gn": (_f(self.norm.weight), _f(self.norm.bias)), "dp": dp,
+                "wqkv": ops.pack_linear_weight(wp.reshape(3 * h * dp, C)), "bqkv": bp.reshape(-1).contiguous(),
+                "wo": ops.pack_linear_weight(self.proj_out.weight.detach().float().reshape(C, C)), "bo": _f(self.proj_out.bias)}
+
+    def run(self, pk, x, arena):
+        B, D, H, W, C = x.t.shape
+        h, dp = self.num_heads, pk["dp"]
+        ch = C // h
+        a = ops.groupnorm_fused(x.t, x.stat, *pk["gn"], eps=self.norm.eps)
+        qkv = ops.linear_tokens(a, pk["wqkv"], bias=pk["bqkv"]).view(B, D * H * W, 3 * h * dp)
+        q, k, v = (qkv[:, :, i * h * dp:(i + 1) * h * dp] for i in range(3))
+        o = ops.attention(q, k, v, heads=h, head_dim=ch, head_dim_padded=dp, scale=ch ** -0.5)
+        return _with_stats(arena, lambda st: ops.linear_tokens(o.view(B, D, H, W, C), pk["wo"], bias=pk["bo"], residual=x.t,
+                                                               stat_sum=st), B, C, D * H * W)
+
+
 class UNet3DModel(nn.Module):
     def __init__(self, image_size, in_channels, model_channels, out_channels, num_res_blocks, attention_resolutions,
                  dropout=0, channel_mult=(1, 2, 4, 8), conv_resample=True, dims=2, num_classes=None,
@@ -191,8 +255,6 @@ class UNet3DModel(nn.Module):
             assert use_spatial_transformer, "You forgot to use the spatial transformer for your cross-attention conditioning..."
             if not isinstance(context_dim, int):
                 context_dim = list(context_dim)
-        if not use_spatial_transformer:
-            raise NotImplementedError("the AttentionBlock (concat-conditioning) variant is SURVEY.md §8f rank 1, not built yet")
         if num_classes is not None or resblock_updown or n_embed is not None:
             raise NotImplementedError("class conditioning / resblock_updown / codebook-id head are unused by the reference configs")
         if num_heads_upsample == -1:
@@ -230,6 +292,9 @@ class UNet3DModel(nn.Module):
                 heads, dim_head = ch // num_head_channels, num_head_channels
             if legacy:
                 dim_head = ch // heads
+            if not use_spatial_transformer:        # the concat-conditioning variant (reference :593-598, 649-654, 690-697)
+                return AttentionBlock(ch, use_checkpoint=use_checkpoint, num_heads=heads, num_head_channels=dim_head,
+                                      use_new_attention_order=use_new_attention_order)
             return SpatialTransformer3D(ch, heads, dim_head, depth=transformer_depth, context_dim=context_dim)
 
         def res(cin, cout):
@@ -304,6 +369,9 @@ class UNet3DModel(nn.Module):
                         offs.append((ca_off, w.shape[0])); ca_off += w.shape[0]
                     e = {"kind": "st", "pk": layer.pack(), "ca": offs}
                     stat_channels += layer.in_channels
+                elif isinstance(layer, AttentionBlock):
+                    e = {"kind": "attn", "pk": layer.pack()}
+                    stat_channels += layer.channels
                 elif isinstance(layer, (Downsample, Upsample)):
                     e = {"kind": "resample", "pk": layer.pack()}
                     stat_channels += layer.out_channels
@@ -316,7 +384,10 @@ class UNet3DModel(nn.Module):
                 entries.append(e)
             pk["blocks"].append(entries)
         pk["emb_w"], pk["emb_b"] = torch.cat(emb_w).contiguous(), torch.cat(emb_b).contiguous()
-        pk["ca_w"], pk["ca_b"] = torch.cat(ca_w).contiguous(), torch.cat(ca_b).contiguous()
+        if ca_w:
+            pk["ca_w"], pk["ca_b"] = torch.cat(ca_w).contiguous(), torch.cat(ca_b).contiguous()
+        else:                                               # no cross-attention (concat variant)
+            pk["ca_w"] = pk["ca_b"] = None
         pk["stat_channels"] = stat_channels
         self._arenas = {}
         pk["out_gn"] = (_f(self.out[0].weight), _f(self.out[0].bias))
@@ -336,6 +407,8 @@ class UNet3DModel(nn.Module):
         """All cross-attention outputs for a (B, 1, context_dim) conditioning: fp32 (B, sum of block widths).
         Depends only on the context, so samplers may compute it once per trajectory."""
         pk = self._ensure_packed()
+        if pk["ca_w"] is None:
+            raise ValueError("this UNet has no cross-attention (use_spatial_transformer=False): there is no context")
         if context.dim() != 3 or context.shape[1] != 1:
             raise ValueError("context_vectors() is the single-token fast path; pass multi-token contexts to forward()")
         return ops.linear_small(context[:, 0].float().contiguous(), pk["ca_w"], pk["ca_b"])
@@ -363,6 +436,10 @@ class UNet3DModel(nn.Module):
                 (context.requires_grad or any(p.requires_grad for p in self.parameters())):
             params = [p for p in self.parameters() if p.requires_grad]
             return _UNetFunction.apply(self, x, timesteps, context, *params)
+        if torch.is_grad_enabled() and context is None and context_vecs is None and (
+                x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            raise NotImplementedError("gradients through the AttentionBlock (concat-conditioning) denoiser are not built: call it "
+                                      "under torch.no_grad() (sampling); training covers the cross-attention denoiser of v2_full")
         with torch.no_grad():
             return self._forward_inference(x, timesteps, context, context_vecs)
 
@@ -376,7 +453,10 @@ class UNet3DModel(nn.Module):
         emb = ops.linear_small(ops.linear_small(t_emb, w0, b0, act_out=ops.ACT_SILU), w2, b2)
         emb_vecs = ops.linear_small(emb, pk["emb_w"], pk["emb_b"], act_in=ops.ACT_SILU)     # every ResBlock's emb_layers at once
         multi = context_vecs is None and context is not None and context.dim() == 3 and context.shape[1] > 1
-        ca_vecs = None if multi else (context_vecs if context_vecs is not None else self.context_vectors(context))
+        if pk["ca_w"] is None:          # no cross-attention layers (concat variant): the conditioning is inside x
+            ca_vecs = None
+        else:
+            ca_vecs = None if multi else (context_vecs if context_vecs is not None else self.context_vectors(context))
 
         arena = self._arenas.get(B)
         if arena is None:
@@ -394,7 +474,7 @@ class UNet3DModel(nn.Module):
                         h = layer.run(e["pk"], h, [None] * len(e["ca"]), arena, context=context)
                     else:
                         h = layer.run(e["pk"], h, [ca_vecs[:, o:o + n] for o, n in e["ca"]], arena)
-                elif e["kind"] == "resample":
+                elif e["kind"] in ("resample", "attn"):
                     h = layer.run(e["pk"], h, arena)
                 else:
                     col = ops.im2col_small(h, batch=B, kp=e["pk"]["kp"])

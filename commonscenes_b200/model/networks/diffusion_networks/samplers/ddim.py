@@ -42,33 +42,52 @@ class DDIMSampler(object):
 
     # ------------------------------------------------------------------------------------------
     def _unet(self):
-        df = self.model.df_module if hasattr(self.model, "df_module") else self.model.df
-        return df.diffusion_net
+        return self._df().diffusion_net
 
-    def _eps(self, x, t_dev, ca_vecs):
+    def _df(self):
+        return self.model.df_module if hasattr(self.model, "df_module") else self.model.df
+
+    def _is_concat(self):
+        return getattr(self._df(), "conditioning_key", None) == "concat"
+
+    def _conditioning(self, cond, uncond, guided):
+        """-> (ca_vecs, concat): the per-trajectory conditioning in kernel form.  Cross-attention: the context-only vectors
+        of all blocks for [uncond; cond]; concat (network.py:25-27): the (2B | B, Cc, D, H, W) volume appended to x."""
+        ctx = torch.cat([uncond, cond]) if guided else cond                          # [uncond; cond] (ddim.py:206-209)
+        if self._is_concat():
+            return None, ctx.float().contiguous()
+        return self._unet().context_vectors(ctx), None
+
+    def _eps(self, x, t_dev, ca_vecs, concat=None):
         """One UNet evaluation for the whole (guided) batch, optionally through a cached CUDA graph."""
         unet = self._unet()
+        if concat is not None:          # x_in = cat([x (repeated for [uncond; cond]), c_concat], dim=1)
+            r = concat.shape[0] // x.shape[0]
+            x = torch.cat([x.repeat(r, 1, 1, 1, 1) if r > 1 else x, concat], dim=1)
+        call = (lambda a, b, c: unet(a, b)) if concat is not None else (lambda a, b, c: unet(a, b, context_vecs=c))
         if not self.use_cuda_graph:
-            return unet(x, t_dev, context_vecs=ca_vecs)
+            return call(x, t_dev, ca_vecs)
         unet._ensure_packed()
         key = (tuple(x.shape), t_dev.shape[0], unet._pack_generation)
         g = self._graphs.get(key)
         if g is None:
-            sx, st, sc = x.clone(), t_dev.clone(), ca_vecs.clone()
+            sx, st, sc = x.clone(), t_dev.clone(), (None if ca_vecs is None else ca_vecs.clone())
             s = torch.cuda.Stream()
             s.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s):
                 for _ in range(2):                      # warm-up: lazy packing, attribute setup, allocator pools
-                    unet(sx, st, context_vecs=sc)
+                    call(sx, st, sc)
             torch.cuda.current_stream().wait_stream(s)
             graph = torch.cuda.CUDAGraph()
             n0 = ops.launch_count()
             with torch.cuda.graph(graph):
-                out = unet(sx, st, context_vecs=sc)
+                out = call(sx, st, sc)
             g = {"graph": graph, "x": sx, "t": st, "c": sc, "out": out, "launches": ops.launch_count() - n0}
             self._graphs.clear()                        # one resident graph (a new shape replaces the old one)
             self._graphs[key] = g
-        g["x"].copy_(x); g["t"].copy_(t_dev); g["c"].copy_(ca_vecs)
+        g["x"].copy_(x); g["t"].copy_(t_dev)
+        if ca_vecs is not None:
+            g["c"].copy_(ca_vecs)
         g["graph"].replay()
         self.kernels_per_eval = g["launches"]
         return g["out"]
@@ -106,13 +125,13 @@ class DDIMSampler(object):
         total_steps = timesteps.shape[0]
 
         guided = unconditional_conditioning is not None and unconditional_guidance_scale != 1.
-        ctx = torch.cat([unconditional_conditioning, cond]) if guided else cond     # [uncond; cond] (ddim.py:206-209)
-        ca_vecs = self._unet().context_vectors(ctx)                                  # once per trajectory
+        ca_vecs, concat = self._conditioning(cond, unconditional_conditioning, guided)     # once per trajectory
         t_dev = torch.empty(2 * b if guided else b, dtype=torch.int64, device=device)
         for i, step in enumerate(time_range):
             index = total_steps - i - 1
             t_dev.fill_(int(step))
-            img, pred_x0 = self._step(img, t_dev, ca_vecs, index, guided, float(unconditional_guidance_scale), temperature)
+            img, pred_x0 = self._step(img, t_dev, ca_vecs, index, guided, float(unconditional_guidance_scale), temperature,
+                                      concat=concat)
             if callback:
                 callback(i)
             if img_callback:
@@ -122,9 +141,9 @@ class DDIMSampler(object):
                 intermediates["pred_x0"].append(pred_x0)
         return img, intermediates
 
-    def _step(self, x, t_dev, ca_vecs, index, guided, scale, temperature=1., want_pred_x0=True):
+    def _step(self, x, t_dev, ca_vecs, index, guided, scale, temperature=1., want_pred_x0=True, concat=None):
         """UNet evaluation (graph replay) + fused CFG / pred_x0 / x_prev update (cs_ddim_step)."""
-        eps = self._eps(x, t_dev, ca_vecs)
+        eps = self._eps(x, t_dev, ca_vecs, concat=concat)
         sigma = float(self.ddim_sigmas[index])
         noise = torch.randn_like(x) * temperature if sigma > 0 else None
         return ops.ddim_step(x, eps, guided=guided, scale=scale, a_t=float(self.ddim_alphas[index]),
@@ -140,7 +159,7 @@ class DDIMSampler(object):
         if use_original_steps or quantize_denoised or score_corrector is not None or mm_cls_free or noise_dropout > 0.:
             raise NotImplementedError("options unused by the shape branch")
         guided = unconditional_conditioning is not None and unconditional_guidance_scale != 1.
-        ctx = torch.cat([unconditional_conditioning, c]) if guided else c
-        ca_vecs = self._unet().context_vectors(ctx)
+        ca_vecs, concat = self._conditioning(c, unconditional_conditioning, guided)
         tt = (torch.cat([t] * 2) if guided else t).to(torch.int64).contiguous()
-        return self._step(x.float().contiguous(), tt, ca_vecs, index, guided, float(unconditional_guidance_scale), temperature)
+        return self._step(x.float().contiguous(), tt, ca_vecs, index, guided, float(unconditional_guidance_scale), temperature,
+                          concat=concat)

@@ -49,8 +49,7 @@ class DDPMSampler(DDIMSampler):
         size = (batch_size, *shape)
         img = torch.randn(size, device=device, generator=generator) if x_T is None else x_T.float().contiguous()
         guided = unconditional_conditioning is not None and unconditional_guidance_scale != 1.
-        ctx = torch.cat([unconditional_conditioning, conditioning]) if guided else conditioning
-        ca_vecs = self._unet().context_vectors(ctx)
+        ca_vecs, concat = self._conditioning(conditioning, unconditional_conditioning, guided)
         t_dev = torch.empty(2 * batch_size if guided else batch_size, dtype=torch.int64, device=device)
         intermediates = {"x_inter": [img], "pred_x0": [img]}
         total = self.ddim_timesteps.shape[0]
@@ -58,7 +57,7 @@ class DDPMSampler(DDIMSampler):
             t = int(t)
             t_dev.fill_(t)
             img, pred_x0 = self.p_sample(img, t_dev, ca_vecs, t, guided, float(unconditional_guidance_scale), temperature,
-                                         generator=generator)
+                                         generator=generator, concat=concat)
             if callback:
                 callback(i)
             if img_callback:
@@ -68,9 +67,10 @@ class DDPMSampler(DDIMSampler):
                 intermediates["pred_x0"].append(pred_x0)
         return img, intermediates
 
-    def p_sample(self, x, t_dev, ca_vecs, t: int, guided: bool, scale: float, temperature=1., noise=None, generator=None):
+    def p_sample(self, x, t_dev, ca_vecs, t: int, guided: bool, scale: float, temperature=1., noise=None, generator=None,
+                 concat=None):
         """One ancestral step at timestep t: UNet evaluation + fused CFG / x0 / posterior sample."""
-        eps = self._eps(x, t_dev, ca_vecs)
+        eps = self._eps(x, t_dev, ca_vecs, concat=concat)
         sigma = float(self.ddim_sigmas[t])
         if sigma > 0 and noise is None:
             noise = torch.randn(x.shape, device=x.device, generator=generator) * temperature

@@ -35,6 +35,11 @@ DF_MODEL_PARAMS = dict(linear_start=0.00085, linear_end=0.012, conditioning_key=
 UNET_PARAMS = dict(image_size=16, in_channels=3, out_channels=3, model_channels=224, num_res_blocks=2,
                    attention_resolutions=[4, 2], channel_mult=[1, 2, 3], num_heads=8, dims=3, use_spatial_transformer=True,
                    transformer_depth=1, context_dim=1280, use_checkpoint=True, legacy=False)
+# config/sdfusion-txt2shape_concat.yaml: conditioning concatenated as a 4th latent channel
+DF_MODEL_PARAMS_CONCAT = dict(DF_MODEL_PARAMS, conditioning_key="concat")
+UNET_PARAMS_CONCAT = dict(image_size=16, in_channels=4, out_channels=3, model_channels=224, num_res_blocks=2,
+                          attention_resolutions=[4, 2], channel_mult=[1, 2, 3], num_heads=8, dims=4, use_spatial_transformer=False,
+                          transformer_depth=1, context_dim=None, use_checkpoint=True, legacy=False)
 # config/vqvae_snet.yaml
 VQ_CONF = dict(model=dict(params=dict(embed_dim=3, n_embed=8192, ddconfig=dict(
     double_z=False, z_channels=3, resolution=64, in_channels=1, out_ch=1, ch=64, ch_mult=[1, 2, 4], num_res_blocks=1,
@@ -58,10 +63,12 @@ def _load_yaml(path):
         return _Cfg.wrap(yaml.safe_load(f))
 
 
-def default_opt(device="cuda", vq_ckpt=None, df_cfg=None, vq_cfg=None, ckpt_dir=None):
-    """The fields of config/v2_full.yaml that the shape branch reads."""
-    return _Cfg.wrap(dict(hyper=dict(batch_size=4, isTrain=True, device=device, distributed=0),
-                          network=dict(df_cfg=df_cfg, vq_cfg=vq_cfg, vq_ckpt=vq_ckpt, ddim_steps=100, ddim_eta=0.0, uc_scale=3.0),
+def default_opt(device="cuda", vq_ckpt=None, df_cfg=None, vq_cfg=None, ckpt_dir=None, conditioning_key="crossattn"):
+    """The fields of config/v2_full.yaml (conditioning_key="concat": config/v2_full_concat.yaml) that the shape branch reads.
+    `df_cfg` (a yaml path, e.g. the reference's config/sdfusion-txt2shape[_concat].yaml) overrides the built-in values."""
+    return _Cfg.wrap(dict(hyper=dict(batch_size=4 if conditioning_key == "crossattn" else 32, isTrain=True, device=device, distributed=0),
+                          network=dict(df_cfg=df_cfg, vq_cfg=vq_cfg, vq_ckpt=vq_ckpt, ddim_steps=100, ddim_eta=0.0, uc_scale=3.0,
+                                       conditioning_key=conditioning_key),
                           misc=dict(debug=0, seed=111, local_rank=0), ckpt_dir=ckpt_dir))
 
 
@@ -94,14 +101,19 @@ class SDFusionText2ShapeModel(BaseModel):
         self.model_name = self.name()
         self.device = opt.hyper.device
 
-        df_conf = _load_yaml(opt.network.df_cfg) if opt.network.df_cfg else _Cfg.wrap(dict(model=dict(params=DF_MODEL_PARAMS), unet=dict(params=UNET_PARAMS)))
+        if opt.network.df_cfg:
+            df_conf = _load_yaml(opt.network.df_cfg)
+        elif opt.network.conditioning_key == "concat":
+            df_conf = _Cfg.wrap(dict(model=dict(params=DF_MODEL_PARAMS_CONCAT), unet=dict(params=UNET_PARAMS_CONCAT)))
+        else:
+            df_conf = _Cfg.wrap(dict(model=dict(params=DF_MODEL_PARAMS), unet=dict(params=UNET_PARAMS)))
         vq_conf = _load_yaml(opt.network.vq_cfg) if opt.network.vq_cfg else _Cfg.wrap(VQ_CONF)
         ddconfig = vq_conf.model.params.ddconfig
         z_sp = ddconfig.resolution // (2 ** (len(ddconfig.ch_mult) - 1))
         self.z_shape = (ddconfig.z_channels, z_sp, z_sp, z_sp)
 
         unet_params = dict(df_conf.unet.params)
-        unet_params.setdefault("use_spatial_transformer", True)
+        unet_params.setdefault("use_spatial_transformer", df_conf.model.params.conditioning_key != "concat")
         self.df = DiffusionUNet(unet_params, vq_conf=vq_conf, conditioning_key=df_conf.model.params.conditioning_key)
         self.df.to(self.device)
         self.init_diffusion_params(uc_scale=3., df_model_params=df_conf.model.params)
@@ -142,6 +154,10 @@ class SDFusionText2ShapeModel(BaseModel):
         self.x = input["sdf"]
         self.rel = input["rel"]
         self.uc_rel = input["uc"]
+        if self.df.conditioning_key == "concat":           # reference :246-248: the 4096-d vector becomes a latent channel
+            B = self.x.shape[0]
+            self.rel = self.rel.view(B, -1, *self.z_shape[1:])
+            self.uc_rel = self.uc_rel.view(B, -1, *self.z_shape[1:])
         if max_sample is not None:
             self.x, self.rel, self.uc_rel = self.x[:max_sample], self.rel[:max_sample], self.uc_rel[:max_sample]
         self.tocuda(var_names=["x"])
@@ -161,7 +177,8 @@ class SDFusionText2ShapeModel(BaseModel):
 
     def apply_model(self, x_noisy, t, cond, return_ids=False):
         if not isinstance(cond, dict):
-            cond = {"c_crossattn": cond if isinstance(cond, list) else [cond]}
+            key = "c_concat" if self.df_module.conditioning_key == "concat" else "c_crossattn"      # reference :281-283
+            cond = {key: cond if isinstance(cond, list) else [cond]}
         out = self.df(x_noisy, t, **cond)
         return out[0] if isinstance(out, tuple) and not return_ids else out
 

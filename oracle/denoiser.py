@@ -24,6 +24,15 @@ UNET_FULL = dict(image_size=16, in_channels=3, out_channels=3, model_channels=22
 UNET_TINY = dict(image_size=8, in_channels=3, out_channels=3, model_channels=32, num_res_blocks=1,
                  attention_resolutions=(4, 2), channel_mult=(1, 2, 3), num_heads=4, dims=3,
                  transformer_depth=1, context_dim=64)
+# config/sdfusion-txt2shape_concat.yaml:13-38: conditioning concatenated on the channel axis
+# (in_channels 4), AttentionBlock self-attention instead of the spatial transformer, `dims: 4` = Conv3d with isotropic
+# stride-2 resampling (ldm_diffusion_util.py:251-252, openai_model_3d.py:150-155, 188)
+UNET_CONCAT_FULL = dict(image_size=16, in_channels=4, out_channels=3, model_channels=224, num_res_blocks=2,
+                        attention_resolutions=(4, 2), channel_mult=(1, 2, 3), num_heads=8, dims=4,
+                        transformer_depth=1, context_dim=None, use_spatial_transformer=False)
+UNET_CONCAT_TINY = dict(image_size=8, in_channels=4, out_channels=3, model_channels=32, num_res_blocks=1,
+                        attention_resolutions=(4, 2), channel_mult=(1, 2, 3), num_heads=4, dims=4,
+                        transformer_depth=1, context_dim=None, use_spatial_transformer=False)
 # config/sdfusion-txt2shape.yaml:3-7
 DIFFUSION = dict(timesteps=1000, linear_start=0.00085, linear_end=0.012)
 
@@ -34,10 +43,14 @@ DIFFUSION = dict(timesteps=1000, linear_start=0.00085, linear_end=0.012)
 def unet_layout(cfg: dict) -> Dict[str, list]:
     """Block structure of UNet3DModel as lists of layer descriptors.
 
-    ("conv", cin, cout) | ("res", cin, cout) | ("st", ch, heads, d_head) | ("down", ch) | ("up", ch)
+    ("conv", cin, cout) | ("res", cin, cout) | ("st", ch, heads, d_head) | ("attn", ch, heads) | ("down", ch) | ("up", ch)
+    use_spatial_transformer=False (the concat variant) puts an AttentionBlock where the transformer would be
+    (openai_model_3d.py:593-598, 649-654, 690-697).
     """
     mc, mult, nrb = cfg["model_channels"], cfg["channel_mult"], cfg["num_res_blocks"]
     heads, attn_res = cfg["num_heads"], tuple(cfg["attention_resolutions"])
+    use_st = cfg.get("use_spatial_transformer", True)
+    att = (lambda c: ("st", c, heads, c // heads)) if use_st else (lambda c: ("attn", c, heads))
     inp: List[list] = [[("conv", cfg["in_channels"], mc)]]
     chans = [mc]
     ch, ds = mc, 1
@@ -46,14 +59,14 @@ def unet_layout(cfg: dict) -> Dict[str, list]:
             layers = [("res", ch, m * mc)]
             ch = m * mc
             if ds in attn_res:
-                layers.append(("st", ch, heads, ch // heads))   # legacy=False: dim_head = ch // num_heads (:584-591)
+                layers.append(att(ch))                          # legacy=False: dim_head = ch // num_heads (:584-591)
             inp.append(layers)
             chans.append(ch)
         if level != len(mult) - 1:
             inp.append([("down", ch)])
             chans.append(ch)
             ds *= 2
-    mid = [("res", ch, ch), ("st", ch, heads, ch // heads), ("res", ch, ch)]
+    mid = [("res", ch, ch), att(ch), ("res", ch, ch)]
     out: List[list] = []
     for level, m in list(enumerate(mult))[::-1]:
         for i in range(nrb + 1):
@@ -61,7 +74,7 @@ def unet_layout(cfg: dict) -> Dict[str, list]:
             layers = [("res", ch + ich, mc * m)]
             ch = mc * m
             if ds in attn_res:
-                layers.append(("st", ch, heads, ch // heads))
+                layers.append(att(ch))
             if level and i == nrb:
                 layers.append(("up", ch))
                 ds //= 2
@@ -112,6 +125,11 @@ def unet_param_shapes(cfg: dict, prefix: str = "diffusion_net.") -> Dict[str, Tu
             for n in ("norm1", "norm2", "norm3"):
                 norm(f"{tb}.{n}", inner)
             conv(name + ".proj_out", inner, ch, 1)
+        elif d[0] == "attn":                                  # AttentionBlock (openai_model_3d.py:324-352): Conv1d k=1
+            _, ch, heads = d
+            norm(name + ".norm", ch)
+            shapes[name + ".qkv.weight"] = (3 * ch, ch, 1); shapes[name + ".qkv.bias"] = (3 * ch,)
+            shapes[name + ".proj_out.weight"] = (ch, ch, 1); shapes[name + ".proj_out.bias"] = (ch,)
         elif d[0] == "down":
             conv(name + ".op", d[1], d[1], 3)
         elif d[0] == "up":
@@ -205,8 +223,25 @@ def spatial_transformer(sd, name: str, x: Tensor, context: Tensor, heads: int) -
     return _conv(sd, name + ".proj_out", t, padding=0) + x
 
 
-def _run_layers(sd, prefix: str, block: Sequence[tuple], h: Tensor, emb: Tensor, context: Tensor) -> Tensor:
-    """TimestepEmbedSequential.forward (openai_model_3d.py:119-127)."""
+def attention_block(sd, name: str, x: Tensor, heads: int) -> Tensor:
+    """AttentionBlock._forward (openai_model_3d.py:358-364) with QKVAttentionLegacy (:386-411): GroupNorm32 (eps 1e-5),
+    1x1 Conv1d qkv, heads split BEFORE the q/k/v split, scale ch^-1/4 on q and on k, softmax in fp32, 1x1 proj_out, + x."""
+    b, c = x.shape[:2]
+    xf = x.reshape(b, c, -1)
+    qkv = F.conv1d(_gn(sd, name + ".norm", xf, 1e-5), sd[name + ".qkv.weight"], sd[name + ".qkv.bias"])
+    bs, width, length = qkv.shape
+    ch = width // (3 * heads)
+    q, k, v = qkv.reshape(bs * heads, ch * 3, length).split(ch, dim=1)
+    scale = 1 / math.sqrt(math.sqrt(ch))
+    weight = torch.softmax(torch.einsum("bct,bcs->bts", q * scale, k * scale).float(), dim=-1)
+    a = torch.einsum("bts,bcs->bct", weight, v).reshape(bs, -1, length)
+    h = F.conv1d(a, sd[name + ".proj_out.weight"], sd[name + ".proj_out.bias"])
+    return (xf + h).reshape(x.shape)
+
+
+def _run_layers(sd, prefix: str, block: Sequence[tuple], h: Tensor, emb: Tensor, context: Tensor, dims: int = 3) -> Tensor:
+    """TimestepEmbedSequential.forward (openai_model_3d.py:119-127).  dims == 3 resamples H, W only; dims == 4 (the concat
+    variant's Conv3d alias) takes the isotropic branches (:154-155, :188)."""
     for li, d in enumerate(block):
         name = f"{prefix}.{li}"
         if d[0] == "conv":
@@ -215,29 +250,38 @@ def _run_layers(sd, prefix: str, block: Sequence[tuple], h: Tensor, emb: Tensor,
             h = res_block(sd, name, h, emb)
         elif d[0] == "st":
             h = spatial_transformer(sd, name, h, context, d[2])
+        elif d[0] == "attn":
+            h = attention_block(sd, name, h, d[2])
         elif d[0] == "down":                                  # Downsample, dims=3: stride (1,2,2) (:188-192)
-            h = _conv(sd, name + ".op", h, stride=(1, 2, 2))
+            h = _conv(sd, name + ".op", h, stride=(1, 2, 2) if dims == 3 else 2)
         elif d[0] == "up":                                    # Upsample, dims=3: (D, 2H, 2W) nearest (:150-157)
-            h = F.interpolate(h, (h.shape[2], h.shape[3] * 2, h.shape[4] * 2), mode="nearest")
+            if dims == 3:
+                h = F.interpolate(h, (h.shape[2], h.shape[3] * 2, h.shape[4] * 2), mode="nearest")
+            else:
+                h = F.interpolate(h, scale_factor=2, mode="nearest")
             h = _conv(sd, name + ".conv", h)
     return h
 
 
-def unet_forward(sd: Dict[str, Tensor], cfg: dict, x: Tensor, t: Tensor, context: Tensor,
-                 prefix: str = "diffusion_net.") -> Tensor:
-    """DiffusionUNet.forward (crossattn, network.py:28-30) -> UNet3DModel.forward (openai_model_3d.py:752-789)."""
+def unet_forward(sd: Dict[str, Tensor], cfg: dict, x: Tensor, t: Tensor, context: Optional[Tensor] = None,
+                 prefix: str = "diffusion_net.", c_concat: Optional[Tensor] = None) -> Tensor:
+    """DiffusionUNet.forward (network.py:24-30: 'crossattn' passes `context`, 'concat' runs the UNet on
+    cat([x, c_concat], dim=1)) -> UNet3DModel.forward (openai_model_3d.py:752-789)."""
     lay = unet_layout(cfg)
+    dims = cfg.get("dims", 3)
+    if c_concat is not None:
+        x = torch.cat([x, c_concat], dim=1)
     emb = timestep_embedding(t, cfg["model_channels"])
     emb = _lin(sd, prefix + "time_embed.2", F.silu(_lin(sd, prefix + "time_embed.0", emb)))
     hs = []
     h = x
     for bi, block in enumerate(lay["input"]):
-        h = _run_layers(sd, f"{prefix}input_blocks.{bi}", block, h, emb, context)
+        h = _run_layers(sd, f"{prefix}input_blocks.{bi}", block, h, emb, context, dims)
         hs.append(h)
-    h = _run_layers(sd, f"{prefix}middle_block", lay["middle"], h, emb, context)
+    h = _run_layers(sd, f"{prefix}middle_block", lay["middle"], h, emb, context, dims)
     for bi, block in enumerate(lay["output"]):
         h = torch.cat([h, hs.pop()], dim=1)
-        h = _run_layers(sd, f"{prefix}output_blocks.{bi}", block, h, emb, context)
+        h = _run_layers(sd, f"{prefix}output_blocks.{bi}", block, h, emb, context, dims)
     return _conv(sd, prefix + "out.2", F.silu(_gn(sd, prefix + "out.0", h, 1e-5)))
 
 
@@ -300,14 +344,16 @@ def ddim_schedule(sched, S: int, eta: float = 0.0):
 
 
 def p_sample_ddim(sd, cfg, dd, x: Tensor, c: Tensor, step: int, index: int, scale: float, uc: Optional[Tensor],
-                  noise: Optional[Tensor] = None):
-    """DDIMSampler.p_sample_ddim (samplers/ddim.py:182-244): CFG batch is [uncond; cond] (:206-210)."""
+                  noise: Optional[Tensor] = None, concat: bool = False):
+    """DDIMSampler.p_sample_ddim (samplers/ddim.py:182-244): CFG batch is [uncond; cond] (:206-210).  concat=True: c / uc are
+    (B, 1, D, H, W) volumes that apply_model routes to c_concat (sdfusion_txt2shape_model.py:281-283)."""
     b = x.shape[0]
     t = torch.full((b,), int(step), dtype=torch.long)
+    net = (lambda xx, tt, cc: unet_forward(sd, cfg, xx, tt, c_concat=cc)) if concat else (lambda xx, tt, cc: unet_forward(sd, cfg, xx, tt, cc))
     if uc is None or scale == 1.0:
-        e_t = unet_forward(sd, cfg, x, t, c)
+        e_t = net(x, t, c)
     else:
-        e_uc, e_c = unet_forward(sd, cfg, torch.cat([x] * 2), torch.cat([t] * 2), torch.cat([uc, c])).chunk(2)
+        e_uc, e_c = net(torch.cat([x] * 2), torch.cat([t] * 2), torch.cat([uc, c])).chunk(2)
         e_t = e_uc + scale * (e_c - e_uc)
     a_t = torch.full((b, 1, 1, 1, 1), float(dd["alphas"][index]))
     a_prev = torch.full((b, 1, 1, 1, 1), float(dd["alphas_prev"][index]))

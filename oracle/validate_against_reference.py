@@ -57,6 +57,19 @@ def ref_unet(cfg, seed):
     return m
 
 
+def ref_unet_concat(cfg, seed):
+    """config/sdfusion-txt2shape_concat.yaml: AttentionBlock variant, conditioning_key='concat' (SURVEY.md §8f rank 1)."""
+    from oracle import weights
+    DiffusionUNet, _, _ = import_reference()
+    params = {k: v for k, v in cfg.items()}
+    params["attention_resolutions"] = list(cfg["attention_resolutions"])
+    params["channel_mult"] = list(cfg["channel_mult"])
+    params.update(use_spatial_transformer=False, context_dim=None, use_checkpoint=False, legacy=False)
+    m = DiffusionUNet(params, conditioning_key="concat").eval()
+    weights.fill_module_(m, seed)
+    return m
+
+
 def ref_vqvae(cfg, seed):
     from oracle import weights
     _, VQVAE, _ = import_reference()
@@ -161,6 +174,18 @@ def main():
             ok &= _cmp("ddim_alphas", torch.tensor(dd["alphas"]), torch.as_tensor(al), 0)
             ok &= _cmp("ddim_alphas_prev", torch.tensor(dd["alphas_prev"]), torch.as_tensor(alp).float(), 0)
             ok &= _cmp("timestep_embedding", D.timestep_embedding(t, 224), U.timestep_embedding(t, 224), 0)
+
+    for tag, cfg in [("tiny", D.UNET_CONCAT_TINY)] + ([("full", D.UNET_CONCAT_FULL)] if args.full else []):
+        m = ref_unet_concat(cfg, seed=7)
+        shapes = D.unet_param_shapes(cfg)
+        ok &= _keys(f"unet_concat[{tag}]", shapes, m)
+        sd = Wt.synth_state_dict(shapes, seed=7)
+        r = cfg["image_size"]
+        g = torch.Generator().manual_seed(8)
+        x = torch.randn(2, 3, r, r, r, generator=g)
+        cc = torch.randn(2, cfg["in_channels"] - 3, r, r, r, generator=g)
+        t = torch.tensor([900, 4])
+        ok &= _cmp(f"unet_forward_concat[{tag}]", D.unet_forward(sd, cfg, x, t, c_concat=cc), m(x, t, c_concat=[cc]))
 
     for tag, cfg in [("tiny", V.VQ_TINY)] + ([("full", V.VQ_FULL)] if args.full else []):
         m = ref_vqvae(cfg, seed=3)

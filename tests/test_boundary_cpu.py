@@ -43,3 +43,13 @@ def test_unet_state_dict_keys_equal_reference_inventory(cfg):
         m = DiffusionUNet(dict(cfg, use_spatial_transformer=True, use_checkpoint=True, legacy=False), conditioning_key="crossattn")
     got = {k: tuple(v.shape) for k, v in m.state_dict().items()}
     assert got == D.unet_param_shapes(cfg)      # the inventory validate_against_reference.py pinned to the reference
+
+
+@pytest.mark.parametrize("cfg", [D.UNET_CONCAT_TINY, D.UNET_CONCAT_FULL], ids=["tiny", "full"])
+def test_concat_unet_state_dict_keys_equal_reference_inventory(cfg):
+    """The AttentionBlock variant (config/sdfusion-txt2shape_concat.yaml): norm / qkv (Conv1d) / proj_out keys."""
+    from commonscenes_b200.model.networks.diffusion_networks.network import DiffusionUNet
+    with torch.device("meta"):
+        m = DiffusionUNet(dict(cfg, use_checkpoint=True, legacy=False), conditioning_key="concat")
+    got = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert got == D.unet_param_shapes(cfg)

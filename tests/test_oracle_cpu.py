@@ -31,6 +31,16 @@ def test_unet_forward_matches_reference_golden(tag, cfg):
     _close(eps, g["eps"])
 
 
+@pytest.mark.parametrize("tag,cfg", [("tiny", D.UNET_CONCAT_TINY), ("full", D.UNET_CONCAT_FULL)])
+def test_concat_unet_forward_matches_reference_golden(tag, cfg):
+    """AttentionBlock / concat-conditioning denoiser vs the reference module's own output."""
+    g = _load(f"unet_concat_{tag}.npz")
+    sd = Wt.synth_state_dict(D.unet_param_shapes(cfg), int(g["weight_seed"]))
+    with torch.no_grad():
+        eps = D.unet_forward(sd, cfg, torch.tensor(g["x"]), torch.tensor(g["t"]), c_concat=torch.tensor(g["c_concat"]))
+    _close(eps, g["eps"])
+
+
 def test_unet_inventory_counts():
     shapes = D.unet_param_shapes(D.UNET_FULL)
     assert len(shapes) == 496                                            # SURVEY.md §8b [probe]
