@@ -44,6 +44,17 @@ def main():
             rows.append((name, ms))
             print(f"torch eager UNet forward, batch 64, {name}: {ms:.1f} ms -> {1000 / ms:.2f} guided steps/s "
                   f"({64 * 557.6 / ms:.0f} TFLOP/s)", flush=True)
+    if "--concat" in sys.argv:       # the concat-conditioning variant (AttentionBlock, in_channels 4, isotropic resampling)
+        ccfg = D.UNET_CONCAT_FULL
+        csd = {k: v.cuda() for k, v in Wt.synth_state_dict(D.unet_param_shapes(ccfg), 111).items()}
+        cc = torch.randn(B, 1, 16, 16, 16, generator=g).cuda()
+        with torch.device("cuda"), torch.no_grad():
+            for name, tf32, ac in (("fp32 (TF32 convs+matmuls)", True, False), ("bf16 autocast", True, True)):
+                torch.backends.cuda.matmul.allow_tf32 = tf32
+                torch.backends.cudnn.allow_tf32 = tf32
+                with torch.autocast("cuda", dtype=torch.bfloat16, enabled=ac):
+                    ms = timed(lambda: D.unet_forward(csd, ccfg, x, t, c_concat=cc), 3)
+                print(f"torch eager CONCAT UNet forward, batch 64, {name}: {ms:.1f} ms -> {1000 / ms:.2f} guided steps/s", flush=True)
     if "--train" in sys.argv:
         B = 32
         sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}

@@ -77,3 +77,25 @@ def test_cfg5_ancestral_sampling_ten_objects(model):
     assert float((z - z3).norm() / z.norm()) > 0.2
     with pytest.raises(ValueError):
         model.rel2shape(data, sampler="plms")
+
+
+def test_concat_variant_rel2shape_through_the_wrapper():
+    """config/v2_full_concat.yaml: rel_mlp emits 4096-d vectors that set_input views as one extra 16^3 latent channel
+    (sdfusion_txt2shape_model.py:246-248); sampling then runs the AttentionBlock denoiser with c_concat."""
+    from commonscenes_b200.model.sdfusion_txt2shape_model import SDFusionText2ShapeModel, default_opt
+    torch.manual_seed(112)
+    m = SDFusionText2ShapeModel(default_opt(device="cuda", conditioning_key="concat"))
+    assert m.df.conditioning_key == "concat" and m.df.diffusion_net.in_channels == 4
+    with torch.no_grad():
+        for p in m.df.parameters():
+            if p.dim() > 1 and float(p.abs().max()) == 0:
+                torch.nn.init.normal_(p, std=0.02)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    n = 4
+    data = {"sdf": torch.zeros(n, 1, 64, 64, 64, device="cuda"), "rel": torch.randn(n, 1, 4096, device="cuda", generator=g),
+            "uc": torch.randn(n, 1, 4096, device="cuda", generator=g)}
+    sdf, z = model_out = m.rel2shape(data, ddim_steps=10, uc_scale=3.0, seed=7, return_latent=True)
+    assert sdf.shape == (n, 1, 64, 64, 64) and z.shape == (n, 3, 16, 16, 16) and torch.isfinite(sdf).all()
+    sub = {k: v[1:3].contiguous() for k, v in data.items()}                      # object independence
+    _, z_sub = m.rel2shape(sub, ddim_steps=10, uc_scale=3.0, seed=7, return_latent=True)
+    assert float((z[1:3] - z_sub).norm() / z_sub.norm()) < 0.1
