@@ -46,6 +46,13 @@ def timed(fn, reps=3):
 for _ in range(2):
     loss, _ = step.step(z, ctx)
 print("loss after warm-up:", loss.item())
+if "--ncu" in sys.argv:      # one eager training step between cudaProfilerStart/Stop (ncu --profile-from-start off)
+    torch.cuda.synchronize()
+    torch.cuda.profiler.start()
+    step.step(z, ctx)
+    torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
+    sys.exit(0)
 ms_eager, _ = timed(lambda: step.step(z, ctx), reps=3)
 print(f"eager train step B={B}: {ms_eager:.1f} ms")
 step.capture(B, 1280)
