@@ -421,7 +421,7 @@ class UNet3DModel(nn.Module):
             tr = self._trainer_obj = UNetTrainer(self)
         return tr
 
-    def forward(self, x, timesteps=None, context=None, y=None, context_vecs=None, **kwargs):
+    def forward(self, x, timesteps=None, context=None, y=None, context_vecs=None, shared_prefix=False, **kwargs):
         """x: (B, C, D, H, W) fp32 NCDHW, timesteps: (B,) int64, context: (B, 1, context_dim) -> eps (B, C, D, H, W).
 
         With autograd enabled and trainable parameters (or a context that requires grad) the result carries a grad_fn:
@@ -429,7 +429,9 @@ class UNet3DModel(nn.Module):
         `context`, as the reference's autograd does (no gradient is produced for x: the reference never asks for it).
 
         Extensions: `context_vecs` = a cached context_vectors(context) result; x may hold B/r samples, in which
-        case sample b reads x[b % (B/r)] (a guided sampler passes x once for [uncond; cond]).
+        case sample b reads x[b % (B/r)] (a guided sampler passes x once for [uncond; cond]); `shared_prefix=True`
+        additionally promises timesteps[b] == timesteps[b % (B/r)], so the layers in front of the first cross-attention are
+        evaluated once per distinct x (see _forward_inference).
         """
         assert (y is not None) == (self.num_classes is not None), "must specify y if and only if the model is class-conditional"
         if torch.is_grad_enabled() and context_vecs is None and context is not None and \
@@ -441,12 +443,13 @@ class UNet3DModel(nn.Module):
             raise NotImplementedError("gradients through the AttentionBlock (concat-conditioning) denoiser are not built: call it "
                                       "under torch.no_grad() (sampling); training covers the cross-attention denoiser of v2_full")
         with torch.no_grad():
-            return self._forward_inference(x, timesteps, context, context_vecs)
+            return self._forward_inference(x, timesteps, context, context_vecs, shared_prefix)
 
-    def _forward_inference(self, x, timesteps, context, context_vecs):
+    def _forward_inference(self, x, timesteps, context, context_vecs, shared_prefix=False):
         _lib.require_device()
         pk = self._ensure_packed()
         B = timesteps.shape[0]
+        Bs = x.shape[0]
         x = x.float().contiguous()
         t_emb = timestep_embedding(timesteps, self.model_channels)
         w0, b0, w2, b2 = pk["te"]
@@ -463,13 +466,30 @@ class UNet3DModel(nn.Module):
             arena = self._arenas[B] = StatArena(x.device, B * pk["stat_channels"] * 2)
         arena.reset()
 
+        # Guided sampling evaluates [uncond; cond] on the SAME x and t: every layer before the first cross-attention sees
+        # identical inputs in both halves (the stem, the two level-0 ResBlocks, the first Downsample and the ResBlock in front
+        # of the first transformer: 11.5 % of the FLOPs).  With shared_prefix those run once on the Bs = B / r samples of x
+        # and their outputs (including the encoder skips) are replicated when the conditioning first enters -- bit-identical
+        # to evaluating them twice.  The caller vouches that timesteps[b] == timesteps[b % Bs] (the samplers build t that way).
+        state = {"shared": bool(shared_prefix) and Bs < B and B % Bs == 0 and pk["ca_w"] is not None and not multi}
+        hs: List[Act] = []
+
+        def replicate(a: Act) -> Act:
+            r = B // Bs
+            return Act(a.t.repeat(r, 1, 1, 1, 1), a.stat.repeat(r, 1, 1))
+
         def run_block(block, entries, h, skip=None):
             for layer, e in zip(block, entries):
+                nb = Bs if state["shared"] else B
                 if e["kind"] == "res":
                     off, n = e["emb"]
-                    h = layer.run(e["pk"], h, emb_vecs[:, off:off + n], arena, skip=skip)
+                    h = layer.run(e["pk"], h, emb_vecs[:nb, off:off + n], arena, skip=skip)
                     skip = None
                 elif e["kind"] == "st":
+                    if state["shared"]:           # the conditioning enters here: leave the shared prefix
+                        h = replicate(h)
+                        hs[:] = [replicate(a) for a in hs]
+                        state["shared"] = False
                     if multi:    # generic cross-attention over all context tokens (attention.py:172-219)
                         h = layer.run(e["pk"], h, [None] * len(e["ca"]), arena, context=context)
                     else:
@@ -477,15 +497,14 @@ class UNet3DModel(nn.Module):
                 elif e["kind"] in ("resample", "attn"):
                     h = layer.run(e["pk"], h, arena)
                 else:
-                    col = ops.im2col_small(h, batch=B, kp=e["pk"]["kp"])
+                    col = ops.im2col_small(h, batch=nb, kp=e["pk"]["kp"])
                     S = col.shape[1] * col.shape[2] * col.shape[3]
-                    h = _with_stats(arena, lambda st: ops.linear_tokens(col, e["pk"]["w"], bias=e["pk"]["b"], stat_sum=st), B,
+                    h = _with_stats(arena, lambda st: ops.linear_tokens(col, e["pk"]["w"], bias=e["pk"]["b"], stat_sum=st), nb,
                                     layer.out_channels, S)
             return h
 
         entries = pk["blocks"]
         n_in = len(self.input_blocks)
-        hs: List[Act] = []
         h = x
         for i, block in enumerate(self.input_blocks):
             h = run_block(block, entries[i], h)

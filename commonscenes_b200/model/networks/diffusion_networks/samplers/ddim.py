@@ -64,7 +64,9 @@ class DDIMSampler(object):
         if concat is not None:          # x_in = cat([x (repeated for [uncond; cond]), c_concat], dim=1)
             r = concat.shape[0] // x.shape[0]
             x = torch.cat([x.repeat(r, 1, 1, 1, 1) if r > 1 else x, concat], dim=1)
-        call = (lambda a, b, c: unet(a, b)) if concat is not None else (lambda a, b, c: unet(a, b, context_vecs=c))
+        # [uncond; cond] share x and t (t_dev is one value, or cat([t] * 2) in p_sample_ddim): shared conditioning-free prefix
+        shared = concat is None and x.shape[0] < t_dev.shape[0]
+        call = (lambda a, b, c: unet(a, b)) if concat is not None else (lambda a, b, c: unet(a, b, context_vecs=c, shared_prefix=shared))
         if not self.use_cuda_graph:
             return call(x, t_dev, ca_vecs)
         unet._ensure_packed()
