@@ -73,6 +73,7 @@ class UNetTrainer:
         self._dpk = None
         self._scratch = None
         self._stat_ws = {}
+        self._zero_arena = None
 
     # ------------------------------------------------------------------------------------------
     # packs
@@ -85,7 +86,7 @@ class UNetTrainer:
         d: Dict[nn.Parameter, torch.Tensor] = {}
 
         def dg(p):
-            d[p] = ops_bwd.pack_dgrad_weight(p if p.dim() == 5 else p.reshape(p.shape[0], p.shape[1], 1, 1, 1))
+            d[p] = ops_bwd.pack_dgrad_weight(p if p.dim() == 5 else p.reshape(p.shape[0], p.shape[1], 1, 1, 1), owner=p)
 
         biggest = 0
         for block in u._blocks():
@@ -155,8 +156,7 @@ class UNetTrainer:
     def _colsums(self, dy):
         """fp32 (B, C, 2) per-sample channel sums of a bf16 channels-last tensor (component 0 = sum)."""
         B, C = dy.shape[0], dy.shape[-1]
-        st = torch.zeros((B, C, 2), dtype=torch.float32, device=dy.device)
-        return ops.groupnorm_stats(dy, st)
+        return ops.groupnorm_stats(dy, ops_bwd.zero_f32((B, C, 2), dy.device))
 
     def _bias_grad(self, sink, param, dy, sums=None):
         if sums is None and dy.shape[-1] > 2048:       # cs_groupnorm_stats handles <= 2048 channels per call
@@ -300,6 +300,15 @@ class UNetTrainer:
     # ------------------------------------------------------------------------------------------
     def backward(self, tape: dict, d_eps: torch.Tensor, sink: Optional[GradSink] = None, need_dcontext: bool = True,
                  on_block_done=None):
+        """See _backward_impl.  Runs it inside the trainer's ZeroArena: the small zero-initialised reduction buffers of the
+        whole backward come from ONE memset."""
+        if self._zero_arena is None or self._zero_arena.buf.device != d_eps.device:
+            self._zero_arena = ops_bwd.ZeroArena(d_eps.device)
+        with self._zero_arena:
+            return self._backward_impl(tape, d_eps, sink, need_dcontext, on_block_done)
+
+    def _backward_impl(self, tape: dict, d_eps: torch.Tensor, sink: Optional[GradSink] = None, need_dcontext: bool = True,
+                       on_block_done=None):
         """d_eps: gradient wrt the fp32 NCDHW output of forward_train.  Accumulates every parameter gradient into `sink`
         (created if None) and returns (sink, d_context (B, 1, context_dim) fp32 or None).
 

@@ -17,16 +17,63 @@ from .ops import _check_act, _pad64, _pad_k, _ptr, _stream, conv3d
 
 
 # ----------------------------------------------------------------------------------------------
+# zero-initialised fp32 scratch (reduction targets of the backward kernels)
+# ----------------------------------------------------------------------------------------------
+class ZeroArena:
+    """One fp32 buffer zeroed by ONE memset per training step, from which the many small accumulation targets of the backward
+    (GroupNorm reduction pairs, per-sample channel sums for bias gradients) are carved -- instead of ~330 tiny fill launches."""
+    current: Optional["ZeroArena"] = None
+
+    def __init__(self, device, numel: int = 24 << 20):
+        self.buf = torch.zeros(numel, dtype=torch.float32, device=device)
+        self.off = 0
+
+    def reset(self):
+        self.buf.zero_()
+        self.off = 0
+
+    def take(self, shape):
+        n = 1
+        for d in shape:
+            n *= int(d)
+        n4 = (n + 3) // 4 * 4
+        if self.off + n4 > self.buf.numel():
+            return None
+        v = self.buf[self.off:self.off + n].view(shape)
+        self.off += n4
+        return v
+
+    def __enter__(self):
+        self.reset()
+        ZeroArena.current = self
+        return self
+
+    def __exit__(self, *exc):
+        ZeroArena.current = None
+
+
+def zero_f32(shape, device) -> torch.Tensor:
+    """A zeroed fp32 tensor: a slice of the active ZeroArena when there is one (and it has room), else torch.zeros."""
+    a = ZeroArena.current
+    if a is not None and a.buf.device == torch.device(device):
+        v = a.take(shape)
+        if v is not None:
+            return v
+    return torch.zeros(shape, dtype=torch.float32, device=device)
+
+
+# ----------------------------------------------------------------------------------------------
 # GEMM-class gradients
 # ----------------------------------------------------------------------------------------------
-def pack_dgrad_weight(w: torch.Tensor) -> torch.Tensor:
+def pack_dgrad_weight(w: torch.Tensor, owner=None) -> torch.Tensor:
     """(Cout, Cin, kd, kh, kw) fp32 -> packed bf16 (Cin, taps, pad64(Cout)) with the filter flipped: the weight with which
     cs_conv3d maps dY (Cout channels) to dX (Cin channels) for a stride-1 convolution."""
     co, ci = w.shape[0], w.shape[1]
     wd = w.detach()
     if wd.is_cuda and wd.dtype == torch.float32 and wd.is_contiguous():
         taps = wd.numel() // (co * ci)
-        out = torch.zeros((ci, taps, _pad64(co)), dtype=torch.bfloat16, device=w.device)
+        from .ops import _pack_buffer
+        out = _pack_buffer("dgrad", owner if owner is not None else w, (ci, taps, _pad64(co)), w.device)
         check(_lib.load().cs_pack_weight(wd.data_ptr(), co, ci, taps, ci, None, out.data_ptr(), _stream()), "cs_pack_weight")
         return out
     wt = wd.reshape(co, ci, -1).flip(2).permute(1, 2, 0)     # (Cin, taps flipped, Cout)
@@ -120,7 +167,7 @@ def groupnorm_bwd(x: torch.Tensor, stat: torch.Tensor, gamma: torch.Tensor, beta
     if (dB, dD * dH * dW, dC) != (B, S, Ct):
         raise _lib.CsError("groupnorm_bwd: dy must cover all channels of the normalised tensor")
     st = _stream()
-    red = torch.zeros((B, Ct, 2), dtype=torch.float32, device=x.device)
+    red = zero_f32((B, Ct, 2), x.device)
     g, bta = _ptr(gamma), _ptr(beta)
     srcs = [(x, C1, p1, 0, extra)] + ([(x2, C2, p2, C1, extra2)] if x2 is not None else [])
     for t, c, p, off, _ in srcs:
