@@ -53,12 +53,12 @@ __global__ void gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ x, int S,
                                      const float* __restrict__ gamma, const float* __restrict__ beta, int groups, float eps,
                                      int act, float* __restrict__ red, int vox_per_cta) {
   __shared__ float g_mean[64], g_rstd[64];
-  extern __shared__ float sred[];   // [cv * 8][2] partial sums per channel
+  extern __shared__ float sred[];   // [R][C][2] per-row-slot partial sums (plain stores + a fixed-order sum: shared-memory
+                                    // float atomics compile to CAS loops, which dominated this kernel)
   const int b = blockIdx.y;
   const int Ct = C1 + C2;
   const int cpg = Ct / groups;
   gn_group_stats(b, S, cpg, stat1, C1, stat2, C2, eps, g_mean, g_rstd, groups);
-  for (int i = threadIdx.x; i < C * 2; i += blockDim.x) sred[i] = 0.f;
   __syncthreads();
   const int cv = C >> 3;
   const int R = blockDim.x / cv;
@@ -95,15 +95,17 @@ __global__ void gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ x, int S,
         s1[2 * j + 1] += z1; s2[2 * j + 1] += z1 * h1;
       }
     }
+    float* mine = sred + (static_cast<long long>(r) * C + v * 8) * 2;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      atomicAdd(&sred[(v * 8 + j) * 2], s1[j]);
-      atomicAdd(&sred[(v * 8 + j) * 2 + 1], s2[j]);
-    }
+    for (int j = 0; j < 8; j += 2)
+      *reinterpret_cast<float4*>(mine + j * 2) = make_float4(s1[j], s2[j], s1[j + 1], s2[j + 1]);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < C * 2; i += blockDim.x)
-    atomicAdd(red + (static_cast<long long>(b) * Ct + ch_off) * 2 + i, sred[i]);
+  for (int i = threadIdx.x; i < C * 2; i += blockDim.x) {
+    float t = 0.f;
+    for (int rr = 0; rr < R; ++rr) t += sred[rr * C * 2 + i];
+    atomicAdd(red + (static_cast<long long>(b) * Ct + ch_off) * 2 + i, t);
+  }
 }
 
 // pass 2: dx = rstd * (gamma * dz - mean_g(gamma dz) - xhat * mean_g(gamma dz xhat)) [+ extra]
@@ -202,7 +204,9 @@ int gn_bwd_launch(const void* x, int B, int S, int C, int pitch, int ch_off, con
   const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x);
   const __nv_bfloat16* db = reinterpret_cast<const __nv_bfloat16*>(dy);
   if (pass == 0) {
-    gn_bwd_reduce_kernel<<<dim3(splits, B), threads, C * 2 * sizeof(float), st>>>(
+    const size_t sm = static_cast<size_t>(R) * C * 2 * sizeof(float);
+    if (sm > 48 * 1024) return set_error(CS_ERR_UNSUPPORTED, "groupnorm_bwd: more than 6144 channels");
+    gn_bwd_reduce_kernel<<<dim3(splits, B), threads, sm, st>>>(
         xb, S, C, pitch, ch_off, db, dy_pitch, dy_off, stat1, C1, stat2, stat2 ? C2 : 0, gamma, beta, groups, eps, act, red, vox);
   } else {
     if (dx_pitch % 8 || (extra && extra_pitch % 8)) return set_error(CS_ERR_INVALID, "groupnorm_bwd: output pitch % 8");
@@ -242,12 +246,14 @@ __global__ void __launch_bounds__(256)
 layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, long long M, int C, int pitch, const __nv_bfloat16* __restrict__ dy,
                      int dy_pitch, const float* __restrict__ gamma, float eps, const __nv_bfloat16* __restrict__ extra,
                      int extra_pitch, __nv_bfloat16* __restrict__ dx, int dx_pitch, float* __restrict__ dgamma,
-                     float* __restrict__ dbeta) {
-  extern __shared__ float sacc[];   // [2][C]
+                     float* __restrict__ dbeta, int warp_slots) {
+  extern __shared__ float sacc[];   // [2][C], or [warps][2][C] when warp_slots
   const int lane = threadIdx.x & 31;
   const int cv = C >> 3;
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sacc[i] = 0.f;
-  __syncthreads();
+  if (!warp_slots) {
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sacc[i] = 0.f;
+    __syncthreads();
+  }
   float g[VPL][8], ag[VPL][8], ab[VPL][8];
 #pragma unroll
   for (int k = 0; k < VPL; ++k)
@@ -325,6 +331,27 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, long long M, int C, in
       }
     }
   }
+  if (warp_slots) {   // one [2][C] slot per warp, plain stores, fixed-order sum (shared float atomics are CAS loops)
+    float* mine = sacc + static_cast<long long>(threadIdx.x >> 5) * 2 * C;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = (lane + 32 * k) * 8 + j;
+        if (c < C) {
+          mine[c] = ag[k][j];
+          mine[C + c] = ab[k][j];
+        }
+      }
+    __syncthreads();
+    const int nw = blockDim.x >> 5;
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+      float t = 0.f;
+      for (int w = 0; w < nw; ++w) t += sacc[w * 2 * C + i];
+      atomicAdd((i < C ? dgamma : dbeta - C) + i, t);
+    }
+    return;
+  }
 #pragma unroll
   for (int k = 0; k < VPL; ++k)
 #pragma unroll
@@ -352,12 +379,13 @@ int layernorm_bwd_launch(const void* x, long long M, int C, int pitch, const voi
   long long blocks = (M + 7) / 8;
   const long long cap = 4ll * num_sms();
   if (blocks > cap) blocks = cap;
-  const size_t sm = 2 * C * sizeof(float);
+  const int warp_slots = (8 * 2 * C * sizeof(float) <= 48 * 1024) ? 1 : 0;
+  const size_t sm = (warp_slots ? 8 : 1) * 2 * C * sizeof(float);
 #define CS_LNB(V)                                                                                                        \
   layernorm_bwd_kernel<V><<<(int)blocks, 256, sm, st>>>(                                                                 \
       reinterpret_cast<const __nv_bfloat16*>(x), M, C, pitch, reinterpret_cast<const __nv_bfloat16*>(dy), dy_pitch, gamma, \
       eps, reinterpret_cast<const __nv_bfloat16*>(extra), extra_pitch, reinterpret_cast<__nv_bfloat16*>(dx), dx_pitch,   \
-      dgamma, dbeta)
+      dgamma, dbeta, warp_slots)
   switch (vpl) {
     case 1: CS_LNB(1); break;
     case 2: CS_LNB(2); break;
