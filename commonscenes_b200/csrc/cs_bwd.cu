@@ -600,12 +600,15 @@ int cast_rows_launch(const float* in, int in_pitch, long long M, int C, void* ou
 // ------------------------------------------------------------------------------------------------
 __global__ void sgemm_small_kernel(const float* __restrict__ A, int lda, int ta, const float* __restrict__ Bm, int ldb, int tb,
                                    float* __restrict__ Cm, int ldc, int M, int N, int K, int accumulate,
-                                   const float* __restrict__ silu_pre, int ld_pre) {
+                                   const float* __restrict__ silu_pre, int ld_pre, int k_chunk) {
   __shared__ float sA[32][33], sB[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8 threads, each 4 rows of a 32 x 32 tile
   const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int k0 = 0; k0 < K; k0 += 32) {
+  const int k_begin = blockIdx.z * k_chunk;            // split-K: long reductions with few output tiles (the per-step
+  const int k_end = min(K, k_begin + k_chunk);         // embedding / context GEMMs) are spread over gridDim.z CTAs
+  K = k_end;
+  for (int k0 = k_begin; k0 < k_end; k0 += 32) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int r = ty + 8 * i;
@@ -641,15 +644,29 @@ __global__ void sgemm_small_kernel(const float* __restrict__ A, int lda, int ta,
       float v = acc[i];
       if (silu_pre) v *= act_grad(silu_pre[static_cast<long long>(m) * ld_pre + n], CS_ACT_SILU);
       float* c = Cm + static_cast<long long>(m) * ldc + n;
-      *c = accumulate ? *c + v : v;
+      if (gridDim.z > 1) atomicAdd(c, v);              // the host zeroed C when it is not an accumulation
+      else *c = accumulate ? *c + v : v;
     }
   }
 }
 int sgemm_small_launch(const float* A, int lda, int ta, const float* Bm, int ldb, int tb, float* Cm, int ldc, int M, int N, int K,
                        int accumulate, const float* silu_pre, int ld_pre, cudaStream_t st) {
   if (M <= 0 || N <= 0 || K <= 0) return CS_OK;
-  sgemm_small_kernel<<<dim3((N + 31) / 32, (M + 31) / 32), 256, 0, st>>>(A, lda, ta, Bm, ldb, tb, Cm, ldc, M, N, K, accumulate,
-                                                                       silu_pre, ld_pre);
+  const int tiles = ((N + 31) / 32) * ((M + 31) / 32);
+  int splits = 1;
+  if (tiles < 2 * num_sms() && K >= 1024) {
+    splits = (4 * num_sms() + tiles - 1) / tiles;
+    if (splits > (K + 255) / 256) splits = (K + 255) / 256;     // at least 256 of K per CTA
+    if (splits < 1) splits = 1;
+  }
+  int k_chunk = ((K + splits - 1) / splits + 31) / 32 * 32;
+  splits = (K + k_chunk - 1) / k_chunk;
+  if (splits > 1 && !accumulate) {
+    cudaError_t e = cudaMemset2DAsync(Cm, static_cast<size_t>(ldc) * sizeof(float), 0, static_cast<size_t>(N) * sizeof(float), M, st);
+    if (e != cudaSuccess) return set_cuda_error(e, "sgemm_small: memset");
+  }
+  sgemm_small_kernel<<<dim3((N + 31) / 32, (M + 31) / 32, splits), 256, 0, st>>>(A, lda, ta, Bm, ldb, tb, Cm, ldc, M, N, K,
+                                                                               accumulate, silu_pre, ld_pre, k_chunk);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error(e, "sgemm_small: launch");
   count_launch();

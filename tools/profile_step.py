@@ -1,4 +1,5 @@
-"""One eager UNet evaluation at batch 64 between cudaProfilerStart/Stop (for `ncu --profile-from-start off`)."""
+"""One eager guided UNet evaluation ([uncond; cond] = batch 64 for 32 objects, shared conditioning-free prefix: exactly what
+bench.py's timed steps replay) between cudaProfilerStart/Stop (for `ncu --profile-from-start off`)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -15,9 +16,9 @@ x = torch.randn(objs, 3, 16, 16, 16, device="cuda")
 t = torch.full((2 * objs,), 500, dtype=torch.int64, device="cuda")
 ca = unet.context_vectors(torch.randn(2 * objs, 1, 1280, device="cuda"))
 for _ in range(2):
-    unet(x, t, context_vecs=ca)
+    unet(x, t, context_vecs=ca, shared_prefix=True)
 torch.cuda.synchronize()
 torch.cuda.profiler.start()
-unet(x, t, context_vecs=ca)
+unet(x, t, context_vecs=ca, shared_prefix=True)
 torch.cuda.synchronize()
 torch.cuda.profiler.stop()
