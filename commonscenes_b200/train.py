@@ -41,6 +41,42 @@ def make_buckets(sizes: List[int], limit: int) -> List[tuple]:
     return buckets
 
 
+def flat_optimizer_state_dict(params, offsets, flat_m, flat_v, step: int, hp: dict) -> dict:
+    """The flat AdamW moments in torch.optim.AdamW.state_dict() layout -- what the reference checkpoints hold
+    (SDFusionText2ShapeModel.save(save_opt=True): sdfusion_txt2shape_model.py:636-650; VAE.save: VAE.py:334-340) -- so a run
+    can move between torch's optimizer and the native step in either direction."""
+    state = {}
+    for i, p in enumerate(params):
+        off, n = offsets[p], p.numel()
+        state[i] = {"step": torch.tensor(float(step)), "exp_avg": flat_m[off:off + n].view(p.shape).clone(),
+                    "exp_avg_sq": flat_v[off:off + n].view(p.shape).clone()}
+    group = dict(lr=hp["lr"], betas=tuple(hp["betas"]), eps=hp["eps"], weight_decay=hp["weight_decay"], amsgrad=False,
+                 maximize=False, foreach=None, capturable=False, differentiable=False, fused=None, decoupled_weight_decay=True,
+                 params=list(range(len(params))))
+    return {"state": state, "param_groups": [group]}
+
+
+def load_flat_optimizer_state(sd: dict, params, offsets, flat_m, flat_v) -> int:
+    """Inverse of flat_optimizer_state_dict for a torch.optim.AdamW state dict over the SAME parameter order; returns the
+    step count (all parameters of a group share it).  Parameters without state (never stepped) keep zero moments."""
+    ids = [i for g in sd["param_groups"] for i in g["params"]]
+    if len(ids) != len(params):
+        raise ValueError(f"optimizer state covers {len(ids)} parameters, the model has {len(params)}")
+    step = 0
+    flat_m.zero_(); flat_v.zero_()
+    for i, p in zip(ids, params):
+        st = sd["state"].get(i)
+        if st is None:
+            continue
+        off, n = offsets[p], p.numel()
+        if tuple(st["exp_avg"].shape) != tuple(p.shape):
+            raise ValueError(f"optimizer state {i}: shape {tuple(st['exp_avg'].shape)} vs parameter {tuple(p.shape)}")
+        flat_m[off:off + n].view(p.shape).copy_(st["exp_avg"])
+        flat_v[off:off + n].view(p.shape).copy_(st["exp_avg_sq"])
+        step = max(step, int(float(st["step"])))
+    return step
+
+
 class DenoiserTrainStep:
     def __init__(self, diff_model, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.01,
                  max_grad_norm: float = 5.0, loss_scale: float = 100.0, group: Optional[dist.ProcessGroup] = None,
@@ -138,10 +174,25 @@ class DenoiserTrainStep:
         return self.loss, d_ctx
 
     # ------------------------------------------------------------------------------------------
+    def optimizer_state_dict(self) -> dict:
+        """torch.optim.AdamW-compatible state (load it with `torch.optim.AdamW(df.parameters()).load_state_dict`)."""
+        hp = dict(lr=self.lr, betas=self.betas, eps=self.eps, weight_decay=self.weight_decay)
+        return flat_optimizer_state_dict(self.params, self.offsets, self.flat_m, self.flat_v, self.step_count, hp)
+
+    def load_optimizer_state_dict(self, sd: dict) -> None:
+        """Resume from a torch.optim.AdamW state dict (e.g. the 'opt' entry of a reference df_*.pth checkpoint)."""
+        self.step_count = load_flat_optimizer_state(sd, self.params, self.offsets, self.flat_m, self.flat_v)
+        self.step_dev.fill_(self.step_count)
+        g = sd["param_groups"][0]
+        self.lr, self.betas, self.eps, self.weight_decay = g["lr"], tuple(g["betas"]), g["eps"], g["weight_decay"]
+
+    # ------------------------------------------------------------------------------------------
     def capture(self, batch: int, context_dim: int, need_dcond: bool = False, warmup: int = 2) -> None:
         """Capture the whole iteration (weight re-pack, forward, backward, all-reduce, clip, AdamW) into ONE CUDA graph for
         a fixed batch size: ~1200 launches per step are then replayed without host work.  The warm-up iterations needed
-        before capture run on zeros and are rolled back (parameters, moments and step counter are restored)."""
+        before capture run on zeros and are rolled back (parameters, moments and step counter are restored).  lr / betas /
+        weight decay are baked into the graph as kernel arguments: re-capture after changing them (an LR schedule that
+        changes every step should use step(), or a piecewise-constant schedule with one capture per plateau)."""
         dev = self.flat_p.device
         zs = self.model.z_shape if hasattr(self.model, "z_shape") else (3, 16, 16, 16)
         self._gz = torch.zeros((batch,) + tuple(zs), dtype=torch.float32, device=dev)
@@ -200,6 +251,7 @@ class _FlatGroup:
         total = sum(sizes)
         self.flat_p, self.flat_g, self.flat_m, self.flat_v = (torch.zeros(total, dtype=torch.float32, device=dev) for _ in range(4))
         self.views: Dict[nn.Parameter, torch.Tensor] = {}
+        self.offsets: Dict[nn.Parameter, int] = {}
         off = 0
         with torch.no_grad():
             for p, n in zip(params, sizes):
@@ -207,9 +259,16 @@ class _FlatGroup:
                 v.copy_(p.data)
                 p.data = v
                 self.views[p] = self.flat_g[off:off + p.numel()].view(p.shape)
+                self.offsets[p] = off
                 off += n
         self.sumsq = torch.zeros((), dtype=torch.float32, device=dev)
         self.step_dev = torch.zeros((), dtype=torch.int32, device=dev)
+
+    def optimizer_state_dict(self, hp: dict) -> dict:
+        return flat_optimizer_state_dict(self.params, self.offsets, self.flat_m, self.flat_v, int(self.step_dev.item()), hp)
+
+    def load_optimizer_state_dict(self, sd: dict) -> None:
+        self.step_dev.fill_(load_flat_optimizer_state(sd, self.params, self.offsets, self.flat_m, self.flat_v))
 
     def clip_and_step(self, lr, betas, eps, weight_decay, max_norm, grad_scale):
         self.step_dev.add_(1)
