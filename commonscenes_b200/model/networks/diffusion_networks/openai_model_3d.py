@@ -476,7 +476,7 @@ class UNet3DModel(nn.Module):
 
         def replicate(a: Act) -> Act:
             r = B // Bs
-            return Act(a.t.repeat(r, 1, 1, 1, 1), a.stat.repeat(r, 1, 1))
+            return Act(torch.cat([a.t] * r), torch.cat([a.stat] * r))     # contiguous block copies (vectorised), not a strided repeat
 
         def run_block(block, entries, h, skip=None):
             for layer, e in zip(block, entries):
