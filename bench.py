@@ -258,7 +258,7 @@ def run_ours(args):
                    "unet_tflop_per_step": 2 * OBJECTS * UNET_GFLOP_PER_SAMPLE / 1e3,
                    "conv_tflop_executed_per_step": conv_tflop,
                    "shared_prefix": "the layers in front of the first cross-attention see identical inputs in the uncond and cond "
-                                    "halves of a guided step and are evaluated once (bit-identical result): executed GEMM FLOPs "
+                                    "halves of a guided step and are evaluated once (same values, same kernels): executed GEMM FLOPs "
                                     "are below the reference algorithm's 35.69 TFLOP",
                    "achieved_tflops_whole_step": 2 * OBJECTS * UNET_GFLOP_PER_SAMPLE / 1e3 / (ms_total / args.steps / 1e3),
                    "achieved_tflops_whole_step_note": "reference-algorithm FLOPs / time (throughput-equivalent, not executed FLOPs)"},

@@ -469,7 +469,8 @@ class UNet3DModel(nn.Module):
         # Guided sampling evaluates [uncond; cond] on the SAME x and t: every layer before the first cross-attention sees
         # identical inputs in both halves (the stem, the two level-0 ResBlocks, the first Downsample and the ResBlock in front
         # of the first transformer: 11.5 % of the FLOPs).  With shared_prefix those run once on the Bs = B / r samples of x
-        # and their outputs (including the encoder skips) are replicated when the conditioning first enters -- bit-identical
+        # and their outputs (including the encoder skips) are replicated when the conditioning first enters -- equal (up to the
+        # fp32-atomic rounding noise any two launches show)
         # to evaluating them twice.  The caller vouches that timesteps[b] == timesteps[b % Bs] (the samplers build t that way).
         state = {"shared": bool(shared_prefix) and Bs < B and B % Bs == 0 and pk["ca_w"] is not None and not multi}
         hs: List[Act] = []
