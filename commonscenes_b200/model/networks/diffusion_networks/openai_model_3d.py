@@ -440,8 +440,9 @@ class UNet3DModel(nn.Module):
             return _UNetFunction.apply(self, x, timesteps, context, *params)
         if torch.is_grad_enabled() and context is None and context_vecs is None and (
                 x.requires_grad or any(p.requires_grad for p in self.parameters())):
-            raise NotImplementedError("gradients through the AttentionBlock (concat-conditioning) denoiser are not built: call it "
-                                      "under torch.no_grad() (sampling); training covers the cross-attention denoiser of v2_full")
+            # no cross-attention context (concat-conditioning variant): the conditioning gradient flows through x itself
+            params = [p for p in self.parameters() if p.requires_grad]
+            return _UNetInputFunction.apply(self, x, timesteps, *params)
         with torch.no_grad():
             return self._forward_inference(x, timesteps, context, context_vecs, shared_prefix)
 
@@ -534,3 +535,24 @@ class _UNetFunction(torch.autograd.Function):
         ctx.tape = None
         grads = tuple(sink.grads.get(p) for p in ctx.params)
         return (None, None, None, dctx) + grads
+
+
+class _UNetInputFunction(torch.autograd.Function):
+    """Autograd bridge for a UNet without cross-attention context (concat variant): gradients for the parameters and for x
+    (whose extra channels carry the conditioning, network.py:25-27)."""
+
+    @staticmethod
+    def forward(ctx, unet, x, timesteps, *params):
+        eps, tape = unet.trainer().forward_train(x.detach(), timesteps, None)
+        ctx.unet, ctx.tape, ctx.params, ctx.need_dx = unet, tape, params, x.requires_grad
+        return eps
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, d_eps):
+        sink, _ = ctx.unet.trainer().backward(ctx.tape, d_eps, need_dcontext=False, need_dx=ctx.need_dx)
+        dx = ctx.tape.get("dx") if ctx.need_dx else None
+        ctx.tape = None
+        grads = tuple(sink.grads.get(p) for p in ctx.params)
+        return (None, dx, None) + grads
+

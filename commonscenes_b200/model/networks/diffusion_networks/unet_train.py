@@ -25,7 +25,7 @@ import torch.nn.functional as F
 from .... import _lib, ops, ops_bwd
 from .attention import SpatialTransformer3D
 from .ldm_diffusion_util import timestep_embedding
-from .openai_model_3d import Act, Downsample, ResBlock, StatArena, Upsample, _f, _with_stats
+from .openai_model_3d import Act, AttentionBlock, Downsample, QKVAttention, ResBlock, StatArena, Upsample, _f, _with_stats
 
 
 class GradSink:
@@ -107,6 +107,17 @@ class UNetTrainer:
                             w[i, :, :dd] = lin.weight.detach().float().reshape(h, dd, cin)
                         d[a.to_q.weight] = ops_bwd.pack_dgrad_weight(w.reshape(3 * h * dp, cin, 1, 1, 1))
                         biggest = max(biggest, 3 * h * dp * ops._pad64(cin))
+                elif isinstance(layer, AttentionBlock):     # concat-conditioning variant: qkv in the head-padded q|k|v layout
+                    C, hh = layer.channels, layer.num_heads
+                    ch = C // hh
+                    dp = _pad_head(ch)
+                    w = torch.zeros(3, hh, dp, C, dtype=torch.float32, device=layer.qkv.weight.device)
+                    w[:, :, :ch] = _qkv_rows_to_packed(layer, layer.qkv.weight.detach().float().reshape(3 * C, C))
+                    d[layer.qkv.weight] = ops_bwd.pack_dgrad_weight(w.reshape(3 * hh * dp, C, 1, 1, 1))
+                    pw = layer.proj_out.weight
+                    d[pw] = ops_bwd.pack_dgrad_weight(pw.reshape(C, C, 1, 1, 1), owner=pw)
+                    biggest = max(biggest, 3 * hh * dp * ops._pad64(C), C * (ops._pad64(C) + 64))
+                    convs = []
                 elif isinstance(layer, Downsample):
                     convs = [layer.op.weight]
                 elif isinstance(layer, Upsample):
@@ -125,6 +136,11 @@ class UNetTrainer:
         wd[:, 0, :27 * co] = w.reshape(co, ci, 27).flip(2).permute(1, 2, 0).reshape(ci, 27 * co)
         d[u.out[2].weight] = ops._pad_k(wd)
         biggest = max(biggest, 128 * ops._pad64(ci), u.model_channels * 128)
+        # stem data gradient (needed when the conditioning is concatenated to x): a 3x3x3 conv model_channels -> in_channels
+        # with the transposed, flipped filter, through the few-output-channel path (one GEMM over the taps + cs_tap_gather)
+        stem = u.input_blocks[0][0]
+        if stem.weight.shape[1] <= 4:
+            d["stem_dx"] = ops.pack_small_cout_conv(stem.weight.detach().float().transpose(0, 1).flip(2, 3, 4).contiguous())
         if self._scratch is None or self._scratch.numel() < biggest:
             self._scratch = torch.empty(biggest, dtype=torch.float32, device=w.device)
         self._dpk, self._key = d, u._pack_generation
@@ -177,7 +193,8 @@ class UNetTrainer:
         _lib.require_device()
         u = self.unet
         pk, _ = self._ensure()
-        if context is None or context.dim() != 3 or context.shape[1] != 1:
+        has_ctx = pk["ca_w"] is not None          # False for the concat-conditioning variant (no cross-attention layers)
+        if has_ctx and (context is None or context.dim() != 3 or context.shape[1] != 1):
             raise NotImplementedError("the training path covers the single-token conditioning of v2_full (VAEGAN_V2FULL.py:237-240)")
         B = timesteps.shape[0]
         x = x.float().contiguous()
@@ -188,7 +205,7 @@ class UNetTrainer:
         h1 = ops.linear_small(t_emb, w0, b0)
         emb = ops.linear_small(h1, w2, b2, act_in=ops.ACT_SILU)
         emb_vecs = ops.linear_small(emb, pk["emb_w"], pk["emb_b"], act_in=ops.ACT_SILU)
-        ctx = context[:, 0].float().contiguous()
+        ctx = context[:, 0].float().contiguous() if has_ctx else None
         tape.update(t_emb=t_emb, h1=h1, emb=emb, ctx=ctx)
         ca = []      # per transformer block: (attn2 module, v2, vec)
         arena = StatArena(x.device, B * pk["stat_channels"] * 2)
@@ -203,6 +220,8 @@ class UNetTrainer:
                     skip = None
                 elif e["kind"] == "st":
                     h = self._st_fwd(layer, e["pk"], h, ctx, arena, records, ca)
+                elif e["kind"] == "attn":
+                    h = self._attn_fwd(layer, e["pk"], h, arena, records)
                 elif e["kind"] == "resample":
                     h = self._resample_fwd(layer, e["pk"], h, arena, records)
                 else:
@@ -295,20 +314,36 @@ class UNetTrainer:
         records.append({"kind": "st", "layer": layer, "pk": pk, "x": x, "g": g, "blocks": blocks, "t_last": t, "out": out})
         return out
 
+    def _attn_fwd(self, layer, pk, x, arena, records):
+        """AttentionBlock (concat variant): x + proj_out(attention(qkv(GroupNorm(x)))), keeping what the backward needs."""
+        B, D, H, W, C = x.t.shape
+        hh, dp = layer.num_heads, pk["dp"]
+        ch = C // hh
+        g = ops.groupnorm_fused(x.t, x.stat, *pk["gn"], eps=layer.norm.eps)
+        qkv = ops.linear_tokens(g, pk["wqkv"], bias=pk["bqkv"]).view(B, D * H * W, 3 * hh * dp)
+        q, k, v = (qkv[:, :, i * hh * dp:(i + 1) * hh * dp] for i in range(3))
+        o, lse = ops_bwd.attention_lse(q, k, v, heads=hh, head_dim=ch, head_dim_padded=dp, scale=ch ** -0.5)
+        o5 = o.view(B, D, H, W, C)
+        out = _tg(_with_stats(arena, lambda st: ops.linear_tokens(o5, pk["wo"], bias=pk["bo"], residual=x.t, stat_sum=st),
+                              B, C, D * H * W))
+        records.append({"kind": "attn", "layer": layer, "pk": pk, "x": x, "g": g, "qkv": qkv, "o": o5, "lse": lse, "out": out})
+        return out
+
     # ------------------------------------------------------------------------------------------
     # backward
     # ------------------------------------------------------------------------------------------
     def backward(self, tape: dict, d_eps: torch.Tensor, sink: Optional[GradSink] = None, need_dcontext: bool = True,
-                 on_block_done=None):
+                 on_block_done=None, need_dx: bool = False):
         """See _backward_impl.  Runs it inside the trainer's ZeroArena: the small zero-initialised reduction buffers of the
-        whole backward come from ONE memset."""
+        whole backward come from ONE memset.  need_dx: also compute the gradient wrt the network input (fp32 NCDHW, left in
+        tape["dx"]) -- the path of the conditioning gradient when it is concatenated to x (concat variant)."""
         if self._zero_arena is None or self._zero_arena.buf.device != d_eps.device:
             self._zero_arena = ops_bwd.ZeroArena(d_eps.device)
         with self._zero_arena:
-            return self._backward_impl(tape, d_eps, sink, need_dcontext, on_block_done)
+            return self._backward_impl(tape, d_eps, sink, need_dcontext, on_block_done, need_dx)
 
     def _backward_impl(self, tape: dict, d_eps: torch.Tensor, sink: Optional[GradSink] = None, need_dcontext: bool = True,
-                       on_block_done=None):
+                       on_block_done=None, need_dx: bool = False):
         """d_eps: gradient wrt the fp32 NCDHW output of forward_train.  Accumulates every parameter gradient into `sink`
         (created if None) and returns (sink, d_context (B, 1, context_dim) fp32 or None).
 
@@ -322,7 +357,7 @@ class UNetTrainer:
         d_eps = d_eps.float().contiguous()
         dev = d_eps.device
         d_emb_vecs = torch.zeros(tape["emb_vecs_shape"], dtype=torch.float32, device=dev)
-        d_ctx = torch.zeros_like(tape["ctx"])
+        d_ctx = torch.zeros_like(tape["ctx"]) if tape["ctx"] is not None else None
         se = F.silu(tape["emb"])
 
         # --- out head: conv3x3x3 224 -> 3 (im2col of d_eps on both sides), GroupNorm + SiLU -----
@@ -348,6 +383,8 @@ class UNetTrainer:
                 self._res_bwd(rec, sink, dpk, d_emb_vecs, se)
             elif kind == "st":
                 self._st_bwd(rec, sink, dpk, tape["ctx"], d_ctx)
+            elif kind == "attn":
+                self._attn_bwd(rec, sink, dpk)
             elif kind == "up":
                 layer, out = rec["layer"], rec["out"]
                 dy = out.grad
@@ -368,6 +405,10 @@ class UNetTrainer:
                 g = dws[:, 0, :27 * cin].reshape(conv.weight.shape[0], 27, cin).permute(0, 2, 1)
                 sink.grad(conv.weight).add_(g.reshape(conv.weight.shape))
                 self._bias_grad(sink, conv.bias, dy)
+                if need_dx:
+                    if "stem_dx" not in dpk:
+                        raise NotImplementedError("input gradient of a stem with more than 4 input channels")
+                    tape["dx"] = ops.conv3d_small_cout(dy, dpk["stem_dx"], None, cin)
             rec["out"].grad = None
             if on_block_done is not None:
                 on_block_done(next(rec["layer"].parameters()))
@@ -382,7 +423,7 @@ class UNetTrainer:
         d_h1 = ops_bwd.sgemm(d_emb, _f(te2.weight), silu_pre=h1)
         ops_bwd.sgemm(d_h1, t_emb, trans_a=True, out=sink.grad(te0.weight), accumulate=True)
         ops_bwd.batch_reduce(d_h1.view(B, -1, 1), 0, sink.grad(te0.bias))
-        return sink, (d_ctx[:, None, :] if need_dcontext else None)
+        return sink, (d_ctx[:, None, :] if need_dcontext and d_ctx is not None else None)
 
     def _res_bwd(self, rec, sink, dpk, d_emb_vecs, se):
         layer, pk, x, skip, out = rec["layer"], rec["pk"], rec["x"], rec["skip"], rec["out"]
@@ -423,6 +464,36 @@ class UNetTrainer:
         _acc(x, dx)
         if skip is not None:
             _acc(skip, dskip)
+
+    def _chan_sums(self, dy):
+        """fp32 (C,) sum over every token of a bf16 channels-last tensor (bias gradients), 2048 channels per launch."""
+        Ct = dy.shape[-1]
+        parts = [self._colsums(dy[..., c0:min(Ct, c0 + 2048)])[:, :, 0].sum(0) for c0 in range(0, Ct, 2048)]
+        return parts[0] if len(parts) == 1 else torch.cat(parts)
+
+    def _attn_bwd(self, rec, sink, dpk):
+        layer, pk, x, out = rec["layer"], rec["pk"], rec["x"], rec["out"]
+        dy = out.grad
+        B, D, H, W, C = dy.shape
+        hh, dp = layer.num_heads, pk["dp"]
+        ch, N = C // hh, D * H * W
+        # out = o Wo + bo + x
+        self._lin_wgrad(sink, layer.proj_out.weight, rec["o"], dy)
+        self._bias_grad(sink, layer.proj_out.bias, dy)
+        do = ops_bwd.conv3d_dgrad(dy, dpk[layer.proj_out.weight], ksize=(1, 1, 1), pad=(0, 0, 0))
+        dqkv = ops_bwd.attention_bwd(rec["qkv"], rec["o"].view(B, N, C), do.view(B, N, C), rec["lse"], heads=hh, head_dim=ch,
+                                     head_dim_padded=dp, scale=ch ** -0.5)
+        dqkv5 = dqkv.view(B, D, H, W, 3 * hh * dp)
+        # qkv = g Wqkv + bqkv in the head-padded q|k|v layout: map the packed gradients back to the parameter's row order
+        dwq = self._lin_wgrad(sink, None, rec["g"], dqkv5)
+        gw = dwq[:, 0, :C].view(3, hh, dp, C)[:, :, :ch]
+        sink.grad(layer.qkv.weight).add_(_qkv_packed_to_rows(layer, gw).reshape(layer.qkv.weight.shape))
+        gb = self._chan_sums(dqkv5).view(3, hh, dp)[:, :, :ch]
+        sink.grad(layer.qkv.bias).add_(_qkv_packed_to_rows(layer, gb))
+        dg = ops_bwd.conv3d_dgrad(dqkv5, dpk[layer.qkv.weight], ksize=(1, 1, 1), pad=(0, 0, 0))
+        dx, _ = ops_bwd.groupnorm_bwd(x.t, x.stat, *pk["gn"], dg, eps=layer.norm.eps, act=ops.ACT_NONE, extra=dy,
+                                      dgamma=sink.grad(layer.norm.weight), dbeta=sink.grad(layer.norm.bias))
+        _acc(x, dx)
 
     def _st_bwd(self, rec, sink, dpk, ctx, d_ctx):
         layer, pk, x, out = rec["layer"], rec["pk"], rec["x"], rec["out"]
@@ -474,6 +545,25 @@ class UNetTrainer:
         dx, _ = ops_bwd.groupnorm_bwd(x.t, x.stat, *pk["gn"], dg, eps=layer.norm.eps, act=ops.ACT_NONE, extra=dy,
                                       dgamma=sink.grad(layer.norm.weight), dbeta=sink.grad(layer.norm.bias))
         _acc(x, dx)
+
+
+def _qkv_rows_to_packed(layer, rows: torch.Tensor) -> torch.Tensor:
+    """AttentionBlock.qkv rows (3C, ...) -> (3, heads, ch, ...): legacy order is [head][q|k|v][ch], new order [q|k|v][head][ch]."""
+    C, hh = layer.channels, layer.num_heads
+    ch = C // hh
+    tail = rows.shape[1:]
+    if isinstance(layer.attention, QKVAttention):
+        return rows.reshape(3, hh, ch, *tail)
+    return rows.reshape(hh, 3, ch, *tail).transpose(0, 1)
+
+
+def _qkv_packed_to_rows(layer, packed: torch.Tensor) -> torch.Tensor:
+    """Inverse of _qkv_rows_to_packed: (3, heads, ch, ...) -> (3C, ...) in the parameter's own row order."""
+    C = layer.channels
+    tail = packed.shape[3:]
+    if isinstance(layer.attention, QKVAttention):
+        return packed.reshape(3 * C, *tail)
+    return packed.transpose(0, 1).reshape(3 * C, *tail)
 
 
 def _pad_head(d: int) -> int:

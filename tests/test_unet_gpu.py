@@ -253,8 +253,7 @@ def test_concat_unet_eps_matches_reference_golden(tag, cfg):
     err = _rel_l2(eps, torch.tensor(g["eps"]))
     print(f"concat unet[{tag}]: rel-L2 vs the reference module {err:.3e}")
     assert err <= REL_L2_TOL
-    with pytest.raises(NotImplementedError):           # training of this variant is not built: fail loudly, never silently
-        m(x, t, c_concat=[cc])
+    assert m(x, t, c_concat=[cc]).requires_grad         # with autograd enabled the result carries the explicit-backward grad_fn
 
 
 def test_concat_guided_ddim_step_matches_oracle():

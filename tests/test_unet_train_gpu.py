@@ -223,3 +223,59 @@ def test_graphed_train_step_matches_eager():
     print(f"graphed vs eager parameter update rel-L2 after 3 steps: {rel:.3e}")
     assert rel < 0.25 and int(sb.step_dev.item()) == 3
     assert float((da - db).norm() / da.norm()) < 0.1
+
+
+def test_concat_unet_backward_matches_oracle_autograd():
+    """Concat-conditioning denoiser (AttentionBlock variant): `loss.backward()` through
+    DiffusionUNet(conditioning_key='concat') -- parameter gradients (incl. the Conv1d qkv / proj_out of every AttentionBlock in
+    the reference's legacy head-major row order) and the gradient of the concatenated conditioning volume, which flows through
+    the stem's input gradient -- vs autograd through the oracle."""
+    from commonscenes_b200.model.networks.diffusion_networks.network import DiffusionUNet
+    cfg, seed = D.UNET_CONCAT_TINY, 71
+    g = torch.Generator().manual_seed(14)
+    B = 4
+    x = torch.randn(B, 3, 8, 8, 8, generator=g)
+    cc = torch.randn(B, 1, 8, 8, 8, generator=g)
+    t = torch.tensor([999, 3, 421, 650])
+    noise = torch.randn(B, 3, 8, 8, 8, generator=g)
+    sd = {k: v.clone().requires_grad_(True) for k, v in Wt.synth_state_dict(D.unet_param_shapes(cfg), seed).items()}
+    cc_ref = cc.clone().requires_grad_(True)
+    eps_ref = D.unet_forward(sd, cfg, x, t, c_concat=cc_ref)
+    loss_ref = torch.nn.functional.mse_loss(eps_ref, noise)
+    keys = list(sd.keys())
+    grads = torch.autograd.grad(loss_ref, [sd[k] for k in keys] + [cc_ref], allow_unused=True)
+    gref, gcc_ref = dict(zip(keys, grads[:-1])), grads[-1]
+
+    m = DiffusionUNet(dict(cfg, use_checkpoint=True, legacy=False), conditioning_key="concat")
+    Wt.fill_module_(m, seed)
+    m = m.cuda()
+    cc_dev = cc.cuda().requires_grad_(True)
+    eps = m(x.cuda(), t.cuda(), c_concat=[cc_dev])
+    assert eps.requires_grad and float((eps.detach().cpu() - eps_ref.detach()).norm() / eps_ref.detach().norm()) <= 3e-2
+    torch.nn.functional.mse_loss(eps, noise.cuda()).backward()
+    named = dict(m.named_parameters())
+    num = den = dot = gg = 0.0
+    worst = []
+    n_el = 0
+    for k, gr in gref.items():
+        got = named[k].grad
+        if gr is None or float(gr.norm()) == 0.0:
+            continue
+        assert got is not None, f"no gradient produced for {k}"
+        got = got.cpu()
+        num += float((got - gr).pow(2).sum()); den += float(gr.pow(2).sum())
+        dot += float((got * gr).sum()); gg += float(got.pow(2).sum())
+        n_el += gr.numel()
+        worst.append((float((got - gr).norm() / gr.norm()), k))
+    worst.sort(reverse=True)
+    rms = (den / n_el) ** 0.5
+    for k, gr in gref.items():
+        if gr is None or float(gr.norm()) == 0.0:
+            continue
+        err = float((named[k].grad.cpu() - gr).norm())
+        assert err <= 0.15 * float(gr.norm()) + 0.05 * rms * gr.numel() ** 0.5, f"{k}: err {err:.3e} vs ref norm {float(gr.norm()):.3e}"
+    total_rel, cos = (num / den) ** 0.5, dot / (den * gg) ** 0.5
+    rel_cc = float((cc_dev.grad.cpu() - gcc_ref).norm() / gcc_ref.norm())
+    print("worst tensors:", [(f"{r:.3e}", k) for r, k in worst[:6]])
+    print(f"concat variant: whole-gradient rel-L2 {total_rel:.3e}, cosine {cos:.6f}; d c_concat rel-L2 {rel_cc:.3e}")
+    assert total_rel < 3e-2 and cos > 0.999 and rel_cc < 3e-2
