@@ -154,6 +154,59 @@ class Sg2ScVAEModel(nn.Module):
         diff_dict = {"sdf": torch.cat(sdf_sel)[:n].cuda(), "uc": torch.cat(uc_sel)[:n].cuda(), "rel": torch.cat(c_sel)[:n].cuda()}
         return torch.cat(cat_sel)[:n], diff_dict
 
+    # ---- checkpoints: the reference's `model{epoch}.pth` layout (VAEGAN_V2FULL.py:687-699 / VAE.py:120-158, 334-340) -------
+    def state_dict(self, epoch=None, counter=None, *args, optimizer_state=None, **kwargs):
+        """Without arguments: the plain nn.Module state dict.  With (epoch, counter): the reference's checkpoint dictionary --
+        this module's tensors plus 'epoch', 'counter', 'vqvae', 'df' and 'opt' (a torch.optim.AdamW state dict, e.g.
+        DenoiserTrainStep.optimizer_state_dict(); {} if none is given)."""
+        sd = super().state_dict(*args, **kwargs)
+        if epoch is None and counter is None:
+            return sd
+        sd = dict(sd)
+        sd.update({"epoch": epoch, "counter": counter, "vqvae": self.Diff.vqvae_module.state_dict(),
+                   "df": self.Diff.df_module.state_dict(), "opt": optimizer_state if optimizer_state is not None else {}})
+        return sd
+
+    def save_checkpoint(self, path, epoch, counter=None, optimizer_state=None):
+        torch.save(self.state_dict(epoch, counter, optimizer_state=optimizer_state), path)
+        return path
+
+    def load_checkpoint(self, ckpt, strict=False):
+        """Restore from a reference-format `model{epoch}.pth` (path or loaded dict) the way VAE.load_networks does: pop
+        'vqvae' / 'df' / 'opt' / 'epoch' / 'counter', load the rest into this module, then the VQ-VAE and the denoiser.
+        strict=False by default: a full v2_full checkpoint also holds the layout branch (box encoder / decoder / manipulator),
+        which this shape-branch class does not have; every shape-branch key must still be present and is loaded.
+        Returns {'epoch', 'counter', 'opt', 'ignored_keys'}: 'opt' is the untouched optimizer state (its LAST
+        len(Diff.trainable_params) entries are the denoiser's, reference :636-645 -- see denoiser_optimizer_state)."""
+        ckpt = dict(torch.load(ckpt, map_location="cpu") if isinstance(ckpt, str) else ckpt)
+        extra = {k: ckpt.pop(k, None) for k in ("vqvae", "df", "opt", "epoch", "counter")}
+        own = set(super().state_dict().keys())
+        missing = sorted(own - set(ckpt))
+        if missing:
+            raise KeyError(f"checkpoint lacks shape-branch tensors: {missing[:5]}{' ...' if len(missing) > 5 else ''}")
+        ignored = sorted(set(ckpt) - own)
+        if ignored and strict:
+            raise KeyError(f"unexpected keys in checkpoint: {ignored[:5]}")
+        self.load_state_dict({k: v for k, v in ckpt.items() if k in own}, strict=True)
+        if extra["vqvae"] is not None:
+            self.Diff.vqvae.load_state_dict(extra["vqvae"])
+        if extra["df"] is not None:
+            self.Diff.df.load_state_dict(extra["df"])
+        return {"epoch": extra["epoch"], "counter": extra["counter"], "opt": extra["opt"], "ignored_keys": ignored}
+
+    def denoiser_optimizer_state(self, opt_state: dict) -> dict:
+        """The denoiser's slice of a reference optimizerFULL state dict, re-indexed from 0 so that
+        DenoiserTrainStep.load_optimizer_state_dict (or torch.optim.AdamW over df.parameters()) accepts it.  The reference
+        builds the optimizer over `params + df_params` (:636-645): the denoiser's parameters are the last entries."""
+        n = len(self.Diff.trainable_params)
+        group = dict(opt_state["param_groups"][0])
+        ids = list(group["params"])
+        if len(ids) < n:
+            raise ValueError(f"optimizer state covers {len(ids)} parameters, fewer than the denoiser's {n}")
+        tail = ids[-n:]
+        group["params"] = list(range(n))
+        return {"state": {j: opt_state["state"][i] for j, i in enumerate(tail) if i in opt_state["state"]}, "param_groups": [group]}
+
     def forward_shape(self, z, dec_objs, dec_objs_grained, dec_triples, dec_text_feat, dec_rel_feat, dec_sdfs, dec_objs_to_scene):
         """The shape-branch lines of Sg2ScVAEModel.forward (:511-521): conditioning -> object selection -> diffusion loss."""
         uc, c = self.encoder_2(z, dec_objs, dec_triples, dec_text_feat, dec_rel_feat)
