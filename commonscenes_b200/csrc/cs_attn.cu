@@ -6,9 +6,10 @@
 // The reference materialises the (B*heads, N, N) fp32 score matrix; this kernel keeps it on chip
 // (online softmax, fp32 statistics).
 //
-// Round-1 implementation: warp-level mma.sync.m16n8k16 (bf16 in, fp32 accumulate), cp.async double
-// buffering of K/V.  Attention is 1.9 % of the path's FLOPs; the tcgen05 version is
-// scheduled after the convolution path is at its roofline.
+// This file: the general kernel -- warp-level mma.sync.m16n8k16 (bf16 in, fp32 accumulate), cp.async double buffering of
+// K/V -- used for every shape the tcgen05 kernel (cs_attn_tc.cu: N % 128 == 0, padded head dim 64) does not take: the
+// N = 256 / d = 84 blocks, the VQ-VAE's single 256-wide head, ragged lengths, multi-token cross-attention contexts, and
+// the training forward (which also writes the log-sum-exp rows the backward of cs_attn_bwd.cu needs).
 //
 // Layout: q[(b*Nq + i) * q_pitch + h*Dp + d], k/v[(b*Nk + j) * kv_pitch + h*Dp + d]  (bf16, head dim
 // zero-padded to Dp by the weight packing), out[(b*Nq + i) * o_pitch + h*d_out + d] for d < d_out.

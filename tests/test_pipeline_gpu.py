@@ -48,7 +48,8 @@ def test_rel2shape_batch32_ddim100_decodes_to_sdf_grids(model):
 
 
 def test_training_forward_loss_matches_definition(model):
-    """SDFusionText2ShapeModel.forward(): encode -> q_sample -> eps prediction -> loss dict (no autograd yet)."""
+    """SDFusionText2ShapeModel.forward(): encode -> q_sample -> eps prediction -> loss dict; the loss carries the explicit-
+    backward grad_fn (the gradients themselves are checked in test_unet_train_gpu.py)."""
     g = torch.Generator(device="cuda").manual_seed(6)
     n = 4
     sdf = (torch.randn(n, 1, 64, 64, 64, device="cuda", generator=g) * 0.1).clamp(-0.2, 0.2)
