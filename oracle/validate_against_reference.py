@@ -215,6 +215,29 @@ def main():
             uc_ref, c_ref = m(*inp)
             uc, c = G.encoder_2(sd, cfg, *inp, training=training)
             ok &= _cmp(f"encoder_2.c[{tag},train={training}]", c, c_ref) and _cmp(f"encoder_2.uc[{tag},train={training}]", uc, uc_ref)
+    # ---- the REAL Sg2ScVAEModel class (stubbed third-party imports, oracle/reference_scene_model.py): encoder_2 wiring ----
+    from oracle import reference_scene_model as RS
+    for tag, cfg in [("tiny", dict(G.GCN_TINY, add_dim=512, rel_hidden=960, rel_out=1280)), ("full", G.GCN_FULL)]:
+        # (the class hard-codes CLIP width 512 and rel_mlp 960 -> 1280, VAEGAN_V2FULL.py:64-66,152)
+        real = RS.build(cfg, seed=9)
+        shapes = G.gcn_param_shapes(cfg)
+        rsd = {k: tuple(v.shape) for k, v in RS.module_state_dict(real).items()}
+        sub = {k: rsd.get(k) for k in shapes}
+        if sub != {k: tuple(v) for k, v in shapes.items()}:
+            bad = [k for k in shapes if rsd.get(k) != tuple(shapes[k])][:5]
+            print(f"BAD Sg2ScVAEModel[{tag}] shape-branch keys: {bad}")
+            ok = False
+        else:
+            print(f"ok  Sg2ScVAEModel[{tag}]: all {len(shapes)} shape-branch keys/shapes present in the real class ({len(rsd)} keys in total)")
+        sd = Wt.synth_state_dict(shapes, seed=10)
+        torch.nn.Module.load_state_dict(real, sd, strict=False)
+        inp = synth_graph(cfg, 9, 20, seed=11)
+        for training in (False, True):
+            real.train(training)
+            uc_ref, c_ref = real.encoder_2(*inp, None)
+            uc, c = G.encoder_2(sd, cfg, *inp, training=training)
+            ok &= _cmp(f"Sg2ScVAEModel.encoder_2.c[{tag},train={training}]", c, c_ref)
+            ok &= _cmp(f"Sg2ScVAEModel.encoder_2.uc[{tag},train={training}]", uc, uc_ref)
     print("ORACLE PINNED" if ok else "ORACLE MISMATCH")
     return 0 if ok else 1
 

@@ -53,3 +53,32 @@ def test_concat_unet_state_dict_keys_equal_reference_inventory(cfg):
         m = DiffusionUNet(dict(cfg, use_checkpoint=True, legacy=False), conditioning_key="concat")
     got = {k: tuple(v.shape) for k, v in m.state_dict().items()}
     assert got == D.unet_param_shapes(cfg)
+
+
+def test_select_sdfs_and_balance_objects_match_the_reference_class(monkeypatch):
+    """Host-side object selection: same picks, in the same order, as the reference's REAL
+    Sg2ScVAEModel.select_sdfs / balance_objects under the same `random` / torch seeds (index work: bit-exact).
+    Golden: tests/golden/select_sdfs.npz (tests/golden/make_golden_scene.py)."""
+    import random
+    import numpy as np
+    from commonscenes_b200.model.VAEGAN_V2FULL import Sg2ScVAEModel
+    g = np.load(os.path.join(ROOT, "tests", "golden", "select_sdfs.npz"))
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)        # select_sdfs ends with .cuda() like the reference
+    m = object.__new__(Sg2ScVAEModel)                                            # the methods only read diffusion_bs
+    scene, objs, grained, sdfs, uc, c = (torch.tensor(g[k]) for k in ("scene", "objs", "grained", "sdfs", "uc", "c"))
+    for bs in (8, 4, 12):
+        m.diffusion_bs = bs
+        random.seed(1000 + bs)
+        cats, d = m.select_sdfs(scene, objs, grained, sdfs, uc, c, random=False)
+        assert np.array_equal(cats.numpy(), g[f"balanced_bs{bs}_cats"])
+        for k in ("sdf", "uc", "rel"):
+            assert np.array_equal(d[k].numpy(), g[f"balanced_bs{bs}_{k}"]), (bs, k)
+        torch.manual_seed(2000 + bs)
+        cats, d = m.select_sdfs(scene, objs, grained, sdfs, uc, c, random=True)
+        assert np.array_equal(cats.numpy(), g[f"random_bs{bs}_cats"]) and np.array_equal(d["sdf"].numpy(), g[f"random_bs{bs}_sdf"])
+    random.seed(77)
+    ids = torch.tensor(g["balance_ids"])
+    assert np.array_equal(m.balance_objects(ids, ids, 3).numpy(), g["balance_n3"])
+    assert np.array_equal(m.balance_objects(ids, ids, 6).numpy(), g["balance_n6"])
+    with pytest.raises(AssertionError):
+        m.balance_objects(ids, ids[:3], 2)

@@ -71,3 +71,27 @@ def test_reference_checkpoint_layout_round_trip(tmp_path):
     for j, p in enumerate(step.params):
         off, n = step.offsets[p], p.numel()
         assert torch.equal(step.flat_m[off:off + n].view(p.shape), info["opt"]["state"][n_graph + j]["exp_avg"])
+
+
+def test_full_reference_checkpoint_inventory_loads(tmp_path):
+    """A checkpoint holding EVERY tensor of the reference's real Sg2ScVAEModel in the v2_full wiring (inventory recorded
+    from the class itself: tests/golden/sg2sc_v2full_state_dict_keys.json) loads into the shape-branch mirror: all of the
+    mirror's keys are found with the right shapes, the layout-branch tensors are reported as ignored."""
+    import json
+    from commonscenes_b200.model.VAEGAN_V2FULL import Sg2ScVAEModel
+    from commonscenes_b200.model.sdfusion_txt2shape_model import default_opt
+    inv = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "sg2sc_v2full_state_dict_keys.json")))
+    df, vq = tmp_path / "df.yaml", tmp_path / "vq.yaml"
+    df.write_text(yaml.safe_dump(TINY_DF)); vq.write_text(yaml.safe_dump(TINY_VQ))
+    vocab = {"object_idx_to_name": [f"o{i}" for i in range(36)], "pred_idx_to_name": [f"p{i}" for i in range(16)]}
+    m = Sg2ScVAEModel(vocab, diff_opt=default_opt(device="cpu", df_cfg=str(df), vq_cfg=str(vq)), embedding_dim=64,
+                      mlp_normalization="batch", residual=True, gconv_num_layers=5)
+    own = {k: list(v.shape) for k, v in m.state_dict().items()}
+    assert len(own) == 171 and all(inv.get(k) == s for k, s in own.items())      # drop-in contract: same names, same shapes
+    g = torch.Generator().manual_seed(0)
+    ck = {k: (torch.randn(s, generator=g) if "num_batches_tracked" not in k else torch.tensor(3)) for k, s in inv.items()}
+    ck.update(epoch=5, counter=99, opt={}, vqvae=m.Diff.vqvae.state_dict(), df=m.Diff.df.state_dict())
+    info = m.load_checkpoint(ck)
+    assert info["epoch"] == 5 and len(info["ignored_keys"]) == len(inv) - 171
+    assert all(not k.startswith(("gconv_net_ec_rel", "rel_mlp", "obj_embeddings_dc", "pred_embeddings_dc")) for k in info["ignored_keys"])
+    assert torch.equal(m.rel_mlp[0].weight, ck["rel_mlp.0.weight"])
