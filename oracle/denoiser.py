@@ -2,6 +2,8 @@
 
 Covers SURVEY.md §8 rows a1-a14: the UNet3DModel forward, the diffusion schedule, q_sample / p_losses,
 the DDIM sampler with classifier-free guidance.  Every function names the reference lines it restates.
+Pinned (oracle/validate_against_reference.py): against the reference modules AND against the real SDFusionText2ShapeModel
+class built on the CPU (oracle/reference_diffusion_model.py): schedule, q_sample, p_losses, forward(), rel2shape.
 All functions are pure: weights come in as a state dict with the reference's key names
 (`diffusion_net.*`), nothing is cached, nothing touches CUDA.
 """

@@ -2,6 +2,8 @@
 (SURVEY.md §8 a17, a18): GraphTripleConv / GraphTripleConvNet2 (model/graph.py:89-288), build_mlp
 (model/layers.py:21-38) and Sg2ScVAEModel.encoder_2 + rel_mlp (model/VAEGAN_V2FULL.py:152-155, 220-242)
 in the v2_full wiring of model/VAE.py:57-63 (embedding_dim 64, hidden 256, CLIP 512, BatchNorm, residual, avg).
+Pinned against the reference modules and against encoder_2 of the REAL Sg2ScVAEModel class
+(oracle/reference_scene_model.py + validate_against_reference.py): max |diff| = 0.
 """
 from __future__ import annotations
 

@@ -238,6 +238,64 @@ def main():
             uc, c = G.encoder_2(sd, cfg, *inp, training=training)
             ok &= _cmp(f"Sg2ScVAEModel.encoder_2.c[{tag},train={training}]", c, c_ref)
             ok &= _cmp(f"Sg2ScVAEModel.encoder_2.uc[{tag},train={training}]", uc, uc_ref)
+    # ---- the REAL SDFusionText2ShapeModel class on CPU (oracle/reference_diffusion_model.py): schedule, q_sample, p_losses,
+    #      forward() = frozen VQ-VAE encode -> randint t -> randn noise -> p_losses (sdfusion_txt2shape_model.py:184-365) ----
+    from oracle import reference_diffusion_model as RD
+    real = RD.build(D.UNET_TINY, V.VQ_TINY, seed_unet=21, seed_vq=22)
+    sd = Wt.synth_state_dict(D.unet_param_shapes(D.UNET_TINY), seed=21)
+    vsd = Wt.synth_state_dict(V.vq_param_shapes(V.VQ_TINY), seed=22)
+    sched = D.register_schedule(**D.DIFFUSION)
+    for k in ("betas", "alphas_cumprod", "alphas_cumprod_prev", "sqrt_alphas_cumprod", "sqrt_one_minus_alphas_cumprod",
+              "log_one_minus_alphas_cumprod", "sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod", "posterior_variance",
+              "posterior_log_variance_clipped", "posterior_mean_coef1", "posterior_mean_coef2", "lvlb_weights"):
+        ok &= _cmp(f"SDFusionText2ShapeModel.{k}", sched[k], getattr(real, k), 0)
+    assert tuple(real.z_shape) == (3, 4, 4, 4) and real.num_timesteps == 1000
+    g = torch.Generator().manual_seed(23)
+    x0 = torch.randn(3, 3, 4, 4, 4, generator=g)            # (the tiny VQ-VAE has 16^3 -> 4^3 latents; the tiny UNet runs any size)
+    x0 = torch.randn(3, 3, 8, 8, 8, generator=g)
+    noise = torch.randn(3, 3, 8, 8, 8, generator=g)
+    cond = torch.randn(3, 1, D.UNET_TINY["context_dim"], generator=g)
+    t = torch.tensor([0, 517, 999])
+    ok &= _cmp("SDFusionText2ShapeModel.q_sample", D.q_sample(sched, x0, t, noise), real.q_sample(x0, t, noise), 0)
+    xr, tr, lr, ldr = real.p_losses(x0, cond, t, noise=noise)
+    xo, to, lo, ldo = D.p_losses(sd, D.UNET_TINY, sched, x0, cond, t, noise)
+    ok &= _cmp("SDFusionText2ShapeModel.p_losses.x_noisy", xo, xr, 0) and _cmp("p_losses.loss", lo, lr)
+    for k in ("loss_simple", "loss_vlb", "loss_total"):
+        ok &= _cmp(f"p_losses.loss_dict[{k}]", ldo[k], ldr[k])
+    # forward(): same RNG draws in the same order
+    sdf = (torch.randn(2, 1, 16, 16, 16, generator=g) * 0.1).clamp(-0.2, 0.2)
+    rel = torch.randn(2, 1, D.UNET_TINY["context_dim"], generator=g)
+    torch.Tensor.cuda = lambda self, *a, **k: self          # BaseModel.tocuda (base_model.py:113-118); stay on the CPU
+    real.set_input({"sdf": sdf, "rel": rel, "uc": rel})
+    torch.manual_seed(24)
+    real.forward()
+    torch.manual_seed(24)
+    z = V.encode_no_quant(vsd, V.VQ_TINY, sdf)
+    tt = torch.randint(0, 1000, (2,)).long()
+    _, _, lo, _ = D.p_losses(sd, D.UNET_TINY, sched, z, rel, tt, torch.randn_like(z))
+    ok &= _cmp("SDFusionText2ShapeModel.forward().loss_df", lo, real.loss_df)
+    # rel2shape (sdfusion_txt2shape_model.py:459-516): one shared x_T for all objects (seeded from time.time()), DDIM with
+    # CFG in mini-batches of 7, decode_no_quant.  The class hard-codes device='cuda' (:485,490; ddim.py:22-26): patched to CPU.
+    import time as _time
+    import numpy as np
+    from model.networks.diffusion_networks.samplers.ddim import DDIMSampler
+    DDIMSampler.register_buffer = lambda self, name, attr: setattr(self, name, attr)
+    _randn, _now = torch.randn, _time.time
+    torch.randn = lambda *a, **k: _randn(*a, **{kk: vv for kk, vv in k.items() if kk != "device"})
+    _time.time = lambda: 1234567.0
+    try:
+        nobj = 9                                           # 7 + 2: exercises the mini-batch loop
+        data = {"sdf": torch.zeros(nobj, 1, 16, 16, 16), "rel": torch.randn(nobj, 1, D.UNET_TINY["context_dim"], generator=g),
+                "uc": torch.randn(nobj, 1, D.UNET_TINY["context_dim"], generator=g)}
+        with torch.no_grad():
+            ref_sdf = real.rel2shape(data, ddim_steps=20, ddim_eta=0.0, uc_scale=3.0)
+            torch.manual_seed(1234567)
+            x_T = _randn((1, 3, 4, 4, 4)).repeat(nobj, 1, 1, 1, 1)
+            z0, _ = D.ddim_sample(sd, D.UNET_TINY, sched, data["rel"], data["uc"], x_T, S=20, eta=0.0, scale=3.0)
+            got = V.decode_no_quant(vsd, V.VQ_TINY, z0)
+        ok &= _cmp("SDFusionText2ShapeModel.rel2shape (9 objects, 20 DDIM steps, CFG 3, decode)", got, ref_sdf, 1e-3)
+    finally:
+        torch.randn, _time.time = _randn, _now
     print("ORACLE PINNED" if ok else "ORACLE MISMATCH")
     return 0 if ok else 1
 

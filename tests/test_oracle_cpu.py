@@ -141,3 +141,19 @@ def test_ddpm_posterior_equals_eta1_ddim_form():
         post = sched["posterior_mean_coef1"][t].double() * x0_ref + sched["posterior_mean_coef2"][t].double() * x
         assert float((ddim_form - post).abs().max()) < 2e-5, t           # fp32 tables vs float64 recomputation
         assert abs(sig[t] - float(torch.exp(0.5 * sched["posterior_log_variance_clipped"][t]))) < 1e-6 or t == 0
+
+
+def test_rel2shape_chain_matches_the_reference_class_golden():
+    """The oracle's free-running chain (shared x_T -> 20 guided DDIM steps on all 9 objects at once -> decode) reproduces what
+    the reference's REAL SDFusionText2ShapeModel.rel2shape computed in mini-batches of 7 (tests/golden/rel2shape_tiny.npz)."""
+    g = _load("rel2shape_tiny.npz")
+    sd = Wt.synth_state_dict(D.unet_param_shapes(D.UNET_TINY), int(g["weight_seed_unet"]))
+    vcfg = dict(V.VQ_TINY, resolution=int(g["resolution"]))
+    vsd = Wt.synth_state_dict(V.vq_param_shapes(vcfg), int(g["weight_seed_vq"]))
+    sched = D.register_schedule(**D.DIFFUSION)
+    rel, uc = torch.tensor(g["rel"]), torch.tensor(g["uc"])
+    x_T = torch.tensor(g["x_T"]).repeat(rel.shape[0], 1, 1, 1, 1)
+    with torch.no_grad():
+        z0, _ = D.ddim_sample(sd, D.UNET_TINY, sched, rel, uc, x_T, S=int(g["steps"]), eta=0.0, scale=3.0)
+        sdf = V.decode_no_quant(vsd, vcfg, z0[torch.tensor(g["rows"])])
+    _close(sdf, g["sdf"], tol=1e-3)
