@@ -320,11 +320,11 @@ def q_sample(sched, x0: Tensor, t: Tensor, noise: Tensor) -> Tensor:
     return sched["sqrt_alphas_cumprod"][t].reshape(shp) * x0 + sched["sqrt_one_minus_alphas_cumprod"][t].reshape(shp) * noise
 
 
-def p_losses(sd, cfg, sched, x0: Tensor, cond: Tensor, t: Tensor, noise: Tensor):
+def p_losses(sd, cfg, sched, x0: Tensor, cond: Tensor, t: Tensor, noise: Tensor, concat: bool = False):
     """sdfusion_txt2shape_model.py:311-345 (eps parameterisation, logvar = 0, l_simple_weight = 1,
-    original_elbo_weight = 0)."""
+    original_elbo_weight = 0).  concat=True: `cond` is the (B, 1, D, H, W) volume apply_model passes as c_concat (:281-283)."""
     x_noisy = q_sample(sched, x0, t, noise)
-    out = unet_forward(sd, cfg, x_noisy, t, cond)
+    out = unet_forward(sd, cfg, x_noisy, t, c_concat=cond) if concat else unet_forward(sd, cfg, x_noisy, t, cond)
     loss_simple = ((out - noise) ** 2).mean(dim=(1, 2, 3, 4))
     loss = loss_simple.mean()
     loss_vlb = (sched["lvlb_weights"][t] * loss_simple).mean()

@@ -61,15 +61,20 @@ def import_reference_diffusion_class():
     return S.SDFusionText2ShapeModel
 
 
-def build(unet_cfg: dict, vq_cfg: dict, seed_unet: int, seed_vq: int, workdir: str | None = None):
-    """The real class on CPU with the oracle's seeded synthetic weights (oracle.weights) in both networks."""
+def build(unet_cfg: dict, vq_cfg: dict, seed_unet: int, seed_vq: int, workdir: str | None = None,
+          conditioning_key: str = "crossattn"):
+    """The real class on CPU with the oracle's seeded synthetic weights (oracle.weights) in both networks.
+    conditioning_key='concat' builds the AttentionBlock variant of config/sdfusion-txt2shape_concat.yaml."""
     from oracle import weights as Wt
     cls = import_reference_diffusion_class()
     workdir = workdir or tempfile.mkdtemp(prefix="cs_ref_diff_")
     unet = dict(unet_cfg)
     unet["attention_resolutions"] = list(unet["attention_resolutions"]); unet["channel_mult"] = list(unet["channel_mult"])
-    unet.update(use_spatial_transformer=True, use_checkpoint=False, legacy=False)
-    df = dict(model=dict(params=dict(linear_start=0.00085, linear_end=0.012, conditioning_key="crossattn", timesteps=1000,
+    if conditioning_key == "concat":
+        unet.update(use_spatial_transformer=False, context_dim=None, use_checkpoint=False, legacy=False)
+    else:
+        unet.update(use_spatial_transformer=True, use_checkpoint=False, legacy=False)
+    df = dict(model=dict(params=dict(linear_start=0.00085, linear_end=0.012, conditioning_key=conditioning_key, timesteps=1000,
                                      scale_factor=0.18215)), unet=dict(params=unet))
     dd = dict(double_z=False, z_channels=vq_cfg["z_channels"], resolution=vq_cfg["resolution"], in_channels=vq_cfg["in_channels"],
               out_ch=vq_cfg["out_ch"], ch=vq_cfg["ch"], ch_mult=list(vq_cfg["ch_mult"]), num_res_blocks=vq_cfg["num_res_blocks"],

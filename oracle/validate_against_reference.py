@@ -296,6 +296,17 @@ def main():
         ok &= _cmp("SDFusionText2ShapeModel.rel2shape (9 objects, 20 DDIM steps, CFG 3, decode)", got, ref_sdf, 1e-3)
     finally:
         torch.randn, _time.time = _randn, _now
+    # concat-conditioning variant through the real wrapper: set_input views the 4096-d rel_mlp output as one 16^3 latent channel
+    # (:246-248, hard-coded 16), apply_model routes it to c_concat (:281-283), p_losses as above
+    realc = RD.build(D.UNET_CONCAT_TINY, V.VQ_TINY, seed_unet=31, seed_vq=32, conditioning_key="concat")
+    csd = Wt.synth_state_dict(D.unet_param_shapes(D.UNET_CONCAT_TINY), seed=31)
+    relc = torch.randn(2, 1, 4096, generator=g)
+    x0c, noisec, tc = torch.randn(2, 3, 16, 16, 16, generator=g), torch.randn(2, 3, 16, 16, 16, generator=g), torch.tensor([12, 801])
+    realc.set_input({"sdf": torch.zeros(2, 1, 16, 16, 16), "rel": relc, "uc": relc})
+    ok &= tuple(realc.rel.shape) == (2, 1, 16, 16, 16)
+    _, _, lr, ldr = realc.p_losses(x0c, realc.rel, tc, noise=noisec)
+    _, _, lo, ldo = D.p_losses(csd, D.UNET_CONCAT_TINY, sched, x0c, relc.view(2, 1, 16, 16, 16), tc, noisec, concat=True)
+    ok &= _cmp("SDFusionText2ShapeModel[concat].p_losses.loss", lo, lr) and _cmp("p_losses[concat].loss_vlb", ldo["loss_vlb"], ldr["loss_vlb"])
     print("ORACLE PINNED" if ok else "ORACLE MISMATCH")
     return 0 if ok else 1
 
