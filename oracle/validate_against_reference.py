@@ -307,6 +307,18 @@ def main():
     _, _, lr, ldr = realc.p_losses(x0c, realc.rel, tc, noise=noisec)
     _, _, lo, ldo = D.p_losses(csd, D.UNET_CONCAT_TINY, sched, x0c, relc.view(2, 1, 16, 16, 16), tc, noisec, concat=True)
     ok &= _cmp("SDFusionText2ShapeModel[concat].p_losses.loss", lo, lr) and _cmp("p_losses[concat].loss_vlb", ldo["loss_vlb"], ldr["loss_vlb"])
+    # guided DDIM step of the concat variant through the reference's own sampler + wrapper (c_concat routing inside apply_model)
+    samp = DDIMSampler(realc)
+    samp.make_schedule(ddim_num_steps=100, ddim_eta=0.0, verbose=False)
+    ddc = D.ddim_schedule(sched, 100)
+    cvol, ucvol = relc.view(2, 1, 16, 16, 16), torch.randn(2, 1, 16, 16, 16, generator=g)
+    with torch.no_grad():
+        for index in (99, 37):
+            step = int(ddc["timesteps"][index])
+            xr, p0r = samp.p_sample_ddim(x0c, cvol, torch.full((2,), step, dtype=torch.long), index=index,
+                                         unconditional_guidance_scale=3.0, unconditional_conditioning=ucvol)
+            xo, p0o, _ = D.p_sample_ddim(csd, D.UNET_CONCAT_TINY, ddc, x0c, cvol, step, index, 3.0, ucvol, concat=True)
+            ok &= _cmp(f"DDIMSampler.p_sample_ddim[concat, index {index}].x_prev", xo, xr) and _cmp("  pred_x0", p0o, p0r)
     print("ORACLE PINNED" if ok else "ORACLE MISMATCH")
     return 0 if ok else 1
 
