@@ -262,6 +262,24 @@ def main():
     ok &= _cmp("SDFusionText2ShapeModel.p_losses.x_noisy", xo, xr, 0) and _cmp("p_losses.loss", lo, lr)
     for k in ("loss_simple", "loss_vlb", "loss_total"):
         ok &= _cmp(f"p_losses.loss_dict[{k}]", ldo[k], ldr[k])
+    # loss.backward() through the real class (what train_3dfront.py:390 does) vs autograd through the oracle: the gradients
+    # the CUDA backward kernels are tested against (tests/test_unet_train_gpu.py) are the reference's own
+    for p_ in real.df.parameters():
+        p_.grad = None
+    with torch.enable_grad():
+        _, _, lr2, _ = real.p_losses(x0, cond, t, noise=noise)
+        lr2.backward()
+        sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+        _, _, lo2, _ = D.p_losses(sdg, D.UNET_TINY, sched, x0, cond, t, noise)
+        og = dict(zip(sdg.keys(), torch.autograd.grad(lo2, list(sdg.values()), allow_unused=True)))
+    worst = 0.0
+    for k, p_ in real.df.named_parameters():
+        if p_.grad is None or og[k] is None:
+            ok &= (p_.grad is None or float(p_.grad.abs().max()) == 0.0) and (og[k] is None or float(og[k].abs().max()) == 0.0)
+            continue
+        worst = max(worst, float((p_.grad - og[k]).abs().max()) / max(1e-12, float(p_.grad.abs().max())))
+    print(f"{'ok ' if worst <= 1e-4 else 'BAD'} SDFusionText2ShapeModel loss.backward(): worst relative gradient difference oracle vs class {worst:.3e} over {len(og)} tensors")
+    ok &= worst <= 1e-4
     # forward(): same RNG draws in the same order
     sdf = (torch.randn(2, 1, 16, 16, 16, generator=g) * 0.1).clamp(-0.2, 0.2)
     rel = torch.randn(2, 1, D.UNET_TINY["context_dim"], generator=g)
