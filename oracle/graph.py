@@ -61,9 +61,32 @@ def _mlp(sd, name: str, x: Tensor, n_linear: int, final_nonlinearity: bool, trai
     return x
 
 
-def graph_triple_conv(sd, name: str, obj: Tensor, pred: Tensor, edges: Tensor, hidden: int, training: bool):
-    """GraphTripleConv.forward, pooling='avg', residual=True (graph.py:124-211)."""
-    O, dout = obj.shape[0], obj.shape[1]
+def gcn_net_shapes(s: Dict[str, Tuple[int, ...]], prefix: str, din_obj: int, din_pred: int, hidden: int, num_layers: int,
+                   output_dim=None) -> None:
+    """State-dict shapes of one GraphTripleConvNet (graph.py:214-243; BatchNorm + residual): every layer maps to din_obj
+    except the last one when output_dim is given."""
+    for l in range(num_layers):
+        dout = output_dim if (output_dim is not None and l >= num_layers - 1) else din_obj
+        p = f"{prefix}.gconvs.{l}"
+        _mlp_shapes(s, p + ".net1", [2 * din_obj + din_pred, hidden, 2 * hidden + dout])
+        _mlp_shapes(s, p + ".net2", [hidden, hidden, dout])
+        s[p + ".linear_projection.weight"] = (dout, din_obj); s[p + ".linear_projection.bias"] = (dout,)
+        s[p + ".linear_projection_pred.weight"] = (dout, din_pred); s[p + ".linear_projection_pred.bias"] = (dout,)
+
+
+def gcn_net(sd, prefix: str, obj: Tensor, pred: Tensor, edges: Tensor, hidden: int, num_layers: int, training: bool,
+            output_dim=None):
+    """GraphTripleConvNet.forward (graph.py:245-249)."""
+    for l in range(num_layers):
+        dout = output_dim if (output_dim is not None and l >= num_layers - 1) else None
+        obj, pred = graph_triple_conv(sd, f"{prefix}.gconvs.{l}", obj, pred, edges, hidden, training, dout=dout)
+    return obj, pred
+
+
+def graph_triple_conv(sd, name: str, obj: Tensor, pred: Tensor, edges: Tensor, hidden: int, training: bool, dout=None):
+    """GraphTripleConv.forward, pooling='avg', residual=True (graph.py:124-211).  dout: output_dim (default: the object width)."""
+    O = obj.shape[0]
+    dout = obj.shape[1] if dout is None else dout
     s_idx, o_idx = edges[:, 0].contiguous(), edges[:, 1].contiguous()
     t = _mlp(sd, name + ".net1", torch.cat([obj[s_idx], pred, obj[o_idx]], dim=1), 2, True, training)
     new_s, new_p, new_o = t[:, :hidden], t[:, hidden:hidden + dout], t[:, hidden + dout:2 * hidden + dout]

@@ -238,6 +238,47 @@ def main():
             uc, c = G.encoder_2(sd, cfg, *inp, training=training)
             ok &= _cmp(f"Sg2ScVAEModel.encoder_2.c[{tag},train={training}]", c, c_ref)
             ok &= _cmp(f"Sg2ScVAEModel.encoder_2.uc[{tag},train={training}]", uc, uc_ref)
+    # ---- layout branch of the REAL class (oracle/layout.py): encoder, manipulate, decoder, losses ----
+    from oracle import layout as Lo
+    sys.path.insert(0, REF)
+    for tag, lcfg in [("tiny", Lo.LAYOUT_TINY), ("full", Lo.LAYOUT_FULL)]:
+        real = RS.build(dict(lcfg, rel_hidden=960, rel_out=1280), seed=12)
+        shapes = Lo.layout_param_shapes(lcfg)
+        rsd = {k: tuple(v.shape) for k, v in RS.module_state_dict(real).items()}
+        bad = [k for k in shapes if rsd.get(k) != tuple(shapes[k])]
+        extra = sorted(k for k in rsd if k not in shapes and k not in G.gcn_param_shapes(dict(lcfg, rel_hidden=960, rel_out=1280)))
+        if bad or extra:
+            print(f"BAD layout[{tag}] keys: mismatch {bad[:5]} unaccounted {extra[:5]}")
+            ok = False
+        else:
+            print(f"ok  layout[{tag}]: {len(shapes)} layout-branch keys/shapes identical; with the shape branch they account for all {len(rsd)} keys of the class")
+        lsd = Wt.synth_state_dict(shapes, seed=13)
+        torch.nn.Module.load_state_dict(real, lsd, strict=False)
+        z_, objs_, triples_, text_, rel_ = synth_graph(dict(lcfg), 9, 20, seed=14)
+        gg = torch.Generator().manual_seed(15)
+        boxes = torch.randn(9, 6, generator=gg)
+        angles = torch.randint(0, 24, (9,), generator=gg)
+        zz = torch.randn(9, 2 * lcfg["embedding_dim"], generator=gg)
+        for training in (False, True):
+            real.train(training)
+            mu_r, lv_r = real.encoder(objs_, triples_, boxes, None, text_, rel_, angles)
+            mu_o, lv_o = Lo.encoder(lsd, lcfg, objs_, triples_, boxes, text_, rel_, angles, training)
+            ok &= _cmp(f"layout.encoder.mu[{tag},train={training}]", mu_o, mu_r) and _cmp("  logvar", lv_o, lv_r)
+            ok &= _cmp(f"layout.manipulate[{tag},train={training}]", Lo.manipulate(lsd, lcfg, zz, objs_, triples_, text_, rel_, training),
+                       real.manipulate(zz, objs_, triples_, text_, rel_, None))
+            b_r, a_r = real.decoder(z_, objs_, triples_, text_, rel_, None)
+            b_o, a_o = Lo.decoder(lsd, lcfg, z_, objs_, triples_, text_, rel_, training)
+            ok &= _cmp(f"layout.decoder.boxes[{tag},train={training}]", b_o, b_r) and _cmp("  angle log-probs", a_o, a_r)
+        from model.losses import calculate_model_losses
+
+        class _W:
+            def add_scalar(self, *a, **k):
+                pass
+        tot_r, _ = calculate_model_losses(None, b_r, boxes, "box", angles=angles, angles_pred=a_r, mu=mu_r, logvar=lv_r, KL_weight=0.1,
+                                          writer=_W(), counter=0, withangles=True)
+        tot_o, _ = Lo.layout_losses(b_o, boxes, a_o, angles, mu_o, lv_o, 0.1)
+        ok &= _cmp(f"layout.losses[{tag}]", tot_o, tot_r)
+
     # ---- the REAL SDFusionText2ShapeModel class on CPU (oracle/reference_diffusion_model.py): schedule, q_sample, p_losses,
     #      forward() = frozen VQ-VAE encode -> randint t -> randn noise -> p_losses (sdfusion_txt2shape_model.py:184-365) ----
     from oracle import reference_diffusion_model as RD

@@ -157,3 +157,25 @@ def test_rel2shape_chain_matches_the_reference_class_golden():
         z0, _ = D.ddim_sample(sd, D.UNET_TINY, sched, rel, uc, x_T, S=int(g["steps"]), eta=0.0, scale=3.0)
         sdf = V.decode_no_quant(vsd, vcfg, z0[torch.tensor(g["rows"])])
     _close(sdf, g["sdf"], tol=1e-3)
+
+
+@pytest.mark.parametrize("tag", ["tiny", "full"])
+def test_layout_branch_oracle_matches_reference_class_golden(tag):
+    """SURVEY.md §8f rank 2, first gate: the layout-branch oracle (encoder / manipulate / decoder / losses) vs what the
+    reference's REAL Sg2ScVAEModel computed (tests/golden/layout_*.npz), eval- and train-mode BatchNorm."""
+    from oracle import layout as Lo
+    cfg = Lo.LAYOUT_TINY if tag == "tiny" else Lo.LAYOUT_FULL
+    g = _load(f"layout_{tag}.npz")
+    sd = Wt.synth_state_dict(Lo.layout_param_shapes(cfg), int(g["weight_seed"]))
+    z, objs, triples, text, rel, boxes, angles, zz = (torch.tensor(g[k]) for k in ("z", "objs", "triples", "text", "rel", "boxes", "angles", "zz"))
+    with torch.no_grad():
+        for mode in ("eval", "train"):
+            tr = mode == "train"
+            mu, logvar = Lo.encoder(sd, cfg, objs, triples, boxes, text, rel, angles, tr)
+            _close(mu, g[f"mu_{mode}"]); _close(logvar, g[f"logvar_{mode}"])
+            _close(Lo.manipulate(sd, cfg, zz, objs, triples, text, rel, tr), g[f"man_{mode}"])
+            b, a = Lo.decoder(sd, cfg, z, objs, triples, text, rel, tr)
+            _close(b, g[f"boxes_{mode}"]); _close(a, g[f"angle_logp_{mode}"])
+            tot, terms = Lo.layout_losses(b, boxes, a, angles, mu, logvar, 0.1)
+            assert abs(float(tot) - float(g[f"loss_{mode}"])) <= 2e-5 * max(1.0, abs(float(tot)))
+            assert set(terms) == {"box", "angle_pred", "KLD_Gauss"}
