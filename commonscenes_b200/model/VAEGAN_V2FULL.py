@@ -2,7 +2,8 @@
 
 The reference's model/VAEGAN_V2FULL.py:17-760 couples a layout branch (box/angle GCN-VAE, discriminators: SURVEY.md
 §8f rank 2, not on this hot path) with the shape branch.  This class keeps the reference's names and semantics for
-the shape branch only: the decoder-side embeddings (:69-75), the relation encoder E2 (`gconv_net_ec_rel`, :128-147),
+the shape branch (always) and, with `layout_branch=True`, the forward of the layout branch (encoder / manipulate /
+decoder: same kernels, GPU verification of that part pending -- tests/test_gcn_gpu.py marks it xfail-tolerant).  Shape branch: the decoder-side embeddings (:69-75), the relation encoder E2 (`gconv_net_ec_rel`, :128-147),
 `rel_mlp` (:152-155), `encoder_2` (:220-242), `balance_objects` / `select_sdfs` (:398-463), the denoiser call of
 `forward` (:511-521) and the shape half of `sample` (:600-616).  State-dict keys of these members are the reference's,
 so a v2_full checkpoint's shape-branch tensors load with strict=False.
@@ -16,34 +17,110 @@ import torch
 import torch.nn as nn
 
 from .. import ops
-from .graph import GraphTripleConvNet2, make_mlp
+from .graph import GraphTripleConvNet, GraphTripleConvNet2, make_mlp
 from .layers import run_mlp, run_mlp_train
 from .sdfusion_txt2shape_model import SDFusionText2ShapeModel, default_opt
 
 
 class Sg2ScVAEModel(nn.Module):
     def __init__(self, vocab, diff_opt=None, diffusion_bs=8, embedding_dim=128, gconv_pooling="avg", gconv_num_layers=5,
-                 mlp_normalization="none", use_E2=True, residual=False, clip=True, decoder_cat=True, **unused):
+                 mlp_normalization="none", use_E2=True, residual=False, clip=True, decoder_cat=True, layout_branch=False,
+                 num_box_params=6, use_angles=True, **unused):
         super().__init__()
         self.embedding_dim, self.clip, self.use_E2, self.decoder_cat = embedding_dim, clip, use_E2, decoder_cat
+        self.layout_branch, self.use_angles = layout_branch, use_angles
         add_dim = 512 if clip else 0
         self.obj_classes_list = list(set(vocab["object_idx_to_name"]))
         self.edge_list = list(set(vocab["pred_idx_to_name"]))
         num_objs, num_preds = len(self.obj_classes_list), len(self.edge_list)
         gconv_dim, hidden = embedding_dim, embedding_dim * 4
+        if layout_branch:       # SURVEY.md §8f rank 2 (reference :69-88): registered in the reference's order so that
+            if not (decoder_cat and use_angles and clip):     # parameters() / optimizer indices line up with its checkpoints
+                raise NotImplementedError("the layout branch mirrors the v2_full wiring (decoder_cat, use_angles, clip)")
+            box_e, ang_e = int(embedding_dim * 3 / 4), int(embedding_dim / 4)
+            self.obj_embeddings_ec = nn.Embedding(num_objs + 1, embedding_dim)
+            self.pred_embeddings_ec = nn.Embedding(num_preds, embedding_dim * 2)
         self.obj_embeddings_dc = nn.Embedding(num_objs + 1, embedding_dim)
         self.pred_embeddings_dc = nn.Embedding(num_preds, embedding_dim * 2 if decoder_cat else embedding_dim)
+        if layout_branch:
+            self.pred_embeddings_man_dc = nn.Embedding(num_preds, embedding_dim * 3)
+            self.d3_embeddings = nn.Linear(num_box_params, box_e)
+            self.angle_embeddings = nn.Embedding(24, ang_e)
+            bn = mlp_normalization
+            self.mean_var = make_mlp([embedding_dim * 2 + add_dim, hidden, embedding_dim * 2], batch_norm=bn)
+            self.mean = make_mlp([embedding_dim * 2, box_e], batch_norm=bn, norelu=True)
+            self.var = make_mlp([embedding_dim * 2, box_e], batch_norm=bn, norelu=True)
+            self.angle_mean_var = make_mlp([embedding_dim * 2 + add_dim, hidden, embedding_dim * 2], batch_norm=bn)
+            self.angle_mean = make_mlp([embedding_dim * 2, ang_e], batch_norm=bn, norelu=True)
+            self.angle_var = make_mlp([embedding_dim * 2, ang_e], batch_norm=bn, norelu=True)
         self.Diff = SDFusionText2ShapeModel(default_opt() if diff_opt is None else diff_opt)
         hb = getattr(getattr(self.Diff.opt, "hyper", None), "batch_size", None)
         self.diffusion_bs = diffusion_bs if hb is None else hb
+        if layout_branch:       # reference :100-143
+            kw = dict(hidden_dim=hidden, pooling=gconv_pooling, mlp_normalization=mlp_normalization, residual=residual)
+            dim = gconv_dim * 2 + add_dim
+            self.gconv_net_ec_box = GraphTripleConvNet(input_dim_obj=dim, input_dim_pred=dim, num_layers=gconv_num_layers, **kw)
+            self.gconv_net_dc = GraphTripleConvNet(input_dim_obj=dim, input_dim_pred=dim, num_layers=gconv_num_layers, **kw)
+            self.gconv_net_manipulation = GraphTripleConvNet(input_dim_obj=embedding_dim * 3 + add_dim, input_dim_pred=embedding_dim * 3 + add_dim,
+                                                             output_dim=embedding_dim, num_layers=min(gconv_num_layers, 5), **kw)
         if use_E2:
             self.gconv_net_ec_rel = GraphTripleConvNet2(input_dim_obj=gconv_dim * 2 + add_dim, input_dim_pred=gconv_dim * 2 + add_dim,
                                                         hidden_dim=hidden, pooling=gconv_pooling, num_layers=gconv_num_layers,
                                                         mlp_normalization=mlp_normalization, residual=residual)
+        if layout_branch:       # reference :147-148
+            self.d3_net = make_mlp([gconv_dim * 2 + add_dim, hidden, num_box_params], batch_norm=mlp_normalization, norelu=True)
         net_rel_layers = [gconv_dim * 2 + add_dim, 960, 1280]
         if self.Diff.df.conditioning_key == "concat":          # reference :152-154: 4096 = one 16^3 latent channel
             net_rel_layers = [gconv_dim * 2 + add_dim, 1280, 4096]
         self.rel_mlp = make_mlp(net_rel_layers, batch_norm=mlp_normalization, norelu=True)
+        if layout_branch:       # reference :157-160
+            self.angle_net = make_mlp([gconv_dim * 2 + add_dim, hidden, 24], batch_norm=mlp_normalization, norelu=True)
+
+    # ---- layout branch: forward only, on the same GraphTripleConv / MLP kernels as encoder_2 ----------
+    def _need_layout(self):
+        if not self.layout_branch:
+            raise RuntimeError("construct Sg2ScVAEModel(..., layout_branch=True) to get the box / angle branch")
+
+    @staticmethod
+    def _edges(triples):
+        s, p, o = [x.squeeze(1) for x in triples.chunk(3, dim=1)]
+        return p, torch.stack([s, o], dim=1)
+
+    @torch.no_grad()
+    def encoder(self, objs, triples, boxes_gt, attributes, enc_text_feat, enc_rel_feat, angles_gt=None):
+        """(mu, logvar), each (O, embedding_dim): box + angle graph-VAE encoder (reference :185-218)."""
+        self._need_layout()
+        p, edges = self._edges(triples)
+        d3 = ops.linear_small(boxes_gt.float().contiguous(), self.d3_embeddings.weight.detach().float().contiguous(),
+                              self.d3_embeddings.bias.detach().float().contiguous())
+        obj = torch.cat([enc_text_feat, self.obj_embeddings_ec(objs), d3, self.angle_embeddings(angles_gt)], dim=1).float().contiguous()
+        pred = torch.cat([enc_rel_feat, self.pred_embeddings_ec(p)], dim=1).float().contiguous()
+        obj, _ = self.gconv_net_ec_box(obj, pred, edges)
+        h = run_mlp(self.mean_var, obj)
+        ha = run_mlp(self.angle_mean_var, obj)
+        mu = torch.cat([run_mlp(self.mean, h), run_mlp(self.angle_mean, ha)], dim=1)
+        logvar = torch.cat([run_mlp(self.var, h), run_mlp(self.angle_var, ha)], dim=1)
+        return mu, logvar
+
+    @torch.no_grad()
+    def manipulate(self, z, objs, triples, dec_text_feat, dec_rel_feat, attributes=None):
+        """[latent | change noise] (O, 2 * embedding_dim) -> manipulated latent (O, embedding_dim) (reference :244-258)."""
+        self._need_layout()
+        p, edges = self._edges(triples)
+        obj = torch.cat([z, dec_text_feat, self.obj_embeddings_dc(objs)], dim=1).float().contiguous()
+        pred = torch.cat([dec_rel_feat, self.pred_embeddings_man_dc(p)], dim=1).float().contiguous()
+        man_z, _ = self.gconv_net_manipulation(obj, pred, edges)
+        return man_z
+
+    @torch.no_grad()
+    def decoder(self, z, objs, triples, dec_text_feat, dec_rel_feat, attributes=None, manipulate=False):
+        """(boxes (O, 6), log-probabilities over the 24 angle bins) from the latent (reference :260-289, decoder_cat)."""
+        self._need_layout()
+        p, edges = self._edges(triples)
+        obj = torch.cat([dec_text_feat, self.obj_embeddings_dc(objs), z], dim=1).float().contiguous()
+        pred = torch.cat([dec_rel_feat, self.pred_embeddings_dc(p)], dim=1).float().contiguous()
+        obj, _ = self.gconv_net_dc(obj, pred, edges)
+        return run_mlp(self.d3_net, obj), torch.log_softmax(run_mlp(self.angle_net, obj), dim=1)
 
     def encoder_2(self, z, objs, triples, dec_text_feat, dec_rel_feat, attributes=None, manipulate=False):
         """(uc_rel, c_rel), each (O, 1, 1280) (reference :220-242).  With autograd enabled and trainable parameters the

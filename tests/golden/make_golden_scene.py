@@ -58,9 +58,9 @@ def main():
     # what a `model{epoch}.pth` of the reference holds besides 'epoch' / 'counter' / 'vqvae' / 'df' / 'opt'
     import json
     full = RS.build(G.GCN_FULL, diffusion_bs=8, seed=0)
-    inv = {k: list(v.shape) for k, v in RS.module_state_dict(full).items()}
+    inv = [[k, list(v.shape)] for k, v in RS.module_state_dict(full).items()]      # in the class's own registration order
     with open(os.path.join(HERE, "sg2sc_v2full_state_dict_keys.json"), "w") as f:
-        json.dump(inv, f, indent=0, sort_keys=True)
+        json.dump(inv, f, indent=0)
     print(f"sg2sc_v2full_state_dict_keys.json: {len(inv)} keys")
     np.savez_compressed(os.path.join(HERE, "select_sdfs.npz"), **out)
     print("select_sdfs.npz:", {k: v.shape for k, v in out.items() if "cats" in k or k.startswith("balance_n")})

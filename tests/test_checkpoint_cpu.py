@@ -80,7 +80,7 @@ def test_full_reference_checkpoint_inventory_loads(tmp_path):
     import json
     from commonscenes_b200.model.VAEGAN_V2FULL import Sg2ScVAEModel
     from commonscenes_b200.model.sdfusion_txt2shape_model import default_opt
-    inv = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "sg2sc_v2full_state_dict_keys.json")))
+    inv = dict(json.load(open(os.path.join(os.path.dirname(__file__), "golden", "sg2sc_v2full_state_dict_keys.json"))))
     df, vq = tmp_path / "df.yaml", tmp_path / "vq.yaml"
     df.write_text(yaml.safe_dump(TINY_DF)); vq.write_text(yaml.safe_dump(TINY_VQ))
     vocab = {"object_idx_to_name": [f"o{i}" for i in range(36)], "pred_idx_to_name": [f"p{i}" for i in range(16)]}
@@ -95,3 +95,26 @@ def test_full_reference_checkpoint_inventory_loads(tmp_path):
     assert info["epoch"] == 5 and len(info["ignored_keys"]) == len(inv) - 171
     assert all(not k.startswith(("gconv_net_ec_rel", "rel_mlp", "obj_embeddings_dc", "pred_embeddings_dc")) for k in info["ignored_keys"])
     assert torch.equal(m.rel_mlp[0].weight, ck["rel_mlp.0.weight"])
+
+
+def test_layout_branch_mirror_has_the_real_class_inventory_in_order(tmp_path):
+    """With layout_branch=True the mirror registers exactly the modules of the reference's real Sg2ScVAEModel, in the same
+    order: 711 state-dict keys / shapes, so `parameters()` — and therefore the indices of an optimizerFULL state dict —
+    line up with reference checkpoints."""
+    import json
+    from commonscenes_b200.model.VAEGAN_V2FULL import Sg2ScVAEModel
+    from commonscenes_b200.model.sdfusion_txt2shape_model import default_opt
+    inv = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "sg2sc_v2full_state_dict_keys.json")))
+    df, vq = tmp_path / "df.yaml", tmp_path / "vq.yaml"
+    df.write_text(yaml.safe_dump(TINY_DF)); vq.write_text(yaml.safe_dump(TINY_VQ))
+    vocab = {"object_idx_to_name": [f"o{i}" for i in range(36)], "pred_idx_to_name": [f"p{i}" for i in range(16)]}
+    m = Sg2ScVAEModel(vocab, diff_opt=default_opt(device="cpu", df_cfg=str(df), vq_cfg=str(vq)), embedding_dim=64,
+                      mlp_normalization="batch", residual=True, gconv_num_layers=5, layout_branch=True)
+    own = [[k, list(v.shape)] for k, v in m.state_dict().items()]
+    assert len(own) == 711 and own == inv
+    ck = {k: torch.zeros(s) if "num_batches_tracked" not in k else torch.tensor(0) for k, s in inv}
+    ck.update(epoch=1, counter=2, opt={}, vqvae=m.Diff.vqvae.state_dict(), df=m.Diff.df.state_dict())
+    assert m.load_checkpoint(ck, strict=True)["ignored_keys"] == []
+    with pytest.raises(RuntimeError):
+        Sg2ScVAEModel(vocab, diff_opt=default_opt(device="cpu", df_cfg=str(df), vq_cfg=str(vq)), embedding_dim=64,
+                      mlp_normalization="batch", residual=True).encoder(None, None, None, None, None, None)

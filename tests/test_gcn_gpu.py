@@ -144,3 +144,46 @@ def test_gcn_backward_kernels_edge_cases():
     dW = torch.zeros(6, 4).cuda()
     ops_bwd.embedding_bwd(rows.cuda(), 2, idx.cuda(), dW)
     assert torch.allclose(dW.cpu(), torch.zeros(6, 4).index_add(0, idx, rows[:, 2:6]), atol=1e-6)
+
+
+@pytest.mark.xfail(strict=False, reason="layout-branch forward (SURVEY.md 8f-2) was added after this round's GPU budget was spent: its first "
+                                        "GPU run is pending; it is built only from the GraphTripleConv / MLP kernels verified above")
+@pytest.mark.parametrize("tag", ["tiny", "full"])
+def test_layout_branch_forward_matches_reference_class_golden(tag, tmp_path):
+    """encoder / manipulate / decoder of Sg2ScVAEModel(layout_branch=True) vs what the reference's REAL class computed
+    (tests/golden/layout_*.npz), eval- and train-mode BatchNorm; fp32 kernels: 1e-4 relative to the output range."""
+    import yaml
+    from oracle import layout as Lo
+    from commonscenes_b200.model.VAEGAN_V2FULL import Sg2ScVAEModel
+    from commonscenes_b200.model.sdfusion_txt2shape_model import default_opt
+    cfg = Lo.LAYOUT_TINY if tag == "tiny" else Lo.LAYOUT_FULL
+    g = np.load(os.path.join(GOLD, f"layout_{tag}.npz"))
+    df = dict(model=dict(params=dict(linear_start=0.00085, linear_end=0.012, conditioning_key="crossattn", timesteps=1000)),
+              unet=dict(params=dict(image_size=8, in_channels=3, out_channels=3, model_channels=32, num_res_blocks=1,
+                                    attention_resolutions=[4, 2], channel_mult=[1, 2, 3], num_heads=4, dims=3, use_spatial_transformer=True,
+                                    transformer_depth=1, context_dim=1280, use_checkpoint=True, legacy=False)))
+    vq = dict(model=dict(params=dict(embed_dim=3, n_embed=64, ddconfig=dict(double_z=False, z_channels=3, resolution=16, in_channels=1, out_ch=1,
+                                                                           ch=16, ch_mult=[1, 2], num_res_blocks=1, attn_resolutions=[], dropout=0.0))))
+    (tmp_path / "df.yaml").write_text(yaml.safe_dump(df)); (tmp_path / "vq.yaml").write_text(yaml.safe_dump(vq))
+    vocab = {"object_idx_to_name": [f"o{i}" for i in range(cfg["num_objs"])], "pred_idx_to_name": [f"p{i}" for i in range(cfg["num_preds"])]}
+    m = Sg2ScVAEModel(vocab, diff_opt=default_opt(device="cuda", df_cfg=str(tmp_path / "df.yaml"), vq_cfg=str(tmp_path / "vq.yaml")),
+                      embedding_dim=cfg["embedding_dim"], mlp_normalization="batch", residual=True, gconv_num_layers=cfg["num_layers"],
+                      layout_branch=True).cuda()
+    shapes = Lo.layout_param_shapes(cfg)
+    z, objs, triples, text, rel, boxes, angles, zz = (torch.tensor(g[k]).cuda() for k in ("z", "objs", "triples", "text", "rel", "boxes", "angles", "zz"))
+
+    def reset():        # train mode updates the running statistics: restore the seeded state before every call
+        m.load_state_dict({k: Wt.synth_tensor(int(g["weight_seed"]), k, tuple(s)) for k, s in shapes.items()}, strict=False)
+
+    def check(got, key):
+        ref = torch.tensor(g[key])
+        err = float((got.cpu() - ref).abs().max())
+        print(f"layout[{tag}] {key}: max abs err {err:.3e} (ref absmax {float(ref.abs().max()):.3f})")
+        assert got.shape == ref.shape and err <= 1e-4 * max(1.0, float(ref.abs().max()))
+    for mode in ("eval", "train"):
+        m.train(mode == "train")
+        reset(); mu, logvar = m.encoder(objs, triples, boxes, None, text, rel, angles)
+        check(mu, f"mu_{mode}"); check(logvar, f"logvar_{mode}")
+        reset(); check(m.manipulate(zz, objs, triples, text, rel), f"man_{mode}")
+        reset(); b, a = m.decoder(z, objs, triples, text, rel)
+        check(b, f"boxes_{mode}"); check(a, f"angle_logp_{mode}")
