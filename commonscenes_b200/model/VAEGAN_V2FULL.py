@@ -122,6 +122,89 @@ class Sg2ScVAEModel(nn.Module):
         obj, _ = self.gconv_net_dc(obj, pred, edges)
         return run_mlp(self.d3_net, obj), torch.log_softmax(run_mlp(self.angle_net, obj), dim=1)
 
+    # ---- evaluation entry points tying both branches together (reference :291-396, 600-616; scripts/eval_3dfront.py) --------
+    def _shape_inputs(self, z, objs, triples, text_feat, rel_feat, dec_sdfs):
+        """encoder_2 -> the objects that own an SDF -> the dictionary SDFusionText2ShapeModel.rel2shape consumes."""
+        uc, c = self.encoder_2(z, objs, triples, text_feat, rel_feat)
+        ids = torch.unique(torch.where(torch.ne(dec_sdfs, torch.zeros_like(dec_sdfs[0])))[0])
+        c = uc if c is None else c
+        return {"sdf": dec_sdfs[ids], "rel": c[ids], "uc": uc[ids]}
+
+    def _insert_zero_nodes(self, z, missing_nodes, distribution=None):
+        """Reference :295-309 / :338-351: a latent row per added node (zeros, or a draw from the fitted Gaussian)."""
+        nodes_added = []
+        for i in range(len(missing_nodes)):
+            ad_id = missing_nodes[i] + i
+            nodes_added.append(ad_id)
+            if distribution is not None:
+                mu, cov = distribution
+                row = torch.from_numpy(np.random.multivariate_normal(mu, cov, 1)).float()
+            else:
+                row = torch.zeros(1, z.shape[1])
+            z = torch.cat([z[:ad_id], row.to(z.device), z[ad_id:]], dim=0)
+        return z, nodes_added
+
+    @torch.no_grad()
+    def sample(self, point_classes_idx, mean_est, cov_est, dec_objs, dec_triplets, dec_sdfs, encoded_dec_text_feat, encoded_dec_rel_feat,
+               attributes=None, gen_shape=False):
+        """Scene sampling (reference :600-616): z ~ N(mean_est, cov_est) per object (numpy RNG, as the reference), optional
+        shape generation for the objects that own an SDF, layout decoding -> ((boxes, angle log-probs), gen_sdf)."""
+        self._need_layout()
+        z = torch.from_numpy(np.random.multivariate_normal(mean_est, cov_est, dec_objs.size(0))).float().to(dec_objs.device)
+        gen_sdf = None
+        if gen_shape:
+            gen_sdf = self.Diff.rel2shape(self._shape_inputs(z, dec_objs, dec_triplets, encoded_dec_text_feat, encoded_dec_rel_feat, dec_sdfs),
+                                          uc_scale=3.)
+        return self.decoder(z, dec_objs, dec_triplets, encoded_dec_text_feat, encoded_dec_rel_feat, attributes), gen_sdf
+
+    @torch.no_grad()
+    def decoder_with_additions(self, z, objs, triples, encoded_dec_text_feat, encoded_dec_rel_feat, dec_sdfs, attributes, missing_nodes,
+                               manipulated_nodes, distribution=None, gen_shape=False):
+        """Node addition (reference :291-333): new nodes get a zero (or sampled) latent, everything is decoded as is."""
+        self._need_layout()
+        z, nodes_added = self._insert_zero_nodes(z, missing_nodes, distribution)
+        gen_sdf = None
+        if gen_shape:
+            gen_sdf = self.Diff.rel2shape(self._shape_inputs(z, objs, triples, encoded_dec_text_feat, encoded_dec_rel_feat, dec_sdfs), uc_scale=3.)
+        pred = self.decoder(z, objs, triples, encoded_dec_text_feat, encoded_dec_rel_feat, attributes)
+        keep = [0.0 if (i in nodes_added or i in manipulated_nodes) else 1.0 for i in range(len(z))]
+        return pred, gen_sdf, torch.tensor(keep, device=z.device).view(-1, 1)
+
+    @torch.no_grad()
+    def decoder_with_changes(self, z, dec_objs, dec_triples, encoded_dec_text_feat, encoded_dec_rel_feat, dec_sdfs, attributes, missing_nodes,
+                             manipulated_nodes, distribution=None, gen_shape=False):
+        """Scene manipulation (reference :335-396): touched nodes (added or edited) get change noise, the manipulator GCN
+        predicts their new latents, untouched nodes keep theirs; then shapes (optional) and layout are decoded."""
+        self._need_layout()
+        z, nodes_added = self._insert_zero_nodes(z, missing_nodes, distribution)
+        change = [np.random.normal(0, 1, self.embedding_dim) if (i in nodes_added or i in manipulated_nodes) else np.zeros(self.embedding_dim)
+                  for i in range(len(z))]
+        change_repr = torch.from_numpy(np.stack(change, axis=0)).float().to(z.device)
+        z_prime = self.manipulate(torch.cat([z, change_repr], dim=1), dec_objs, dec_triples, encoded_dec_text_feat, encoded_dec_rel_feat, attributes)
+        if not getattr(self, "replace_all_latent", False):
+            for node in sorted(nodes_added + list(manipulated_nodes)):
+                z = torch.cat([z[:node], z_prime[node:node + 1], z[node + 1:]], dim=0)
+        else:
+            z = z_prime
+        gen_sdf = None
+        if gen_shape:
+            gen_sdf = self.Diff.rel2shape(self._shape_inputs(z, dec_objs, dec_triples, encoded_dec_text_feat, encoded_dec_rel_feat, dec_sdfs),
+                                          uc_scale=3.)
+        pred = self.decoder(z, dec_objs, dec_triples, encoded_dec_text_feat, encoded_dec_rel_feat, attributes)
+        keep = [0.0 if (i in nodes_added or i in manipulated_nodes) else 1.0 for i in range(len(pred[0]))]
+        return pred, gen_sdf, torch.tensor(keep, device=z.device).view(-1, 1)
+
+    @staticmethod
+    def lr_lambda(counter):
+        """Step schedule of optimizerFULL (reference :620-633): 1e-4 -> 5e-5 (20k) -> 1e-5 (60k) -> 5e-6 (100k)."""
+        if counter < 20000:
+            return 1.0
+        if counter < 60000:
+            return 5e-5 / 1e-4
+        if counter < 100000:
+            return 1e-5 / 1e-4
+        return 5e-6 / 1e-4
+
     def encoder_2(self, z, objs, triples, dec_text_feat, dec_rel_feat, attributes=None, manipulate=False):
         """(uc_rel, c_rel), each (O, 1, 1280) (reference :220-242).  With autograd enabled and trainable parameters the
         outputs carry a grad_fn whose backward runs the explicit GCN / MLP gradient kernels (encoder_2_backward) and fills

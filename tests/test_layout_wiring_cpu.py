@@ -70,3 +70,52 @@ def test_layout_forward_wiring_matches_reference_class(tag, tmp_path, monkeypatc
         for got, key in ((mu, "mu"), (logvar, "logvar"), (man, "man"), (b, "boxes"), (a, "angle_logp")):
             ref = torch.tensor(g[f"{key}_{mode}"])
             assert got.shape == ref.shape and float((got - ref).abs().max()) <= 2e-5 * max(1.0, float(ref.abs().max())), (key, mode)
+
+
+def test_eval_entry_points_match_the_reference_class(tmp_path, monkeypatch):
+    """Sg2ScVAEModel.sample / decoder_with_changes / decoder_with_additions / lr_lambda (the calls scripts/eval_3dfront.py and
+    the trainer make) vs the reference's REAL class (tests/golden/scene_eval.npz): same numpy RNG draws, node insertion,
+    change noise, manipulator, objects / conditioning handed to the denoiser, layout decode and `keep` mask.  Kernel entry
+    points are torch stand-ins here (host wiring only); Diff.rel2shape is a recorder on both sides."""
+    from oracle import graph as G
+    _stand_ins(monkeypatch)
+    from commonscenes_b200.model.VAEGAN_V2FULL import Sg2ScVAEModel
+    from commonscenes_b200.model.sdfusion_txt2shape_model import default_opt
+    g = np.load(os.path.join(GOLD, "scene_eval.npz"))
+    cfg = dict(Lo.LAYOUT_TINY, rel_hidden=960, rel_out=1280)
+    (tmp_path / "df.yaml").write_text(yaml.safe_dump(TINY_DF)); (tmp_path / "vq.yaml").write_text(yaml.safe_dump(TINY_VQ))
+    vocab = {"object_idx_to_name": [f"o{i}" for i in range(cfg["num_objs"])], "pred_idx_to_name": [f"p{i}" for i in range(cfg["num_preds"])]}
+    m = Sg2ScVAEModel(vocab, diff_opt=default_opt(device="cpu", df_cfg=str(tmp_path / "df.yaml"), vq_cfg=str(tmp_path / "vq.yaml")),
+                      embedding_dim=64, mlp_normalization="batch", residual=True, gconv_num_layers=cfg["num_layers"], layout_branch=True)
+    shapes = dict(Lo.layout_param_shapes(Lo.LAYOUT_TINY)); shapes.update(G.gcn_param_shapes(cfg))
+    m.load_state_dict(Wt.synth_state_dict(shapes, int(g["weight_seed"])), strict=True)
+    m.eval()
+    rec = {}
+
+    def rel2shape(d, uc_scale=None, **kw):
+        rec["d"] = d
+        return d["rel"].sum(dim=(1, 2))
+    monkeypatch.setattr(m.Diff, "rel2shape", rel2shape)
+    z, objs, triples, text, rel, sdfs = (torch.tensor(g[k]) for k in ("z", "objs", "triples", "text", "rel", "sdfs"))
+    mean_est, cov_est = g["mean_est"], g["cov_est"]
+
+    def same(got, key, tol=2e-5):
+        ref = torch.tensor(g[key])
+        assert tuple(got.shape) == tuple(ref.shape), key
+        assert float((got - ref).abs().max()) <= tol * max(1.0, float(ref.abs().max())), key
+
+    np.random.seed(7)
+    (boxes, ang), gen = m.sample(None, mean_est, cov_est, objs, triples, sdfs, text, rel, None, gen_shape=True)
+    same(boxes, "sample_boxes"); same(ang, "sample_angles"); same(gen, "sample_gen")
+    same(rec["d"]["rel"], "sample_rel"); same(rec["d"]["uc"], "sample_uc"); same(rec["d"]["sdf"], "sample_sdf", 0)
+    np.random.seed(8)
+    (boxes, ang), gen, keep = m.decoder_with_changes(z[:-1], objs, triples, text, rel, sdfs, None, [3], [5], gen_shape=True)
+    same(boxes, "chg_boxes"); same(ang, "chg_angles"); same(keep, "chg_keep", 0); same(rec["d"]["rel"], "chg_rel"); same(rec["d"]["uc"], "chg_uc")
+    np.random.seed(9)
+    (boxes, ang), gen, keep = m.decoder_with_changes(z[:-1], objs, triples, text, rel, sdfs, None, [3], [5], distribution=(mean_est, cov_est))
+    same(boxes, "chgd_boxes"); same(keep, "chgd_keep", 0)
+    assert gen is None
+    np.random.seed(10)
+    (boxes, ang), gen, keep = m.decoder_with_additions(z[:-2], objs, triples, text, rel, sdfs, None, [2, 6], [0], gen_shape=True)
+    same(boxes, "add_boxes"); same(ang, "add_angles"); same(keep, "add_keep", 0); same(rec["d"]["rel"], "add_rel")
+    assert np.allclose([m.lr_lambda(c) for c in (0, 19999, 20000, 59999, 60000, 99999, 100000, 10 ** 7)], g["lr_lambda"])
