@@ -367,6 +367,47 @@ class Sg2ScVAEModel(nn.Module):
         group["params"] = list(range(n))
         return {"state": {j: opt_state["state"][i] for j, i in enumerate(tail) if i in opt_state["state"]}, "param_groups": [group]}
 
+    def forward(self, enc_objs, enc_triples, enc, enc_text_feat, enc_rel_feat, attributes, enc_objs_to_scene, dec_objs, dec_objs_grained,
+                dec_triples, dec, dec_text_feat, dec_rel_feat, dec_attributes, dec_objs_to_scene, missing_nodes, manipulated_nodes, dec_sdfs,
+                enc_angles=None, dec_angles=None):
+        """The training forward the reference's trainer calls (VAEGAN_V2FULL.py:466-560, via VAE.forward_mani): encode the
+        layout -> reparameterise -> insert added nodes -> manipulate touched nodes -> scene-graph conditioning (encoder_2) ->
+        object selection -> diffusion loss (self.Diff.loss_df, with its grad_fn) -> decode the layout.  Returns the reference's
+        tuple (mu, logvar, orig_gt_d3, orig_gt_angles, orig_gt_shapes, orig_d3, orig_angles, d3_pred, angles_pred,
+        [obj_selected, None], keep).  Layout tensors carry no gradient here (its backward is not built); the shape branch's
+        loss back-propagates into the denoiser, rel_mlp, gconv_net_ec_rel and the decoder embeddings."""
+        self._need_layout()
+        mu, logvar = self.encoder(enc_objs, enc_triples, enc, attributes, enc_text_feat, enc_rel_feat, enc_angles)
+        if getattr(self, "use_AE", False):
+            z = mu
+        else:
+            std = torch.exp(0.5 * logvar)
+            z = torch.randn_like(std).mul(std).add_(mu)
+        z, nodes_added = self._insert_zero_nodes(z, missing_nodes)
+        change = [np.random.normal(0, 1, self.embedding_dim) if (i in nodes_added or i in manipulated_nodes) else np.zeros(self.embedding_dim)
+                  for i in range(len(z))]
+        change_repr = torch.from_numpy(np.stack(change, axis=0)).float().to(z.device)
+        z_prime = self.manipulate(torch.cat([z, change_repr], dim=1), dec_objs, dec_triples, dec_text_feat, dec_rel_feat, attributes)
+        if not getattr(self, "replace_all_latent", False):
+            for node in sorted(nodes_added + list(manipulated_nodes)):
+                z = torch.cat([z[:node], z_prime[node:node + 1], z[node + 1:]], dim=0)
+        else:
+            z = z_prime
+        uc_rel_feat, c_rel_feat = self.encoder_2(z, dec_objs, dec_triples, dec_text_feat, dec_rel_feat, attributes)
+        if c_rel_feat is None:
+            c_rel_feat = uc_rel_feat
+        obj_selected, diff_dict = self.select_sdfs(dec_objs_to_scene, dec_objs, dec_objs_grained, dec_sdfs, uc_rel_feat, c_rel_feat, random=False)
+        self.Diff.set_input(diff_dict)
+        self.Diff.set_requires_grad([self.Diff.df], requires_grad=True)
+        self.Diff.forward()
+        d3_pred, angles_pred = self.decoder(z, dec_objs, dec_triples, dec_text_feat, dec_rel_feat, attributes)
+        kept = [i for i in range(len(d3_pred)) if i not in nodes_added and i not in manipulated_nodes]
+        idx = torch.tensor(kept, dtype=torch.long, device=d3_pred.device)
+        keep = torch.zeros(len(d3_pred), 1, device=d3_pred.device)
+        keep[idx] = 1.0
+        return (mu, logvar, dec[idx], dec_angles[idx], dec_sdfs[idx], d3_pred[idx], angles_pred[idx], d3_pred, angles_pred,
+                [obj_selected, None], keep)
+
     def forward_shape(self, z, dec_objs, dec_objs_grained, dec_triples, dec_text_feat, dec_rel_feat, dec_sdfs, dec_objs_to_scene):
         """The shape-branch lines of Sg2ScVAEModel.forward (:511-521): conditioning -> object selection -> diffusion loss."""
         uc, c = self.encoder_2(z, dec_objs, dec_triples, dec_text_feat, dec_rel_feat)

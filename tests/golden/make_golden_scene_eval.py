@@ -65,6 +65,30 @@ def main():
     np.random.seed(10)
     (boxes, ang), gen, keep = real.decoder_with_additions(z[:-2], objs, triples, text, rel, sdfs, None, [2, 6], [0], gen_shape=True)
     out.update(add_boxes=boxes.numpy(), add_angles=ang.numpy(), add_keep=keep.numpy(), add_rel=rec["d"]["rel"].numpy())
+    # ---- the training forward (VAEGAN_V2FULL.py:466-560): two scenes, one node added, one node manipulated ----
+    import random
+    real.train()
+    torch.nn.Module.load_state_dict(real, Wt.synth_state_dict(shapes, SEED), strict=True)
+    seen = {}
+    real.Diff.set_input = lambda d: seen.update(d={k: v.clone() for k, v in d.items()})
+    real.Diff.set_requires_grad = lambda *a, **k: None
+    real.Diff.forward = lambda: None
+    real.diffusion_bs = 6
+    g2 = torch.Generator().manual_seed(502)
+    enc_objs, enc_triples = objs[:-1], triples[(triples[:, 0] < O - 1) & (triples[:, 2] < O - 1)]       # the encoder graph lacks the added node
+    enc_boxes, enc_angles = torch.randn(O - 1, 6, generator=g2), torch.randint(0, 24, (O - 1,), generator=g2)
+    dec_boxes, dec_angles = torch.randn(O, 6, generator=g2), torch.randint(0, 24, (O,), generator=g2)
+    enc_text, enc_rel = text[:-1], torch.randn(enc_triples.shape[0], 512, generator=g2)
+    scene_of = torch.tensor([0, 0, 0, 0, 1, 1, 1, 1, 1])
+    grained = objs * 2
+    torch.manual_seed(11); np.random.seed(12); random.seed(13)
+    res = real.forward(enc_objs, enc_triples, enc_boxes, enc_text, enc_rel, None, None, objs, grained, triples, dec_boxes, text, rel, None,
+                       scene_of, [8], [2], sdfs, enc_angles=enc_angles, dec_angles=dec_angles)
+    names = ("mu", "logvar", "orig_gt_d3", "orig_gt_angles", "orig_gt_shapes", "orig_d3", "orig_angles", "d3_pred", "angles_pred")
+    out.update({f"fwd_{n}": r.numpy() for n, r in zip(names, res[:9])})
+    out.update(fwd_obj_selected=res[9][0].numpy(), fwd_keep=res[10].numpy(), fwd_rel=seen["d"]["rel"].numpy(), fwd_uc=seen["d"]["uc"].numpy(),
+               fwd_sdf=seen["d"]["sdf"].numpy(), fwd_enc_triples=enc_triples.numpy(), fwd_enc_boxes=enc_boxes.numpy(), fwd_enc_angles=enc_angles.numpy(),
+               fwd_dec_boxes=dec_boxes.numpy(), fwd_dec_angles=dec_angles.numpy(), fwd_enc_rel=enc_rel.numpy(), fwd_scene_of=scene_of.numpy())
     out["lr_lambda"] = np.asarray([real.lr_lambda(c) for c in (0, 19999, 20000, 59999, 60000, 99999, 100000, 10 ** 7)])
     np.savez_compressed(os.path.join(HERE, "scene_eval.npz"), **out)
     print("scene_eval.npz:", {k: v.shape for k, v in out.items() if k.endswith(("boxes", "keep"))})
