@@ -194,6 +194,30 @@ class Sg2ScVAEModel(nn.Module):
         keep = [0.0 if (i in nodes_added or i in manipulated_nodes) else 1.0 for i in range(len(pred[0]))]
         return pred, gen_sdf, torch.tensor(keep, device=z.device).view(-1, 1)
 
+    @torch.no_grad()
+    def collect_train_statistics(self, train_loader, with_points=False):
+        """Mean and covariance of the layout latents over a data loader (reference :700-760): the Gaussian `sample` draws
+        from.  Batches are the collate dictionaries of the reference's dataset (data['decoder'][...]); a batch equal to -1
+        is skipped; box rows are [6 box parameters | angle bin + 1]."""
+        self._need_layout()
+        dev = self.obj_embeddings_dc.weight.device
+        means = []
+        for data in train_loader:
+            if isinstance(data, int) and data == -1:
+                continue
+            d = data["decoder"]
+            objs, triples, tight_boxes = d["objs"].to(dev), d["tripltes"].to(dev), d["boxes"].to(dev)
+            text = d["text_feats"].to(dev) if "text_feats" in d and "rel_feats" in d else None
+            rel = d["rel_feats"].to(dev) if text is not None else None
+            angles = tight_boxes[:, 6].long() - 1
+            angles = torch.where(angles > 0, angles, torch.zeros_like(angles))
+            mean, _ = self.encoder(objs, triples, tight_boxes[:, :6], None, text, rel, angles)
+            means.append(mean.cpu().clone())
+        mean_cat = torch.cat(means, dim=0)
+        mean_est = torch.mean(mean_cat, dim=0, keepdim=True)
+        cov_est = np.cov((mean_cat - mean_est).numpy().T)
+        return mean_est[0], cov_est
+
     @staticmethod
     def lr_lambda(counter):
         """Step schedule of optimizerFULL (reference :620-633): 1e-4 -> 5e-5 (20k) -> 1e-5 (60k) -> 5e-6 (100k)."""

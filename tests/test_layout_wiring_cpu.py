@@ -160,3 +160,63 @@ def test_training_forward_matches_the_reference_class(tmp_path, monkeypatch):
     for k in ("rel", "uc", "sdf"):
         ref = t(f"fwd_{k}")
         assert float((seen["d"][k] - ref).abs().max()) <= 2e-5 * max(1.0, float(ref.abs().max())), k
+
+
+def test_vae_dispatcher_v2_full(tmp_path, monkeypatch):
+    """model.VAE.VAE(type='v2_full') — the class the reference's scripts construct: yaml path in, forward_mani's 14-tuple,
+    checkpoint save / load_networks in the reference's directory layout, latent statistics for sampling."""
+    from oracle import graph as G
+    _stand_ins(monkeypatch)
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    from commonscenes_b200.model.VAE import VAE
+    (tmp_path / "df.yaml").write_text(yaml.safe_dump(TINY_DF)); (tmp_path / "vq.yaml").write_text(yaml.safe_dump(TINY_VQ))
+    v2 = dict(hyper=dict(batch_size=6, isTrain=True, device="cpu", distributed=0),
+              network=dict(df_cfg=str(tmp_path / "df.yaml"), vq_cfg=str(tmp_path / "vq.yaml"), vq_ckpt=None, ddim_steps=100, ddim_eta=0.0, uc_scale=3.0),
+              misc=dict(debug=0, seed=111, local_rank=0))
+    (tmp_path / "v2_full.yaml").write_text(yaml.safe_dump(v2))
+    vocab = {"object_idx_to_name": [f"o{i}" for i in range(10)], "pred_idx_to_name": [f"p{i}" for i in range(6)]}
+    with pytest.raises(NotImplementedError):
+        VAE(type="v1_box", vocab=vocab)
+    torch.manual_seed(3)
+    m = VAE(root=str(tmp_path), type="v2_full", diff_opt=str(tmp_path / "v2_full.yaml"), vocab=vocab, with_angles=True, residual=True)
+    assert m.vae_v2.diffusion_bs == 6 and len(m.vae_v2.state_dict()) == 711
+    g = np.load(os.path.join(GOLD, "scene_eval.npz"))
+    t = lambda k: torch.tensor(g[k])
+    objs, triples, text, rel, sdfs = t("objs"), t("triples"), t("text"), t("rel"), t("sdfs")
+    monkeypatch.setattr(m.vae_v2.Diff, "set_input", lambda d: None)
+    monkeypatch.setattr(m.vae_v2.Diff, "forward", lambda: None)
+    args = (objs[:-1], t("fwd_enc_triples"), t("fwd_enc_boxes"), t("fwd_enc_angles"), None, text[:-1], t("fwd_enc_rel"), None, None, objs, objs * 2,
+            triples, t("fwd_dec_boxes"), t("fwd_dec_angles"), sdfs, None, text, rel, None, t("fwd_scene_of"), [8], [2])
+    import random
+    with torch.no_grad():
+        torch.manual_seed(1); np.random.seed(2); random.seed(3)
+        out = m.forward_mani(*args)
+        torch.manual_seed(1); np.random.seed(2); random.seed(3)
+        ref = m.vae_v2.forward(args[0], args[1], args[2], args[5], args[6], None, None, objs, objs * 2, triples, args[12], text, rel, None,
+                               args[19], [8], [2], sdfs, args[3], args[13])
+    assert len(out) == 14 and out[2] is None and out[3] is None and out[9] is None
+    for a, b in zip((out[0], out[1], out[4], out[5], out[6], out[7], out[8], out[10], out[11], out[13]),
+                    (ref[0], ref[1], ref[2], ref[3], ref[4], ref[5], ref[6], ref[7], ref[8], ref[10])):
+        assert torch.equal(a, b)
+    # checkpoint directory layout of the reference: <exp>/checkpoint/model{epoch}.pth
+    os.makedirs(tmp_path / "exp" / "checkpoint")
+    m.save(str(tmp_path / "exp"), "checkpoint", 7, counter=123)
+    torch.manual_seed(4)
+    m2 = VAE(root=str(tmp_path), type="v2_full", diff_opt=str(tmp_path / "v2_full.yaml"), vocab=vocab, with_angles=True, residual=True)
+    assert not torch.equal(m2.vae_v2.rel_mlp[0].weight, m.vae_v2.rel_mlp[0].weight)
+    m2.load_networks(str(tmp_path / "exp"), 7)
+    assert m2.epoch == 7 and m2.counter == 123
+    for (k, a), (_, b) in zip(m.vae_v2.state_dict().items(), m2.vae_v2.state_dict().items()):
+        assert torch.equal(a, b), k
+    # latent statistics (collect_train_statistics): mean / covariance of the encoder means over a loader, -1 batches skipped
+    m.eval()
+    boxes7 = torch.cat([t("fwd_dec_boxes"), (t("fwd_dec_angles") + 1).float()[:, None]], dim=1)
+    batch = {"decoder": {"objs": objs, "tripltes": triples, "boxes": boxes7, "obj_to_scene": None, "triple_to_scene": None, "text_feats": text,
+                         "rel_feats": rel}}
+    m.compute_statistics(str(tmp_path / "exp"), 7, [batch, -1, batch])
+    ang = torch.where(t("fwd_dec_angles") > 0, t("fwd_dec_angles"), torch.zeros_like(t("fwd_dec_angles")))
+    with torch.no_grad():
+        mu, _ = m.vae_v2.encoder(objs, triples, t("fwd_dec_boxes"), None, text, rel, ang)
+    mu2 = torch.cat([mu, mu])
+    assert torch.allclose(m.mean_est, mu2.mean(0), atol=1e-6) and np.allclose(m.cov_est, np.cov((mu2 - mu2.mean(0)).numpy().T), atol=1e-6)
+    assert os.path.exists(tmp_path / "exp" / "checkpoint" / "model_stats_7.pkl")
