@@ -17,8 +17,8 @@ import torch
 import torch.nn as nn
 
 from .. import ops
-from .graph import GraphTripleConvNet, GraphTripleConvNet2, make_mlp
-from .layers import run_mlp, run_mlp_train
+from .graph import GraphTripleConvNet, GraphTripleConvNet2, gcn_apply, make_mlp
+from .layers import mlp_apply, run_mlp, run_mlp_train
 from .sdfusion_txt2shape_model import SDFusionText2ShapeModel, default_opt
 
 
@@ -86,41 +86,39 @@ class Sg2ScVAEModel(nn.Module):
         s, p, o = [x.squeeze(1) for x in triples.chunk(3, dim=1)]
         return p, torch.stack([s, o], dim=1)
 
-    @torch.no_grad()
     def encoder(self, objs, triples, boxes_gt, attributes, enc_text_feat, enc_rel_feat, angles_gt=None):
-        """(mu, logvar), each (O, embedding_dim): box + angle graph-VAE encoder (reference :185-218)."""
+        """(mu, logvar), each (O, embedding_dim): box + angle graph-VAE encoder (reference :185-218).  Like every layout
+        method it takes part in autograd: with gradients enabled `loss.backward()` runs the explicit GCN / MLP backward
+        kernels (graph.gcn_apply, layers.mlp_apply); embedding lookups, concatenations and the losses are torch glue."""
         self._need_layout()
         p, edges = self._edges(triples)
-        d3 = ops.linear_small(boxes_gt.float().contiguous(), self.d3_embeddings.weight.detach().float().contiguous(),
-                              self.d3_embeddings.bias.detach().float().contiguous())
+        d3 = mlp_apply([self.d3_embeddings], boxes_gt.float().contiguous())
         obj = torch.cat([enc_text_feat, self.obj_embeddings_ec(objs), d3, self.angle_embeddings(angles_gt)], dim=1).float().contiguous()
         pred = torch.cat([enc_rel_feat, self.pred_embeddings_ec(p)], dim=1).float().contiguous()
-        obj, _ = self.gconv_net_ec_box(obj, pred, edges)
-        h = run_mlp(self.mean_var, obj)
-        ha = run_mlp(self.angle_mean_var, obj)
-        mu = torch.cat([run_mlp(self.mean, h), run_mlp(self.angle_mean, ha)], dim=1)
-        logvar = torch.cat([run_mlp(self.var, h), run_mlp(self.angle_var, ha)], dim=1)
+        obj, _ = gcn_apply(self.gconv_net_ec_box, obj, pred, edges)
+        h = mlp_apply(self.mean_var, obj)
+        ha = mlp_apply(self.angle_mean_var, obj)
+        mu = torch.cat([mlp_apply(self.mean, h), mlp_apply(self.angle_mean, ha)], dim=1)
+        logvar = torch.cat([mlp_apply(self.var, h), mlp_apply(self.angle_var, ha)], dim=1)
         return mu, logvar
 
-    @torch.no_grad()
     def manipulate(self, z, objs, triples, dec_text_feat, dec_rel_feat, attributes=None):
         """[latent | change noise] (O, 2 * embedding_dim) -> manipulated latent (O, embedding_dim) (reference :244-258)."""
         self._need_layout()
         p, edges = self._edges(triples)
         obj = torch.cat([z, dec_text_feat, self.obj_embeddings_dc(objs)], dim=1).float().contiguous()
         pred = torch.cat([dec_rel_feat, self.pred_embeddings_man_dc(p)], dim=1).float().contiguous()
-        man_z, _ = self.gconv_net_manipulation(obj, pred, edges)
+        man_z, _ = gcn_apply(self.gconv_net_manipulation, obj, pred, edges)
         return man_z
 
-    @torch.no_grad()
     def decoder(self, z, objs, triples, dec_text_feat, dec_rel_feat, attributes=None, manipulate=False):
         """(boxes (O, 6), log-probabilities over the 24 angle bins) from the latent (reference :260-289, decoder_cat)."""
         self._need_layout()
         p, edges = self._edges(triples)
         obj = torch.cat([dec_text_feat, self.obj_embeddings_dc(objs), z], dim=1).float().contiguous()
         pred = torch.cat([dec_rel_feat, self.pred_embeddings_dc(p)], dim=1).float().contiguous()
-        obj, _ = self.gconv_net_dc(obj, pred, edges)
-        return run_mlp(self.d3_net, obj), torch.log_softmax(run_mlp(self.angle_net, obj), dim=1)
+        obj, _ = gcn_apply(self.gconv_net_dc, obj, pred, edges)
+        return mlp_apply(self.d3_net, obj), torch.log_softmax(mlp_apply(self.angle_net, obj), dim=1)
 
     # ---- evaluation entry points tying both branches together (reference :291-396, 600-616; scripts/eval_3dfront.py) --------
     def _shape_inputs(self, z, objs, triples, text_feat, rel_feat, dec_sdfs):
@@ -398,8 +396,8 @@ class Sg2ScVAEModel(nn.Module):
         layout -> reparameterise -> insert added nodes -> manipulate touched nodes -> scene-graph conditioning (encoder_2) ->
         object selection -> diffusion loss (self.Diff.loss_df, with its grad_fn) -> decode the layout.  Returns the reference's
         tuple (mu, logvar, orig_gt_d3, orig_gt_angles, orig_gt_shapes, orig_d3, orig_angles, d3_pred, angles_pred,
-        [obj_selected, None], keep).  Layout tensors carry no gradient here (its backward is not built); the shape branch's
-        loss back-propagates into the denoiser, rel_mlp, gconv_net_ec_rel and the decoder embeddings."""
+        [obj_selected, None], keep).  With autograd enabled every returned tensor and self.Diff.loss_df carry grad_fns: the
+        trainer's `loss.backward()` (train_3dfront.py:387-390) reaches all branches through the explicit backward kernels."""
         self._need_layout()
         mu, logvar = self.encoder(enc_objs, enc_triples, enc, attributes, enc_text_feat, enc_rel_feat, enc_angles)
         if getattr(self, "use_AE", False):

@@ -134,5 +134,37 @@ class GraphTripleConvNet(nn.Module):
         return d_obj, d_pred
 
 
+class _GcnNetFunction(torch.autograd.Function):
+    """Autograd bridge for a whole GraphTripleConvNet: forward = forward_train, backward = the explicit backward kernels."""
+
+    @staticmethod
+    def forward(ctx, net, obj_vecs, pred_vecs, edges, *params):
+        o, p, tapes = net.forward_train(obj_vecs.detach(), pred_vecs.detach(), edges)
+        ctx.net, ctx.tapes, ctx.params = net, tapes, params
+        ctx.need = (obj_vecs.requires_grad, pred_vecs.requires_grad)
+        ctx.set_materialize_grads(False)
+        return o, p
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, d_o, d_p):
+        from .networks.diffusion_networks.unet_train import GradSink
+        sink = GradSink()
+        if d_o is None:       # only the predicate output was used downstream
+            last = ctx.net.gconvs[-1]
+            d_o = torch.zeros((ctx.tapes[-1][0].shape[0], last.output_dim), dtype=torch.float32, device=d_p.device)
+        d_obj, d_pred = ctx.net.backward(ctx.tapes, d_o, d_p, sink)
+        ctx.tapes = None
+        return (None, d_obj if ctx.need[0] else None, d_pred if ctx.need[1] else None, None) + tuple(sink.grads.get(p) for p in ctx.params)
+
+
+def gcn_apply(net: GraphTripleConvNet, obj_vecs, pred_vecs, edges):
+    """net(obj_vecs, pred_vecs, edges) that takes part in autograd (see layers.mlp_apply)."""
+    params = [p for p in net.parameters() if p.requires_grad]
+    if torch.is_grad_enabled() and (obj_vecs.requires_grad or pred_vecs.requires_grad or params):
+        return _GcnNetFunction.apply(net, obj_vecs.float().contiguous(), pred_vecs.float().contiguous(), edges, *params)
+    return net(obj_vecs, pred_vecs, edges)
+
+
 class GraphTripleConvNet2(GraphTripleConvNet):
     """Identical stack under the name the relation encoder E2 uses (model/graph.py:252-288)."""

@@ -29,8 +29,8 @@ def build_mlp(dim_list, activation="relu", batch_norm="none", dropout=0, final_n
 
 
 @torch.no_grad()
-def run_mlp(mlp: nn.Sequential, x: torch.Tensor) -> torch.Tensor:
-    """Execute a build_mlp stack on an fp32 (M, C) CUDA matrix."""
+def run_mlp(mlp, x: torch.Tensor) -> torch.Tensor:
+    """Execute a build_mlp stack (nn.Sequential or list of its layers) on an fp32 (M, C) CUDA matrix."""
     mods = list(mlp)
     i = 0
     while i < len(mods):
@@ -86,8 +86,9 @@ def linear_backward(lin: nn.Linear, x: torch.Tensor, dy: torch.Tensor, sink, nee
 
 
 @torch.no_grad()
-def run_mlp_train(mlp: nn.Sequential, x: torch.Tensor):
-    """run_mlp that also returns the tape [(module, input, output, training)] its backward needs."""
+def run_mlp_train(mlp, x: torch.Tensor):
+    """run_mlp that also returns the tape [(module, input, output, training)] its backward needs (mlp: an nn.Sequential of
+    build_mlp, or a plain list of such layers)."""
     mods = list(mlp)
     tape = []
     i = 0
@@ -140,3 +141,33 @@ def mlp_backward(tape, dy: torch.Tensor, sink, need_dx: bool = True):
             dy = ops_bwd.batchnorm_relu_bwd(x, y, dy, None, torch.zeros(x.shape[1], device=x.device),
                                             torch.ones(x.shape[1], device=x.device), False, eps=0.0, relu=True)
     return dy
+
+
+class _MlpFunction(torch.autograd.Function):
+    """Autograd bridge for a build_mlp stack: forward = run_mlp_train, backward = mlp_backward (explicit kernels)."""
+
+    @staticmethod
+    def forward(ctx, mlp, x, *params):
+        y, tape = run_mlp_train(mlp, x.detach().float().contiguous())
+        ctx.tape, ctx.params, ctx.need_dx = tape, params, x.requires_grad
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dy):
+        from .networks.diffusion_networks.unet_train import GradSink
+        sink = GradSink()
+        dx = mlp_backward(ctx.tape, dy.float().contiguous(), sink, need_dx=ctx.need_dx)
+        ctx.tape = None
+        return (None, dx if ctx.need_dx else None) + tuple(sink.grads.get(p) for p in ctx.params)
+
+
+def mlp_apply(mlp, x: torch.Tensor) -> torch.Tensor:
+    """run_mlp that takes part in autograd: with gradients enabled and something to differentiate, the result carries a
+    grad_fn whose backward runs the explicit MLP gradient kernels (what `loss.backward()` does in the reference)."""
+    mods = list(mlp)
+    params = [p for m in mods for p in m.parameters() if p.requires_grad]
+    if torch.is_grad_enabled() and (x.requires_grad or params):
+        return _MlpFunction.apply(mods, x, *params)
+    return run_mlp(mods, x)
+

@@ -220,3 +220,107 @@ def test_vae_dispatcher_v2_full(tmp_path, monkeypatch):
     mu2 = torch.cat([mu, mu])
     assert torch.allclose(m.mean_est, mu2.mean(0), atol=1e-6) and np.allclose(m.cov_est, np.cov((mu2 - mu2.mean(0)).numpy().T), atol=1e-6)
     assert os.path.exists(tmp_path / "exp" / "checkpoint" / "model_stats_7.pkl")
+
+
+def _backward_stand_ins(monkeypatch):
+    """torch stand-ins for the backward entry points (cs_sgemm_small, cs_batchnorm_relu_bwd, cs_gcn_scatter_mean_bwd,
+    cs_gcn_gather_triples_bwd) — host wiring only, like _stand_ins."""
+    from commonscenes_b200 import ops_bwd
+
+    def sgemm(a, b, *, trans_a=False, trans_b=False, out=None, accumulate=False, silu_pre=None):
+        assert silu_pre is None
+        r = (a.t() if trans_a else a) @ (b.t() if trans_b else b)
+        if out is None:
+            return r
+        out.copy_(out + r if accumulate else r)
+        return out
+
+    def bn_bwd(x, y, dy, gamma, rm, rv, training, eps=1e-5, relu=True, dgamma=None, dbeta=None):
+        d = dy * (y > 0) if relu else dy
+        if training:
+            mean, var = x.mean(0), x.var(0, unbiased=False)
+        else:
+            mean, var = rm, rv
+        rstd = torch.rsqrt(var + eps)
+        xh = (x - mean) * rstd
+        g = gamma if gamma is not None else torch.ones_like(mean)
+        if dgamma is not None:
+            dgamma += (d * xh).sum(0)
+        if dbeta is not None:
+            dbeta += d.sum(0)
+        if training:
+            return g * rstd * (d - d.mean(0) - xh * (d * xh).mean(0))
+        return g * rstd * d
+
+    def scatter_bwd(d_pooled, edges, hidden, mid, mid_w=None):
+        O, T = d_pooled.shape[0], edges.shape[0]
+        ones = torch.ones(T)
+        cnt = torch.zeros(O).index_add(0, edges[:, 0], ones).index_add(0, edges[:, 1], ones).clamp(min=1)
+        w = d_pooled / cnt[:, None]
+        m = mid if mid is not None else torch.zeros(T, mid_w or 0)
+        return torch.cat([w[edges[:, 0]], m, w[edges[:, 1]]], dim=1)
+
+    def gather_bwd(d_in, edges, Do, Dp, d_obj, d_pred, accumulate=True):
+        if not accumulate:
+            d_obj.zero_(); d_pred.zero_()
+        d_obj.index_add_(0, edges[:, 0], d_in[:, :Do]); d_obj.index_add_(0, edges[:, 1], d_in[:, Do + Dp:])
+        d_pred += d_in[:, Do:Do + Dp]
+    for name, fn in (("sgemm", sgemm), ("batchnorm_relu_bwd", bn_bwd), ("gcn_scatter_mean_bwd", scatter_bwd), ("gcn_gather_triples_bwd", gather_bwd)):
+        monkeypatch.setattr(ops_bwd, name, fn)
+
+
+def test_layout_backward_wiring_matches_oracle_autograd(tmp_path, monkeypatch):
+    """`loss.backward()` through the layout branch of the mirror — generic autograd bridges over the explicit GCN / MLP backward
+    (graph.gcn_apply, layers.mlp_apply) with torch glue for embeddings / concatenations / reparameterisation / losses — vs
+    autograd through the oracle (itself pinned to the real class incl. its losses): every layout parameter's gradient,
+    train-mode BatchNorm.  Kernel entry points are torch stand-ins (wiring only)."""
+    _stand_ins(monkeypatch)
+    _backward_stand_ins(monkeypatch)
+    from commonscenes_b200.model.VAEGAN_V2FULL import Sg2ScVAEModel
+    from commonscenes_b200.model.sdfusion_txt2shape_model import default_opt
+    cfg = Lo.LAYOUT_TINY
+    g = np.load(os.path.join(GOLD, "layout_tiny.npz"))
+    (tmp_path / "df.yaml").write_text(yaml.safe_dump(TINY_DF)); (tmp_path / "vq.yaml").write_text(yaml.safe_dump(TINY_VQ))
+    vocab = {"object_idx_to_name": [f"o{i}" for i in range(cfg["num_objs"])], "pred_idx_to_name": [f"p{i}" for i in range(cfg["num_preds"])]}
+    m = Sg2ScVAEModel(vocab, diff_opt=default_opt(device="cpu", df_cfg=str(tmp_path / "df.yaml"), vq_cfg=str(tmp_path / "vq.yaml")),
+                      embedding_dim=64, mlp_normalization="batch", residual=True, gconv_num_layers=cfg["num_layers"], layout_branch=True)
+    shapes = Lo.layout_param_shapes(cfg)
+    sd0 = Wt.synth_state_dict(shapes, 55)
+    m.load_state_dict(sd0, strict=False)
+    m.train()
+    pnames = {k for k, _ in m.named_parameters()}
+    sd = {k: (v.clone().requires_grad_(True) if k in pnames else v.clone()) for k, v in sd0.items()}
+    z, objs, triples, text, rel, boxes, angles, zz = (torch.tensor(g[k]) for k in ("z", "objs", "triples", "text", "rel", "boxes", "angles", "zz"))
+    eps = torch.randn(objs.shape[0], 64, generator=torch.Generator().manual_seed(1))
+
+    def loss_of(enc, dec, man):
+        mu, logvar = enc()
+        zs = eps * torch.exp(0.5 * logvar) + mu
+        b, a = dec(zs)
+        tot, _ = Lo.layout_losses(b, boxes, a, angles, mu, logvar, 0.1)
+        return tot + man().pow(2).mean()
+    ref = loss_of(lambda: Lo.encoder(sd, cfg, objs, triples, boxes, text, rel, angles, True),
+                  lambda zs: Lo.decoder(sd, cfg, zs, objs, triples, text, rel, True),
+                  lambda: Lo.manipulate(sd, cfg, zz, objs, triples, text, rel, True))
+    ref.backward()
+    got = loss_of(lambda: m.encoder(objs, triples, boxes, None, text, rel, angles),
+                  lambda zs: m.decoder(zs, objs, triples, text, rel),
+                  lambda: m.manipulate(zz, objs, triples, text, rel))
+    assert got.requires_grad and abs(float(got) - float(ref)) <= 1e-5 * abs(float(ref))
+    got.backward()
+    named = dict(m.named_parameters())
+    refs = [t.grad for k, t in sd.items() if k in pnames and t.grad is not None]
+    rms = (sum(float(r.pow(2).sum()) for r in refs) / sum(r.numel() for r in refs)) ** 0.5
+    checked = 0
+    for k in shapes:
+        if k not in pnames:
+            continue
+        r, p = sd[k].grad, named[k].grad
+        if r is None or float(r.norm()) == 0.0:
+            assert p is None or float(p.abs().max()) <= 1e-6, k
+            continue
+        assert p is not None, f"no gradient for {k}"
+        err, rn = float((p - r).norm()), float(r.norm())
+        assert err <= 1e-4 * rn + 1e-5 * rms * r.numel() ** 0.5, f"{k}: err {err:.3e} vs ref norm {rn:.3e}"
+        checked += 1
+    assert checked > 150
