@@ -187,3 +187,65 @@ def test_layout_branch_forward_matches_reference_class_golden(tag, tmp_path):
         reset(); check(m.manipulate(zz, objs, triples, text, rel), f"man_{mode}")
         reset(); b, a = m.decoder(z, objs, triples, text, rel)
         check(b, f"boxes_{mode}"); check(a, f"angle_logp_{mode}")
+
+
+@pytest.mark.xfail(strict=False, reason="layout-branch backward (SURVEY.md 8f-2) was added after this round's GPU budget was spent: first GPU "
+                                        "run pending; wiring is CPU-verified (tests/test_layout_wiring_cpu.py), kernels are the ones verified above")
+def test_layout_branch_gradients_match_oracle_autograd(tmp_path):
+    """`loss.backward()` through encoder -> reparameterise -> decoder (+ manipulate) of Sg2ScVAEModel(layout_branch=True) on the
+    GPU vs autograd through the oracle (pinned to the real class): every layout parameter gradient, train-mode BatchNorm."""
+    import yaml
+    from oracle import layout as Lo
+    from commonscenes_b200.model.VAEGAN_V2FULL import Sg2ScVAEModel
+    from commonscenes_b200.model.sdfusion_txt2shape_model import default_opt
+    cfg = Lo.LAYOUT_TINY
+    g = np.load(os.path.join(GOLD, "layout_tiny.npz"))
+    df = dict(model=dict(params=dict(linear_start=0.00085, linear_end=0.012, conditioning_key="crossattn", timesteps=1000)),
+              unet=dict(params=dict(image_size=8, in_channels=3, out_channels=3, model_channels=32, num_res_blocks=1,
+                                    attention_resolutions=[4, 2], channel_mult=[1, 2, 3], num_heads=4, dims=3, use_spatial_transformer=True,
+                                    transformer_depth=1, context_dim=1280, use_checkpoint=True, legacy=False)))
+    vq = dict(model=dict(params=dict(embed_dim=3, n_embed=64, ddconfig=dict(double_z=False, z_channels=3, resolution=16, in_channels=1, out_ch=1,
+                                                                           ch=16, ch_mult=[1, 2], num_res_blocks=1, attn_resolutions=[], dropout=0.0))))
+    (tmp_path / "df.yaml").write_text(yaml.safe_dump(df)); (tmp_path / "vq.yaml").write_text(yaml.safe_dump(vq))
+    vocab = {"object_idx_to_name": [f"o{i}" for i in range(cfg["num_objs"])], "pred_idx_to_name": [f"p{i}" for i in range(cfg["num_preds"])]}
+    m = Sg2ScVAEModel(vocab, diff_opt=default_opt(device="cuda", df_cfg=str(tmp_path / "df.yaml"), vq_cfg=str(tmp_path / "vq.yaml")),
+                      embedding_dim=64, mlp_normalization="batch", residual=True, gconv_num_layers=cfg["num_layers"], layout_branch=True)
+    shapes = Lo.layout_param_shapes(cfg)
+    sd0 = Wt.synth_state_dict(shapes, 55)
+    m.load_state_dict(sd0, strict=False)
+    m = m.cuda().train()
+    pnames = {k for k, _ in m.named_parameters()}
+    sd = {k: (v.clone().requires_grad_(True) if k in pnames else v.clone()) for k, v in sd0.items()}
+    z, objs, triples, text, rel, boxes, angles, zz = (torch.tensor(g[k]) for k in ("z", "objs", "triples", "text", "rel", "boxes", "angles", "zz"))
+    eps = torch.randn(objs.shape[0], 64, generator=torch.Generator().manual_seed(1))
+
+    def loss_of(enc, dec, man, dev):
+        mu, logvar = enc()
+        b, a = dec(eps.to(dev) * torch.exp(0.5 * logvar) + mu)
+        tot, _ = Lo.layout_losses(b, boxes.to(dev), a, angles.to(dev), mu, logvar, 0.1)
+        return tot + man().pow(2).mean()
+    ref = loss_of(lambda: Lo.encoder(sd, cfg, objs, triples, boxes, text, rel, angles, True),
+                  lambda zs: Lo.decoder(sd, cfg, zs, objs, triples, text, rel, True),
+                  lambda: Lo.manipulate(sd, cfg, zz, objs, triples, text, rel, True), "cpu")
+    ref.backward()
+    c = lambda t: t.cuda()
+    got = loss_of(lambda: m.encoder(c(objs), c(triples), c(boxes), None, c(text), c(rel), c(angles)),
+                  lambda zs: m.decoder(zs, c(objs), c(triples), c(text), c(rel)),
+                  lambda: m.manipulate(c(zz), c(objs), c(triples), c(text), c(rel)), "cuda")
+    assert abs(float(got.detach()) - float(ref.detach())) <= 1e-4 * abs(float(ref.detach()))
+    got.backward()
+    named = dict(m.named_parameters())
+    refs = [t.grad for k, t in sd.items() if k in pnames and t.grad is not None]
+    rms = (sum(float(r.pow(2).sum()) for r in refs) / sum(r.numel() for r in refs)) ** 0.5
+    worst = 0.0
+    for k in shapes:
+        if k not in pnames or sd[k].grad is None or float(sd[k].grad.norm()) == 0.0:
+            continue
+        r, p = sd[k].grad, named[k].grad
+        assert p is not None, f"no gradient for {k}"
+        err, rn = float((p.cpu() - r).norm()), float(r.norm())
+        floor = 1e-4 * rms * r.numel() ** 0.5
+        if rn > floor:
+            worst = max(worst, err / rn)
+        assert err <= 1e-3 * rn + floor, f"{k}: err {err:.3e} vs ref norm {rn:.3e}"
+    print(f"layout backward on the GPU: worst parameter-gradient rel-L2 {worst:.2e}")
