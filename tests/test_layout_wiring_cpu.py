@@ -324,3 +324,19 @@ def test_layout_backward_wiring_matches_oracle_autograd(tmp_path, monkeypatch):
         assert err <= 1e-4 * rn + 1e-5 * rms * r.numel() ** 0.5, f"{k}: err {err:.3e} vs ref norm {rn:.3e}"
         checked += 1
     assert checked > 150
+
+
+@pytest.mark.parametrize("tag", ["tiny", "full"])
+def test_losses_mirror_matches_reference_function(tag):
+    """model/losses.py mirror vs the totals the reference's own calculate_model_losses produced on the real class's outputs
+    (stored in tests/golden/layout_*.npz), and bce_loss vs its closed form."""
+    from commonscenes_b200.model.losses import bce_loss, calculate_model_losses
+    g = np.load(os.path.join(GOLD, f"layout_{tag}.npz"))
+    t = lambda k: torch.tensor(g[k])
+    for mode in ("eval", "train"):
+        tot, d = calculate_model_losses(None, t(f"boxes_{mode}"), t("boxes"), "box", angles=t("angles"), angles_pred=t(f"angle_logp_{mode}"),
+                                        mu=t(f"mu_{mode}"), logvar=t(f"logvar_{mode}"), KL_weight=0.1, withangles=True)
+        assert abs(float(tot) - float(g[f"loss_{mode}"])) <= 2e-5 * abs(float(tot)) and set(d) == {"box", "angle_pred", "KLD_Gauss"}
+    x, y = torch.randn(50, generator=torch.Generator().manual_seed(0)) * 5, (torch.arange(50) % 2).float()
+    ref = (x.clamp(min=0) - x * y + (1 + (-x.abs()).exp()).log())
+    assert torch.allclose(bce_loss(x, y, reduce=False), ref, atol=1e-6) and abs(float(bce_loss(x, y)) - float(ref.mean())) < 1e-6
