@@ -36,6 +36,7 @@ class VAE(nn.Module):
                                     gconv_num_layers=5, use_angles=with_angles, use_E2=with_E2, residual=residual, clip=clip,
                                     gconv_pooling=gconv_pooling, num_box_params=num_box_params, layout_branch=True)
         self.vae_v2.replace_all_latent = replace_latent
+        self.vae_v2.optimizer_ini()
 
     def set_cuda(self):
         self.vae_v2.cuda()
@@ -55,10 +56,16 @@ class VAE(nn.Module):
         info = self.vae_v2.load_checkpoint(os.path.join(exp, "checkpoint", "model{}.pth".format(epoch)), strict=False)
         if info["epoch"] is not None:
             self.epoch, self.counter = info["epoch"], info["counter"]
-        self.optimizer_state = None if restart_optim else info["opt"]      # hand to DenoiserTrainStep / torch.optim.AdamW
+        self.optimizer_state = None if restart_optim else info["opt"]      # also available to DenoiserTrainStep (denoiser_optimizer_state)
+        if not restart_optim and info["opt"]:
+            self.vae_v2.optimizerFULL.load_state_dict(info["opt"])
+            self.vae_v2.scheduler = torch.optim.lr_scheduler.LambdaLR(self.vae_v2.optimizerFULL, lr_lambda=self.vae_v2.lr_lambda,
+                                                                      last_epoch=int(self.counter - 1))
         return info
 
     def save(self, exp, outf, epoch, counter=None, optimizer_state=None):
+        if optimizer_state is None:
+            optimizer_state = self.vae_v2.optimizerFULL.state_dict()
         return self.vae_v2.save_checkpoint(os.path.join(exp, outf, "model{}.pth".format(epoch)), epoch, counter, optimizer_state)
 
     def compute_statistics(self, exp, epoch, stats_dataloader, force=False):

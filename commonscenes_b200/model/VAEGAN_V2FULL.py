@@ -216,6 +216,20 @@ class Sg2ScVAEModel(nn.Module):
         cov_est = np.cov((mean_cat - mean_est).numpy().T)
         return mean_est[0], cov_est
 
+    def optimizer_ini(self):
+        """optimizerFULL over this module's parameters followed by the denoiser's (reference :634-672): torch.optim.AdamW(lr
+        1e-4) + LambdaLR(lr_lambda).  With layout_branch=True the parameter order is the reference's, so the 'opt' entry of a
+        reference `model{epoch}.pth` loads directly (`optimizerFULL.load_state_dict`)."""
+        params = [p for p in self.parameters() if p.requires_grad]
+        self.optimizerFULL = torch.optim.AdamW(params + list(self.Diff.trainable_params), lr=1e-4)
+        self.scheduler = torch.optim.lr_scheduler.LambdaLR(self.optimizerFULL, lr_lambda=self.lr_lambda)
+        self.optimizers = [self.optimizerFULL]
+
+    def update_learning_rate(self):
+        """reference :674-681 (called once per iteration by the trainer)."""
+        self.scheduler.step()
+        return self.optimizers[0].param_groups[0]["lr"]
+
     @staticmethod
     def lr_lambda(counter):
         """Step schedule of optimizerFULL (reference :620-633): 1e-4 -> 5e-5 (20k) -> 1e-5 (60k) -> 5e-6 (100k)."""

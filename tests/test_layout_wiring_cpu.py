@@ -200,12 +200,23 @@ def test_vae_dispatcher_v2_full(tmp_path, monkeypatch):
         assert torch.equal(a, b)
     # checkpoint directory layout of the reference: <exp>/checkpoint/model{epoch}.pth
     os.makedirs(tmp_path / "exp" / "checkpoint")
+    gg = torch.Generator().manual_seed(9)
+    for p_ in m.vae_v2.optimizerFULL.param_groups[0]["params"]:      # optimizerFULL = AdamW over [this module's params] + [denoiser's]
+        p_.grad = torch.randn(p_.shape, generator=gg) * 1e-3
+    m.vae_v2.optimizerFULL.step()
+    assert len(m.vae_v2.optimizerFULL.param_groups[0]["params"]) == len(list(m.vae_v2.parameters())) + len(m.vae_v2.Diff.trainable_params)
     m.save(str(tmp_path / "exp"), "checkpoint", 7, counter=123)
     torch.manual_seed(4)
     m2 = VAE(root=str(tmp_path), type="v2_full", diff_opt=str(tmp_path / "v2_full.yaml"), vocab=vocab, with_angles=True, residual=True)
     assert not torch.equal(m2.vae_v2.rel_mlp[0].weight, m.vae_v2.rel_mlp[0].weight)
     m2.load_networks(str(tmp_path / "exp"), 7)
     assert m2.epoch == 7 and m2.counter == 123
+    # (LambdaLR(last_epoch=counter - 1) takes its initial step at construction, as in the reference: last_epoch == counter)
+    sa, sb = m.vae_v2.optimizerFULL.state_dict()["state"], m2.vae_v2.optimizerFULL.state_dict()["state"]
+    assert len(sa) == len(sb) > 700 and all(torch.equal(sa[i]["exp_avg"], sb[i]["exp_avg"]) for i in sa)
+    assert m2.vae_v2.scheduler.last_epoch == 123 and abs(m2.vae_v2.update_learning_rate() - 1e-4) < 1e-12
+    for (_, a), (_, b) in zip(m.vae_v2.Diff.df.state_dict().items(), m2.vae_v2.Diff.df.state_dict().items()):
+        assert torch.equal(a, b)
     for (k, a), (_, b) in zip(m.vae_v2.state_dict().items(), m2.vae_v2.state_dict().items()):
         assert torch.equal(a, b), k
     # latent statistics (collect_train_statistics): mean / covariance of the encoder means over a loader, -1 batches skipped
