@@ -154,7 +154,6 @@ class _GcnNetFunction(torch.autograd.Function):
             last = ctx.net.gconvs[-1]
             d_o = torch.zeros((ctx.tapes[-1][0].shape[0], last.output_dim), dtype=torch.float32, device=d_p.device)
         d_obj, d_pred = ctx.net.backward(ctx.tapes, d_o, d_p, sink)
-        ctx.tapes = None
         return (None, d_obj if ctx.need[0] else None, d_pred if ctx.need[1] else None, None) + tuple(sink.grads.get(p) for p in ctx.params)
 
 

@@ -157,8 +157,7 @@ class _MlpFunction(torch.autograd.Function):
     def backward(ctx, dy):
         from .networks.diffusion_networks.unet_train import GradSink
         sink = GradSink()
-        dx = mlp_backward(ctx.tape, dy.float().contiguous(), sink, need_dx=ctx.need_dx)
-        ctx.tape = None
+        dx = mlp_backward(ctx.tape, dy.float().contiguous(), sink, need_dx=ctx.need_dx)     # (tape kept: retain_graph re-runs work)
         return (None, dx if ctx.need_dx else None) + tuple(sink.grads.get(p) for p in ctx.params)
 
 

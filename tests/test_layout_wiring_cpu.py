@@ -351,3 +351,39 @@ def test_losses_mirror_matches_reference_function(tag):
     x, y = torch.randn(50, generator=torch.Generator().manual_seed(0)) * 5, (torch.arange(50) % 2).float()
     ref = (x.clamp(min=0) - x * y + (1 + (-x.abs()).exp()).log())
     assert torch.allclose(bce_loss(x, y, reduce=False), ref, atol=1e-6) and abs(float(bce_loss(x, y)) - float(ref.mean())) < 1e-6
+
+
+def test_box_discriminator_matches_reference_class(monkeypatch):
+    """BoxDiscriminator mirror (Linear + BatchNorm on the MLP kernels via the autograd bridge, LeakyReLU / Sigmoid / penalty as
+    torch glue) vs the reference's own class (tests/golden/box_discriminator.npz): outputs, gradient-penalty terms and the
+    parameter gradients, including the reference's quirk that the regulariser's inner backward also deposits gradients on D."""
+    _stand_ins(monkeypatch)
+    _backward_stand_ins(monkeypatch)
+    from commonscenes_b200.model.discriminators import BoxDiscriminator
+    g = np.load(os.path.join(GOLD, "box_discriminator.npz"))
+    d = BoxDiscriminator(6, 16, 36).train()
+    assert list(d.state_dict().keys()) == ["D.0.weight", "D.0.bias", "D.1.weight", "D.1.bias", "D.1.running_mean", "D.1.running_var",
+                                           "D.1.num_batches_tracked", "D.3.weight", "D.3.bias", "D.4.weight", "D.4.bias", "D.4.running_mean",
+                                           "D.4.running_var", "D.4.num_batches_tracked", "D.6.weight", "D.6.bias"]
+    objs, triples, boxes, keep = (torch.tensor(g[k]) for k in ("objs", "triples", "boxes", "keep"))
+    modes = {"plain": dict(), "keeps": dict(keeps=keep), "real": dict(with_grad=True, is_real=True), "fake_keeps": dict(keeps=keep, with_grad=True, is_real=False)}
+    for name, kw in modes.items():
+        Wt.fill_module_(d, int(g["weight_seed"]))
+        d.zero_grad()
+        y, reg = d(objs, triples, boxes.clone(), **kw)
+        (y.mean() + (reg.mean() if reg is not None else 0.0)).backward()
+        assert np.allclose(y.detach().numpy(), g[f"{name}_y"], atol=1e-6)
+        assert (reg is None) == (f"{name}_reg" not in g.files)
+        if reg is not None:
+            assert np.allclose(reg.detach().numpy(), g[f"{name}_reg"], rtol=1e-4, atol=1e-7)
+        for k, p in d.named_parameters():
+            gr = p.grad.numpy()
+            if f"{name}_grad_{k}" in g.files:
+                ref = g[f"{name}_grad_{k}"]
+                assert float(np.linalg.norm(gr - ref)) <= 1e-4 * float(np.linalg.norm(ref)) + 1e-6 * ref.size ** 0.5, (name, k)
+            else:       # large tensors are stored as norm + seeded random projection + leading slice
+                nrm, dot = g[f"{name}_gsum_{k}"]
+                proj = np.random.RandomState(int(g["weight_seed"])).standard_normal(gr.size).astype(np.float32)
+                assert abs(float(np.linalg.norm(gr)) - nrm) <= 1e-4 * nrm and abs(float(gr.reshape(-1) @ proj) - dot) <= 1e-3 * nrm
+                assert np.allclose(gr.reshape(-1)[:512], g[f"{name}_ghead_{k}"], rtol=1e-3, atol=1e-6 * nrm)
+        assert int(d.D[1].num_batches_tracked) == 1
