@@ -249,3 +249,29 @@ def test_layout_branch_gradients_match_oracle_autograd(tmp_path):
             worst = max(worst, err / rn)
         assert err <= 1e-3 * rn + floor, f"{k}: err {err:.3e} vs ref norm {rn:.3e}"
     print(f"layout backward on the GPU: worst parameter-gradient rel-L2 {worst:.2e}")
+
+
+@pytest.mark.xfail(strict=False, reason="BoxDiscriminator mirror was added after this round's GPU budget was spent: first GPU run pending; "
+                                        "wiring is CPU-verified (tests/test_layout_wiring_cpu.py)")
+def test_box_discriminator_on_gpu_matches_reference_golden():
+    from commonscenes_b200.model.discriminators import BoxDiscriminator
+    g = np.load(os.path.join(GOLD, "box_discriminator.npz"))
+    d = BoxDiscriminator(6, 16, 36)
+    objs, triples, boxes, keep = (torch.tensor(g[k]).cuda() for k in ("objs", "triples", "boxes", "keep"))
+    modes = {"plain": dict(), "keeps": dict(keeps=keep), "real": dict(with_grad=True, is_real=True), "fake_keeps": dict(keeps=keep, with_grad=True, is_real=False)}
+    for name, kw in modes.items():
+        Wt.fill_module_(d, int(g["weight_seed"]))
+        d = d.cuda().train()
+        d.zero_grad()
+        y, reg = d(objs, triples, boxes.clone(), **kw)
+        (y.mean() + (reg.mean() if reg is not None else 0.0)).backward()
+        assert np.allclose(y.detach().cpu().numpy(), g[f"{name}_y"], atol=1e-5)
+        if reg is not None:
+            assert np.allclose(reg.detach().cpu().numpy(), g[f"{name}_reg"], rtol=1e-3, atol=1e-6)
+        for k, p in d.named_parameters():
+            if f"{name}_grad_{k}" in g.files:
+                ref = g[f"{name}_grad_{k}"]
+                assert float(np.linalg.norm(p.grad.cpu().numpy() - ref)) <= 1e-3 * float(np.linalg.norm(ref)) + 1e-5 * ref.size ** 0.5, (name, k)
+            else:
+                nrm = float(g[f"{name}_gsum_{k}"][0])
+                assert abs(float(p.grad.norm()) - nrm) <= 1e-3 * nrm, (name, k)
