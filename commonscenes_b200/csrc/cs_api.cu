@@ -9,10 +9,10 @@ const char* last_error();
 unsigned long long launch_count();
 void reset_launch_count();
 
-int gn_stats_launch(const void*, int, int, int, int, float*, int, cudaStream_t);
-int gn_finalize_launch(float*, const float*, const float*, int, int, int, int, float, float*, cudaStream_t);
+int gn_stats_launch(const void*, int, int, int, int, long long*, int, cudaStream_t);
+int gn_finalize_launch(long long*, const float*, const float*, int, int, int, int, float, float*, cudaStream_t);
 int gn_apply_launch(const void*, int, int, int, int, const float*, int, void*, int, int, cudaStream_t);
-int gn_apply_fused_launch(const void*, int, int, int, int, int, const float*, int, const float*, int, const float*,
+int gn_apply_fused_launch(const void*, int, int, int, int, int, const long long*, int, const long long*, int, const float*,
                           const float*, int, float, void*, int, int, cudaStream_t);
 int layernorm_launch(const void*, long long, int, int, const float*, const float*, float, void*, int, cudaStream_t);
 int attention_launch(const void*, const void*, const void*, void*, int, int, int, int, int, int, int, int, int,
@@ -42,7 +42,7 @@ int scatter_mean_bwd_launch(const float*, int, const long long*, int, int, const
                             int, cudaStream_t);
 int gather_triples_bwd_launch(const float*, int, int, int, int, const long long*, int, float*, float*, cudaStream_t);
 int embedding_bwd_launch(const float*, int, int, int, const long long*, int, int, float*, cudaStream_t);
-int gn_bwd_launch(const void*, int, int, int, int, int, const void*, int, int, const float*, int, const float*, int, const float*,
+int gn_bwd_launch(const void*, int, int, int, int, int, const void*, int, int, const long long*, int, const long long*, int, const float*,
                   const float*, int, float, int, float*, const void*, int, void*, int, int, cudaStream_t);
 int batch_reduce_launch(const float*, int, int, int, int, float*, cudaStream_t);
 int layernorm_bwd_launch(const void*, long long, int, int, const void*, int, const float*, float, const void*, int, void*, int,
@@ -65,6 +65,7 @@ int attention_bwd_launch(const void*, const void*, const void*, const void*, con
                          void*, int, int, int, int, int, int, int, int, int, float, cudaStream_t);
 int pack_weight_launch(const float*, int, int, int, int, void*, void*, cudaStream_t);
 void igemm_set_debug(int);
+void igemm_variant_counts(unsigned long long*, int);
 int cast_bf16_launch(const float*, long long, void*, cudaStream_t);
 int vq_quantize_launch(const float*, int, int, long long, const float*, int, const float*, const float*, int, float*,
                        long long*, cudaStream_t);
@@ -107,7 +108,7 @@ int cs_conv3d(const cs_conv3d_args* a, cs_stream_t stream) {
   g.bias = a->bias; g.rowvec = a->rowvec; g.rowvec_pitch = a->rowvec_pitch;
   g.residual = a->residual; g.res_pitch = a->res_pitch;
   g.out = a->out; g.out_pitch = a->out_pitch; g.out_mode = a->out_mode; g.act = a->act;
-  g.stat_sum = a->stat_sum; g.stat_pitch = a->stat_pitch; g.bn_hint = a->bn_hint;
+  g.stat_sum = reinterpret_cast<long long*>(a->stat_sum); g.stat_pitch = a->stat_pitch; g.bn_hint = a->bn_hint;
   if (g.kd < 1 || g.kh < 1 || g.kw < 1 || g.sd < 1 || g.sh < 1 || g.sw < 1 || g.B < 1)
     return cs::set_error(CS_ERR_INVALID, "cs_conv3d: bad filter/stride/batch");
   return cs::igemm_launch(g, S(stream));
@@ -128,13 +129,13 @@ int cs_conv3d_wgrad(const cs_conv3d_wgrad_args* a, cs_stream_t stream) {
   return cs::wgrad_launch(g, S(stream));
 }
 
-int cs_groupnorm_stats(const void* x, int32_t B, int32_t Sp, int32_t C, int32_t pitch, float* stat,
+int cs_groupnorm_stats(const void* x, int32_t B, int32_t Sp, int32_t C, int32_t pitch, int64_t* stat,
                        int32_t stat_pitch, cs_stream_t stream) {
-  return cs::gn_stats_launch(x, B, Sp, C, pitch, stat, stat_pitch, S(stream));
+  return cs::gn_stats_launch(x, B, Sp, C, pitch, reinterpret_cast<long long*>(stat), stat_pitch, S(stream));
 }
-int cs_groupnorm_finalize(float* stat, const float* gamma, const float* beta, int32_t B, int32_t C, int32_t groups,
+int cs_groupnorm_finalize(int64_t* stat, const float* gamma, const float* beta, int32_t B, int32_t C, int32_t groups,
                           int32_t Sp, float eps, float* scale_shift, cs_stream_t stream) {
-  return cs::gn_finalize_launch(stat, gamma, beta, B, C, groups, Sp, eps, scale_shift, S(stream));
+  return cs::gn_finalize_launch(reinterpret_cast<long long*>(stat), gamma, beta, B, C, groups, Sp, eps, scale_shift, S(stream));
 }
 int cs_groupnorm_apply(const void* x, int32_t B, int32_t Sp, int32_t C, int32_t pitch, const float* scale_shift,
                        int32_t ss_pitch, void* y, int32_t y_pitch, int32_t act, cs_stream_t stream) {
@@ -249,13 +250,17 @@ int cs_embedding_bwd(const float* d_rows, int32_t pitch, int32_t col_off, int32_
 }
 
 void cs_debug_set(int32_t flags) { cs::igemm_set_debug(flags); }
+void cs_conv3d_variant_counts(uint64_t* out4, int32_t reset) {
+  cs::igemm_variant_counts(reinterpret_cast<unsigned long long*>(out4), reset);
+}
 
 int cs_groupnorm_apply_fused(const void* x, int32_t B, int32_t Sp, int32_t C, int32_t pitch, int32_t ch_off,
-                             const float* stat1, int32_t C1, const float* stat2, int32_t C2, const float* gamma,
+                             const int64_t* stat1, int32_t C1, const int64_t* stat2, int32_t C2, const float* gamma,
                              const float* beta, int32_t groups, float eps, void* y, int32_t y_pitch, int32_t act,
                              cs_stream_t stream) {
   if (!x || !stat1 || !y) return cs::set_error(CS_ERR_INVALID, "cs_groupnorm_apply_fused: null pointer");
-  return cs::gn_apply_fused_launch(x, B, Sp, C, pitch, ch_off, stat1, C1, stat2, C2, gamma, beta, groups, eps, y, y_pitch,
+  return cs::gn_apply_fused_launch(x, B, Sp, C, pitch, ch_off, reinterpret_cast<const long long*>(stat1), C1,
+                                   reinterpret_cast<const long long*>(stat2), C2, gamma, beta, groups, eps, y, y_pitch,
                                    act, S(stream));
 }
 
@@ -265,10 +270,11 @@ int cs_cast_f32_to_bf16(const float* x, int64_t n, void* y, cs_stream_t stream) 
 
 // ---- training path -----------------------------------------------------------------------------------------------
 int cs_groupnorm_bwd(const void* x, int32_t B, int32_t Sp, int32_t C, int32_t pitch, int32_t ch_off, const void* dy,
-                     int32_t dy_pitch, int32_t dy_off, const float* stat1, int32_t C1, const float* stat2, int32_t C2,
+                     int32_t dy_pitch, int32_t dy_off, const int64_t* stat1, int32_t C1, const int64_t* stat2, int32_t C2,
                      const float* gamma, const float* beta, int32_t groups, float eps, int32_t act, float* red,
                      const void* extra, int32_t extra_pitch, void* dx, int32_t dx_pitch, int32_t pass, cs_stream_t stream) {
-  return cs::gn_bwd_launch(x, B, Sp, C, pitch, ch_off, dy, dy_pitch, dy_off, stat1, C1, stat2, C2, gamma, beta, groups, eps, act,
+  return cs::gn_bwd_launch(x, B, Sp, C, pitch, ch_off, dy, dy_pitch, dy_off, reinterpret_cast<const long long*>(stat1), C1,
+                           reinterpret_cast<const long long*>(stat2), C2, gamma, beta, groups, eps, act,
                            red, extra, extra_pitch, dx, dx_pitch, pass, S(stream));
 }
 int cs_batch_reduce(const float* in, int32_t B, int32_t C, int32_t comp, int32_t ncomp, float* out, cs_stream_t stream) {

@@ -23,24 +23,10 @@ __device__ __forceinline__ float act_grad(float z, int act) {
 
 // group statistics of sample b from the per-channel (sum, sumsq) of the two concatenated sources (same arithmetic as
 // gn_apply_fused_kernel so forward and backward see identical mean / rstd)
-__device__ __forceinline__ void gn_group_stats(int b, int S, int cpg, const float* stat1, int C1, const float* stat2, int C2,
-                                               float eps, float* g_mean, float* g_rstd, int groups) {
-  if (threadIdx.x < groups) {
-    double s = 0.0, q = 0.0;
-    for (int j = 0; j < cpg; ++j) {
-      const int c = threadIdx.x * cpg + j;
-      const float* sp = (c < C1) ? stat1 + (static_cast<long long>(b) * C1 + c) * 2
-                                 : stat2 + (static_cast<long long>(b) * C2 + (c - C1)) * 2;
-      s += sp[0];
-      q += sp[1];
-    }
-    const double inv_n = 1.0 / (static_cast<double>(S) * cpg);
-    const double mean = s * inv_n;
-    double var = q * inv_n - mean * mean;
-    if (var < 0.0) var = 0.0;
-    g_mean[threadIdx.x] = static_cast<float>(mean);
-    g_rstd[threadIdx.x] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
-  }
+__device__ __forceinline__ void gn_group_stats(int b, int S, int cpg, const long long* stat1, int C1, const long long* stat2,
+                                               int C2, float eps, float* g_mean, float* g_rstd, int groups) {
+  if (threadIdx.x < groups)
+    stat_group_mean_rstd(b, threadIdx.x, cpg, S, stat1, C1, stat2, C2, eps, g_mean[threadIdx.x], g_rstd[threadIdx.x]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -49,7 +35,7 @@ __device__ __forceinline__ void gn_group_stats(int b, int S, int cpg, const floa
 // ------------------------------------------------------------------------------------------------
 __global__ void gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ x, int S, int C, int pitch, int ch_off,
                                      const __nv_bfloat16* __restrict__ dy, int dy_pitch, int dy_off,
-                                     const float* __restrict__ stat1, int C1, const float* __restrict__ stat2, int C2,
+                                     const long long* __restrict__ stat1, int C1, const long long* __restrict__ stat2, int C2,
                                      const float* __restrict__ gamma, const float* __restrict__ beta, int groups, float eps,
                                      int act, float* __restrict__ red, int vox_per_cta) {
   __shared__ float g_mean[64], g_rstd[64];
@@ -111,7 +97,7 @@ __global__ void gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ x, int S,
 // pass 2: dx = rstd * (gamma * dz - mean_g(gamma dz) - xhat * mean_g(gamma dz xhat)) [+ extra]
 __global__ void gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, int S, int C, int pitch, int ch_off,
                                     const __nv_bfloat16* __restrict__ dy, int dy_pitch, int dy_off,
-                                    const float* __restrict__ stat1, int C1, const float* __restrict__ stat2, int C2,
+                                    const long long* __restrict__ stat1, int C1, const long long* __restrict__ stat2, int C2,
                                     const float* __restrict__ gamma, const float* __restrict__ beta, int groups, float eps,
                                     int act, const float* __restrict__ red, const __nv_bfloat16* __restrict__ extra,
                                     int extra_pitch, __nv_bfloat16* __restrict__ dx, int dx_pitch, int vox_per_cta) {
@@ -192,7 +178,7 @@ static int gn_geometry(int B, int S, int C, int groups, int* threads, int* R, in
 }
 
 int gn_bwd_launch(const void* x, int B, int S, int C, int pitch, int ch_off, const void* dy, int dy_pitch, int dy_off,
-                  const float* stat1, int C1, const float* stat2, int C2, const float* gamma, const float* beta, int groups,
+                  const long long* stat1, int C1, const long long* stat2, int C2, const float* gamma, const float* beta, int groups,
                   float eps, int act, float* red, const void* extra, int extra_pitch, void* dx, int dx_pitch, int pass,
                   cudaStream_t st) {
   const int Ct = C1 + (stat2 ? C2 : 0);
@@ -790,6 +776,10 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
   }
   float clip = grad_scale;
   if (sumsq) {
+    // a non-finite gradient norm (a NaN / Inf anywhere in the gradient) would turn the clip factor, and with it every
+    // parameter, into NaN: skip the update instead (the reference zeroes NaN gradients before optimizer.step(),
+    // scripts/train_3dfront.py:401-405; skipping is the conservative equivalent for a flat buffer)
+    if (!isfinite(*sumsq)) return;
     const float norm = sqrtf(*sumsq) * grad_scale;
     clip *= fminf(1.f, max_norm / (norm + 1e-6f));
   }

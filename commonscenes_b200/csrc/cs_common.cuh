@@ -224,6 +224,42 @@ __host__ __device__ __forceinline__ uint32_t umma_idesc_bf16_m128(uint32_t n) {
 }
 
 // ----------------------------------------------------------------------------------------------
+// GroupNorm sum buffers: per-(sample, channel) {sum, sum of squares} held as 64-bit FIXED-POINT integers.
+// Many CTAs / warps contribute partial sums to the same (sample, channel) cell; integer addition is associative, so
+// the totals are bit-identical from run to run whatever order the atomics land in (fp32 atomics are not: two identical
+// launches used to differ by 6e-3..1e-2 rel-L2 after the bf16 roundings downstream).  Each fp32 partial (a sum over >= 32
+// voxels) is rounded once to 2^-20 (sums) / 2^-12 (sums of squares): absolute error <= 5e-7 / 1.2e-4 per partial, far
+// below the fp32 rounding of the partial itself for the activations of this path; range +-8.8e12 / +-2.2e15 (the
+// float -> integer conversion saturates).
+// ----------------------------------------------------------------------------------------------
+static constexpr float kStatSumScale = 1048576.f;      // 2^20
+static constexpr float kStatSqScale = 4096.f;          // 2^12
+__device__ __forceinline__ void stat_add(long long* cell, float s, float q) {
+  atomicAdd(reinterpret_cast<unsigned long long*>(cell), static_cast<unsigned long long>(__float2ll_rn(s * kStatSumScale)));
+  atomicAdd(reinterpret_cast<unsigned long long*>(cell + 1), static_cast<unsigned long long>(__float2ll_rn(q * kStatSqScale)));
+}
+// Group statistics of GroupNorm(cat(src1, src2)) for group g of sample b from the fixed-point sums: the integer cells
+// of the group's channels are added exactly, then converted once (fp64).
+__device__ __forceinline__ void stat_group_mean_rstd(int b, int g, int cpg, long long S, const long long* stat1, int C1,
+                                                     const long long* stat2, int C2, float eps, float& mean_out,
+                                                     float& rstd_out) {
+  long long s = 0, q = 0;
+  for (int j = 0; j < cpg; ++j) {
+    const int c = g * cpg + j;
+    const long long* sp = (c < C1) ? stat1 + (static_cast<long long>(b) * C1 + c) * 2
+                                   : stat2 + (static_cast<long long>(b) * C2 + (c - C1)) * 2;
+    s += sp[0];
+    q += sp[1];
+  }
+  const double inv_n = 1.0 / (static_cast<double>(S) * cpg);
+  const double mean = static_cast<double>(s) * (1.0 / kStatSumScale) * inv_n;
+  double var = static_cast<double>(q) * (1.0 / kStatSqScale) * inv_n - mean * mean;
+  if (var < 0.0) var = 0.0;
+  mean_out = static_cast<float>(mean);
+  rstd_out = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+}
+
+// ----------------------------------------------------------------------------------------------
 // small numeric helpers
 // ----------------------------------------------------------------------------------------------
 // x * sigmoid(x); approximate division (MUFU.RCP + FMUL, <= 2 ulp) keeps the bandwidth-bound kernels off the issue limit

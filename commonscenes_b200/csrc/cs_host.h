@@ -38,7 +38,7 @@ struct IgemmArgs {
   const float* rowvec; int rowvec_pitch;
   const void* residual; int res_pitch;
   void* out; int out_pitch; int out_mode; int act;
-  float* stat_sum; int stat_pitch;
+  long long* stat_sum; int stat_pitch;
   int bn_hint;  // 0 = choose automatically
 };
 

@@ -362,9 +362,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
             if (lane == j) { mys = s; myq = q; }
           }
           if (lane < 16 && n + lane < p.Cout && quarter * 32 < p.rows) {
-            float* sp = p.stat_sum + (static_cast<long long>(b) * p.stat_pitch + n + lane) * 2;
-            atomicAdd(sp, mys);
-            atomicAdd(sp + 1, myq);
+            stat_add(p.stat_sum + (static_cast<long long>(b) * p.stat_pitch + n + lane) * 2, mys, myq);
           }
         }
       }
@@ -415,6 +413,15 @@ int igemm2_launch(const CUtensorMap& tmA1, const CUtensorMap& tmA2, const CUtens
 
 static int g_debug_flags = 0;
 void igemm_set_debug(int flags) { g_debug_flags = flags; }
+// launches per kernel variant since the last reset: 0 = one 128-voxel tile per CTA, 1 = pair / hybrid work list (two
+// accumulators share each weight slab), 2 = CTA-pair kernel (cta_group::2), 3 = CTA pairs with two accumulators ("quad")
+static unsigned long long g_variant_count[4] = {0, 0, 0, 0};
+void igemm_variant_counts(unsigned long long* out4, int reset) {
+  for (int i = 0; i < 4; ++i) {
+    if (out4) out4[i] = g_variant_count[i];
+    if (reset) g_variant_count[i] = 0;
+  }
+}
 int igemm_debug_flags() { return g_debug_flags; }
 
 int igemm_launch(const IgemmArgs& a, cudaStream_t stream) {
@@ -567,6 +574,7 @@ int igemm_launch(const IgemmArgs& a, cudaStream_t stream) {
     int st2 = (227 * 1024 - 4096 - 8 * 2048) / (p.mt * kABytes + (bn / 2) * 128);
     if (st2 > kMaxStages) st2 = kMaxStages;
     if (g_debug_flags & 2048) fprintf(stderr, "  -> CTA-pair kernel, mt=%d, %d stages\n", p.mt, st2);
+    ++g_variant_count[p.mt == 2 ? 3 : 2];
     return igemm2_launch(tmA1, tmA2, tmWh, p, st2, stream);
   }
   static int attr_smem[2] = {0, 0};
@@ -588,6 +596,7 @@ int igemm_launch(const IgemmArgs& a, cudaStream_t stream) {
     igemm_kernel<8><<<grid, 320, smem_bytes, stream>>>(tmA1, tmA2, tmW, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error(e, "igemm: launch");
+  ++g_variant_count[p.n_pair_items > 0 ? 1 : 0];
   count_launch();
   return CS_OK;
 }

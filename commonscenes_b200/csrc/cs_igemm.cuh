@@ -40,7 +40,7 @@ struct IgemmParams {
   int out_mode;
   int act;
   // optional fused GroupNorm statistics of the OUTPUT: per (sample, channel) sum and sum of squares
-  float* stat_sum;        // [B][stat_pitch][2] fp32, atomically accumulated, or null
+  long long* stat_sum;    // [B][stat_pitch][2] 64-bit fixed point (cs_common.cuh stat_add), atomically accumulated, or null
   int stat_pitch;
 };
 

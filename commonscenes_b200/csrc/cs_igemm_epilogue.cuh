@@ -10,7 +10,7 @@ namespace cs {
 // Per warp: 32 accumulator rows.  Columns are processed 64 at a time: TMEM -> registers (4 x tcgen05.ld in
 // flight), + column vector (bias + per-sample vector, staged once per tile in shared memory), + residual
 // (fetched coalesced through the staging buffer), activation / GEGLU, GroupNorm sums (butterfly
-// transpose-reduce), pack to bf16, stage in 128B-XOR-swizzled shared memory and write out with every store
+// transpose-reduce, then order-independent fixed-point atomics), pack to bf16, stage in 128B-XOR-swizzled shared memory and write out with every store
 // instruction covering whole 128-byte row segments.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void colsum32(float (&a)[32], int lane) {
@@ -113,9 +113,7 @@ __device__ __forceinline__ void epilogue_fast_tile(const IgemmParams& p, uint32_
       colsum32(a, lane);
       colsum32(q2, lane);
       if (lane < out_cols && rows_valid > 0) {
-        float* sp = p.stat_sum + (static_cast<long long>(b) * p.stat_pitch + out_n + lane) * 2;
-        atomicAdd(sp, a[0]);
-        atomicAdd(sp + 1, q2[0]);
+        stat_add(p.stat_sum + (static_cast<long long>(b) * p.stat_pitch + out_n + lane) * 2, a[0], q2[0]);
       }
     }
     // pack -> swizzled staging -> coalesced global stores

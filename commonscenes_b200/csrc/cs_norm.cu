@@ -14,10 +14,10 @@
 namespace cs {
 
 // ------------------------------------------------------------------------------------------------
-// per-(sample, channel) sum / sum-of-squares, atomically added into stat[B][stat_pitch][2]
+// per-(sample, channel) sum / sum-of-squares, added into the fixed-point cells stat[B][stat_pitch][2] (order-independent)
 // ------------------------------------------------------------------------------------------------
 __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x, int S, int C, int pitch,
-                                float* __restrict__ stat, int stat_pitch, int vox_per_cta) {
+                                long long* __restrict__ stat, int stat_pitch, int vox_per_cta) {
   extern __shared__ float red[];  // [R][cv][16]
   const int cv = C >> 3;
   const int R = blockDim.x / cv;
@@ -46,41 +46,37 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x, int S, int 
     for (int j = 0; j < 8; ++j) { dst[j] = s[j]; dst[8 + j] = q[j]; }
   }
   __syncthreads();
-  // thread t < cv*16 reduces one (vector, component) over the R rows
-  for (int t = threadIdx.x; t < cv * 16; t += blockDim.x) {
-    float acc = 0.f;
-    for (int rr = 0; rr < R; ++rr) acc += red[rr * cv * 16 + t];
-    const int vv = t >> 4, comp = t & 15;
-    const int c = vv * 8 + (comp & 7);
-    atomicAdd(stat + (static_cast<long long>(b) * stat_pitch + c) * 2 + (comp >> 3), acc);
+  // thread t < cv*8 reduces one channel's (sum, sumsq) over the R rows in a fixed order
+  for (int t = threadIdx.x; t < cv * 8; t += blockDim.x) {
+    const int vv = t >> 3, j = t & 7;
+    float acc_s = 0.f, acc_q = 0.f;
+    for (int rr = 0; rr < R; ++rr) {
+      acc_s += red[(rr * cv + vv) * 16 + j];
+      acc_q += red[(rr * cv + vv) * 16 + 8 + j];
+    }
+    stat_add(stat + (static_cast<long long>(b) * stat_pitch + vv * 8 + j) * 2, acc_s, acc_q);
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 // finalize: (sum, sumsq) -> per-(sample, channel) affine (scale, shift); clears the accumulators
 // ------------------------------------------------------------------------------------------------
-__global__ void gn_finalize_kernel(float* __restrict__ stat, const float* __restrict__ gamma,
+__global__ void gn_finalize_kernel(long long* __restrict__ stat, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, int C, int groups, int S, float eps,
                                    float2* __restrict__ ss) {
-  extern __shared__ float sm[];  // [C][2]
+  extern __shared__ long long sm64[];  // [C][2]
   const int b = blockIdx.x;
-  float* st = stat + static_cast<long long>(b) * C * 2;
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = st[i];
+  long long* st = stat + static_cast<long long>(b) * C * 2;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm64[i] = st[i];
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) st[i] = 0.f;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) st[i] = 0;
   const int cpg = C / groups;
-  const double inv_n = 1.0 / (static_cast<double>(S) * cpg);
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const int g0 = (c / cpg) * cpg;
-    double s = 0.0, q = 0.0;
-    for (int j = 0; j < cpg; ++j) { s += sm[2 * (g0 + j)]; q += sm[2 * (g0 + j) + 1]; }
-    const double mean = s * inv_n;
-    double var = q * inv_n - mean * mean;
-    if (var < 0.0) var = 0.0;
-    const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    float mean, rstd;
+    stat_group_mean_rstd(0, c / cpg, cpg, S, sm64, C, nullptr, 0, eps, mean, rstd);
     const float ga = gamma ? gamma[c] : 1.f;
     const float be = beta ? beta[c] : 0.f;
-    ss[static_cast<long long>(b) * C + c] = make_float2(ga * rstd, be - static_cast<float>(mean) * rstd * ga);
+    ss[static_cast<long long>(b) * C + c] = make_float2(ga * rstd, be - mean * rstd * ga);
   }
 }
 
@@ -130,29 +126,14 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x, int S, int 
 // may be normalised more than once (block output -> next block AND decoder skip).
 // ------------------------------------------------------------------------------------------------
 __global__ void gn_apply_fused_kernel(const __nv_bfloat16* __restrict__ x, int S, int C, int pitch, int ch_off,
-                                      const float* __restrict__ stat1, int C1, const float* __restrict__ stat2, int C2,
+                                      const long long* __restrict__ stat1, int C1, const long long* __restrict__ stat2, int C2,
                                       const float* __restrict__ gamma, const float* __restrict__ beta, int groups,
                                       float eps, __nv_bfloat16* __restrict__ y, int y_pitch, int act, int vox_per_cta) {
   __shared__ float g_mean[64], g_rstd[64];
   const int b = blockIdx.y;
   const int Ct = C1 + C2;
   const int cpg = Ct / groups;
-  if (threadIdx.x < groups) {
-    double s = 0.0, q = 0.0;
-    for (int j = 0; j < cpg; ++j) {
-      const int c = threadIdx.x * cpg + j;
-      const float* sp = (c < C1) ? stat1 + (static_cast<long long>(b) * C1 + c) * 2
-                                 : stat2 + (static_cast<long long>(b) * C2 + (c - C1)) * 2;
-      s += sp[0];
-      q += sp[1];
-    }
-    const double inv_n = 1.0 / (static_cast<double>(S) * cpg);
-    const double mean = s * inv_n;
-    double var = q * inv_n - mean * mean;
-    if (var < 0.0) var = 0.0;
-    g_mean[threadIdx.x] = static_cast<float>(mean);
-    g_rstd[threadIdx.x] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
-  }
+  if (threadIdx.x < groups) stat_group_mean_rstd(b, threadIdx.x, cpg, S, stat1, C1, stat2, C2, eps, g_mean[threadIdx.x], g_rstd[threadIdx.x]);
   __syncthreads();
   const int cv = C >> 3;
   const int R = blockDim.x / cv;
@@ -274,7 +255,7 @@ __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long 
 // ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
-int gn_stats_launch(const void* x, int B, int S, int C, int pitch, float* stat, int stat_pitch,
+int gn_stats_launch(const void* x, int B, int S, int C, int pitch, long long* stat, int stat_pitch,
                     cudaStream_t st) {
   if (C % 8 || pitch % 8 || C > 2048 || reinterpret_cast<uintptr_t>(x) % 16)
     return set_error(CS_ERR_INVALID, "groupnorm_stats: C and pitch must be multiples of 8 (C <= 2048), x 16B aligned");
@@ -295,11 +276,11 @@ int gn_stats_launch(const void* x, int B, int S, int C, int pitch, float* stat, 
   return CS_OK;
 }
 
-int gn_finalize_launch(float* stat, const float* gamma, const float* beta, int B, int C, int groups, int S,
+int gn_finalize_launch(long long* stat, const float* gamma, const float* beta, int B, int C, int groups, int S,
                        float eps, float* scale_shift, cudaStream_t st) {
   if (groups <= 0 || C % groups) return set_error(CS_ERR_INVALID, "groupnorm_finalize: C % groups != 0");
   if (C > 4096) return set_error(CS_ERR_INVALID, "groupnorm_finalize: C too large");
-  gn_finalize_kernel<<<B, 256, static_cast<size_t>(C) * 2 * sizeof(float), st>>>(
+  gn_finalize_kernel<<<B, 256, static_cast<size_t>(C) * 2 * sizeof(long long), st>>>(
       stat, gamma, beta, C, groups, S, eps, reinterpret_cast<float2*>(scale_shift));
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error(e, "groupnorm_finalize: launch");
@@ -355,8 +336,8 @@ int layernorm_launch(const void* x, long long M, int C, int pitch, const float* 
   return CS_OK;
 }
 
-int gn_apply_fused_launch(const void* x, int B, int S, int C, int pitch, int ch_off, const float* stat1, int C1,
-                          const float* stat2, int C2, const float* gamma, const float* beta, int groups, float eps, void* y,
+int gn_apply_fused_launch(const void* x, int B, int S, int C, int pitch, int ch_off, const long long* stat1, int C1,
+                          const long long* stat2, int C2, const float* gamma, const float* beta, int groups, float eps, void* y,
                           int y_pitch, int act, cudaStream_t st) {
   const int Ct = C1 + (stat2 ? C2 : 0);
   if (C % 8 || pitch % 8 || y_pitch % 8 || ch_off % 8 || C > 2048 || reinterpret_cast<uintptr_t>(x) % 16 ||

@@ -3,7 +3,7 @@
 The reference's model/VAEGAN_V2FULL.py:17-760 couples a layout branch (box/angle GCN-VAE, discriminators: SURVEY.md
 §8f rank 2, not on this hot path) with the shape branch.  This class keeps the reference's names and semantics for
 the shape branch (always) and, with `layout_branch=True`, the forward of the layout branch (encoder / manipulate /
-decoder: same kernels, GPU verification of that part pending -- tests/test_gcn_gpu.py marks it xfail-tolerant).  Shape branch: the decoder-side embeddings (:69-75), the relation encoder E2 (`gconv_net_ec_rel`, :128-147),
+decoder: same kernels, GPU-verified against the real class's goldens in tests/test_gcn_gpu.py).  Shape branch: the decoder-side embeddings (:69-75), the relation encoder E2 (`gconv_net_ec_rel`, :128-147),
 `rel_mlp` (:152-155), `encoder_2` (:220-242), `balance_objects` / `select_sdfs` (:398-463), the denoiser call of
 `forward` (:511-521) and the shape half of `sample` (:600-616).  State-dict keys of these members are the reference's,
 so a v2_full checkpoint's shape-branch tensors load with strict=False.
@@ -75,6 +75,16 @@ class Sg2ScVAEModel(nn.Module):
         self.rel_mlp = make_mlp(net_rel_layers, batch_norm=mlp_normalization, norelu=True)
         if layout_branch:       # reference :157-160
             self.angle_net = make_mlp([gconv_dim * 2 + add_dim, hidden, 24], batch_norm=mlp_normalization, norelu=True)
+        # initialisation (reference :162-172): kaiming-normal Linear weights, same modules in the same order (the RNG stream
+        # of a from-scratch run then matches the reference's); angle_net keeps torch's default init there too
+        from .graph import _init_weights
+        if layout_branch:
+            for mod in (self.d3_embeddings, self.mean_var, self.mean, self.var, self.d3_net):
+                mod.apply(_init_weights)
+        self.rel_mlp.apply(_init_weights)
+        if layout_branch and use_angles:
+            for mod in (self.angle_mean_var, self.angle_mean, self.angle_var):
+                mod.apply(_init_weights)
 
     # ---- layout branch: forward only, on the same GraphTripleConv / MLP kernels as encoder_2 ----------
     def _need_layout(self):

@@ -28,6 +28,14 @@ def build_mlp(dim_list, activation="relu", batch_norm="none", dropout=0, final_n
     return nn.Sequential(*layers)
 
 
+def _bn_momentum(m: nn.BatchNorm1d) -> float:
+    """torch semantics: momentum=None is a cumulative moving average, factor 1 / num_batches_tracked (already bumped)."""
+    if m.momentum is not None:
+        return float(m.momentum)
+    n = int(m.num_batches_tracked) if m.num_batches_tracked is not None else 0
+    return 1.0 / max(n, 1)
+
+
 @torch.no_grad()
 def run_mlp(mlp, x: torch.Tensor) -> torch.Tensor:
     """Execute a build_mlp stack (nn.Sequential or list of its layers) on an fp32 (M, C) CUDA matrix."""
@@ -45,7 +53,7 @@ def run_mlp(mlp, x: torch.Tensor) -> torch.Tensor:
             if training and m.track_running_stats:
                 m.num_batches_tracked += 1
             x = ops.batchnorm_relu(x, m.weight, m.bias, m.running_mean, m.running_var, training,
-                                   momentum=0.1 if m.momentum is None else m.momentum, eps=m.eps, relu=relu)
+                                   momentum=_bn_momentum(m), eps=m.eps, relu=relu)
             i += 2 if relu else 1
         elif isinstance(m, nn.ReLU):
             x = ops.batchnorm_relu(x, None, None, torch.zeros(x.shape[1], device=x.device), torch.ones(x.shape[1], device=x.device),
@@ -105,7 +113,7 @@ def run_mlp_train(mlp, x: torch.Tensor):
             if training and m.track_running_stats:
                 m.num_batches_tracked += 1
             y = ops.batchnorm_relu(x, m.weight, m.bias, m.running_mean, m.running_var, training,
-                                   momentum=0.1 if m.momentum is None else m.momentum, eps=m.eps, relu=relu)
+                                   momentum=_bn_momentum(m), eps=m.eps, relu=relu)
             tape.append(("bn_relu" if relu else "bn", m, x, y, training))
             i += 2 if relu else 1
         elif isinstance(m, nn.ReLU):

@@ -33,7 +33,8 @@ def _f(t: torch.Tensor) -> torch.Tensor:
 
 class Act:
     """A channels-last bf16 activation together with the per-(sample, channel) (sum, sum of squares) its producer's
-    epilogue accumulated — everything a later GroupNorm of this tensor needs (fp32 (B, C, 2), read-only for consumers)."""
+    epilogue accumulated — everything a later GroupNorm of this tensor needs (int64 fixed point (B, C, 2), read-only for
+    consumers; order-independent integer accumulation makes every forward bit-reproducible)."""
     __slots__ = ("t", "stat")
 
     def __init__(self, t, stat):
@@ -41,11 +42,11 @@ class Act:
 
 
 class StatArena:
-    """One zero-initialised fp32 buffer per forward pass from which the GroupNorm sum buffers are carved (a single memset
+    """One zero-initialised int64 (fixed-point sums) buffer per forward pass from which the GroupNorm sum buffers are carved (a single memset
     instead of one per tensor; CUDA-graph friendly: the buffer is persistent, the memset is captured)."""
 
     def __init__(self, device, numel):
-        self.buf = torch.zeros(numel, dtype=torch.float32, device=device)
+        self.buf = torch.zeros(numel, dtype=ops.STAT_DTYPE, device=device)
         self.off = 0
 
     def reset(self):

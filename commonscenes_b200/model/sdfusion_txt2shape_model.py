@@ -255,10 +255,11 @@ class SDFusionText2ShapeModel(BaseModel):
         self.switch_train()
 
     @torch.no_grad()
-    def rel2shape(self, data, ddim_steps=100, ddim_eta=0.0, uc_scale=None, seed=None, return_latent=False, sampler="ddim"):
+    def rel2shape(self, data, ddim_steps=100, ddim_eta=0.0, uc_scale=None, seed=None, return_latent=False, sampler="ddim",
+                  ddpm_timesteps=None):
         """Scene-graph conditioning -> (O, 1, R, R, R) SDFs.  One shared x_T for all objects (reference :487-491).
-        sampler="ddpm": ancestral sampling over all num_timesteps (BASELINE cfg5; samplers/ddpm.py) instead of DDIM —
-        `ddim_steps` is then ignored unless it is smaller than num_timesteps AND explicitly meant to truncate (tests)."""
+        sampler="ddpm": ancestral sampling (BASELINE cfg5; samplers/ddpm.py) instead of DDIM: `ddim_steps` is ignored and
+        the chain runs over all num_timesteps, or starts at t = ddpm_timesteps - 1 when `ddpm_timesteps` is given."""
         self.switch_eval()
         self.set_input(data)
         ddim_steps = self.ddim_steps if ddim_steps is None else ddim_steps
@@ -273,7 +274,7 @@ class SDFusionText2ShapeModel(BaseModel):
                 self.ddpm_sampler = DDPMSampler(self)
             samples, _ = self.ddpm_sampler.sample(batch_size=B, shape=self.z_shape, conditioning=self.rel, x_T=noise,
                                                   unconditional_guidance_scale=uc_scale, unconditional_conditioning=self.uc_rel,
-                                                  timesteps=None if ddim_steps in (None, 100) else ddim_steps, generator=gen)
+                                                  timesteps=ddpm_timesteps, generator=gen)
         elif sampler == "ddim":
             samples, _ = self.ddim_sampler.sample(S=ddim_steps, batch_size=B, shape=self.z_shape, conditioning=self.rel, x_T=noise,
                                                   verbose=False, unconditional_guidance_scale=uc_scale,

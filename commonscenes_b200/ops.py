@@ -72,6 +72,16 @@ def reset_launch_count() -> None:
     _lib.load().cs_reset_launch_count()
 
 
+CONV_VARIANTS = ("one tile per CTA", "pair / hybrid work list", "CTA-pair kernel (cta_group::2)", "CTA pairs x two accumulators")
+
+
+def conv3d_variant_counts(reset: bool = False) -> dict:
+    """cs_conv3d launches per kernel variant since the last reset (which code path a shape / batch size selects)."""
+    buf = (C.c_uint64 * 4)()
+    _lib.load().cs_conv3d_variant_counts(buf, int(reset))
+    return dict(zip(CONV_VARIANTS, (int(v) for v in buf)))
+
+
 # ----------------------------------------------------------------------------------------------
 # weight packing (one-off, at load / after an optimizer step) — layout plumbing, done with torch
 # ----------------------------------------------------------------------------------------------
@@ -254,7 +264,7 @@ def conv3d(x: torch.Tensor, weight: torch.Tensor, *, ksize: Sequence[int] = (3, 
         a.residual, a.res_pitch = residual.data_ptr(), rp
     a.out, a.out_pitch, a.out_mode, a.act = out.data_ptr(), out_pitch, out_mode, act
     if stat_sum is not None:
-        a.stat_sum, a.stat_pitch = stat_sum.data_ptr(), stat_sum.shape[1]
+        a.stat_sum, a.stat_pitch = _check_stat(stat_sum, "conv3d.stat_sum").data_ptr(), stat_sum.shape[1]
     a.bn_hint = bn_hint
     prof = ConvProfiler.active
     if prof is not None:
@@ -279,20 +289,35 @@ def linear_tokens(x: torch.Tensor, weight: torch.Tensor, **kw) -> torch.Tensor:
 _ws: dict = {}
 
 
-def _workspace(device: torch.device, key: str, numel: int, zero: bool = False) -> torch.Tensor:
+def _workspace(device: torch.device, key: str, numel: int, zero: bool = False, dtype=torch.float32) -> torch.Tensor:
     k = (device, key)
     t = _ws.get(k)
     if t is None or t.numel() < numel:
-        t = torch.zeros(numel, dtype=torch.float32, device=device)
+        t = torch.zeros(numel, dtype=dtype, device=device)
         _ws[k] = t
     return t
 
 
+STAT_DTYPE = torch.int64     # GroupNorm sum buffers: 64-bit fixed point, see include/cs_b200.h (cs_groupnorm_stats)
+STAT_SUM_SCALE, STAT_SQ_SCALE = float(1 << 20), float(1 << 12)
+
+
+def stat_to_float(stat: torch.Tensor) -> torch.Tensor:
+    """(B, C, 2) fixed-point GroupNorm sums -> fp64 (sum, sum of squares) (tests / diagnostics)."""
+    return torch.stack([stat[..., 0].double() / STAT_SUM_SCALE, stat[..., 1].double() / STAT_SQ_SCALE], dim=-1)
+
+
+def _check_stat(stat: Optional[torch.Tensor], name: str) -> Optional[torch.Tensor]:
+    if stat is not None and (stat.dtype != STAT_DTYPE or not stat.is_cuda or not stat.is_contiguous()):
+        raise _lib.CsError(f"{name}: GroupNorm sum buffers are contiguous int64 (B, C, 2) CUDA tensors (fixed point)")
+    return stat
+
+
 def zero_stat_buffer(device: torch.device, B: int, C: int) -> torch.Tensor:
-    """(B, C, 2) fp32 view of the shared GroupNorm-sum workspace.  It is all-zero on return (the finalize
+    """(B, C, 2) int64 (fixed-point) view of the shared GroupNorm-sum workspace.  It is all-zero on return (the finalize
     kernel clears what it consumes); pass it as `stat_sum` to conv3d and then to the groupnorm that follows,
     with no other groupnorm in between."""
-    return _workspace(device, "gn_stat", B * C * 2)[:B * C * 2].view(B, C, 2)
+    return _workspace(device, "gn_stat", B * C * 2, dtype=STAT_DTYPE)[:B * C * 2].view(B, C, 2)
 
 
 def groupnorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, groups: int = 32, eps: float = 1e-5,
@@ -314,13 +339,13 @@ def groupnorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, group
         raise _lib.CsError("groupnorm: bad output shape")
     st = _stream()
     if stat_sum is None:
-        stat = _workspace(x.device, "gn_stat", B * Ct * 2)  # kept all-zero between calls by finalize
+        stat = _workspace(x.device, "gn_stat", B * Ct * 2, dtype=STAT_DTYPE)  # kept all-zero between calls by finalize
         check(lib.cs_groupnorm_stats(x.data_ptr(), B, S, C1, p1, stat.data_ptr(), Ct, st), "cs_groupnorm_stats")
         if x2 is not None:
-            check(lib.cs_groupnorm_stats(x2.data_ptr(), B, S, C2, p2, stat.data_ptr() + C1 * 8, Ct, st),
+            check(lib.cs_groupnorm_stats(x2.data_ptr(), B, S, C2, p2, stat.data_ptr() + C1 * 16, Ct, st),
                   "cs_groupnorm_stats")
     else:
-        stat = stat_sum
+        stat = _check_stat(stat_sum, "groupnorm.stat_sum")
     ss = _workspace(x.device, "gn_ss", B * Ct * 2)
     check(lib.cs_groupnorm_finalize(stat.data_ptr(), _ptr(_f32(gamma, "gamma")), _ptr(_f32(beta, "beta")), B, Ct,
                                     groups, S, eps, ss.data_ptr(), st), "cs_groupnorm_finalize")
@@ -333,8 +358,9 @@ def groupnorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, group
 
 
 def groupnorm_stats(x: torch.Tensor, stat: torch.Tensor) -> torch.Tensor:
-    """Accumulate the per-(sample, channel) sum / sum of squares of x into the ZEROED fp32 buffer stat (B, C, 2)."""
+    """Accumulate the per-(sample, channel) sum / sum of squares of x into the ZEROED fixed-point buffer stat (B, C, 2)."""
     B, D, H, W, Cc, p = _check_act(x, "groupnorm_stats.x")
+    _check_stat(stat, "groupnorm_stats.stat")
     check(_lib.load().cs_groupnorm_stats(x.data_ptr(), B, D * H * W, Cc, p, stat.data_ptr(), Cc, _stream()), "cs_groupnorm_stats")
     return stat
 
@@ -342,9 +368,10 @@ def groupnorm_stats(x: torch.Tensor, stat: torch.Tensor) -> torch.Tensor:
 def groupnorm_fused(x: torch.Tensor, stat: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, groups: int = 32,
                     eps: float = 1e-5, act: int = ACT_NONE, x2: Optional[torch.Tensor] = None,
                     stat2: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """act(GroupNorm(cat(x, x2))) from per-channel sums that already exist (`stat`, `stat2`: fp32 (B, C, 2) written by the
+    """act(GroupNorm(cat(x, x2))) from per-channel sums that already exist (`stat`, `stat2`: int64 fixed-point (B, C, 2) written by the
     producing conv's epilogue or by groupnorm_stats).  One kernel per source; nothing is cleared."""
     lib = _lib.load()
+    _check_stat(stat, "groupnorm_fused.stat"), _check_stat(stat2, "groupnorm_fused.stat2")
     B, D, H, W, C1, p1 = _check_act(x, "groupnorm_fused.x")
     S = D * H * W
     C2 = 0

@@ -54,6 +54,11 @@ def rel2shape_sharded(diff_model, data: dict, ddim_steps: int = 100, ddim_eta: f
         return diff_model.rel2shape(data, ddim_steps=ddim_steps, ddim_eta=ddim_eta, uc_scale=uc_scale, seed=seed, **sampler_kw)
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     n = data["rel"].shape[0]
+    if seed is None:        # the reference seeds x_T from the clock (:487): draw ONE seed on rank 0 so every rank shares x_T
+        import time
+        box = torch.tensor([int(time.time())], dtype=torch.int64, device=data["rel"].device)
+        dist.broadcast(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        seed = int(box.item())
     lo, hi = partition(n, world)[rank]
     if hi > lo:
         local = {k: v[lo:hi] for k, v in data.items()}

@@ -134,12 +134,17 @@ class DenoiserTrainStep:
                 dist.all_reduce(self.flat_g[lo:hi], op=dist.ReduceOp.SUM, group=self.group)
 
     def step(self, z: torch.Tensor, cond: torch.Tensor, t: Optional[torch.Tensor] = None, noise: Optional[torch.Tensor] = None,
-             need_dcond: bool = False):
+             need_dcond: bool = False, grad_weight: float = 1.0):
         """One optimisation step on this rank's shard.  z: (B, 3, 16, 16, 16) fp32 latents (VQVAE encode_only output),
-        cond: (B, 1, context_dim) fp32.  Returns (loss tensor on the device [mean MSE, unscaled], d_cond or None)."""
+        cond: (B, 1, context_dim) fp32.  Returns (loss tensor on the device [mean MSE, unscaled], d_cond or None).
+        grad_weight: this rank's share of the global batch relative to an equal split (n_local * world / n_total), so that
+        the 1/world mean over ranks is the global-batch mean even when the shards are ragged.  B == 0 (more ranks than
+        objects) contributes zero gradients but still takes part in every collective."""
         m = self.model
         B = z.shape[0]
         dev = z.device
+        if B == 0:
+            return self._step_without_objects(cond)
         if t is None:
             t = torch.randint(0, m.num_timesteps, (B,), device=dev).long()
         if noise is None:
@@ -147,7 +152,7 @@ class DenoiserTrainStep:
         x_t = m.q_sample(z, t, noise)
         eps, tape = self.trainer.forward_train(x_t, t, cond)
         self.loss.zero_()
-        d_eps = ops_bwd.mse_loss_grad(eps, noise.float().contiguous(), self.loss, loss_scale=self.loss_scale)
+        d_eps = ops_bwd.mse_loss_grad(eps, noise.float().contiguous(), self.loss, loss_scale=self.loss_scale * grad_weight)
         self.flat_g.zero_()
         sink = GradSink(self.views)
         if self.world > 1:
@@ -161,6 +166,19 @@ class DenoiserTrainStep:
             torch.cuda.current_stream().wait_stream(self.comm_stream)
         else:
             _, d_ctx = self.trainer.backward(tape, d_eps, sink=sink, need_dcontext=need_dcond)
+        return self._clip_and_update(d_ctx)
+
+    def _step_without_objects(self, cond):
+        """This rank holds no object of the global batch: zero gradients into every bucket's all-reduce, same update."""
+        self.loss.zero_()
+        self.flat_g.zero_()
+        if self.world > 1:
+            self._allreduce_ready(0, list(range(len(self.buckets))))
+            if self.comm_stream is not None:
+                torch.cuda.current_stream().wait_stream(self.comm_stream)
+        return self._clip_and_update(torch.zeros_like(cond))
+
+    def _clip_and_update(self, d_ctx):
         self.step_count += 1
         self.step_dev.add_(1)
         self.sumsq.zero_()
@@ -236,6 +254,10 @@ class DenoiserTrainStep:
             self._gn.copy_(noise)
         self.graph.replay()
         self.step_count += 1
+        # the replay re-packed and then updated the weights in place (raw-pointer kernels: no autograd version bump), so
+        # the module's cached kernel-layout copies (emb / cross-attention matrices, DDIM graph) are stale for anyone
+        # evaluating between steps: invalidate, as step() does
+        self.unet._packed = None
         return self._gout
 
 
@@ -307,22 +329,33 @@ class ShapeBranchTrainStep:
         return partition(n_selected, self.world)[self.rank]
 
     def step(self, z, objs, triples, text_feat, rel_feat, sdfs, rows: Optional[torch.Tensor] = None,
-             t: Optional[torch.Tensor] = None, noise: Optional[torch.Tensor] = None):
+             t: Optional[torch.Tensor] = None, noise: Optional[torch.Tensor] = None, n_total: Optional[int] = None):
         """z (O, 64) layout latents, objs (O,), triples (T, 3), CLIP features (O, 512) / (T, 512), sdfs (O, 1, 64, 64, 64).
-        rows: indices of the objects that enter the denoiser on THIS rank (default: this rank's block of all O objects);
+        rows: indices of the objects that enter the denoiser on THIS rank (default: this rank's block of all O objects;
+        may be empty); n_total: objects entering the denoiser over all ranks (default: O, or len(rows) * world for given rows);
         t / noise: optional fixed timesteps and noise for those rows.  Returns (loss [mean MSE on this rank], d_z (O, 64))."""
         m = self.model
         O = objs.shape[0]
         if rows is None:
             lo, hi = self.shard(O)
             rows = torch.arange(lo, hi, device=objs.device)
+            n_total = O
+        elif n_total is None:       # caller-chosen rows: the global count is the sum over ranks
+            n_total = int(rows.shape[0]) * self.world
+        n_local = int(rows.shape[0])
+        # global-batch mean (not a mean of per-rank means): weight this rank's mean gradient by n_local * world / n_total
+        weight = n_local * self.world / max(n_total, 1)
         uc, c, tape = m.encoder_2_train(z, objs, triples, text_feat, rel_feat)
         c = uc if c is None else c
-        with torch.no_grad():
-            lat = m.Diff.vqvae(sdfs[rows].to(c.device), forward_no_quant=True, encode_only=True)
-        loss, d_c_rows = self.denoiser.step(lat, c[rows].contiguous(), t=t, noise=noise, need_dcond=True)
+        if n_local:
+            with torch.no_grad():
+                lat = m.Diff.vqvae(sdfs[rows].to(c.device), forward_no_quant=True, encode_only=True)
+        else:
+            lat = torch.zeros((0,) + tuple(m.Diff.z_shape), dtype=torch.float32, device=c.device)
+        loss, d_c_rows = self.denoiser.step(lat, c[rows].contiguous(), t=t, noise=noise, need_dcond=True, grad_weight=weight)
         d_c = torch.zeros((O, c.shape[-1]), dtype=torch.float32, device=c.device)
-        d_c.index_copy_(0, rows, d_c_rows.reshape(rows.shape[0], -1).float())
+        if n_local:
+            d_c.index_copy_(0, rows, d_c_rows.reshape(n_local, -1).float())
         g = self.graph_params
         g.flat_g.zero_()
         _, d_z = m.encoder_2_backward(tape, d_c=d_c if m.use_E2 else None, d_uc=None if m.use_E2 else d_c, sink=GradSink(g.views))

@@ -70,7 +70,7 @@ typedef struct cs_conv3d_args {
   const float* rowvec; int32_t rowvec_pitch;         /* [B][pitch] per-sample vector or NULL */
   const void* residual; int32_t res_pitch;           /* bf16 [B*Do*Ho*Wo][pitch] or NULL */
   void* out; int32_t out_pitch; int32_t out_mode; int32_t act;
-  float* stat_sum; int32_t stat_pitch;               /* optional fused GroupNorm sums [B][pitch][2] */
+  int64_t* stat_sum; int32_t stat_pitch;             /* optional fused GroupNorm sums [B][pitch][2], fixed point (below) */
   int32_t bn_hint;                                   /* N tile override, 0 = auto */
 } cs_conv3d_args;
 int cs_conv3d(const cs_conv3d_args* args, cs_stream_t stream);
@@ -101,7 +101,7 @@ int cs_unpack_wgrad(const float* dw, int32_t Cout, int32_t taps, int32_t C1, int
  *   pass 1: dx = rstd * (gamma dz - mean_g(gamma dz) - xhat mean_g(gamma dz xhat)) + extra       (extra optional, bf16)
  * Parameter gradients: dbeta[c] = sum_b red[b][c][0], dgamma[c] = sum_b red[b][c][1] (cs_batch_reduce). */
 int cs_groupnorm_bwd(const void* x, int32_t B, int32_t S, int32_t C, int32_t pitch, int32_t ch_off, const void* dy,
-                     int32_t dy_pitch, int32_t dy_off, const float* stat1, int32_t C1, const float* stat2, int32_t C2,
+                     int32_t dy_pitch, int32_t dy_off, const int64_t* stat1, int32_t C1, const int64_t* stat2, int32_t C2,
                      const float* gamma, const float* beta, int32_t groups, float eps, int32_t act, float* red,
                      const void* extra, int32_t extra_pitch, void* dx, int32_t dx_pitch, int32_t pass, cs_stream_t stream);
 /* out[c] += sum_b in[b][c][comp]   (in: fp32 [B][C][ncomp]) */
@@ -161,11 +161,15 @@ int cs_attention_bwd(const void* q, const void* k, const void* v, const void* o,
 
 /* ---- GroupNorm (GroupNorm32: ldm_diffusion_util.py:237-239; Normalize: attention.py:78-79,
  *      vqvae_modules.py:13-21) --------------------------------------------------------------- */
+/* GroupNorm sum buffers are int64 FIXED POINT: stat[b][c][0] = round(2^20 * sum), stat[b][c][1] = round(2^12 * sum of
+ * squares), accumulated with integer atomics, so the totals (and everything normalised with them) are bit-identical from
+ * run to run regardless of the order in which CTAs contribute -- the reference's GroupNorm is deterministic too.
+ * Zero the buffer before the first producer writes into it. */
 /* stat[b][c][0..1] += sum / sum of squares over the S voxels of sample b */
-int cs_groupnorm_stats(const void* x, int32_t B, int32_t S, int32_t C, int32_t pitch, float* stat,
+int cs_groupnorm_stats(const void* x, int32_t B, int32_t S, int32_t C, int32_t pitch, int64_t* stat,
                        int32_t stat_pitch, cs_stream_t stream);
 /* (sum,sumsq) -> scale_shift[b][c] = (gamma*rstd, beta - mean*rstd*gamma); zeroes `stat` */
-int cs_groupnorm_finalize(float* stat, const float* gamma, const float* beta, int32_t B, int32_t C,
+int cs_groupnorm_finalize(int64_t* stat, const float* gamma, const float* beta, int32_t B, int32_t C,
                           int32_t groups, int32_t S, float eps, float* scale_shift, cs_stream_t stream);
 /* y = act(x * scale + shift) */
 int cs_groupnorm_apply(const void* x, int32_t B, int32_t S, int32_t C, int32_t pitch,
@@ -177,7 +181,7 @@ int cs_groupnorm_apply(const void* x, int32_t B, int32_t S, int32_t C, int32_t p
  * (written by cs_conv3d's stat_sum epilogue or cs_groupnorm_stats); x is the source that owns those channels.  The sums
  * are read only, so one tensor can be normalised by several consumers. */
 int cs_groupnorm_apply_fused(const void* x, int32_t B, int32_t S, int32_t C, int32_t pitch, int32_t ch_off,
-                             const float* stat1, int32_t C1, const float* stat2, int32_t C2, const float* gamma,
+                             const int64_t* stat1, int32_t C1, const int64_t* stat2, int32_t C2, const float* gamma,
                              const float* beta, int32_t groups, float eps, void* y, int32_t y_pitch, int32_t act,
                              cs_stream_t stream);
 
@@ -276,6 +280,10 @@ int cs_cast_f32_to_bf16(const float* x, int64_t n, void* y, cs_stream_t stream);
 /* tuning experiments only (tools/): bit 0 = drop the epilogue's global stores, bit 1 = empty epilogue, bit 2 = no MMA.
  * Results are WRONG while any bit is set; 0 restores normal operation. */
 void cs_debug_set(int32_t flags);
+/* cs_conv3d launches per kernel variant since the last reset (diagnostics for the parity tests: which variant a shape took):
+ * out4[0] one 128-voxel tile per CTA, [1] pair / hybrid work list, [2] CTA-pair kernel (cta_group::2), [3] CTA pairs with two
+ * accumulators.  out4 may be NULL (reset only). */
+void cs_conv3d_variant_counts(uint64_t* out4, int32_t reset);
 
 #ifdef __cplusplus
 }

@@ -24,6 +24,10 @@ CASES = [
     (2, 448, 0, 3584, (4, 8, 8), 1, (1, 1, 1)),
     (3, 96, 32, 40, (2, 4, 4), 3, (1, 1, 1)),
     (1, 672, 672, 672, (16, 4, 4), 3, (1, 1, 1)),
+    # the training batch of BASELINE cfg3 (32 objects): the dgrad takes the pair / quad igemm variants, the wgrad its full K split
+    (32, 224, 0, 224, (16, 16, 16), 3, (1, 1, 1)),
+    (32, 448, 0, 448, (16, 8, 8), 3, (1, 1, 1)),
+    (32, 448, 224, 224, (16, 16, 16), 3, (1, 1, 1)),
 ]
 
 
@@ -83,8 +87,8 @@ def test_groupnorm_bwd(C1, C2, act):
     x_cl = _cl(x)
     x1 = x_cl[..., :C1].contiguous()
     x2 = x_cl[..., C1:].contiguous() if C2 else None
-    s1 = ops.groupnorm_stats(x1, torch.zeros(B, C1, 2, device=dev))
-    s2 = ops.groupnorm_stats(x2, torch.zeros(B, C2, 2, device=dev)) if C2 else None
+    s1 = ops.groupnorm_stats(x1, torch.zeros(B, C1, 2, dtype=ops.STAT_DTYPE, device=dev))
+    s2 = ops.groupnorm_stats(x2, torch.zeros(B, C2, 2, dtype=ops.STAT_DTYPE, device=dev)) if C2 else None
     ex_cl = _cl(ex)
     e1 = ex_cl[..., :C1].contiguous()
     e2 = ex_cl[..., C1:].contiguous() if C2 else None

@@ -146,8 +146,6 @@ def test_gcn_backward_kernels_edge_cases():
     assert torch.allclose(dW.cpu(), torch.zeros(6, 4).index_add(0, idx, rows[:, 2:6]), atol=1e-6)
 
 
-@pytest.mark.xfail(strict=False, reason="layout-branch forward (SURVEY.md 8f-2) was added after this round's GPU budget was spent: its first "
-                                        "GPU run is pending; it is built only from the GraphTripleConv / MLP kernels verified above")
 @pytest.mark.parametrize("tag", ["tiny", "full"])
 def test_layout_branch_forward_matches_reference_class_golden(tag, tmp_path):
     """encoder / manipulate / decoder of Sg2ScVAEModel(layout_branch=True) vs what the reference's REAL class computed
@@ -189,8 +187,6 @@ def test_layout_branch_forward_matches_reference_class_golden(tag, tmp_path):
         check(b, f"boxes_{mode}"); check(a, f"angle_logp_{mode}")
 
 
-@pytest.mark.xfail(strict=False, reason="layout-branch backward (SURVEY.md 8f-2) was added after this round's GPU budget was spent: first GPU "
-                                        "run pending; wiring is CPU-verified (tests/test_layout_wiring_cpu.py), kernels are the ones verified above")
 def test_layout_branch_gradients_match_oracle_autograd(tmp_path):
     """`loss.backward()` through encoder -> reparameterise -> decoder (+ manipulate) of Sg2ScVAEModel(layout_branch=True) on the
     GPU vs autograd through the oracle (pinned to the real class): every layout parameter gradient, train-mode BatchNorm."""
@@ -251,8 +247,6 @@ def test_layout_branch_gradients_match_oracle_autograd(tmp_path):
     print(f"layout backward on the GPU: worst parameter-gradient rel-L2 {worst:.2e}")
 
 
-@pytest.mark.xfail(strict=False, reason="BoxDiscriminator mirror was added after this round's GPU budget was spent: first GPU run pending; "
-                                        "wiring is CPU-verified (tests/test_layout_wiring_cpu.py)")
 def test_box_discriminator_on_gpu_matches_reference_golden():
     from commonscenes_b200.model.discriminators import BoxDiscriminator
     g = np.load(os.path.join(GOLD, "box_discriminator.npz"))

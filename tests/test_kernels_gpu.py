@@ -72,6 +72,45 @@ def test_conv3d_matches_torch(ops, case):
     _report(name, _ncdhw(got), ref, rtol=2 ** -7, atol=2e-3)
 
 
+# The benchmarked batch (32 objects x CFG = 64): the 16^3-level convs take the CTA-pair / two-accumulator ("quad") kernel, the
+# deeper levels the pair / hybrid work lists -- variants the B <= 4 cases above never select (cs_igemm.cu: igemm_launch).
+CONV_CASES_B64 = [
+    # name, Cin (C1, C2), Cout, (D, H, W), expected variant
+    ("b64_224to224_16^3", (224, 0), 224, (16, 16, 16), "CTA pairs x two accumulators"),
+    ("b64_448to448_16^3", (448, 0), 448, (16, 16, 16), "CTA pairs x two accumulators"),
+    ("b64_448+224to224_16^3", (448, 224), 224, (16, 16, 16), "CTA pairs x two accumulators"),
+    ("b64_672to224_16^3", (672, 0), 224, (16, 16, 16), "CTA pairs x two accumulators"),
+    ("b64_448to448_16x8x8", (448, 0), 448, (16, 8, 8), "pair / hybrid work list"),
+    ("b64_672to672_16x4x4", (672, 0), 672, (16, 4, 4), "pair / hybrid work list"),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES_B64, ids=[c[0] for c in CONV_CASES_B64])
+def test_conv3d_benchmark_batch_matches_torch(ops, case):
+    name, (C1, C2), Cout, (D, H, W), want = case
+    B = 64
+    g = torch.Generator(device="cuda").manual_seed(4321)
+    x = torch.randn(B, C1 + C2, D, H, W, device="cuda", generator=g)
+    w = torch.randn(Cout, C1 + C2, 3, 3, 3, device="cuda", generator=g) / math.sqrt((C1 + C2) * 27)
+    b = torch.randn(Cout, device="cuda", generator=g)
+    ref = F.conv3d(_bf(x).float(), _bf(w).float(), b, padding=1)
+    stat = torch.zeros(B, Cout, 2, dtype=ops.STAT_DTYPE, device="cuda")
+    ops.conv3d_variant_counts(reset=True)
+    if C2:
+        got = ops.conv3d(_cl(x[:, :C1]), ops.pack_conv_weight(w, split=(C1, C2)), x2=_cl(x[:, C1:]), bias=b, stat_sum=stat)
+    else:
+        got = ops.conv3d(_cl(x), ops.pack_conv_weight(w), bias=b, stat_sum=stat)
+    torch.cuda.synchronize()
+    ran = [k for k, v in ops.conv3d_variant_counts(reset=True).items() if v]
+    print(f"{name}: kernel variant {ran}")
+    _report(name, _ncdhw(got), ref, rtol=2 ** -7, atol=2e-3)
+    gotf = got.float()
+    s_ref = torch.stack([gotf.sum(dim=(1, 2, 3)), (gotf * gotf).sum(dim=(1, 2, 3))], dim=-1)     # sums of the fp32 values
+    _report(name + "_stats", ops.stat_to_float(stat).float(), s_ref, rtol=2e-3, atol=1.0)   # that were rounded to bf16
+    if want is not None:
+        assert ran == [want], f"{name}: expected the '{want}' variant at batch 64, got {ran}"
+
+
 def test_conv3d_epilogue_rowvec_residual_stats(ops):
     B, C, D, H, W = 2, 224, 16, 8, 8
     g = torch.Generator(device="cuda").manual_seed(7)
@@ -81,12 +120,15 @@ def test_conv3d_epilogue_rowvec_residual_stats(ops):
     rv = torch.randn(B, C, device="cuda", generator=g)
     res = torch.randn(B, C, D, H, W, device="cuda", generator=g)
     ref = F.conv3d(_bf(x).float(), _bf(w).float(), b, padding=1) + rv[:, :, None, None, None] + _bf(res).float()
-    stat = torch.zeros(B, C, 2, device="cuda")
+    stat = torch.zeros(B, C, 2, dtype=ops.STAT_DTYPE, device="cuda")
     got = ops.conv3d(_cl(x), ops.pack_conv_weight(w), bias=b, rowvec=rv, residual=_cl(res), stat_sum=stat)
+    stat_again = torch.zeros_like(stat)
+    ops.conv3d(_cl(x), ops.pack_conv_weight(w), bias=b, rowvec=rv, residual=_cl(res), stat_sum=stat_again)
     torch.cuda.synchronize()
     _report("epilogue", _ncdhw(got), ref, rtol=2 ** -7, atol=4e-3)
     s_ref = torch.stack([ref.sum(dim=(2, 3, 4)), (ref * ref).sum(dim=(2, 3, 4))], dim=-1)
-    _report("fused_stats", stat, s_ref, rtol=1e-3, atol=0.5)
+    _report("fused_stats", ops.stat_to_float(stat).float(), s_ref, rtol=1e-3, atol=0.5)
+    assert torch.equal(stat, stat_again), "fixed-point GroupNorm sums must be bit-identical from launch to launch"
 
 
 def test_conv3d_two_sources_equals_concat(ops):

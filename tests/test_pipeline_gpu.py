@@ -70,11 +70,11 @@ def test_cfg5_ancestral_sampling_ten_objects(model):
     n = 10
     data = {"sdf": torch.zeros(n, 1, 64, 64, 64, device="cuda"), "rel": torch.randn(n, 1, 1280, device="cuda", generator=g),
             "uc": torch.randn(n, 1, 1280, device="cuda", generator=g)}
-    sdf, z = model.rel2shape(data, ddim_steps=40, uc_scale=3.0, seed=3, return_latent=True, sampler="ddpm")
+    sdf, z = model.rel2shape(data, ddpm_timesteps=40, uc_scale=3.0, seed=3, return_latent=True, sampler="ddpm")
     assert sdf.shape == (n, 1, 64, 64, 64) and torch.isfinite(sdf).all() and torch.isfinite(z).all()
-    _, z2 = model.rel2shape(data, ddim_steps=40, uc_scale=3.0, seed=3, return_latent=True, sampler="ddpm")
+    _, z2 = model.rel2shape(data, ddpm_timesteps=40, uc_scale=3.0, seed=3, return_latent=True, sampler="ddpm")
     assert float((z - z2).norm() / z.norm()) < 5e-2
-    _, z3 = model.rel2shape(data, ddim_steps=40, uc_scale=3.0, seed=4, return_latent=True, sampler="ddpm")
+    _, z3 = model.rel2shape(data, ddpm_timesteps=40, uc_scale=3.0, seed=4, return_latent=True, sampler="ddpm")
     assert float((z - z3).norm() / z.norm()) > 0.2
     with pytest.raises(ValueError):
         model.rel2shape(data, sampler="plms")

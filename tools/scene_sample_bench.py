@@ -45,7 +45,7 @@ def run(**kw):
 
 
 run(ddim_steps=5)                                   # warm-up: packing, graph capture
-run(ddim_steps=20, sampler="ddpm")
+run(ddpm_timesteps=20, sampler="ddpm")
 t_ddim = run(ddim_steps=100)
 t_ddpm = run(sampler="ddpm")
 if rank == 0:
