@@ -9,12 +9,25 @@ reference architecture (413.5 M parameters), inputs synthetic (`data: synthetic`
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
 N > 1 is launched by torchrun (one rank per GPU); objects shard across ranks with no data-path collective
-(SURVEY.md §8e), so scaling is weak: every rank denoises its own 32 objects and `value` counts all of them.
+(SURVEY.md §8e), so the headline scaling is weak: every rank denoises its own 32 objects and `value` counts all of them.
 
 JSON line keys beyond the base contract: `roofline` (tensor-pipe fraction of the implicit-GEMM kernel, timed
 live with CUDA events around every cs_conv3d launch of an instrumented step), `cpu_baseline` (the oracle — a
 CPU restatement of the reference — on this host's cores, bounded sample), `e2e` (same step through the public
-sampler API with HOST buffers in and out), `clocks`, `gpu_launches`.
+sampler API with HOST buffers in and out), `clocks`, `gpu_launches`, and two secondary blocks measured in the same
+process after the headline loop:
+  `train` — BASELINE cfg3/cfg4: the data-parallel denoiser training step (32 objects per rank; re-pack, forward,
+            backward, bucketed NCCL all-reduce of the fp32 gradients overlapped with the backward, clip, AdamW) in ONE
+            CUDA graph — the path that HAS a collective;
+  `cfg5`  — BASELINE cfg5's scene: 10 objects, guided DDIM S=100 + VQ-VAE decode to 64^3, the 20 forwards of each step
+            split across the ranks (CFG-pair split, one all_gather of eps per step).
+
+`--impl reference` (rank 0 only) times the reference's algorithm (the oracle port, pinned to the reference modules at max
+|diff| 0) on the host cores: every timed step is ONE mini-batch of 7 objects with CFG (UNet batch 14) — the mini-batch
+size the reference's own rel2shape uses (sdfusion_txt2shape_model.py:493-497) — and `value` scales it to the 32-object
+step (`extrapolation`).  When a GPU is visible it also runs the same oracle ops eagerly on cuda:0 (`gpu_comparator`:
+ATen/cuDNN kernels, TF32 and bf16 autocast, full batch 64, no extrapolation): what the reference's code reaches on this
+GPU without this repo.
 """
 from __future__ import annotations
 
@@ -32,6 +45,9 @@ sys.path.insert(0, ROOT)
 OBJECTS = 32                      # cfg2: batch-32 sampling
 UNET_GFLOP_PER_SAMPLE = 557.6     # SURVEY.md §8d (2*MAC, probe of the reference's own module)
 METRIC = "denoising-steps/sec (64^3 SDF latent, bs32)"
+WORKLOAD = ("cfg2 guided DDIM step: UNet3DModel (413.5M params, random init) on 32 objects x CFG = batch 64 of 3x16^3 "
+            "latents of 64^3 SDFs + fused CFG/x_prev update; DDIM S=100 eta=0 scale=3")
+TRAFFIC_FILE = os.path.join(ROOT, "profiles", "r2_igemm_dram_step_b64.json")
 
 
 def _peaks():
@@ -41,6 +57,17 @@ def _peaks():
         return float(p["bf16_tflops_sustained"]), float(p["hbm_gbs"]), "measured"
     except Exception:
         return 1400.0, 6650.0, "fallback"
+
+
+def _measured_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the implicit-GEMM launches of one step, from the committed ncu
+    capture of tools/profile_step.py (summarised by tools/ncu_summary.py --dram).  None when the capture is absent."""
+    try:
+        with open(TRAFFIC_FILE) as f:
+            t = json.load(f)
+        return t
+    except Exception:
+        return None
 
 
 class ClockSampler(threading.Thread):
@@ -76,9 +103,14 @@ class ClockSampler(threading.Thread):
 # ------------------------------------------------------------------------------------------------
 # CPU leg: the oracle (port of the reference) on host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_oracle_steps_per_s(repeats: int, warmup: int):
-    """Times the oracle's guided UNet evaluation for ONE object (batch 2 = [uncond; cond]) and scales linearly to the
-    32-object step (the reference's CPU cost is linear in batch: BASELINE.md §4).  Returns (steps/s, cores, sample)."""
+REF_MINI_BATCH = 7               # the reference's rel2shape mini-batch (sdfusion_txt2shape_model.py:493)
+
+
+def cpu_oracle_steps_per_s(repeats: int, warmup: int, objects: int = REF_MINI_BATCH):
+    """Times the oracle's guided DDIM step (p_sample_ddim: UNet on [uncond; cond] + the x_prev update) for ONE mini-batch
+    of `objects` objects and scales linearly to the 32-object step (the reference itself walks a 32-object step in
+    mini-batches; its CPU cost is linear in batch: BASELINE.md §4).  Returns (steps/s, cores, sample text, seconds per
+    timed mini-batch step)."""
     import torch
     from oracle import denoiser as D, weights as Wt
     cores = os.cpu_count() or 1
@@ -88,8 +120,8 @@ def cpu_oracle_steps_per_s(repeats: int, warmup: int):
     sched = D.register_schedule(**D.DIFFUSION)
     dd = D.ddim_schedule(sched, 100)
     g = torch.Generator().manual_seed(111)
-    x = torch.randn(1, 3, 16, 16, 16, generator=g)
-    c, uc = torch.randn(1, 1, 1280, generator=g), torch.randn(1, 1, 1280, generator=g)
+    x = torch.randn(objects, 3, 16, 16, 16, generator=g)
+    c, uc = torch.randn(objects, 1, 1280, generator=g), torch.randn(objects, 1, 1280, generator=g)
     times = []
     with torch.no_grad():
         for i in range(warmup + repeats):
@@ -97,27 +129,73 @@ def cpu_oracle_steps_per_s(repeats: int, warmup: int):
             D.p_sample_ddim(sd, cfg, dd, x, c, int(dd["timesteps"][-1]), 99, 3.0, uc)
             if i >= warmup:
                 times.append(time.perf_counter() - t0)
-    per_object = sum(times) / len(times)
-    sample = (f"oracle p_sample_ddim (fp32 torch CPU) on 1 object with CFG (UNet batch 2), mean of {repeats} after {warmup} warm-up, "
-              f"x{OBJECTS} linear extrapolation to the {OBJECTS}-object step")
-    return 1.0 / (per_object * OBJECTS), cores, sample
+    per_mb = sum(times) / len(times)
+    factor = OBJECTS / objects
+    sample = (f"oracle p_sample_ddim (fp32 torch CPU, {cores} threads) on one mini-batch of {objects} objects with CFG (UNet batch "
+              f"{2 * objects}), mean of {repeats} after {warmup} warm-up; x{factor:.3f} linear extrapolation to the {OBJECTS}-object step")
+    return 1.0 / (per_mb * factor), cores, sample, per_mb
+
+
+def gpu_comparator():
+    """The reference's algorithm as plain PyTorch eager ops (ATen / cuDNN) on cuda:0, full batch 64: fp32 with TF32 (torch's
+    default for convs, what the reference's own code would run) and bf16 autocast.  None without a GPU."""
+    try:
+        import torch
+        if not torch.cuda.is_available():
+            return None
+        from oracle import denoiser as D, weights as Wt
+        cfg = D.UNET_FULL
+        sd = {k: v.cuda() for k, v in Wt.synth_state_dict(D.unet_param_shapes(cfg), 111).items()}
+        g = torch.Generator().manual_seed(0)
+        B = 2 * OBJECTS
+        x = torch.randn(B, 3, 16, 16, 16, generator=g).cuda()
+        t = torch.full((B,), 500).cuda()
+        ctx = torch.randn(B, 1, 1280, generator=g).cuda()
+        torch.backends.cudnn.benchmark = True
+        out = {"what": "oracle.denoiser.unet_forward (= the reference's op sequence) eager on cuda:0, UNet batch 64, "
+                       "mean of 3 after 1 warm-up, CUDA events", "unit": "ms per guided UNet evaluation"}
+        with torch.device("cuda"), torch.no_grad():
+            for name, ac in (("fp32_tf32", False), ("bf16_autocast", True)):
+                torch.backends.cuda.matmul.allow_tf32 = True
+                torch.backends.cudnn.allow_tf32 = True
+                with torch.autocast("cuda", dtype=torch.bfloat16, enabled=ac):
+                    D.unet_forward(sd, cfg, x, t, ctx)
+                    torch.cuda.synchronize()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    for _ in range(3):
+                        D.unet_forward(sd, cfg, x, t, ctx)
+                    e1.record()
+                    torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / 3
+                out[name] = {"ms": ms, "steps_per_s": 1000.0 / ms}
+        return out
+    except Exception as e:          # the CPU number must not depend on the comparator
+        return {"error": f"{type(e).__name__}: {e}"[:300]}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    val, cores, sample = cpu_oracle_steps_per_s(repeats=max(1, args.steps), warmup=max(1, min(args.warmup, 2)))
+    objs = int(os.environ.get("CS_REF_OBJECTS", REF_MINI_BATCH))
+    val, cores, sample, per_mb = cpu_oracle_steps_per_s(repeats=max(1, args.steps), warmup=max(1, args.warmup), objects=objs)
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "steps/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1000.0 / val, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * per_mb, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "cfg2 guided DDIM step (UNet3DModel 413.5M params, 32 objects x CFG = batch 64, 3x16^3 latents of 64^3 SDFs), "
-                               "reference algorithm on host CPU", "objects_per_step": OBJECTS},
+        "config": {"workload": WORKLOAD, "objects_per_gpu": OBJECTS, "global_objects": OBJECTS,
+                   "arm": "reference algorithm (oracle port) on the host CPU"},
+        "extrapolation": {"objects_timed_per_step": objs, "unet_batch_timed": 2 * objs, "factor": OBJECTS / objs,
+                          "ms_per_full_step": 1000.0 / val,
+                          "note": "ms_per_step is the MEASURED time of one timed step (one reference-sized mini-batch); value = "
+                                  "1 / (ms_per_step * factor): steps/s of the 32-object step"},
         "cpu_baseline": {"value": val, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if not args.no_gpu_comparator:
+        line["gpu_comparator"] = gpu_comparator()
     print(json.dumps(line), flush=True)
 
 
@@ -127,10 +205,9 @@ def run_reference(args):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from commonscenes_b200 import _lib, ops
-    from commonscenes_b200.model.networks.diffusion_networks.network import DiffusionUNet
-    from commonscenes_b200.model.networks.diffusion_networks.samplers.ddim import DDIMSampler
-    from commonscenes_b200.model.sdfusion_txt2shape_model import UNET_PARAMS, diffusion_schedule
+    from commonscenes_b200 import _lib, ops, parallel
+    from commonscenes_b200.model.sdfusion_txt2shape_model import SDFusionText2ShapeModel, default_opt
+    from commonscenes_b200.train import DenoiserTrainStep
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -140,22 +217,17 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     _lib.require_device()
     dev = torch.device("cuda", local)
-    torch.manual_seed(111 + rank)
+    torch.manual_seed(111)                              # identical weights on every rank (data-parallel replicas)
 
-    with torch.device(dev):
-        df = DiffusionUNet(dict(UNET_PARAMS), conditioning_key="crossattn")
+    model = SDFusionText2ShapeModel(default_opt(device=f"cuda:{local}"))     # denoiser + frozen VQ-VAE, reference wiring
+    df = model.df
+    with torch.no_grad():
         for p in df.parameters():                       # the reference zero-inits 18 convs: give them weights
             if p.dim() > 1 and float(p.abs().max()) == 0:
                 torch.nn.init.normal_(p, std=0.02)
     df.eval()
-    sched = diffusion_schedule()
-
-    class Host:                                         # what DDIMSampler needs from SDFusionText2ShapeModel
-        num_timesteps = 1000
-        betas = sched["betas"].to(dev)
-        alphas_cumprod = sched["alphas_cumprod"].to(dev)
-    Host.df = df
-    sampler = DDIMSampler(Host(), use_cuda_graph=True)
+    torch.manual_seed(111 + rank)                       # per-rank inputs
+    sampler = model.ddim_sampler
     sampler.make_schedule(100, ddim_eta=0.0, verbose=False)
     unet = df.diffusion_net
     steps_tab = sampler.ddim_timesteps[::-1]
@@ -179,6 +251,13 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def max_over_ranks(*vals):
+        if world == 1:
+            return vals
+        tt = torch.tensor(vals, device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return tuple(float(v) for v in tt)
 
     # ---- device-resident loop (`value`) ----
     img = x
@@ -229,15 +308,68 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel: CUDA events around every implicit-GEMM launch of one eager step ----
     prof = ops.ConvProfiler()
+    ops.conv3d_variant_counts(reset=True)
     with prof:
         unet(x, t_dev, context_vecs=ca, shared_prefix=True)      # the same evaluation the timed steps replay
     torch.cuda.synchronize()
     conv_ms, conv_tflop, n_conv = prof.summary()
+    variants = ops.conv3d_variant_counts(reset=True)
 
-    if world > 1:
-        tt = torch.tensor([ms_total, ms_e2e], device=dev, dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms_total, ms_e2e = float(tt[0]), float(tt[1])
+    # ---- cfg5: one 10-object scene, guided DDIM S=100 + decode, the 2 x 10 forwards of a step split over the ranks ----
+    cfg5 = None
+    if not args.no_cfg5:
+        n5 = 10
+        g5 = torch.Generator(device=dev).manual_seed(5)
+        data5 = {"sdf": torch.zeros(n5, 1, 64, 64, 64, device=dev), "rel": torch.randn(n5, 1, 1280, device=dev, generator=g5),
+                 "uc": torch.randn(n5, 1, 1280, device=dev, generator=g5)}
+        parallel.rel2shape_pair_sharded(model, data5, ddim_steps=5, uc_scale=3.0, seed=7)          # warm-up: graph capture, VQ-VAE packs
+        barrier()
+        e0.record()
+        sdf5 = parallel.rel2shape_pair_sharded(model, data5, ddim_steps=100, uc_scale=3.0, seed=7)
+        e1.record()
+        barrier()
+        (ms5,) = max_over_ranks(e0.elapsed_time(e1))
+        units = [hi - lo for lo, hi in parallel.pair_units(n5, world)]
+        cfg5 = {"workload": "BASELINE cfg5 scene: 10 objects, guided DDIM S=100 (scale 3) + VQ-VAE decode to 64^3", "seconds": ms5 / 1e3,
+                "objects_per_s": n5 / (ms5 / 1e3), "forwards_per_rank_per_step": units,
+                "collective": "one all_gather of eps (48 KiB per forward) per step" if world > 1 else "none (one rank)",
+                "finite": bool(torch.isfinite(sdf5).all()), "shape": list(sdf5.shape)}
+        del sdf5, data5
+
+    # ---- train: the data-parallel denoiser training step (cfg3 / cfg4), one CUDA graph incl. the NCCL all-reduces ----
+    train = None
+    if not args.no_train:
+        per_rank = 32
+        stepper = DenoiserTrainStep(model)
+        z = torch.randn(per_rank, 3, 16, 16, 16, device=dev)
+        ctx = torch.randn(per_rank, 1, 1280, device=dev)
+        stepper.capture(per_rank, 1280)
+        for _ in range(3):
+            stepper.step_graphed(z, ctx)
+        barrier()
+        k_train = 10
+        e0.record()
+        for _ in range(k_train):
+            loss_t, _ = stepper.step_graphed(z, ctx)
+        e1.record()
+        barrier()
+        (ms_train,) = max_over_ranks(e0.elapsed_time(e1) / k_train)
+        chk = stepper.flat_p.double().sum().reshape(1)
+        same = True
+        if world > 1:
+            lo_, hi_ = chk.clone(), chk.clone()
+            dist.all_reduce(lo_, op=dist.ReduceOp.MIN)
+            dist.all_reduce(hi_, op=dist.ReduceOp.MAX)
+            same = bool(torch.equal(lo_, hi_))
+        train = {"workload": "BASELINE cfg3/cfg4 denoiser training step: 32 objects per rank, weight re-pack + forward + backward + "
+                             "bucketed gradient all-reduce + clip 5.0 + AdamW in one CUDA graph",
+                 "ms_per_step": ms_train, "steps_per_s": 1000.0 / ms_train, "objects_per_s": per_rank * world * 1000.0 / ms_train,
+                 "objects_per_rank": per_rank, "allreduce_bytes": int(stepper.flat_g.numel()) * 4 if world > 1 else 0,
+                 "allreduce_dtype": "f32", "bucket_mb": 256, "buckets": len(stepper.buckets),
+                 "algorithmic_tflops": 3 * per_rank * world * UNET_GFLOP_PER_SAMPLE / ms_train,
+                 "replicas_identical": same, "loss": float(loss_t), "peak_mem_gib": torch.cuda.max_memory_allocated() / 2 ** 30}
+
+    ms_total, ms_e2e = max_over_ranks(ms_total, ms_e2e)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -247,34 +379,43 @@ def run_ours(args):
     value = world * args.steps / (ms_total / 1e3)
     e2e_value = world * k_e2e / (ms_e2e / 1e3)
     achieved = conv_tflop / (conv_ms / 1e3)
+    traffic = _measured_traffic()
     line = {
         "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "cfg2 guided DDIM step: UNet3DModel (413.5M params, random init) on 32 objects x CFG = batch 64 of 3x16^3 "
-                               "latents of 64^3 SDFs + fused CFG/x_prev update; DDIM S=100 eta=0 scale=3",
+        "config": {"workload": WORKLOAD,
                    "objects_per_gpu": OBJECTS, "global_objects": OBJECTS * world, "parallelism": f"objects sharded x{world}, no data-path collective",
                    "cache": "per-step working set (0.83 GB bf16 weights + activations) exceeds the 126 MB L2; no explicit flush",
                    "unet_tflop_per_step": 2 * OBJECTS * UNET_GFLOP_PER_SAMPLE / 1e3,
                    "conv_tflop_executed_per_step": conv_tflop,
-                   "shared_prefix": "the layers in front of the first cross-attention see identical inputs in the uncond and cond "
-                                    "halves of a guided step and are evaluated once (same values, same kernels): executed GEMM FLOPs "
-                                    "are below the reference algorithm's 35.69 TFLOP",
+                   "exact_identities": "executed GEMM FLOPs are below the reference algorithm's 35.69 TFLOP: (1) the layers in front of "
+                                       "the first cross-attention see identical inputs in the uncond and cond halves of a guided step "
+                                       "and are evaluated once; (2) nearest-upsample + 3x3x3 conv runs as four 3x2x2 phase convs on the "
+                                       "low-resolution tensor (12 of 27 taps) when that path is enabled",
                    "achieved_tflops_whole_step": 2 * OBJECTS * UNET_GFLOP_PER_SAMPLE / 1e3 / (ms_total / args.steps / 1e3),
-                   "achieved_tflops_whole_step_note": "reference-algorithm FLOPs / time (throughput-equivalent, not executed FLOPs)"},
+                   "achieved_tflops_whole_step_note": "reference-algorithm FLOPs / time (throughput-equivalent, not executed FLOPs)",
+                   "conv_kernel_variants": variants},
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                     "traffic": 448716288, "kernel": "cs::igemm_kernel (tcgen05 implicit GEMM)", "launches_per_step": n_conv,
-                     "traffic_note": "dram__bytes_read+write of ONE representative launch from ncu --set full (profiles/r1e_igemm_shape3.txt: "
-                                     "conv3d 448->448 @16^3 batch 64, 2841 GFLOP); its algorithmic bytes are 481 MB "
-                                     "(235 MB in + 11 MB weights + 235 MB out), i.e. no re-reads from HBM",
+                     "traffic": None if traffic is None else traffic.get("dram_bytes_per_step"),
+                     "kernel": "cs::igemm_kernel / cs::igemm2_kernel (tcgen05 implicit GEMM)", "launches_per_step": n_conv,
+                     "traffic_note": ("no committed ncu capture found" if traffic is None else
+                                      f"dram__bytes_read.sum + dram__bytes_write.sum summed over the {traffic.get('launches')} implicit-GEMM "
+                                      f"launches of ONE guided step (ncu, {os.path.relpath(TRAFFIC_FILE, ROOT)}); algorithmic bytes of the "
+                                      "same launches (inputs + weights + outputs, bf16): "
+                                      f"{traffic.get('algorithmic_bytes_per_step')}"),
                      "ms_per_step_in_kernel": conv_ms, "peak_source": f"bf16_tflops_sustained ({peak_src})",
-                     "note": "achieved = algorithmic 2*MAC FLOPs of every cs_conv3d launch of one step / sum of their CUDA-event durations"},
+                     "note": "achieved = executed 2*MAC FLOPs of every cs_conv3d launch of one step / sum of their CUDA-event durations"},
         "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": k_e2e},
         "gpu_launches": kernels_per_step * args.steps,
         "clocks": clock_rec,
     }
+    if train is not None:
+        line["train"] = train
+    if cfg5 is not None:
+        line["cfg5"] = cfg5
     if world == 1 and not args.no_cpu_baseline:
-        v, cores, sample = cpu_oracle_steps_per_s(repeats=3, warmup=1)
+        v, cores, sample, _ = cpu_oracle_steps_per_s(repeats=3, warmup=1)
         line["cpu_baseline"] = {"value": v, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample}
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -288,6 +429,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-comparator", action="store_true")
+    ap.add_argument("--no-train", action="store_true")
+    ap.add_argument("--no-cfg5", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

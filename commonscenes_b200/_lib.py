@@ -35,6 +35,7 @@ class Conv3dArgs(C.Structure):
         ("out", _vp), ("out_pitch", _i32), ("out_mode", _i32), ("act", _i32),
         ("stat_sum", _vp), ("stat_pitch", _i32),
         ("bn_hint", _i32),
+        ("up_f", _i32 * 3), ("up_o", _i32 * 3),
     ]
 
 
@@ -79,6 +80,7 @@ SIGNATURES = {
     "cs_attention_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32,
                                 _i32, _i32, _f32, _vp]),
     "cs_groupnorm_stats": (_i32, [_vp, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
+    "cs_channel_sums": (_i32, [_vp, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
     "cs_groupnorm_finalize": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _vp, _vp]),
     "cs_groupnorm_apply": (_i32, [_vp, _i32, _i32, _i32, _i32, _vp, _i32, _vp, _i32, _i32, _vp]),
     "cs_groupnorm_apply_fused": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _i32, _f32, _vp, _i32,

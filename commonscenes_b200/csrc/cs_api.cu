@@ -10,6 +10,7 @@ unsigned long long launch_count();
 void reset_launch_count();
 
 int gn_stats_launch(const void*, int, int, int, int, long long*, int, cudaStream_t);
+int channel_sums_f32_launch(const void*, int, int, int, int, float*, int, cudaStream_t);
 int gn_finalize_launch(long long*, const float*, const float*, int, int, int, int, float, float*, cudaStream_t);
 int gn_apply_launch(const void*, int, int, int, int, const float*, int, void*, int, int, cudaStream_t);
 int gn_apply_fused_launch(const void*, int, int, int, int, int, const long long*, int, const long long*, int, const float*,
@@ -109,6 +110,7 @@ int cs_conv3d(const cs_conv3d_args* a, cs_stream_t stream) {
   g.residual = a->residual; g.res_pitch = a->res_pitch;
   g.out = a->out; g.out_pitch = a->out_pitch; g.out_mode = a->out_mode; g.act = a->act;
   g.stat_sum = reinterpret_cast<long long*>(a->stat_sum); g.stat_pitch = a->stat_pitch; g.bn_hint = a->bn_hint;
+  for (int i = 0; i < 3; ++i) { g.up_f[i] = a->up_f[i]; g.up_o[i] = a->up_o[i]; }
   if (g.kd < 1 || g.kh < 1 || g.kw < 1 || g.sd < 1 || g.sh < 1 || g.sw < 1 || g.B < 1)
     return cs::set_error(CS_ERR_INVALID, "cs_conv3d: bad filter/stride/batch");
   return cs::igemm_launch(g, S(stream));
@@ -132,6 +134,11 @@ int cs_conv3d_wgrad(const cs_conv3d_wgrad_args* a, cs_stream_t stream) {
 int cs_groupnorm_stats(const void* x, int32_t B, int32_t Sp, int32_t C, int32_t pitch, int64_t* stat,
                        int32_t stat_pitch, cs_stream_t stream) {
   return cs::gn_stats_launch(x, B, Sp, C, pitch, reinterpret_cast<long long*>(stat), stat_pitch, S(stream));
+}
+int cs_channel_sums(const void* x, int32_t B, int32_t Sp, int32_t C, int32_t pitch, float* out, int32_t out_pitch,
+                    cs_stream_t stream) {
+  if (!x || !out) return cs::set_error(CS_ERR_INVALID, "cs_channel_sums: null pointer");
+  return cs::channel_sums_f32_launch(x, B, Sp, C, pitch, out, out_pitch, S(stream));
 }
 int cs_groupnorm_finalize(int64_t* stat, const float* gamma, const float* beta, int32_t B, int32_t C, int32_t groups,
                           int32_t Sp, float eps, float* scale_shift, cs_stream_t stream) {

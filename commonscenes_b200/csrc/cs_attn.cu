@@ -224,6 +224,8 @@ static int attention_launch_t(const void* q, const void* k, const void* v, void*
 
 int attention_tc_launch(const void* q, const void* k, const void* v, void* out, int B, int H, int N, int q_pitch,
                         int kv_pitch, int o_pitch, int d_out, float scale, cudaStream_t st);
+int attention_tc2_launch(const void* q, const void* k, const void* v, void* out, float* lse, int B, int H, int N, int q_pitch,
+                         int kv_pitch, int o_pitch, int d_out, float scale, cudaStream_t st);
 int igemm_debug_flags();
 
 int attention_lse_launch(const void* q, const void* k, const void* v, void* out, int B, int H, int Nq, int Nk,
@@ -242,6 +244,12 @@ int attention_lse_launch(const void* q, const void* k, const void* v, void* out,
   if (reinterpret_cast<uintptr_t>(q) % 16 || reinterpret_cast<uintptr_t>(k) % 16 ||
       reinterpret_cast<uintptr_t>(v) % 16 || reinterpret_cast<uintptr_t>(out) % 4 || (H * d_out) % 2)
     return set_error(CS_ERR_INVALID, "attention: q/k/v must be 16-byte aligned");
+  // tcgen05 paths: the two-sweep kernel (cs_attn_tc2.cu; also produces the log-sum-exp rows of the training forward) when
+  // the sequence splits into 256-query blocks, else the first-generation kernel (cs_attn_tc.cu).  Debug flag 128 = mma.sync
+  // kernel, 16384 = first-generation tcgen05 kernel (A/B timing).
+  if (Dp == 64 && Nq == Nk && Nq % 256 == 0 && d_out % 8 == 0 && o_pitch % 8 == 0 && (H * d_out) % 8 == 0 &&
+      reinterpret_cast<uintptr_t>(out) % 16 == 0 && !(igemm_debug_flags() & (128 | 16384)))
+    return attention_tc2_launch(q, k, v, out, lse, B, H, Nq, q_pitch, kv_pitch, o_pitch, d_out, scale, st);
   if (!lse && Dp == 64 && Nq == Nk && Nq % 128 == 0 && !(igemm_debug_flags() & 128))   // tcgen05 path (cs_attn_tc.cu)
     return attention_tc_launch(q, k, v, out, B, H, Nq, q_pitch, kv_pitch, o_pitch, d_out, scale, st);
   switch (Dp) {

@@ -40,6 +40,11 @@ struct IgemmArgs {
   void* out; int out_pitch; int out_mode; int act;
   long long* stat_sum; int stat_pitch;
   int bn_hint;  // 0 = choose automatically
+  // Phase launch of "nearest-upsample by (f_d, f_h, f_w), then conv": the conv over the up-sampled tensor restricted to
+  // the output voxels congruent to (o_d, o_h, o_w) modulo the factors is a SMALLER conv over the low-resolution input
+  // (merged taps, ops.pack_upsample_phase_weights); this launch computes that conv and scatters its rows into the
+  // full-resolution output.  up_f all 1 (or 0) = ordinary launch.
+  int up_f[3], up_o[3];
 };
 
 int igemm_launch(const IgemmArgs& a, cudaStream_t stream);

@@ -515,6 +515,15 @@ int igemm_launch(const IgemmArgs& a, cudaStream_t stream) {
   p.out = a.out; p.out_pitch = a.out_pitch; p.out_mode = a.out_mode; p.act = a.act;
   p.stat_sum = a.stat_sum; p.stat_pitch = a.stat_pitch;
   if (p.stat_sum && p.bb > 1 && (p.bd * p.bh * p.bw) % 32) return set_error(CS_ERR_UNSUPPORTED, "igemm: fused stats need a multiple of 32 voxels per sample per tile");
+  p.remap = 0;
+  for (int i = 0; i < 3; ++i) {
+    p.up_f[i] = a.up_f[i] > 0 ? a.up_f[i] : 1;
+    p.up_o[i] = a.up_o[i];
+    if (p.up_f[i] != 1) p.remap = 1;
+    if (p.up_o[i] < 0 || p.up_o[i] >= p.up_f[i]) return set_error(CS_ERR_INVALID, "igemm: phase offset must lie in [0, factor)");
+  }
+  if (p.remap && (!p.fast_epilogue || p.bb != 1))
+    return set_error(CS_ERR_UNSUPPORTED, "igemm: phase launches need the bf16 channels-last epilogue and >= 128 voxels per sample");
   if (p.out_mode == CS_OUT_BF16_NDHWC && (a.out_pitch % 8 || reinterpret_cast<uintptr_t>(a.out) % 16))
     return set_error(CS_ERR_INVALID, "igemm: bf16 output must be 16-byte aligned with pitch % 8 == 0");
   if (p.residual && (a.res_pitch % 8 || reinterpret_cast<uintptr_t>(a.residual) % 16))

@@ -39,6 +39,11 @@ struct IgemmParams {
   int out_pitch;          // elements per output row (NDHWC modes)
   int out_mode;
   int act;
+  // Optional output-row remap ("phase" launch of a nearest-upsample + conv, see IgemmArgs::up_*): output voxel (d, h, w) of
+  // this launch's grid lands at (d * up_f[0] + up_o[0], h * up_f[1] + up_o[1], w * up_f[2] + up_o[2]) of a tensor whose
+  // spatial extent is (Do * up_f[0], Ho * up_f[1], Wo * up_f[2]).  remap == 0: rows are written where they are computed.
+  int remap;
+  int up_f[3], up_o[3];
   // optional fused GroupNorm statistics of the OUTPUT: per (sample, channel) sum and sum of squares
   long long* stat_sum;    // [B][stat_pitch][2] 64-bit fixed point (cs_common.cuh stat_add), atomically accumulated, or null
   int stat_pitch;

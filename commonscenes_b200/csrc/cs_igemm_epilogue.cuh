@@ -34,6 +34,20 @@ __device__ __forceinline__ void epilogue_fast_tile(const IgemmParams& p, uint32_
   // Two warps share each 32-row quarter: `half` selects the even / odd 32-column chunks.
   const int rows_valid = min(32, p.rows - warp_rows0);          // <= 0: nothing to do for this warp
   const long long m_w0 = m_tile0 + warp_rows0;
+  // global output row of the 4 accumulator rows this lane loads the residual for / stores (r = it * 8 + lane / 4)
+  long long orow[4];
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    long long m = m_w0 + it * 8 + (lane >> 2);
+    if (p.remap) {            // phase launch: (b, d, h, w) of this launch's grid -> strided position in the full-resolution output
+      const int w = static_cast<int>(m % p.Wo); m /= p.Wo;
+      const int h = static_cast<int>(m % p.Ho); m /= p.Ho;
+      const int d = static_cast<int>(m % p.Do); m /= p.Do;
+      m = ((m * (p.Do * p.up_f[0]) + d * p.up_f[0] + p.up_o[0]) * (p.Ho * p.up_f[1]) + h * p.up_f[1] + p.up_o[1]) *
+              (p.Wo * p.up_f[2]) + w * p.up_f[2] + p.up_o[2];
+    }
+    orow[it] = m;
+  }
   const bool geglu = (p.act == CS_ACT_GEGLU);
   const int sw = (lane >> 1) & 3;                               // XOR swizzle of this lane's staging row (64-byte rows)
   for (int c0 = half * 32; c0 < p.BN; c0 += chunk_stride) {
@@ -52,7 +66,7 @@ __device__ __forceinline__ void epilogue_fast_tile(const IgemmParams& p, uint32_
         const int r = it * 8 + (lane >> 2), ch = lane & 3;
         rr[it] = make_uint4(0u, 0u, 0u, 0u);
         if (r < rows_valid && ch * 8 < ncols)
-          rr[it] = __ldg(reinterpret_cast<const uint4*>(rbase + (m_w0 + r) * p.res_pitch + n + ch * 8));
+          rr[it] = __ldg(reinterpret_cast<const uint4*>(rbase + orow[it] * p.res_pitch + n + ch * 8));
       }
 #pragma unroll
       for (int it = 0; it < 4; ++it) {
@@ -101,7 +115,7 @@ __device__ __forceinline__ void epilogue_fast_tile(const IgemmParams& p, uint32_
     if (geglu) {
       // packed weight rows interleave 16 value / 16 gate columns: out[j] = v[j] * gelu(v[16 + j])
 #pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = v[j] * gelu_erf_fast(v[16 + j]);
+      for (int j = 0; j < 16; ++j) v[j] = v[j] * gelu_tanh_fit(v[16 + j]);
       out_cols = ncols >> 1;
       out_n = n >> 1;
     }
@@ -139,7 +153,7 @@ __device__ __forceinline__ void epilogue_fast_tile(const IgemmParams& p, uint32_
     for (int it = 0; it < 4; ++it) {
       const int r = it * 8 + (lane >> 2), ch = lane & 3;
       if (r < rows_valid && ch < out_chunks && !(p.debug & 1))
-        *reinterpret_cast<uint4*>(obase + (m_w0 + r) * p.out_pitch + out_n + ch * 8) = oo[it];
+        *reinterpret_cast<uint4*>(obase + orow[it] * p.out_pitch + out_n + ch * 8) = oo[it];
     }
     __syncwarp();
   }

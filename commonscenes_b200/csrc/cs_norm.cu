@@ -58,6 +58,46 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x, int S, int 
   }
 }
 
+// Same reduction with fp32 accumulators (atomicAdd): the per-sample channel sums of GRADIENT tensors (bias gradients of the
+// training path), whose magnitudes span a floating-point range the fixed-point cells do not cover.
+__global__ void channel_sums_f32_kernel(const __nv_bfloat16* __restrict__ x, int S, int C, int pitch, float* __restrict__ out,
+                                        int out_pitch, int vox_per_cta) {
+  extern __shared__ float red[];  // [R][cv][16]
+  const int cv = C >> 3;
+  const int R = blockDim.x / cv;
+  const int r = threadIdx.x / cv;
+  const int v = threadIdx.x - r * cv;
+  const int b = blockIdx.y;
+  const int s_begin = blockIdx.x * vox_per_cta;
+  const int s_end = min(S, s_begin + vox_per_cta);
+  if (r < R) {
+    float s[8], q[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+    const __nv_bfloat16* xb = x + (static_cast<long long>(b) * S) * pitch + v * 8;
+    for (int i = s_begin + r; i < s_end; i += R) {
+      const uint4 u = *reinterpret_cast<const uint4*>(xb + static_cast<long long>(i) * pitch);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16x2(w[j]);
+        s[2 * j] += f.x; q[2 * j] += f.x * f.x;
+        s[2 * j + 1] += f.y; q[2 * j + 1] += f.y * f.y;
+      }
+    }
+    float* dst = red + (r * cv + v) * 16;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { dst[j] = s[j]; dst[8 + j] = q[j]; }
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < cv * 16; t += blockDim.x) {
+    float acc = 0.f;
+    for (int rr = 0; rr < R; ++rr) acc += red[rr * cv * 16 + t];
+    const int vv = t >> 4, comp = t & 15;
+    atomicAdd(out + (static_cast<long long>(b) * out_pitch + vv * 8 + (comp & 7)) * 2 + (comp >> 3), acc);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // finalize: (sum, sumsq) -> per-(sample, channel) affine (scale, shift); clears the accumulators
 // ------------------------------------------------------------------------------------------------
@@ -272,6 +312,25 @@ int gn_stats_launch(const void* x, int B, int S, int C, int pitch, long long* st
                                                            pitch, stat, stat_pitch, vox);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error(e, "groupnorm_stats: launch");
+  count_launch();
+  return CS_OK;
+}
+
+int channel_sums_f32_launch(const void* x, int B, int S, int C, int pitch, float* out, int out_pitch, cudaStream_t st) {
+  if (C % 8 || pitch % 8 || C > 2048 || reinterpret_cast<uintptr_t>(x) % 16)
+    return set_error(CS_ERR_INVALID, "channel_sums: C and pitch must be multiples of 8 (C <= 2048), x 16B aligned");
+  const int cv = C / 8;
+  int R = 256 / cv; if (R < 1) R = 1;
+  const int threads = ((R * cv + 31) / 32) * 32;
+  int splits = (4 * num_sms() + B - 1) / B;
+  int vox = (S + splits - 1) / splits;
+  if (vox < R) vox = R;
+  splits = (S + vox - 1) / vox;
+  const size_t smem = static_cast<size_t>(R) * cv * 16 * sizeof(float);
+  channel_sums_f32_kernel<<<dim3(splits, B), threads, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), S, C, pitch, out,
+                                                                   out_pitch, vox);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(e, "channel_sums: launch");
   count_launch();
   return CS_OK;
 }

@@ -18,6 +18,7 @@ attention kernel).
 from __future__ import annotations
 
 import math
+import os
 from typing import Optional
 
 import torch
@@ -58,7 +59,7 @@ class GEGLU(nn.Module):
 
 
 class FeedForward(nn.Module):
-    FUSE_GEGLU = False
+    FUSE_GEGLU = os.environ.get("CS_FUSE_GEGLU", "1") != "0"
 
     def __init__(self, dim, dim_out=None, mult=4, glu=False, dropout=0.):
         super().__init__()
@@ -69,20 +70,21 @@ class FeedForward(nn.Module):
         self.net = nn.Sequential(GEGLU(dim, inner_dim), nn.Dropout(dropout), nn.Linear(inner_dim, dim_out))
 
     def pack(self):
-        # FUSE_GEGLU: x * gelu(gate) inside the GEMM epilogue (ACT_GEGLU).  Measured on B200 at batch 64 the K=448/672
-        # projection is epilogue-bound, and 112 erf evaluations per accumulator row on 8 epilogue warps cost more
-        # (454 us) than the plain GEMM (264 us) plus the bandwidth-bound cs_geglu pass (110 us): off by default.
-        if FeedForward.FUSE_GEGLU:
-            w1, b1 = ops.pack_geglu_weight(self.net[0].proj.weight, self.net[0].proj.bias)
-        else:
-            w1, b1 = ops.pack_linear_weight(self.net[0].proj.weight), self.net[0].proj.bias.detach().float().contiguous()
-        return {"w1": w1, "b1": b1, "fused": FeedForward.FUSE_GEGLU,
+        # "w1" / "b1": the plain projection (the training path keeps the pre-activation for the backward: unet_train.py).
+        # "w1f" / "b1f": rows interleaved 16 value / 16 gate columns for the ACT_GEGLU epilogue, packed on first inference use.
+        return {"w1": ops.pack_linear_weight(self.net[0].proj.weight), "b1": self.net[0].proj.bias.detach().float().contiguous(),
+                "w1f": None, "b1f": None, "fused": False,
                 "w2": ops.pack_linear_weight(self.net[2].weight), "b2": self.net[2].bias.detach().float().contiguous()}
 
-    @staticmethod
-    def run(pk, x_ln, residual):
-        if pk["fused"]:
-            h = ops.linear_tokens(x_ln, pk["w1"], bias=pk["b1"], act=ops.ACT_GEGLU)
+    def run(self, pk, x_ln, residual):
+        # FUSE_GEGLU: x * gelu(gate) inside the projection's epilogue (ACT_GEGLU): the (tokens, 8 C) pre-activation -- 470 MB
+        # per launch at batch 64 -- is never written or re-read.  Round 1 measured this SLOWER (454 us vs 264 + 110 us) because
+        # the erf evaluation (exp + reciprocal) made the epilogue issue-bound; with gelu_tanh_fit (cs_common.cuh: one
+        # MUFU.TANH + 9 FP instructions, 2.9e-5 from the erf form) the epilogue fits under the K = 448 / 672 main loop.
+        if FeedForward.FUSE_GEGLU:
+            if pk["w1f"] is None:
+                pk["w1f"], pk["b1f"] = ops.pack_geglu_weight(self.net[0].proj.weight, self.net[0].proj.bias)
+            h = ops.linear_tokens(x_ln, pk["w1f"], bias=pk["b1f"], act=ops.ACT_GEGLU)
         else:
             h = ops.geglu(ops.linear_tokens(x_ln, pk["w1"], bias=pk["b1"]))
         return ops.linear_tokens(h, pk["w2"], bias=pk["b2"], residual=residual)
@@ -179,11 +181,11 @@ class BasicTransformerBlock(nn.Module):
                 pk["attn2"] = self.attn2.pack_cross()          # packed on first use: the v2_full path never needs it
             x = self.attn1.run_self(pk["attn1"], ops.layernorm(x, *pk["ln1"], eps=self.norm1.eps), residual=x)
             x = self.attn2.run_cross(pk["attn2"], ops.layernorm(x, *pk["ln2"], eps=self.norm2.eps), context, residual=x)
-            return FeedForward.run(pk["ff"], ops.layernorm(x, *pk["ln3"], eps=self.norm3.eps), residual=x)
+            return self.ff.run(pk["ff"], ops.layernorm(x, *pk["ln3"], eps=self.norm3.eps), residual=x)
         # x = attn1(norm1(x)) + x ; x = attn2(norm2(x), ctx) + x   [attn2 == ctx_vec, independent of x]
         x = self.attn1.run_self(pk["attn1"], ops.layernorm(x, *pk["ln1"], eps=self.norm1.eps), residual=x, rowvec=ctx_vec)
         # x = ff(norm3(x)) + x
-        return FeedForward.run(pk["ff"], ops.layernorm(x, *pk["ln3"], eps=self.norm3.eps), residual=x)
+        return self.ff.run(pk["ff"], ops.layernorm(x, *pk["ln3"], eps=self.norm3.eps), residual=x)
 
 
 def init_weights(m):

@@ -96,12 +96,33 @@ class Upsample(nn.Module):
         if use_conv:
             self.conv = conv_nd(dims, self.channels, self.out_channels, 3, padding=padding)
 
+    PHASE_CONV = True      # inference: fold the nearest-upsample into the conv (four / eight merged-tap phase convs)
+
     def pack(self):
-        return {"w": ops.pack_conv_weight(self.conv.weight), "b": _f(self.conv.bias)} if self.use_conv else {}
+        return {"w": ops.pack_conv_weight(self.conv.weight), "b": _f(self.conv.bias), "phases": None} if self.use_conv else {}
 
     def run(self, pk, x, arena):
         # dims == 3 keeps D and doubles H, W (the inherited "video" convention, :150-153); dims == 4 is isotropic
-        u = ops.upsample_nearest(x.t, (1, 2, 2) if self.dims == 3 else (2, 2, 2))
+        factors = (1, 2, 2) if self.dims == 3 else (2, 2, 2)
+        B, D, H, W, _ = x.t.shape
+        if self.use_conv and Upsample.PHASE_CONV and D * H * W >= 128:
+            # F.interpolate(nearest) + conv3x3x3 (:150-158) as one merged-tap conv per output phase on the LOW-resolution
+            # tensor (ops.pack_upsample_phase_weights): no up-sampled intermediate, 12 of 27 taps (8 when isotropic)
+            if pk["phases"] is None:
+                pk["phases"] = ops.pack_upsample_phase_weights(self.conv.weight, factors)
+            out = torch.empty((B, D * factors[0], H * factors[1], W * factors[2], self.out_channels), dtype=torch.bfloat16,
+                              device=x.t.device)
+
+            def make(st):
+                for offs, ks, pad, pad_back, w in pk["phases"]:
+                    ops.conv3d(x.t, w, ksize=ks, pad=pad, pad_back=pad_back, bias=pk["b"], stat_sum=st, out=out, phase=(factors, offs))
+                return out
+            if (D * H * W) % 32 == 0:
+                stat = arena.take(B, self.out_channels)
+                return Act(make(stat), stat)
+            stat = arena.take(B, self.out_channels)
+            return Act(make(None), ops.groupnorm_stats(out, stat))
+        u = ops.upsample_nearest(x.t, factors)
         B, D, H, W, _ = u.shape
         if not self.use_conv:
             stat = arena.take(B, self.channels)

@@ -29,7 +29,8 @@ class DDIMSampler(object):
         self.ddpm_num_timesteps = model.num_timesteps
         self.schedule = schedule
         self.use_cuda_graph = use_cuda_graph
-        self._graphs = {}
+        self.max_graphs = int(kwargs.get("max_graphs", 4))
+        self._graphs = {}                               # (x shape, batch, weight generation) -> captured evaluation, LRU order
 
     def make_schedule(self, ddim_num_steps, ddim_discretize="uniform", ddim_eta=0., verbose=True):
         self.ddim_timesteps = make_ddim_timesteps(ddim_discr_method=ddim_discretize, num_ddim_timesteps=ddim_num_steps,
@@ -85,8 +86,16 @@ class DDIMSampler(object):
             with torch.cuda.graph(graph):
                 out = call(sx, st, sc)
             g = {"graph": graph, "x": sx, "t": st, "c": sc, "out": out, "launches": ops.launch_count() - n0}
-            self._graphs.clear()                        # one resident graph (a new shape replaces the old one)
+            # a few resident graphs, least recently used first out: the ragged last mini-batch of a scene, or a trainer
+            # alternating validation batch sizes, must not re-capture (two warm-up evaluations + capture) on every call;
+            # graphs of an older weight packing can never be hit again and go first
+            for k in [k for k in self._graphs if k[2] != unet._pack_generation]:
+                del self._graphs[k]
+            while len(self._graphs) >= self.max_graphs:
+                del self._graphs[next(iter(self._graphs))]
             self._graphs[key] = g
+        else:
+            self._graphs[key] = self._graphs.pop(key)   # mark as most recently used
         g["x"].copy_(x); g["t"].copy_(t_dev)
         if ca_vecs is not None:
             g["c"].copy_(ca_vecs)

@@ -172,10 +172,10 @@ class UNetTrainer:
     def _colsums(self, dy):
         """fp32 (B, C, 2) per-sample channel sums of a bf16 channels-last tensor (component 0 = sum)."""
         B, C = dy.shape[0], dy.shape[-1]
-        return ops.groupnorm_stats(dy, ops_bwd.zero_f32((B, C, 2), dy.device))
+        return ops_bwd.channel_sums(dy, ops_bwd.zero_f32((B, C, 2), dy.device))
 
     def _bias_grad(self, sink, param, dy, sums=None):
-        if sums is None and dy.shape[-1] > 2048:       # cs_groupnorm_stats handles <= 2048 channels per call
+        if sums is None and dy.shape[-1] > 2048:       # cs_channel_sums handles <= 2048 channels per call
             g = sink.grad(param)
             for c0 in range(0, dy.shape[-1], 2048):
                 c1 = min(dy.shape[-1], c0 + 2048)

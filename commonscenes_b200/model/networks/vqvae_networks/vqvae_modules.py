@@ -66,13 +66,30 @@ class Upsample(_Packed):
         if self.with_conv:
             self.conv = torch.nn.Conv3d(in_channels, in_channels, kernel_size=3, stride=1, padding=1)
 
+    PHASE_CONV = True      # fold the nearest-upsample into the conv: eight 2x2x2 merged-tap phase convs (8 of 27 taps)
+
     def pack(self):
-        return (ops.pack_conv_weight(self.conv.weight), _f(self.conv.bias)) if self.with_conv else None
+        if not self.with_conv:
+            return None
+        if Upsample.PHASE_CONV:
+            return ops.pack_upsample_phase_weights(self.conv.weight, (2, 2, 2)), _f(self.conv.bias)
+        return ops.pack_conv_weight(self.conv.weight), _f(self.conv.bias)
 
     def run(self, x):
+        if self.with_conv and Upsample.PHASE_CONV and x.shape[1] * x.shape[2] * x.shape[3] >= 128:
+            # F.interpolate(scale 2, nearest) + conv3x3x3 (vqvae_modules.py:33-40) == one 2x2x2 conv per output parity class on
+            # the low-resolution tensor (ops.pack_upsample_phase_weights): the 8x larger intermediate is never written
+            phases, b = self._pk()
+            B, D, H, W, C = x.shape
+            out = torch.empty((B, 2 * D, 2 * H, 2 * W, self.conv.out_channels), dtype=torch.bfloat16, device=x.device)
+            for offs, ks, pad, pad_back, w in phases:
+                ops.conv3d(x, w, ksize=ks, pad=pad, pad_back=pad_back, bias=b, out=out, phase=((2, 2, 2), offs))
+            return out
         x = ops.upsample_nearest(x, (2, 2, 2))
         if self.with_conv:
             w, b = self._pk()
+            if Upsample.PHASE_CONV:        # tiny grids (tests): the plain path needs the un-merged filter
+                w = ops.pack_conv_weight(self.conv.weight)
             x = ops.conv3d(x, w, bias=b)
         return x
 

@@ -22,7 +22,7 @@ from ._lib import (ACT_GEGLU, ACT_GELU, ACT_NONE, ACT_SILU, OUT_BF16_NDHWC, OUT_
                    Conv3dArgs, check)
 
 __all__ = [
-    "ACT_NONE", "ACT_SILU", "ACT_GELU", "ACT_GEGLU", "pack_geglu_weight", "pack_patch_weight", "conv3d", "linear_tokens", "groupnorm", "layernorm", "attention",
+    "ACT_NONE", "ACT_SILU", "ACT_GELU", "ACT_GEGLU", "pack_geglu_weight", "pack_patch_weight", "pack_upsample_phase_weights", "conv3d", "linear_tokens", "groupnorm", "layernorm", "attention",
     "geglu", "upsample_nearest", "im2col_small", "timestep_embedding", "linear_small", "ddim_step",
     "q_sample", "to_channels_last", "to_ncdhw", "pack_conv_weight", "pack_linear_weight", "launch_count",
     "reset_launch_count", "zero_stat_buffer", "groupnorm_stats", "groupnorm_fused", "ConvProfiler", "vq_quantize", "channel_mix", "pack_small_cout_conv", "conv3d_small_cout", "gcn_gather_triples", "gcn_scatter_mean",
@@ -142,6 +142,38 @@ def pack_conv_weight(w: torch.Tensor, split=None, owner=None) -> torch.Tensor:
     return _pad_k(wd.reshape(co, ci, -1).permute(0, 2, 1), split)
 
 
+_PHASE_TAPS = {0: ((1., 0., 0.), (0., 1., 1.)), 1: ((1., 1., 0.), (0., 0., 1.))}     # offset -> (2 merged taps) x (3 taps)
+
+
+def pack_upsample_phase_weights(w: torch.Tensor, factors: Sequence[int]):
+    """nearest-upsample by `factors` (each 1 or 2) followed by a 3x3x3 / pad 1 conv == one conv per output phase over the
+    LOW-resolution tensor: along an axis with factor 2, output index 2i reads up-sampled rows 2i-1, 2i, 2i+1 = low-res rows
+    i-1, i, i, and 2i+1 reads 2i, 2i+1, 2i+2 = rows i, i, i+1, so the three taps merge into two:
+        offset 0: (w0, w1 + w2) with one zero row in front;   offset 1: (w0 + w1, w2) with one zero row behind.
+    (Upsample, openai_model_3d.py:150-158; vqvae_modules.py:42-47.)  Taps are summed in fp32 and rounded to bf16 once.
+    Returns [(offsets, ksize, pad, pad_back, packed weight)], one entry per phase."""
+    if w.dim() != 5 or tuple(w.shape[2:]) != (3, 3, 3) or any(f not in (1, 2) for f in factors):
+        raise _lib.CsError("pack_upsample_phase_weights: a (Cout, Cin, 3, 3, 3) filter and factors in {1, 2}")
+    wf = w.detach().float()
+    out = []
+    for od in range(factors[0]):
+        for oh in range(factors[1]):
+            for ow in range(factors[2]):
+                offs = (od, oh, ow)
+                m = wf
+                ksize, pad, pad_back = [], [], []
+                for axis, (f, o) in enumerate(zip(factors, offs)):
+                    if f == 1:
+                        ksize.append(3); pad.append(1); pad_back.append(1)
+                        continue
+                    t = torch.tensor(_PHASE_TAPS[o], dtype=torch.float32, device=wf.device)          # (2, 3)
+                    m = torch.tensordot(m, t, dims=([2 + axis], [1]))                                 # merged axis goes last
+                    m = m.movedim(-1, 2 + axis)
+                    ksize.append(2); pad.append(1 - o); pad_back.append(o)
+                out.append((offs, tuple(ksize), tuple(pad), tuple(pad_back), pack_conv_weight(m.contiguous())))
+    return out
+
+
 def pack_geglu_weight(w: torch.Tensor, b: torch.Tensor):
     """GEGLU projection (2*inner, in): reorder rows so every 32-column group of the GEMM output holds 16 value
     columns followed by their 16 gate columns (what the ACT_GEGLU epilogue expects).  Returns (packed w, fp32 bias)."""
@@ -181,6 +213,7 @@ class ConvProfiler:
 
     def __init__(self):
         self.records = []   # (start_event, end_event, flops, tag)
+        self.bytes = 0      # algorithmic bytes of the recorded launches: activations in + weights + residual + output
 
     def __enter__(self):
         ConvProfiler.active = self
@@ -203,10 +236,14 @@ def conv3d(x: torch.Tensor, weight: torch.Tensor, *, ksize: Sequence[int] = (3, 
            pad_back: Optional[Sequence[int]] = None, bias: Optional[torch.Tensor] = None,
            rowvec: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
            x2: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, out_mode: int = OUT_BF16_NDHWC,
-           act: int = ACT_NONE, stat_sum: Optional[torch.Tensor] = None, bn_hint: int = 0) -> torch.Tensor:
+           act: int = ACT_NONE, stat_sum: Optional[torch.Tensor] = None, bn_hint: int = 0,
+           phase: Optional[Tuple[Sequence[int], Sequence[int]]] = None) -> torch.Tensor:
     """act(conv3d(cat(x, x2)) + bias + rowvec[b] + residual) on the tcgen05 implicit-GEMM kernel.
 
     `weight` is the packed (Cout, taps, Cin) bf16 tensor of `pack_conv_weight`.
+    `phase` = ((f_d, f_h, f_w), (o_d, o_h, o_w)): phase launch of a nearest-upsample + conv (pack_upsample_phase_weights):
+    the rows of this (low-resolution) conv are scattered to the voxels of `out` (required, full resolution) congruent to
+    the offsets modulo the factors.
     """
     lib = _lib.load()
     B, D, H, W, C1, p1 = _check_act(x, "conv3d.x")
@@ -226,6 +263,9 @@ def conv3d(x: torch.Tensor, weight: torch.Tensor, *, ksize: Sequence[int] = (3, 
     Do = (D + pad[0] + pb[0] - kd) // stride[0] + 1
     Ho = (H + pad[1] + pb[1] - kh) // stride[1] + 1
     Wo = (W + pad[2] + pb[2] - kw) // stride[2] + 1
+    fd, fh, fw = (1, 1, 1) if phase is None else tuple(int(f) for f in phase[0])
+    if phase is not None and (out is None or out_mode != OUT_BF16_NDHWC or residual is not None):
+        raise _lib.CsError("conv3d: a phase launch writes into a caller-provided bf16 channels-last `out` and takes no residual")
     if out is None:
         if out_mode == OUT_BF16_NDHWC:
             out = torch.empty((B, Do, Ho, Wo, Cres), dtype=torch.bfloat16, device=x.device)
@@ -239,8 +279,10 @@ def conv3d(x: torch.Tensor, weight: torch.Tensor, *, ksize: Sequence[int] = (3, 
         out_pitch = 0
     else:
         want = torch.bfloat16 if out_mode == OUT_BF16_NDHWC else torch.float32
-        if out.dtype != want or tuple(out.shape) != (B, Do, Ho, Wo, Cres) or out.stride(-1) != 1:
+        if out.dtype != want or tuple(out.shape) != (B, Do * fd, Ho * fh, Wo * fw, Cres) or out.stride(-1) != 1:
             raise _lib.CsError(f"conv3d: output must be {want} (B, Do, Ho, Wo, Cout)")
+        if phase is not None:
+            _check_act(out, "conv3d.out")
         out_pitch = out.stride(3)
     a = Conv3dArgs()
     a.in1, a.C1, a.in1_pitch = x.data_ptr(), C1, p1
@@ -266,6 +308,9 @@ def conv3d(x: torch.Tensor, weight: torch.Tensor, *, ksize: Sequence[int] = (3, 
     if stat_sum is not None:
         a.stat_sum, a.stat_pitch = _check_stat(stat_sum, "conv3d.stat_sum").data_ptr(), stat_sum.shape[1]
     a.bn_hint = bn_hint
+    if phase is not None:
+        a.up_f[:] = [fd, fh, fw]
+        a.up_o[:] = [int(o) for o in phase[1]]
     prof = ConvProfiler.active
     if prof is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -274,6 +319,8 @@ def conv3d(x: torch.Tensor, weight: torch.Tensor, *, ksize: Sequence[int] = (3, 
     if prof is not None:
         e1.record()
         flops = 2.0 * B * Do * Ho * Wo * Cout * (C1 + C2) * kd * kh * kw
+        prof.bytes += 2 * B * D * H * W * (C1 + C2) + 2 * weight.numel() + out.numel() * out.element_size() \
+            + (0 if residual is None else 2 * residual.numel())
         prof.records.append((e0, e1, flops, f"{C1 + C2}->{Cout} k{kd}{kh}{kw} s{stride[0]}{stride[1]}{stride[2]} @{Do}x{Ho}x{Wo} B{B}"))
     return out
 

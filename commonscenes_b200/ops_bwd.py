@@ -190,6 +190,15 @@ def groupnorm_bwd(x: torch.Tensor, stat: torch.Tensor, gamma: torch.Tensor, beta
     return outs[0], (outs[1] if len(outs) > 1 else None)
 
 
+def channel_sums(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """out (B, C, 2) fp32 += per-sample (sum, sum of squares) over the voxels of a bf16 channels-last tensor (bias gradients)."""
+    B, D, H, W, Cc, p = _check_act(x, "channel_sums.x")
+    if out.dtype != torch.float32 or not out.is_contiguous() or tuple(out.shape) != (B, Cc, 2):
+        raise _lib.CsError("channel_sums: out must be contiguous fp32 (B, C, 2)")
+    check(_lib.load().cs_channel_sums(x.data_ptr(), B, D * H * W, Cc, p, out.data_ptr(), Cc, _stream()), "cs_channel_sums")
+    return out
+
+
 def batch_reduce(stat: torch.Tensor, comp: int, out: torch.Tensor) -> torch.Tensor:
     """out (C,) += sum_b stat[b, :, comp]   (stat fp32 (B, C, ncomp) contiguous)."""
     B, Cc, n = stat.shape

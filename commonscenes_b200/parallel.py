@@ -67,3 +67,90 @@ def rel2shape_sharded(diff_model, data: dict, ddim_steps: int = 100, ddim_eta: f
         r = diff_model.z_shape[-1] * 4
         out = torch.zeros((0, 1, r, r, r), dtype=torch.float32, device=data["rel"].device)
     return gather_objects(out, n, group)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# CFG-pair split (SURVEY.md §8e "Sampling partition", cfg5): a scene has fewer objects than a box has GPUs (10 objects
+# on 8 ranks leave a 2:1 imbalance), but the unconditional and the conditional evaluation of one object are independent
+# too.  The 2·O UNet forwards of a guided step -- ordered [uncond_0..uncond_{O-1}; cond_0..cond_{O-1}] like the
+# reference's batch (samplers/ddim.py:206-209) -- are block-partitioned over the ranks (20 forwards -> 3,3,3,3,2,2,2,2).
+# This path HAS an exchange step: the guidance e = e_uc + s (e_c - e_uc) needs both halves of an object, so every step
+# ends with one all_gather of the eps rows (48 KiB fp32 each); after it every rank applies the (tiny, fused) update to all
+# O latents, so x never travels.  The VQ-VAE decode at the end is object-sharded and gathered as in rel2shape_sharded.
+# ----------------------------------------------------------------------------------------------------------------------
+def pair_units(num_objects: int, world_size: int) -> List[Tuple[int, int]]:
+    """[lo, hi) ranges over the 2 * num_objects forwards of a guided step, one per rank."""
+    return partition(2 * num_objects, world_size)
+
+
+def exchange_eps(local_eps: torch.Tensor, num_objects: int, group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
+    """all_gather of each rank's eps rows back into the (2 * O, ...) [uncond; cond] batch (ragged blocks are padded)."""
+    return gather_objects(local_eps, 2 * num_objects, group)
+
+
+@torch.no_grad()
+def rel2shape_pair_sharded(diff_model, data: dict, ddim_steps: int = 100, ddim_eta: float = 0.0, uc_scale: float = 3.0,
+                           seed: Optional[int] = None, group: Optional[dist.ProcessGroup] = None, sampler: str = "ddim",
+                           ddpm_timesteps: Optional[int] = None, return_latent: bool = False):
+    """SDFusionText2ShapeModel.rel2shape with the 2 * O forwards of every guided step split across the ranks of `group`
+    (see above).  Same arguments and result as rel2shape_sharded; all ranks must pass the same `data` (and `seed`)."""
+    from . import ops
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return diff_model.rel2shape(data, ddim_steps=ddim_steps, ddim_eta=ddim_eta, uc_scale=uc_scale, seed=seed,
+                                    sampler=sampler, ddpm_timesteps=ddpm_timesteps, return_latent=return_latent)
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    m = diff_model
+    m.switch_eval()
+    m.set_input(data)
+    dev = m.rel.device
+    n = m.rel.shape[0]
+    if seed is None:
+        import time
+        box = torch.tensor([int(time.time())], dtype=torch.int64, device=dev)
+        dist.broadcast(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        seed = int(box.item())
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(int(seed))                           # same stream on every rank: x_T and the per-step noise agree
+    x = torch.randn((1, *m.z_shape), device=dev, generator=gen).repeat(n, 1, 1, 1, 1)       # one shared x_T (reference :487-491)
+    if sampler == "ddpm":
+        if getattr(m, "ddpm_sampler", None) is None:
+            from .model.networks.diffusion_networks.samplers.ddpm import DDPMSampler
+            m.ddpm_sampler = DDPMSampler(m)
+        s = m.ddpm_sampler
+        s.make_schedule(ddpm_timesteps)
+        order = [(int(t), int(t)) for t in s.ddim_timesteps[::-1]]                        # (timestep, table index)
+    elif sampler == "ddim":
+        s = m.ddim_sampler
+        s.make_schedule(ddim_num_steps=ddim_steps, ddim_eta=ddim_eta, verbose=False)
+        total = s.ddim_timesteps.shape[0]
+        order = [(int(t), total - i - 1) for i, t in enumerate(s.ddim_timesteps[::-1])]
+    else:
+        raise ValueError(f"unknown sampler '{sampler}' (ddim | ddpm)")
+    lo, hi = pair_units(n, world)[rank]
+    units = torch.arange(lo, hi, device=dev)
+    ca_all, concat = s._conditioning(m.rel, m.uc_rel, True)                                 # rows [uncond; cond]
+    if concat is not None:
+        raise NotImplementedError("the CFG-pair split is built for the cross-attention conditioning of v2_full")
+    ca = ca_all[lo:hi].contiguous()
+    obj_of_unit = units % n
+    t_dev = torch.empty(hi - lo, dtype=torch.int64, device=dev)
+    for step, index in order:
+        if hi > lo:
+            t_dev.fill_(step)
+            eps_local = s._eps(x.index_select(0, obj_of_unit), t_dev, ca)
+        else:
+            eps_local = x.new_zeros((0,) + tuple(x.shape[1:]))
+        eps = exchange_eps(eps_local.float(), n, group)                                      # the path's collective
+        sigma = float(s.ddim_sigmas[index])
+        noise = torch.randn(x.shape, device=dev, generator=gen) if sigma > 0 else None
+        x, _ = ops.ddim_step(x, eps.contiguous(), guided=True, scale=float(uc_scale), a_t=float(s.ddim_alphas[index]),
+                             a_prev=float(s.ddim_alphas_prev[index]), sigma=sigma,
+                             sqrt_one_minus_at=float(s.ddim_sqrt_one_minus_alphas[index]), noise=noise, want_pred_x0=False)
+    olo, ohi = partition(n, world)[rank]
+    if ohi > olo:
+        dec = m.vqvae_module.decode_no_quant(x[olo:ohi].contiguous())
+    else:
+        r = m.z_shape[-1] * 4
+        dec = torch.zeros((0, 1, r, r, r), dtype=torch.float32, device=dev)
+    out = gather_objects(dec, n, group)
+    return (out, x) if return_latent else out

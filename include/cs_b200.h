@@ -72,6 +72,14 @@ typedef struct cs_conv3d_args {
   void* out; int32_t out_pitch; int32_t out_mode; int32_t act;
   int64_t* stat_sum; int32_t stat_pitch;             /* optional fused GroupNorm sums [B][pitch][2], fixed point (below) */
   int32_t bn_hint;                                   /* N tile override, 0 = auto */
+  /* Phase launch of "nearest-upsample by up_f = (f_d, f_h, f_w), then conv" (Upsample, openai_model_3d.py:130-158;
+   * vqvae_modules.py:33-47): restricted to the output voxels congruent to up_o modulo up_f, that conv equals a conv with
+   * MERGED taps over the low-resolution input (a 3-tap axis with factor 2 becomes 2 taps: 12 of 27 taps for (1,2,2), 8 for
+   * (2,2,2)), so the up-sampled tensor is never built and 56-70 % of the MACs disappear.  This launch runs that smaller
+   * conv (in1 = low-resolution tensor, weight = the phase's merged filter, pads = the phase's) and writes output voxel
+   * (d, h, w) to (d f_d + o_d, h f_h + o_h, w f_w + o_w) of `out`, whose extent is (Do f_d, Ho f_h, Wo f_w).  All factors
+   * 0 or 1 = ordinary launch.  bf16 channels-last output only. */
+  int32_t up_f[3], up_o[3];
 } cs_conv3d_args;
 int cs_conv3d(const cs_conv3d_args* args, cs_stream_t stream);
 
@@ -168,6 +176,10 @@ int cs_attention_bwd(const void* q, const void* k, const void* v, const void* o,
 /* stat[b][c][0..1] += sum / sum of squares over the S voxels of sample b */
 int cs_groupnorm_stats(const void* x, int32_t B, int32_t S, int32_t C, int32_t pitch, int64_t* stat,
                        int32_t stat_pitch, cs_stream_t stream);
+/* out[b][c][0..1] += (sum, sum of squares) over the S voxels of sample b, fp32 accumulators: channel sums of gradient tensors
+ * (bias gradients of nn.Conv3d / nn.Linear in the training path) */
+int cs_channel_sums(const void* x, int32_t B, int32_t S, int32_t C, int32_t pitch, float* out, int32_t out_pitch,
+                    cs_stream_t stream);
 /* (sum,sumsq) -> scale_shift[b][c] = (gamma*rstd, beta - mean*rstd*gamma); zeroes `stat` */
 int cs_groupnorm_finalize(int64_t* stat, const float* gamma, const float* beta, int32_t B, int32_t C,
                           int32_t groups, int32_t S, float eps, float* scale_shift, cs_stream_t stream);

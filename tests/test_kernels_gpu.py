@@ -111,6 +111,39 @@ def test_conv3d_benchmark_batch_matches_torch(ops, case):
         assert ran == [want], f"{name}: expected the '{want}' variant at batch 64, got {ran}"
 
 
+@pytest.mark.parametrize("case", [("unet_448_1x2x2", 4, 448, 448, (16, 8, 8), (1, 2, 2)), ("unet_672_1x2x2", 4, 672, 672, (16, 4, 4), (1, 2, 2)),
+                                  ("vq_256_2x2x2", 1, 256, 256, (16, 16, 16), (2, 2, 2)), ("b64_448_1x2x2", 64, 448, 448, (16, 8, 8), (1, 2, 2))],
+                         ids=lambda c: c[0])
+def test_upsample_conv_as_phase_convs_matches_torch(ops, case):
+    """nearest-upsample + 3x3x3 conv (Upsample: openai_model_3d.py:150-158, vqvae_modules.py:33-40) evaluated as merged-tap
+    phase convs on the low-resolution tensor vs F.interpolate + F.conv3d in fp32; fused GroupNorm sums included."""
+    name, B, Cin, Cout, (D, H, W), f = case
+    g = torch.Generator(device="cuda").manual_seed(99)
+    x = torch.randn(B, Cin, D, H, W, device="cuda", generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, 3, device="cuda", generator=g) / math.sqrt(Cin * 27)
+    b = torch.randn(Cout, device="cuda", generator=g)
+    ref = F.conv3d(F.interpolate(_bf(x).float(), scale_factor=tuple(float(v) for v in f), mode="nearest"), _bf(w).float(), b, padding=1)
+    out = torch.full((B, D * f[0], H * f[1], W * f[2], Cout), float("nan"), dtype=torch.bfloat16, device="cuda")
+    stat = torch.zeros(B, Cout, 2, dtype=ops.STAT_DTYPE, device="cuda")
+    phases = ops.pack_upsample_phase_weights(w, f)
+    assert len(phases) == f[0] * f[1] * f[2]
+    xc = _cl(x)
+    for offs, ks, pad, pad_back, wp in phases:
+        ops.conv3d(xc, wp, ksize=ks, pad=pad, pad_back=pad_back, bias=b, stat_sum=stat, out=out, phase=(f, offs))
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all(), "every output voxel must be written by exactly one phase"
+    # the merged taps are rounded to bf16 AFTER summation while the fp32 comparison rounds every tap separately: the two filter
+    # roundings differ by up to 2^-8 per weight, so the element-wise bound carries an absolute term that scales with
+    # sqrt(K) * |w| * |x| (measured max 2.2e-2 at |y| ~ 7); the relative L2 error is the sharp criterion (measured 2.2e-3)
+    _report(name, _ncdhw(out), ref, rtol=2 ** -6, atol=3e-2)
+    rel = float((_ncdhw(out) - ref).norm() / ref.norm())
+    print(f"{name}: rel-L2 {rel:.3e}")
+    assert rel < 4e-3, f"{name}: rel-L2 {rel}"
+    of = out.float()
+    s_ref = torch.stack([of.sum(dim=(1, 2, 3)), (of * of).sum(dim=(1, 2, 3))], dim=-1)
+    _report(name + "_stats", ops.stat_to_float(stat).float(), s_ref, rtol=2e-3, atol=1.0)
+
+
 def test_conv3d_epilogue_rowvec_residual_stats(ops):
     B, C, D, H, W = 2, 224, 16, 8, 8
     g = torch.Generator(device="cuda").manual_seed(7)
@@ -257,6 +290,36 @@ def test_attention(ops, N, heads, d, dp):
     attn = torch.softmax(qf @ kf.transpose(-1, -2) * scale, dim=-1)
     ref = (attn @ vf).permute(0, 2, 1, 3).reshape(B, N, heads * d)
     _report("attention", got.float(), ref, rtol=2e-2, atol=1e-2)
+
+
+def test_attention_two_sweep_kernel_many_items_and_lse(ops):
+    """The two-sweep tcgen05 kernel (cs_attn_tc2.cu) with more work items than SMs (every persistent CTA walks ~5 (sample,
+    head, 256-query block) items: barrier phases across items), peaked score rows (|s| up to ~40: the final-maximum
+    subtraction must hold), the log-sum-exp rows of the training forward, and bit-reproducibility."""
+    from commonscenes_b200 import ops_bwd
+    B, N, heads, d, dp = 24, 1024, 8, 56, 64
+    g = torch.Generator(device="cuda").manual_seed(3)
+    qkv = torch.zeros(B, N, 3 * heads * dp, device="cuda")
+    for i in range(3):
+        for h in range(heads):
+            sc = 3.0 if i < 2 else 1.0
+            qkv[:, :, (i * heads + h) * dp:(i * heads + h) * dp + d] = sc * torch.randn(B, N, d, device="cuda", generator=g)
+    qkv = _bf(qkv)
+    q, k, v = (qkv[:, :, i * heads * dp:(i + 1) * heads * dp] for i in range(3))
+    scale = d ** -0.5
+    got = ops.attention(q, k, v, heads=heads, head_dim=d, head_dim_padded=dp, scale=scale)
+    got2, lse = ops_bwd.attention_lse(q, k, v, heads=heads, head_dim=d, head_dim_padded=dp, scale=scale)
+    torch.cuda.synchronize()
+    assert torch.equal(got, got2)
+
+    def split(t):
+        return t.float().reshape(B, N, heads, dp)[..., :d].permute(0, 2, 1, 3)
+    qf, kf, vf = split(q), split(k), split(v)
+    sraw = qf @ kf.transpose(-1, -2) * scale
+    ref = (torch.softmax(sraw, dim=-1) @ vf).permute(0, 2, 1, 3).reshape(B, N, heads * d)
+    _report("attention_tc2", got.float(), ref, rtol=2e-2, atol=1e-2)
+    lse_ref = torch.logsumexp(sraw, dim=-1) * 1.4426950408889634          # base 2, (B, heads, N)
+    _report("attention_tc2_lse", lse, lse_ref, rtol=1e-3, atol=2e-2)
 
 
 def test_attention_cross_short_context(ops):

@@ -20,6 +20,13 @@ def test_partition_covers_everything_in_order():
     assert parallel.partition(10, 8) == [(0, 2), (2, 4), (4, 5), (5, 6), (6, 7), (7, 8), (8, 9), (9, 10)]   # cfg5: 2,2,1,1,1,1,1,1
 
 
+def test_cfg_pair_units_balance_cfg5():
+    """cfg5: 10 objects x CFG = 20 forwards over 8 ranks -> 3,3,3,3,2,2,2,2 instead of the 2:1 object split."""
+    sizes = [hi - lo for lo, hi in parallel.pair_units(10, 8)]
+    assert sizes == [3, 3, 3, 3, 2, 2, 2, 2] and parallel.pair_units(10, 8)[-1][1] == 20
+    assert [hi - lo for lo, hi in parallel.pair_units(1, 2)] == [1, 1]      # one object: uncond on rank 0, cond on rank 1
+
+
 class _StubDiff:
     """Stands in for SDFusionText2ShapeModel on CPU: 'decodes' each object to a volume filled with a value that
     depends only on that object's conditioning, so the gathered result reveals any mis-ordering."""
@@ -42,6 +49,10 @@ def _worker(rank, world, port, n_obj, ret):
         loc = parallel.shard(data["rel"], rank, world)
         back = parallel.gather_objects(loc, n_obj)
         ok = ok and torch.equal(back, data["rel"])
+        # CFG-pair split: each rank evaluates its block of the 2 * O [uncond; cond] forwards, exchange_eps rebuilds the batch
+        full = torch.randn(2 * n_obj, 3, 2, 2, 2, generator=torch.Generator().manual_seed(7))
+        ulo, uhi = parallel.pair_units(n_obj, world)[rank]
+        ok = ok and torch.equal(parallel.exchange_eps(full[ulo:uhi].clone(), n_obj), full)
         ret[rank] = bool(ok)
     finally:
         dist.destroy_process_group()

@@ -225,6 +225,45 @@ def test_graphed_train_step_matches_eager():
     assert float((da - db).norm() / da.norm()) < 0.1
 
 
+def test_evaluation_between_graphed_steps_sees_current_weights():
+    """Mid-training validation: an evaluation (UNet forward / DDIM graph) between two replays of the captured training step
+    must use the weights of that moment.  The AdamW kernel writes through raw pointers (no autograd version bump), so
+    step_graphed() has to invalidate the module's packed-weight cache itself; compare every evaluation against a second
+    module that was freshly given the same parameter values (an eager repack)."""
+    from commonscenes_b200.model.sdfusion_txt2shape_model import SDFusionText2ShapeModel, diffusion_schedule
+    from commonscenes_b200.train import DenoiserTrainStep
+    cfg = D.UNET_TINY
+
+    class Stub:
+        q_sample = SDFusionText2ShapeModel.q_sample
+        z_shape = (3, 8, 8, 8)
+
+        def __init__(self, df):
+            self.df, self.num_timesteps, self.device = df, 1000, "cuda"
+            for k, v in diffusion_schedule(1000, 0.00085, 0.012).items():
+                setattr(self, k, v.cuda())
+
+    g = torch.Generator().manual_seed(13)
+    B = 4
+    z = torch.randn(B, 3, 8, 8, 8, generator=g).cuda()
+    ctx = torch.randn(B, 1, cfg["context_dim"], generator=g).cuda()
+    t = torch.tensor([10, 999, 500, 250]).cuda()
+    noise = torch.randn(B, 3, 8, 8, 8, generator=g).cuda()
+    m, fresh = _build(cfg, 62), _build(cfg, 62)
+    step = DenoiserTrainStep(Stub(m), lr=5e-2)               # a large step: stale weights would be far off
+    step.capture(B, cfg["context_dim"])
+    outs = []
+    for i in range(3):
+        with torch.no_grad():
+            got = m(z, t, c_crossattn=[ctx])
+            fresh.load_state_dict(m.state_dict())            # eager repack of the same values (version counters bump)
+            want = fresh(z, t, c_crossattn=[ctx])
+        assert torch.equal(got, want), f"evaluation after {i} graphed steps used stale packed weights"
+        outs.append(got)
+        step.step_graphed(z, ctx, t=t, noise=noise)
+    assert float((outs[1] - outs[0]).abs().max()) > 0 and float((outs[2] - outs[1]).abs().max()) > 0
+
+
 def test_concat_unet_backward_matches_oracle_autograd():
     """Concat-conditioning denoiser (AttentionBlock variant): `loss.backward()` through
     DiffusionUNet(conditioning_key='concat') -- parameter gradients (incl. the Conv1d qkv / proj_out of every AttentionBlock in

@@ -22,3 +22,13 @@ torch.cuda.profiler.start()
 unet(x, t, context_vecs=ca, shared_prefix=True)
 torch.cuda.synchronize()
 torch.cuda.profiler.stop()
+if "--algo-bytes" in sys.argv:      # algorithmic traffic of the implicit-GEMM launches of this step (for tools/dram_summary.py)
+    import json
+    from commonscenes_b200 import ops
+    prof = ops.ConvProfiler()
+    with prof:
+        unet(x, t, context_vecs=ca, shared_prefix=True)
+    torch.cuda.synchronize()
+    ms, tflop, n = prof.summary()
+    with open(sys.argv[sys.argv.index("--algo-bytes") + 1], "w") as f:
+        json.dump({"launches": n, "algorithmic_bytes_per_step": prof.bytes, "tflop_per_step": tflop}, f)
