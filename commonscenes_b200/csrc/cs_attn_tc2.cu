@@ -50,6 +50,15 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 u;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(addr) : "memory");
+  return u;
+}
+
 // 32 lanes x 32 consecutive fp32 columns into r[0..32)
 __device__ __forceinline__ void tmem_ld32p(uint32_t taddr, uint32_t* r) {
   asm volatile(
@@ -67,7 +76,8 @@ __device__ __forceinline__ void tmem_ld32p(uint32_t taddr, uint32_t* r) {
 __global__ void __launch_bounds__(kT2Threads, 1)
 attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int N,
-                     int H, int o_pitch, int d_out, float scale_log2, int n_items) {
+                     int H, int o_pitch, int d_out, float scale_log2, int n_items, int dbg) {
+  // dbg (tuning experiments only, results are wrong): 1 = no exponentials (FMA instead), 2 = no P stores, 4 = skip sweep 1
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ Atc2Bars bars;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -113,7 +123,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         mbar_arrive_expect_tx(&bars.q_full, 2 * kT2Tile);
         tma_load_2d(&tmQ, &bars.q_full, sQ, h * 64, row_base + q0);
         tma_load_2d(&tmQ, &bars.q_full, sQ + kT2Tile, h * 64, row_base + q0 + 128);
-        for (int sweep = 0; sweep < 2; ++sweep)
+        for (int sweep = (dbg & 4) ? 1 : 0; sweep < 2; ++sweep)
           for (int j = 0; j < T; ++j) {
             const int ks = kc % kT2KS;
             mbar_wait(&bars.k_empty[ks], ((kc / kT2KS) & 1) ^ 1);
@@ -159,7 +169,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
         mbar_wait(&bars.q_full, it & 1);
         tc_fence_after();
-        for (int j = 0; j < T; ++j) issue_qk();                                   // sweep 1: row maxima only
+        for (int j = 0; j < ((dbg & 4) ? 0 : T); ++j) issue_qk();                 // sweep 1: row maxima only
         for (int j = 0; j <= T; ++j) {                                            // sweep 2: S again, then O += P V one tile behind
           if (j < T) issue_qk();
           if (j > 0) {
@@ -199,6 +209,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const uint32_t t_o = tmem + (static_cast<uint32_t>(quarter * 32) << 16) + 256u + static_cast<uint32_t>(g * 64);
     uint8_t* sPg = sP + g * 2 * kT2Tile;
     uint8_t* p_row = sPg + r * 128;
+    const uint32_t p_row_s = smem_u32(p_row);                   // explicit shared-space stores (generic ST.E was being split)
     const uint32_t swz = static_cast<uint32_t>(r & 7);
     int sc = 0, pc = 0, it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
@@ -207,8 +218,8 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const long long row0 = static_cast<long long>(b) * N + qb * 256 + g * 128;   // first global token row of this group's tile
       uint32_t raw[128];
       // ---- sweep 1: row maximum over all keys ----
-      float m = -INFINITY;
-      for (int j = 0; j < T; ++j) {
+      float m = (dbg & 4) ? 40.f : -INFINITY;
+      for (int j = 0; j < ((dbg & 4) ? 0 : T); ++j) {
         mbar_wait(&bars.s_full[g], sc & 1);
         tc_fence_after();
 #pragma unroll
@@ -242,17 +253,19 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         uint32_t pk[64];
 #pragma unroll
         for (int i = 0; i < 128; i += 2) {
-          const float p0 = ex2_approx(fmaf(__uint_as_float(raw[i]), scale_log2, -msc));
-          const float p1 = ex2_approx(fmaf(__uint_as_float(raw[i + 1]), scale_log2, -msc));
+          float p0 = fmaf(__uint_as_float(raw[i]), scale_log2, -msc), p1 = fmaf(__uint_as_float(raw[i + 1]), scale_log2, -msc);
+          if (!(dbg & 1)) { p0 = ex2_approx(p0); p1 = ex2_approx(p1); }
           l0 += p0;
           l1 += p1;
           pk[i >> 1] = pack_bf16x2(p0, p1);
         }
         mbar_wait(&bars.p_empty[g], (pc & 1) ^ 1);             // P V of the previous tile has consumed the buffer
+        if (!(dbg & 2)) {
 #pragma unroll
-        for (int chunk = 0; chunk < 16; ++chunk)               // 16 chunks of 8 keys (16 B) per row
-          *reinterpret_cast<uint4*>(p_row + (chunk >> 3) * kT2Tile + (((chunk & 7) ^ swz) << 4)) =
-              make_uint4(pk[chunk * 4], pk[chunk * 4 + 1], pk[chunk * 4 + 2], pk[chunk * 4 + 3]);
+          for (int chunk = 0; chunk < 16; ++chunk)             // 16 chunks of 8 keys (16 B) per row
+            st_shared_v4(p_row_s + static_cast<uint32_t>((chunk >> 3) * kT2Tile) + (((static_cast<uint32_t>(chunk) & 7u) ^ swz) << 4),
+                         pk[chunk * 4], pk[chunk * 4 + 1], pk[chunk * 4 + 2], pk[chunk * 4 + 3]);
+        }
         fence_proxy_async();                                   // generic-proxy smem writes -> visible to the MMA (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars.p_full[g]);
@@ -277,7 +290,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         u.y = pack_bf16x2(__uint_as_float(raw[chunk * 8 + 2]) * inv, __uint_as_float(raw[chunk * 8 + 3]) * inv);
         u.z = pack_bf16x2(__uint_as_float(raw[chunk * 8 + 4]) * inv, __uint_as_float(raw[chunk * 8 + 5]) * inv);
         u.w = pack_bf16x2(__uint_as_float(raw[chunk * 8 + 6]) * inv, __uint_as_float(raw[chunk * 8 + 7]) * inv);
-        *reinterpret_cast<uint4*>(p_row + ((static_cast<uint32_t>(chunk) ^ swz) << 4)) = u;
+        st_shared_v4(p_row_s + ((static_cast<uint32_t>(chunk) ^ swz) << 4), u.x, u.y, u.z, u.w);
       }
       if (g == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
       __nv_bfloat16* og = out + row0 * o_pitch + h * d_out;
@@ -286,7 +299,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         const int idx = i * 128 + gt;
         const int rr = idx >> 3, ch = idx & 7;
         if (ch * 8 < d_out) {                                  // d_out % 8 == 0 on this path (host-checked)
-          const uint4 u = *reinterpret_cast<const uint4*>(sPg + rr * 128 + ((ch ^ (rr & 7)) << 4));
+          const uint4 u = ld_shared_v4(smem_u32(sPg) + static_cast<uint32_t>(rr * 128 + ((ch ^ (rr & 7)) << 4)));
           *reinterpret_cast<uint4*>(og + static_cast<long long>(rr) * o_pitch + ch * 8) = u;
         }
       }
@@ -302,6 +315,8 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     tmem_dealloc(tmem, 512);
   }
 }
+
+int igemm_debug_flags();
 
 int attention_tc2_launch(const void* q, const void* k, const void* v, void* out, float* lse, int B, int H, int N, int q_pitch,
                          int kv_pitch, int o_pitch, int d_out, float scale, cudaStream_t st) {
@@ -325,7 +340,7 @@ int attention_tc2_launch(const void* q, const void* k, const void* v, void* out,
   const int n_items = B * H * (N / 256);
   const int grid = n_items < num_sms() ? n_items : num_sms();
   attention_tc2_kernel<<<grid, kT2Threads, smem, st>>>(tq, tk, tv, reinterpret_cast<__nv_bfloat16*>(out), lse, N, H, o_pitch, d_out,
-                                                       scale * 1.4426950408889634f, n_items);
+                                                       scale * 1.4426950408889634f, n_items, (igemm_debug_flags() >> 16) & 7);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error(e, "attention_tc2: launch");
   count_launch();
