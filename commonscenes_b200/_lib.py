@@ -108,6 +108,11 @@ SIGNATURES = {
     "cs_embedding_bwd": (_i32, [_vp, _i32, _i32, _i32, _vp, _i32, _i32, _vp, _vp]),
     "cs_tap_gather": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "cs_cast_f32_to_bf16": (_i32, [_vp, _i64, _vp, _vp]),
+    "cs_nn_distance": (_i32, [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "cs_nn_distance_grad": (_i32, [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "cs_approx_match": (_i32, [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "cs_match_cost": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),
+    "cs_match_cost_grad": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
     "cs_debug_set": (None, [_i32]),
     "cs_conv3d_variant_counts": (None, [_vp, _i32]),
     "cs_vq_quantize": (_i32, [_vp, _i32, _i32, _i64, _vp, _i32, _vp, _vp, _i32, _vp, _vp, _vp]),

@@ -70,6 +70,12 @@ void igemm_variant_counts(unsigned long long*, int);
 int cast_bf16_launch(const float*, long long, void*, cudaStream_t);
 int vq_quantize_launch(const float*, int, int, long long, const float*, int, const float*, const float*, int, float*,
                        long long*, cudaStream_t);
+int nn_distance_launch(const float*, const float*, int, int, int, float*, int*, float*, int*, cudaStream_t);
+int nn_distance_grad_launch(const float*, const float*, int, int, int, const float*, const int*, const float*, const int*, float*,
+                            float*, cudaStream_t);
+int approx_match_launch(const float*, const float*, int, int, int, float*, float*, cudaStream_t);
+int match_cost_launch(const float*, const float*, const float*, int, int, int, float*, cudaStream_t);
+int match_cost_grad_launch(const float*, const float*, const float*, int, int, int, float*, float*, cudaStream_t);
 }  // namespace cs
 
 static inline cudaStream_t S(cs_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
@@ -347,5 +353,26 @@ int cs_attention_bwd(const void* q, const void* k, const void* v, const void* o,
                      cs_stream_t stream) {
   return cs::attention_bwd_launch(q, k, v, o, dout, lse, dsum_ws, dq, dk, dv, B, H, N, Dp, qkv_pitch, o_pitch, do_pitch,
                                   dqkv_pitch, d_out, scale, S(stream));
+}
+int cs_nn_distance(const float* xyz1, const float* xyz2, int32_t b, int32_t n, int32_t m, float* dist1, int32_t* idx1,
+                   float* dist2, int32_t* idx2, cs_stream_t stream) {
+  return cs::nn_distance_launch(xyz1, xyz2, b, n, m, dist1, idx1, dist2, idx2, S(stream));
+}
+int cs_nn_distance_grad(const float* xyz1, const float* xyz2, int32_t b, int32_t n, int32_t m, const float* grad_dist1,
+                        const int32_t* idx1, const float* grad_dist2, const int32_t* idx2, float* grad_xyz1, float* grad_xyz2,
+                        cs_stream_t stream) {
+  return cs::nn_distance_grad_launch(xyz1, xyz2, b, n, m, grad_dist1, idx1, grad_dist2, idx2, grad_xyz1, grad_xyz2, S(stream));
+}
+int cs_approx_match(const float* xyz1, const float* xyz2, int32_t b, int32_t n, int32_t m, float* match, float* temp,
+                    cs_stream_t stream) {
+  return cs::approx_match_launch(xyz1, xyz2, b, n, m, match, temp, S(stream));
+}
+int cs_match_cost(const float* xyz1, const float* xyz2, const float* match, int32_t b, int32_t n, int32_t m, float* cost,
+                  cs_stream_t stream) {
+  return cs::match_cost_launch(xyz1, xyz2, match, b, n, m, cost, S(stream));
+}
+int cs_match_cost_grad(const float* xyz1, const float* xyz2, const float* match, int32_t b, int32_t n, int32_t m, float* grad1,
+                       float* grad2, cs_stream_t stream) {
+  return cs::match_cost_grad_launch(xyz1, xyz2, match, b, n, m, grad1, grad2, S(stream));
 }
 }  // extern "C"

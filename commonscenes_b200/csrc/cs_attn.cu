@@ -226,6 +226,8 @@ int attention_tc_launch(const void* q, const void* k, const void* v, void* out, 
                         int kv_pitch, int o_pitch, int d_out, float scale, cudaStream_t st);
 int attention_tc2_launch(const void* q, const void* k, const void* v, void* out, float* lse, int B, int H, int N, int q_pitch,
                          int kv_pitch, int o_pitch, int d_out, float scale, cudaStream_t st);
+int attention_tc3_launch(const void* q, const void* k, const void* v, void* out, float* lse, int B, int H, int N, int q_pitch,
+                         int kv_pitch, int o_pitch, int d_out, float scale, cudaStream_t st);
 int igemm_debug_flags();
 
 int attention_lse_launch(const void* q, const void* k, const void* v, void* out, int B, int H, int Nq, int Nk,
@@ -247,6 +249,10 @@ int attention_lse_launch(const void* q, const void* k, const void* v, void* out,
   // tcgen05 paths: the two-sweep kernel (cs_attn_tc2.cu; also produces the log-sum-exp rows of the training forward) when
   // the sequence splits into 256-query blocks, else the first-generation kernel (cs_attn_tc.cu).  Debug flag 128 = mma.sync
   // kernel, 16384 = first-generation tcgen05 kernel (A/B timing).
+  // Third generation (cs_attn_tc3.cu: staggered query-tile pipelines, P through TMEM) first; debug flag 32768 = second generation.
+  if (Dp == 64 && Nq == Nk && Nq % 128 == 0 && d_out % 8 == 0 && o_pitch % 8 == 0 && (H * d_out) % 8 == 0 &&
+      reinterpret_cast<uintptr_t>(out) % 16 == 0 && !(igemm_debug_flags() & (128 | 16384 | 32768)))
+    return attention_tc3_launch(q, k, v, out, lse, B, H, Nq, q_pitch, kv_pitch, o_pitch, d_out, scale, st);
   if (Dp == 64 && Nq == Nk && Nq % 256 == 0 && d_out % 8 == 0 && o_pitch % 8 == 0 && (H * d_out) % 8 == 0 &&
       reinterpret_cast<uintptr_t>(out) % 16 == 0 && !(igemm_debug_flags() & (128 | 16384)))
     return attention_tc2_launch(q, k, v, out, lse, B, H, Nq, q_pitch, kv_pitch, o_pitch, d_out, scale, st);

@@ -1,0 +1,368 @@
+// tcgen05 self-attention, third generation: the kernel for the denoiser's 1024-token transformer blocks
+// (8 heads, d_head 56 zero-padded to 64; reference semantics: CrossAttention.forward as self-attention,
+// model/networks/diffusion_networks/attention.py:172-219 -- softmax(q k^T * d^-0.5) v per head, no mask).
+//
+// What the ncu source page of the two-sweep kernel (cs_attn_tc2.cu, profiles/r2c_attn_tc2.txt: 34 % tensor-pipe active)
+// and its decomposition (tools/attn_decomp.py, gpurun_out/r2d_attn_decomp.log) showed:
+//   * sweep 1 (row maxima) is a SERIAL chain per query tile -- Q K^T (256 clk) -> tcgen05.ld (~400) -> release S -> next
+//     Q K^T -- during which the exponential unit idles; sweep 2 is bound by the exponentials (16 MUFU lanes per SM:
+//     1024 clk per 128 x 128 tile) during which the tensor pipe idles.  Both query tiles of a CTA ran the same sweep at
+//     the same time, so the two phases never overlapped: 7.5 k + 27 k + 5 k (epilogue) clk per 256-query item;
+//   * P went to the MMA through shared memory: 32 KB of st.shared per key tile, and P V with N = 64 re-reads the 128 x 16
+//     A slab from shared memory for every 32 clk of math (192 B/clk against a 128 B/clk port).
+// This kernel keeps the two-sweep arithmetic (identical results: final row maximum first, then p = exp2(s c - m c), O
+// accumulated in TMEM without any rescale) and changes the schedule:
+//   * the two 128-query tiles of a CTA are INDEPENDENT pipelines (own TMA warp, own MMA-issuing warp, own four softmax
+//     warps, own K / V rings and barriers) running HALF AN ITEM APART: while one group does its exponentials (sweep 2)
+//     the other does its maxima (sweep 1), so the MUFU unit always has a sweep 2 to chew on and the tensor pipe takes
+//     the other group's Q K^T in its shadow;
+//   * P never touches shared memory: the softmax warps write it to TMEM (tcgen05.st, bf16 pairs) and P V takes its A
+//     operand from TMEM (tcgen05.mma [d], [a], b-desc); only V is read from shared memory.
+// TMEM per group (256 columns): S 128 | P 64 (128 bf16) | O 64.  Shared memory per group: Q 16 KB, K 3 x 16 KB, V 2 x 16 KB.
+// Roles (384 threads): warps 0 / 2 = TMA producers of group 0 / 1, warps 1 / 3 = MMA issuers (warp 1 also owns the TMEM
+// allocation), warps 4-7 = softmax group 0, warps 8-11 = softmax group 1 (a warp touches TMEM lanes 32 (warp % 4) .. + 32).
+#include "cs_host.h"
+
+namespace cs {
+
+static constexpr int kT3Threads = 384;
+static constexpr int kT3Tile = 128 * 128;   // bytes of a [128 rows][64 bf16] tile
+static constexpr int kT3KS = 3;             // K stages per group
+static constexpr int kT3VS = 2;             // V stages per group
+static constexpr int kT3GroupSmem = (1 + kT3KS + kT3VS) * kT3Tile;
+
+struct __align__(8) Atc3Bars {
+  uint64_t q_full, q_empty;
+  uint64_t k_full[kT3KS], k_empty[kT3KS];
+  uint64_t v_full[kT3VS], v_empty[kT3VS];
+  uint64_t s_full, s_empty, p_full, p_empty, o_full, o_empty;
+};
+
+__device__ __forceinline__ float t3_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void t3_st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 t3_ld_shared_v4(uint32_t addr) {
+  uint4 u;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(addr) : "memory");
+  return u;
+}
+// 32 lanes x 32 consecutive 32-bit columns: registers <- TMEM
+__device__ __forceinline__ void t3_tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+// 32 lanes x 32 consecutive 32-bit columns: TMEM <- registers
+__device__ __forceinline__ void t3_tmem_st32(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      :
+      : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void t3_tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] * B[smem]; bf16 x bf16 -> f32, issued by ONE thread.  A: 128 lanes x 8 columns (16 bf16 along K).
+__device__ __forceinline__ void t3_umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n"
+      :
+      : "r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(kT3Threads, 1)
+attention_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                     const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int N,
+                     int H, int o_pitch, int d_out, float scale_log2, int n_tiles, int dbg) {
+  // dbg (tuning experiments only, results are wrong): 1 = no exponentials, 8 = both groups start together (no stagger)
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ Atc3Bars bars2[2];
+  __shared__ uint64_t go_bar;
+  __shared__ uint32_t tmem_base_s;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int T = N / 128;                                // key tiles = query tiles per (sample, head)
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+    for (int g = 0; g < 2; ++g) {
+      Atc3Bars& b = bars2[g];
+      mbar_init(&b.q_full, 1); mbar_init(&b.q_empty, 1);
+      for (int i = 0; i < kT3KS; ++i) { mbar_init(&b.k_full[i], 1); mbar_init(&b.k_empty[i], 1); }
+      for (int i = 0; i < kT3VS; ++i) { mbar_init(&b.v_full[i], 1); mbar_init(&b.v_empty[i], 1); }
+      mbar_init(&b.s_full, 1); mbar_init(&b.s_empty, 4);
+      mbar_init(&b.p_full, 4); mbar_init(&b.p_empty, 1);
+      mbar_init(&b.o_full, 1); mbar_init(&b.o_empty, 4);
+    }
+    mbar_init(&go_bar, 4);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&tmem_base_s, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+
+  const int g = (warp < 4) ? (warp >> 1) : ((warp - 4) >> 2);      // which query-tile pipeline this warp serves
+  Atc3Bars& bars = bars2[g];
+  uint8_t* sQ = smem + g * kT3GroupSmem;
+  uint8_t* sK = sQ + kT3Tile;
+  uint8_t* sV = sK + kT3KS * kT3Tile;
+  const uint32_t tm_s = tmem + static_cast<uint32_t>(g * 256);     // S: 128 fp32 columns
+  const uint32_t tm_p = tm_s + 128u;                               // P: 64 columns of bf16 pairs
+  const uint32_t tm_o = tm_s + 192u;                               // O: 64 fp32 columns
+  const int first_tile = blockIdx.x * 2 + g, tile_step = gridDim.x * 2;
+
+  if (warp < 4 && (warp & 1) == 0) {
+    // =========================== TMA producer of group g ===========================
+    if (lane == 0) {
+      int kc = 0, vc = 0, it = 0;
+      for (int tile = first_tile; tile < n_tiles; tile += tile_step, ++it) {
+        const int qt = tile % T, bh = tile / T;
+        const int h = bh % H, b = bh / H;
+        const int row_base = b * N;
+        mbar_wait(&bars.q_empty, (it & 1) ^ 1);
+        mbar_arrive_expect_tx(&bars.q_full, kT3Tile);
+        tma_load_2d(&tmQ, &bars.q_full, sQ, h * 64, row_base + qt * 128);
+        for (int sweep = 0; sweep < 2; ++sweep)
+          for (int j = 0; j < T; ++j) {
+            const int ks = kc % kT3KS;
+            mbar_wait(&bars.k_empty[ks], ((kc / kT3KS) & 1) ^ 1);
+            mbar_arrive_expect_tx(&bars.k_full[ks], kT3Tile);
+            tma_load_2d(&tmK, &bars.k_full[ks], sK + ks * kT3Tile, h * 64, row_base + j * 128);
+            ++kc;
+            if (sweep == 1) {
+              const int vs = vc % kT3VS;
+              mbar_wait(&bars.v_empty[vs], ((vc / kT3VS) & 1) ^ 1);
+              mbar_arrive_expect_tx(&bars.v_full[vs], kT3Tile);
+              tma_load_2d(&tmV, &bars.v_full[vs], sV + vs * kT3Tile, h * 64, row_base + j * 128);
+              ++vc;
+            }
+          }
+      }
+    }
+  } else if (warp < 4) {
+    // =========================== MMA issuer of group g ===========================
+    if (lane == 0) {
+      const uint32_t idesc_s = umma_idesc_bf16_m128(128);
+      const uint32_t idesc_o = umma_idesc_bf16_m128_bmn(64);
+      const uint64_t qdesc = umma_desc_k_sw128(smem_u32(sQ));
+      int kc = 0, vc = 0, it = 0, sc = 0, pc = 0;
+      auto issue_qk = [&]() {                      // S = Q K^T on the next K stage
+        const int ks = kc % kT3KS;
+        mbar_wait(&bars.k_full[ks], (kc / kT3KS) & 1);
+        mbar_wait(&bars.s_empty, (sc & 1) ^ 1);    // the softmax warps have pulled the previous S tile into registers
+        tc_fence_after();
+        const uint64_t kdesc = umma_desc_k_sw128(smem_u32(sK + ks * kT3Tile));
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tm_s, qdesc + static_cast<uint64_t>(k * 2), kdesc + static_cast<uint64_t>(k * 2), idesc_s, k > 0);
+        umma_commit(&bars.s_full);
+        umma_commit(&bars.k_empty[ks]);
+        ++sc;
+        ++kc;
+      };
+      if (g == 1 && !(dbg & 8) && first_tile < n_tiles) mbar_wait(&go_bar, 0);   // half an item behind group 0
+      for (int tile = first_tile; tile < n_tiles; tile += tile_step, ++it) {
+        mbar_wait(&bars.q_full, it & 1);
+        tc_fence_after();
+        for (int j = 0; j < T; ++j) issue_qk();                                   // sweep 1: row maxima only
+        for (int j = 0; j <= T; ++j) {                                            // sweep 2: S again, then O += P V one tile behind
+          if (j < T) issue_qk();
+          if (j == T - 1) umma_commit(&bars.q_empty);                             // Q is dead once the last Q K^T has retired
+          if (j > 0) {
+            const int vs = vc % kT3VS;
+            mbar_wait(&bars.v_full[vs], (vc / kT3VS) & 1);
+            mbar_wait(&bars.p_full, pc & 1);
+            if (j == 1) mbar_wait(&bars.o_empty, (it & 1) ^ 1);                   // previous item's O tile has been read out
+            tc_fence_after();
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {                                         // 16 keys per MMA: 8 columns of P, 2 KB of V
+              const uint64_t vdesc = umma_desc_mn_sw128(smem_u32(sV + vs * kT3Tile + k * 2048), 16384u, 1024u);
+              t3_umma_ts(tm_o, tm_p + static_cast<uint32_t>(k * 8), vdesc, idesc_o, (j > 1 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(&bars.p_empty);
+            umma_commit(&bars.v_empty[vs]);
+            ++pc;
+            ++vc;
+          }
+        }
+        umma_commit(&bars.o_full);
+      }
+    }
+  } else {
+    // =========================== softmax warps of group g ===========================
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;                          // query row inside the tile = TMEM lane
+    const int gt = (warp - 4 - g * 4) * 32 + lane;              // 0..127 inside the group
+    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t t_s = tm_s + lane_off, t_p = tm_p + lane_off, t_o = tm_o + lane_off;
+    // output staging: the first V stage (every P V of the item has retired when it is used, and the producer cannot reach
+    // the next item's first V load before these warps have released five of its sweep-1 score tiles)
+    const uint32_t stage_s = smem_u32(sV);
+    const uint32_t row_s = stage_s + static_cast<uint32_t>(r * 128);
+    const uint32_t swz = static_cast<uint32_t>(r & 7);
+    int sc = 0, pc = 0, it = 0;
+    for (int tile = first_tile; tile < n_tiles; tile += tile_step, ++it) {
+      const int qt = tile % T, bh = tile / T;
+      const int h = bh % H, b = bh / H;
+      const long long row0 = static_cast<long long>(b) * N + qt * 128;            // first global token row of the tile
+      uint32_t raw[128];
+      // ---- sweep 1: row maximum over all keys ----
+      float m = -INFINITY;
+      for (int j = 0; j < T; ++j) {
+        mbar_wait(&bars.s_full, sc & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < 4; ++c) t3_tmem_ld32(t_s + static_cast<uint32_t>(c * 32), raw + c * 32);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars.s_empty);
+        ++sc;
+        float mx0 = m, mx1 = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 128; i += 4) {
+          mx0 = fmaxf(mx0, fmaxf(__uint_as_float(raw[i]), __uint_as_float(raw[i + 1])));
+          mx1 = fmaxf(mx1, fmaxf(__uint_as_float(raw[i + 2]), __uint_as_float(raw[i + 3])));
+        }
+        m = fmaxf(mx0, mx1);
+      }
+      if (g == 0 && it == 0) {                                  // group 1 starts its first sweep 1 now
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&go_bar);
+      }
+      // ---- sweep 2: probabilities against the final maximum, P -> bf16 -> TMEM, row sum ----
+      const float msc = m * scale_log2;
+      float l0 = 0.f, l1 = 0.f;
+      for (int j = 0; j < T; ++j) {
+        mbar_wait(&bars.s_full, sc & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < 4; ++c) t3_tmem_ld32(t_s + static_cast<uint32_t>(c * 32), raw + c * 32);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars.s_empty);              // Q K^T of the next tile may overwrite S now
+        ++sc;
+        uint32_t pk[64];
+#pragma unroll
+        for (int i = 0; i < 128; i += 2) {
+          float p0 = fmaf(__uint_as_float(raw[i]), scale_log2, -msc), p1 = fmaf(__uint_as_float(raw[i + 1]), scale_log2, -msc);
+          if (!(dbg & 1)) { p0 = t3_ex2(p0); p1 = t3_ex2(p1); }
+          l0 += p0;
+          l1 += p1;
+          pk[i >> 1] = pack_bf16x2(p0, p1);
+        }
+        mbar_wait(&bars.p_empty, (pc & 1) ^ 1);                 // P V of the previous tile has consumed the P columns
+        tc_fence_after();
+        t3_tmem_st32(t_p, pk);
+        t3_tmem_st32(t_p + 32u, pk + 32);
+        t3_tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars.p_full);
+        ++pc;
+      }
+      // ---- output: O / l, staged through shared memory, written as whole rows ----
+      mbar_wait(&bars.o_full, it & 1);                          // every P V of this item has retired
+      tc_fence_after();
+      t3_tmem_ld32(t_o, raw);
+      t3_tmem_ld32(t_o + 32u, raw + 32);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars.o_empty);
+      const float l = l0 + l1;
+      const float inv = 1.f / l;
+      if (lse) lse[(static_cast<long long>(b) * H + h) * N + qt * 128 + r] = msc + log2f(l);
+#pragma unroll
+      for (int chunk = 0; chunk < 8; ++chunk) {
+        const uint32_t ux = pack_bf16x2(__uint_as_float(raw[chunk * 8 + 0]) * inv, __uint_as_float(raw[chunk * 8 + 1]) * inv);
+        const uint32_t uy = pack_bf16x2(__uint_as_float(raw[chunk * 8 + 2]) * inv, __uint_as_float(raw[chunk * 8 + 3]) * inv);
+        const uint32_t uz = pack_bf16x2(__uint_as_float(raw[chunk * 8 + 4]) * inv, __uint_as_float(raw[chunk * 8 + 5]) * inv);
+        const uint32_t uw = pack_bf16x2(__uint_as_float(raw[chunk * 8 + 6]) * inv, __uint_as_float(raw[chunk * 8 + 7]) * inv);
+        t3_st_shared_v4(row_s + ((static_cast<uint32_t>(chunk) ^ swz) << 4), ux, uy, uz, uw);
+      }
+      if (g == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+      __nv_bfloat16* og = out + row0 * o_pitch + h * d_out;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int idx = i * 128 + gt;
+        const int rr = idx >> 3, ch = idx & 7;
+        if (ch * 8 < d_out) {                                  // d_out % 8 == 0 on this path (host-checked)
+          const uint4 u = t3_ld_shared_v4(stage_s + static_cast<uint32_t>(rr * 128 + ((ch ^ (rr & 7)) << 4)));
+          *reinterpret_cast<uint4*>(og + static_cast<long long>(rr) * o_pitch + ch * 8) = u;
+        }
+      }
+      // staging reads done before anything of the next item can land in the V stage
+      if (g == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+int igemm_debug_flags();
+
+int attention_tc3_launch(const void* q, const void* k, const void* v, void* out, float* lse, int B, int H, int N, int q_pitch,
+                         int kv_pitch, int o_pitch, int d_out, float scale, cudaStream_t st) {
+  if (N % 128 || d_out % 8 || d_out > 64 || o_pitch % 8 || (H * d_out) % 8 || reinterpret_cast<uintptr_t>(out) % 16)
+    return set_error(CS_ERR_INVALID, "attention_tc3: N % 128, d_out % 8 (<= 64), 16-byte aligned output rows");
+  CUtensorMap tq, tk, tv;
+  const uint32_t box[2] = {64u, 128u}, es[2] = {1u, 1u};
+  const uint64_t dims[2] = {static_cast<uint64_t>(H) * 64, static_cast<uint64_t>(B) * N};
+  const uint64_t sq[1] = {static_cast<uint64_t>(q_pitch) * 2}, skv[1] = {static_cast<uint64_t>(kv_pitch) * 2};
+  int rc = make_tensor_map(&tq, q, 2, dims, sq, box, es);
+  if (rc) return rc;
+  if ((rc = make_tensor_map(&tk, k, 2, dims, skv, box, es))) return rc;
+  if ((rc = make_tensor_map(&tv, v, 2, dims, skv, box, es))) return rc;
+  const int smem = 2 * kT3GroupSmem + 1024;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(attention_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return set_cuda_error(e, "attention_tc3: cudaFuncSetAttribute");
+    attr = true;
+  }
+  const int n_tiles = B * H * (N / 128);
+  const int pairs = (n_tiles + 1) / 2;
+  const int grid = pairs < num_sms() ? pairs : num_sms();
+  attention_tc3_kernel<<<grid, kT3Threads, smem, st>>>(tq, tk, tv, reinterpret_cast<__nv_bfloat16*>(out), lse, N, H, o_pitch, d_out,
+                                                       scale * 1.4426950408889634f, n_tiles, (igemm_debug_flags() >> 16) & 15);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(e, "attention_tc3: launch");
+  count_launch();
+  return CS_OK;
+}
+
+}  // namespace cs

@@ -289,6 +289,29 @@ int cs_embedding_bwd(const float* d_rows, int32_t pitch, int32_t col_off, int32_
 /* contiguous fp32 -> bf16 (keys / values of a multi-token cross-attention context, attention.py:186-187) */
 int cs_cast_f32_to_bf16(const float* x, int64_t n, void* y, cs_stream_t stream);
 
+/* ---- point-cloud distances of the evaluation chain behind the decoded SDFs; fp32, contiguous (b, n, 3) /
+ * (b, m, 3) point sets.  Bit-equal to the reference's own CUDA kernels (same per-thread operation order). ---- */
+/* squared distance to / index of the nearest point of the other set, both directions
+ * (extension/chamfer.cu:12-153 chamfer_cuda_forward; scripts/pytorch_structural_losses/src/nndistance.cu:1-128 nndistance).
+ * Ties go to the lowest index.  An empty opposite set yields zeros (the zero-initialised outputs of extension/dist_chamfer.py:20-24). */
+int cs_nn_distance(const float* xyz1, const float* xyz2, int32_t b, int32_t n, int32_t m, float* dist1, int32_t* idx1,
+                   float* dist2, int32_t* idx2, cs_stream_t stream);
+/* gradients of (dist1, dist2) w.r.t. both point sets; zero-fills grad_xyz1 (b, n, 3) / grad_xyz2 (b, m, 3) first
+ * (extension/chamfer.cu:155-195 chamfer_cuda_backward; nndistance.cu:129-155 nndistancegrad) */
+int cs_nn_distance_grad(const float* xyz1, const float* xyz2, int32_t b, int32_t n, int32_t m, const float* grad_dist1,
+                        const int32_t* idx1, const float* grad_dist2, const int32_t* idx2, float* grad_xyz1, float* grad_xyz2,
+                        cs_stream_t stream);
+/* approximate earth-mover matching: match (b, m, n) fp32, temp (b, 2 (n + m)) fp32 scratch
+ * (scripts/pytorch_structural_losses/src/approxmatch.cu:3-182, :293-301 approxmatch; structural_loss.cpp:21-37 ApproxMatch) */
+int cs_approx_match(const float* xyz1, const float* xyz2, int32_t b, int32_t n, int32_t m, float* match, float* temp,
+                    cs_stream_t stream);
+/* cost[i] = sum_{k,j} match[i][k][j] |xyz2[i][k] - xyz1[i][j]|   (approxmatch.cu:184-222, :303-311; structural_loss.cpp:39-52) */
+int cs_match_cost(const float* xyz1, const float* xyz2, const float* match, int32_t b, int32_t n, int32_t m, float* cost,
+                  cs_stream_t stream);
+/* d cost / d xyz1 (b, n, 3) and d cost / d xyz2 (b, m, 3)   (approxmatch.cu:227-291, :313-322; structural_loss.cpp:54-70) */
+int cs_match_cost_grad(const float* xyz1, const float* xyz2, const float* match, int32_t b, int32_t n, int32_t m, float* grad1,
+                       float* grad2, cs_stream_t stream);
+
 /* tuning experiments only (tools/): bit 0 = drop the epilogue's global stores, bit 1 = empty epilogue, bit 2 = no MMA.
  * Results are WRONG while any bit is set; 0 restores normal operation. */
 void cs_debug_set(int32_t flags);

@@ -320,6 +320,41 @@ def test_attention_two_sweep_kernel_many_items_and_lse(ops):
     _report("attention_tc2", got.float(), ref, rtol=2e-2, atol=1e-2)
     lse_ref = torch.logsumexp(sraw, dim=-1) * 1.4426950408889634          # base 2, (B, heads, N)
     _report("attention_tc2_lse", lse, lse_ref, rtol=1e-3, atol=2e-2)
+    # the default path is the third-generation kernel (cs_attn_tc3.cu): same arithmetic as the second generation
+    # (debug flag 32768 selects it), so the two must agree bit for bit
+    from commonscenes_b200 import _lib
+    _lib.load().cs_debug_set(32768)
+    try:
+        gen2 = ops.attention(q, k, v, heads=heads, head_dim=d, head_dim_padded=dp, scale=scale)
+        torch.cuda.synchronize()
+    finally:
+        _lib.load().cs_debug_set(0)
+    assert torch.equal(got, gen2), f"gen 3 vs gen 2: max |diff| {float((got.float() - gen2.float()).abs().max())}"
+
+
+@pytest.mark.parametrize("B,N,heads", [(3, 384, 1), (1, 128, 1), (5, 640, 3), (2, 2048, 2)])
+def test_attention_gen3_odd_tile_counts(ops, B, N, heads):
+    """cs_attn_tc3.cu: an odd number of 128-query tiles (the second pipeline of the last CTA has one item less or none),
+    one-tile sequences, more key tiles than K stages."""
+    d, dp = 56, 64
+    g = torch.Generator(device="cuda").manual_seed(N)
+    qkv = torch.zeros(B, N, 3 * heads * dp, device="cuda")
+    for i in range(3):
+        for h in range(heads):
+            qkv[:, :, (i * heads + h) * dp:(i * heads + h) * dp + d] = 1.5 * torch.randn(B, N, d, device="cuda", generator=g)
+    qkv = _bf(qkv)
+    q, k, v = (qkv[:, :, i * heads * dp:(i + 1) * heads * dp] for i in range(3))
+    scale = d ** -0.5
+    got = ops.attention(q, k, v, heads=heads, head_dim=d, head_dim_padded=dp, scale=scale)
+    again = ops.attention(q, k, v, heads=heads, head_dim=d, head_dim_padded=dp, scale=scale)
+    torch.cuda.synchronize()
+    assert torch.equal(got, again)
+
+    def split(t):
+        return t.float().reshape(B, N, heads, dp)[..., :d].permute(0, 2, 1, 3)
+    qf, kf, vf = split(q), split(k), split(v)
+    ref = (torch.softmax(qf @ kf.transpose(-1, -2) * scale, dim=-1) @ vf).permute(0, 2, 1, 3).reshape(B, N, heads * d)
+    _report("attention_tc3", got.float(), ref, rtol=2e-2, atol=1e-2)
 
 
 def test_attention_cross_short_context(ops):
