@@ -370,9 +370,21 @@ def run_ours(args):
                  "replicas_identical": same, "loss": float(loss_t), "peak_mem_gib": torch.cuda.max_memory_allocated() / 2 ** 30}
 
     ms_total, ms_e2e = max_over_ranks(ms_total, ms_e2e)
-    if rank != 0:
+
+    def leave():
+        """Multi-rank exit.  The data-parallel training step lives in CUDA graphs that hold NCCL kernels; tearing the
+        communicator down under them (destroy_process_group) blocked forever on a 2-GPU box (gpurun_out/r2e_bench_2gpu.log:
+        the JSON line was printed, then the job sat until the time limit).  Every rank therefore meets at a last barrier,
+        drains its device and leaves without running the NCCL teardown."""
         if world > 1:
-            dist.destroy_process_group()
+            dist.barrier()
+            torch.cuda.synchronize()
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
+
+    if rank != 0:
+        leave()
         return
 
     peak_tf, peak_hbm, peak_src = _peaks()
@@ -418,8 +430,7 @@ def run_ours(args):
         v, cores, sample, _ = cpu_oracle_steps_per_s(repeats=3, warmup=1)
         line["cpu_baseline"] = {"value": v, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    leave()
 
 
 def main():
