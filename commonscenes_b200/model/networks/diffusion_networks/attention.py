@@ -152,9 +152,12 @@ class CrossAttention(nn.Module):
     # --- cross-attention with a single context token: attn2(x, ctx) == to_out(to_v(ctx)) ---
     def composed_single_token(self):
         """(W_out @ W_v, b_out) in fp32: maps the context token straight to the block's additive vector."""
-        wo = self.to_out[0].weight.detach().double()
-        wv = self.to_v.weight.detach().double()
-        return (wo @ wv).float().contiguous(), self.to_out[0].bias.detach().float().contiguous()
+        # fp32 on the library's own small-GEMM kernel (K = inner dim <= 672, no split-K: deterministic).  This fold runs
+        # after every optimizer step of the native training loop; torch's fp64 matmul put a cuBLAS/cutlass kernel there.
+        from .... import ops_bwd
+        wo = self.to_out[0].weight.detach().float().contiguous()
+        wv = self.to_v.weight.detach().float().contiguous()
+        return ops_bwd.sgemm(wo, wv), self.to_out[0].bias.detach().float().contiguous()
 
 
 class BasicTransformerBlock(nn.Module):
