@@ -18,16 +18,24 @@
 //     the other group's Q K^T in its shadow;
 //   * P never touches shared memory: the softmax warps write it to TMEM (tcgen05.st, bf16 pairs) and P V takes its A
 //     operand from TMEM (tcgen05.mma [d], [a], b-desc); only V is read from shared memory.
+//   * sweep 2 is software-pipelined inside a softmax warp: the score row is pulled out of TMEM in two 64-column halves,
+//     the second half (and, at the end of a tile, the first half of the NEXT tile) is in flight (tcgen05.ld is asynchronous
+//     until tcgen05.wait::ld) while the exponentials of the half already in registers run, so the exponential unit -- the
+//     bound of this head size: 16 MUFU lanes per SM against 256 tensor FLOPs per score element -- is not left idle for the
+//     TMEM read latency of every tile (ncu source page of the unpipelined version: 56 % of a softmax warp's time inside
+//     the exponential block, the rest in tcgen05.ld / barrier waits; XU pipe 55 % busy).
 // TMEM per group (256 columns): S 128 | P 64 (128 bf16) | O 64.  Shared memory per group: Q 16 KB, K 3 x 16 KB, V 2 x 16 KB.
-// Roles: warps 0 / 2 = TMA producers of group 0 / 1, warps 1 / 3 = MMA issuers (warp 1 also owns the TMEM allocation), then
-// 4 * HALVES softmax warps per group (a warp touches TMEM lanes 32 (warp % 4) .. + 32).  HALVES = 2: two warps share every
-// 32-row quarter and take 64 of the 128 score columns each -- twice the warps per scheduler to hide the tcgen05.ld / MUFU
-// latencies of a tile; the row maximum and the row sum are combined through shared memory once per item.
+// Roles (384 threads): warps 0 / 2 = TMA producers of group 0 / 1, warps 1 / 3 = MMA issuers (warp 1 also owns the TMEM
+// allocation), warps 4-7 = softmax group 0, warps 8-11 = softmax group 1 (a warp touches TMEM lanes 32 (warp % 4) .. + 32).
+// Tried and dropped (gpurun_out/r2f_attn_bench.log, r2g_attn_bench.log): eight softmax warps per query tile (two per row
+// quarter, 64 columns each: 0.249 vs 0.235 ms -- they run in lock step, so no extra overlap) and a one-sweep variant with an
+// online maximum and lazy O rescale in TMEM (0.262 ms: both pipelines then want the exponential unit all the time and
+// nothing fills its gaps).
 #include "cs_host.h"
 
 namespace cs {
 
-template <int HALVES> struct T3Cfg { static constexpr int kThreads = 128 + 2 * 128 * HALVES; };
+static constexpr int kT3Threads = 384;
 static constexpr int kT3Tile = 128 * 128;   // bytes of a [128 rows][64 bf16] tile
 static constexpr int kT3KS = 3;             // K stages per group
 static constexpr int kT3VS = 2;             // V stages per group
@@ -93,19 +101,15 @@ __device__ __forceinline__ void t3_umma_ts(uint32_t tmem_d, uint32_t tmem_a, uin
       : "memory");
 }
 
-template <int HALVES>
-__global__ void __launch_bounds__(T3Cfg<HALVES>::kThreads, 1)
+__global__ void __launch_bounds__(kT3Threads, 1)
 attention_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int N,
                      int H, int o_pitch, int d_out, float scale_log2, int n_tiles, int dbg) {
-  // dbg (tuning experiments only, results are wrong): 1 = no exponentials, 8 = both groups start together (no stagger)
+  // dbg (tuning experiments only): 8 = both groups start together (no stagger)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ Atc3Bars bars2[2];
   __shared__ uint64_t go_bar;
   __shared__ uint32_t tmem_base_s;
-  __shared__ float xmax[2][2][128], xsum[2][2][128];      // HALVES == 2: per group, per column half, per row
-  constexpr int SW = 4 * HALVES;                          // softmax warps per group
-  constexpr int CW = 128 / HALVES;                        // score columns per softmax warp
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -118,11 +122,11 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       mbar_init(&b.q_full, 1); mbar_init(&b.q_empty, 1);
       for (int i = 0; i < kT3KS; ++i) { mbar_init(&b.k_full[i], 1); mbar_init(&b.k_empty[i], 1); }
       for (int i = 0; i < kT3VS; ++i) { mbar_init(&b.v_full[i], 1); mbar_init(&b.v_empty[i], 1); }
-      mbar_init(&b.s_full, 1); mbar_init(&b.s_empty, SW);
-      mbar_init(&b.p_full, SW); mbar_init(&b.p_empty, 1);
-      mbar_init(&b.o_full, 1); mbar_init(&b.o_empty, SW);
+      mbar_init(&b.s_full, 1); mbar_init(&b.s_empty, 4);
+      mbar_init(&b.p_full, 4); mbar_init(&b.p_empty, 1);
+      mbar_init(&b.o_full, 1); mbar_init(&b.o_empty, 4);
     }
-    mbar_init(&go_bar, SW);
+    mbar_init(&go_bar, 4);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -134,7 +138,7 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
 
-  const int g = (warp < 4) ? (warp >> 1) : ((warp - 4) / SW);      // which query-tile pipeline this warp serves
+  const int g = (warp < 4) ? (warp >> 1) : ((warp - 4) >> 2);      // which query-tile pipeline this warp serves
   Atc3Bars& bars = bars2[g];
   uint8_t* sQ = smem + g * kT3GroupSmem;
   uint8_t* sK = sQ + kT3Tile;
@@ -224,34 +228,31 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   } else {
     // =========================== softmax warps of group g ===========================
     const int quarter = warp & 3;
-    const int half = ((warp - 4) % SW) >> 2;                    // which CW score columns (0 when HALVES == 1)
     const int r = quarter * 32 + lane;                          // query row inside the tile = TMEM lane
-    const int gt = ((warp - 4) % SW) * 32 + lane;               // 0 .. 32 SW - 1 inside the group
+    const int gt = ((warp - 4) & 3) * 32 + lane;                // 0..127 inside the group
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
-    const uint32_t t_s = tm_s + lane_off + static_cast<uint32_t>(half * CW);
-    const uint32_t t_p = tm_p + lane_off + static_cast<uint32_t>(half * (CW / 2));
-    const uint32_t t_o = tm_o + lane_off + static_cast<uint32_t>(half * (64 / HALVES));
+    const uint32_t t_s = tm_s + lane_off, t_p = tm_p + lane_off, t_o = tm_o + lane_off;
     // output staging: the first V stage (every P V of the item has retired when it is used, and the producer cannot reach
     // the next item's first V load before these warps have released five of its sweep-1 score tiles)
     const uint32_t stage_s = smem_u32(sV);
     const uint32_t row_s = stage_s + static_cast<uint32_t>(r * 128);
     const uint32_t swz = static_cast<uint32_t>(r & 7);
     auto group_sync = [&]() {
-      if (g == 0) asm volatile("bar.sync 1, %0;" ::"n"(32 * SW) : "memory"); else asm volatile("bar.sync 2, %0;" ::"n"(32 * SW) : "memory");
+      if (g == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
     };
     int sc = 0, pc = 0, it = 0;
     for (int tile = first_tile; tile < n_tiles; tile += tile_step, ++it) {
       const int qt = tile % T, bh = tile / T;
       const int h = bh % H, b = bh / H;
       const long long row0 = static_cast<long long>(b) * N + qt * 128;            // first global token row of the tile
-      uint32_t raw[CW];
+      uint32_t ra[64], rb[64];                                  // a score row (sweep 1); sweep 2 lands 32-column quarters in ra
       // ---- sweep 1: row maximum over all keys ----
       float m = -INFINITY;
       for (int j = 0; j < T; ++j) {
         mbar_wait(&bars.s_full, sc & 1);
         tc_fence_after();
-#pragma unroll
-        for (int c = 0; c < CW / 32; ++c) t3_tmem_ld32(t_s + static_cast<uint32_t>(c * 32), raw + c * 32);
+        t3_tmem_ld32(t_s, ra); t3_tmem_ld32(t_s + 32u, ra + 32);
+        t3_tmem_ld32(t_s + 64u, rb); t3_tmem_ld32(t_s + 96u, rb + 32);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
@@ -259,83 +260,91 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         ++sc;
         float mx0 = m, mx1 = -INFINITY;
 #pragma unroll
-        for (int i = 0; i < CW; i += 4) {
-          mx0 = fmaxf(mx0, fmaxf(__uint_as_float(raw[i]), __uint_as_float(raw[i + 1])));
-          mx1 = fmaxf(mx1, fmaxf(__uint_as_float(raw[i + 2]), __uint_as_float(raw[i + 3])));
+        for (int i = 0; i < 64; i += 2) {
+          mx0 = fmaxf(mx0, fmaxf(__uint_as_float(ra[i]), __uint_as_float(ra[i + 1])));
+          mx1 = fmaxf(mx1, fmaxf(__uint_as_float(rb[i]), __uint_as_float(rb[i + 1])));
         }
         m = fmaxf(mx0, mx1);
-      }
-      if (HALVES == 2) {                                        // the other half of the columns belongs to another warp
-        xmax[g][half][r] = m;
-        group_sync();
-        m = fmaxf(m, xmax[g][half ^ 1][r]);
       }
       if (g == 0 && it == 0) {                                  // group 1 starts its first sweep 1 now
         __syncwarp();
         if (lane == 0) mbar_arrive(&go_bar);
       }
-      // ---- sweep 2: probabilities against the final maximum, P -> bf16 -> TMEM, row sum ----
+      // ---- sweep 2: probabilities against the final maximum, P -> bf16 -> TMEM, row sum; software-pipelined ----
       const float msc = m * scale_log2;
       float l0 = 0.f, l1 = 0.f;
+      mbar_wait(&bars.s_full, sc & 1);                          // first quarter of the first tile
+      tc_fence_after();
+      t3_tmem_ld32(t_s, ra);
+      uint32_t* const rq0 = ra;                                 // two 32-column landing buffers, used alternately
+      uint32_t* const rq1 = ra + 32;
       for (int j = 0; j < T; ++j) {
-        mbar_wait(&bars.s_full, sc & 1);
-        tc_fence_after();
+        uint32_t pk[64];
+        auto exp32 = [&](const uint32_t* src, uint32_t* dst) {  // 32 scores -> 16 packed bf16 pairs, row sum
 #pragma unroll
-        for (int c = 0; c < CW / 32; ++c) t3_tmem_ld32(t_s + static_cast<uint32_t>(c * 32), raw + c * 32);
+          for (int i = 0; i < 32; i += 2) {
+            const float p0 = t3_ex2(fmaf(__uint_as_float(src[i]), scale_log2, -msc));
+            const float p1 = t3_ex2(fmaf(__uint_as_float(src[i + 1]), scale_log2, -msc));
+            l0 += p0;
+            l1 += p1;
+            dst[i >> 1] = pack_bf16x2(p0, p1);
+          }
+        };
+        tmem_ld_wait();                                         // rq0 = columns 0..31 of S_j
+        t3_tmem_ld32(t_s + 32u, rq1);                           // the next quarter flies while this one is exponentiated
+        exp32(rq0, pk);
         tmem_ld_wait();
+        t3_tmem_ld32(t_s + 64u, rq0);
+        exp32(rq1, pk + 16);
+        tmem_ld_wait();
+        t3_tmem_ld32(t_s + 96u, rq1);
+        exp32(rq0, pk + 32);
+        tmem_ld_wait();                                         // the whole row of S_j has left TMEM
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars.s_empty);              // Q K^T of the next tile may overwrite S now
         ++sc;
-        uint32_t pk[CW / 2];
-#pragma unroll
-        for (int i = 0; i < CW; i += 2) {
-          float p0 = fmaf(__uint_as_float(raw[i]), scale_log2, -msc), p1 = fmaf(__uint_as_float(raw[i + 1]), scale_log2, -msc);
-          if (!(dbg & 1)) { p0 = t3_ex2(p0); p1 = t3_ex2(p1); }
-          l0 += p0;
-          l1 += p1;
-          pk[i >> 1] = pack_bf16x2(p0, p1);
+        exp32(rq1, pk + 48);                                    // Q K^T (j + 1) runs under these exponentials
+        if (j + 1 < T) {                                        // first quarter of the next tile: in flight during the P hand-off
+          mbar_wait(&bars.s_full, sc & 1);
+          tc_fence_after();
+          t3_tmem_ld32(t_s, rq0);
         }
         mbar_wait(&bars.p_empty, (pc & 1) ^ 1);                 // P V of the previous tile has consumed the P columns
         tc_fence_after();
-#pragma unroll
-        for (int c = 0; c < CW / 64; ++c) t3_tmem_st32(t_p + static_cast<uint32_t>(c * 32), pk + c * 32);
+        t3_tmem_st32(t_p, pk);
+        t3_tmem_st32(t_p + 32u, pk + 32);
         t3_tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars.p_full);
         ++pc;
       }
-      float l = l0 + l1;
-      if (HALVES == 2) {
-        xsum[g][half][r] = l;
-        group_sync();
-        l = (half == 0) ? l + xsum[g][1][r] : xsum[g][0][r] + l;     // same order in both warps
-      }
       // ---- output: O / l, staged through shared memory, written as whole rows ----
       mbar_wait(&bars.o_full, it & 1);                          // every P V of this item has retired
       tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < 2 / HALVES; ++c) t3_tmem_ld32(t_o + static_cast<uint32_t>(c * 32), raw + c * 32);
+      t3_tmem_ld32(t_o, ra);
+      t3_tmem_ld32(t_o + 32u, ra + 32);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars.o_empty);
+      const float l = l0 + l1;
       const float inv = 1.f / l;
-      if (lse && half == 0) lse[(static_cast<long long>(b) * H + h) * N + qt * 128 + r] = msc + log2f(l);
+      if (lse) lse[(static_cast<long long>(b) * H + h) * N + qt * 128 + r] = msc + log2f(l);
 #pragma unroll
-      for (int chunk = 0; chunk < 8 / HALVES; ++chunk) {
-        const uint32_t ux = pack_bf16x2(__uint_as_float(raw[chunk * 8 + 0]) * inv, __uint_as_float(raw[chunk * 8 + 1]) * inv);
-        const uint32_t uy = pack_bf16x2(__uint_as_float(raw[chunk * 8 + 2]) * inv, __uint_as_float(raw[chunk * 8 + 3]) * inv);
-        const uint32_t uz = pack_bf16x2(__uint_as_float(raw[chunk * 8 + 4]) * inv, __uint_as_float(raw[chunk * 8 + 5]) * inv);
-        const uint32_t uw = pack_bf16x2(__uint_as_float(raw[chunk * 8 + 6]) * inv, __uint_as_float(raw[chunk * 8 + 7]) * inv);
-        t3_st_shared_v4(row_s + ((static_cast<uint32_t>(chunk + half * (8 / HALVES)) ^ swz) << 4), ux, uy, uz, uw);
+      for (int chunk = 0; chunk < 8; ++chunk) {
+        const uint32_t ux = pack_bf16x2(__uint_as_float(ra[chunk * 8 + 0]) * inv, __uint_as_float(ra[chunk * 8 + 1]) * inv);
+        const uint32_t uy = pack_bf16x2(__uint_as_float(ra[chunk * 8 + 2]) * inv, __uint_as_float(ra[chunk * 8 + 3]) * inv);
+        const uint32_t uz = pack_bf16x2(__uint_as_float(ra[chunk * 8 + 4]) * inv, __uint_as_float(ra[chunk * 8 + 5]) * inv);
+        const uint32_t uw = pack_bf16x2(__uint_as_float(ra[chunk * 8 + 6]) * inv, __uint_as_float(ra[chunk * 8 + 7]) * inv);
+        t3_st_shared_v4(row_s + ((static_cast<uint32_t>(chunk) ^ swz) << 4), ux, uy, uz, uw);
       }
       group_sync();
       __nv_bfloat16* og = out + row0 * o_pitch + h * d_out;
 #pragma unroll
-      for (int i = 0; i < 8 / HALVES; ++i) {
-        const int idx = i * (32 * SW) + gt;
+      for (int i = 0; i < 8; ++i) {
+        const int idx = i * 128 + gt;
         const int rr = idx >> 3, ch = idx & 7;
         if (ch * 8 < d_out) {                                  // d_out % 8 == 0 on this path (host-checked)
           const uint4 u = t3_ld_shared_v4(stage_s + static_cast<uint32_t>(rr * 128 + ((ch ^ (rr & 7)) << 4)));
@@ -372,21 +381,15 @@ int attention_tc3_launch(const void* q, const void* k, const void* v, void* out,
   const int smem = 2 * kT3GroupSmem + 1024;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(attention_tc3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(attention_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return set_cuda_error(e, "attention_tc3: cudaFuncSetAttribute");
     attr = true;
   }
   const int n_tiles = B * H * (N / 128);
   const int pairs = (n_tiles + 1) / 2;
   const int grid = pairs < num_sms() ? pairs : num_sms();
-  const int dbg = (igemm_debug_flags() >> 16) & 15;
-  if (dbg & 2)      // A/B timing: four softmax warps per query tile (one per 32-row quarter, 128 columns each)
-    attention_tc3_kernel<1><<<grid, T3Cfg<1>::kThreads, smem, st>>>(tq, tk, tv, reinterpret_cast<__nv_bfloat16*>(out), lse, N, H, o_pitch,
-                                                                    d_out, scale * 1.4426950408889634f, n_tiles, dbg);
-  else
-    attention_tc3_kernel<2><<<grid, T3Cfg<2>::kThreads, smem, st>>>(tq, tk, tv, reinterpret_cast<__nv_bfloat16*>(out), lse, N, H, o_pitch,
-                                                                    d_out, scale * 1.4426950408889634f, n_tiles, dbg);
+  attention_tc3_kernel<<<grid, kT3Threads, smem, st>>>(tq, tk, tv, reinterpret_cast<__nv_bfloat16*>(out), lse, N, H, o_pitch, d_out,
+                                                       scale * 1.4426950408889634f, n_tiles, (igemm_debug_flags() >> 16) & 15);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error(e, "attention_tc3: launch");
   count_launch();

@@ -7,7 +7,7 @@ B, H, N, d, dp = 64, 8, 1024, 56, 64
 qkv = torch.randn(B, N, 3 * H * dp, device="cuda").to(torch.bfloat16)
 q, k, v = (qkv[:, :, i * H * dp:(i + 1) * H * dp] for i in range(3))
 fl = 4.0 * B * H * N * N * d
-for name, flag in (("tcgen05 gen 3 (staggered, P in TMEM)", 0), ("gen 3, four softmax warps per tile", 2 << 16), ("gen 3, no stagger", 8 << 16), ("gen 3, no exponentials", 1 << 16),
+for name, flag in (("tcgen05 gen 3 (staggered pipelines, P in TMEM)", 0), ("gen 3, no stagger", 8 << 16),
                    ("tcgen05 two-sweep (gen 2)", 32768), ("tcgen05 gen 1", 16384), ("mma.sync", 128)):
     _lib.load().cs_debug_set(flag)
     for _ in range(3):
@@ -19,7 +19,7 @@ for name, flag in (("tcgen05 gen 3 (staggered, P in TMEM)", 0), ("gen 3, four so
         o = ops.attention(q, k, v, heads=H, head_dim=d, head_dim_padded=dp, scale=d ** -0.5)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 10
-    print(f"{name:38s}: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s (unpadded FLOPs)")
+    print(f"{name:46s}: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s (unpadded FLOPs)")
     if flag == 0:
         o_tc = o.float()
     else:

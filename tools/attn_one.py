@@ -1,5 +1,5 @@
 """One launch of the N = 1024 self-attention core at the cfg2 batch (B = 64, 8 heads, d = 56 padded to 64) for `ncu --set full`:
-    ncu --set full --clock-control none --import-source on -k regex:attention_tc3 -s 3 -c 1 -o gpurun_out/x python tools/attn_one.py"""
+    ncu --set full --clock-control none --import-source on -k regex:attention_tc -s 3 -c 1 -o gpurun_out/x python tools/attn_one.py"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
