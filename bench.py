@@ -19,6 +19,8 @@ process after the headline loop:
   `train` — BASELINE cfg3/cfg4: the data-parallel denoiser training step (32 objects per rank; re-pack, forward,
             backward, bucketed NCCL all-reduce of the fp32 gradients overlapped with the backward, clip, AdamW) in ONE
             CUDA graph — the path that HAS a collective;
+  `train_branch` — the same with everything around it: scene graphs -> GCN-E2 + rel_mlp -> frozen VQ-VAE encode of the 64^3
+            SDFs -> denoiser -> gradient back into the graph networks -> both optimizers, also ONE CUDA graph;
   `cfg5`  — BASELINE cfg5's scene: 10 objects, guided DDIM S=100 + VQ-VAE decode to 64^3, the 20 forwards of each step
             split across the ranks (CFG-pair split, one all_gather of eps per step).
 
@@ -206,8 +208,9 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from commonscenes_b200 import _lib, ops, parallel
-    from commonscenes_b200.model.sdfusion_txt2shape_model import SDFusionText2ShapeModel, default_opt
-    from commonscenes_b200.train import DenoiserTrainStep
+    from commonscenes_b200.model.sdfusion_txt2shape_model import default_opt
+    from commonscenes_b200.model.VAEGAN_V2FULL import Sg2ScVAEModel
+    from commonscenes_b200.train import ShapeBranchTrainStep
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -219,7 +222,12 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     torch.manual_seed(111)                              # identical weights on every rank (data-parallel replicas)
 
-    model = SDFusionText2ShapeModel(default_opt(device=f"cuda:{local}"))     # denoiser + frozen VQ-VAE, reference wiring
+    # the v2_full scene model around the denoiser (GCN-E2 + rel_mlp + embeddings: 11 M parameters) -- its shape branch is what
+    # the `train_branch` block steps; every other block uses its .Diff (denoiser + frozen VQ-VAE, reference wiring)
+    vocab = {"object_idx_to_name": [f"o{i}" for i in range(36)], "pred_idx_to_name": [f"p{i}" for i in range(16)]}
+    scene = Sg2ScVAEModel(vocab, diff_opt=default_opt(device=f"cuda:{local}"), embedding_dim=64, mlp_normalization="batch",
+                          residual=True, gconv_num_layers=5).to(torch.device("cuda", local))
+    model = scene.Diff
     df = model.df
     with torch.no_grad():
         for p in df.parameters():                       # the reference zero-inits 18 convs: give them weights
@@ -337,10 +345,11 @@ def run_ours(args):
         del sdf5, data5
 
     # ---- train: the data-parallel denoiser training step (cfg3 / cfg4), one CUDA graph incl. the NCCL all-reduces ----
-    train = None
+    train = train_branch = None
     if not args.no_train:
         per_rank = 32
-        stepper = DenoiserTrainStep(model)
+        branch = ShapeBranchTrainStep(scene)
+        stepper = branch.denoiser
         z = torch.randn(per_rank, 3, 16, 16, 16, device=dev)
         ctx = torch.randn(per_rank, 1, 1280, device=dev)
         stepper.capture(per_rank, 1280)
@@ -368,6 +377,41 @@ def run_ours(args):
                  "allreduce_dtype": "f32", "bucket_mb": 256, "buckets": len(stepper.buckets),
                  "algorithmic_tflops": 3 * per_rank * world * UNET_GFLOP_PER_SAMPLE / ms_train,
                  "replicas_identical": same, "loss": float(loss_t), "peak_mem_gib": torch.cuda.max_memory_allocated() / 2 ** 30}
+        del stepper.graph
+        stepper.graph = None
+
+        # ---- train_branch: the WHOLE v2_full shape-branch iteration (cfg3 per rank, cfg4 at 8 ranks) as one CUDA graph ----
+        # per rank 4 scenes x 8 objects with 12 edges each; every rank runs the (tiny) graph networks on the global batch so that
+        # BatchNorm statistics equal the single-process ones, and the denoiser on its own 32 objects
+        scenes, per_scene, edges = 4 * world, 8, 12
+        gb = torch.Generator().manual_seed(4242)                      # identical batch on every rank
+        O_g, T_g = scenes * per_scene, scenes * edges
+        sub = torch.randint(0, per_scene, (scenes, edges), generator=gb)
+        obj = (sub + torch.randint(1, per_scene, (scenes, edges), generator=gb)) % per_scene
+        off = (torch.arange(scenes) * per_scene).view(-1, 1)
+        triples = torch.stack([sub + off, torch.randint(1, 16, (scenes, edges), generator=gb), obj + off], dim=-1).view(T_g, 3).to(dev)
+        objs = torch.randint(1, 36, (O_g,), generator=gb).to(dev)
+        zl, text, relf = (torch.randn(n, d_, generator=gb).to(dev) for n, d_ in ((O_g, 64), (O_g, 512), (T_g, 512)))
+        sdfs = (torch.randn(O_g, 1, 64, 64, 64, generator=gb) * 0.1).clamp_(-0.2, 0.2).to(dev)
+        branch.capture(O_g, T_g)
+        for _ in range(3):
+            branch.step_graphed(zl, objs, triples, text, relf, sdfs)
+        barrier()
+        e0.record()
+        for _ in range(k_train):
+            loss_b, _ = branch.step_graphed(zl, objs, triples, text, relf, sdfs)
+        e1.record()
+        barrier()
+        (ms_branch,) = max_over_ranks(e0.elapsed_time(e1) / k_train)
+        train_branch = {"workload": "BASELINE cfg3 (per rank) / cfg4 (8 ranks): whole v2_full shape-branch iteration -- scene graphs (4 scenes x "
+                                    "8 objects, 12 edges each, per rank) -> GCN-E2 + rel_mlp (train-mode BatchNorm) -> frozen VQ-VAE encode of 64^3 "
+                                    "SDFs -> denoiser fwd/bwd -> gradient back into the graph networks -> clip + AdamW on both groups, one CUDA graph",
+                        "ms_per_step": ms_branch, "objects_per_s": per_rank * world * 1000.0 / ms_branch, "scenes_per_s": scenes * 1000.0 / ms_branch,
+                        "global_objects": O_g, "global_triples": T_g, "objects_per_rank": per_rank,
+                        "collectives": (f"{len(stepper.buckets)} bucketed all-reduces of the denoiser gradients ({int(stepper.flat_g.numel()) * 4} B fp32) "
+                                        f"+ 1 of the graph-side gradients ({int(branch.graph_params.flat_g.numel()) * 4} B)")
+                                       if world > 1 else "none (one rank)",
+                        "loss": float(loss_b), "finite": bool(torch.isfinite(loss_b))}
 
     ms_total, ms_e2e = max_over_ranks(ms_total, ms_e2e)
 
@@ -424,6 +468,8 @@ def run_ours(args):
     }
     if train is not None:
         line["train"] = train
+    if train_branch is not None:
+        line["train_branch"] = train_branch
     if cfg5 is not None:
         line["cfg5"] = cfg5
     if world == 1 and not args.no_cpu_baseline:

@@ -363,3 +363,89 @@ class ShapeBranchTrainStep:
             dist.all_reduce(g.flat_g, op=dist.ReduceOp.SUM, group=self.group)
         g.clip_and_step(max_norm=self.max_grad_norm, grad_scale=1.0 / self.world, **self.hp)
         return loss, d_z
+
+    # ------------------------------------------------------------------------------------------
+    def capture(self, n_objs: int, n_triples: int, n_rows: Optional[int] = None, z_dim: int = 64, clip_dim: int = 512,
+                sdf_res: int = 64, warmup: int = 2) -> None:
+        """Capture the WHOLE iteration -- encoder_2 forward, frozen VQ-VAE encode, denoiser re-pack / forward / backward with
+        its bucketed all-reduce, the graph-side backward and its all-reduce, clip + AdamW of both groups -- into ONE CUDA
+        graph for a fixed batch geometry (n_objs objects, n_triples triples, n_rows of them entering the denoiser on this
+        rank; default: this rank's block).  Eager, the iteration is host-launch bound (~2300 launches; 107 ms against 82 ms
+        for the graphed denoiser part alone on 4 GPUs).  Inputs are copied into static buffers by step_graphed().  The
+        warm-up iterations run on zeros and are rolled back: both flat parameter groups, their moments and step counters,
+        and every module buffer (BatchNorm running statistics)."""
+        m = self.model
+        dev = self.graph_params.flat_p.device
+        if n_rows is None:
+            lo, hi = self.shard(n_objs)
+            rows = torch.arange(lo, hi, device=dev)
+            n_total = n_objs
+        else:
+            rows = torch.arange(n_rows, device=dev)
+            n_total = n_rows * self.world
+        zs = tuple(m.Diff.z_shape)
+        self._s = dict(z=torch.zeros(n_objs, z_dim, device=dev), objs=torch.zeros(n_objs, dtype=torch.int64, device=dev),
+                       triples=torch.zeros(n_triples, 3, dtype=torch.int64, device=dev),
+                       text=torch.zeros(n_objs, clip_dim, device=dev), rel=torch.zeros(n_triples, clip_dim, device=dev),
+                       sdfs=torch.zeros(n_objs, 1, sdf_res, sdf_res, sdf_res, device=dev), rows=rows,
+                       t=torch.zeros(rows.shape[0], dtype=torch.int64, device=dev),
+                       noise=torch.zeros((rows.shape[0],) + zs, device=dev))
+        self._s_total = n_total
+        d, gp = self.denoiser, self.graph_params
+        saved = [t.clone() for t in (d.flat_p, d.flat_m, d.flat_v, d.step_dev, gp.flat_p, gp.flat_m, gp.flat_v, gp.step_dev)]
+        saved_count = d.step_count
+        bufs = {n: b.clone() for n, b in m.named_buffers()}
+
+        def restore():
+            for dst, src in zip((d.flat_p, d.flat_m, d.flat_v, d.step_dev, gp.flat_p, gp.flat_m, gp.flat_v, gp.step_dev), saved):
+                dst.copy_(src)
+            d.step_count = saved_count
+            with torch.no_grad():
+                for n, b in m.named_buffers():
+                    b.copy_(bufs[n])
+
+        def run():
+            st = self._s
+            return self.step(st["z"], st["objs"], st["triples"], st["text"], st["rel"], st["sdfs"], rows=st["rows"], t=st["t"],
+                             noise=st["noise"], n_total=self._s_total)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                run()
+        torch.cuda.current_stream().wait_stream(side)
+        restore()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._gout = run()
+        restore()                       # capture does not execute, but step() bumped the host-side counters
+        d.unet._packed = None
+        self.graph = g
+
+    def step_graphed(self, z, objs, triples, text_feat, rel_feat, sdfs, rows: Optional[torch.Tensor] = None,
+                     t: Optional[torch.Tensor] = None, noise: Optional[torch.Tensor] = None):
+        """step() through the captured graph (capture() first, same geometry).  rows: which objects enter the denoiser on this
+        rank (same count as captured; default: the captured rows).  Returns (loss, d_z): overwritten by the next replay."""
+        if getattr(self, "graph", None) is None:
+            raise RuntimeError("ShapeBranchTrainStep.step_graphed: call capture() first")
+        st = self._s
+        for key, src in (("z", z), ("objs", objs), ("triples", triples), ("text", text_feat), ("rel", rel_feat), ("sdfs", sdfs)):
+            if tuple(src.shape) != tuple(st[key].shape):
+                raise ValueError(f"step_graphed: {key} has shape {tuple(src.shape)}, captured {tuple(st[key].shape)}")
+            st[key].copy_(src)
+        if rows is not None:
+            if tuple(rows.shape) != tuple(st["rows"].shape):
+                raise ValueError("step_graphed: the number of denoiser rows is part of the captured geometry")
+            st["rows"].copy_(rows)
+        if t is None:
+            torch.randint(0, self.model.Diff.num_timesteps, st["t"].shape, device=st["t"].device, out=st["t"])
+        else:
+            st["t"].copy_(t)
+        if noise is None:
+            st["noise"].normal_()
+        else:
+            st["noise"].copy_(noise)
+        self.graph.replay()
+        self.denoiser.step_count += 1
+        self.denoiser.unet._packed = None       # weights were updated in place by raw-pointer kernels (see DenoiserTrainStep)
+        return self._gout

@@ -98,3 +98,42 @@ def test_shape_branch_loss_decreases_over_steps():
         losses.append(loss.item())
     print("losses:", [f"{l:.4f}" for l in losses])
     assert losses[-1] < losses[0]
+
+
+def test_graphed_whole_iteration_equals_eager():
+    """ShapeBranchTrainStep.capture / step_graphed: the whole cfg3 iteration as ONE CUDA graph.  Two models with identical
+    weights take two steps each on identical inputs, one eagerly and one through the graph: same losses (the forward is
+    deterministic), parameters equal up to the order of the bf16 / fp32 atomics inside the denoiser's weight gradients, and
+    the BatchNorm running statistics -- touched by the warm-up iterations, then rolled back -- identical."""
+    from commonscenes_b200.train import ShapeBranchTrainStep
+    batches = [{k: v.cuda() for k, v in _scene_batch(2, 4, 6, 36, 16, seed=s).items()} for s in (11, 12)]
+    O, T = batches[0]["objs"].shape[0], batches[0]["triples"].shape[0]
+    g = torch.Generator().manual_seed(9)
+    ts = [torch.randint(0, 1000, (O,), generator=g).cuda() for _ in range(2)]
+    noises = [torch.randn(O, 3, 16, 16, 16, generator=g).cuda() for _ in range(2)]
+    me, mg = _model(55), _model(55)
+    eager, graphed = ShapeBranchTrainStep(me), ShapeBranchTrainStep(mg)
+    graphed.capture(O, T)
+    assert torch.equal(eager.graph_params.flat_p, graphed.graph_params.flat_p)          # warm-up rolled back
+    assert torch.equal(eager.denoiser.flat_p, graphed.denoiser.flat_p)
+    for (n1, b1), (n2, b2) in zip(me.named_buffers(), mg.named_buffers()):
+        assert n1 == n2 and torch.equal(b1, b2), n1
+    for i, b in enumerate(batches):
+        le, dze = eager.step(b["z"], b["objs"], b["triples"], b["text"], b["rel"], b["sdfs"], t=ts[i], noise=noises[i])
+        lg, dzg = graphed.step_graphed(b["z"], b["objs"], b["triples"], b["text"], b["rel"], b["sdfs"], t=ts[i], noise=noises[i])
+        le, lg = float(le), float(lg)
+        print(f"step {i}: eager loss {le:.6f}, graphed loss {lg:.6f}")
+        # step 0 starts from identical weights: same loss (deterministic forward); gradients differ only by the order of the
+        # atomics in the denoiser's weight / context gradients (two EAGER runs differ by 1.7e-3 in d_z too, tools/dbg_graph.py).
+        # Afterwards AdamW's normalised update amplifies those differences (measured: 10 % in d_z at step 1), so only the
+        # loss is compared there.
+        assert abs(le - lg) <= (1e-6 if i == 0 else 1e-2) * abs(le)
+        if i == 0:
+            assert float((dze - dzg).norm()) <= 1e-2 * float(dze.norm()) + 1e-8
+            pe, pg = eager.graph_params.flat_p, graphed.graph_params.flat_p
+            assert float((pe - pg).norm()) <= 1e-3 * float(pe.norm())
+            de, dg = eager.denoiser.flat_p, graphed.denoiser.flat_p
+            assert float((de - dg).norm()) <= 1e-3 * float(de.norm())
+        assert torch.isfinite(dzg).all()
+    assert int(eager.denoiser.step_dev) == int(graphed.denoiser.step_dev) == 2
+    assert int(mg.rel_mlp[1].num_batches_tracked) == int(me.rel_mlp[1].num_batches_tracked) == 4
