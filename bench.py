@@ -337,12 +337,23 @@ def run_ours(args):
         e1.record()
         barrier()
         (ms5,) = max_over_ranks(e0.elapsed_time(e1))
+        # the same scene with the full 1000-step ancestral DDPM chain BASELINE cfg5 names (not a reference capability: the
+        # reference samples with DDIM only; parity of this sampler is unpinned by construction)
+        parallel.rel2shape_pair_sharded(model, data5, uc_scale=3.0, seed=7, sampler="ddpm", ddpm_timesteps=10)     # warm-up
+        barrier()
+        e0.record()
+        sdf5p = parallel.rel2shape_pair_sharded(model, data5, uc_scale=3.0, seed=7, sampler="ddpm")
+        e1.record()
+        barrier()
+        (ms5p,) = max_over_ranks(e0.elapsed_time(e1))
         units = [hi - lo for lo, hi in parallel.pair_units(n5, world)]
-        cfg5 = {"workload": "BASELINE cfg5 scene: 10 objects, guided DDIM S=100 (scale 3) + VQ-VAE decode to 64^3", "seconds": ms5 / 1e3,
-                "objects_per_s": n5 / (ms5 / 1e3), "forwards_per_rank_per_step": units,
+        cfg5 = {"workload": "BASELINE cfg5 scene: 10 objects, guided DDIM S=100 (scale 3) + VQ-VAE decode to 64^3; ddpm_*: the same scene "
+                            "with 1000 ancestral DDPM steps", "seconds": ms5 / 1e3,
+                "objects_per_s": n5 / (ms5 / 1e3), "ddpm_seconds": ms5p / 1e3, "ddpm_object_steps_per_s": 1000 * n5 / (ms5p / 1e3),
+                "ddpm_finite": bool(torch.isfinite(sdf5p).all()), "forwards_per_rank_per_step": units,
                 "collective": "one all_gather of eps (48 KiB per forward) per step" if world > 1 else "none (one rank)",
                 "finite": bool(torch.isfinite(sdf5).all()), "shape": list(sdf5.shape)}
-        del sdf5, data5
+        del sdf5, sdf5p, data5
 
     # ---- train: the data-parallel denoiser training step (cfg3 / cfg4), one CUDA graph incl. the NCCL all-reduces ----
     train = train_branch = None
