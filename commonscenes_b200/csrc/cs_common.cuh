@@ -264,6 +264,16 @@ __device__ __forceinline__ void stat_group_mean_rstd(int b, int g, int cpg, long
 // ----------------------------------------------------------------------------------------------
 // x * sigmoid(x); approximate division (MUFU.RCP + FMUL, <= 2 ulp) keeps the bandwidth-bound kernels off the issue limit
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.f + __expf(-x)); }
+// x * sigmoid(x) = h + h tanh(h), h = x / 2: ONE MUFU op (tanh.approx, relative error 2^-11) instead of two (ex2 + rcp) and
+// half the FP instructions -- for the streaming GroupNorm-apply pass, whose bf16 output rounds at 2^-9.  Absolute error
+// <= |x| * 2.4e-4 (the cancellation in 1 + tanh(h) for very negative x costs relative, not absolute, accuracy there:
+// silu(-8) = -2.7e-3 is returned within 2e-3, the size of a bf16 ulp of the O(1) activations around it).
+__device__ __forceinline__ float silu_tanh_f(float x) {
+  const float h = 0.5f * x;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
 __device__ __forceinline__ float gelu_erf_f(float x) {
   return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
 }

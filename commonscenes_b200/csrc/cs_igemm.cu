@@ -460,7 +460,7 @@ int igemm_launch(const IgemmArgs& a, cudaStream_t stream) {
   // tiles that span several samples (tiny grids) can use the fast epilogue when nothing in it is per-sample
   p.fast_epilogue = (p.out_mode == CS_OUT_BF16_NDHWC && a.Cout % 8 == 0 && (p.bb == 1 || (!p.rowvec && !p.stat_sum))) ? 1 : 0;
   // Pair mode (two 128-voxel accumulators per CTA share every weight slab): the main loop is bound by the rate at
-  // which one SM can ingest operands (~90 B/clk measured: profiles/r1_tma_ingest.txt), and pairing cuts the bytes per
+  // which one SM can ingest operands (~90 B/clk measured: profiles/r1_experiments.txt, "TMA producer only"), and pairing cuts the bytes per
   // MMA cycle from (16 + BN/8) KB / (BN/2 + ..) to 0.68x.  It gives up the TMEM double buffer (exposed epilogue), so it
   // is used for long K loops (3x3x3 convs) when the halved tile count still fills the 148 SMs well.
   const int kiters = a.kd * a.kh * a.kw * ((a.C1 + 63) / 64 + (a.C2 + 63) / 64);

@@ -168,7 +168,8 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x, int S, int 
 __global__ void gn_apply_fused_kernel(const __nv_bfloat16* __restrict__ x, int S, int C, int pitch, int ch_off,
                                       const long long* __restrict__ stat1, int C1, const long long* __restrict__ stat2, int C2,
                                       const float* __restrict__ gamma, const float* __restrict__ beta, int groups,
-                                      float eps, __nv_bfloat16* __restrict__ y, int y_pitch, int act, int vox_per_cta) {
+                                      float eps, __nv_bfloat16* __restrict__ y, int y_pitch, int act, int vox_per_cta,
+                                      int exact_silu) {
   __shared__ float g_mean[64], g_rstd[64];
   const int b = blockIdx.y;
   const int Ct = C1 + C2;
@@ -202,8 +203,9 @@ __global__ void gn_apply_fused_kernel(const __nv_bfloat16* __restrict__ x, int S
     for (int j = 0; j < 4; ++j) {
       const float2 f = unpack_bf16x2(w[j]);
       float y0 = fmaf(f.x, a[2 * j].x, a[2 * j].y), y1 = fmaf(f.y, a[2 * j + 1].x, a[2 * j + 1].y);
-      if (act == CS_ACT_SILU) { y0 = silu_f(y0); y1 = silu_f(y1); }
-      else if (act == CS_ACT_GELU) { y0 = gelu_erf_fast(y0); y1 = gelu_erf_fast(y1); }
+      if (act == CS_ACT_SILU) {
+        if (exact_silu) { y0 = silu_f(y0); y1 = silu_f(y1); } else { y0 = silu_tanh_f(y0); y1 = silu_tanh_f(y1); }
+      } else if (act == CS_ACT_GELU) { y0 = gelu_erf_fast(y0); y1 = gelu_erf_fast(y1); }
       o[j] = pack_bf16x2(y0, y1);
     }
     *reinterpret_cast<uint4*>(yb + static_cast<long long>(i) * y_pitch) = make_uint4(o[0], o[1], o[2], o[3]);
@@ -395,6 +397,8 @@ int layernorm_launch(const void* x, long long M, int C, int pitch, const float* 
   return CS_OK;
 }
 
+int igemm_debug_flags();
+
 int gn_apply_fused_launch(const void* x, int B, int S, int C, int pitch, int ch_off, const long long* stat1, int C1,
                           const long long* stat2, int C2, const float* gamma, const float* beta, int groups, float eps, void* y,
                           int y_pitch, int act, cudaStream_t st) {
@@ -414,7 +418,7 @@ int gn_apply_fused_launch(const void* x, int B, int S, int C, int pitch, int ch_
   splits = (S + vox - 1) / vox;
   gn_apply_fused_kernel<<<dim3(splits, B), threads, 0, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(x), S, C, pitch, ch_off, stat1, C1, stat2, stat2 ? C2 : 0, gamma, beta, groups,
-      eps, reinterpret_cast<__nv_bfloat16*>(y), y_pitch, act, vox);
+      eps, reinterpret_cast<__nv_bfloat16*>(y), y_pitch, act, vox, (igemm_debug_flags() >> 21) & 1);   // debug bit 21: ex2 + rcp SiLU (A/B)
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error(e, "groupnorm_apply_fused: launch");
   count_launch();

@@ -31,6 +31,7 @@ class DDIMSampler(object):
         self.use_cuda_graph = use_cuda_graph
         self.max_graphs = int(kwargs.get("max_graphs", 4))
         self._graphs = {}                               # (x shape, batch, weight generation) -> captured evaluation, LRU order
+        self._frozen = False
 
     def make_schedule(self, ddim_num_steps, ddim_discretize="uniform", ddim_eta=0., verbose=True):
         self.ddim_timesteps = make_ddim_timesteps(ddim_discr_method=ddim_discretize, num_ddim_timesteps=ddim_num_steps,
@@ -59,6 +60,22 @@ class DDIMSampler(object):
             return None, ctx.float().contiguous()
         return self._unet().context_vectors(ctx), None
 
+    def frozen_weights(self):
+        """Context manager for a sampling trajectory: the UNet's packed-weight cache is validated ONCE (walking the 496
+        parameters' versions costs ~0.4 ms of host time, which a 1000-step chain on a small per-rank batch cannot hide);
+        weights must not change inside the block."""
+        sampler = self
+
+        class _Frozen:
+            def __enter__(self_inner):
+                sampler._unet()._ensure_packed()
+                self_inner.prev, sampler._frozen = sampler._frozen, True
+
+            def __exit__(self_inner, *exc):
+                sampler._frozen = self_inner.prev
+                return False
+        return _Frozen()
+
     def _eps(self, x, t_dev, ca_vecs, concat=None):
         """One UNet evaluation for the whole (guided) batch, optionally through a cached CUDA graph."""
         unet = self._unet()
@@ -70,7 +87,8 @@ class DDIMSampler(object):
         call = (lambda a, b, c: unet(a, b)) if concat is not None else (lambda a, b, c: unet(a, b, context_vecs=c, shared_prefix=shared))
         if not self.use_cuda_graph:
             return call(x, t_dev, ca_vecs)
-        unet._ensure_packed()
+        if not self._frozen:            # inside frozen_weights() the packing was checked once for the whole trajectory
+            unet._ensure_packed()
         key = (tuple(x.shape), t_dev.shape[0], unet._pack_generation)
         g = self._graphs.get(key)
         if g is None:
@@ -138,18 +156,19 @@ class DDIMSampler(object):
         guided = unconditional_conditioning is not None and unconditional_guidance_scale != 1.
         ca_vecs, concat = self._conditioning(cond, unconditional_conditioning, guided)     # once per trajectory
         t_dev = torch.empty(2 * b if guided else b, dtype=torch.int64, device=device)
-        for i, step in enumerate(time_range):
-            index = total_steps - i - 1
-            t_dev.fill_(int(step))
-            img, pred_x0 = self._step(img, t_dev, ca_vecs, index, guided, float(unconditional_guidance_scale), temperature,
-                                      concat=concat)
-            if callback:
-                callback(i)
-            if img_callback:
-                img_callback(pred_x0, i)
-            if index % log_every_t == 0 or index == total_steps - 1:
-                intermediates["x_inter"].append(img)
-                intermediates["pred_x0"].append(pred_x0)
+        with self.frozen_weights():
+            for i, step in enumerate(time_range):
+                index = total_steps - i - 1
+                t_dev.fill_(int(step))
+                img, pred_x0 = self._step(img, t_dev, ca_vecs, index, guided, float(unconditional_guidance_scale), temperature,
+                                          concat=concat)
+                if callback:
+                    callback(i)
+                if img_callback:
+                    img_callback(pred_x0, i)
+                if index % log_every_t == 0 or index == total_steps - 1:
+                    intermediates["x_inter"].append(img)
+                    intermediates["pred_x0"].append(pred_x0)
         return img, intermediates
 
     def _step(self, x, t_dev, ca_vecs, index, guided, scale, temperature=1., want_pred_x0=True, concat=None):

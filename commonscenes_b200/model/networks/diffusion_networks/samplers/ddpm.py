@@ -53,18 +53,19 @@ class DDPMSampler(DDIMSampler):
         t_dev = torch.empty(2 * batch_size if guided else batch_size, dtype=torch.int64, device=device)
         intermediates = {"x_inter": [img], "pred_x0": [img]}
         total = self.ddim_timesteps.shape[0]
-        for i, t in enumerate(self.ddim_timesteps[::-1]):
-            t = int(t)
-            t_dev.fill_(t)
-            img, pred_x0 = self.p_sample(img, t_dev, ca_vecs, t, guided, float(unconditional_guidance_scale), temperature,
-                                         generator=generator, concat=concat)
-            if callback:
-                callback(i)
-            if img_callback:
-                img_callback(pred_x0, i)
-            if t % log_every_t == 0 or t == total - 1:
-                intermediates["x_inter"].append(img)
-                intermediates["pred_x0"].append(pred_x0)
+        with self.frozen_weights():
+            for i, t in enumerate(self.ddim_timesteps[::-1]):
+                t = int(t)
+                t_dev.fill_(t)
+                img, pred_x0 = self.p_sample(img, t_dev, ca_vecs, t, guided, float(unconditional_guidance_scale), temperature,
+                                             generator=generator, concat=concat)
+                if callback:
+                    callback(i)
+                if img_callback:
+                    img_callback(pred_x0, i)
+                if t % log_every_t == 0 or t == total - 1:
+                    intermediates["x_inter"].append(img)
+                    intermediates["pred_x0"].append(pred_x0)
         return img, intermediates
 
     def p_sample(self, x, t_dev, ca_vecs, t: int, guided: bool, scale: float, temperature=1., noise=None, generator=None,

@@ -134,18 +134,26 @@ def rel2shape_pair_sharded(diff_model, data: dict, ddim_steps: int = 100, ddim_e
     ca = ca_all[lo:hi].contiguous()
     obj_of_unit = units % n
     t_dev = torch.empty(hi - lo, dtype=torch.int64, device=dev)
-    for step, index in order:
-        if hi > lo:
-            t_dev.fill_(step)
-            eps_local = s._eps(x.index_select(0, obj_of_unit), t_dev, ca)
-        else:
-            eps_local = x.new_zeros((0,) + tuple(x.shape[1:]))
-        eps = exchange_eps(eps_local.float(), n, group)                                      # the path's collective
-        sigma = float(s.ddim_sigmas[index])
-        noise = torch.randn(x.shape, device=dev, generator=gen) if sigma > 0 else None
-        x, _ = ops.ddim_step(x, eps.contiguous(), guided=True, scale=float(uc_scale), a_t=float(s.ddim_alphas[index]),
-                             a_prev=float(s.ddim_alphas_prev[index]), sigma=sigma,
-                             sqrt_one_minus_at=float(s.ddim_sqrt_one_minus_alphas[index]), noise=noise, want_pred_x0=False)
+    # the exchange step: every rank's eps rows, padded to the largest block, land in ONE pre-allocated buffer through a
+    # single all_gather_into_tensor; `take` maps the (world * max_n) padded rows back to the (2 n) [uncond; cond] order
+    bounds = pair_units(n, world)
+    max_n = max(b_hi - b_lo for b_lo, b_hi in bounds)
+    row_shape = tuple(x.shape[1:])
+    send = torch.zeros((max_n,) + row_shape, dtype=torch.float32, device=dev)
+    recv = torch.empty((world * max_n,) + row_shape, dtype=torch.float32, device=dev)
+    take = torch.tensor([r * max_n + i for r, (b_lo, b_hi) in enumerate(bounds) for i in range(b_hi - b_lo)], dtype=torch.int64, device=dev)
+    with s.frozen_weights():
+        for step, index in order:
+            if hi > lo:
+                t_dev.fill_(step)
+                send[:hi - lo].copy_(s._eps(x.index_select(0, obj_of_unit), t_dev, ca))
+            dist.all_gather_into_tensor(recv, send, group=group)                                 # the path's collective
+            eps = recv.index_select(0, take)
+            sigma = float(s.ddim_sigmas[index])
+            noise = torch.randn(x.shape, device=dev, generator=gen) if sigma > 0 else None
+            x, _ = ops.ddim_step(x, eps, guided=True, scale=float(uc_scale), a_t=float(s.ddim_alphas[index]),
+                                 a_prev=float(s.ddim_alphas_prev[index]), sigma=sigma,
+                                 sqrt_one_minus_at=float(s.ddim_sqrt_one_minus_alphas[index]), noise=noise, want_pred_x0=False)
     olo, ohi = partition(n, world)[rank]
     if ohi > olo:
         dec = m.vqvae_module.decode_no_quant(x[olo:ohi].contiguous())

@@ -1,0 +1,30 @@
+"""GroupNorm-apply (+SiLU) pass at the three spatial levels of the denoiser, batch 64: tanh-form SiLU (default) vs ex2 + rcp
+(cs_debug_set bit 21).  CUDA events, L2-cold (a 512 MB buffer is written between launches)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from commonscenes_b200 import _lib, ops
+flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+for (hw, C) in ((16, 224), (8, 448), (4, 672), (16, 448)):
+    B, S = 64, 16 * hw * hw
+    x = torch.randn(B, 16, hw, hw, C, device="cuda").to(torch.bfloat16)
+    stat = ops.zero_stat_buffer(x.device, B, C)
+    ops.groupnorm_stats(x, stat)
+    ga, be = torch.randn(C, device="cuda"), torch.randn(C, device="cuda")
+    outs = {}
+    for name, flag in (("tanh-form SiLU", 0), ("ex2 + rcp SiLU", 1 << 21)):
+        _lib.load().cs_debug_set(flag)
+        ts = []
+        for _ in range(6):
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            y = ops.groupnorm_fused(x, stat, ga, be, groups=32, eps=1e-5, act=ops.ACT_SILU)
+            e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        us = 1e3 * sorted(ts)[len(ts) // 2]
+        outs[name] = y.float()
+        print(f"S={S:5d} C={C:4d} {name:16s}: {us:7.1f} us  {2 * x.numel() * 2 / us / 1e6:6.2f} TB/s (read + write)")
+    _lib.load().cs_debug_set(0)
+    a, b = outs["tanh-form SiLU"], outs["ex2 + rcp SiLU"]
+    print(f"        tanh-form vs ex2+rcp: max |diff| {float((a - b).abs().max()):.3e}, rel-L2 {float((a - b).norm() / b.norm()):.3e}")
