@@ -11,7 +11,7 @@ namespace cs {
 
 __device__ __forceinline__ float act_grad(float z, int act) {
   if (act == CS_ACT_SILU) {
-    const float s = __fdividef(1.f, 1.f + __expf(-z));
+    const float s = fmaf(0.5f, tanh_approx_f(0.5f * z), 0.5f);   // sigmoid through ONE MUFU op (tanh.approx, 2^-11)
     return s * (1.f + z * (1.f - s));
   }
   if (act == CS_ACT_GELU) {
@@ -33,53 +33,83 @@ __device__ __forceinline__ void gn_group_stats(int b, int S, int cpg, const long
 // GroupNorm(+act) backward, pass 1: red[b][c][0] += sum_v dz, red[b][c][1] += sum_v dz * xhat   (c = concat channel)
 // with z = gamma * xhat + beta, dz = dy * act'(z).  x is the source that owns concat channels [ch_off, ch_off + C).
 // ------------------------------------------------------------------------------------------------
-__global__ void gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ x, int S, int C, int pitch, int ch_off,
-                                     const __nv_bfloat16* __restrict__ dy, int dy_pitch, int dy_off,
-                                     const long long* __restrict__ stat1, int C1, const long long* __restrict__ stat2, int C2,
-                                     const float* __restrict__ gamma, const float* __restrict__ beta, int groups, float eps,
-                                     int act, float* __restrict__ red, int vox_per_cta) {
+__global__ void __launch_bounds__(256, 2)
+gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ x, int S, int C, int pitch, int ch_off,
+                     const __nv_bfloat16* __restrict__ dy, int dy_pitch, int dy_off,
+                     const long long* __restrict__ stat1, int C1, const long long* __restrict__ stat2, int C2,
+                     const float* __restrict__ gamma, const float* __restrict__ beta, int groups, float eps,
+                     int act, float* __restrict__ red, int vox_per_cta) {
   __shared__ float g_mean[64], g_rstd[64];
   extern __shared__ float sred[];   // [R][C][2] per-row-slot partial sums (plain stores + a fixed-order sum: shared-memory
                                     // float atomics compile to CAS loops, which dominated this kernel)
   const int b = blockIdx.y;
   const int Ct = C1 + C2;
   const int cpg = Ct / groups;
-  gn_group_stats(b, S, cpg, stat1, C1, stat2, C2, eps, g_mean, g_rstd, groups);
-  __syncthreads();
   const int cv = C >> 3;
   const int R = blockDim.x / cv;
   const int r = threadIdx.x / cv;
   const int v = threadIdx.x - r * cv;
-  if (r < R) {
-    float ga[8], be[8], mu[8], rs[8], s1[8], s2[8];
+  const bool active = r < R;
+  const int s_begin = blockIdx.x * vox_per_cta;
+  const int s_end = min(S, s_begin + vox_per_cta);
+  const __nv_bfloat16* xb = x + (static_cast<long long>(b) * S) * pitch + v * 8;
+  const __nv_bfloat16* db = dy + (static_cast<long long>(b) * S) * dy_pitch + dy_off + v * 8;
+  // first rows and the affine parameters are requested before the statistics prologue (one-wave launch: nothing else
+  // hides that latency), then the loop keeps the next batch in flight while it reduces the current one
+  constexpr int U = 2;
+  uint4 cx[U], cd[U];
+#pragma unroll
+  for (int k = 0; k < U; ++k) {
+    const int i = s_begin + r + k * R;
+    if (active && i < s_end) {
+      cx[k] = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<long long>(i) * pitch));
+      cd[k] = __ldg(reinterpret_cast<const uint4*>(db + static_cast<long long>(i) * dy_pitch));
+    }
+  }
+  float ga[8], be[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = ch_off + v * 8 + j;
+    ga[j] = (active && gamma) ? __ldg(gamma + c) : 1.f;
+    be[j] = (active && beta) ? __ldg(beta + c) : 0.f;
+  }
+  gn_group_stats(b, S, cpg, stat1, C1, stat2, C2, eps, g_mean, g_rstd, groups);
+  __syncthreads();
+  if (active) {
+    float rs[8], nm[8], s1[8], s2[8];     // xhat = x * rstd + (-mean * rstd)
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int c = ch_off + v * 8 + j;
-      const int g = c / cpg;
-      ga[j] = gamma ? __ldg(gamma + c) : 1.f;
-      be[j] = beta ? __ldg(beta + c) : 0.f;
-      mu[j] = g_mean[g];
+      const int g = (ch_off + v * 8 + j) / cpg;
       rs[j] = g_rstd[g];
+      nm[j] = -g_mean[g] * rs[j];
       s1[j] = s2[j] = 0.f;
     }
-    const int s_begin = blockIdx.x * vox_per_cta;
-    const int s_end = min(S, s_begin + vox_per_cta);
-    const __nv_bfloat16* xb = x + (static_cast<long long>(b) * S) * pitch + v * 8;
-    const __nv_bfloat16* db = dy + (static_cast<long long>(b) * S) * dy_pitch + dy_off + v * 8;
-#pragma unroll 2
-    for (int i = s_begin + r; i < s_end; i += R) {
-      const uint4 u = *reinterpret_cast<const uint4*>(xb + static_cast<long long>(i) * pitch);
-      const uint4 d = *reinterpret_cast<const uint4*>(db + static_cast<long long>(i) * dy_pitch);
-      const uint32_t xw[4] = {u.x, u.y, u.z, u.w}, dw[4] = {d.x, d.y, d.z, d.w};
+    for (int i0 = s_begin + r; i0 < s_end; i0 += U * R) {
+      uint4 nx[U], nd[U];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 xf = unpack_bf16x2(xw[j]), df = unpack_bf16x2(dw[j]);
-        const float h0 = (xf.x - mu[2 * j]) * rs[2 * j], h1 = (xf.y - mu[2 * j + 1]) * rs[2 * j + 1];
-        const float z0 = df.x * act_grad(fmaf(ga[2 * j], h0, be[2 * j]), act);
-        const float z1 = df.y * act_grad(fmaf(ga[2 * j + 1], h1, be[2 * j + 1]), act);
-        s1[2 * j] += z0; s2[2 * j] += z0 * h0;
-        s1[2 * j + 1] += z1; s2[2 * j + 1] += z1 * h1;
+      for (int k = 0; k < U; ++k) {
+        const int i = i0 + (U + k) * R;
+        if (i < s_end) {
+          nx[k] = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<long long>(i) * pitch));
+          nd[k] = __ldg(reinterpret_cast<const uint4*>(db + static_cast<long long>(i) * dy_pitch));
+        }
       }
+#pragma unroll
+      for (int k = 0; k < U; ++k) {
+        if (i0 + k * R >= s_end) break;
+        const uint32_t xw[4] = {cx[k].x, cx[k].y, cx[k].z, cx[k].w}, dw[4] = {cd[k].x, cd[k].y, cd[k].z, cd[k].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 xf = unpack_bf16x2(xw[j]), df = unpack_bf16x2(dw[j]);
+          const float h0 = fmaf(xf.x, rs[2 * j], nm[2 * j]), h1 = fmaf(xf.y, rs[2 * j + 1], nm[2 * j + 1]);
+          const float z0 = df.x * act_grad(fmaf(ga[2 * j], h0, be[2 * j]), act);
+          const float z1 = df.y * act_grad(fmaf(ga[2 * j + 1], h1, be[2 * j + 1]), act);
+          s1[2 * j] += z0; s2[2 * j] = fmaf(z0, h0, s2[2 * j]);
+          s1[2 * j + 1] += z1; s2[2 * j + 1] = fmaf(z1, h1, s2[2 * j + 1]);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < U; ++k) { cx[k] = nx[k]; cd[k] = nd[k]; }
     }
     float* mine = sred + (static_cast<long long>(r) * C + v * 8) * 2;
 #pragma unroll
@@ -95,16 +125,47 @@ __global__ void gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ x, int S,
 }
 
 // pass 2: dx = rstd * (gamma * dz - mean_g(gamma dz) - xhat * mean_g(gamma dz xhat)) [+ extra]
-__global__ void gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, int S, int C, int pitch, int ch_off,
-                                    const __nv_bfloat16* __restrict__ dy, int dy_pitch, int dy_off,
-                                    const long long* __restrict__ stat1, int C1, const long long* __restrict__ stat2, int C2,
-                                    const float* __restrict__ gamma, const float* __restrict__ beta, int groups, float eps,
-                                    int act, const float* __restrict__ red, const __nv_bfloat16* __restrict__ extra,
-                                    int extra_pitch, __nv_bfloat16* __restrict__ dx, int dx_pitch, int vox_per_cta) {
+__global__ void __launch_bounds__(256, 2)
+gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, int S, int C, int pitch, int ch_off,
+                    const __nv_bfloat16* __restrict__ dy, int dy_pitch, int dy_off,
+                    const long long* __restrict__ stat1, int C1, const long long* __restrict__ stat2, int C2,
+                    const float* __restrict__ gamma, const float* __restrict__ beta, int groups, float eps,
+                    int act, const float* __restrict__ red, const __nv_bfloat16* __restrict__ extra,
+                    int extra_pitch, __nv_bfloat16* __restrict__ dx, int dx_pitch, int vox_per_cta) {
   __shared__ float g_mean[64], g_rstd[64], g_a[64], g_b[64];
   const int b = blockIdx.y;
   const int Ct = C1 + C2;
   const int cpg = Ct / groups;
+  const int cv = C >> 3;
+  const int R = blockDim.x / cv;
+  const int r = threadIdx.x / cv;
+  const int v = threadIdx.x - r * cv;
+  const bool active = r < R;
+  const int s_begin = blockIdx.x * vox_per_cta;
+  const int s_end = min(S, s_begin + vox_per_cta);
+  const __nv_bfloat16* xb = x + (static_cast<long long>(b) * S) * pitch + v * 8;
+  const __nv_bfloat16* db = dy + (static_cast<long long>(b) * S) * dy_pitch + dy_off + v * 8;
+  const __nv_bfloat16* eb = extra ? extra + (static_cast<long long>(b) * S) * extra_pitch + v * 8 : nullptr;
+  __nv_bfloat16* ob = dx + (static_cast<long long>(b) * S) * dx_pitch + v * 8;
+  constexpr int U = 2;
+  uint4 cx[U], cd[U], ce[U];
+#pragma unroll
+  for (int k = 0; k < U; ++k) {
+    const int i = s_begin + r + k * R;
+    ce[k] = make_uint4(0u, 0u, 0u, 0u);
+    if (active && i < s_end) {
+      cx[k] = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<long long>(i) * pitch));
+      cd[k] = __ldg(reinterpret_cast<const uint4*>(db + static_cast<long long>(i) * dy_pitch));
+      if (eb) ce[k] = __ldg(reinterpret_cast<const uint4*>(eb + static_cast<long long>(i) * extra_pitch));
+    }
+  }
+  float ga[8], be[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = ch_off + v * 8 + j;
+    ga[j] = (active && gamma) ? __ldg(gamma + c) : 1.f;
+    be[j] = (active && beta) ? __ldg(beta + c) : 0.f;
+  }
   gn_group_stats(b, S, cpg, stat1, C1, stat2, C2, eps, g_mean, g_rstd, groups);
   if (threadIdx.x < groups) {
     double sa = 0.0, sb = 0.0;
@@ -119,49 +180,52 @@ __global__ void gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, int S, 
     g_b[threadIdx.x] = static_cast<float>(sb * inv_n);
   }
   __syncthreads();
-  const int cv = C >> 3;
-  const int R = blockDim.x / cv;
-  const int r = threadIdx.x / cv;
-  const int v = threadIdx.x - r * cv;
-  if (r >= R) return;
-  float ga[8], be[8], mu[8], rs[8], ma[8], mb[8];
+  if (!active) return;
+  float rs[8], nm[8], ma[8], mb[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const int c = ch_off + v * 8 + j;
-    const int g = c / cpg;
-    ga[j] = gamma ? __ldg(gamma + c) : 1.f;
-    be[j] = beta ? __ldg(beta + c) : 0.f;
-    mu[j] = g_mean[g]; rs[j] = g_rstd[g]; ma[j] = g_a[g]; mb[j] = g_b[g];
+    const int g = (ch_off + v * 8 + j) / cpg;
+    rs[j] = g_rstd[g]; nm[j] = -g_mean[g] * rs[j]; ma[j] = g_a[g]; mb[j] = g_b[g];
   }
-  const int s_begin = blockIdx.x * vox_per_cta;
-  const int s_end = min(S, s_begin + vox_per_cta);
-  const __nv_bfloat16* xb = x + (static_cast<long long>(b) * S) * pitch + v * 8;
-  const __nv_bfloat16* db = dy + (static_cast<long long>(b) * S) * dy_pitch + dy_off + v * 8;
-  const __nv_bfloat16* eb = extra ? extra + (static_cast<long long>(b) * S) * extra_pitch + v * 8 : nullptr;
-  __nv_bfloat16* ob = dx + (static_cast<long long>(b) * S) * dx_pitch + v * 8;
-#pragma unroll 2
-  for (int i = s_begin + r; i < s_end; i += R) {
-    const uint4 u = *reinterpret_cast<const uint4*>(xb + static_cast<long long>(i) * pitch);
-    const uint4 d = *reinterpret_cast<const uint4*>(db + static_cast<long long>(i) * dy_pitch);
-    uint4 e = make_uint4(0u, 0u, 0u, 0u);
-    if (eb) e = *reinterpret_cast<const uint4*>(eb + static_cast<long long>(i) * extra_pitch);
-    const uint32_t xw[4] = {u.x, u.y, u.z, u.w}, dw[4] = {d.x, d.y, d.z, d.w}, ew[4] = {e.x, e.y, e.z, e.w};
-    uint32_t o[4];
+  for (int i0 = s_begin + r; i0 < s_end; i0 += U * R) {
+    uint4 nx[U], nd[U], ne[U];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 xf = unpack_bf16x2(xw[j]), df = unpack_bf16x2(dw[j]), ef = unpack_bf16x2(ew[j]);
-      const float h0 = (xf.x - mu[2 * j]) * rs[2 * j], h1 = (xf.y - mu[2 * j + 1]) * rs[2 * j + 1];
-      const float z0 = df.x * act_grad(fmaf(ga[2 * j], h0, be[2 * j]), act);
-      const float z1 = df.y * act_grad(fmaf(ga[2 * j + 1], h1, be[2 * j + 1]), act);
-      const float o0 = rs[2 * j] * (ga[2 * j] * z0 - ma[2 * j] - h0 * mb[2 * j]) + ef.x;
-      const float o1 = rs[2 * j + 1] * (ga[2 * j + 1] * z1 - ma[2 * j + 1] - h1 * mb[2 * j + 1]) + ef.y;
-      o[j] = pack_bf16x2(o0, o1);
+    for (int k = 0; k < U; ++k) {
+      const int i = i0 + (U + k) * R;
+      ne[k] = make_uint4(0u, 0u, 0u, 0u);
+      if (i < s_end) {
+        nx[k] = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<long long>(i) * pitch));
+        nd[k] = __ldg(reinterpret_cast<const uint4*>(db + static_cast<long long>(i) * dy_pitch));
+        if (eb) ne[k] = __ldg(reinterpret_cast<const uint4*>(eb + static_cast<long long>(i) * extra_pitch));
+      }
     }
-    *reinterpret_cast<uint4*>(ob + static_cast<long long>(i) * dx_pitch) = make_uint4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      const int i = i0 + k * R;
+      if (i >= s_end) break;
+      const uint32_t xw[4] = {cx[k].x, cx[k].y, cx[k].z, cx[k].w}, dw[4] = {cd[k].x, cd[k].y, cd[k].z, cd[k].w},
+                     ew[4] = {ce[k].x, ce[k].y, ce[k].z, ce[k].w};
+      uint32_t o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 xf = unpack_bf16x2(xw[j]), df = unpack_bf16x2(dw[j]), ef = unpack_bf16x2(ew[j]);
+        const float h0 = fmaf(xf.x, rs[2 * j], nm[2 * j]), h1 = fmaf(xf.y, rs[2 * j + 1], nm[2 * j + 1]);
+        const float z0 = df.x * act_grad(fmaf(ga[2 * j], h0, be[2 * j]), act);
+        const float z1 = df.y * act_grad(fmaf(ga[2 * j + 1], h1, be[2 * j + 1]), act);
+        const float o0 = fmaf(rs[2 * j], fmaf(ga[2 * j], z0, -fmaf(h0, mb[2 * j], ma[2 * j])), ef.x);
+        const float o1 = fmaf(rs[2 * j + 1], fmaf(ga[2 * j + 1], z1, -fmaf(h1, mb[2 * j + 1], ma[2 * j + 1])), ef.y);
+        o[j] = pack_bf16x2(o0, o1);
+      }
+      *reinterpret_cast<uint4*>(ob + static_cast<long long>(i) * dx_pitch) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+#pragma unroll
+    for (int k = 0; k < U; ++k) { cx[k] = nx[k]; cd[k] = nd[k]; ce[k] = ne[k]; }
   }
 }
 
-static int gn_geometry(int B, int S, int C, int groups, int* threads, int* R, int* splits, int* vox) {
+// One wave: `slots` = CTAs resident at once (occupancy x SMs); each CTA streams one contiguous slab of a sample, so the
+// statistics prologue is paid once per slot and there is no partial second wave (same rule as gn_apply_fused_launch).
+static int gn_geometry(int B, int S, int C, int groups, int slots, int* threads, int* R, int* splits, int* vox) {
   const int cv = C / 8;
   if (cv > 1024) return 1;
   int r = 256 / cv;
@@ -169,7 +233,8 @@ static int gn_geometry(int B, int S, int C, int groups, int* threads, int* R, in
   int t = (r * cv + 31) / 32 * 32;
   if (t < 64) t = 64;
   if (t < groups) t = groups;
-  int sp = (8 * num_sms() + B - 1) / B;
+  int sp = slots / B;
+  if (sp < 1) sp = 1;
   int vx = (S + sp - 1) / sp;
   if (vx < 4 * r) vx = 4 * r;
   sp = (S + vx - 1) / vx;
@@ -186,7 +251,17 @@ int gn_bwd_launch(const void* x, int B, int S, int C, int pitch, int ch_off, con
     return set_error(CS_ERR_INVALID, "groupnorm_bwd: channels/pitches must be multiples of 8, <= 64 groups");
   if (B == 0 || S == 0) return CS_OK;
   int threads, R, splits, vox;
-  if (gn_geometry(B, S, C, groups, &threads, &R, &splits, &vox)) return set_error(CS_ERR_INVALID, "groupnorm_bwd: C too large");
+  {
+    int r0 = 256 / (C / 8 > 0 ? C / 8 : 1);
+    if (r0 < 1) r0 = 1;
+    int occ = 0;
+    cudaError_t oe = pass == 0
+        ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gn_bwd_reduce_kernel, 256, static_cast<size_t>(r0) * C * 2 * sizeof(float))
+        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gn_bwd_apply_kernel, 256, 0);
+    if (oe != cudaSuccess || occ < 1) occ = 2;
+    if (gn_geometry(B, S, C, groups, occ * num_sms(), &threads, &R, &splits, &vox))
+      return set_error(CS_ERR_INVALID, "groupnorm_bwd: C too large");
+  }
   const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x);
   const __nv_bfloat16* db = reinterpret_cast<const __nv_bfloat16*>(dy);
   if (pass == 0) {

@@ -268,11 +268,14 @@ __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.f + __
 // half the FP instructions -- for the streaming GroupNorm-apply pass, whose bf16 output rounds at 2^-9.  Absolute error
 // <= |x| * 2.4e-4 (the cancellation in 1 + tanh(h) for very negative x costs relative, not absolute, accuracy there:
 // silu(-8) = -2.7e-3 is returned within 2e-3, the size of a bf16 ulp of the O(1) activations around it).
-__device__ __forceinline__ float silu_tanh_f(float x) {
-  const float h = 0.5f * x;
+__device__ __forceinline__ float tanh_approx_f(float h) {
   float t;
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
-  return fmaf(h, t, h);
+  return t;
+}
+__device__ __forceinline__ float silu_tanh_f(float x) {
+  const float h = 0.5f * x;
+  return fmaf(h, tanh_approx_f(h), h);
 }
 __device__ __forceinline__ float gelu_erf_f(float x) {
   return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));

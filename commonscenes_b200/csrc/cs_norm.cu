@@ -165,50 +165,80 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x, int S, int 
 // (scale, shift) pairs of its 8 channels and streams its slab of voxels.  Sums are only read, never cleared: a tensor
 // may be normalised more than once (block output -> next block AND decoder skip).
 // ------------------------------------------------------------------------------------------------
-__global__ void gn_apply_fused_kernel(const __nv_bfloat16* __restrict__ x, int S, int C, int pitch, int ch_off,
-                                      const long long* __restrict__ stat1, int C1, const long long* __restrict__ stat2, int C2,
-                                      const float* __restrict__ gamma, const float* __restrict__ beta, int groups,
-                                      float eps, __nv_bfloat16* __restrict__ y, int y_pitch, int act, int vox_per_cta,
-                                      int exact_silu) {
+__global__ void __launch_bounds__(256, 3)
+gn_apply_fused_kernel(const __nv_bfloat16* __restrict__ x, int S, int C, int pitch, int ch_off,
+                      const long long* __restrict__ stat1, int C1, const long long* __restrict__ stat2, int C2,
+                      const float* __restrict__ gamma, const float* __restrict__ beta, int groups,
+                      float eps, __nv_bfloat16* __restrict__ y, int y_pitch, int act, int vox_per_cta,
+                      int exact_silu) {
   __shared__ float g_mean[64], g_rstd[64];
   const int b = blockIdx.y;
   const int Ct = C1 + C2;
   const int cpg = Ct / groups;
-  if (threadIdx.x < groups) stat_group_mean_rstd(b, threadIdx.x, cpg, S, stat1, C1, stat2, C2, eps, g_mean[threadIdx.x], g_rstd[threadIdx.x]);
-  __syncthreads();
   const int cv = C >> 3;
   const int R = blockDim.x / cv;
   const int r = threadIdx.x / cv;
   const int v = threadIdx.x - r * cv;
-  if (r >= R) return;
-  float2 a[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = ch_off + v * 8 + j;      // channel index inside the concatenation
-    const int g = c / cpg;
-    const float ga = gamma ? __ldg(gamma + c) : 1.f, be = beta ? __ldg(beta + c) : 0.f;
-    const float sc = ga * g_rstd[g];
-    a[j] = make_float2(sc, be - g_mean[g] * sc);
-  }
+  const bool active = r < R;
   const int s_begin = blockIdx.x * vox_per_cta;
   const int s_end = min(S, s_begin + vox_per_cta);
   const __nv_bfloat16* xb = x + (static_cast<long long>(b) * S) * pitch + v * 8;
   __nv_bfloat16* yb = y + (static_cast<long long>(b) * S) * y_pitch + v * 8;
-#pragma unroll 4
-  for (int i = s_begin + r; i < s_end; i += R) {
-    const uint4 u = *reinterpret_cast<const uint4*>(xb + static_cast<long long>(i) * pitch);
-    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-    uint32_t o[4];
+  // The first slab rows and the affine parameters are requested BEFORE the statistics prologue, so the DRAM latency of
+  // both runs under the fp64 group reduction instead of after it (the launch is one wave: nothing else would hide it).
+  constexpr int U = 4;
+  uint4 cur[U];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 f = unpack_bf16x2(w[j]);
-      float y0 = fmaf(f.x, a[2 * j].x, a[2 * j].y), y1 = fmaf(f.y, a[2 * j + 1].x, a[2 * j + 1].y);
-      if (act == CS_ACT_SILU) {
-        if (exact_silu) { y0 = silu_f(y0); y1 = silu_f(y1); } else { y0 = silu_tanh_f(y0); y1 = silu_tanh_f(y1); }
-      } else if (act == CS_ACT_GELU) { y0 = gelu_erf_fast(y0); y1 = gelu_erf_fast(y1); }
-      o[j] = pack_bf16x2(y0, y1);
+  for (int k = 0; k < U; ++k) {
+    const int i = s_begin + r + k * R;
+    if (active && i < s_end) cur[k] = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<long long>(i) * pitch));
+  }
+  float ga[8], be[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = ch_off + v * 8 + j;      // channel index inside the concatenation
+    ga[j] = (active && gamma) ? __ldg(gamma + c) : 1.f;
+    be[j] = (active && beta) ? __ldg(beta + c) : 0.f;
+  }
+  if (threadIdx.x < groups) stat_group_mean_rstd(b, threadIdx.x, cpg, S, stat1, C1, stat2, C2, eps, g_mean[threadIdx.x], g_rstd[threadIdx.x]);
+  __syncthreads();
+  if (!active) return;
+  // tanh-form SiLU works on h = y / 2: the (exact) halving is folded into the affine pair
+  const bool fast_silu = act == CS_ACT_SILU && !exact_silu;
+  const float pre = fast_silu ? 0.5f : 1.f;
+  float2 a[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int g = (ch_off + v * 8 + j) / cpg;
+    const float sc = ga[j] * g_rstd[g];
+    a[j] = make_float2(pre * sc, pre * (be[j] - g_mean[g] * sc));
+  }
+  for (int i0 = s_begin + r; i0 < s_end; i0 += U * R) {
+    uint4 nxt[U];
+#pragma unroll
+    for (int k = 0; k < U; ++k) {     // next batch in flight while this one is transformed
+      const int i = i0 + (U + k) * R;
+      if (i < s_end) nxt[k] = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<long long>(i) * pitch));
     }
-    *reinterpret_cast<uint4*>(yb + static_cast<long long>(i) * y_pitch) = make_uint4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      const int i = i0 + k * R;
+      if (i >= s_end) break;
+      const uint32_t w[4] = {cur[k].x, cur[k].y, cur[k].z, cur[k].w};
+      uint32_t o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16x2(w[j]);
+        float y0 = fmaf(f.x, a[2 * j].x, a[2 * j].y), y1 = fmaf(f.y, a[2 * j + 1].x, a[2 * j + 1].y);
+        if (fast_silu) { y0 = fmaf(y0, tanh_approx_f(y0), y0); y1 = fmaf(y1, tanh_approx_f(y1), y1); }
+        else if (act == CS_ACT_SILU) { y0 = silu_f(y0); y1 = silu_f(y1); }
+        else if (act == CS_ACT_GELU) { y0 = gelu_erf_fast(y0); y1 = gelu_erf_fast(y1); }
+        o[j] = pack_bf16x2(y0, y1);
+      }
+      *reinterpret_cast<uint4*>(yb + static_cast<long long>(i) * y_pitch) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+#pragma unroll
+    for (int k = 0; k < U; ++k) cur[k] = nxt[k];
   }
 }
 
@@ -412,7 +442,15 @@ int gn_apply_fused_launch(const void* x, int B, int S, int C, int pitch, int ch_
   int R = 256 / cv; if (R < 1) R = 1;
   int threads = ((R * cv + 31) / 32) * 32;
   if (threads < 64) threads = 64;   // the prologue needs one thread per group
-  int splits = (8 * num_sms() + B - 1) / B;
+  // ONE wave: as many CTAs as are resident at once (occupancy x SMs), each streaming one contiguous slab of a sample.
+  // (Sizing for 8 CTAs per SM when 5 fit left a 0.6-wave tail and paid the statistics prologue twice per SM slot;
+  // debug bit 22 restores that geometry for A/B, tools/gn_bench.py.)
+  static int occ = 0;
+  if (!occ) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gn_apply_fused_kernel, 256, 0) != cudaSuccess || occ < 1) occ = 4;
+  }
+  int splits = (igemm_debug_flags() >> 22) & 1 ? (8 * num_sms() + B - 1) / B : (occ * num_sms()) / B;
+  if (splits < 1) splits = 1;
   int vox = (S + splits - 1) / splits;
   if (vox < 4 * R) vox = 4 * R;
   splits = (S + vox - 1) / vox;

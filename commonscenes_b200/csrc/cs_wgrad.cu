@@ -18,6 +18,7 @@
 //
 // Roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-9 = epilogue (two warps per
 // TMEM lane quarter, each draining alternate 32-column chunks: the accumulators are single-buffered, so the epilogue is exposed).
+#include <cstdlib>
 #include "cs_common.cuh"
 #include "cs_host.h"
 #include "cs_wgrad.cuh"
@@ -252,18 +253,31 @@ int wgrad_launch(const WgradArgs& a, cudaStream_t stream) {
   p.m_chunks = (p.B / p.bb) * (p.Do / p.bd) * (p.Ho / p.bh) * (p.Wo / p.bw);
   const int units = p.ntaps * p.n_pairs * p.n_tiles;
   const int sms = num_sms();
-  // Split of the voxel axis: pick the number of splits whose item count fills whole rounds of the persistent CTAs best
-  // (items / (ceil(items / SMs) * SMs)), keeping >= 16 K chunks per item and preferring fewer, longer items on ties
-  // (each item pays one exposed epilogue).
+  // Split of the voxel axis.  An item costs its K chunks of MMAs plus ONE exposed epilogue (the accumulators are single
+  // buffered: 2 x 128 lanes x BN columns of red.global.add.f32) plus a pipeline refill.  Pick the split that minimises
+  //   rounds x (chunks per item x clk per chunk + epilogue + refill)   over the persistent CTAs.  The per-column epilogue
+  // cost was swept on the B200 (profiles/r2p_wgrad_split.log: 0 / 20 / 44 / 88 clk -> 18.7 / 18.6 / 18.2 / 17.9 ms over
+  // the UNet's wgrad shapes at batch 32): the total is flat, i.e. the epilogue is NOT what holds this kernel at ~0.95
+  // PFLOP/s; 88 is kept.  CS_WGRAD_EPI overrides it for such sweeps.
+  static int epi_clk = -1;
+  if (epi_clk < 0) {
+    const char* e = getenv("CS_WGRAD_EPI");
+    epi_clk = e ? atoi(e) : 88;
+    if (epi_clk < 0) epi_clk = 0;
+  }
+  int n_acc = 1;
+  if (p.C1pad > 128 || p.C2pad > 128) n_acc = 2;
+  const double clk_chunk = static_cast<double>(n_acc) * (p.rows >> 4) * (p.BN / 2.0);
+  const double clk_item_fixed = static_cast<double>(n_acc) * p.BN * epi_clk + 2000.0;
   const int max_split = p.m_chunks / 16 > 0 ? p.m_chunks / 16 : 1;
   int nsplit = 1;
-  double best = 0.0;
+  double best = 1e300;
   for (int ns = 1; ns <= max_split && ns <= 64; ++ns) {
     const long long items = static_cast<long long>(units) * ns;
     const long long rounds = (items + sms - 1) / sms;
-    double eff = static_cast<double>(items) / static_cast<double>(rounds * sms);
-    eff *= 1.0 - 0.02 * static_cast<double>(rounds > 8 ? 8 : rounds) / (static_cast<double>(p.m_chunks) / ns / 64.0 + 1.0);  // epilogue share
-    if (eff > best + 1e-3) { best = eff; nsplit = ns; }
+    const double cpi = static_cast<double>((p.m_chunks + ns - 1) / ns);
+    const double cost = static_cast<double>(rounds) * (cpi * clk_chunk + clk_item_fixed);
+    if (cost < best * (1.0 - 1e-3)) { best = cost; nsplit = ns; }
   }
   p.nsplit = nsplit;
   p.n_items = units * nsplit;
