@@ -17,7 +17,7 @@ CS_OK, CS_ERR_INVALID, CS_ERR_CUDA, CS_ERR_UNSUPPORTED, CS_ERR_NO_DEVICE = range
 OUT_BF16_NDHWC, OUT_F32_NCDHW, OUT_F32_NDHWC = 0, 1, 2
 ACT_NONE, ACT_SILU, ACT_GELU, ACT_GEGLU = 0, 1, 2, 3
 
-_vp, _i32, _i64, _f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+_vp, _i32, _i64, _f32, _f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double
 
 
 class Conv3dArgs(C.Structure):
@@ -113,6 +113,8 @@ SIGNATURES = {
     "cs_approx_match": (_i32, [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
     "cs_match_cost": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),
     "cs_match_cost_grad": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "cs_surface_count": (_i32, [_vp, _i32, _i32, _i32, _i32, _f64, _vp, _vp, _vp, _vp, _vp]),
+    "cs_surface_emit": (_i32, [_vp, _i32, _i32, _i32, _i32, _f64, _f64, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "cs_debug_set": (None, [_i32]),
     "cs_conv3d_variant_counts": (None, [_vp, _i32]),
     "cs_vq_quantize": (_i32, [_vp, _i32, _i32, _i64, _vp, _i32, _vp, _vp, _i32, _vp, _vp, _vp]),

@@ -1,0 +1,269 @@
+// SDF grid -> iso-surface vertices (+ triangles) on the device: the consumer of the decoded 64^3 SDFs in the reference's
+// evaluation chain.
+//
+// Reference: model/diff_utils/util_3d.py:194-235 sdf_to_mesh -- per object a device->host copy of the grid and
+// mcubes.marching_cubes(sdf_i, level) on ONE CPU core, then `verts / n_cell - .5`; scripts/eval_3dfront.py:313-317,
+// 589-592 consume `.verts_list()` only (re-sampled by helpers/util.py:31-45 and sent to the Chamfer kernels).
+// PyMCubes is a third-party package absent from the reference tree and from this image (parity unpinned):
+// the algorithm restated here is the published one -- a corner is inside when value <= level, every grid edge whose two
+// corners differ carries ONE vertex at x1 + (level - f1) / (f2 - f1) (double precision) -- which fixes the vertex SET;
+// vertices are emitted in (voxel linear index, axis) order and the triangles follow the generated 256-case table of
+// oracle/mesh.py / commonscenes_b200/model/diff_utils/util_3d.py (closed loops of the crossings, watertight).
+//
+// HBM-bound integer work, four small launches per batch of grids (no host loop over objects, no device->host copy of the
+// grids): classify (flags + per-256-voxel counts) -> scan (one CTA per object) -> vertices (+ per-voxel vertex offsets)
+// -> triangles.  The only host round trip is the (objects x 2) int32 totals needed to size the outputs.
+#include "cs_host.h"
+#include "../../include/cs_b200.h"
+
+namespace cs {
+
+static constexpr int kMcChunk = 256;   // voxels per CTA (one thread each), consecutive in memory (z fastest)
+
+__device__ __forceinline__ int mc_block_exclusive_scan(int v, int* total) {
+  // 256 threads: warp shuffles + one shared row
+  __shared__ int wsum[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  __syncthreads();                 // wsum may still be read by a previous call
+  if (lane == 31) wsum[warp] = inc;
+  __syncthreads();
+  int base = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) {
+    const int s = wsum[w];
+    if (w < warp) base += s;
+    tot += s;
+  }
+  *total = tot;
+  return base + inc - v;
+}
+
+struct McGrid {
+  int nx, ny, nz;
+  long long vox;     // nx * ny * nz
+  int chunks;        // ceil(vox / 256)
+};
+
+__device__ __forceinline__ bool mc_inside(float f, double level) { return static_cast<double>(f) <= level; }
+
+// flags: bit a = the edge from this voxel towards +axis a (0 = x, slowest; 2 = z, fastest) crosses the level
+__device__ __forceinline__ int mc_voxel(const float* __restrict__ g, const McGrid& gr, long long i, double level, int* kase) {
+  const int z = static_cast<int>(i % gr.nz);
+  const int y = static_cast<int>((i / gr.nz) % gr.ny);
+  const int x = static_cast<int>(i / (static_cast<long long>(gr.nz) * gr.ny));
+  const long long sy = gr.nz, sx = static_cast<long long>(gr.nz) * gr.ny;
+  const bool hx = x + 1 < gr.nx, hy = y + 1 < gr.ny, hz = z + 1 < gr.nz;
+  const bool c0 = mc_inside(__ldg(g + i), level);
+  const bool c1 = hx && mc_inside(__ldg(g + i + sx), level);
+  const bool c2 = hy && mc_inside(__ldg(g + i + sy), level);
+  const bool c4 = hz && mc_inside(__ldg(g + i + 1), level);
+  int flags = 0;
+  if (hx && c1 != c0) flags |= 1;
+  if (hy && c2 != c0) flags |= 2;
+  if (hz && c4 != c0) flags |= 4;
+  int k = -1;
+  if (hx && hy && hz) {       // this voxel is the low corner of a cell: corner c = dx + 2 dy + 4 dz
+    k = (c0 ? 1 : 0) | (c1 ? 2 : 0) | (c2 ? 4 : 0) | (c4 ? 16 : 0);
+    if (mc_inside(__ldg(g + i + sx + sy), level)) k |= 8;
+    if (mc_inside(__ldg(g + i + sx + 1), level)) k |= 32;
+    if (mc_inside(__ldg(g + i + sy + 1), level)) k |= 64;
+    if (mc_inside(__ldg(g + i + sx + sy + 1), level)) k |= 128;
+  }
+  *kase = k;
+  return flags;
+}
+
+__global__ void __launch_bounds__(kMcChunk)
+mc_classify_kernel(const float* __restrict__ sdf, McGrid gr, double level, const uint8_t* __restrict__ tri_count,
+                   uint8_t* __restrict__ vflags, int* __restrict__ chunk_counts) {
+  const int b = blockIdx.y;
+  const long long i = static_cast<long long>(blockIdx.x) * kMcChunk + threadIdx.x;
+  int nv = 0, nt = 0;
+  if (i < gr.vox) {
+    int kase;
+    const int flags = mc_voxel(sdf + b * gr.vox, gr, i, level, &kase);
+    vflags[b * gr.vox + i] = static_cast<uint8_t>(flags);
+    nv = __popc(flags);
+    nt = kase >= 0 ? __ldg(tri_count + kase) : 0;
+  }
+  // block sums (order-free integer adds)
+  nv = __reduce_add_sync(0xffffffffu, nv);
+  nt = __reduce_add_sync(0xffffffffu, nt);
+  __shared__ int sv[8], stt[8];
+  if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = nv; stt[threadIdx.x >> 5] = nt; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int a = 0, c = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { a += sv[w]; c += stt[w]; }
+    int* cc = chunk_counts + (static_cast<long long>(b) * gr.chunks + blockIdx.x) * 2;
+    cc[0] = a; cc[1] = c;
+  }
+}
+
+// one CTA per object: exclusive scan of the per-chunk (vertex, triangle) counts in place, totals[b] = (V_b, T_b)
+__global__ void __launch_bounds__(1024)
+mc_scan_kernel(int* __restrict__ chunk_counts, int chunks, int* __restrict__ totals) {
+  __shared__ int sv[1024], st[1024];
+  int* cc = chunk_counts + static_cast<long long>(blockIdx.x) * chunks * 2;
+  const int per = (chunks + 1023) / 1024;
+  const int lo = threadIdx.x * per, hi = min(chunks, lo + per);
+  int av = 0, at = 0;
+  for (int c = lo; c < hi; ++c) { av += cc[2 * c]; at += cc[2 * c + 1]; }
+  sv[threadIdx.x] = av; st[threadIdx.x] = at;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {       // Hillis-Steele inclusive scan
+    int tv = 0, tt = 0;
+    if (threadIdx.x >= o) { tv = sv[threadIdx.x - o]; tt = st[threadIdx.x - o]; }
+    __syncthreads();
+    sv[threadIdx.x] += tv; st[threadIdx.x] += tt;
+    __syncthreads();
+  }
+  int bv = sv[threadIdx.x] - av, bt = st[threadIdx.x] - at;
+  for (int c = lo; c < hi; ++c) {
+    const int v = cc[2 * c], t = cc[2 * c + 1];
+    cc[2 * c] = bv; cc[2 * c + 1] = bt;
+    bv += v; bt += t;
+  }
+  if (threadIdx.x == 1023) { totals[2 * blockIdx.x] = sv[1023]; totals[2 * blockIdx.x + 1] = st[1023]; }
+}
+
+__global__ void __launch_bounds__(kMcChunk)
+mc_vertices_kernel(const float* __restrict__ sdf, McGrid gr, double level, double inv_scale, const uint8_t* __restrict__ vflags,
+                   const int* __restrict__ chunk_offsets, const long long* __restrict__ vert_base,
+                   int* __restrict__ voff, float* __restrict__ verts) {
+  const int b = blockIdx.y;
+  const long long i = static_cast<long long>(blockIdx.x) * kMcChunk + threadIdx.x;
+  const bool live = i < gr.vox;
+  const int flags = live ? vflags[b * gr.vox + i] : 0;
+  int total;
+  const int within = mc_block_exclusive_scan(__popc(flags), &total);
+  if (!live) return;
+  int o = chunk_offsets[(static_cast<long long>(b) * gr.chunks + blockIdx.x) * 2] + within;
+  voff[b * gr.vox + i] = o;
+  if (!flags) return;
+  const float* g = sdf + b * gr.vox;
+  const int z = static_cast<int>(i % gr.nz);
+  const int y = static_cast<int>((i / gr.nz) % gr.ny);
+  const int x = static_cast<int>(i / (static_cast<long long>(gr.nz) * gr.ny));
+  const long long stride[3] = {static_cast<long long>(gr.nz) * gr.ny, gr.nz, 1};
+  const double f1 = static_cast<double>(__ldg(g + i));
+  float* out = verts + (vert_base[b] + o) * 3;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    if (!(flags & (1 << a))) continue;
+    const double f2 = static_cast<double>(__ldg(g + i + stride[a]));
+    const double t = __ddiv_rn(__dsub_rn(level, f1), __dsub_rn(f2, f1));
+    double p[3] = {static_cast<double>(x), static_cast<double>(y), static_cast<double>(z)};
+    p[a] = __dadd_rn(p[a], t);
+    // util_3d.py:221  verts_i / n_cell - .5  (float64), then .float()
+#pragma unroll
+    for (int d = 0; d < 3; ++d) out[d] = static_cast<float>(__dsub_rn(__ddiv_rn(p[d], inv_scale), 0.5));
+    out += 3;
+  }
+}
+
+__global__ void __launch_bounds__(kMcChunk)
+mc_triangles_kernel(const float* __restrict__ sdf, McGrid gr, double level, const uint8_t* __restrict__ vflags,
+                    const int* __restrict__ voff, const int* __restrict__ chunk_offsets, const uint8_t* __restrict__ tri_count,
+                    const uint8_t* __restrict__ tri_table, int max_tris, const long long* __restrict__ tri_base,
+                    long long* __restrict__ faces) {
+  const int b = blockIdx.y;
+  const long long i = static_cast<long long>(blockIdx.x) * kMcChunk + threadIdx.x;
+  int kase = -1;
+  if (i < gr.vox) mc_voxel(sdf + b * gr.vox, gr, i, level, &kase);
+  const int nt = kase >= 0 ? __ldg(tri_count + kase) : 0;
+  int total;
+  const int within = mc_block_exclusive_scan(nt, &total);
+  if (!nt) return;
+  const long long sy = gr.nz, sx = static_cast<long long>(gr.nz) * gr.ny;
+  const uint8_t* fl = vflags + b * gr.vox;
+  const int* vo = voff + b * gr.vox;
+  long long* out = faces + (tri_base[b] + chunk_offsets[(static_cast<long long>(b) * gr.chunks + blockIdx.x) * 2 + 1] + within) * 3;
+  const uint8_t* tab = tri_table + kase * max_tris * 3;
+  for (int t = 0; t < nt; ++t) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int e = __ldg(tab + t * 3 + k);     // edge id = 4 * axis + u + 2 v, (u, v) = offsets along the two other axes
+      const int a = e >> 2, u = e & 1, v = (e >> 1) & 1;
+      long long w = i;
+      if (a == 0) w += u * sy + v;              // other axes (y, z)
+      else if (a == 1) w += u * sx + v;         // (x, z)
+      else w += u * sx + v * sy;                // (x, y)
+      const int f = fl[w];
+      out[k] = vo[w] + __popc(f & ((1 << a) - 1));
+    }
+    out += 3;
+  }
+}
+
+static int mc_check(const void* sdf, int B, int nx, int ny, int nz) {
+  if (!sdf || B < 0 || nx < 2 || ny < 2 || nz < 2) return set_error(CS_ERR_INVALID, "surface: need a (B, nx, ny, nz) grid with every extent >= 2");
+  if (static_cast<long long>(nx) * ny * nz > (1ll << 30)) return set_error(CS_ERR_UNSUPPORTED, "surface: grid too large (int32 vertex offsets)");
+  return CS_OK;
+}
+
+static McGrid mc_grid(int nx, int ny, int nz) {
+  McGrid g;
+  g.nx = nx; g.ny = ny; g.nz = nz;
+  g.vox = static_cast<long long>(nx) * ny * nz;
+  g.chunks = static_cast<int>((g.vox + kMcChunk - 1) / kMcChunk);
+  return g;
+}
+
+}  // namespace cs
+
+extern "C" {
+
+int cs_surface_count(const float* sdf, int32_t B, int32_t nx, int32_t ny, int32_t nz, double level, const uint8_t* tri_count,
+                     uint8_t* vflags, int32_t* chunk_counts, int32_t* totals, cs_stream_t stream) {
+  using namespace cs;
+  if (int rc = mc_check(sdf, B, nx, ny, nz)) return rc;
+  if (B == 0) return CS_OK;
+  const McGrid g = mc_grid(nx, ny, nz);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  mc_classify_kernel<<<dim3(g.chunks, B), kMcChunk, 0, st>>>(sdf, g, level, tri_count, vflags, chunk_counts);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(e, "surface_count: classify launch");
+  count_launch();
+  mc_scan_kernel<<<B, 1024, 0, st>>>(chunk_counts, g.chunks, totals);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(e, "surface_count: scan launch");
+  count_launch();
+  return CS_OK;
+}
+
+int cs_surface_emit(const float* sdf, int32_t B, int32_t nx, int32_t ny, int32_t nz, double level, double n_cell,
+                    const uint8_t* vflags, const int32_t* chunk_offsets, const uint8_t* tri_count, const uint8_t* tri_table,
+                    int32_t max_tris, const int64_t* vert_base, const int64_t* tri_base, int32_t* voff, float* verts,
+                    int64_t* faces, cs_stream_t stream) {
+  using namespace cs;
+  if (int rc = mc_check(sdf, B, nx, ny, nz)) return rc;
+  if (B == 0) return CS_OK;
+  if (!(n_cell > 0.0)) return set_error(CS_ERR_INVALID, "surface_emit: n_cell must be positive");
+  const McGrid g = mc_grid(nx, ny, nz);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  mc_vertices_kernel<<<dim3(g.chunks, B), kMcChunk, 0, st>>>(sdf, g, level, n_cell, vflags, chunk_offsets,
+                                                             reinterpret_cast<const long long*>(vert_base), voff, verts);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(e, "surface_emit: vertex launch");
+  count_launch();
+  if (faces) {
+    if (!tri_table || !tri_count || max_tris < 1) return set_error(CS_ERR_INVALID, "surface_emit: triangle table missing");
+    mc_triangles_kernel<<<dim3(g.chunks, B), kMcChunk, 0, st>>>(sdf, g, level, vflags, voff, chunk_offsets, tri_count, tri_table,
+                                                                max_tris, reinterpret_cast<const long long*>(tri_base),
+                                                                reinterpret_cast<long long*>(faces));
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error(e, "surface_emit: triangle launch");
+    count_launch();
+  }
+  return CS_OK;
+}
+
+}  // extern "C"

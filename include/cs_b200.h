@@ -312,6 +312,25 @@ int cs_match_cost(const float* xyz1, const float* xyz2, const float* match, int3
 int cs_match_cost_grad(const float* xyz1, const float* xyz2, const float* match, int32_t b, int32_t n, int32_t m, float* grad1,
                        float* grad2, cs_stream_t stream);
 
+/* ---- SDF grid -> iso-surface points (+ triangles): the step between the decoded 64^3 SDFs and the point-cloud distances
+ * (model/diff_utils/util_3d.py:194-235 sdf_to_mesh = mcubes.marching_cubes per object on the CPU, `verts / n_cell - .5`;
+ * scripts/eval_3dfront.py:313-317, 589-592 consume the vertices only).  sdf: (B, nx, ny, nz) fp32 contiguous; a corner is
+ * inside when value <= level; one vertex per grid edge whose corners differ, at x1 + (level - f1) / (f2 - f1) in double
+ * precision; order = (voxel linear index, axis).  Two calls with ONE host read of `totals` in between (it sizes the
+ * outputs): ---- */
+/* pass 1: vflags (B * nx*ny*nz) u8 edge flags per voxel, chunk_counts (B, ceil(vox / 256), 2) int32 = per-object EXCLUSIVE
+ * prefix of (vertices, triangles) per 256-voxel chunk, totals (B, 2) int32 = (vertices, triangles) per object.
+ * tri_count: device (256,) u8 triangles per cell case (bit c of the case = corner c = dx + 2 dy + 4 dz inside). */
+int cs_surface_count(const float* sdf, int32_t B, int32_t nx, int32_t ny, int32_t nz, double level, const uint8_t* tri_count,
+                     uint8_t* vflags, int32_t* chunk_counts, int32_t* totals, cs_stream_t stream);
+/* pass 2: verts (sum V, 3) fp32 = index coordinates / n_cell - 0.5, object b starting at row vert_base[b]; voff (B * vox)
+ * int32 scratch (vertex offset of every voxel); faces (sum T, 3) int64 of per-object vertex indices from row tri_base[b],
+ * or NULL to skip the triangles.  tri_table: device (256, max_tris, 3) u8 edge ids (4 * axis + u + 2 v). */
+int cs_surface_emit(const float* sdf, int32_t B, int32_t nx, int32_t ny, int32_t nz, double level, double n_cell,
+                    const uint8_t* vflags, const int32_t* chunk_offsets, const uint8_t* tri_count, const uint8_t* tri_table,
+                    int32_t max_tris, const int64_t* vert_base, const int64_t* tri_base, int32_t* voff, float* verts,
+                    int64_t* faces, cs_stream_t stream);
+
 /* tuning experiments only (tools/): bit 0 = drop the epilogue's global stores, bit 1 = empty epilogue, bit 2 = no MMA.
  * Results are WRONG while any bit is set; 0 restores normal operation. */
 void cs_debug_set(int32_t flags);

@@ -378,6 +378,21 @@ def main():
                                          unconditional_guidance_scale=3.0, unconditional_conditioning=ucvol)
             xo, p0o, _ = D.p_sample_ddim(csd, D.UNET_CONCAT_TINY, ddc, x0c, cvol, step, index, 3.0, ucvol, concat=True)
             ok &= _cmp(f"DDIMSampler.p_sample_ddim[concat, index {index}].x_prev", xo, xr) and _cmp("  pred_x0", p0o, p0r)
+    # helpers/util.py:31-45 sample_points: the file imports pytorch3d (absent), so only that function's source is executed
+    import ast
+    src = open(os.path.join(REF, "helpers", "util.py")).read()
+    fn = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "sample_points")
+    ns = {"torch": torch}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "helpers/util.py", "exec"), ns)
+    from oracle import mesh as M
+    for n_pts in (12000, 700):
+        pts = torch.randn(n_pts, 3, generator=g)
+        torch.manual_seed(5)
+        (r,) = ns["sample_points"]([pts], 5000)
+        torch.manual_seed(5)
+        o = pts[M.sample_points_indices(n_pts, 5000)]
+        ok &= _cmp(f"helpers.util.sample_points[{n_pts} -> 5000]", o, r, tol=0.0)
+    print("sdf_to_mesh: PyMCubes / pytorch3d are absent here -- oracle/mesh.py is pinned by properties only (parity unpinned)")
     print("ORACLE PINNED" if ok else "ORACLE MISMATCH")
     return 0 if ok else 1
 
