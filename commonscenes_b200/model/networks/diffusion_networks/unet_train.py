@@ -31,13 +31,23 @@ from .openai_model_3d import Act, AttentionBlock, Downsample, QKVAttention, ResB
 class GradSink:
     """fp32 gradient tensors keyed by parameter (created zeroed on first use, or views into a caller-provided flat buffer)."""
 
-    def __init__(self, views: Optional[Dict[nn.Parameter, torch.Tensor]] = None):
+    def __init__(self, views: Optional[Dict[nn.Parameter, torch.Tensor]] = None,
+                 packed: Optional[Dict[nn.Parameter, torch.Tensor]] = None):
+        """packed: parameters whose gradient is kept in the weight-gradient kernel's PACKED layout (Cout, taps, padded Cin)
+        -- slots of a flat buffer that the fused optimizer (cs_adamw_repack) reads directly; they have no parameter-layout
+        gradient tensor at all."""
         self.views = views
+        self.packed = packed or {}
         self.grads: Dict[nn.Parameter, torch.Tensor] = {}
+
+    def packed_slot(self, p: Optional[nn.Parameter]) -> Optional[torch.Tensor]:
+        return None if p is None else self.packed.get(p)
 
     def grad(self, p: nn.Parameter) -> torch.Tensor:
         g = self.grads.get(p)
         if g is None:
+            if p in self.packed:
+                raise KeyError("this parameter's gradient lives in a packed slot (GradSink.packed_slot); use ops_bwd.unpack_wgrad")
             g = self.views[p] if self.views is not None else torch.zeros(p.shape, dtype=torch.float32, device=p.device)
             self.grads[p] = g
         return g
@@ -154,6 +164,13 @@ class UNetTrainer:
         c2 = 0 if x2 is None else x2.shape[-1]
         co, taps = dy.shape[-1], ksize[0] * ksize[1] * ksize[2]
         cp = ops._pad64(c1) + ops._pad64(c2)
+        slot = sink.packed_slot(param)
+        if slot is not None:
+            # fused-optimizer mode: accumulate straight into the parameter's packed slot (zeroed by the previous update)
+            if tuple(slot.shape) != (co, taps, cp):
+                raise RuntimeError(f"packed gradient slot {tuple(slot.shape)} does not match the layer ({co}, {taps}, {cp})")
+            ops_bwd.conv3d_wgrad(x, dy, slot, ksize=ksize, stride=stride, pad=pad, x2=x2)
+            return None
         if param is not None and taps == 1 and x2 is None and cp == c1:
             # a linear layer without channel padding: the packed gradient layout IS the parameter's (out, in) layout
             ops_bwd.conv3d_wgrad(x, dy, sink.grad(param).view(co, 1, c1), ksize=ksize, stride=stride, pad=pad)

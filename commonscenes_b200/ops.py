@@ -107,6 +107,15 @@ def _pad_k(wt: torch.Tensor, split=None) -> torch.Tensor:
 _PACK_BUFFERS = {}
 
 
+# Keys of cached pack buffers that somebody else keeps current (the fused optimizer kernel cs_adamw_repack rewrites the bf16
+# packs of the weights it updates): pack_conv_weight / pack_dgrad_weight return such a buffer without launching.
+_PACK_MAINTAINED = set()
+
+
+def _pack_key(kind: str, owner, shape):
+    return (kind, id(owner), tuple(shape))
+
+
 def _pack_buffer(kind: str, owner, shape, device) -> torch.Tensor:
     """Destination of a device-side weight pack.  For an nn.Parameter `owner` the buffer is cached per (layout, parameter):
     the pack kernels never write the pad columns, so it is zero-filled ONCE and re-packed in place after every optimizer
@@ -136,7 +145,10 @@ def pack_conv_weight(w: torch.Tensor, split=None, owner=None) -> torch.Tensor:
         parts = [ci] if split is None else [int(c) for c in split]
         if sum(parts) != ci:
             raise _lib.CsError(f"pack: channel split {parts} does not sum to {ci}")
-        out = _pack_buffer("fwd" + str(tuple(parts)), owner if owner is not None else w, (co, taps, sum(_pad64(c) for c in parts)), w.device)
+        own, kind, shape = owner if owner is not None else w, "fwd" + str(tuple(parts)), (co, taps, sum(_pad64(c) for c in parts))
+        out = _pack_buffer(kind, own, shape, w.device)
+        if _pack_key(kind, own, shape) in _PACK_MAINTAINED:
+            return out
         check(_lib.load().cs_pack_weight(wd.data_ptr(), co, ci, taps, parts[0], out.data_ptr(), None, _stream()), "cs_pack_weight")
         return out
     return _pad_k(wd.reshape(co, ci, -1).permute(0, 2, 1), split)

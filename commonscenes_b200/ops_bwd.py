@@ -72,8 +72,11 @@ def pack_dgrad_weight(w: torch.Tensor, owner=None) -> torch.Tensor:
     wd = w.detach()
     if wd.is_cuda and wd.dtype == torch.float32 and wd.is_contiguous():
         taps = wd.numel() // (co * ci)
-        from .ops import _pack_buffer
-        out = _pack_buffer("dgrad", owner if owner is not None else w, (ci, taps, _pad64(co)), w.device)
+        from .ops import _pack_buffer, _pack_key, _PACK_MAINTAINED
+        own, shape = owner if owner is not None else w, (ci, taps, _pad64(co))
+        out = _pack_buffer("dgrad", own, shape, w.device)
+        if _pack_key("dgrad", own, shape) in _PACK_MAINTAINED:
+            return out
         check(_lib.load().cs_pack_weight(wd.data_ptr(), co, ci, taps, ci, None, out.data_ptr(), _stream()), "cs_pack_weight")
         return out
     wt = wd.reshape(co, ci, -1).flip(2).permute(1, 2, 0)     # (Cin, taps flipped, Cout)

@@ -19,11 +19,14 @@ from __future__ import annotations
 
 from typing import Dict, List, Optional
 
+import ctypes as C
+import os
+
 import torch
 import torch.distributed as dist
 import torch.nn as nn
 
-from . import ops, ops_bwd
+from . import _lib, ops, ops_bwd
 from .model.networks.diffusion_networks.unet_train import GradSink
 
 
@@ -77,13 +80,25 @@ def load_flat_optimizer_state(sd: dict, params, offsets, flat_m, flat_v) -> int:
     return step
 
 
+class _RepackEntry(C.Structure):
+    """cs_repack_entry of include/cs_b200.h."""
+    _fields_ = [("p_off", C.c_int64), ("g_off", C.c_int64), ("first_tile", C.c_int64), ("fwd", C.c_void_p), ("dgrad", C.c_void_p),
+                ("Cout", C.c_int32), ("Cin", C.c_int32), ("taps", C.c_int32), ("C1", C.c_int32), ("group", C.c_int32), ("reserved", C.c_int32)]
+
+
 class DenoiserTrainStep:
     def __init__(self, diff_model, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.01,
                  max_grad_norm: float = 5.0, loss_scale: float = 100.0, group: Optional[dist.ProcessGroup] = None,
-                 bucket_mb: int = 256):
+                 bucket_mb: int = 256, fused_update: Optional[bool] = None):
         """diff_model: SDFusionText2ShapeModel mirror (uses .df.diffusion_net, the schedule tables and q_sample).
         Defaults follow the reference: AdamW lr 1e-4 (VAEGAN_V2FULL.py:642-650; torch's default betas/eps/decay), clip 5.0
-        (train_3dfront.py:399), total loss weight 100 on loss_df (train_3dfront.py:387)."""
+        (train_3dfront.py:399), total loss weight 100 on loss_df (train_3dfront.py:387).
+
+        fused_update (default: on for CUDA parameters): the GEMM-class weights that have both kernel-layout packs keep their
+        gradient in the weight-gradient kernel's packed layout and are updated by ONE cs_adamw_repack launch (clip + AdamW +
+        both bf16 re-packs + clearing the gradient), instead of un-pack / AdamW / two pack kernels per weight.  The flat
+        buffers then hold the remaining ("plain") parameters first and those weights after them; `offsets` is still the
+        position of every parameter in flat_p / flat_m / flat_v, `flat_g` is laid out [plain | packed slots]."""
         self.model = diff_model
         self.unet = diff_model.df.diffusion_net
         self.trainer = self.unet.trainer()
@@ -94,32 +109,134 @@ class DenoiserTrainStep:
         self.step_count = 0
         params = [p for p in self.unet.parameters() if p.requires_grad]
         dev = params[0].device
-        sizes = [(p.numel() + 3) // 4 * 4 for p in params]          # keep every view 16-byte aligned
-        total = sum(sizes)
+        self.fused = (dev.type == "cuda") if fused_update is None else (bool(fused_update) and dev.type == "cuda")
+        regular = self._discover_packed_weights(params) if self.fused else {}
+        self.fused = bool(regular)
+        plain = [p for p in params if p not in regular]
+        packed = [p for p in params if p in regular]
+        order = plain + packed                                      # flat layout; `params` keeps the module's order
+        sizes = {p: (p.numel() + 3) // 4 * 4 for p in params}       # keep every view 16-byte aligned
+        total = sum(sizes.values())
+        self.n_plain = sum(sizes[p] for p in plain)
+        g_sizes = {p: (regular[p]["slot"] if p in regular else sizes[p]) for p in params}
         self.flat_p = torch.zeros(total, dtype=torch.float32, device=dev)
-        self.flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_g = torch.zeros(sum(g_sizes.values()), dtype=torch.float32, device=dev)
         self.flat_m = torch.zeros(total, dtype=torch.float32, device=dev)
         self.flat_v = torch.zeros(total, dtype=torch.float32, device=dev)
         self.views: Dict[nn.Parameter, torch.Tensor] = {}
+        self.packed_views: Dict[nn.Parameter, torch.Tensor] = {}
         self.offsets: Dict[nn.Parameter, int] = {}
-        off = 0
+        self.g_offsets: Dict[nn.Parameter, int] = {}
+        off = goff = 0
         with torch.no_grad():
-            for p, n in zip(params, sizes):
+            for p in order:
                 v = self.flat_p[off:off + p.numel()].view(p.shape)
                 v.copy_(p.data)
                 p.data = v
-                self.views[p] = self.flat_g[off:off + p.numel()].view(p.shape)
-                self.offsets[p] = off
-                off += n
+                if p in regular:
+                    r = regular[p]
+                    self.packed_views[p] = self.flat_g[goff:goff + r["slot"]].view(r["Cout"], r["taps"], r["ctot"])
+                else:
+                    self.views[p] = self.flat_g[goff:goff + p.numel()].view(p.shape)
+                self.offsets[p], self.g_offsets[p] = off, goff
+                off += sizes[p]
+                goff += g_sizes[p]
         self.params = params
+        # "everything at or after this flat_g offset is final once the backward has passed parameter p": the packed slots follow
+        # the module's parameter order (the backward finishes them from the last to the first), the plain region in front of
+        # them is only final when the whole backward is (time_embed comes last)
+        self._final_from: Dict[nn.Parameter, int] = {}
+        nxt = int(self.flat_g.numel())
+        for p in reversed(params):
+            if p in regular:
+                nxt = self.g_offsets[p]
+            self._final_from[p] = nxt if self.fused else self.g_offsets[p]
         self.step_dev = torch.zeros((), dtype=torch.int32, device=dev)     # device copy of step_count (graph replays)
         self.graph = None
         self.sumsq = torch.zeros((), dtype=torch.float32, device=dev)
         self.loss = torch.zeros((), dtype=torch.float32, device=dev)
-        # gradient buckets in parameter order; the backward fills them from the last to the first
-        self.buckets: List[tuple] = make_buckets(sizes, bucket_mb * (1 << 20) // 4)
+        # gradient buckets in flat_g order; the backward fills them from the last to the first
+        self.buckets: List[tuple] = make_buckets([g_sizes[p] for p in order], bucket_mb * (1 << 20) // 4)
         self.comm_stream = torch.cuda.Stream(device=dev) if self.world > 1 else None
         self.unet._packed = None        # parameters moved: rebuild the kernel-layout copies
+        if self.fused:
+            self._build_repack_table(packed, regular)
+            self.refresh_packs()
+
+    # ------------------------------------------------------------------------------------------
+    # fused optimizer: packed-gradient weights
+    # ------------------------------------------------------------------------------------------
+    def _discover_packed_weights(self, params) -> dict:
+        """The parameters whose forward AND data-gradient kernel layouts are plain re-orderings of the parameter itself
+        (ResBlock / Down / Upsample convs, skip 1x1x1s, proj_in / proj_out, to_out, ff.net[2]): they own one cached "fwd" and
+        one "dgrad" pack buffer after a pack pass.  Weights packed through a re-arranged temporary (q|k|v, GEGLU rows,
+        up-sample phase filters, the few-channel stem / head) stay on the un-pack + cs_adamw + cs_pack_weight path."""
+        import ast
+        from . import ops as _ops
+        self.unet._packed = None
+        self.trainer._ensure()
+        by_id = {id(p): p for p in params}
+        found: Dict[nn.Parameter, dict] = {}
+        for (kind, pid, shape), (ref, buf) in list(_ops._PACK_BUFFERS.items()):
+            p = by_id.get(pid)
+            if p is None or ref() is not p or buf.device != p.device:
+                continue
+            d = found.setdefault(p, {"fwd": []})
+            if kind == "dgrad":
+                d["dgrad"] = (buf, (kind, pid, shape))
+            elif kind.startswith("fwd"):
+                d["fwd"].append((buf, (kind, pid, shape), ast.literal_eval(kind[3:])))
+        regular = {}
+        for p, d in found.items():
+            if "dgrad" not in d or len(d["fwd"]) != 1:
+                continue
+            fwd, fkey, parts = d["fwd"][0]
+            co, ci = p.shape[0], p.shape[1]
+            taps = p.numel() // (co * ci)
+            ctot = fwd.shape[2]
+            if co % 8 or ci % 8 or parts[0] % 8 or tuple(fwd.shape) != (co, taps, ctot) or tuple(d["dgrad"][0].shape) != (ci, taps, _ops._pad64(co)):
+                continue
+            regular[p] = dict(fwd=fwd, dgrad=d["dgrad"][0], keys=(fkey, d["dgrad"][1]), Cout=co, Cin=ci, taps=taps, C1=int(parts[0]),
+                              ctot=ctot, slot=co * taps * ctot)
+        return regular
+
+    def _build_repack_table(self, packed, regular) -> None:
+        entries = (_RepackEntry * len(packed))()
+        self._repack_tile_ci = int(os.environ.get("CS_REPACK_TILE_CI", "32"))     # 16 or 32 input channels per tile
+        tile = 0
+        self._regular_keys = []
+        for i, p in enumerate(packed):
+            r = regular[p]
+            group = max(1, 27 // r["taps"])      # ci tiles per CTA: a 1x1x1 weight gets CTAs as large as a 3x3x3 one
+            entries[i] = _RepackEntry(self.offsets[p], self.g_offsets[p], tile, r["fwd"].data_ptr(), r["dgrad"].data_ptr(),
+                                      r["Cout"], r["Cin"], r["taps"], r["C1"], group, 0)
+            tiles_ci = (r["Cin"] + self._repack_tile_ci - 1) // self._repack_tile_ci
+            tile += ((r["Cout"] + 15) // 16) * ((tiles_ci + group - 1) // group)
+            self._regular_keys += list(r["keys"])
+        raw = torch.frombuffer(bytearray(bytes(entries)), dtype=torch.uint8).clone()
+        self._repack_table = raw.to(self.flat_p.device)
+        self._repack_n, self._repack_tiles = len(packed), tile
+        self._repack_taps = max(regular[p]["taps"] for p in packed)
+        self._repack_params = packed
+        self._repack_keep = [regular[p]["fwd"] for p in packed] + [regular[p]["dgrad"] for p in packed]     # keep the buffers alive
+        self._regular_versions = None
+
+    def refresh_packs(self) -> None:
+        """Rebuild the bf16 packs of the fused-update weights from the fp32 master weights with the stand-alone pack kernels
+        (after anything other than cs_adamw_repack changed them: construction, load_state_dict, a rolled-back warm-up)."""
+        if not self.fused:
+            self.unet._packed = None
+            return
+        from . import ops as _ops
+        _ops._PACK_MAINTAINED.difference_update(self._regular_keys)
+        self.unet._packed = None
+        self.trainer._ensure()
+        _ops._PACK_MAINTAINED.update(self._regular_keys)
+        self._regular_versions = sum(p._version for p in self._repack_params)
+
+    def _check_packs_current(self) -> None:
+        if self.fused and sum(p._version for p in self._repack_params) != self._regular_versions:
+            self.refresh_packs()        # somebody wrote the parameters through torch (load_state_dict, an initialiser)
 
     # ------------------------------------------------------------------------------------------
     def _allreduce_ready(self, done_off: int, pending: List[int]):
@@ -149,29 +266,34 @@ class DenoiserTrainStep:
             t = torch.randint(0, m.num_timesteps, (B,), device=dev).long()
         if noise is None:
             noise = torch.randn_like(z)
+        self._check_packs_current()
         x_t = m.q_sample(z, t, noise)
         eps, tape = self.trainer.forward_train(x_t, t, cond)
         self.loss.zero_()
         d_eps = ops_bwd.mse_loss_grad(eps, noise.float().contiguous(), self.loss, loss_scale=self.loss_scale * grad_weight)
-        self.flat_g.zero_()
-        sink = GradSink(self.views)
+        self._zero_grads()
+        sink = GradSink(self.views, self.packed_views)
         if self.world > 1:
             pending = list(range(len(self.buckets)))
             # the backward visits layers in reverse parameter order: once a layer is done, its gradients and those of every
             # later parameter are final, so the buckets lying wholly beyond that offset can be reduced while the backward
             # continues (time_embed comes last: bucket 0 goes out after the backward).
             _, d_ctx = self.trainer.backward(tape, d_eps, sink=sink, need_dcontext=need_dcond,
-                                             on_block_done=lambda p: self._allreduce_ready(self.offsets[p], pending))
+                                             on_block_done=lambda p: self._allreduce_ready(self._final_from[p], pending))
             self._allreduce_ready(0, pending)
             torch.cuda.current_stream().wait_stream(self.comm_stream)
         else:
             _, d_ctx = self.trainer.backward(tape, d_eps, sink=sink, need_dcontext=need_dcond)
         return self._clip_and_update(d_ctx)
 
+    def _zero_grads(self) -> None:
+        # the packed slots were cleared by the previous cs_adamw_repack (and start zeroed): only the plain region needs a memset
+        (self.flat_g[:self.n_plain] if self.fused else self.flat_g).zero_()
+
     def _step_without_objects(self, cond):
         """This rank holds no object of the global batch: zero gradients into every bucket's all-reduce, same update."""
         self.loss.zero_()
-        self.flat_g.zero_()
+        self._zero_grads()
         if self.world > 1:
             self._allreduce_ready(0, list(range(len(self.buckets))))
             if self.comm_stream is not None:
@@ -185,9 +307,16 @@ class DenoiserTrainStep:
         ops_bwd.sumsq(self.flat_g, self.sumsq)
         # gradients were summed over ranks: the mean (DDP semantics) is a scale folded into the optimizer kernel
         gscale = 1.0 / self.world
-        ops_bwd.adamw_step(self.flat_p, self.flat_g, self.flat_m, self.flat_v, lr=self.lr, betas=self.betas, eps=self.eps,
-                           weight_decay=self.weight_decay, sumsq_buf=self.sumsq, max_norm=self.max_grad_norm, grad_scale=gscale,
-                           step_dev=self.step_dev)
+        n = self.n_plain if self.fused else self.flat_p.numel()
+        ops_bwd.adamw_step(self.flat_p[:n], self.flat_g[:n], self.flat_m[:n], self.flat_v[:n], lr=self.lr, betas=self.betas,
+                           eps=self.eps, weight_decay=self.weight_decay, sumsq_buf=self.sumsq, max_norm=self.max_grad_norm,
+                           grad_scale=gscale, step_dev=self.step_dev)
+        if self.fused:
+            _lib.check(_lib.load().cs_adamw_repack(
+                self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.flat_m.data_ptr(), self.flat_v.data_ptr(),
+                self._repack_table.data_ptr(), self._repack_n, self._repack_tiles, self._repack_taps, self._repack_tile_ci, self.lr, self.betas[0],
+                self.betas[1], self.eps, self.weight_decay, 0, self.sumsq.data_ptr(), self.max_grad_norm, gscale,
+                self.step_dev.data_ptr(), torch.cuda.current_stream().cuda_stream), "cs_adamw_repack")
         self.unet._packed = None        # weights changed in place (kernel write: no autograd version bump)
         return self.loss, d_ctx
 
@@ -233,7 +362,7 @@ class DenoiserTrainStep:
         with torch.cuda.graph(g):
             self._gout = self.step(self._gz, self._gc, t=self._gt, noise=self._gn, need_dcond=need_dcond)
         restore()      # capture does not execute, but step() bumped the host-side counter
-        self.unet._packed = None
+        self.refresh_packs()        # the warm-up updates rewrote the fused-update packs: rebuild them from the restored weights
         self.graph = g
 
     def step_graphed(self, z: torch.Tensor, cond: torch.Tensor, t: Optional[torch.Tensor] = None,
@@ -242,6 +371,7 @@ class DenoiserTrainStep:
         are overwritten by the next replay."""
         if self.graph is None:
             raise RuntimeError("DenoiserTrainStep.step_graphed: call capture() first")
+        self._check_packs_current()
         self._gz.copy_(z)
         self._gc.copy_(cond)
         if t is None:
@@ -419,7 +549,7 @@ class ShapeBranchTrainStep:
         with torch.cuda.graph(g):
             self._gout = run()
         restore()                       # capture does not execute, but step() bumped the host-side counters
-        d.unet._packed = None
+        d.refresh_packs()               # (the warm-up updates rewrote the fused-update packs)
         self.graph = g
 
     def step_graphed(self, z, objs, triples, text_feat, rel_feat, sdfs, rows: Optional[torch.Tensor] = None,
@@ -428,6 +558,7 @@ class ShapeBranchTrainStep:
         rank (same count as captured; default: the captured rows).  Returns (loss, d_z): overwritten by the next replay."""
         if getattr(self, "graph", None) is None:
             raise RuntimeError("ShapeBranchTrainStep.step_graphed: call capture() first")
+        self.denoiser._check_packs_current()
         st = self._s
         for key, src in (("z", z), ("objs", objs), ("triples", triples), ("text", text_feat), ("rel", rel_feat), ("sdfs", sdfs)):
             if tuple(src.shape) != tuple(st[key].shape):

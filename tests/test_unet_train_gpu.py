@@ -319,3 +319,70 @@ def test_concat_unet_backward_matches_oracle_autograd():
     print(f"concat variant: whole-gradient rel-L2 {total_rel:.3e}, cosine {cos:.6f}; d c_concat rel-L2 {rel_cc:.3e}")
     # measured 2.0e-2 / 0.9998 / 2.1e-2 (tiny configuration, every activation and activation gradient in bf16)
     assert total_rel < 4e-2 and cos > 0.999 and rel_cc < 4e-2
+
+
+def test_fused_update_equals_the_separate_kernels():
+    """cs_adamw_repack (packed-gradient slots -> clip + AdamW + both bf16 packs in one pass) against the un-pack / cs_adamw /
+    cs_pack_weight sequence it replaces: same parameters and moments after two steps, and the packs it maintains equal a
+    fresh pack of the updated weights (evaluation through them == evaluation of a module freshly loaded with those weights)."""
+    from commonscenes_b200.model.sdfusion_txt2shape_model import SDFusionText2ShapeModel, diffusion_schedule
+    from commonscenes_b200.train import DenoiserTrainStep
+    cfg = D.UNET_TINY
+
+    class Stub:
+        q_sample = SDFusionText2ShapeModel.q_sample
+        z_shape = (3, 8, 8, 8)
+
+        def __init__(self, df):
+            self.df, self.num_timesteps, self.device = df, 1000, "cuda"
+            for k, v in diffusion_schedule(1000, 0.00085, 0.012).items():
+                setattr(self, k, v.cuda())
+
+    g = torch.Generator().manual_seed(14)
+    B = 4
+    z = torch.randn(B, 3, 8, 8, 8, generator=g).cuda()
+    ctx = torch.randn(B, 1, cfg["context_dim"], generator=g).cuda()
+    t = torch.tensor([10, 999, 500, 250]).cuda()
+    noise = torch.randn(B, 3, 8, 8, 8, generator=g).cuda()
+    ma, mb, fresh = _build(cfg, 64), _build(cfg, 64), _build(cfg, 64)
+    p_start = {n: p.detach().clone() for n, p in ma.named_parameters()}
+    sa, sb = DenoiserTrainStep(Stub(ma), lr=1e-3, fused_update=False), DenoiserTrainStep(Stub(mb), lr=1e-3)
+    assert sb.fused and not sa.fused
+    n_packed = sum(p.numel() for p in sb.packed_views)
+    print(f"fused-update weights: {len(sb.packed_views)} tensors, {n_packed / sum(p.numel() for p in sb.params):.1%} of the parameters")
+    assert len(sb.packed_views) >= 10
+    for it in range(2):
+        la, _ = sa.step(z, ctx, t=t, noise=noise)
+        lb, _ = sb.step(z, ctx, t=t, noise=noise)
+        assert abs(la.item() - lb.item()) <= 1e-3 * abs(la.item())
+        if it == 0:
+            # after ONE step the moments are the clipped gradients themselves ((1 - beta) g, (1 - beta2) g^2): a direct comparison
+            # of the packed-slot gradients with the un-packed ones, parameter by parameter (two launches of the fp32-atomic
+            # weight-gradient kernel differ by rounding only)
+            oa, ob = sa.optimizer_state_dict(), sb.optimizer_state_dict()
+            worst = 0.0
+            for i in oa["state"]:
+                for k in ("exp_avg", "exp_avg_sq"):
+                    a, b = oa["state"][i][k], ob["state"][i][k]
+                    worst = max(worst, float((a - b).norm()) / (float(a.norm()) + 1e-30))
+            print(f"fused vs separate: worst per-parameter moment rel-L2 after 1 step {worst:.3e}")
+            assert worst < 1e-4
+    num = den = 0.0
+    for (n, pa), (_, pb) in zip(ma.named_parameters(), mb.named_parameters()):
+        ua, ub = pa.detach() - p_start[n], pb.detach() - p_start[n]
+        num += float((ua - ub).double().pow(2).sum()); den += float(ua.double().pow(2).sum())
+    print(f"fused vs separate: parameter-update rel-L2 after 2 steps {(num / den) ** 0.5:.3e}")
+    assert (num / den) ** 0.5 < 5e-2          # rounding noise through AdamW's sign-like first steps at lr 1e-3, not layout errors
+    assert float(sb.flat_g[sb.n_plain:].abs().max()) == 0.0     # the packed slots were cleared by the update
+    with torch.no_grad():
+        got = mb(z, t, c_crossattn=[ctx])
+        fresh.load_state_dict(mb.state_dict())
+        want = fresh(z, t, c_crossattn=[ctx])
+    assert torch.equal(got, want), "packs written by cs_adamw_repack differ from a fresh pack of the same weights"
+    # parameters written through torch (a checkpoint load) are noticed and re-packed
+    with torch.no_grad():
+        mb.load_state_dict(ma.state_dict())
+    sb.step(z, ctx, t=t, noise=noise); sa.step(z, ctx, t=t, noise=noise)
+    with torch.no_grad():
+        fresh.load_state_dict(mb.state_dict())
+        assert torch.equal(mb(z, t, c_crossattn=[ctx]), fresh(z, t, c_crossattn=[ctx]))

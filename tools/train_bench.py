@@ -73,11 +73,9 @@ d_eps = ops_bwd.mse_loss_grad(eps, noise, lbuf, loss_scale=100.0)
 ops.reset_launch_count()
 ms_bwd, _ = timed(lambda: tr.backward(tr.forward_train(x_t, t, ctx)[1], d_eps, need_dcontext=False))
 launches = ops.launch_count() / 3
-ms_opt, _ = timed(lambda: (step.sumsq.zero_(), ops_bwd.sumsq(step.flat_g, step.sumsq),
-                           ops_bwd.adamw_step(step.flat_p, step.flat_g, step.flat_m, step.flat_v, lr=1e-4, step=3,
-                                              sumsq_buf=step.sumsq, max_norm=5.0)))
+ms_opt, _ = timed(lambda: step._clip_and_update(None))      # sumsq + AdamW (+ the fused re-pack of the packed-gradient weights)
 print(f"re-pack (fwd + dgrad layouts): {ms_pack:.1f} ms | forward_train {ms_fwd:.1f} ms | fwd+backward {ms_bwd:.1f} ms "
-      f"(backward ~{ms_bwd - ms_fwd:.1f} ms, {launches:.0f} launches fwd+bwd) | sumsq+adamw {ms_opt:.2f} ms")
+      f"(backward ~{ms_bwd - ms_fwd:.1f} ms, {launches:.0f} launches fwd+bwd) | clip + optimizer (+ fused re-pack) {ms_opt:.2f} ms")
 print(f"memory: allocated {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB peak")
 if "--profile" in sys.argv:
     from torch.profiler import profile, ProfilerActivity
