@@ -106,7 +106,18 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ C
         const uint32_t tx = static_cast<uint32_t>((it.nblk_a + nblk_b) * p.rows * 128);
         const CUtensorMap* tmx = it.src ? &tmX2 : &tmX1;
         const int n0 = it.nt * p.BN;
-        for (int c = it.c_first; c < it.c_last; ++c) {
+        // Experiment switch (CS_WGRAD_ROTATE=1, off by default).  The main loop is operand-delivery bound: issuing HALF the
+        // MMAs (CS_WGRAD_ORDER=2) leaves the kernel time unchanged (0.351 vs 0.358 ms, profiles/r2y_wgrad_experiments.log).  The
+        // items that share a voxel range walk it in lock step and ask the same L2 lines at the same instant; starting every
+        // item at its own rotation of the range (to spread the requests over the L2 slices) was measured SLOWER (18.8 vs
+        // 17.8 ms over the UNet's shapes): the lock step is what keeps the shared operands hot, so it stays.
+        const int n_ch = it.c_last - it.c_first;
+        const int units = p.ntaps * p.n_pairs * p.n_tiles;
+        const int rot = (p.rotate && n_ch > 0) ? static_cast<int>((static_cast<long long>(item % units) * n_ch) / units) : 0;
+        for (int cc = 0; cc < n_ch; ++cc) {
+          int c = cc + rot;
+          if (c >= n_ch) c -= n_ch;
+          c += it.c_first;
           int m = c;
           const int tw = m % tiles_w; m /= tiles_w;
           const int th = m % tiles_h; m /= tiles_h;
@@ -146,12 +157,26 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ C
           const uint32_t a_lo = ((sa >> 4) & 0x3FFFu) | lbo_bits;
           const uint32_t a2_lo = (((sa + 2 * kBlkBytes) >> 4) & 0x3FFFu) | lbo_bits;
           const uint32_t b_lo = (((sa + 4 * kBlkBytes) >> 4) & 0x3FFFu) | lbo_bits;
+          if (p.mma_order == 0) {
 #pragma unroll 4
-          for (int k = 0; k < ksteps; ++k) {
-            // 16 voxels = two 8-row swizzle atoms = 2048 B = 128 encoded address units
-            const uint64_t bd = (static_cast<uint64_t>(desc_hi) << 32) | (b_lo + 128u * k);
-            umma_bf16(tmem_base, (static_cast<uint64_t>(desc_hi) << 32) | (a_lo + 128u * k), bd, idesc, accumulate);
-            if (two) umma_bf16(tmem_base + 256u, (static_cast<uint64_t>(desc_hi) << 32) | (a2_lo + 128u * k), bd, idesc, accumulate);
+            for (int k = 0; k < ksteps; ++k) {
+              // 16 voxels = two 8-row swizzle atoms = 2048 B = 128 encoded address units
+              const uint64_t bd = (static_cast<uint64_t>(desc_hi) << 32) | (b_lo + 128u * k);
+              umma_bf16(tmem_base, (static_cast<uint64_t>(desc_hi) << 32) | (a_lo + 128u * k), bd, idesc, accumulate);
+              if (two) umma_bf16(tmem_base + 256u, (static_cast<uint64_t>(desc_hi) << 32) | (a2_lo + 128u * k), bd, idesc, accumulate);
+              accumulate = 1;
+            }
+          } else {      // experiment (CS_WGRAD_ORDER=1): one accumulator's K steps back to back, then the other's
+#pragma unroll 4
+            for (int k = 0; k < ksteps; ++k)
+              umma_bf16(tmem_base, (static_cast<uint64_t>(desc_hi) << 32) | (a_lo + 128u * k),
+                        (static_cast<uint64_t>(desc_hi) << 32) | (b_lo + 128u * k), idesc, k ? 1u : accumulate);
+            if (two && p.mma_order != 2) {      // 2 = diagnostic: skip the second accumulator (WRONG results; is the loop load- or MMA-bound?)
+#pragma unroll 4
+              for (int k = 0; k < ksteps; ++k)
+                umma_bf16(tmem_base + 256u, (static_cast<uint64_t>(desc_hi) << 32) | (a2_lo + 128u * k),
+                          (static_cast<uint64_t>(desc_hi) << 32) | (b_lo + 128u * k), idesc, k ? 1u : accumulate);
+            }
             accumulate = 1;
           }
           umma_commit(&bars.empty[stage]);
@@ -280,6 +305,14 @@ int wgrad_launch(const WgradArgs& a, cudaStream_t stream) {
     if (cost < best * (1.0 - 1e-3)) { best = cost; nsplit = ns; }
   }
   p.nsplit = nsplit;
+  {
+    static int order = -1;
+    if (order < 0) { const char* o = getenv("CS_WGRAD_ORDER"); order = o ? atoi(o) : 0; }
+    p.mma_order = order;
+    static int rotate = -1;
+    if (rotate < 0) { const char* r = getenv("CS_WGRAD_ROTATE"); rotate = r ? atoi(r) : 0; }
+    p.rotate = rotate;
+  }
   p.n_items = units * nsplit;
   p.dw = a.dw;
 

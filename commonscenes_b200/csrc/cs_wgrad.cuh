@@ -15,6 +15,8 @@ struct WgradArgs {
 };
 
 struct WgradParams {
+  int rotate;        // 1 = every item starts at its own rotation of its voxel range (spreads the L2 requests)
+  int mma_order;     // 0 = interleave the two accumulators per K step; 1 = one accumulator's K steps, then the other's (experiment)
   int B, Do, Ho, Wo;
   int bb, bd, bh, bw, rows;               // voxel box of one K chunk (rows = 64 voxels)
   int kd, kh, kw, sd, sh, sw, pd, ph, pw, ntaps;
