@@ -202,16 +202,17 @@ class DenoiserTrainStep:
 
     def _build_repack_table(self, packed, regular) -> None:
         entries = (_RepackEntry * len(packed))()
-        self._repack_tile_ci = int(os.environ.get("CS_REPACK_TILE_CI", "32"))     # 16 or 32 input channels per tile
+        self._repack_tile_ci = 16
         tile = 0
         self._regular_keys = []
         for i, p in enumerate(packed):
             r = regular[p]
-            group = max(1, 27 // r["taps"])      # ci tiles per CTA: a 1x1x1 weight gets CTAs as large as a 3x3x3 one
+            gmax = max(1, 27 // r["taps"])       # a tile = 16 co x (16 * group) ci x taps: <= 432 cells per output channel;
+            c16 = (r["Cin"] + 15) // 16          # equal-width tiles (448 input channels of a 1x1x1 weight -> 2 x 224, not 432 + 16)
+            group = -(-c16 // -(-c16 // gmax))
             entries[i] = _RepackEntry(self.offsets[p], self.g_offsets[p], tile, r["fwd"].data_ptr(), r["dgrad"].data_ptr(),
                                       r["Cout"], r["Cin"], r["taps"], r["C1"], group, 0)
-            tiles_ci = (r["Cin"] + self._repack_tile_ci - 1) // self._repack_tile_ci
-            tile += ((r["Cout"] + 15) // 16) * ((tiles_ci + group - 1) // group)
+            tile += ((r["Cout"] + 15) // 16) * ((r["Cin"] + 16 * group - 1) // (16 * group))
             self._regular_keys += list(r["keys"])
         raw = torch.frombuffer(bytearray(bytes(entries)), dtype=torch.uint8).clone()
         self._repack_table = raw.to(self.flat_p.device)

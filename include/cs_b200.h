@@ -151,20 +151,22 @@ int cs_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, 
              float weight_decay, int32_t step, const float* sumsq, float max_norm, float grad_scale, const int32_t* step_dev,
              cs_stream_t stream);
 /* Fused clip + AdamW + re-pack for GEMM-class weights whose gradient lives in the PACKED layout cs_conv3d_wgrad writes.
- * One table entry per parameter (device array, sorted by first_tile); a tile = 16 output x tile_ci (16 or 32) input channels x
- * all taps, tiles of a parameter numbered (co block) * ceil(ceil(Cin / tile_ci) / group) + (ci tile group) from its first_tile
- * (`first_tile` / `n_tiles` count CTAs = tile groups; at most 256 entries):
- *   p / m / v : fp32 at p_off, the parameter's own (Cout, Cin, taps) layout (AdamW as in cs_adamw, same arithmetic)
+ * One table entry per parameter (device array, sorted by first_tile, at most 256 entries).  A tile = 16 output channels x
+ * (16 * group) input channels x all taps (group * taps <= 27, i.e. at most 432 cells per output channel); the tiles of a
+ * parameter are numbered (co block) * ceil(Cin / (16 * group)) + (ci block) from its first_tile; n_tiles = their total:
+ *   p / m / v : fp32 at p_off, the parameter's own (Cout, Cin, taps) layout (AdamW as in cs_adamw; the quotient
+ *               m / (sqrt(v) / bc2 + eps) is evaluated with a 2-ulp division)
  *   g         : fp32 at g_off, packed [Cout][taps][pad64(C1) + pad64(Cin - C1)]; READ AND ZEROED (ready for the next step)
  *   fwd/dgrad : the two bf16 layouts of cs_pack_weight, rewritten from the updated weights (NULL = skip)
- * Replaces cs_unpack_wgrad + cs_adamw + cs_pack_weight for those parameters.  Channel counts and C1 are multiples of 8.
- * A non-finite *sumsq skips the update (gradient cells are still cleared). */
+ * Replaces cs_unpack_wgrad + cs_adamw + cs_pack_weight for those parameters.  Channel counts and C1 are multiples of 8;
+ * tile_ci must be 16.  A non-finite *sumsq skips the update (gradient cells are still cleared).  Persistent kernel
+ * (one CTA per SM, 218 KB of shared memory: two cp.async-filled stages of gradient + p + m + v tiles). */
 typedef struct {
   int64_t p_off, g_off, first_tile;
   void* fwd;
   void* dgrad;
   int32_t Cout, Cin, taps, C1;
-  int32_t group;   /* consecutive ci tiles one CTA handles (>= 1; e.g. 27 / taps so that 1x1x1 weights get CTAs as large as 3x3x3 ones) */
+  int32_t group;   /* tile width along Cin in units of 16 channels (>= 1, group * taps <= 27; 27 for 1x1x1 weights, 1 for 3x3x3) */
   int32_t reserved;
 } cs_repack_entry;
 int cs_adamw_repack(float* p, float* g, float* m, float* v, const cs_repack_entry* table, int32_t n_entries, int64_t n_tiles,
