@@ -109,7 +109,24 @@ _PACK_BUFFERS = {}
 
 # Keys of cached pack buffers that somebody else keeps current (the fused optimizer kernel cs_adamw_repack rewrites the bf16
 # packs of the weights it updates): pack_conv_weight / pack_dgrad_weight return such a buffer without launching.
-_PACK_MAINTAINED = set()
+# key -> (weak reference to the owning parameter, its autograd version when the registration was made).  An id() can be reused
+# by a new tensor once the old one is collected, and a parameter written through torch (load_state_dict, an initialiser, an
+# in-place op) bumps its version while the fused kernel does not: either way the registration is void and the pack is rebuilt.
+_PACK_MAINTAINED = {}
+
+
+def _pack_maintain(key, owner) -> None:
+    _PACK_MAINTAINED[key] = (weakref.ref(owner), owner._version)
+
+
+def _pack_is_maintained(key, owner) -> bool:
+    hit = _PACK_MAINTAINED.get(key)
+    if hit is None:
+        return False
+    if hit[0]() is owner and owner._version == hit[1]:
+        return True
+    del _PACK_MAINTAINED[key]
+    return False
 
 
 def _pack_key(kind: str, owner, shape):
@@ -147,7 +164,7 @@ def pack_conv_weight(w: torch.Tensor, split=None, owner=None) -> torch.Tensor:
             raise _lib.CsError(f"pack: channel split {parts} does not sum to {ci}")
         own, kind, shape = owner if owner is not None else w, "fwd" + str(tuple(parts)), (co, taps, sum(_pad64(c) for c in parts))
         out = _pack_buffer(kind, own, shape, w.device)
-        if _pack_key(kind, own, shape) in _PACK_MAINTAINED:
+        if _pack_is_maintained(_pack_key(kind, own, shape), own):
             return out
         check(_lib.load().cs_pack_weight(wd.data_ptr(), co, ci, taps, parts[0], out.data_ptr(), None, _stream()), "cs_pack_weight")
         return out

@@ -72,10 +72,10 @@ def pack_dgrad_weight(w: torch.Tensor, owner=None) -> torch.Tensor:
     wd = w.detach()
     if wd.is_cuda and wd.dtype == torch.float32 and wd.is_contiguous():
         taps = wd.numel() // (co * ci)
-        from .ops import _pack_buffer, _pack_key, _PACK_MAINTAINED
+        from .ops import _pack_buffer, _pack_key, _pack_is_maintained
         own, shape = owner if owner is not None else w, (ci, taps, _pad64(co))
         out = _pack_buffer("dgrad", own, shape, w.device)
-        if _pack_key("dgrad", own, shape) in _PACK_MAINTAINED:
+        if _pack_is_maintained(_pack_key("dgrad", own, shape), own):
             return out
         check(_lib.load().cs_pack_weight(wd.data_ptr(), co, ci, taps, ci, None, out.data_ptr(), _stream()), "cs_pack_weight")
         return out

@@ -213,7 +213,7 @@ class DenoiserTrainStep:
             entries[i] = _RepackEntry(self.offsets[p], self.g_offsets[p], tile, r["fwd"].data_ptr(), r["dgrad"].data_ptr(),
                                       r["Cout"], r["Cin"], r["taps"], r["C1"], group, 0)
             tile += ((r["Cout"] + 15) // 16) * ((r["Cin"] + 16 * group - 1) // (16 * group))
-            self._regular_keys += list(r["keys"])
+            self._regular_keys += [(k, p) for k in r["keys"]]
         raw = torch.frombuffer(bytearray(bytes(entries)), dtype=torch.uint8).clone()
         self._repack_table = raw.to(self.flat_p.device)
         self._repack_n, self._repack_tiles = len(packed), tile
@@ -229,11 +229,21 @@ class DenoiserTrainStep:
             self.unet._packed = None
             return
         from . import ops as _ops
-        _ops._PACK_MAINTAINED.difference_update(self._regular_keys)
+        for key, _ in self._regular_keys:
+            _ops._PACK_MAINTAINED.pop(key, None)
         self.unet._packed = None
         self.trainer._ensure()
-        _ops._PACK_MAINTAINED.update(self._regular_keys)
+        for key, p in self._regular_keys:
+            _ops._pack_maintain(key, p)
         self._regular_versions = sum(p._version for p in self._repack_params)
+
+    def __del__(self):
+        try:        # the packs of these weights are no longer kept current by anybody
+            from . import ops as _ops
+            for key, _ in getattr(self, "_regular_keys", []):
+                _ops._PACK_MAINTAINED.pop(key, None)
+        except Exception:
+            pass
 
     def _check_packs_current(self) -> None:
         if self.fused and sum(p._version for p in self._repack_params) != self._regular_versions:

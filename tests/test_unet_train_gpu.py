@@ -382,6 +382,9 @@ def test_fused_update_equals_the_separate_kernels():
     # parameters written through torch (a checkpoint load) are noticed and re-packed
     with torch.no_grad():
         mb.load_state_dict(ma.state_dict())
+        fresh.load_state_dict(ma.state_dict())
+        # ... even by an evaluation that never goes through the training step (the registrations carry the parameter versions)
+        assert torch.equal(mb(z, t, c_crossattn=[ctx]), fresh(z, t, c_crossattn=[ctx]))
     sb.step(z, ctx, t=t, noise=noise); sa.step(z, ctx, t=t, noise=noise)
     with torch.no_grad():
         fresh.load_state_dict(mb.state_dict())
