@@ -44,6 +44,30 @@ def make_buckets(sizes: List[int], limit: int) -> List[tuple]:
     return buckets
 
 
+def fused_gradient_layout(sizes: List[int], slots: List[Optional[int]]):
+    """Flat-buffer layout of the fused-update mode, from the per-parameter sizes (elements, module order) and, for the
+    packed-gradient weights, their slot sizes (None = plain parameter).  Parameters sit [plain ... | packed ...] (each part
+    in module order) in flat_p / flat_m / flat_v and, with the slot sizes, in flat_g.  Returns (p_off, g_off, final_from,
+    n_plain, order): `final_from[i]` = the flat_g offset from which everything is final once the backward -- which walks the
+    parameters from the last to the first -- has passed parameter i: the start of the first packed slot at or after i
+    (the plain region in front of the slots is only final when the whole backward is)."""
+    n = len(sizes)
+    order = [i for i in range(n) if slots[i] is None] + [i for i in range(n) if slots[i] is not None]
+    p_off, g_off = [0] * n, [0] * n
+    po = go = 0
+    for i in order:
+        p_off[i], g_off[i] = po, go
+        po += sizes[i]
+        go += sizes[i] if slots[i] is None else slots[i]
+    n_plain = sum(sizes[i] for i in range(n) if slots[i] is None)
+    final_from, nxt = [0] * n, go
+    for i in reversed(range(n)):
+        if slots[i] is not None:
+            nxt = g_off[i]
+        final_from[i] = nxt
+    return p_off, g_off, final_from, n_plain, order
+
+
 def flat_optimizer_state_dict(params, offsets, flat_m, flat_v, step: int, hp: dict) -> dict:
     """The flat AdamW moments in torch.optim.AdamW.state_dict() layout -- what the reference checkpoints hold
     (SDFusionText2ShapeModel.save(save_opt=True): sdfusion_txt2shape_model.py:636-650; VAE.save: VAE.py:334-340) -- so a run
@@ -112,24 +136,24 @@ class DenoiserTrainStep:
         self.fused = (dev.type == "cuda") if fused_update is None else (bool(fused_update) and dev.type == "cuda")
         regular = self._discover_packed_weights(params) if self.fused else {}
         self.fused = bool(regular)
-        plain = [p for p in params if p not in regular]
+        sizes = [(p.numel() + 3) // 4 * 4 for p in params]          # keep every view 16-byte aligned
+        slots = [regular[p]["slot"] if p in regular else None for p in params]
+        p_off, g_off, final_from, self.n_plain, order = fused_gradient_layout(sizes, slots)
         packed = [p for p in params if p in regular]
-        order = plain + packed                                      # flat layout; `params` keeps the module's order
-        sizes = {p: (p.numel() + 3) // 4 * 4 for p in params}       # keep every view 16-byte aligned
-        total = sum(sizes.values())
-        self.n_plain = sum(sizes[p] for p in plain)
-        g_sizes = {p: (regular[p]["slot"] if p in regular else sizes[p]) for p in params}
+        total = sum(sizes)
+        g_sizes = [sizes[i] if slots[i] is None else slots[i] for i in range(len(params))]
         self.flat_p = torch.zeros(total, dtype=torch.float32, device=dev)
-        self.flat_g = torch.zeros(sum(g_sizes.values()), dtype=torch.float32, device=dev)
+        self.flat_g = torch.zeros(sum(g_sizes), dtype=torch.float32, device=dev)
         self.flat_m = torch.zeros(total, dtype=torch.float32, device=dev)
         self.flat_v = torch.zeros(total, dtype=torch.float32, device=dev)
         self.views: Dict[nn.Parameter, torch.Tensor] = {}
         self.packed_views: Dict[nn.Parameter, torch.Tensor] = {}
         self.offsets: Dict[nn.Parameter, int] = {}
         self.g_offsets: Dict[nn.Parameter, int] = {}
-        off = goff = 0
+        self._final_from: Dict[nn.Parameter, int] = {}
         with torch.no_grad():
-            for p in order:
+            for i in order:
+                p, off, goff = params[i], p_off[i], g_off[i]
                 v = self.flat_p[off:off + p.numel()].view(p.shape)
                 v.copy_(p.data)
                 p.data = v
@@ -139,24 +163,15 @@ class DenoiserTrainStep:
                 else:
                     self.views[p] = self.flat_g[goff:goff + p.numel()].view(p.shape)
                 self.offsets[p], self.g_offsets[p] = off, goff
-                off += sizes[p]
-                goff += g_sizes[p]
+                # without packed slots flat_g is laid out like flat_p and a parameter's own offset is the bound
+                self._final_from[p] = final_from[i] if self.fused else goff
         self.params = params
-        # "everything at or after this flat_g offset is final once the backward has passed parameter p": the packed slots follow
-        # the module's parameter order (the backward finishes them from the last to the first), the plain region in front of
-        # them is only final when the whole backward is (time_embed comes last)
-        self._final_from: Dict[nn.Parameter, int] = {}
-        nxt = int(self.flat_g.numel())
-        for p in reversed(params):
-            if p in regular:
-                nxt = self.g_offsets[p]
-            self._final_from[p] = nxt if self.fused else self.g_offsets[p]
         self.step_dev = torch.zeros((), dtype=torch.int32, device=dev)     # device copy of step_count (graph replays)
         self.graph = None
         self.sumsq = torch.zeros((), dtype=torch.float32, device=dev)
         self.loss = torch.zeros((), dtype=torch.float32, device=dev)
         # gradient buckets in flat_g order; the backward fills them from the last to the first
-        self.buckets: List[tuple] = make_buckets([g_sizes[p] for p in order], bucket_mb * (1 << 20) // 4)
+        self.buckets: List[tuple] = make_buckets([g_sizes[i] for i in order], bucket_mb * (1 << 20) // 4)
         self.comm_stream = torch.cuda.Stream(device=dev) if self.world > 1 else None
         self.unet._packed = None        # parameters moved: rebuild the kernel-layout copies
         if self.fused:

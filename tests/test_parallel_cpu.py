@@ -125,3 +125,38 @@ def test_bucketed_allreduce_schedule_world2():
         p.join(timeout=120)
         assert p.exitcode == 0
     assert dict(ret) == {0: True, 1: True}
+
+
+def test_fused_gradient_layout_keeps_the_bucket_schedule_valid():
+    """Fused-update mode (packed-gradient slots behind the plain parameters): walking the parameters from the last to the
+    first, `final_from` never decreases below data that is still being written, and every bucket goes out exactly once."""
+    from commonscenes_b200.train import fused_gradient_layout, make_buckets
+    sizes = [8, 400, 16, 16, 1200, 8, 640, 32, 24]
+    slots = [None, 448, None, None, 1280, None, 704, None, None]      # conv weights own (larger, padded) packed slots
+    p_off, g_off, final_from, n_plain, order = fused_gradient_layout(sizes, slots)
+    assert n_plain == sum(s for s, k in zip(sizes, slots) if k is None)
+    assert sorted(order) == list(range(len(sizes))) and [i for i in order if slots[i] is None] == [0, 2, 3, 5, 7, 8]
+    total_g = n_plain + sum(k for k in slots if k is not None)
+    # plain parameters keep identical offsets in flat_p and flat_g; packed slots follow in module order
+    assert all(p_off[i] == g_off[i] for i in range(len(sizes)) if slots[i] is None)
+    assert [g_off[i] for i in (1, 4, 6)] == [n_plain, n_plain + 448, n_plain + 448 + 1280]
+    buckets = make_buckets([sizes[i] if slots[i] is None else slots[i] for i in order], 600)
+    assert buckets[0][0] == 0 and buckets[-1][1] == total_g
+    written_from = total_g                     # lowest flat_g offset a not-yet-visited parameter may still write to
+    sent = set()
+    for i in reversed(range(len(sizes))):      # the backward visits parameters from the last to the first
+        lo = final_from[i]
+        # everything at or after `lo` must belong to parameters already visited (index >= i)
+        for j in range(i):
+            if slots[j] is not None:
+                assert g_off[j] + slots[j] <= lo
+            else:
+                assert g_off[j] + sizes[j] <= n_plain <= lo
+        for b, (blo, bhi) in enumerate(buckets):
+            if blo >= lo:
+                sent.add(b)
+        assert lo <= written_from
+        written_from = lo
+    assert final_from[0] == n_plain            # the plain region is only final after the whole backward
+    sent |= set(range(len(buckets)))           # the final _allreduce_ready(0, ...) sends the rest
+    assert sent == set(range(len(buckets)))
