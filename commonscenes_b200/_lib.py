@@ -113,6 +113,7 @@ SIGNATURES = {
     "cs_approx_match": (_i32, [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
     "cs_match_cost": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),
     "cs_match_cost_grad": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "cs_batch_reduce_many": (_i32, [_vp, _i32, _vp]),
     "cs_adamw_repack": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _f32, _f32, _f32, _f32, _f32, _i32, _vp, _f32, _f32, _vp, _vp]),
     "cs_surface_count": (_i32, [_vp, _i32, _i32, _i32, _i32, _f64, _vp, _vp, _vp, _vp, _vp]),
     "cs_surface_emit": (_i32, [_vp, _i32, _i32, _i32, _i32, _f64, _f64, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),

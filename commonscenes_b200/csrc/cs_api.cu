@@ -46,6 +46,7 @@ int embedding_bwd_launch(const float*, int, int, int, const long long*, int, int
 int gn_bwd_launch(const void*, int, int, int, int, int, const void*, int, int, const long long*, int, const long long*, int, const float*,
                   const float*, int, float, int, float*, const void*, int, void*, int, int, cudaStream_t);
 int batch_reduce_launch(const float*, int, int, int, int, float*, cudaStream_t);
+int batch_reduce_many_launch(const cs_reduce_item*, int, cudaStream_t);
 int layernorm_bwd_launch(const void*, long long, int, int, const void*, int, const float*, float, const void*, int, void*, int,
                          float*, float*, cudaStream_t);
 int geglu_bwd_launch(const void*, long long, int, int, const void*, int, void*, int, cudaStream_t);
@@ -292,6 +293,11 @@ int cs_groupnorm_bwd(const void* x, int32_t B, int32_t Sp, int32_t C, int32_t pi
 }
 int cs_batch_reduce(const float* in, int32_t B, int32_t C, int32_t comp, int32_t ncomp, float* out, cs_stream_t stream) {
   return cs::batch_reduce_launch(in, B, C, comp, ncomp, out, S(stream));
+}
+int cs_batch_reduce_many(const cs_reduce_item* items, int32_t n, cs_stream_t stream) {
+  if (n <= 0) return CS_OK;
+  if (!items) return cs::set_error(CS_ERR_INVALID, "batch_reduce_many: null item array");
+  return cs::batch_reduce_many_launch(items, n, S(stream));
 }
 int cs_layernorm_bwd(const void* x, int64_t M, int32_t C, int32_t pitch, const void* dy, int32_t dy_pitch, const float* gamma,
                      float eps, const void* extra, int32_t extra_pitch, void* dx, int32_t dx_pitch, float* dgamma, float* dbeta,

@@ -356,7 +356,9 @@ class UNetTrainer:
         tape["dx"]) -- the path of the conditioning gradient when it is concatenated to x (concat variant)."""
         if self._zero_arena is None or self._zero_arena.buf.device != d_eps.device:
             self._zero_arena = ops_bwd.ZeroArena(d_eps.device)
-        with self._zero_arena:
+        # the tiny per-parameter reductions (d beta / d gamma, bias gradients) are queued and issued 24 per launch at the end of
+        # every block (before on_block_done, whose caller may send those gradients off) and at the end of the backward
+        with self._zero_arena, ops_bwd.ReduceQueue():
             return self._backward_impl(tape, d_eps, sink, need_dcontext, on_block_done, need_dx)
 
     def _backward_impl(self, tape: dict, d_eps: torch.Tensor, sink: Optional[GradSink] = None, need_dcontext: bool = True,
@@ -391,6 +393,7 @@ class UNetTrainer:
         dh, _ = ops_bwd.groupnorm_bwd(h.t, h.stat, *pk["out_gn"], da, eps=u.out[0].eps, act=ops.ACT_SILU,
                                       dgamma=sink.grad(u.out[0].weight), dbeta=sink.grad(u.out[0].bias))
         _acc(h, dh)
+        ops_bwd.flush_reductions()
         if on_block_done is not None:
             on_block_done(u.out[0].weight)
 
@@ -427,6 +430,7 @@ class UNetTrainer:
                         raise NotImplementedError("input gradient of a stem with more than 4 input channels")
                     tape["dx"] = ops.conv3d_small_cout(dy, dpk["stem_dx"], None, cin)
             rec["out"].grad = None
+            ops_bwd.flush_reductions()
             if on_block_done is not None:
                 on_block_done(next(rec["layer"].parameters()))
 

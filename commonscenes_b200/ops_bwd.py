@@ -185,9 +185,9 @@ def groupnorm_bwd(x: torch.Tensor, stat: torch.Tensor, gamma: torch.Tensor, beta
                                        dx.data_ptr(), c, 1, st), "cs_groupnorm_bwd")
             outs.append(dx)
     if dbeta is not None:
-        check(lib.cs_batch_reduce(red.data_ptr(), B, Ct, 0, 2, dbeta.data_ptr(), st), "cs_batch_reduce")
+        batch_reduce(red, 0, dbeta)
     if dgamma is not None:
-        check(lib.cs_batch_reduce(red.data_ptr(), B, Ct, 1, 2, dgamma.data_ptr(), st), "cs_batch_reduce")
+        batch_reduce(red, 1, dgamma)
     if not need_dx:
         return None, None
     return outs[0], (outs[1] if len(outs) > 1 else None)
@@ -202,8 +202,72 @@ def channel_sums(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
     return out
 
 
+class _ReduceItem(C.Structure):
+    """cs_reduce_item of include/cs_b200.h."""
+    _fields_ = [("inp", C.c_void_p), ("out", C.c_void_p), ("B", C.c_int32), ("C", C.c_int32), ("comp", C.c_int32), ("ncomp", C.c_int32)]
+
+
+class ReduceQueue:
+    """Collects batch_reduce() calls and issues them together (cs_batch_reduce_many: 24 per launch) at flush().  The backward
+    of the denoiser ends every block with a handful of these tiny reductions; queued, ~244 launches per step become ~40.
+    Inputs and outputs are kept alive until the flush; two items with the same output never share a launch, so the order of
+    the additions into a parameter gradient is the program order (bit-reproducible, replicas stay identical)."""
+    current: Optional["ReduceQueue"] = None
+
+    def __init__(self):
+        self.items = []
+
+    def add(self, stat, comp, out):
+        self.items.append((stat, comp, out))
+
+    def flush(self):
+        if not self.items:
+            return
+        lib, st = _lib.load(), _stream()
+        batch, seen = [], set()
+
+        def go():
+            if batch:
+                arr = (_ReduceItem * len(batch))(*batch)
+                check(lib.cs_batch_reduce_many(arr, len(batch), st), "cs_batch_reduce_many")
+                batch.clear(); seen.clear()
+        for stat, comp, out in self.items:
+            key = out.data_ptr()
+            if key in seen:
+                go()
+            B, Cc, n = stat.shape
+            batch.append(_ReduceItem(stat.data_ptr(), key, B, Cc, comp, n))
+            seen.add(key)
+        go()
+        self.items = []
+
+    def __enter__(self):
+        self._prev = ReduceQueue.current
+        ReduceQueue.current = self
+        return self
+
+    def __exit__(self, *exc):
+        ReduceQueue.current = self._prev
+        if exc[0] is None:
+            self.flush()
+        else:
+            self.items = []
+
+
+def flush_reductions() -> None:
+    """Issue the queued batch reductions now (a point where their outputs must be final: a gradient bucket goes out)."""
+    if ReduceQueue.current is not None:
+        ReduceQueue.current.flush()
+
+
 def batch_reduce(stat: torch.Tensor, comp: int, out: torch.Tensor) -> torch.Tensor:
-    """out (C,) += sum_b stat[b, :, comp]   (stat fp32 (B, C, ncomp) contiguous)."""
+    """out (C,) += sum_b stat[b, :, comp]   (stat fp32 (B, C, ncomp) contiguous).  Inside a ReduceQueue the launch is deferred
+    to its next flush()."""
+    if stat.dtype != torch.float32 or out.dtype != torch.float32 or not stat.is_contiguous() or not out.is_contiguous():
+        raise _lib.CsError("batch_reduce: contiguous fp32 tensors required")
+    if ReduceQueue.current is not None:
+        ReduceQueue.current.add(stat, comp, out)
+        return out
     B, Cc, n = stat.shape
     check(_lib.load().cs_batch_reduce(stat.data_ptr(), B, Cc, comp, n, out.data_ptr(), _stream()), "cs_batch_reduce")
     return out

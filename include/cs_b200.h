@@ -114,6 +114,14 @@ int cs_groupnorm_bwd(const void* x, int32_t B, int32_t S, int32_t C, int32_t pit
                      const void* extra, int32_t extra_pitch, void* dx, int32_t dx_pitch, int32_t pass, cs_stream_t stream);
 /* out[c] += sum_b in[b][c][comp]   (in: fp32 [B][C][ncomp]) */
 int cs_batch_reduce(const float* in, int32_t B, int32_t C, int32_t comp, int32_t ncomp, float* out, cs_stream_t stream);
+/* n such reductions at once: `items` is a HOST array (copied into kernel arguments, 24 per launch); items must not share an
+ * output within one call */
+typedef struct {
+  const float* in;
+  float* out;
+  int32_t B, C, comp, ncomp;
+} cs_reduce_item;
+int cs_batch_reduce_many(const cs_reduce_item* items, int32_t n, cs_stream_t stream);
 /* nn.LayerNorm backward (attention.py:229-231): dx = LN'(x) dy + extra; dgamma / dbeta accumulated (+=) */
 int cs_layernorm_bwd(const void* x, int64_t M, int32_t C, int32_t pitch, const void* dy, int32_t dy_pitch, const float* gamma,
                      float eps, const void* extra, int32_t extra_pitch, void* dx, int32_t dx_pitch, float* dgamma, float* dbeta,
