@@ -695,9 +695,10 @@ int cast_rows_launch(const float* in, int in_pitch, long long M, int C, void* ou
 // C[M][N] = (accumulate ? C : 0) + op(A)[M][K] * op(B)[K][N], row-major, op = optional transpose; optional SiLU'(pre)
 // multiplier on the output (pre[M][N] = the pre-activation whose SiLU fed the forward).  Tiny problems (M or N = batch).
 // ------------------------------------------------------------------------------------------------
-__global__ void sgemm_small_kernel(const float* __restrict__ A, int lda, int ta, const float* __restrict__ Bm, int ldb, int tb,
-                                   float* __restrict__ Cm, int ldc, int M, int N, int K, int accumulate,
-                                   const float* __restrict__ silu_pre, int ld_pre, int k_chunk) {
+__global__ void __launch_bounds__(256)
+sgemm_small_kernel(const float* __restrict__ A, int lda, int ta, const float* __restrict__ Bm, int ldb, int tb,
+                   float* __restrict__ Cm, int ldc, int M, int N, int K, int accumulate,
+                   const float* __restrict__ silu_pre, int ld_pre, int k_chunk) {
   __shared__ float sA[32][33], sB[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8 threads, each 4 rows of a 32 x 32 tile
   const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
@@ -705,27 +706,40 @@ __global__ void sgemm_small_kernel(const float* __restrict__ A, int lda, int ta,
   const int k_begin = blockIdx.z * k_chunk;            // split-K: long reductions with few output tiles (the per-step
   const int k_end = min(K, k_begin + k_chunk);         // embedding / context GEMMs) are spread over gridDim.z CTAs
   K = k_end;
+  // The K loop is a chain of global-memory round trips (these problems are latency-, not throughput-bound: M or K is the
+  // batch size): the next 32-wide slab is fetched into registers while the current one is multiplied out of shared memory.
+  float ra[4], rb[4];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = ty + 8 * i;
+      if (!ta) {
+        const int m = m0 + r, k = k0 + tx;
+        ra[i] = (m < M && k < K) ? A[static_cast<long long>(m) * lda + k] : 0.f;
+      } else {
+        const int k = k0 + r, m = m0 + tx;
+        ra[i] = (m < M && k < K) ? A[static_cast<long long>(k) * lda + m] : 0.f;
+      }
+      if (!tb) {
+        const int k = k0 + r, n = n0 + tx;
+        rb[i] = (k < K && n < N) ? Bm[static_cast<long long>(k) * ldb + n] : 0.f;
+      } else {
+        const int n = n0 + r, k = k0 + tx;
+        rb[i] = (k < K && n < N) ? Bm[static_cast<long long>(n) * ldb + k] : 0.f;
+      }
+    }
+  };
+  if (k_begin < k_end) fetch(k_begin);
   for (int k0 = k_begin; k0 < k_end; k0 += 32) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int r = ty + 8 * i;
-      // sA[r][tx] = op(A)[m0 + r][k0 + tx]; read along the contiguous axis of the stored matrix
-      if (!ta) {
-        const int m = m0 + r, k = k0 + tx;
-        sA[r][tx] = (m < M && k < K) ? A[static_cast<long long>(m) * lda + k] : 0.f;
-      } else {
-        const int k = k0 + r, m = m0 + tx;
-        sA[tx][r] = (m < M && k < K) ? A[static_cast<long long>(k) * lda + m] : 0.f;
-      }
-      if (!tb) {
-        const int k = k0 + r, n = n0 + tx;
-        sB[r][tx] = (k < K && n < N) ? Bm[static_cast<long long>(k) * ldb + n] : 0.f;
-      } else {
-        const int n = n0 + r, k = k0 + tx;
-        sB[tx][r] = (k < K && n < N) ? Bm[static_cast<long long>(n) * ldb + k] : 0.f;
-      }
+      // sA[row m][k], sB[k][col n]; the stored matrices were read along their contiguous axis
+      if (!ta) sA[r][tx] = ra[i]; else sA[tx][r] = ra[i];
+      if (!tb) sB[r][tx] = rb[i]; else sB[tx][r] = rb[i];
     }
     __syncthreads();
+    if (k0 + 32 < k_end) fetch(k0 + 32);
 #pragma unroll 8
     for (int k = 0; k < 32; ++k) {
       const float b = sB[k][tx];
@@ -739,10 +753,15 @@ __global__ void sgemm_small_kernel(const float* __restrict__ A, int lda, int ta,
     const int m = m0 + ty + 8 * i, n = n0 + tx;
     if (m < M && n < N) {
       float v = acc[i];
-      if (silu_pre) v *= act_grad(silu_pre[static_cast<long long>(m) * ld_pre + n], CS_ACT_SILU);
       float* c = Cm + static_cast<long long>(m) * ldc + n;
-      if (gridDim.z > 1) atomicAdd(c, v);              // the host zeroed C when it is not an accumulation
-      else *c = accumulate ? *c + v : v;
+      if (gridDim.z > 1) {
+        // split-K partial sums: the SiLU' factor is linear in the sum, so it may be applied per partial
+        if (silu_pre) v *= act_grad(silu_pre[static_cast<long long>(m) * ld_pre + n], CS_ACT_SILU);
+        atomicAdd(c, v);              // the host zeroed C when it is not an accumulation
+      } else {
+        if (silu_pre) v *= act_grad(silu_pre[static_cast<long long>(m) * ld_pre + n], CS_ACT_SILU);
+        *c = accumulate ? *c + v : v;
+      }
     }
   }
 }
@@ -751,9 +770,9 @@ int sgemm_small_launch(const float* A, int lda, int ta, const float* Bm, int ldb
   if (M <= 0 || N <= 0 || K <= 0) return CS_OK;
   const int tiles = ((N + 31) / 32) * ((M + 31) / 32);
   int splits = 1;
-  if (tiles < 2 * num_sms() && K >= 1024) {
+  if (tiles < 2 * num_sms() && K >= 256) {
     splits = (4 * num_sms() + tiles - 1) / tiles;
-    if (splits > (K + 255) / 256) splits = (K + 255) / 256;     // at least 256 of K per CTA
+    if (splits > (K + 127) / 128) splits = (K + 127) / 128;     // at least 128 of K (four serial slabs) per CTA
     if (splits < 1) splits = 1;
   }
   int k_chunk = ((K + splits - 1) / splits + 31) / 32 * 32;
