@@ -10,9 +10,11 @@ Reference lines (dataset/threedfront_dataset.py):
                 :503-508 relation features looked up by the relation's words
 
 HDF5: the reference reads the grids with h5py, which this image does not have and which cannot be installed (no network).
-`load_sdf_grid` therefore uses h5py WHEN IMPORTABLE and otherwise accepts the same array exported once as
-`ori_sample_grid.npy` next to the .h5 (`export_sdf_npy`, to be run where h5py exists); a missing reader is an error, never a
-silent substitute.  Parity of the h5 branch is unpinned here (no h5py, no HDF5 file in the image); everything after the
+`load_sdf_grid` uses h5py WHEN IMPORTABLE and otherwise the pure-Python reader `dataset/hdf5_lite.py` (classic HDF5 file
+format: contiguous or chunked + gzip datasets -- what the SDF pre-processing writes); an `ori_sample_grid.npy` exported next
+to the .h5 (`export_sdf_npy`) is still accepted.  A file neither can read is an error, never a silent substitute.  The
+container parsing is pinned against files produced by an independent minimal writer that follows the HDF5 specification
+(tests/test_hdf5_cpu.py), NOT against libhdf5 (no HDF5 library or file in the image: parity unpinned); everything after the
 array is read (shape, dtype, clamp, zero grids, ordering) is pinned by tests/test_formats_cpu.py.
 """
 from __future__ import annotations
@@ -41,9 +43,10 @@ def sdf_path_for_model(model_path: str) -> str:
 def _read_h5(path: str) -> np.ndarray:
     try:
         import h5py  # noqa: WPS433  (optional dependency, absent in this image)
-    except ImportError as e:
-        raise RuntimeError(f"{path}: reading HDF5 needs h5py, which is not installed; export the grid once with "
-                           f"commonscenes_b200.dataset.formats.export_sdf_npy where h5py exists") from e
+    except ImportError:
+        from . import hdf5_lite         # classic-format reader in pure Python (superblock 0, chunked + gzip datasets)
+        with hdf5_lite.File(path) as f:
+            return f[SDF_KEY][:].astype(np.float32)
     with h5py.File(path, "r") as f:
         return f[SDF_KEY][:].astype(np.float32)
 
@@ -57,8 +60,8 @@ def export_sdf_npy(h5_path: str) -> str:
 
 def load_sdf_grid(path: Optional[str], res: int = 64, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """(1, res, res, res) fp32 SDF of one object, clamped to +-0.2 like the reference (:389-390); `path` None = an object
-    without a model (floor / `_scene_`): zeros (:384-385, :455-456).  `path` may name the .h5 (h5py, or its exported .npy
-    twin when h5py is absent) or a .npy directly.  `out`: optional destination (e.g. a slice of a pinned batch buffer)."""
+    without a model (floor / `_scene_`): zeros (:384-385, :455-456).  `path` may name the .h5 (read with h5py when importable, else with
+    dataset/hdf5_lite.py; its exported .npy twin is used when the .h5 itself is missing) or a .npy directly.  `out`: optional destination (e.g. a slice of a pinned batch buffer)."""
     if out is None:
         out = torch.empty((1, res, res, res), dtype=torch.float32)
     if tuple(out.shape) != (1, res, res, res) or out.dtype != torch.float32:
@@ -67,7 +70,7 @@ def load_sdf_grid(path: Optional[str], res: int = 64, out: Optional[torch.Tensor
         out.zero_()
         return out
     npy = path if path.endswith(".npy") else os.path.splitext(path)[0] + ".npy"
-    if path.endswith(".npy") or (os.path.exists(npy) and not _have_h5py()):
+    if path.endswith(".npy") or (not os.path.exists(path) and os.path.exists(npy)):
         arr = np.load(npy).astype(np.float32, copy=False)
     else:
         arr = _read_h5(path)

@@ -22,8 +22,8 @@ def test_sdf_grid_matches_the_reference_statements(tmp_path):
     with pytest.raises(ValueError):
         np.save(tmp_path / "bad.npy", raw[:100])
         F.load_sdf_grid(str(tmp_path / "bad.npy"))
-    with pytest.raises(RuntimeError):
-        F.load_sdf_grid(str(tmp_path / "missing" / "ori_sample_grid.h5"))     # no h5py and no exported twin: loud
+    with pytest.raises(FileNotFoundError):
+        F.load_sdf_grid(str(tmp_path / "missing" / "ori_sample_grid.h5"))     # neither the .h5 nor an exported twin: loud
     assert F.sdf_path_for_model("/d/3D-FUTURE-model/abc/raw_model.obj") == "/d/3D-FUTURE-SDF/abc/ori_sample_grid.h5"
 
 
