@@ -205,7 +205,7 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ 
             const uint32_t a2_lo = (((sa + kABytes2) >> 4) & 0x3FFFu) | 0x10000u;
             const uint32_t b_lo = (((sa + mt * kABytes2) >> 4) & 0x3FFFu) | 0x10000u;
 #pragma unroll 4
-            for (int k = 0; k < ksteps; ++k) {
+            for (int k = 0; k < ksteps && !(p.debug & 4); ++k) {
               const uint64_t bd = (static_cast<uint64_t>(desc_hi) << 32) | (b_lo + 2u * k);
               umma2_bf16(d_tmem, (static_cast<uint64_t>(desc_hi) << 32) | (a_lo + 2u * k), bd, idesc, accumulate);
               if (mt == 2) umma2_bf16(d_tmem + 256u, (static_cast<uint64_t>(desc_hi) << 32) | (a2_lo + 2u * k), bd, idesc, accumulate);
@@ -254,7 +254,7 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ 
         mbar_wait(&bars.tmem_full[ab], buf_phase[ab]);
         tc_fence_after();
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(ab * 256);
-        epilogue_fast_tile(p, t_row, lane, half, 64, quarter * 32, m_tile0, b, n0, bars.colvec[ab], stage_buf);
+        if (!(p.debug & 2)) epilogue_fast_tile(p, t_row, lane, half, 64, quarter * 32, m_tile0, b, n0, bars.colvec[ab], stage_buf);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {

@@ -6,7 +6,10 @@ from commonscenes_b200 import ops
 from commonscenes_b200.model.networks.diffusion_networks.network import DiffusionUNet
 from commonscenes_b200.model.sdfusion_txt2shape_model import UNET_PARAMS
 
-objs = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+objs = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 32
+if "--debug" in sys.argv:      # cs_debug_set switches (tuning experiments)
+    from commonscenes_b200 import _lib as _l
+    _l.load().cs_debug_set(int(sys.argv[sys.argv.index("--debug") + 1]))
 cfg = UNET_PARAMS
 torch.manual_seed(0)
 with torch.device("cuda"):
