@@ -224,8 +224,8 @@ extern "C" {
 int cs_surface_count(const float* sdf, int32_t B, int32_t nx, int32_t ny, int32_t nz, double level, const uint8_t* tri_count,
                      uint8_t* vflags, int32_t* chunk_counts, int32_t* totals, cs_stream_t stream) {
   using namespace cs;
+  if (B == 0) return CS_OK;                      // an empty batch (its buffers may be null)
   if (int rc = mc_check(sdf, B, nx, ny, nz)) return rc;
-  if (B == 0) return CS_OK;
   const McGrid g = mc_grid(nx, ny, nz);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   mc_classify_kernel<<<dim3(g.chunks, B), kMcChunk, 0, st>>>(sdf, g, level, tri_count, vflags, chunk_counts);
@@ -244,8 +244,8 @@ int cs_surface_emit(const float* sdf, int32_t B, int32_t nx, int32_t ny, int32_t
                     int32_t max_tris, const int64_t* vert_base, const int64_t* tri_base, int32_t* voff, float* verts,
                     int64_t* faces, cs_stream_t stream) {
   using namespace cs;
-  if (int rc = mc_check(sdf, B, nx, ny, nz)) return rc;
   if (B == 0) return CS_OK;
+  if (int rc = mc_check(sdf, B, nx, ny, nz)) return rc;
   if (!(n_cell > 0.0)) return set_error(CS_ERR_INVALID, "surface_emit: n_cell must be positive");
   const McGrid g = mc_grid(nx, ny, nz);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

@@ -107,8 +107,8 @@ def sdf_to_mesh(sdf: torch.Tensor, level: float = 0.02, color=None, render_all: 
         n_mesh = min(bs, 16)
     grids = sdf[:n_mesh, 0].detach().float()
     verts, faces, tot = surface_extract(grids, level)
-    v_split = torch.split(verts, [int(v) for v in tot[:, 0]])
-    f_split = torch.split(faces, [int(t) for t in tot[:, 1]])
+    v_split = torch.split(verts, [int(v) for v in tot[:, 0]]) if n_mesh else ()
+    f_split = torch.split(faces, [int(t) for t in tot[:, 1]]) if n_mesh else ()
     rgb = []
     for v in v_split:
         text = torch.ones_like(v)

@@ -107,3 +107,16 @@ def test_sdf_to_mesh_sample_points_chamfer_chain():
     assert pts.shape == (16, 5000, 3)
     d1, d2 = ext.chamferDist()(pts, pts.roll(1, 0))
     assert bool(torch.isfinite(d1).all()) and float(ext.chamferDist()(pts, pts)[0].max()) == 0.0
+
+
+def test_empty_batch_and_all_inside_grids():
+    u = _u3d()
+    verts, faces, tot = u.surface_extract(torch.zeros((0, 8, 8, 8), device="cuda"), 0.02)
+    assert verts.shape == (0, 3) and faces.shape == (0, 3) and tot.shape == (0, 2)
+    m = u.sdf_to_mesh(torch.zeros((0, 1, 8, 8, 8), device="cuda"))
+    assert len(m) == 0 and m.verts_list() == []
+    # a grid entirely below the level has no crossing edge either
+    verts, faces, tot = u.surface_extract(torch.full((2, 8, 8, 8), -1.0, device="cuda"), 0.02)
+    assert verts.shape == (0, 3) and int(tot.sum()) == 0
+    with pytest.raises(Exception):
+        u.surface_extract(torch.zeros((1, 8, 8, 8)), 0.02)        # CPU tensor: no CPU path
